@@ -1,0 +1,168 @@
+/*
+ * rxmd_b200.h -- C ABI of the B200-native ReaxFF + QEq hot path behind RXMD's entry points.
+ *
+ * The reference (USCCACS/RXMD) has no FFI: the per-timestep hot path sits behind four external
+ * Fortran subroutines that share module-global state.  Each function below names the reference
+ * interface it replaces (file:line under the reference's src/).  A Fortran host binds them with
+ * `bind(C)` interfaces (see rxmd_b200/gpu_shim.F90 and INTEGRATION.md); the Python harness binds
+ * the same symbols through ctypes.  Only plain pointers, ints and doubles cross the boundary.
+ *
+ * Array conventions (identical to the Fortran host's memory):
+ *   - per-atom 1-D arrays: double[nbuffer]            (atype, q, qsfp, qsfv, ...)
+ *   - per-atom 3-vectors : double[3*nbuffer], x[0..nbuffer) y[..] z[..]   == pos(NBUFFER,3)
+ *   - parameter arrays   : 1-based Fortran arrays passed by their first element, column-major
+ *   - residents are elements 0..natoms-1 (Fortran 1..NATOMS)
+ * All calls are synchronous at return (the host reads `f` right after FORCE, src/main.F90:86-97).
+ * One host thread per handle; a handle owns one CUDA device (one MPI rank == one GPU).
+ */
+#ifndef RXMD_B200_H
+#define RXMD_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* status codes; 1..3 map 1:1 onto the reference's three overflow traps */
+#define RXG_OK                 0
+#define RXG_ERR_MAXNEIGHBS     1   /* src/main.F90:403  "overflow of max # in neighbor list"      */
+#define RXG_ERR_MAXNEIGHBS10   2   /* src/qeq.F90:248   "nbplist greater then MAXNEIGHBS10"       */
+#define RXG_ERR_NBUFFER        3   /* src/comm.F90:467  "over capacity in append_atoms"           */
+#define RXG_ERR_CUDA           4
+#define RXG_ERR_NCCL           5
+#define RXG_ERR_ARG            6
+#define RXG_ERR_STATE          7
+
+typedef void *rxg_handle;
+
+/* Run-time configuration: the reference's compile-time capacities (src/module.F90:80-84) and the
+ * rxmd.in / command-line switches the hot path reads (src/cmdline.F90:255-297). */
+typedef struct rxg_config {
+  int device;         /* CUDA device ordinal for this rank                                   */
+  int nbuffer;        /* NBUFFER: capacity of every per-atom array (residents + ghosts)      */
+  int maxneighbs;     /* MAXNEIGHBS   (30)   bonded-list row width                           */
+  int maxneighbs10;   /* MAXNEIGHBS10 (1500) trap threshold for 10 A rows                    */
+  int nmincell;       /* NMINCELL (4): FORCE halo depth in bonded cells                      */
+  int isQEq;          /* 0 skip, 1 CG, 2 extended Lagrangian (one CG step)                   */
+  int NMAXQEq;        /* max CG iterations                                                   */
+  int isPQEq;         /* 1: PQEq / ENbond_PQEq variants                                      */
+  int isEfield;       /* 1: EEfield add-on (src/module.F90:359)                              */
+  int eFieldDir;      /* 1..3                                                                */
+  double QEq_tol;     /* CG stop tolerance                                                   */
+  double Lex_fqs;     /* extended-Lagrangian mixing (src/qeq.F90:53)                         */
+  double eFieldStrength;
+} rxg_config;
+
+/* Flattened `module parameters` (src/module.F90:620-723) + derived tables, exactly as the host
+ * computed them in GETPARAMS (src/param.F90), CUTOFFLENGTH and POTENTIALTABLE (src/init.F90). */
+typedef struct rxg_ff {
+  int nso, nboty, nvaty, ntoty, nhbty, ntable;
+  double vpar1, vpar2, cutoff_vpar30;
+  double rctap, rctap2, UDR, UDRi;
+  /* per atom type, [nso] */
+  const double *Val, *Valval, *Valangle, *Vale, *mass, *plp1, *plp2, *nlpopt;
+  const double *povun2, *povun3, *povun4, *povun5, *povun6, *povun7, *povun8;
+  const double *pval3, *pval5, *chi, *eta;
+  /* per bond type, [nboty]; swtch is switch(1:3,nboty) */
+  const double *cBOp1, *cBOp3, *cBOp5, *pbo2h, *pbo4h, *pbo6h, *pbo2, *pbo4, *pbo6, *swtch;
+  const double *rc2, *pboc1, *pboc3, *pboc4, *pboc5, *ovc, *v13cor;
+  const double *Desig, *Depi, *Depipi, *pbe1, *pbe2, *povun1;
+  /* per valence-angle type, [nvaty] */
+  const double *theta00, *pval1, *pval2, *pval4, *pval6, *pval7, *pval8, *pval9, *pval10;
+  const double *ppen1, *ppen2, *ppen3, *ppen4, *pcoa1, *pcoa2, *pcoa3, *pcoa4;
+  /* per torsion type, [ntoty] */
+  const double *ptor1, *ptor2, *ptor3, *ptor4, *V1, *V2, *V3, *pcot1, *pcot2;
+  /* per hydrogen-bond type, [nhbty] */
+  const double *phb1, *phb2, *phb3, *r0hb;
+  /* lookup tables, column-major: inxn2(nso,nso) inxn3(nso,nso,nso) inxn3hb(..) inxn4(nso^4) */
+  const int *inxn2, *inxn3, *inxn3hb, *inxn4;
+  /* r^2-space tables: TBL_Evdw(0:1,NTABLE,nboty), TBL_Eclmb(0:1,NTABLE,nboty), TBL_Eclmb_QEq(NTABLE,nboty) */
+  const double *TBL_Evdw, *TBL_Eclmb, *TBL_Eclmb_QEq;
+  /* PQEq (module pqeq_vars, src/module.F90:336-615); NULL / 0 when isPQEq == 0 */
+  int ntype_pqeq;
+  const int *isPolarizable;          /* [ntype_pqeq] 0/1 */
+  const double *Zpqeq, *Kspqeq;      /* [ntype_pqeq] */
+  const int *inxnpqeq;               /* (ntype_pqeq,ntype_pqeq) */
+  const double *TBL_Eclmb_pcc, *TBL_Eclmb_psc, *TBL_Eclmb_pss; /* (ntype_pqeq^2,NTABLE,0:1) */
+} rxg_ff;
+
+/* Box, cell grids and rank topology (src/init.F90:74-100,525-607,636-668). */
+typedef struct rxg_box {
+  double HH[9];        /* HH(3,3,0) column-major                                             */
+  double HHi[9];       /* matinv(HH), column-major                                           */
+  double lata, latb, latc;
+  double LBOX[3];      /* 1/vprocs                                                           */
+  double OBOX[3];      /* LBOX*vID                                                           */
+  double lcsize[3];    /* bonded cell size, normalised                                       */
+  double nblcsize[3];  /* non-bonded cell size, normalised                                   */
+  int cc[3];           /* bonded cells per domain                                            */
+  int nbcc[3];         /* non-bonded cells per domain                                        */
+  int nbnmesh;         /* stencil size                                                       */
+  int vprocs[3];
+  int vID[3];
+  int myparity[3];
+  int target_node[6];  /* +x,-x,+y,-y,+z,-z neighbour ranks                                  */
+  int myid, nprocs;
+  const int *nbmesh;   /* nbmesh(3,nbnmesh) column-major                                     */
+} rxg_box;
+
+/* ---- life cycle ------------------------------------------------------------------------- */
+/* replaces the allocation part of INITSYSTEM (src/init.F90:110-201) for the device mirrors   */
+int rxg_create(const rxg_config *cfg, rxg_handle *out);
+/* replaces reading `module parameters` + TBL_* globals inside FORCE/QEq (src/pot.F90:3, src/qeq.F90:3) */
+int rxg_set_forcefield(rxg_handle h, const rxg_ff *ff);
+/* replaces reading HH/HHi/LBOX/OBOX/cc/lcsize/nbcc/nblcsize/nbmesh/target_node globals       */
+int rxg_set_box(rxg_handle h, const rxg_box *box);
+/* communicator: nccl_unique_id is the 128-byte ncclUniqueId broadcast by the host (MPI_Bcast in
+ * the Fortran shim, TCPStore in the harness).  Not needed when nprocs == 1.
+ * Replaces MPI_SEND/MPI_RECV/MPI_ALLREDUCE inside COPYATOMS/QEq (src/comm.F90:291-364, src/qeq.F90:107-144,357). */
+int rxg_comm_init(rxg_handle h, int rank, int nranks, const void *nccl_unique_id);
+int rxg_destroy(rxg_handle h);
+const char *rxg_last_error(rxg_handle h);
+
+/* ---- the drop-in entry points (host buffers in, host buffers out) -------------------------- */
+/* subroutine QEq(atype,pos,q)   src/qeq.F90:2     (also writes qsfp,qsfv when isQEq==1, :42-43) */
+int rxg_qeq(rxg_handle h, const int *natoms, const double *atype, const double *pos, double *q,
+            double *qsfp, double *qsfv, int *nstep_qeq);
+/* subroutine PQEq(atype,pos,q)  src/pqeq.F90:2    (spos = shell displacements, inout) */
+int rxg_pqeq(rxg_handle h, const int *natoms, const double *atype, const double *pos, double *q,
+             double *spos, double *qsfp, double *qsfv, int *nstep_qeq);
+/* subroutine FORCE(atype,pos,f,q) src/pot.F90:2   PE(0:13) overwritten, astr(1:6) incremented (:65-72) */
+int rxg_force(rxg_handle h, const int *natoms, const double *atype, const double *pos, double *f,
+              const double *q, double *PE, double *astr);
+/* call COPYATOMS(MODE_MOVE,[0,0,0],atype,pos,v,f,q)  src/main.F90:75, src/comm.F90:2,238-256
+ * natoms is in/out; every listed array is compacted exactly like the reference's finalize(). */
+int rxg_move(rxg_handle h, int *natoms, double *atype, double *pos, double *v, double *q,
+             double *qs, double *qt, double *qsfp, double *qsfv);
+/* WriteBND's inputs (src/fileio.F90:56-121): nbrlist(NBUFFER,0:MAXNEIGHBS) and BO(0,:,:) as
+ * double[nbuffer*maxneighbs] (atom index fastest), valid after rxg_force */
+int rxg_fetch_bonds(rxg_handle h, int *nbrlist, double *BO0);
+/* it_timer(1:30) slots filled from CUDA-event timings, in milliseconds (src/module.F90:215-217) */
+int rxg_timers(rxg_handle h, double *it_timer_ms);
+
+/* ---- device-resident stepping: the reference main-loop body src/main.F90:64-98
+ * executed nsteps times without host round trips (mdmode 1 NVE; vkick src/main.F90:192-207).   */
+int rxg_state_upload(rxg_handle h, int natoms, const double *atype, const double *pos,
+                     const double *v, const double *q, const double *qsfp, const double *qsfv);
+/* dt in reduced time units (dt[fs]/UTIME, src/init.F90:66); qstep as in rxmd.in; Lex_w2 src/init.F90:69 */
+int rxg_md_run(rxg_handle h, int nsteps, double dt, int qstep, double Lex_w2, int step0);
+/* initial QEq+FORCE of src/main.F90:27-32 on the resident state */
+int rxg_md_prime(rxg_handle h);
+int rxg_state_download(rxg_handle h, int *natoms, double *atype, double *pos, double *v, double *f,
+                       double *q, double *qsfp, double *qsfv);
+/* PE(0:13) of the last FORCE, kinetic energy sum_i hmas*v^2 (PRINTE src/main.F90:225-229), sum q,
+ * last nstep_qeq, accumulated astr(1:6) */
+int rxg_md_observe(rxg_handle h, double *PE, double *KE, double *qsum, int *nstep_qeq, double *astr);
+
+/* ---- introspection used by the parity tests (device -> host copies of hot-path products) ---- */
+/* name in: "copyptr"(7 ints) "nbrlist" "nbrindx" "nbp_rowptr"(int64) "nbp_col" "qeq_rowptr" "qeq_col"
+ * "qeq_val" "BO"(4 planes) "delta" "deltap" "atype" "pos" "q" "f" "qs" "qt" "gs" "gt" "hs" "ht" "cdbnd" "ccbnd"
+ * "nlp" "dDlp" "deltalp" "cell_bonded" "cell_nb" ...; returns element count through *count;
+ * out may be NULL to query the count only. */
+int rxg_debug_fetch(rxg_handle h, const char *name, void *out, long long capacity_bytes, long long *count);
+/* kernels launched so far by this handle (bench.py's gpu_launches) */
+long long rxg_launch_count(rxg_handle h);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RXMD_B200_H */
