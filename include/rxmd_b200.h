@@ -12,6 +12,8 @@
  *   - per-atom 3-vectors : double[3*nbuffer], x[0..nbuffer) y[..] z[..]   == pos(NBUFFER,3)
  *   - parameter arrays   : 1-based Fortran arrays passed by their first element, column-major
  *   - residents are elements 0..natoms-1 (Fortran 1..NATOMS)
+ *   - `pos` is in/out in QEq/FORCE exactly as in the reference: COPYATOMS maps positions to normalised
+ *     coordinates and back on every call (src/comm.F90:222-227,260-264), which perturbs them by ~1 ulp
  * All calls are synchronous at return (the host reads `f` right after FORCE, src/main.F90:86-97).
  * One host thread per handle; a handle owns one CUDA device (one MPI rank == one GPU).
  */
@@ -121,13 +123,13 @@ const char *rxg_last_error(rxg_handle h);
 
 /* ---- the drop-in entry points (host buffers in, host buffers out) -------------------------- */
 /* subroutine QEq(atype,pos,q)   src/qeq.F90:2     (also writes qsfp,qsfv when isQEq==1, :42-43) */
-int rxg_qeq(rxg_handle h, const int *natoms, const double *atype, const double *pos, double *q,
+int rxg_qeq(rxg_handle h, const int *natoms, const double *atype, double *pos, double *q,
             double *qsfp, double *qsfv, int *nstep_qeq);
 /* subroutine PQEq(atype,pos,q)  src/pqeq.F90:2    (spos = shell displacements, inout) */
-int rxg_pqeq(rxg_handle h, const int *natoms, const double *atype, const double *pos, double *q,
+int rxg_pqeq(rxg_handle h, const int *natoms, const double *atype, double *pos, double *q,
              double *spos, double *qsfp, double *qsfv, int *nstep_qeq);
 /* subroutine FORCE(atype,pos,f,q) src/pot.F90:2   PE(0:13) overwritten, astr(1:6) incremented (:65-72) */
-int rxg_force(rxg_handle h, const int *natoms, const double *atype, const double *pos, double *f,
+int rxg_force(rxg_handle h, const int *natoms, const double *atype, double *pos, double *f,
               const double *q, double *PE, double *astr);
 /* call COPYATOMS(MODE_MOVE,[0,0,0],atype,pos,v,f,q)  src/main.F90:75, src/comm.F90:2,238-256
  * natoms is in/out; every listed array is compacted exactly like the reference's finalize(). */

@@ -1,0 +1,583 @@
+// rxg_api.cu -- C-ABI entry points of librxmd_b200.so (see include/rxmd_b200.h) and the per-call orchestration.
+// No CPU fallback exists: every entry point fails with RXG_ERR_CUDA when no sm_100 device is usable.
+#include "rxg_common.cuh"
+#include "rxg_halo_cells.cuh"
+#include "rxg_lists_qeq.cuh"
+#include "rxg_bonded.cuh"
+
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+using namespace rxg;
+
+namespace {
+
+template <typename T>
+int dalloc(Ctx *c, T **p, size_t n) {
+  RXG_CUDA(cudaMalloc((void **)p, sizeof(T) * (n ? n : 1)));
+  c->allocs.push_back((void *)*p);
+  RXG_CUDA(cudaMemsetAsync(*p, 0, sizeof(T) * (n ? n : 1), c->st));
+  return RXG_OK;
+}
+
+template <typename T>
+int upload(Ctx *c, const T *host, size_t n, const T **dev) {
+  T *d = nullptr;
+  RXG_CUDA(cudaMalloc((void **)&d, sizeof(T) * (n ? n : 1)));
+  if (n) RXG_CUDA(cudaMemcpy(d, host, sizeof(T) * n, cudaMemcpyHostToDevice));
+  c->ff_allocs.push_back(d);
+  *dev = d;
+  return RXG_OK;
+}
+
+int setup_grid(Ctx *c, DevGrid &g, const int *cc, const double *cs, int L) {
+  g.L = L;
+  for (int a = 0; a < 3; a++) { g.nc[a] = cc[a]; g.dim[a] = cc[a] + 2 * L; g.cs[a] = cs[a]; }
+  long long ncell = (long long)g.dim[0] * g.dim[1] * g.dim[2];
+  if (ncell > 2000000000LL) { c->err = "cell grid too large"; return RXG_ERR_ARG; }
+  g.ncell = (int)ncell;
+  RXG_TRY(dalloc(c, &g.cell_of, c->NB));
+  RXG_TRY(dalloc(c, &g.start, (size_t)g.ncell + 2));
+  RXG_TRY(dalloc(c, &g.fill, (size_t)g.ncell + 1));
+  RXG_TRY(dalloc(c, &g.order, c->NB));
+  RXG_TRY(dalloc(c, &g.sorted, c->NB));
+  return RXG_OK;
+}
+
+int stage_ensure(Ctx *c, size_t bytes) {
+  if (bytes > c->h_stage_bytes) {
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    c->h_stage_bytes = bytes + bytes / 8;
+    RXG_CUDA(cudaMallocHost((void **)&c->h_stage, c->h_stage_bytes));
+  }
+  return RXG_OK;
+}
+
+// host array with leading dimension NB (planes) -> device plane array; n leading entries of each of `planes` planes
+int h2d_planes(Ctx *c, double *dev, const double *host, int planes, int n) {
+  for (int p = 0; p < planes; p++)
+    RXG_CUDA(cudaMemcpyAsync(dev + (size_t)p * c->NB, host + (size_t)p * c->NB, sizeof(double) * n, cudaMemcpyHostToDevice, c->st));
+  return RXG_OK;
+}
+int d2h_planes(Ctx *c, double *host, const double *dev, int planes, int n) {
+  for (int p = 0; p < planes; p++)
+    RXG_CUDA(cudaMemcpyAsync(host + (size_t)p * c->NB, dev + (size_t)p * c->NB, sizeof(double) * n, cudaMemcpyDeviceToHost, c->st));
+  return RXG_OK;
+}
+
+struct Timer {
+  Ctx *c;
+  int slot;
+  Timer(Ctx *c_, int s) : c(c_), slot(s) { cudaEventRecord(c->ev0, c->st); }
+  ~Timer() {
+    cudaEventRecord(c->ev1, c->st);
+    cudaEventSynchronize(c->ev1);
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    c->timers_ms[slot] += ms;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------------
+// subroutine QEq on device-resident state, reference src/qeq.F90:2-178
+int qeq_device(Ctx *c) {
+  const int isQEq = c->cfg.isQEq;
+  if (isQEq != 1 && isQEq != 2) return RXG_OK;
+  const int n = c->natoms, NB = c->NB;
+  const int nmax = (isQEq == 1) ? c->cfg.NMAXQEq : 1;
+  int nprev = c->cp[6] > n ? c->cp[6] : n;
+  LAUNCH(c, k_qeq_init, cdiv(nprev, 256), 256, 0, n, nprev, c->q, c->qst, c->hsq, c->qsfp, c->qsfv, isQEq, c->cfg.Lex_fqs);
+  double QCopyDr[3] = {c->ff.rctap / c->box.lata, c->ff.rctap / c->box.latb, c->ff.rctap / c->box.latc};
+  RXG_TRY(halo_copy(c, QCopyDr));
+  LAUNCH(c, k_types, cdiv(c->cp[6], 256), 256, 0, c->atype, c->cp[6], c->itype, c->gid);
+  RXG_TRY(bin_grid(c, c->gnb));
+  RXG_TRY(build_pairlist<true>(c));
+  RXG_TRY(halo_qcopy(c, 1));
+  const int rgrid = cdiv((long long)n * 32, 256);
+  RXG_CUDA(cudaMemsetAsync(c->d_acc, 0, sizeof(double) * 16, c->st));
+  const bool strict = c->strict;
+  double4 *rowbuf = (double4 *)c->tmp;
+  auto gradient = [&]() {
+    if (!strict) {
+      LAUNCH(c, k_gradient, rgrid, 256, 0, n, c->rowptr, c->col, c->val, c->qst, c->itype, c->d_ff, c->gst, c->d_acc);
+    } else {
+      LAUNCH(c, k_rows_strict_grad, cdiv(n, 64), 64, 0, n, c->rowptr, c->col, c->val, c->qst, c->itype, c->d_ff, c->gst);
+      LAUNCH(c, k_seq_reduce, 1, 1, 0, 2, n, rowbuf, c->hsq, c->gst, c->qst, c->d_acc);
+    }
+  };
+  gradient();
+  LAUNCH(c, k_h_from_g, cdiv(n, 256), 256, 0, n, c->gst, c->hsq);
+  RXG_TRY(halo_qcopy(c, 2));
+  double GEst2 = 1e99;
+  int it;
+  for (it = 0; it < nmax; it++) {
+    LAUNCH(c, k_clear_iter, 1, 1, 0, c->d_acc);
+    if (!strict) {
+      LAUNCH(c, k_hsh, rgrid, 256, 0, n, c->rowptr, c->col, c->val, c->hsq, c->gst, c->itype, c->d_ff, c->d_acc);
+    } else {
+      LAUNCH(c, k_rows_strict_hsh, cdiv(n, 64), 64, 0, n, c->rowptr, c->col, c->val, c->hsq, c->itype, c->d_ff, rowbuf);
+      LAUNCH(c, k_seq_reduce, 1, 1, 0, 0, n, rowbuf, c->hsq, c->gst, c->qst, c->d_acc);
+    }
+    RXG_CUDA(cudaMemcpyAsync(c->h_acc, c->d_acc, sizeof(double) * 5, cudaMemcpyDeviceToHost, c->st));
+    RXG_CUDA(cudaStreamSynchronize(c->st));
+    double GEst1 = c->h_acc[0];
+    if (0.5 * (std::fabs(GEst2) + std::fabs(GEst1)) < c->cfg.QEq_tol) break;                    // src/qeq.F90:114
+    if (std::fabs(GEst2) > 0.0 && std::fabs(GEst1 / GEst2 - 1.0) < c->cfg.QEq_tol) break;      // src/qeq.F90:115
+    GEst2 = GEst1;
+    float lmin_s = (float)(c->h_acc[3] / c->h_acc[1]);   // real(4) :: lmin, src/qeq.F90:23,133
+    float lmin_t = (float)(c->h_acc[4] / c->h_acc[2]);
+    LAUNCH(c, k_qupdate, cdiv(n, 256), 256, 0, n, lmin_s, lmin_t, c->hsq, c->qst, c->d_acc);
+    if (strict) LAUNCH(c, k_seq_reduce, 1, 1, 0, 1, n, rowbuf, c->hsq, c->gst, c->qst, c->d_acc);
+    LAUNCH(c, k_qfinal, cdiv(n, 256), 256, 0, n, c->qst, c->q, c->hsq, c->d_acc);
+    RXG_TRY(halo_qcopy(c, 1));
+    LAUNCH(c, k_roll_gnew, 1, 1, 0, c->d_acc);
+    gradient();
+    LAUNCH(c, k_hupdate, cdiv(n, 256), 256, 0, n, c->gst, c->hsq, c->d_acc);
+    RXG_TRY(halo_qcopy(c, 2));
+  }
+  c->nstep_qeq = it;
+  (void)NB;
+  return RXG_OK;
+}
+
+}   // namespace
+
+// ====================================================================================================
+extern "C" {
+
+int rxg_create(const rxg_config *cfg, rxg_handle *out) {
+  if (!cfg || !out) return RXG_ERR_ARG;
+  *out = nullptr;
+  Ctx *c = new Ctx();
+  c->cfg = *cfg;
+  c->NB = cfg->nbuffer;
+  c->MAXN = cfg->maxneighbs;
+  c->dev = cfg->device;
+  const char *so = getenv("RXG_STRICT_ORDER");
+  c->strict = so && so[0] == '1';
+  *out = c;   // returned even on failure so that rxg_last_error can be read
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+    c->err = "no CUDA device: librxmd_b200 has no CPU fallback";
+    return RXG_ERR_CUDA;
+  }
+  RXG_CUDA(cudaSetDevice(c->dev));
+  cudaDeviceProp prop;
+  RXG_CUDA(cudaGetDeviceProperties(&prop, c->dev));
+  if (prop.major != 10) {
+    c->err = std::string("device '") + prop.name + "' is not sm_100: this library is built for B200 only";
+    return RXG_ERR_CUDA;
+  }
+  RXG_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+  RXG_CUDA(cudaEventCreate(&c->ev0));
+  RXG_CUDA(cudaEventCreate(&c->ev1));
+  const size_t NB = c->NB, NS = NB * (size_t)c->MAXN;
+  RXG_TRY(dalloc(c, &c->pos, 3 * NB)); RXG_TRY(dalloc(c, &c->v, 3 * NB)); RXG_TRY(dalloc(c, &c->f, 3 * NB));
+  RXG_TRY(dalloc(c, &c->atype, NB)); RXG_TRY(dalloc(c, &c->q, NB)); RXG_TRY(dalloc(c, &c->qsfp, NB)); RXG_TRY(dalloc(c, &c->qsfv, NB));
+  RXG_TRY(dalloc(c, &c->qst, NB)); RXG_TRY(dalloc(c, &c->hsq, NB)); RXG_TRY(dalloc(c, &c->gst, NB));
+  RXG_TRY(dalloc(c, &c->itype, NB)); RXG_TRY(dalloc(c, &c->gid, NB)); RXG_TRY(dalloc(c, &c->frcindx, NB));
+  RXG_TRY(dalloc(c, &c->tmp, 12 * NB));
+  RXG_TRY(dalloc(c, &c->nbrcnt, NB)); RXG_TRY(dalloc(c, &c->nbrlist, NS)); RXG_TRY(dalloc(c, &c->nbrindx, NS));
+  RXG_TRY(dalloc(c, &c->rowptr, NB + 2)); RXG_TRY(dalloc(c, &c->rowcnt, NB + 2));
+  for (int k = 0; k < 4; k++) RXG_TRY(dalloc(c, &c->BO[k], NS));
+  for (int k = 0; k < 3; k++) { RXG_TRY(dalloc(c, &c->dln[k], NS)); RXG_TRY(dalloc(c, &c->cB[k], NS)); }
+  RXG_TRY(dalloc(c, &c->dBOp, NS)); RXG_TRY(dalloc(c, &c->A0, NS)); RXG_TRY(dalloc(c, &c->A1, NS));
+  RXG_TRY(dalloc(c, &c->A2, NS)); RXG_TRY(dalloc(c, &c->A3, NS)); RXG_TRY(dalloc(c, &c->cdslot, NS));
+  RXG_TRY(dalloc(c, &c->delta, NB)); RXG_TRY(dalloc(c, &c->deltap1, NB)); RXG_TRY(dalloc(c, &c->deltap2, NB));
+  RXG_TRY(dalloc(c, &c->nlp, NB)); RXG_TRY(dalloc(c, &c->dDlp, NB)); RXG_TRY(dalloc(c, &c->deltalp, NB));
+  RXG_TRY(dalloc(c, &c->ccbnd, NB)); RXG_TRY(dalloc(c, &c->cdbnd, NB));
+  RXG_TRY(dalloc(c, &c->d_acc, 64)); RXG_TRY(dalloc(c, &c->d_flag, 8));
+  RXG_CUDA(cudaMallocHost((void **)&c->h_acc, sizeof(double) * 64));
+  RXG_CUDA(cudaMallocHost((void **)&c->h_int, sizeof(int) * 16));
+  RXG_TRY(ensure_blk(c, NB));
+  RXG_CUDA(cudaStreamSynchronize(c->st));
+  return RXG_OK;
+}
+
+int rxg_set_forcefield(rxg_handle h, const rxg_ff *ff) {
+  Ctx *c = (Ctx *)h;
+  if (!c || !ff) return RXG_ERR_ARG;
+  RXG_CUDA(cudaSetDevice(c->dev));
+  for (void *p : c->ff_allocs) cudaFree(p);
+  c->ff_allocs.clear();
+  DevFF &d = c->ff;
+  d.nso = ff->nso; d.nboty = ff->nboty; d.nvaty = ff->nvaty; d.ntoty = ff->ntoty; d.nhbty = ff->nhbty; d.ntable = ff->ntable;
+  d.vpar1 = ff->vpar1; d.vpar2 = ff->vpar2; d.cutoff_vpar30 = ff->cutoff_vpar30;
+  d.rctap = ff->rctap; d.rctap2 = ff->rctap2; d.UDR = ff->UDR; d.UDRi = ff->UDRi;
+  const size_t ns = ff->nso, nb = ff->nboty, nv = ff->nvaty, nt = ff->ntoty, nh = ff->nhbty;
+#define UP(name, n) RXG_TRY(upload(c, ff->name, (n), &d.name))
+  UP(Val, ns); UP(Valval, ns); UP(Valangle, ns); UP(Vale, ns); UP(mass, ns); UP(plp1, ns); UP(plp2, ns); UP(nlpopt, ns);
+  UP(povun2, ns); UP(povun3, ns); UP(povun4, ns); UP(povun5, ns); UP(povun6, ns); UP(povun7, ns); UP(povun8, ns);
+  UP(pval3, ns); UP(pval5, ns); UP(chi, ns); UP(eta, ns);
+  UP(cBOp1, nb); UP(cBOp3, nb); UP(cBOp5, nb); UP(pbo2h, nb); UP(pbo4h, nb); UP(pbo6h, nb); UP(pbo2, nb); UP(pbo4, nb); UP(pbo6, nb);
+  UP(swtch, 3 * nb); UP(rc2, nb); UP(pboc1, nb); UP(pboc3, nb); UP(pboc4, nb); UP(pboc5, nb); UP(ovc, nb); UP(v13cor, nb);
+  UP(Desig, nb); UP(Depi, nb); UP(Depipi, nb); UP(pbe1, nb); UP(pbe2, nb); UP(povun1, nb);
+  UP(theta00, nv); UP(pval1, nv); UP(pval2, nv); UP(pval4, nv); UP(pval6, nv); UP(pval7, nv); UP(pval8, nv); UP(pval9, nv); UP(pval10, nv);
+  UP(ppen1, nv); UP(ppen2, nv); UP(ppen3, nv); UP(ppen4, nv); UP(pcoa1, nv); UP(pcoa2, nv); UP(pcoa3, nv); UP(pcoa4, nv);
+  UP(ptor1, nt); UP(ptor2, nt); UP(ptor3, nt); UP(ptor4, nt); UP(V1, nt); UP(V2, nt); UP(V3, nt); UP(pcot1, nt); UP(pcot2, nt);
+  UP(phb1, nh); UP(phb2, nh); UP(phb3, nh); UP(r0hb, nh);
+  UP(inxn2, ns * ns); UP(inxn3, ns * ns * ns); UP(inxn3hb, ns * ns * ns); UP(inxn4, ns * ns * ns * ns);
+  UP(TBL_Eclmb_QEq, (size_t)ff->ntable * nb);
+#undef UP
+  // interleave the vdW and Coulomb tables: one 32-byte record per (inxn, itb) node
+  std::vector<double4> tnb((size_t)ff->ntable * nb);
+  for (size_t x = 0; x < nb; x++)
+    for (size_t i = 0; i < (size_t)ff->ntable; i++) {
+      size_t k = 2 * (i + (size_t)ff->ntable * x);
+      tnb[x * ff->ntable + i] = make_double4(ff->TBL_Evdw[k], ff->TBL_Evdw[k + 1], ff->TBL_Eclmb[k], ff->TBL_Eclmb[k + 1]);
+    }
+  RXG_TRY(upload(c, tnb.data(), tnb.size(), &d.TBL_nb));
+  if (!c->d_ff) RXG_CUDA(cudaMalloc((void **)&c->d_ff, sizeof(DevFF)));
+  RXG_CUDA(cudaMemcpy(c->d_ff, &d, sizeof(DevFF), cudaMemcpyHostToDevice));
+  c->have_ff = true;
+  return RXG_OK;
+}
+
+int rxg_set_box(rxg_handle h, const rxg_box *box) {
+  Ctx *c = (Ctx *)h;
+  if (!c || !box) return RXG_ERR_ARG;
+  RXG_CUDA(cudaSetDevice(c->dev));
+  if (c->have_box) { c->err = "rxg_set_box may be called once per handle"; return RXG_ERR_STATE; }
+  c->box = *box;
+  c->box.nbmesh = nullptr;
+  if (box->nprocs != 1) { c->err = "multi-rank decomposition needs rxg_comm_init (not available in this build)"; return RXG_ERR_ARG; }
+  RXG_TRY(setup_grid(c, c->gb, box->cc, box->lcsize, RXG_MAXLAYERS));
+  RXG_TRY(setup_grid(c, c->gnb, box->nbcc, box->nblcsize, RXG_MAXLAYERS_NB));
+  // stencil -> z-runs, preserving the reference's mesh order (src/init.F90:563-592: i, j outer, k inner)
+  std::vector<int> runs;
+  for (int m = 0; m < box->nbnmesh; m++) {
+    int dx = box->nbmesh[3 * m], dy = box->nbmesh[3 * m + 1], dz = box->nbmesh[3 * m + 2];
+    size_t nr = runs.size() / 4;
+    if (nr && runs[4 * (nr - 1)] == dx && runs[4 * (nr - 1) + 1] == dy && runs[4 * (nr - 1) + 3] + 1 == dz)
+      runs[4 * (nr - 1) + 3] = dz;
+    else { runs.push_back(dx); runs.push_back(dy); runs.push_back(dz); runs.push_back(dz); }
+  }
+  c->nruns = (int)(runs.size() / 4);
+  RXG_CUDA(cudaMalloc((void **)&c->d_runs, sizeof(int) * (runs.size() + 4)));
+  RXG_CUDA(cudaMemcpy(c->d_runs, runs.data(), sizeof(int) * runs.size(), cudaMemcpyHostToDevice));
+  RXG_CUDA(cudaStreamSynchronize(c->st));
+  c->have_box = true;
+  return RXG_OK;
+}
+
+int rxg_comm_init(rxg_handle h, int rank, int nranks, const void *id) {
+  Ctx *c = (Ctx *)h;
+  (void)rank; (void)id;
+  if (nranks == 1) return RXG_OK;
+  c->err = "rxg_comm_init: NCCL halo exchange not built in this version";
+  return RXG_ERR_NCCL;
+}
+
+int rxg_destroy(rxg_handle h) {
+  Ctx *c = (Ctx *)h;
+  if (!c) return RXG_OK;
+  if (c->st) {
+    cudaSetDevice(c->dev);
+    cudaStreamSynchronize(c->st);
+    for (void *p : c->allocs) cudaFree(p);
+    for (void *p : c->ff_allocs) cudaFree(p);
+    for (void *p : {(void *)c->col, (void *)c->val, (void *)c->d_blk, (void *)c->d_blk64, (void *)c->d_runs, (void *)c->d_ff})
+      if (p) cudaFree(p);
+    if (c->h_acc) cudaFreeHost(c->h_acc);
+    if (c->h_int) cudaFreeHost(c->h_int);
+    if (c->h_stage) cudaFreeHost(c->h_stage);
+    cudaEventDestroy(c->ev0);
+    cudaEventDestroy(c->ev1);
+    cudaStreamDestroy(c->st);
+  }
+  delete c;
+  return RXG_OK;
+}
+
+const char *rxg_last_error(rxg_handle h) { return h ? ((Ctx *)h)->err.c_str() : "null handle"; }
+
+static int check_ready(Ctx *c, int natoms) {
+  if (!c) return RXG_ERR_ARG;
+  if (!c->have_ff || !c->have_box) { c->err = "rxg_set_forcefield / rxg_set_box not called"; return RXG_ERR_STATE; }
+  if (natoms < 0 || natoms > c->NB) { c->err = "natoms outside [0, nbuffer]"; return RXG_ERR_ARG; }
+  cudaSetDevice(c->dev);
+  return RXG_OK;
+}
+
+int rxg_qeq(rxg_handle h, const int *natoms, const double *atype, double *pos, double *q, double *qsfp, double *qsfv,
+            int *nstep_qeq) {
+  Ctx *c = (Ctx *)h;
+  RXG_TRY(check_ready(c, natoms ? *natoms : -1));
+  const int n = *natoms;
+  c->natoms = n;
+  RXG_TRY(h2d_planes(c, c->atype, atype, 1, n));
+  RXG_TRY(h2d_planes(c, c->pos, pos, 3, n));
+  RXG_TRY(h2d_planes(c, c->q, q, 1, n));
+  if (c->cfg.isQEq == 2) { RXG_TRY(h2d_planes(c, c->qsfp, qsfp, 1, n)); }
+  {
+    Timer t(c, 0);
+    RXG_TRY(qeq_device(c));
+  }
+  RXG_TRY(d2h_planes(c, q, c->q, 1, c->cp[6] > n ? c->cp[6] : n));
+  RXG_TRY(d2h_planes(c, pos, c->pos, 3, n));
+  if (c->cfg.isQEq == 1 && qsfp && qsfv) { RXG_TRY(d2h_planes(c, qsfp, c->qsfp, 1, n)); RXG_TRY(d2h_planes(c, qsfv, c->qsfv, 1, n)); }
+  RXG_CUDA(cudaStreamSynchronize(c->st));
+  if (nstep_qeq) *nstep_qeq = c->nstep_qeq;
+  return RXG_OK;
+}
+
+int rxg_pqeq(rxg_handle h, const int *, const double *, double *, double *, double *, double *, double *, int *) {
+  Ctx *c = (Ctx *)h;
+  if (c) c->err = "PQEq is not implemented in this version (SURVEY 8a row a18)";
+  return RXG_ERR_STATE;
+}
+
+int rxg_force(rxg_handle h, const int *natoms, const double *atype, double *pos, double *f, const double *q, double *PE,
+              double *astr) {
+  Ctx *c = (Ctx *)h;
+  RXG_TRY(check_ready(c, natoms ? *natoms : -1));
+  const int n = *natoms;
+  c->natoms = n;
+  RXG_TRY(h2d_planes(c, c->atype, atype, 1, n));
+  RXG_TRY(h2d_planes(c, c->pos, pos, 3, n));
+  RXG_TRY(h2d_planes(c, c->q, q, 1, n));
+  {
+    Timer t(c, 1);
+    RXG_TRY(force_device(c));
+  }
+  RXG_TRY(d2h_planes(c, f, c->f, 3, n));
+  RXG_TRY(d2h_planes(c, pos, c->pos, 3, n));
+  RXG_CUDA(cudaStreamSynchronize(c->st));
+  if (PE) for (int k = 0; k < 14; k++) PE[k] = c->PE[k];
+  if (astr) for (int k = 0; k < 6; k++) astr[k] += c->astr[k];
+  return RXG_OK;
+}
+
+int rxg_move(rxg_handle h, int *natoms, double *atype, double *pos, double *v, double *q, double *qs, double *qt, double *qsfp,
+             double *qsfv) {
+  Ctx *c = (Ctx *)h;
+  RXG_TRY(check_ready(c, natoms ? *natoms : -1));
+  const int n = *natoms;
+  c->natoms = n;
+  RXG_TRY(h2d_planes(c, c->atype, atype, 1, n));
+  RXG_TRY(h2d_planes(c, c->pos, pos, 3, n));
+  RXG_TRY(h2d_planes(c, c->v, v, 3, n));
+  RXG_TRY(h2d_planes(c, c->q, q, 1, n));
+  RXG_TRY(h2d_planes(c, c->qsfp, qsfp, 1, n));
+  RXG_TRY(h2d_planes(c, c->qsfv, qsfv, 1, n));
+  // qs/qt travel with the atom in the reference (src/comm.F90:164-171); the device keeps them packed
+  if (qs && qt) {
+    RXG_TRY(stage_ensure(c, sizeof(double) * 2 * (size_t)n));
+    for (int i = 0; i < n; i++) { c->h_stage[2 * i] = qs[i]; c->h_stage[2 * i + 1] = qt[i]; }
+    RXG_CUDA(cudaMemcpyAsync(c->qst, c->h_stage, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, c->st));
+  }
+  {
+    Timer t(c, 2);
+    RXG_TRY(halo_move(c));
+  }
+  const int m = c->natoms;
+  RXG_TRY(d2h_planes(c, atype, c->atype, 1, m));
+  RXG_TRY(d2h_planes(c, pos, c->pos, 3, m));
+  RXG_TRY(d2h_planes(c, v, c->v, 3, m));
+  RXG_TRY(d2h_planes(c, q, c->q, 1, m));
+  RXG_TRY(d2h_planes(c, qsfp, c->qsfp, 1, m));
+  RXG_TRY(d2h_planes(c, qsfv, c->qsfv, 1, m));
+  if (qs && qt) {
+    RXG_TRY(stage_ensure(c, sizeof(double) * 2 * (size_t)m));
+    RXG_CUDA(cudaMemcpyAsync(c->h_stage, c->qst, sizeof(double) * 2 * m, cudaMemcpyDeviceToHost, c->st));
+    RXG_CUDA(cudaStreamSynchronize(c->st));
+    for (int i = 0; i < m; i++) { qs[i] = c->h_stage[2 * i]; qt[i] = c->h_stage[2 * i + 1]; }
+  }
+  RXG_CUDA(cudaStreamSynchronize(c->st));
+  *natoms = m;
+  return RXG_OK;
+}
+
+int rxg_fetch_bonds(rxg_handle h, int *nbrlist, double *BO0) {
+  Ctx *c = (Ctx *)h;
+  RXG_TRY(check_ready(c, 0));
+  // reference layout: nbrlist(NBUFFER,0:MAXNEIGHBS) / BO(0,NBUFFER,MAXNEIGHBS), atom index fastest (src/init.F90:163,175)
+  const int n = c->cp[6], MAXN = c->MAXN, NB = c->NB;
+  std::vector<int> cnt(n), lst((size_t)n * MAXN);
+  std::vector<double> bo((size_t)n * MAXN);
+  RXG_CUDA(cudaMemcpy(cnt.data(), c->nbrcnt, sizeof(int) * n, cudaMemcpyDeviceToHost));
+  RXG_CUDA(cudaMemcpy(lst.data(), c->nbrlist, sizeof(int) * n * MAXN, cudaMemcpyDeviceToHost));
+  RXG_CUDA(cudaMemcpy(bo.data(), c->BO[0], sizeof(double) * n * MAXN, cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; i++) {
+    if (nbrlist) nbrlist[i] = cnt[i];
+    for (int s = 0; s < cnt[i] && s < MAXN; s++) {
+      if (nbrlist) nbrlist[(size_t)(s + 1) * NB + i] = lst[(size_t)i * MAXN + s] + 1;   // 1-based atom indices
+      if (BO0) BO0[(size_t)s * NB + i] = bo[(size_t)i * MAXN + s];
+    }
+  }
+  return RXG_OK;
+}
+
+int rxg_timers(rxg_handle h, double *t) {
+  Ctx *c = (Ctx *)h;
+  if (!c || !t) return RXG_ERR_ARG;
+  for (int k = 0; k < 30; k++) t[k] = c->timers_ms[k];
+  return RXG_OK;
+}
+
+long long rxg_launch_count(rxg_handle h) { return h ? ((Ctx *)h)->launches : 0; }
+
+// ---- device-resident stepping -----------------------------------------------------------------------------
+int rxg_state_upload(rxg_handle h, int natoms, const double *atype, const double *pos, const double *v, const double *q,
+                     const double *qsfp, const double *qsfv) {
+  Ctx *c = (Ctx *)h;
+  RXG_TRY(check_ready(c, natoms));
+  c->natoms = natoms;
+  for (int k = 0; k < 7; k++) c->cp[k] = natoms;
+  RXG_TRY(h2d_planes(c, c->atype, atype, 1, natoms));
+  RXG_TRY(h2d_planes(c, c->pos, pos, 3, natoms));
+  if (v) RXG_TRY(h2d_planes(c, c->v, v, 3, natoms)); else RXG_CUDA(cudaMemsetAsync(c->v, 0, sizeof(double) * 3 * c->NB, c->st));
+  if (q) RXG_TRY(h2d_planes(c, c->q, q, 1, natoms)); else RXG_CUDA(cudaMemsetAsync(c->q, 0, sizeof(double) * c->NB, c->st));
+  if (qsfp) RXG_TRY(h2d_planes(c, c->qsfp, qsfp, 1, natoms)); else RXG_CUDA(cudaMemsetAsync(c->qsfp, 0, sizeof(double) * c->NB, c->st));
+  if (qsfv) RXG_TRY(h2d_planes(c, c->qsfv, qsfv, 1, natoms)); else RXG_CUDA(cudaMemsetAsync(c->qsfv, 0, sizeof(double) * c->NB, c->st));
+  RXG_CUDA(cudaStreamSynchronize(c->st));
+  return RXG_OK;
+}
+
+int rxg_md_prime(rxg_handle h) {
+  Ctx *c = (Ctx *)h;
+  RXG_TRY(check_ready(c, c ? c->natoms : -1));
+  RXG_TRY(qeq_device(c));
+  RXG_TRY(force_device(c));
+  RXG_CUDA(cudaStreamSynchronize(c->st));
+  return RXG_OK;
+}
+
+int rxg_md_run(rxg_handle h, int nsteps, double dt, int qstep, double Lex_w2, int step0) {
+  Ctx *c = (Ctx *)h;
+  RXG_TRY(check_ready(c, c ? c->natoms : -1));
+  if (qstep < 1) qstep = 1;
+  for (int nstep = step0; nstep < step0 + nsteps; nstep++) {
+    int n = c->natoms;
+    // vkick(1) ; qsfv,qsfp ; pos += dt v      (src/main.F90:64-72)
+    LAUNCH(c, k_md_first_half, cdiv(n, 256), 256, 0, n, c->NB, dt, Lex_w2, c->itype, c->d_ff, c->pos, c->v, c->f, c->q, c->qsfp, c->qsfv);
+    RXG_TRY(halo_move(c));                                   // :75
+    if (nstep % qstep == 0) RXG_TRY(qeq_device(c));          // :77-83
+    RXG_TRY(force_device(c));                                // :84
+    n = c->natoms;
+    // kinetic stress, vkick(1), qsfv                        (src/main.F90:86-98)
+    LAUNCH(c, k_md_second_half, cdiv(n, 256), 256, 0, n, c->NB, dt, Lex_w2, c->itype, c->d_ff, c->v, c->f, c->q, c->qsfp, c->qsfv, c->d_acc + 40);
+  }
+  RXG_CUDA(cudaStreamSynchronize(c->st));
+  return RXG_OK;
+}
+
+int rxg_state_download(rxg_handle h, int *natoms, double *atype, double *pos, double *v, double *f, double *q, double *qsfp,
+                       double *qsfv) {
+  Ctx *c = (Ctx *)h;
+  RXG_TRY(check_ready(c, c ? c->natoms : -1));
+  const int n = c->natoms;
+  if (natoms) *natoms = n;
+  if (atype) RXG_TRY(d2h_planes(c, atype, c->atype, 1, n));
+  if (pos) RXG_TRY(d2h_planes(c, pos, c->pos, 3, n));
+  if (v) RXG_TRY(d2h_planes(c, v, c->v, 3, n));
+  if (f) RXG_TRY(d2h_planes(c, f, c->f, 3, n));
+  if (q) RXG_TRY(d2h_planes(c, q, c->q, 1, n));
+  if (qsfp) RXG_TRY(d2h_planes(c, qsfp, c->qsfp, 1, n));
+  if (qsfv) RXG_TRY(d2h_planes(c, qsfv, c->qsfv, 1, n));
+  RXG_CUDA(cudaStreamSynchronize(c->st));
+  return RXG_OK;
+}
+
+int rxg_md_observe(rxg_handle h, double *PE, double *KE, double *qsum, int *nstep_qeq, double *astr) {
+  Ctx *c = (Ctx *)h;
+  RXG_TRY(check_ready(c, c ? c->natoms : -1));
+  const int n = c->natoms;
+  RXG_CUDA(cudaMemsetAsync(c->d_acc + 48, 0, sizeof(double) * 2, c->st));
+  LAUNCH(c, k_observe, cdiv(n, 256), 256, 0, n, c->NB, c->itype, c->d_ff, c->v, c->q, c->d_acc + 48);
+  RXG_CUDA(cudaMemcpyAsync(c->h_acc + 40, c->d_acc + 40, sizeof(double) * 10, cudaMemcpyDeviceToHost, c->st));
+  RXG_CUDA(cudaStreamSynchronize(c->st));
+  if (PE) {
+    c->PE[0] = 0;
+    for (int k = 1; k < 14; k++) c->PE[0] += c->PE[k];   // PRINTE, src/main.F90:232
+    for (int k = 0; k < 14; k++) PE[k] = c->PE[k];
+  }
+  if (KE) *KE = c->h_acc[48];
+  if (qsum) *qsum = c->h_acc[49];
+  if (nstep_qeq) *nstep_qeq = c->nstep_qeq;
+  if (astr) for (int k = 0; k < 6; k++) astr[k] = c->astr[k] + c->h_acc[40 + k];
+  return RXG_OK;
+}
+
+// ---- introspection for the parity tests ----------------------------------------------------------------------
+int rxg_debug_fetch(rxg_handle h, const char *name, void *out, long long cap, long long *count) {
+  Ctx *c = (Ctx *)h;
+  if (!c || !name) return RXG_ERR_ARG;
+  cudaSetDevice(c->dev);
+  cudaStreamSynchronize(c->st);
+  const std::string s(name);
+  const long long n6 = c->cp[6] > c->natoms ? c->cp[6] : c->natoms, nat = c->natoms, NS = n6 * c->MAXN;
+  const void *src = nullptr;
+  long long bytes = 0, cnt = 0;
+  std::vector<double> tmpd;
+  auto dev = [&](const void *p, long long n, size_t esz) { src = p; cnt = n; bytes = n * (long long)esz; };
+  if (s == "copyptr") {
+    cnt = 7;
+    if (count) *count = cnt;
+    if (out) { if (cap < 28) return RXG_ERR_ARG; memcpy(out, c->cp, 28); }
+    return RXG_OK;
+  }
+  if (s == "nnz") {
+    if (count) *count = 1;
+    if (out) { if (cap < 8) return RXG_ERR_ARG; memcpy(out, &c->nnz, 8); }
+    return RXG_OK;
+  }
+  // 3-vector planes are returned compact [3][n6]
+  if (s == "pos" || s == "f" || s == "v") {
+    const double *p = s == "pos" ? c->pos : (s == "f" ? c->f : c->v);
+    cnt = 3 * n6;
+    if (count) *count = cnt;
+    if (out) {
+      if (cap < cnt * 8) return RXG_ERR_ARG;
+      for (int a = 0; a < 3; a++)
+        RXG_CUDA(cudaMemcpy((double *)out + a * n6, p + (size_t)a * c->NB, sizeof(double) * n6, cudaMemcpyDeviceToHost));
+    }
+    return RXG_OK;
+  }
+  if (s == "atype") dev(c->atype, n6, 8);
+  else if (s == "q") dev(c->q, n6, 8);
+  else if (s == "qst") dev(c->qst, 2 * n6, 8);
+  else if (s == "gst") dev(c->gst, 2 * nat, 8);
+  else if (s == "hsq") dev(c->hsq, 4 * n6, 8);
+  else if (s == "frcindx") dev(c->frcindx, n6, 4);
+  else if (s == "itype") dev(c->itype, n6, 4);
+  else if (s == "gid") dev(c->gid, n6, 4);
+  else if (s == "cell_bonded") dev(c->gb.cell_of, n6, 4);
+  else if (s == "cell_nb") dev(c->gnb.cell_of, n6, 4);
+  else if (s == "nbrcnt") dev(c->nbrcnt, n6, 4);
+  else if (s == "nbrlist") dev(c->nbrlist, NS, 4);
+  else if (s == "nbrindx") dev(c->nbrindx, NS, 4);
+  else if (s == "rowptr") dev(c->rowptr, nat + 1, 8);
+  else if (s == "col") dev(c->col, c->nnz, 4);
+  else if (s == "val") dev(c->val, c->nnz, 8);
+  else if (s == "BO0") dev(c->BO[0], NS, 8);
+  else if (s == "BO1") dev(c->BO[1], NS, 8);
+  else if (s == "BO2") dev(c->BO[2], NS, 8);
+  else if (s == "BO3") dev(c->BO[3], NS, 8);
+  else if (s == "dln_BOp1") dev(c->dln[0], NS, 8);
+  else if (s == "dln_BOp2") dev(c->dln[1], NS, 8);
+  else if (s == "dln_BOp3") dev(c->dln[2], NS, 8);
+  else if (s == "dBOp") dev(c->dBOp, NS, 8);
+  else if (s == "A0") dev(c->A0, NS, 8);
+  else if (s == "A1") dev(c->A1, NS, 8);
+  else if (s == "A2") dev(c->A2, NS, 8);
+  else if (s == "A3") dev(c->A3, NS, 8);
+  else if (s == "delta") dev(c->delta, n6, 8);
+  else if (s == "deltap1") dev(c->deltap1, n6, 8);
+  else if (s == "deltap2") dev(c->deltap2, n6, 8);
+  else if (s == "nlp") dev(c->nlp, n6, 8);
+  else if (s == "dDlp") dev(c->dDlp, n6, 8);
+  else if (s == "deltalp") dev(c->deltalp, n6, 8);
+  else if (s == "cdbnd") dev(c->cdbnd, n6, 8);
+  else if (s == "ccbnd") dev(c->ccbnd, n6, 8);
+  else { c->err = "rxg_debug_fetch: unknown name " + s; return RXG_ERR_ARG; }
+  if (count) *count = cnt;
+  if (out) {
+    if (cap < bytes) return RXG_ERR_ARG;
+    if (bytes) RXG_CUDA(cudaMemcpy(out, src, bytes, cudaMemcpyDeviceToHost));
+  }
+  return RXG_OK;
+}
+
+}   // extern "C"

@@ -1,0 +1,932 @@
+// rxg_bonded.cuh -- bond orders (kernel group B), energy/force terms (C1-C6), bonded-force finalisation (C7),
+// FORCE orchestration and the device-resident integrator kernels.
+// Reference: src/bo.F90 (BOCALC), src/pot.F90 (FORCE and all terms), src/main.F90:64-98,192-207.
+//
+// Restructuring relative to the reference (results equal up to fp64 summation order):
+//  * every ForceB/ForceBbo call is linear in per-bond data, so energy kernels only ACCUMULATE the coefficient
+//    triple (cf1,cf2,cf3 of src/pot.F90:1331) per directed bond slot, and cdbnd per atom; one gather kernel per
+//    atom then produces the bond forces and ccbnd without atomics (k_final1), a second applies ccbnd (k_final2).
+//  * the serial, order-dependent ForceBondedTerms loop (src/pot.F90:125-140) becomes the
+//    predicate `j < i` on reference local indices inside k_final1.
+//  * ENbond evaluates each resident's full 10 A row (both directions of a pair) so that no force is scattered;
+//    energies are still counted once, on the side the reference counts them (gid(j) < gid(i)).
+#pragma once
+#include "rxg_lists_qeq.cuh"
+
+namespace rxg {
+
+constexpr double MAXANGLE = 0.999999999999, MINANGLE = -0.999999999999, NSMALL = 1e-10;   // src/module.F90:85-87
+constexpr double PI_RX = 3.14159265358979;                                                  // src/module.F90:90
+constexpr double MINBO0 = 1e-4, CUTOF2_ESUB = 1e-4;                                         // src/module.F90:61-62
+constexpr double CECHRGE = 23.02;                                                           // src/module.F90:683
+constexpr double RCHB2 = 100.0;                                                             // src/module.F90:677-678
+
+// d_acc layout for FORCE: 16+k = PE(k) k=1..13 ; 32.. reserved (nnz) ; 34..39 astr ; 40..45 kinetic astr ; 48 KE ; 49 sum q
+constexpr int ACC_PE = 16, ACC_ASTR = 34;
+
+struct Bonds {   // per directed slot [i*MAXN + s]
+  int MAXN;
+  const int *cnt, *lst, *idx;
+  double *BO0, *BO1, *BO2, *BO3, *dln1, *dln2, *dln3, *dBOp, *A0, *A1, *A2, *A3;
+  double *cB0, *cB1, *cB2, *cdslot;
+};
+
+// ---------------------------------------------------------------------------------------------------
+// B1: BOPRIM, src/bo.F90:28-118.  One thread per atom; each directed slot evaluates the (bitwise symmetric)
+// pair expression itself instead of mirroring through nbrindx; deltap(i,1) is the atom's own row sum.
+__global__ void __launch_bounds__(128) k_boprim(int ntot, const double *__restrict__ pos, int NB, const int *__restrict__ itype,
+                                                const DevFF *__restrict__ ffp, Bonds B, double *__restrict__ deltap1,
+                                                double *__restrict__ deltap2, double *__restrict__ cdbnd,
+                                                double *__restrict__ ccbnd) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ntot) return;
+  const DevFF &ff = *ffp;
+  const int ity = itype[i];
+  cdbnd[i] = 0.0;
+  ccbnd[i] = 0.0;
+  if (ity <= 0) { deltap1[i] = 0.0; deltap2[i] = 0.0; return; }
+  const double xi = pos[i], yi = pos[NB + i], zi = pos[2 * NB + i];
+  double dp = -ff.Val[ity - 1];
+  const int n = B.cnt[i];
+  for (int s = 0; s < n; s++) {
+    size_t a = (size_t)i * B.MAXN + s;
+    int j = B.lst[a];
+    int x = ff.inxn2[(ity - 1) + ff.nso * (itype[j] - 1)] - 1;
+    double dx = sub_rn(xi, pos[j]), dy = sub_rn(yi, pos[NB + j]), dz = sub_rn(zi, pos[2 * NB + j]);
+    double dr2 = dist2_rn(dx, dy, dz);
+    double b0 = 0, b1 = 0, b2 = 0, b3 = 0, l1 = 0, l2 = 0, l3 = 0, db = 0;
+    if (x >= 0 && dr2 <= ff.rc2[x]) {
+      double a1 = ff.cBOp1[x] * pow(dr2, ff.pbo2h[x]);
+      double a2 = ff.cBOp3[x] * pow(dr2, ff.pbo4h[x]);
+      double a3 = ff.cBOp5[x] * pow(dr2, ff.pbo6h[x]);
+      b1 = ff.swtch[3 * x] * exp(a1);
+      b2 = ff.swtch[3 * x + 1] * exp(a2);
+      b3 = ff.swtch[3 * x + 2] * exp(a3);
+      b1 = (1.0 + ff.cutoff_vpar30) * b1;
+      if ((b1 + b2) + b3 > ff.cutoff_vpar30) {
+        l1 = ff.swtch[3 * x] * ff.pbo2[x] * a1 / dr2;
+        l2 = ff.swtch[3 * x + 1] * ff.pbo4[x] * a2 / dr2;
+        l3 = ff.swtch[3 * x + 2] * ff.pbo6[x] * a3 / dr2;
+        db = (b1 * l1 + b2 * l2) + b3 * l3;
+        b1 = b1 - ff.cutoff_vpar30;
+        b0 = (b1 + b2) + b3;
+        dp += b0;
+      } else {
+        b1 = b2 = b3 = 0.0;
+      }
+    }
+    B.BO0[a] = b0; B.BO1[a] = b1; B.BO2[a] = b2; B.BO3[a] = b3;
+    B.dln1[a] = l1; B.dln2[a] = l2; B.dln3[a] = l3; B.dBOp[a] = db;
+    B.cB0[a] = 0.0; B.cB1[a] = 0.0; B.cB2[a] = 0.0; B.cdslot[a] = 0.0;
+  }
+  deltap1[i] = dp;
+  deltap2[i] = dp + ff.Val[ity - 1] - ff.Valval[ity - 1];   // src/bo.F90:149-152
+}
+
+// B2: BOFULL, src/bo.F90:121-298; each slot computes its own side (A2/A3 are side specific, the rest symmetric)
+__global__ void __launch_bounds__(128) k_bofull(int ntot, const int *__restrict__ itype, const DevFF *__restrict__ ffp, Bonds B,
+                                                const double *__restrict__ deltap1, const double *__restrict__ deltap2,
+                                                double *__restrict__ delta) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ntot) return;
+  const DevFF &ff = *ffp;
+  const int ity = itype[i];
+  if (ity <= 0) { delta[i] = 0.0; return; }
+  const double Vi = ff.Val[ity - 1];
+  const double dpi = deltap1[i], dp2i = deltap2[i];
+  const double e1i = exp(-ff.vpar1 * dpi), e2i = exp(-ff.vpar2 * dpi);
+  double dsum = 0.0;
+  const int n = B.cnt[i];
+  for (int s = 0; s < n; s++) {
+    size_t a = (size_t)i * B.MAXN + s;
+    int j = B.lst[a];
+    int jty = itype[j];
+    int x = ff.inxn2[(ity - 1) + ff.nso * (jty - 1)] - 1;
+    if (x < 0) continue;
+    const double Vj = ff.Val[jty - 1];
+    const double dpj = deltap1[j], dp2j = deltap2[j];
+    const double e1j = exp(-ff.vpar1 * dpj), e2j = exp(-ff.vpar2 * dpj);
+    double fn2 = e1i + e1j;
+    double fn3 = (-1.0 / ff.vpar2) * log(0.5 * (e2i + e2j));
+    double fn23 = fn2 + fn3;
+    double BOp0 = B.BO0[a], bp2 = B.BO2[a], bp3 = B.BO3[a];
+    double fn1 = 0.5 * ((Vi + fn2) / (Vi + fn23) + (Vj + fn2) / (Vj + fn23));
+    const bool no_ovc = ff.ovc[x] < 1e-3, no_v13 = ff.v13cor[x] < 1e-3;
+    if (no_ovc) fn1 = 1.0;
+    double BOpsqr = BOp0 * BOp0;
+    double p3 = ff.pboc3[x], p4 = ff.pboc4[x], p5 = ff.pboc5[x];
+    double fn4 = 1.0 / (1.0 + exp(-p3 * (p4 * BOpsqr - dp2i) + p5));
+    double fn5 = 1.0 / (1.0 + exp(-p3 * (p4 * BOpsqr - dp2j) + p5));
+    if (no_v13) { fn4 = 1.0; fn5 = 1.0; }
+    double fn45 = fn4 * fn5, fn145 = fn1 * fn45, fn1145 = fn1 * fn145;
+    double B0 = BOp0 * fn145, B2 = bp2 * fn1145, B3 = bp3 * fn1145;
+    if (B0 < 1e-10) B0 = 0.0;
+    if (B2 < 1e-10) B2 = 0.0;
+    if (B3 < 1e-10) B3 = 0.0;
+    double B1 = B0 - B2 - B3;
+    double u1ij = Vi + fn23, u1ji = Vj + fn23;
+    double u1ij_inv2 = 1.0 / (u1ij * u1ij), u1ji_inv2 = 1.0 / (u1ji * u1ji);
+    double Cf1A = 0.5 * fn3 * (u1ij_inv2 + u1ji_inv2);
+    double Cf1B = -0.5 * ((u1ij - fn3) * u1ij_inv2 + (u1ji - fn3) * u1ji_inv2);
+    double e22 = e2i + e2j;
+    double Cf1ij = (-Cf1A * ff.pboc1[x] * e1i) + (Cf1B * e2i) / e22;
+    double p34 = p3 * p4;
+    double u45ij = p5 + p3 * dp2i - p34 * BOpsqr;
+    double u45ji = p5 + p3 * dp2j - p34 * BOpsqr;
+    double x45ij = exp(u45ij), x45ji = exp(u45ji);
+    double ex1 = 1.0 / (1.0 + x45ij), ex2 = 1.0 / (1.0 + x45ji);
+    double ex12 = ex1 * ex2;
+    double Cf45ij = -x45ij * ex12 * ex1, Cf45ji = -x45ji * ex12 * ex2;
+    if (no_ovc) Cf1ij = 0.0;
+    if (no_v13) { Cf45ij = 0.0; Cf45ji = 0.0; }
+    double fn45_inv = 1.0 / fn45;
+    double Cf1ij_div1 = Cf1ij / fn1;
+    B.BO0[a] = B0; B.BO1[a] = B1; B.BO2[a] = B2; B.BO3[a] = B3;
+    B.A0[a] = fn145;
+    B.A1[a] = -2.0 * p34 * BOp0 * (Cf45ij + Cf45ji) * fn45_inv;
+    double a2 = Cf1ij_div1 + (p3 * Cf45ij * fn45_inv);
+    B.A2[a] = a2;
+    B.A3[a] = a2 + Cf1ij_div1;
+    dsum += B0;
+  }
+  delta[i] = -Vi + dsum;   // src/bo.F90:292-295
+}
+
+// ---------------------------------------------------------------------------------------------------
+template <int NV>
+__device__ __forceinline__ void block_add(double (&v)[NV], double *__restrict__ acc) {
+  block_accumulate<NV>(v, acc);
+}
+
+// pack {x,y,z,q} and {itype,gid} for the non-bonded gathers
+__global__ void k_pack_pq(int ntot, const double *__restrict__ pos, int NB, const double *__restrict__ q,
+                          const int *__restrict__ itype, const int *__restrict__ gid, double4 *__restrict__ pq,
+                          int2 *__restrict__ tg) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ntot) return;
+  pq[i] = make_double4(pos[i], pos[NB + i], pos[2 * NB + i], q[i]);
+  tg[i] = make_int2(itype[i], gid[i]);
+}
+
+// C6: ENbond, src/pot.F90:676-781.  One warp per resident row of the 10 A list.
+// HALF=true is the literal form (gid(j)<gid(i), forces scattered to j); HALF=false evaluates the full row.
+template <bool HALF>
+__global__ void __launch_bounds__(256) k_enbond(int natoms, const long long *__restrict__ rowptr, const int *__restrict__ col,
+                                                const double4 *__restrict__ pq, const int2 *__restrict__ tg,
+                                                const DevFF *__restrict__ ffp, double *__restrict__ f, int NB,
+                                                double *__restrict__ acc) {
+  const int lane = threadIdx.x & 31;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  double part[3] = {0.0, 0.0, 0.0};
+  double vir[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  if (i < natoms) {
+    const DevFF &ff = *ffp;
+    const double4 pi = pq[i];
+    const int2 ti = tg[i];
+    double fx = 0, fy = 0, fz = 0;
+    long long s = rowptr[i], e = rowptr[i + 1];
+    for (long long k = s + lane; k < e; k += 32) {
+      int j = __ldcs(col + k);
+      int2 tj = tg[j];
+      bool lower = tj.y < ti.y;
+      if (HALF ? !lower : (tj.y == ti.y)) continue;
+      double4 pj = pq[j];
+      double dx = sub_rn(pi.x, pj.x), dy = sub_rn(pi.y, pj.y), dz = sub_rn(pi.z, pj.z);
+      double dr2 = dist2_rn(dx, dy, dz);
+      if (!(dr2 <= ff.rctap2)) continue;
+      int inxn = ff.inxn2[(ti.x - 1) + ff.nso * (tj.x - 1)];
+      int itb = (int)mul_rn(dr2, ff.UDRi);
+      if (inxn <= 0 || itb < 1 || itb + 1 > ff.ntable) continue;   // out of bounds in the reference
+      double drtb = mul_rn(sub_rn(dr2, mul_rn((double)itb, ff.UDR)), ff.UDRi);
+      double drtb1 = 1.0 - drtb;
+      const double4 *T = ff.TBL_nb + (size_t)(inxn - 1) * ff.ntable + (itb - 1);
+      double4 T0 = T[0], T1 = T[1];
+      double qij = pi.w * pj.w;
+      double PEvdw = drtb1 * T0.x + drtb * T1.x;
+      double CEvdw = drtb1 * T0.y + drtb * T1.y;
+      double PEclmb = (drtb1 * T0.z + drtb * T1.z) * qij;
+      double CEclmb = (drtb1 * T0.w + drtb * T1.w) * qij;
+      if (lower) { part[0] += PEvdw; part[1] += PEclmb; }
+      double cc = CEvdw + CEclmb;
+      fx -= cc * dx; fy -= cc * dy; fz -= cc * dz;
+      if (!HALF) {   // pair virial, half from each side: sum_atoms pos_a f_b of src/pot.F90:65-72 restricted to this pair
+        double h = -0.5 * cc;
+        vir[0] += h * dx * dx; vir[1] += h * dy * dy; vir[2] += h * dz * dz;
+        vir[3] += h * dy * dz; vir[4] += h * dz * dx; vir[5] += h * dx * dy;
+      }
+      if (HALF) {
+        atomicAdd(&f[j], cc * dx);
+        atomicAdd(&f[NB + j], cc * dy);
+        atomicAdd(&f[2 * NB + j], cc * dz);
+      }
+    }
+    fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
+    if (lane == 0) {
+      atomicAdd(&f[i], fx);
+      atomicAdd(&f[NB + i], fy);
+      atomicAdd(&f[2 * NB + i], fz);
+      part[2] = CECHRGE * (ff.chi[ti.x - 1] * pi.w + 0.5 * ff.eta[ti.x - 1] * pi.w * pi.w);   // src/pot.F90:708
+    }
+  }
+  block_add<3>(part, acc + ACC_PE + 11);
+  if (!HALF) block_add<6>(vir, acc + ACC_ASTR);
+}
+
+// Elnpr preparation loop, src/pot.F90:183-209 (all atoms)
+__global__ void k_elnpr_prep(int ntot, const int *__restrict__ itype, const DevFF *__restrict__ ffp,
+                             const double *__restrict__ delta, double *__restrict__ nlp, double *__restrict__ dDlp,
+                             double *__restrict__ deltalp) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ntot) return;
+  int ity = itype[i];
+  if (ity <= 0) return;
+  const DevFF &ff = *ffp;
+  int t = ity - 1;
+  double deltaE = -ff.Vale[t] + ff.Val[t] + delta[i];
+  double dEh = deltaE * 0.5;
+  int idEh = (int)dEh;
+  double u = 2.0 + deltaE - 2 * idEh;
+  double explp1 = exp(-ff.plp1[t] * (u * u));
+  dDlp[i] = 2.0 * ff.plp1[t] * explp1 * u;
+  double nl = explp1 - (double)idEh;
+  nlp[i] = nl;
+  deltalp[i] = (ff.mass[t] > 21.0) ? 0.0 : ff.nlpopt[t] - nl;
+}
+
+// C1 + C2: Ebond (src/pot.F90:926-977) and the Elnpr main loop (src/pot.F90:211-306); one thread per resident,
+// all coefficient updates land in the atom's own slots.
+__global__ void __launch_bounds__(128) k_ebond_elnpr(int natoms, const int *__restrict__ itype, const int *__restrict__ gid,
+                                                     const DevFF *__restrict__ ffp, Bonds B, const double *__restrict__ delta,
+                                                     const double *__restrict__ dDlp, const double *__restrict__ deltalp,
+                                                     double *__restrict__ acc) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double part[4] = {0.0, 0.0, 0.0, 0.0};   // PE(1..4)
+  if (i < natoms && itype[i] > 0) {
+    const DevFF &ff = *ffp;
+    const int ity = itype[i], t = ity - 1, iid = gid[i];
+    const int n = B.cnt[i];
+    double sum_ovun1 = 0.0, sum_ovun2 = 0.0;
+    for (int s = 0; s < n; s++) {
+      size_t a = (size_t)i * B.MAXN + s;
+      int j = B.lst[a];
+      int x = ff.inxn2[t + ff.nso * (itype[j] - 1)] - 1;
+      if (x < 0) continue;
+      double b0 = B.BO0[a], b1 = B.BO1[a], b2 = B.BO2[a], b3 = B.BO3[a];
+      sum_ovun1 += ff.povun1[x] * ff.Desig[x] * b0;
+      sum_ovun2 += (delta[j] - deltalp[j]) * (b2 + b3);
+      if (gid[j] < iid) {   // Ebond
+        double bp = pow(b1, ff.pbe2[x]);
+        double ex = exp(ff.pbe1[x] * (1.0 - bp));
+        part[0] += -ff.Desig[x] * b1 * ex - ff.Depi[x] * b2 - ff.Depipi[x] * b3;
+        double CEbo = -ff.Desig[x] * ex * (1.0 - ff.pbe1[x] * ff.pbe2[x] * bp);
+        B.cB0[a] += CEbo;
+        B.cB1[a] += -ff.Depi[x] - CEbo;
+        B.cB2[a] += -ff.Depipi[x] - CEbo;
+      }
+    }
+    const double dlp = deltalp[i], dl = delta[i], dD = dDlp[i];
+    double expvd2 = exp(-75.0 * dlp);
+    double dElp = ff.plp2[t] * ((1.0 + expvd2) + 75.0 * dlp * expvd2) / ((1.0 + expvd2) * (1.0 + expvd2));
+    double expovun1 = ff.povun3[t] * exp(ff.povun4[t] * sum_ovun2);
+    double deltalpcorr = dl - dlp / (1.0 + expovun1);
+    double expovun2 = exp(ff.povun2[t] * deltalpcorr);
+    double DlpV_i = 1.0 / (deltalpcorr + ff.Val[t] + 1e-8);
+    double expovun2n = 1.0 / expovun2;
+    double expovun6 = exp(ff.povun6[t] * deltalpcorr);
+    double expovun8 = ff.povun7[t] * exp(ff.povun8[t] * sum_ovun2);
+    double div1 = 1.0 / (1.0 + expovun1), div2 = 1.0 / (1.0 + expovun2), div2n = 1.0 / (1.0 + expovun2n),
+           div8 = 1.0 / (1.0 + expovun8);
+    double PElp = ff.plp2[t] * dlp / (1.0 + expvd2);
+    double PEover = sum_ovun1 * DlpV_i * deltalpcorr * div2;
+    double PEunder = -ff.povun5[t] * (1.0 - expovun6) * div2n * div8;
+    part[1] = PElp; part[2] = PEover; part[3] = PEunder;
+    double CElp1 = dElp * dD;
+    double CEover1 = deltalpcorr * DlpV_i * div2;
+    double CEover2 = sum_ovun1 * DlpV_i * div2 * (1.0 - deltalpcorr * DlpV_i - ff.povun2[t] * deltalpcorr * div2n);
+    double CEover3 = CEover2 * (1.0 - dD * div1);
+    double CEover4 = CEover2 * dlp * ff.povun4[t] * expovun1 * (div1 * div1);
+    double CEunder1 = (ff.povun5[t] * ff.povun6[t] * expovun6 * div8 + PEunder * ff.povun2[t] * expovun2n) * div2n;
+    double CEunder2 = -PEunder * ff.povun8[t] * expovun8 * div8;
+    double CEunder3 = CEunder1 * (1.0 - dD * div1);
+    double CEunder4 = CEunder1 * dlp * ff.povun4[t] * expovun1 * (div1 * div1) + CEunder2;
+    for (int s = 0; s < n; s++) {
+      size_t a = (size_t)i * B.MAXN + s;
+      int j = B.lst[a];
+      int x = ff.inxn2[t + ff.nso * (itype[j] - 1)] - 1;
+      if (x < 0) continue;
+      double bpp = B.BO2[a] + B.BO3[a];
+      double dj = delta[j] - deltalp[j], oj = 1.0 - dDlp[j];
+      double CEover5 = CEover1 * ff.povun1[x] * ff.Desig[x];
+      double CElp_b = CElp1 + CEover3 + CEover5 + CEunder3;
+      double CElp_bpp = CEover4 * dj + CEunder4 * dj;
+      B.cB0[a] += CElp_b;          // coeff = (b, b+bpp, b+bpp) -> cf = (b, bpp, bpp)
+      B.cB1[a] += CElp_bpp;
+      B.cB2[a] += CElp_bpp;
+      B.cdslot[a] += CEover4 * oj * bpp + CEunder4 * oj * bpp;   // cdbnd(j) += CElp_d
+    }
+  }
+  block_add<4>(part, acc + ACC_PE + 1);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// direction forces of an angle i-j-k (ForceA3, src/pot.F90:1462-1521): returns fij (on i) and fjk (=-force on k)
+__device__ __forceinline__ void a3_forces(double coeff, const double *da0, double n0, const double *da1, double n1,
+                                          double *fij, double *fjk) {
+  double C00 = n0 * n0, C01 = (da0[0] * da1[0] + da0[1] * da1[1]) + da0[2] * da1[2], C11 = n1 * n1;
+  double coCC = coeff * (1.0 / (n0 * n1));
+  double Ci1 = -(C01 / C00), Ck2 = C01 / C11;
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    fij[c] = coCC * (Ci1 * da0[c] + da1[c]);
+    fjk[c] = -coCC * (-da0[c] + Ck2 * da1[c]);
+  }
+}
+
+__device__ __forceinline__ void atomic_add3(double *__restrict__ f, int NB, int i, double x, double y, double z) {
+  atomicAdd(&f[i], x);
+  atomicAdd(&f[NB + i], y);
+  atomicAdd(&f[2 * NB + i], z);
+}
+
+// C3: E3b, src/pot.F90:319-557.  One warp per centre atom j; lanes take the (i1<k1) pairs.
+__global__ void __launch_bounds__(128) k_e3b(int natoms, const double *__restrict__ pos, int NB, const int *__restrict__ itype,
+                                             const DevFF *__restrict__ ffp, Bonds B, const double *__restrict__ delta,
+                                             const double *__restrict__ nlp, const double *__restrict__ dDlp,
+                                             double *__restrict__ cdbnd, double *__restrict__ f, double *__restrict__ acc) {
+  const int lane = threadIdx.x & 31;
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  double part[3] = {0.0, 0.0, 0.0};   // PE(5..7)
+  if (j < natoms && itype[j] > 0) {
+    const DevFF &ff = *ffp;
+    const int jty = itype[j], tj = jty - 1;
+    const int n = B.cnt[j];
+    const size_t row = (size_t)j * B.MAXN;
+    // per-atom sums (every lane computes them redundantly from the same <=30 values)
+    double sum_BO8 = 0.0, sum_SBO1 = 0.0;
+    for (int s = 0; s < n; s++) {
+      double b0 = B.BO0[row + s];
+      double b2 = b0 * b0, b4 = b2 * b2;
+      sum_BO8 -= b4 * b4;
+      sum_SBO1 += B.BO2[row + s] + B.BO3[row + s];
+    }
+    const double prod_SBO = exp(sum_BO8);
+    const double dj = delta[j];
+    const double delta_ang = dj + ff.Val[tj] - ff.Valangle[tj];
+    const double nlpj = nlp[j], dDlpj = dDlp[j];
+    const double xj = pos[j], yj = pos[NB + j], zj = pos[2 * NB + j];
+    double S_d = 0.0, S_6 = 0.0, S_5 = 0.0;   // sums of CE3body_d(1), CEval(6), CEval(5) over this centre's angles
+    double fjx = 0, fjy = 0, fjz = 0;
+    const int npairs = n * (n - 1) / 2;
+    for (int p = lane; p < npairs; p += 32) {
+      // unrank p -> (i1 < k1)
+      int i1 = 0, rem = p;
+      while (rem >= n - 1 - i1) { rem -= n - 1 - i1; i1++; }
+      int k1 = i1 + 1 + rem;
+      double BOij0 = B.BO0[row + i1], BOjk0 = B.BO0[row + k1];
+      double BOij = BOij0 - CUTOF2_ESUB, BOjk = BOjk0 - CUTOF2_ESUB;
+      if (!(BOij > 0.0) || !(BOjk > 0.0) || !(BOij0 * BOjk0 > CUTOF2_ESUB)) continue;
+      int i = B.lst[row + i1], k = B.lst[row + k1];
+      int ity = itype[i], kty = itype[k];
+      int inxn = ff.inxn3[(ity - 1) + ff.nso * (tj + ff.nso * (kty - 1))];
+      if (inxn == 0) continue;
+      int x = inxn - 1;
+      double rij[3] = {pos[i] - xj, pos[NB + i] - yj, pos[2 * NB + i] - zj};
+      double rjk[3] = {xj - pos[k], yj - pos[NB + k], zj - pos[2 * NB + k]};
+      double nij = sqrt((rij[0] * rij[0] + rij[1] * rij[1]) + rij[2] * rij[2]);
+      double njk = sqrt((rjk[0] * rjk[0] + rjk[1] * rjk[1]) + rjk[2] * rjk[2]);
+      double cos_ijk = -((rij[0] * rjk[0] + rij[1] * rjk[1]) + rij[2] * rjk[2]) / (nij * njk);
+      if (cos_ijk > MAXANGLE) cos_ijk = MAXANGLE;
+      if (cos_ijk < MINANGLE) cos_ijk = MINANGLE;
+      double theta_ijk = acos(cos_ijk);
+      double sin_ijk = sin(theta_ijk);
+      // --- valence angle
+      double pv1 = ff.pval1[x], pv2 = ff.pval2[x], pv3 = ff.pval3[tj], pv4 = ff.pval4[x], pv5 = ff.pval5[tj];
+      double exp3ij = exp(-pv3 * pow(BOij, pv4)), exp3jk = exp(-pv3 * pow(BOjk, pv4));
+      double fn7ij = 1.0 - exp3ij, fn7jk = 1.0 - exp3jk;
+      double exp6 = exp(ff.pval6[x] * delta_ang), exp7 = exp(-ff.pval7[x] * delta_ang);
+      double trm8 = 1.0 + exp6 + exp7;
+      double fn8j = pv5 - (pv5 - 1.0) * (2.0 + exp6) / trm8;
+      double pv8 = ff.pval8[x], pv9 = ff.pval9[x], pv10 = ff.pval10[x];
+      double SBO = sum_SBO1 + (1.0 - prod_SBO) * (-delta_ang - pv8 * nlpj);
+      double SBO2 = 0.0, CSBO2 = 0.0;
+      if (SBO > 0) { SBO2 = pow(SBO, pv9); CSBO2 = pv9 * pow(SBO, pv9 - 1.0); }
+      if (SBO > 1) { SBO2 = 2.0 - pow(2.0 - SBO, pv9); CSBO2 = pv9 * pow(2.0 - SBO, pv9 - 1.0); }
+      if (SBO > 2) { SBO2 = 2.0; CSBO2 = 0.0; }
+      double th00 = ff.theta00[x];
+      double e10 = exp(-pv10 * (2.0 - SBO2));
+      double theta0 = PI_RX - th00 * (1.0 - e10);
+      double theta_diff = theta0 - theta_ijk;
+      double exp2 = exp(-pv2 * theta_diff * theta_diff);
+      double PEval = fn7ij * fn7jk * fn8j * (pv1 - pv1 * exp2);
+      double Cf7ij = pv3 * pv4 * pow(BOij, pv4 - 1.0) * exp3ij;
+      double Cf7jk = pv3 * pv4 * pow(BOjk, pv4 - 1.0) * exp3jk;
+      double Cf8j = (1.0 - pv5) / (trm8 * trm8) *
+                    (ff.pval6[x] * exp6 * trm8 - (2.0 + exp6) * (ff.pval6[x] * exp6 - ff.pval7[x] * exp7));
+      double Ctheta0 = pv10 * th00 * e10;
+      double dSBO1 = -8.0 * prod_SBO * (delta_ang + pv8 * nlpj);
+      double dSBO2 = (prod_SBO - 1.0) * (1.0 - pv8 * dDlpj);
+      double CEval1 = Cf7ij * fn7jk * fn8j * pv1 * (1.0 - exp2);
+      double CEval2 = fn7ij * Cf7jk * fn8j * pv1 * (1.0 - exp2);
+      double CEval3 = fn7ij * fn7jk * Cf8j * pv1 * (1.0 - exp2);
+      double CEval4 = 2.0 * pv1 * pv2 * fn7ij * fn7jk * fn8j * exp2 * theta_diff;
+      double CEval5 = CEval4 * Ctheta0 * CSBO2;
+      double CEval6 = CEval5 * dSBO1;
+      double CEval7 = CEval5 * dSBO2;
+      double CEval8 = CEval4 / sin_ijk;
+      // --- penalty
+      double pp2 = ff.ppen2[x], pp3 = ff.ppen3[x], pp4 = ff.ppen4[x];
+      double exp_pen3 = exp(-pp3 * dj), exp_pen4 = exp(pp4 * dj);
+      double trm_pen34 = 1.0 + exp_pen3 + exp_pen4;
+      double fn9 = (2.0 + exp_pen3) / trm_pen34;
+      double PEpen = ff.ppen1[x] * fn9 * exp(-pp2 * (BOij - 2.0) * (BOij - 2.0)) * exp(-pp2 * (BOjk - 2.0) * (BOjk - 2.0));
+      double Cf9j = (-pp3 * exp_pen3 * trm_pen34 - (2.0 + exp_pen3) * (-pp3 * exp_pen3 + pp4 * exp_pen4)) / (trm_pen34 * trm_pen34);
+      double CEpen1 = Cf9j / fn9 * PEpen;
+      double CEpen2 = -2.0 * pp2 * (BOij - 2.0) * PEpen;
+      double CEpen3 = -2.0 * pp2 * (BOjk - 2.0) * PEpen;
+      // --- 3-body conjugation
+      double sum_BOi = delta[i] + ff.Val[ity - 1], sum_BOk = delta[k] + ff.Val[kty - 1];
+      double delta_val = dj + ff.Val[tj] - ff.Valval[tj];
+      double pc2 = ff.pcoa2[x], pc3 = ff.pcoa3[x], pc4 = ff.pcoa4[x];
+      double exp_coa2 = exp(pc2 * delta_val);
+      double ui = -BOij + sum_BOi, uk = -BOjk + sum_BOk;
+      double PEcoa = ff.pcoa1[x] / (1.0 + exp_coa2) * exp(-pc3 * (ui * ui)) * exp(-pc3 * (uk * uk)) *
+                     exp(-pc4 * ((BOij - 1.5) * (BOij - 1.5))) * exp(-pc4 * ((BOjk - 1.5) * (BOjk - 1.5)));
+      double CEcoa1 = -2.0 * pc4 * (BOij - 1.5) * PEcoa;
+      double CEcoa2 = -2.0 * pc4 * (BOjk - 1.5) * PEcoa;
+      double CEcoa3 = -pc2 * exp_coa2 / (1.0 + exp_coa2) * PEcoa;
+      double CEcoa4 = -2.0 * pc3 * ui * PEcoa;
+      double CEcoa5 = -2.0 * pc3 * uk * PEcoa;
+      part[0] += PEval; part[1] += PEpen; part[2] += PEcoa;
+      // ForceB on BO_ij and BO_jk: both bonds are slots of this centre
+      atomicAdd(&B.cB0[row + i1], CEpen2 + CEcoa1 - CEcoa4 + CEval1);
+      atomicAdd(&B.cB0[row + k1], CEpen3 + CEcoa2 - CEcoa5 + CEval2);
+      // cdbnd(i) += CE3body_d(2) ; cdbnd(k) += CE3body_d(3)   -> addressed to the partners of those slots
+      atomicAdd(&B.cdslot[row + i1], CEcoa4);
+      atomicAdd(&B.cdslot[row + k1], CEcoa5);
+      S_d += CEpen1 + CEcoa3 + CEval3 + CEval7;
+      S_6 += CEval6;
+      S_5 += CEval5;
+      double fij[3], fjk[3];
+      a3_forces(CEval8, rij, nij, rjk, njk, fij, fjk);
+      atomic_add3(f, NB, i, fij[0], fij[1], fij[2]);
+      atomic_add3(f, NB, k, -fjk[0], -fjk[1], -fjk[2]);
+      fjx += -fij[0] + fjk[0]; fjy += -fij[1] + fjk[1]; fjz += -fij[2] + fjk[2];
+    }
+    S_d = warp_sum(S_d); S_6 = warp_sum(S_6); S_5 = warp_sum(S_5);
+    fjx = warp_sum(fjx); fjy = warp_sum(fjy); fjz = warp_sum(fjz);
+    if (lane == 0 && npairs > 0) atomic_add3(f, NB, j, fjx, fjy, fjz);
+    // the reference's inner loop over ALL neighbours of j per angle (src/pot.F90:526-532), summed analytically
+    if (S_d != 0.0 || S_6 != 0.0 || S_5 != 0.0) {
+      for (int s = lane; s < n; s += 32) {
+        double b0 = B.BO0[row + s];
+        double b2 = b0 * b0, b3 = b2 * b0;
+        atomicAdd(&B.cB0[row + s], S_d + S_6 * (b3 * b3 * b0));
+        atomicAdd(&B.cB1[row + s], S_5);
+        atomicAdd(&B.cB2[row + s], S_5);
+      }
+    }
+  }
+  block_add<3>(part, acc + ACC_PE + 5);
+}
+
+// C5: Ehb, src/pot.F90:559-673.  One warp per resident i; for every donor-H bond the lanes scan i's 10 A row.
+__global__ void __launch_bounds__(128) k_ehb(int natoms, const double *__restrict__ pos, int NB, const int *__restrict__ itype,
+                                             const DevFF *__restrict__ ffp, Bonds B, const long long *__restrict__ rowptr,
+                                             const int *__restrict__ col, double *__restrict__ f, double *__restrict__ acc) {
+  const int lane = threadIdx.x & 31;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  double part[1] = {0.0};
+  if (i < natoms && itype[i] > 0) {
+    const DevFF &ff = *ffp;
+    const int ity = itype[i];
+    const int n = B.cnt[i];
+    const size_t row = (size_t)i * B.MAXN;
+    const double xi = pos[i], yi = pos[NB + i], zi = pos[2 * NB + i];
+    for (int s = 0; s < n; s++) {
+      int j = B.lst[row + s];
+      int jty = itype[j];
+      double bo = B.BO0[row + s];
+      if (!((jty == 2) && (bo > MINBO0))) continue;   // hydrogen is hard-coded as type 2
+      const double xj = pos[j], yj = pos[NB + j], zj = pos[2 * NB + j];
+      double rij[3] = {xi - xj, yi - yj, zi - zj};
+      double nij = sqrt((rij[0] * rij[0] + rij[1] * rij[1]) + rij[2] * rij[2]);
+      double cb = 0.0, fi[3] = {0, 0, 0}, fj[3] = {0, 0, 0};
+      long long rs = rowptr[i], re = rowptr[i + 1];
+      for (long long kk = rs + lane; kk < re; kk += 32) {
+        int k = col[kk];
+        int kty = itype[k];
+        int inxnhb = ff.inxn3hb[(ity - 1) + ff.nso * ((jty - 1) + ff.nso * (kty - 1))];
+        if (!((j != k) && (i != k) && (inxnhb != 0))) continue;
+        double xk = pos[k], yk = pos[NB + k], zk = pos[2 * NB + k];
+        double rik2 = dist2_rn(sub_rn(xi, xk), sub_rn(yi, yk), sub_rn(zi, zk));
+        if (!(rik2 < RCHB2)) continue;
+        int x = inxnhb - 1;
+        double rjk[3] = {xj - xk, yj - yk, zj - zk};
+        double njk = sqrt((rjk[0] * rjk[0] + rjk[1] * rjk[1]) + rjk[2] * rjk[2]);
+        double cos_ijk = -((rij[0] * rjk[0] + rij[1] * rjk[1]) + rij[2] * rjk[2]) / (nij * njk);
+        if (cos_ijk > MAXANGLE) cos_ijk = MAXANGLE;
+        if (cos_ijk < MINANGLE) cos_ijk = MINANGLE;
+        double theta_ijk = acos(cos_ijk);
+        double sh = sin(0.5 * theta_ijk);
+        double s2 = sh * sh;
+        double sin_xhz4 = s2 * s2;
+        double cos_xhz1 = 1.0 - cos_ijk;
+        double r0 = ff.r0hb[x], p1 = ff.phb1[x], p2 = ff.phb2[x], p3 = ff.phb3[x];
+        double exp_hb2 = exp(-p2 * bo);
+        double exp_hb3 = exp(-p3 * (r0 / njk + njk / r0 - 2.0));
+        double PEhb = p1 * (1.0 - exp_hb2) * exp_hb3 * sin_xhz4;
+        part[0] += PEhb;
+        cb += p1 * p2 * exp_hb2 * exp_hb3 * sin_xhz4;
+        double CEhb2 = -0.5 * p1 * (1.0 - exp_hb2) * exp_hb3 * cos_xhz1;
+        double CEhb3 = -PEhb * p3 * (-r0 / (njk * njk) + 1.0 / r0) * (1.0 / njk);
+        double fij[3], fjk[3];
+        a3_forces(CEhb2, rij, nij, rjk, njk, fij, fjk);
+        double ff3[3] = {CEhb3 * rjk[0], CEhb3 * rjk[1], CEhb3 * rjk[2]};
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          fi[c] += fij[c];
+          fj[c] += -fij[c] + fjk[c] - ff3[c];
+        }
+        atomic_add3(f, NB, k, -fjk[0] + ff3[0], -fjk[1] + ff3[1], -fjk[2] + ff3[2]);
+      }
+      cb = warp_sum(cb);
+#pragma unroll
+      for (int c = 0; c < 3; c++) { fi[c] = warp_sum(fi[c]); fj[c] = warp_sum(fj[c]); }
+      if (lane == 0) {
+        if (cb != 0.0) atomicAdd(&B.cB0[row + s], cb);   // ForceB(i,j1,...,CEhb(1))
+        atomic_add3(f, NB, i, fi[0], fi[1], fi[2]);
+        atomic_add3(f, NB, j, fj[0], fj[1], fj[2]);
+      }
+    }
+  }
+  block_add<1>(part, acc + ACC_PE + 10);
+}
+
+// normalised cross product with the reference's floor on the norm (cross_product, src/pot.F90:1524-1543)
+__device__ __forceinline__ double cross_n(const double *a, double na, const double *b, double nb, double *c) {
+  double a0 = a[0] / na, a1 = a[1] / na, a2 = a[2] / na;
+  double b0 = b[0] / nb, b1 = b[1] / nb, b2 = b[2] / nb;
+  c[0] = a1 * b2 - a2 * b1;
+  c[1] = a2 * b0 - a0 * b2;
+  c[2] = a0 * b1 - a1 * b0;
+  double n = sqrt((c[0] * c[0] + c[1] * c[1]) + c[2] * c[2]);
+  return n < NSMALL ? NSMALL : n;
+}
+
+// C4: E4b, src/pot.F90:980-1227.  One warp per atom j; central bonds j-k1 in sequence; lanes take the (i1,l1) pairs.
+__global__ void __launch_bounds__(128) k_e4b(int natoms, const double *__restrict__ pos, int NB, const int *__restrict__ itype,
+                                             const int *__restrict__ gid, const DevFF *__restrict__ ffp, Bonds B,
+                                             const double *__restrict__ delta, double *__restrict__ cdbnd,
+                                             double *__restrict__ f, double *__restrict__ acc) {
+  const int lane = threadIdx.x & 31;
+  const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  double part[2] = {0.0, 0.0};   // PE(8..9)
+  if (j < natoms && itype[j] > 0) {
+    const DevFF &ff = *ffp;
+    const int jty = itype[j], jid = gid[j];
+    const int nj = B.cnt[j];
+    const size_t rowj = (size_t)j * B.MAXN;
+    const double delta_ang_j = delta[j] + ff.Val[jty - 1] - ff.Valangle[jty - 1];
+    const double xj = pos[j], yj = pos[NB + j], zj = pos[2 * NB + j];
+    double fj[3] = {0, 0, 0}, cdj = 0.0;
+    for (int k1 = 0; k1 < nj; k1++) {
+      double BOjk0 = B.BO0[rowj + k1];
+      if (!(BOjk0 > CUTOF2_ESUB)) continue;
+      int k = B.lst[rowj + k1];
+      if (!(jid < gid[k])) continue;
+      double BOjk = BOjk0 - CUTOF2_ESUB;
+      int kty = itype[k];
+      const int nk = B.cnt[k];
+      const size_t rowk = (size_t)k * B.MAXN;
+      double delta_ang_jk = delta_ang_j + (delta[k] + ff.Val[kty - 1] - ff.Valangle[kty - 1]);
+      const double xk = pos[k], yk = pos[NB + k], zk = pos[2 * NB + k];
+      double rjk[3] = {xj - xk, yj - yk, zj - zk};
+      double njk = sqrt((rjk[0] * rjk[0] + rjk[1] * rjk[1]) + rjk[2] * rjk[2]);
+      double BOpi_jk = B.BO2[rowj + k1];
+      double fk[3] = {0, 0, 0}, cdk = 0.0, cjk0 = 0.0, cjk1 = 0.0;
+      const int ncomb = nj * nk;
+      for (int p = lane; p < ncomb; p += 32) {
+        int i1 = p / nk, l1 = p - i1 * nk;
+        double BOij0 = B.BO0[rowj + i1];
+        if (!((BOij0 > CUTOF2_ESUB) && ((BOij0 * BOjk0) > CUTOF2_ESUB))) continue;
+        int i = B.lst[rowj + i1];
+        if (i == k) continue;
+        double BOkl0 = B.BO0[rowk + l1];
+        if (!((BOkl0 > CUTOF2_ESUB) && (BOjk0 * BOkl0 > CUTOF2_ESUB))) continue;
+        int l = B.lst[rowk + l1];
+        int ity = itype[i], lty = itype[l];
+        int inxn = ff.inxn4[(ity - 1) + ff.nso * ((jty - 1) + ff.nso * ((kty - 1) + ff.nso * (lty - 1)))];
+        if (!((inxn != 0) && (i != l) && (j != l))) continue;
+        if (!((BOij0 * (BOjk0 * BOjk0) * BOkl0) > MINBO0)) continue;
+        int x = inxn - 1;
+        double BOij = BOij0 - CUTOF2_ESUB, BOkl = BOkl0 - CUTOF2_ESUB;
+        double rij[3] = {pos[i] - xj, pos[NB + i] - yj, pos[2 * NB + i] - zj};
+        double nij = sqrt((rij[0] * rij[0] + rij[1] * rij[1]) + rij[2] * rij[2]);
+        double cos_ijk = -((rij[0] * rjk[0] + rij[1] * rjk[1]) + rij[2] * rjk[2]) / (nij * njk);
+        if (cos_ijk > MAXANGLE) cos_ijk = MAXANGLE;
+        if (cos_ijk < MINANGLE) cos_ijk = MINANGLE;
+        double theta_ijk = acos(cos_ijk);
+        double sin_ijk = sin(theta_ijk);
+        double tan_ijk_i = 1.0 / tan(theta_ijk);
+        double crs_ijk[3];
+        double ncr1 = cross_n(rij, nij, rjk, njk, crs_ijk);
+        double rkl[3] = {xk - pos[l], yk - pos[NB + l], zk - pos[2 * NB + l]};
+        double nkl = sqrt((rkl[0] * rkl[0] + rkl[1] * rkl[1]) + rkl[2] * rkl[2]);
+        double pt1 = ff.ptor1[x], pt2 = ff.ptor2[x], pt3 = ff.ptor3[x], pt4 = ff.ptor4[x];
+        double V1 = ff.V1[x], V2 = ff.V2[x], V3 = ff.V3[x], pc1 = ff.pcot1[x], pc2 = ff.pcot2[x];
+        double et1 = exp(-pt2 * BOij), et2 = exp(-pt2 * BOjk), et3 = exp(-pt2 * BOkl);
+        double exp_tor3 = exp(-pt3 * delta_ang_jk), exp_tor4 = exp(pt4 * delta_ang_jk);
+        double exp_tor34_i = 1.0 / (1.0 + exp_tor3 + exp_tor4);
+        double fn10 = (1.0 - et1) * (1.0 - et2) * (1.0 - et3);
+        double fn11 = (2.0 + exp_tor3) * exp_tor34_i;
+        double fn12 = exp(-pc2 * ((BOij - 1.5) * (BOij - 1.5) + (BOjk - 1.5) * (BOjk - 1.5) + (BOkl - 1.5) * (BOkl - 1.5)));
+        double btb2 = 2.0 - BOpi_jk - fn11;
+        double exp_tor1 = exp(pt1 * (btb2 * btb2));
+        double cos_jkl = -((rjk[0] * rkl[0] + rjk[1] * rkl[1]) + rjk[2] * rkl[2]) / (njk * nkl);
+        if (cos_jkl > MAXANGLE) cos_jkl = MAXANGLE;
+        if (cos_jkl < MINANGLE) cos_jkl = MINANGLE;
+        double theta_jkl = acos(cos_jkl);
+        double sin_jkl = sin(theta_jkl);
+        double tan_jkl_i = 1.0 / tan(theta_jkl);
+        double crs_jkl[3];
+        double ncr2 = cross_n(rjk, njk, rkl, nkl, crs_jkl);
+        double cw = ((crs_ijk[0] * crs_jkl[0] + crs_ijk[1] * crs_jkl[1]) + crs_ijk[2] * crs_jkl[2]) / (ncr1 * ncr2);
+        if (cw > MAXANGLE) cw = MAXANGLE;
+        if (cw < MINANGLE) cw = MINANGLE;
+        double omega = acos(cw);
+        double cw_sqr = cw * cw;
+        double cos_2w = cos(2.0 * omega);
+        double c2 = 1.0 - cos_2w;
+        double c3 = 1.0 + cos(3.0 * omega);
+        double Vsum = V1 * (1.0 + cw) + V2 * exp_tor1 * c2 + V3 * c3;
+        double PEtors = 0.5 * fn10 * sin_ijk * sin_jkl * Vsum;
+        double PEconj = pc1 * fn12 * (1.0 + (cw_sqr - 1.0) * sin_ijk * sin_jkl);
+        part[0] += PEtors; part[1] += PEconj;
+        double CEtors1 = 0.5 * sin_ijk * sin_jkl * Vsum;
+        double CEtors2 = -pt1 * fn10 * sin_ijk * sin_jkl * V2 * exp_tor1 * btb2 * c2;
+        double dfn11 = (-pt3 * exp_tor3 + (pt3 * exp_tor3 - pt4 * exp_tor4) * (2.0 + exp_tor3) * exp_tor34_i) * exp_tor34_i;
+        double CEtors3 = CEtors2 * dfn11;
+        double CEtors4 = CEtors1 * pt2 * et1 * (1.0 - et2) * (1.0 - et3);
+        double CEtors5 = CEtors1 * pt2 * (1.0 - et1) * et2 * (1.0 - et3);
+        double CEtors6 = CEtors1 * pt2 * (1.0 - et1) * (1.0 - et2) * et3;
+        double cmn = -0.5 * fn10 * Vsum;
+        double CEtors7 = cmn * sin_jkl * tan_ijk_i;
+        double CEtors8 = cmn * sin_ijk * tan_jkl_i;
+        double CEtors9 = fn10 * sin_ijk * sin_jkl * (0.5 * V1 - 2.0 * V2 * exp_tor1 * cw + 1.5 * V3 * (cos_2w + 2.0 * cw_sqr));
+        double Cconj = -2.0 * pc2 * PEconj;
+        double CEconj4 = -pc1 * fn12 * (cw_sqr - 1.0) * tan_ijk_i * sin_jkl;
+        double CEconj5 = -pc1 * fn12 * (cw_sqr - 1.0) * sin_ijk * tan_jkl_i;
+        double CEconj6 = 2.0 * pc1 * fn12 * cw * sin_ijk * sin_jkl;
+        double Cb_ij = Cconj * (BOij - 1.5) + CEtors4;
+        double Cb_jk = Cconj * (BOjk - 1.5) + CEtors5;
+        double Cb_kl = Cconj * (BOkl - 1.5) + CEtors6;
+        double Ca_ijk = CEconj4 + CEtors7, Ca_jkl = CEconj5 + CEtors8, Ca_ijkl = CEconj6 + CEtors9;
+        cdj += CEtors3;
+        cdk += CEtors3;
+        atomicAdd(&B.cB0[rowj + i1], Cb_ij);   // ForceB on BO_ij (slot of j)
+        cjk0 += Cb_jk;                         // ForceBbo on BO_jk: coeff (b, b+t2, b) -> cf (b, t2, 0)
+        cjk1 += CEtors2;
+        atomicAdd(&B.cB0[rowk + l1], Cb_kl);   // ForceB on BO_kl (slot of k)
+        // --- direction forces: ForceA3(i,j,k), ForceA3(j,k,l), ForceA4(i,j,k,l)  (src/pot.F90:1369-1521)
+        double f1[3], f2[3], g1[3], g2[3];
+        a3_forces(Ca_ijk, rij, nij, rjk, njk, f1, f2);
+        a3_forces(Ca_jkl, rjk, njk, rkl, nkl, g1, g2);
+        double C00 = nij * nij, C01 = (rij[0] * rjk[0] + rij[1] * rjk[1]) + rij[2] * rjk[2],
+               C02 = (rij[0] * rkl[0] + rij[1] * rkl[1]) + rij[2] * rkl[2];
+        double C11 = njk * njk, C12 = (rjk[0] * rkl[0] + rjk[1] * rkl[1]) + rjk[2] * rkl[2], C22 = nkl * nkl;
+        double D0 = C00 * C11 - C01 * C01, D1 = C11 * C22 - C12 * C12;
+        double coDD = Ca_ijkl * (1.0 / sqrt(D0 * D1));
+        double com = C01 * C12 - C02 * C11;
+        double Cwi0 = C11 / D0 * com, Cwi1 = -(C12 + C01 / D0 * com), Cwi2 = C11;
+        double Cwj0 = -(C12 + (C11 + C01) / D0 * com);
+        double Cwj1 = -(-C12 - 2 * C02 - C22 / D1 * com - (C00 + C01) / D0 * com);
+        double Cwj2 = -(C01 + C11 + C12 / D1 * com);
+        double Cwl0 = -C11, Cwl1 = (C01 + C12 / D1 * com), Cwl2 = -(C11 / D1 * com);
+        double Fi[3], Fl[3];
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+          double hij = coDD * (Cwi0 * rij[c] + Cwi1 * rjk[c] + Cwi2 * rkl[c]);
+          double hjk = coDD * ((Cwj0 + Cwi0) * rij[c] + (Cwj1 + Cwi1) * rjk[c] + (Cwj2 + Cwi2) * rkl[c]);
+          double hkl = -coDD * (Cwl0 * rij[c] + Cwl1 * rjk[c] + Cwl2 * rkl[c]);
+          Fi[c] = f1[c] + hij;
+          fj[c] += (-f1[c] + f2[c]) + g1[c] + (-hij + hjk);
+          fk[c] += -f2[c] + (-g1[c] + g2[c]) + (-hjk + hkl);
+          Fl[c] = -g2[c] - hkl;
+        }
+        atomic_add3(f, NB, i, Fi[0], Fi[1], Fi[2]);
+        atomic_add3(f, NB, l, Fl[0], Fl[1], Fl[2]);
+      }
+      cdk = warp_sum(cdk); cjk0 = warp_sum(cjk0); cjk1 = warp_sum(cjk1);
+#pragma unroll
+      for (int c = 0; c < 3; c++) fk[c] = warp_sum(fk[c]);
+      if (lane == 0 && (cdk != 0.0 || cjk0 != 0.0 || fk[0] != 0.0 || fk[1] != 0.0 || fk[2] != 0.0)) {
+        atomicAdd(&cdbnd[k], cdk);
+        atomicAdd(&B.cB0[rowj + k1], cjk0);
+        atomicAdd(&B.cB1[rowj + k1], cjk1);
+        atomic_add3(f, NB, k, fk[0], fk[1], fk[2]);
+      }
+    }
+    cdj = warp_sum(cdj);
+#pragma unroll
+    for (int c = 0; c < 3; c++) fj[c] = warp_sum(fj[c]);
+    if (lane == 0 && (cdj != 0.0 || fj[0] != 0.0 || fj[1] != 0.0 || fj[2] != 0.0)) {
+      atomicAdd(&cdbnd[j], cdj);
+      atomic_add3(f, NB, j, fj[0], fj[1], fj[2]);
+    }
+  }
+  block_add<2>(part, acc + ACC_PE + 8);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// C7: ForceBondedTerms (src/pot.F90:113-144) + ForceD/ForceB/ForceBbo (src/pot.F90:1230-1365) as gathers.
+// pass 0: cdbnd(i) total = own accumulator + what neighbours addressed to i through their slots
+__global__ void k_final0(int ntot, Bonds B, double *__restrict__ cdbnd) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ntot) return;
+  double s = cdbnd[i];
+  const int n = B.cnt[i];
+  for (int k = 0; k < n; k++) {
+    size_t a = (size_t)i * B.MAXN + k;
+    int j = B.lst[a];
+    s += B.cdslot[(size_t)j * B.MAXN + B.idx[a]];
+  }
+  cdbnd[i] = s;
+}
+// pass 1: bond forces on atom i from every one of its bonds, and ccbnd(i) with the reference's order predicate
+__global__ void __launch_bounds__(128) k_final1(int ntot, const double *__restrict__ pos, int NB, Bonds B,
+                                                const double *__restrict__ cdbnd, double *__restrict__ ccbnd,
+                                                double *__restrict__ f) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ntot) return;
+  const int n = B.cnt[i];
+  if (n == 0) { ccbnd[i] = 0.0; return; }
+  const double xi = pos[i], yi = pos[NB + i], zi = pos[2 * NB + i];
+  const double cdi = cdbnd[i];
+  double fx = 0, fy = 0, fz = 0, cc = 0.0;
+  for (int k = 0; k < n; k++) {
+    size_t a = (size_t)i * B.MAXN + k;
+    int j = B.lst[a];
+    size_t b = (size_t)j * B.MAXN + B.idx[a];
+    double cdj = cdbnd[j];
+    double c1e = B.cB0[a] + B.cB0[b];                  // energy-term coefficients of both orientations
+    double c2 = B.cB1[a] + B.cB1[b], c3 = B.cB2[a] + B.cB2[b];
+    double c1 = c1e + cdi + cdj;                       // + ForceD(i) and ForceD(j) (src/pot.F90:1243-1245)
+    double b0 = B.BO0[a], b2 = B.BO2[a], b3 = B.BO3[a], A1 = B.A1[a], db = B.dBOp[a];
+    double Cb = c1 * (B.A0[a] + b0 * A1) * db + c2 * b2 * (B.dln2[a] + A1 * db) + c3 * b3 * (B.dln3[a] + A1 * db);
+    double dx = xi - pos[j], dy = yi - pos[NB + j], dz = zi - pos[2 * NB + j];
+    fx -= Cb * dx; fy -= Cb * dy; fz -= Cb * dz;
+    double A2 = B.A2[a];
+    cc += c1e * b0 * A2 + (c2 * b2 + c3 * b3) * B.A3[a];
+    cc += cdi * b0 * A2;                               // ForceD(i): Cbond(2), always consumed
+    if (j < i) cc += cdj * b0 * A2;                    // ForceD(j): Cbond(3), consumed only if it ran before i (Q1)
+  }
+  ccbnd[i] = cc;
+  atomic_add3(f, NB, i, fx, fy, fz);
+}
+// pass 2: f(i) -= sum_j (ccbnd(i)+ccbnd(j)) dBOp (ri-rj)     (src/pot.F90:129-135 seen from both ends of a bond)
+__global__ void __launch_bounds__(128) k_final2(int ntot, const double *__restrict__ pos, int NB, Bonds B,
+                                                const double *__restrict__ ccbnd, double *__restrict__ f) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= ntot) return;
+  const int n = B.cnt[i];
+  if (n == 0) return;
+  const double xi = pos[i], yi = pos[NB + i], zi = pos[2 * NB + i];
+  const double cci = ccbnd[i];
+  double fx = 0, fy = 0, fz = 0;
+  for (int k = 0; k < n; k++) {
+    size_t a = (size_t)i * B.MAXN + k;
+    int j = B.lst[a];
+    double w = (cci + ccbnd[j]) * B.dBOp[a];
+    fx -= w * (xi - pos[j]); fy -= w * (yi - pos[NB + j]); fz -= w * (zi - pos[2 * NB + j]);
+  }
+  f[i] += fx; f[NB + i] += fy; f[2 * NB + i] += fz;
+}
+
+// virial accumulation over residents and ghosts before the copy-back, src/pot.F90:65-72
+__global__ void __launch_bounds__(256) k_virial(int ntot, const double *__restrict__ pos, const double *__restrict__ f, int NB,
+                                                double *__restrict__ acc) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double part[6] = {0, 0, 0, 0, 0, 0};
+  if (i < ntot) {
+    double x = pos[i], y = pos[NB + i], z = pos[2 * NB + i], fx = f[i], fy = f[NB + i], fz = f[2 * NB + i];
+    part[0] = x * fx; part[1] = y * fy; part[2] = z * fz; part[3] = y * fz; part[4] = z * fx; part[5] = x * fy;
+  }
+  block_add<6>(part, acc + ACC_ASTR);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// integrator halves of the main loop, src/main.F90:64-72 and :86-98 (vkick :192-207)
+__global__ void k_md_first_half(int n, int NB, double dt, double Lex_w2, const int *__restrict__ itype,
+                                const DevFF *__restrict__ ffp, double *__restrict__ pos, double *__restrict__ v,
+                                const double *__restrict__ f, const double *__restrict__ q, double *__restrict__ qsfp,
+                                double *__restrict__ qsfv) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double dthm = dt * 0.5 / ffp->mass[itype[i] - 1];
+  double sv = qsfv[i] + 0.5 * dt * Lex_w2 * (q[i] - qsfp[i]);
+  qsfv[i] = sv;
+  qsfp[i] = qsfp[i] + dt * sv;
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    double vv = add_rn(v[(size_t)c * NB + i], mul_rn(mul_rn(1.0, dthm), f[(size_t)c * NB + i]));
+    v[(size_t)c * NB + i] = vv;
+    pos[(size_t)c * NB + i] = add_rn(pos[(size_t)c * NB + i], mul_rn(dt, vv));
+  }
+}
+__global__ void __launch_bounds__(256) k_md_second_half(int n, int NB, double dt, double Lex_w2, const int *__restrict__ itype,
+                                                        const DevFF *__restrict__ ffp, double *__restrict__ v,
+                                                        const double *__restrict__ f, const double *__restrict__ q,
+                                                        const double *__restrict__ qsfp, double *__restrict__ qsfv,
+                                                        double *__restrict__ acc) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double part[6] = {0, 0, 0, 0, 0, 0};
+  if (i < n) {
+    double m = ffp->mass[itype[i] - 1];
+    double dthm = dt * 0.5 / m;
+    double vx = v[i], vy = v[NB + i], vz = v[2 * NB + i];
+    part[0] = vx * vx * m; part[1] = vy * vy * m; part[2] = vz * vz * m;
+    part[3] = vy * vz * m; part[4] = vz * vx * m; part[5] = vx * vy * m;
+    v[i] = add_rn(vx, mul_rn(dthm, f[i]));
+    v[NB + i] = add_rn(vy, mul_rn(dthm, f[NB + i]));
+    v[2 * NB + i] = add_rn(vz, mul_rn(dthm, f[2 * NB + i]));
+    qsfv[i] = qsfv[i] + 0.5 * dt * Lex_w2 * (q[i] - qsfp[i]);
+  }
+  block_add<6>(part, acc);
+}
+// KE = sum hmas*v^2 and sum q (PRINTE, src/main.F90:225-230)
+__global__ void __launch_bounds__(256) k_observe(int n, int NB, const int *__restrict__ itype, const DevFF *__restrict__ ffp,
+                                                 const double *__restrict__ v, const double *__restrict__ q,
+                                                 double *__restrict__ acc) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double part[2] = {0, 0};
+  if (i < n) {
+    double hm = 0.5 * ffp->mass[itype[i] - 1];
+    double vx = v[i], vy = v[NB + i], vz = v[2 * NB + i];
+    part[0] = hm * ((vx * vx + vy * vy) + vz * vz);
+    part[1] = q[i];
+  }
+  block_add<2>(part, acc);
+}
+
+// ---------------------------------------------------------------------------------------------------
+inline Bonds make_bonds(Ctx *c) {
+  Bonds B;
+  B.MAXN = c->MAXN; B.cnt = c->nbrcnt; B.lst = c->nbrlist; B.idx = c->nbrindx;
+  B.BO0 = c->BO[0]; B.BO1 = c->BO[1]; B.BO2 = c->BO[2]; B.BO3 = c->BO[3];
+  B.dln1 = c->dln[0]; B.dln2 = c->dln[1]; B.dln3 = c->dln[2]; B.dBOp = c->dBOp;
+  B.A0 = c->A0; B.A1 = c->A1; B.A2 = c->A2; B.A3 = c->A3;
+  B.cB0 = c->cB[0]; B.cB1 = c->cB[1]; B.cB2 = c->cB[2]; B.cdslot = c->cdslot;
+  return B;
+}
+
+// subroutine FORCE on device-resident state, reference src/pot.F90:2-90
+inline int force_device(Ctx *c) {
+  const int NB = c->NB, n = c->natoms;
+  RXG_CUDA(cudaMemsetAsync(c->f, 0, sizeof(double) * 3 * NB, c->st));
+  RXG_CUDA(cudaMemsetAsync(c->d_acc + ACC_PE, 0, sizeof(double) * 24, c->st));
+  double dr[3];
+  for (int a = 0; a < 3; a++) dr[a] = c->cfg.nmincell * c->box.lcsize[a];
+  RXG_TRY(halo_copy(c, dr));                                    // src/pot.F90:28
+  const int nt = c->cp[6];
+  LAUNCH(c, k_types, cdiv(nt, 256), 256, 0, c->atype, nt, c->itype, c->gid);
+  RXG_TRY(bin_grid(c, c->gb));                                  // :30
+  RXG_TRY(bin_grid(c, c->gnb));                                 // :31
+  RXG_TRY(build_nbrlist(c));                                    // :33
+  RXG_TRY(build_pairlist<false>(c));                            // :34
+  Bonds B = make_bonds(c);
+  LAUNCH(c, k_boprim, cdiv(nt, 128), 128, 0, nt, c->pos, NB, c->itype, c->d_ff, B, c->deltap1, c->deltap2, c->cdbnd, c->ccbnd);
+  LAUNCH(c, k_bofull, cdiv(nt, 128), 128, 0, nt, c->itype, c->d_ff, B, c->deltap1, c->deltap2, c->delta);
+  // ---- energy terms (src/pot.F90:49-57)
+  double4 *pq = (double4 *)c->tmp;                 // scratch: {x,y,z,q} and {itype,gid}
+  int2 *tg = (int2 *)(c->tmp + 4 * (size_t)NB);
+  LAUNCH(c, k_pack_pq, cdiv(nt, 256), 256, 0, nt, c->pos, NB, c->q, c->itype, c->gid, pq, tg);
+  // the full-row form needs every partner's image inside this rank's halo: true when the FORCE halo >= rctap
+  bool full_ok = true;
+  const double lat[3] = {c->box.lata, c->box.latb, c->box.latc};
+  for (int a = 0; a < 3; a++)
+    if (dr[a] * lat[a] < c->ff.rctap) full_ok = false;
+  const int wgrid = cdiv((long long)n * 32, 256);
+  if (!full_ok) LAUNCH(c, (k_enbond<true>), wgrid, 256, 0, n, c->rowptr, c->col, pq, tg, c->d_ff, c->f, NB, c->d_acc);
+  LAUNCH(c, k_elnpr_prep, cdiv(nt, 256), 256, 0, nt, c->itype, c->d_ff, c->delta, c->nlp, c->dDlp, c->deltalp);
+  LAUNCH(c, k_ebond_elnpr, cdiv(n, 128), 128, 0, n, c->itype, c->gid, c->d_ff, B, c->delta, c->dDlp, c->deltalp, c->d_acc);
+  const int wgrid128 = cdiv((long long)n * 32, 128);
+  LAUNCH(c, k_ehb, wgrid128, 128, 0, n, c->pos, NB, c->itype, c->d_ff, B, c->rowptr, c->col, c->f, c->d_acc);
+  LAUNCH(c, k_e3b, wgrid128, 128, 0, n, c->pos, NB, c->itype, c->d_ff, B, c->delta, c->nlp, c->dDlp, c->cdbnd, c->f, c->d_acc);
+  LAUNCH(c, k_e4b, wgrid128, 128, 0, n, c->pos, NB, c->itype, c->gid, c->d_ff, B, c->delta, c->cdbnd, c->f, c->d_acc);
+  // ---- ForceBondedTerms (src/pot.F90:63)
+  LAUNCH(c, k_final0, cdiv(nt, 128), 128, 0, nt, B, c->cdbnd);
+  LAUNCH(c, k_final1, cdiv(nt, 128), 128, 0, nt, c->pos, NB, B, c->cdbnd, c->ccbnd, c->f);
+  LAUNCH(c, k_final2, cdiv(nt, 128), 128, 0, nt, c->pos, NB, B, c->ccbnd, c->f);
+  LAUNCH(c, k_virial, cdiv(nt, 256), 256, 0, nt, c->pos, c->f, NB, c->d_acc);   // :65-72
+  // full-row ENbond puts both halves of a pair force on residents, so its virial is taken per pair inside the kernel
+  if (full_ok) LAUNCH(c, (k_enbond<false>), wgrid, 256, 0, n, c->rowptr, c->col, pq, tg, c->d_ff, c->f, NB, c->d_acc);
+  RXG_TRY(halo_cpbk(c));                                                          // :74
+  RXG_CUDA(cudaMemcpyAsync(c->h_acc + ACC_PE, c->d_acc + ACC_PE, sizeof(double) * 24, cudaMemcpyDeviceToHost, c->st));
+  RXG_CUDA(cudaStreamSynchronize(c->st));
+  c->PE[0] = 0.0;
+  for (int k = 1; k < 14; k++) c->PE[k] = c->h_acc[ACC_PE + k];
+  for (int k = 0; k < 6; k++) c->astr[k] = c->h_acc[ACC_ASTR + k];
+  return RXG_OK;
+}
+
+}   // namespace rxg

@@ -1,0 +1,144 @@
+// rxg_common.cuh -- shared declarations of the B200 hot-path library (device context, helpers).
+#pragma once
+#include <cuda_runtime.h>
+#include <cstdint>
+#include <cstdio>
+#include <string>
+#include <vector>
+#include "../../include/rxmd_b200.h"
+
+#define RXG_MAXLAYERS 5       // reference src/module.F90:44
+#define RXG_MAXLAYERS_NB 10   // reference src/module.F90:45
+
+namespace rxg {
+
+// ---- round-to-nearest fp64 arithmetic that ptxas may not contract into FMA.  Used wherever a result
+// feeds a comparison or an index (cell ids, cut-off tests, table weights) so that it is bit-identical to
+// an x86-64 build of the reference without FMA (hard part 3).
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double add_rn(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
+// gfortran sum(a(1:3)*b(1:3)) == ((a1*b1 + a2*b2) + a3*b3)
+__device__ __forceinline__ double dot3_rn(double a0, double a1, double a2, double b0, double b1, double b2) {
+  return add_rn(add_rn(mul_rn(a0, b0), mul_rn(a1, b1)), mul_rn(a2, b2));
+}
+__device__ __forceinline__ double dist2_rn(double dx, double dy, double dz) {
+  return add_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)), mul_rn(dz, dz));
+}
+__device__ __forceinline__ int nint_d(double x) { return (int)llround(x); }
+
+// Force-field tables resident in HBM (device pointers); filled by rxg_set_forcefield from rxg_ff.
+// Indexing is 0-based here: type t = ity-1, bond type x = inxn-1; inxn* tables keep 1-based VALUES (0 = none).
+struct DevFF {
+  int nso, nboty, nvaty, ntoty, nhbty, ntable;
+  double vpar1, vpar2, cutoff_vpar30, rctap, rctap2, UDR, UDRi;
+  const double *Val, *Valval, *Valangle, *Vale, *mass, *plp1, *plp2, *nlpopt;
+  const double *povun2, *povun3, *povun4, *povun5, *povun6, *povun7, *povun8, *pval3, *pval5, *chi, *eta;
+  const double *cBOp1, *cBOp3, *cBOp5, *pbo2h, *pbo4h, *pbo6h, *pbo2, *pbo4, *pbo6, *swtch;
+  const double *rc2, *pboc1, *pboc3, *pboc4, *pboc5, *ovc, *v13cor, *Desig, *Depi, *Depipi, *pbe1, *pbe2, *povun1;
+  const double *theta00, *pval1, *pval2, *pval4, *pval6, *pval7, *pval8, *pval9, *pval10;
+  const double *ppen1, *ppen2, *ppen3, *ppen4, *pcoa1, *pcoa2, *pcoa3, *pcoa4;
+  const double *ptor1, *ptor2, *ptor3, *ptor4, *V1, *V2, *V3, *pcot1, *pcot2;
+  const double *phb1, *phb2, *phb3, *r0hb;
+  const int *inxn2, *inxn3, *inxn3hb, *inxn4;
+  const double *TBL_Eclmb_QEq;   // (NTABLE, nboty) column-major, as given
+  const double4 *TBL_nb;         // [(inxn-1)*NTABLE + (itb-1)] = {Evdw, CEvdw, Eclmb, CEclmb}: one 32-byte sector per node
+};
+
+// One linked-cell grid (replaces header/llist/nacell, reference src/main.F90:277-318) as a counting sort.
+struct DevGrid {
+  int nc[3], L, dim[3];
+  int ncell;            // dim[0]*dim[1]*dim[2], z fastest
+  double cs[3];         // normalised cell size
+  int *cell_of;         // [NB] linear cell id of each atom (-1: atype==0, skipped like the reference)
+  int *start;           // [ncell+1] exclusive prefix of the per-cell counts
+  int *fill;            // [ncell] scratch
+  int *order;           // [NB] atom indices sorted by cell; inside a cell DESCENDING index (= the reference's
+                        //      head-insertion order, so rows come out in the reference's own order)
+  double4 *sorted;      // [NB] {x,y,z, bits(index | type<<32)} in `order` order
+};
+
+struct Ctx {
+  rxg_config cfg;
+  rxg_box box;
+  bool have_ff = false, have_box = false;
+  int dev = 0;
+  cudaStream_t st = nullptr;
+  std::string err;
+  long long launches = 0;
+  // ---- per-atom arrays, capacity NB ------------------------------------------------------------------
+  int NB = 0, MAXN = 0;
+  int natoms = 0;
+  int cp[7] = {0, 0, 0, 0, 0, 0, 0};   // copyptr(0:6), reference src/module.F90:234
+  double *pos = nullptr, *v = nullptr, *f = nullptr;            // [3*NB], x|y|z planes
+  double *atype = nullptr, *q = nullptr, *qsfp = nullptr, *qsfv = nullptr;
+  double2 *qst = nullptr;   // {qs, qt}      (reference qs(:), qt(:))
+  double4 *hsq = nullptr;   // {hs, ht, q, -} gather pack of get_hsh; .z mirrors q for residents+ghosts
+  double2 *gst = nullptr;   // {gs, gt}
+  int *itype = nullptr, *gid = nullptr, *frcindx = nullptr;
+  double *tmp = nullptr;    // [12*NB] scratch for MOVE compaction
+  // ---- cells -------------------------------------------------------------------------------------------
+  DevGrid gb, gnb;
+  int *d_runs = nullptr;    // stencil runs {dx,dy,dzlo,dzhi}
+  int nruns = 0;
+  // ---- lists -------------------------------------------------------------------------------------------
+  int *nbrcnt = nullptr, *nbrlist = nullptr, *nbrindx = nullptr;   // [NB], [NB*MAXN], [NB*MAXN]
+  long long *rowptr = nullptr;   // [NB+1] 10 A list, CSR over residents
+  int *rowcnt = nullptr;
+  int *col = nullptr;            // [nnz_cap]
+  double *val = nullptr;         // [nnz_cap] hessian (QEq list only)
+  long long nnz_cap = 0, nnz = 0;
+  bool list_is_qeq = false;
+  // ---- bond-order products, [NB*MAXN] unless noted -----------------------------------------------------------
+  double *BO[4] = {nullptr, nullptr, nullptr, nullptr}, *dln[3] = {nullptr, nullptr, nullptr}, *dBOp = nullptr;
+  double *A0 = nullptr, *A1 = nullptr, *A2 = nullptr, *A3 = nullptr;
+  double *cB[3] = {nullptr, nullptr, nullptr};   // accumulated bond coefficients (cf1,cf2,cf3 of ForceBbo) per directed slot
+  double *cdslot = nullptr;                        // cdbnd contributions addressed to the partner of a slot
+  double *delta = nullptr, *deltap1 = nullptr, *deltap2 = nullptr, *nlp = nullptr, *dDlp = nullptr, *deltalp = nullptr;
+  double *ccbnd = nullptr, *cdbnd = nullptr;
+  // ---- scalars ---------------------------------------------------------------------------------------------
+  double *d_acc = nullptr;   // [64] reduction targets
+  int *d_flag = nullptr;     // [8]  error / overflow flags
+  int *d_blk = nullptr;      // scan scratch
+  long long *d_blk64 = nullptr;
+  int nblk_cap = 0;
+  double *h_acc = nullptr;   // pinned mirror of d_acc
+  int *h_int = nullptr;      // pinned
+  double PE[14] = {0};
+  double astr[6] = {0};
+  int nstep_qeq = 0;
+  DevFF ff;                 // host copy of the device pointer table
+  DevFF *d_ff = nullptr;
+  std::vector<void *> ff_allocs, allocs;
+  bool strict = false;      // RXG_STRICT_ORDER=1: serial-order, FMA-free CG for bit-level validation (small systems)
+  double timers_ms[30] = {0};
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  // ---- staging (pinned) ------------------------------------------------------------------------------------
+  double *h_stage = nullptr;
+  size_t h_stage_bytes = 0;
+};
+
+#define RXG_CUDA(call)                                                                                   \
+  do {                                                                                                   \
+    cudaError_t e_ = (call);                                                                             \
+    if (e_ != cudaSuccess) {                                                                             \
+      c->err = std::string("CUDA error: ") + cudaGetErrorString(e_) + " at " + __FILE__ + ":" + std::to_string(__LINE__); \
+      return RXG_ERR_CUDA;                                                                               \
+    }                                                                                                    \
+  } while (0)
+
+#define RXG_TRY(call)            \
+  do {                           \
+    int rc_ = (call);            \
+    if (rc_ != RXG_OK) return rc_; \
+  } while (0)
+
+inline int cdiv(long long a, int b) { return (int)((a + b - 1) / b); }
+
+#define LAUNCH(c, kern, grid, block, smem, ...)                 \
+  do {                                                          \
+    kern<<<(grid), (block), (smem), (c)->st>>>(__VA_ARGS__);    \
+    (c)->launches++;                                            \
+  } while (0)
+
+}   // namespace rxg
