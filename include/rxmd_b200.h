@@ -118,6 +118,8 @@ int rxg_set_box(rxg_handle h, const rxg_box *box);
  * the Fortran shim, TCPStore in the harness).  Not needed when nprocs == 1.
  * Replaces MPI_SEND/MPI_RECV/MPI_ALLREDUCE inside COPYATOMS/QEq (src/comm.F90:291-364, src/qeq.F90:107-144,357). */
 int rxg_comm_init(rxg_handle h, int rank, int nranks, const void *nccl_unique_id);
+/* rank 0 creates the 128-byte id and the host broadcasts it (MPI_Bcast / TCPStore) before rxg_comm_init */
+int rxg_comm_unique_id(void *out128);
 int rxg_destroy(rxg_handle h);
 const char *rxg_last_error(rxg_handle h);
 
@@ -138,7 +140,11 @@ int rxg_move(rxg_handle h, int *natoms, double *atype, double *pos, double *v, d
 /* WriteBND's inputs (src/fileio.F90:56-121): nbrlist(NBUFFER,0:MAXNEIGHBS) and BO(0,:,:) as
  * double[nbuffer*maxneighbs] (atom index fastest), valid after rxg_force */
 int rxg_fetch_bonds(rxg_handle h, int *nbrlist, double *BO0);
-/* it_timer(1:30) slots filled from CUDA-event timings, in milliseconds (src/module.F90:215-217) */
+/* 30 doubles of accumulated timings (the analogue of it_timer(1:30), src/module.F90:215-217), milliseconds unless noted:
+ * [0] rxg_qeq  [1] rxg_force  [2] rxg_move (device part, CUDA events)   [3] rxg_md_run total (CUDA events)
+ * [4] QEq inside md_run  [5] FORCE inside md_run  [6] MOVE inside md_run  [7] md steps (count)
+ * [10] get_hsh SpMV kernel total (CUDA events)  [11] its launches  [12] get_gradient SpMV kernel  [13] its launches
+ * [14] nnz of the last QEq matrix  [15] residents  [16] residents+ghosts at the last QEq  [17] CG iterations (count) */
 int rxg_timers(rxg_handle h, double *it_timer_ms);
 
 /* ---- device-resident stepping: the reference main-loop body src/main.F90:64-98

@@ -5,6 +5,7 @@
 #include "rxg_lists_qeq.cuh"
 #include "rxg_bonded.cuh"
 
+#include <chrono>
 #include <cmath>
 #include <cstdlib>
 #include <cstring>
@@ -80,33 +81,44 @@ struct Timer {
 };
 
 // ---------------------------------------------------------------------------------------------------
-// subroutine QEq on device-resident state, reference src/qeq.F90:2-178
-int qeq_device(Ctx *c) {
-  const int isQEq = c->cfg.isQEq;
-  if (isQEq != 1 && isQEq != 2) return RXG_OK;
-  const int n = c->natoms, NB = c->NB;
-  const int nmax = (isQEq == 1) ? c->cfg.NMAXQEq : 1;
-  int nprev = c->cp[6] > n ? c->cp[6] : n;
-  LAUNCH(c, k_qeq_init, cdiv(nprev, 256), 256, 0, n, nprev, c->q, c->qst, c->hsq, c->qsfp, c->qsfv, isQEq, c->cfg.Lex_fqs);
-  double QCopyDr[3] = {c->ff.rctap / c->box.lata, c->ff.rctap / c->box.latb, c->ff.rctap / c->box.latc};
-  RXG_TRY(halo_copy(c, QCopyDr));
-  LAUNCH(c, k_types, cdiv(c->cp[6], 256), 256, 0, c->atype, c->cp[6], c->itype, c->gid);
-  RXG_TRY(bin_grid(c, c->gnb));
-  RXG_TRY(build_pairlist<true>(c));
-  RXG_TRY(halo_qcopy(c, 1));
+// MPI_ALLREDUCE(SUM) of a few doubles (src/qeq.F90:107,129,144,357) as ncclAllReduce on the compute stream
+int allreduce_acc(Ctx *c, int first, int count) {
+  if (!c->comm) return RXG_OK;
+  ncclResult_t r = ncclAllReduce(c->d_acc + first, c->d_acc + first, count, ncclDouble, ncclSum, c->comm, c->st);
+  if (r != ncclSuccess) { c->err = std::string("NCCL error: ") + ncclGetErrorString(r); return RXG_ERR_NCCL; }
+  c->nccl_msgs++;
+  return RXG_OK;
+}
+
+// literal two-product CG of src/qeq.F90:86-166 (qeq_mode 1) and its serial-order variant (strict)
+int qeq_cg_literal(Ctx *c, int nmax, int *iters) {
+  const int n = c->natoms;
   const int rgrid = cdiv((long long)n * 32, 256);
-  RXG_CUDA(cudaMemsetAsync(c->d_acc, 0, sizeof(double) * 16, c->st));
   const bool strict = c->strict;
   double4 *rowbuf = (double4 *)c->tmp;
-  auto gradient = [&]() {
+  RXG_TRY(halo_qcopy(c, 1));
+  auto harvest_grad = [&]() {   // call only after a stream sync
+    if (c->grad_pending) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, c->evk[2], c->evk[3]);
+      c->timers_ms[12] += ms;
+      c->timers_ms[13] += 1;
+      c->grad_pending = false;
+    }
+  };
+  auto gradient = [&]() -> int {
     if (!strict) {
+      cudaEventRecord(c->evk[2], c->st);
       LAUNCH(c, k_gradient, rgrid, 256, 0, n, c->rowptr, c->col, c->val, c->qst, c->itype, c->d_ff, c->gst, c->d_acc);
+      cudaEventRecord(c->evk[3], c->st);
+      c->grad_pending = true;
     } else {
       LAUNCH(c, k_rows_strict_grad, cdiv(n, 64), 64, 0, n, c->rowptr, c->col, c->val, c->qst, c->itype, c->d_ff, c->gst);
       LAUNCH(c, k_seq_reduce, 1, 1, 0, 2, n, rowbuf, c->hsq, c->gst, c->qst, c->d_acc);
     }
+    return allreduce_acc(c, 7, 2);
   };
-  gradient();
+  RXG_TRY(gradient());
   LAUNCH(c, k_h_from_g, cdiv(n, 256), 256, 0, n, c->gst, c->hsq);
   RXG_TRY(halo_qcopy(c, 2));
   double GEst2 = 1e99;
@@ -114,13 +126,23 @@ int qeq_device(Ctx *c) {
   for (it = 0; it < nmax; it++) {
     LAUNCH(c, k_clear_iter, 1, 1, 0, c->d_acc);
     if (!strict) {
+      cudaEventRecord(c->evk[0], c->st);
       LAUNCH(c, k_hsh, rgrid, 256, 0, n, c->rowptr, c->col, c->val, c->hsq, c->gst, c->itype, c->d_ff, c->d_acc);
+      cudaEventRecord(c->evk[1], c->st);
     } else {
       LAUNCH(c, k_rows_strict_hsh, cdiv(n, 64), 64, 0, n, c->rowptr, c->col, c->val, c->hsq, c->itype, c->d_ff, rowbuf);
       LAUNCH(c, k_seq_reduce, 1, 1, 0, 0, n, rowbuf, c->hsq, c->gst, c->qst, c->d_acc);
     }
+    RXG_TRY(allreduce_acc(c, 0, 5));
     RXG_CUDA(cudaMemcpyAsync(c->h_acc, c->d_acc, sizeof(double) * 5, cudaMemcpyDeviceToHost, c->st));
     RXG_CUDA(cudaStreamSynchronize(c->st));
+    if (!strict) {
+      float ms = 0;
+      cudaEventElapsedTime(&ms, c->evk[0], c->evk[1]);
+      c->timers_ms[10] += ms;
+      c->timers_ms[11] += 1;
+      harvest_grad();
+    }
     double GEst1 = c->h_acc[0];
     if (0.5 * (std::fabs(GEst2) + std::fabs(GEst1)) < c->cfg.QEq_tol) break;                    // src/qeq.F90:114
     if (std::fabs(GEst2) > 0.0 && std::fabs(GEst1 / GEst2 - 1.0) < c->cfg.QEq_tol) break;      // src/qeq.F90:115
@@ -129,15 +151,86 @@ int qeq_device(Ctx *c) {
     float lmin_t = (float)(c->h_acc[4] / c->h_acc[2]);
     LAUNCH(c, k_qupdate, cdiv(n, 256), 256, 0, n, lmin_s, lmin_t, c->hsq, c->qst, c->d_acc);
     if (strict) LAUNCH(c, k_seq_reduce, 1, 1, 0, 1, n, rowbuf, c->hsq, c->gst, c->qst, c->d_acc);
+    RXG_TRY(allreduce_acc(c, 5, 2));
     LAUNCH(c, k_qfinal, cdiv(n, 256), 256, 0, n, c->qst, c->q, c->hsq, c->d_acc);
     RXG_TRY(halo_qcopy(c, 1));
     LAUNCH(c, k_roll_gnew, 1, 1, 0, c->d_acc);
-    gradient();
+    RXG_TRY(gradient());
     LAUNCH(c, k_hupdate, cdiv(n, 256), 256, 0, n, c->gst, c->hsq, c->d_acc);
     RXG_TRY(halo_qcopy(c, 2));
   }
+  *iters = it;
+  return RXG_OK;
+}
+
+// single-pass CG (default): one sparse product per iteration, see rxg_lists_qeq.cuh
+int qeq_cg_single(Ctx *c, int nmax, int *iters) {
+  const int n = c->natoms;
+  const int rgrid = cdiv((long long)n * 32, 256);
+  RXG_TRY(halo_refresh(c, 1, 0));   // ghost qs,qt (MODE_QCOPY1, src/qeq.F90:86)
+  LAUNCH(c, (k_spmv1<true>), rgrid, 256, 0, n, c->rowptr, c->col, c->val, c->qst, c->qst, c->q, c->gst, c->tst, c->ust, c->wst,
+         c->itype, c->d_ff, c->d_acc);
+  RXG_TRY(allreduce_acc(c, 7, 2));
+  LAUNCH(c, k_h_from_g2, cdiv(n, 256), 256, 0, n, c->gst, c->hst);
+  RXG_TRY(halo_refresh(c, 3, 0));   // ghost hs,ht (MODE_QCOPY2, :93)
+  double GEst2 = 1e99;
+  int it;
+  for (it = 0; it < nmax; it++) {
+    LAUNCH(c, k_clear_iter, 1, 1, 0, c->d_acc);
+    cudaEventRecord(c->evk[0], c->st);
+    LAUNCH(c, (k_spmv1<false>), rgrid, 256, 0, n, c->rowptr, c->col, c->val, c->hst, c->qst, c->q, c->gst, c->tst, c->ust, c->wst,
+           c->itype, c->d_ff, c->d_acc);
+    cudaEventRecord(c->evk[1], c->st);
+    RXG_TRY(allreduce_acc(c, 0, 5));
+    RXG_CUDA(cudaMemcpyAsync(c->h_acc, c->d_acc, sizeof(double) * 5, cudaMemcpyDeviceToHost, c->st));
+    RXG_CUDA(cudaStreamSynchronize(c->st));
+    float ms = 0;
+    cudaEventElapsedTime(&ms, c->evk[0], c->evk[1]);
+    c->timers_ms[10] += ms;
+    c->timers_ms[11] += 1;
+    double GEst1 = c->h_acc[0];
+    if (0.5 * (std::fabs(GEst2) + std::fabs(GEst1)) < c->cfg.QEq_tol) break;                    // src/qeq.F90:114
+    if (std::fabs(GEst2) > 0.0 && std::fabs(GEst1 / GEst2 - 1.0) < c->cfg.QEq_tol) break;      // src/qeq.F90:115
+    GEst2 = GEst1;
+    float lmin_s = (float)(c->h_acc[3] / c->h_acc[1]);   // real(4) :: lmin, src/qeq.F90:23,133
+    float lmin_t = (float)(c->h_acc[4] / c->h_acc[2]);
+    LAUNCH(c, k_roll_g, 1, 1, 0, c->d_acc);
+    LAUNCH(c, k_cg_update1, cdiv(n, 256), 256, 0, n, lmin_s, lmin_t, c->hst, c->tst, c->ust, c->qst, c->gst, c->wst, c->d_acc);
+    RXG_TRY(allreduce_acc(c, 5, 4));
+    LAUNCH(c, k_cg_update2, cdiv(n, 256), 256, 0, n, c->qst, c->gst, c->hst, c->q, c->d_acc);
+    RXG_TRY(halo_refresh(c, 3, 0));
+  }
+  // the reference converts positions to normalised coordinates and back in every COPYATOMS call: QCOPY1 + QCOPY2
+  // before the loop and two per completed iteration (src/qeq.F90:86,93,153,164); apply them in one launch
+  if (c->cp[6] > 0)
+    LAUNCH(c, k_roundtrip, cdiv(c->cp[6], 256), 256, 0, c->pos, c->NB, c->cp[6], make_boxdev(c->box), 2 + 2 * it);
+  *iters = it;
+  return RXG_OK;
+}
+
+// subroutine QEq on device-resident state, reference src/qeq.F90:2-178
+int qeq_device(Ctx *c) {
+  const int isQEq = c->cfg.isQEq;
+  if (isQEq != 1 && isQEq != 2) return RXG_OK;
+  const int n = c->natoms;
+  const int nmax = (isQEq == 1) ? c->cfg.NMAXQEq : 1;
+  int nprev = c->cp[6] > n ? c->cp[6] : n;
+  if (nprev > 0)
+    LAUNCH(c, k_qeq_init, cdiv(nprev, 256), 256, 0, n, nprev, c->q, c->qst, c->hsq, c->qsfp, c->qsfv, isQEq, c->cfg.Lex_fqs);
+  double QCopyDr[3] = {c->ff.rctap / c->box.lata, c->ff.rctap / c->box.latb, c->ff.rctap / c->box.latc};
+  RXG_TRY(halo_copy(c, QCopyDr));
+  if (c->cp[6] > 0) LAUNCH(c, k_types, cdiv(c->cp[6], 256), 256, 0, c->atype, c->cp[6], c->itype, c->gid);
+  RXG_TRY(bin_grid(c, c->gnb));
+  RXG_TRY(build_pairlist<true>(c));
+  RXG_CUDA(cudaMemsetAsync(c->d_acc, 0, sizeof(double) * 16, c->st));
+  int it = 0;
+  if (c->strict || c->qeq_mode == 1) RXG_TRY(qeq_cg_literal(c, nmax, &it));
+  else RXG_TRY(qeq_cg_single(c, nmax, &it));
   c->nstep_qeq = it;
-  (void)NB;
+  c->timers_ms[14] = (double)c->nnz;
+  c->timers_ms[15] = n;
+  c->timers_ms[16] = c->cp[6];
+  c->timers_ms[17] += it;
   return RXG_OK;
 }
 
@@ -156,6 +249,8 @@ int rxg_create(const rxg_config *cfg, rxg_handle *out) {
   c->dev = cfg->device;
   const char *so = getenv("RXG_STRICT_ORDER");
   c->strict = so && so[0] == '1';
+  const char *tp = getenv("RXG_QEQ_TWOPASS");
+  c->qeq_mode = (tp && tp[0] == '1') ? 1 : 0;
   *out = c;   // returned even on failure so that rxg_last_error can be read
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
@@ -172,10 +267,15 @@ int rxg_create(const rxg_config *cfg, rxg_handle *out) {
   RXG_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
   RXG_CUDA(cudaEventCreate(&c->ev0));
   RXG_CUDA(cudaEventCreate(&c->ev1));
+  RXG_CUDA(cudaEventCreate(&c->evm0));
+  RXG_CUDA(cudaEventCreate(&c->evm1));
+  for (int k = 0; k < 4; k++) RXG_CUDA(cudaEventCreate(&c->evk[k]));
   const size_t NB = c->NB, NS = NB * (size_t)c->MAXN;
   RXG_TRY(dalloc(c, &c->pos, 3 * NB)); RXG_TRY(dalloc(c, &c->v, 3 * NB)); RXG_TRY(dalloc(c, &c->f, 3 * NB));
   RXG_TRY(dalloc(c, &c->atype, NB)); RXG_TRY(dalloc(c, &c->q, NB)); RXG_TRY(dalloc(c, &c->qsfp, NB)); RXG_TRY(dalloc(c, &c->qsfv, NB));
   RXG_TRY(dalloc(c, &c->qst, NB)); RXG_TRY(dalloc(c, &c->hsq, NB)); RXG_TRY(dalloc(c, &c->gst, NB));
+  RXG_TRY(dalloc(c, &c->hst, NB)); RXG_TRY(dalloc(c, &c->tst, NB)); RXG_TRY(dalloc(c, &c->ust, NB)); RXG_TRY(dalloc(c, &c->wst, NB));
+  RXG_TRY(dalloc(c, &c->sel, NB)); c->sel_cap = (int)NB;
   RXG_TRY(dalloc(c, &c->itype, NB)); RXG_TRY(dalloc(c, &c->gid, NB)); RXG_TRY(dalloc(c, &c->frcindx, NB));
   RXG_TRY(dalloc(c, &c->tmp, 12 * NB));
   RXG_TRY(dalloc(c, &c->nbrcnt, NB)); RXG_TRY(dalloc(c, &c->nbrlist, NS)); RXG_TRY(dalloc(c, &c->nbrindx, NS));
@@ -187,7 +287,8 @@ int rxg_create(const rxg_config *cfg, rxg_handle *out) {
   RXG_TRY(dalloc(c, &c->delta, NB)); RXG_TRY(dalloc(c, &c->deltap1, NB)); RXG_TRY(dalloc(c, &c->deltap2, NB));
   RXG_TRY(dalloc(c, &c->nlp, NB)); RXG_TRY(dalloc(c, &c->dDlp, NB)); RXG_TRY(dalloc(c, &c->deltalp, NB));
   RXG_TRY(dalloc(c, &c->ccbnd, NB)); RXG_TRY(dalloc(c, &c->cdbnd, NB));
-  RXG_TRY(dalloc(c, &c->d_acc, 64)); RXG_TRY(dalloc(c, &c->d_flag, 8));
+  RXG_TRY(dalloc(c, &c->s3, 3 * NB)); RXG_TRY(dalloc(c, &c->sbo, NB));
+  RXG_TRY(dalloc(c, &c->d_acc, 64)); RXG_TRY(dalloc(c, &c->d_flag, 16));
   RXG_CUDA(cudaMallocHost((void **)&c->h_acc, sizeof(double) * 64));
   RXG_CUDA(cudaMallocHost((void **)&c->h_int, sizeof(int) * 16));
   RXG_TRY(ensure_blk(c, NB));
@@ -241,7 +342,6 @@ int rxg_set_box(rxg_handle h, const rxg_box *box) {
   if (c->have_box) { c->err = "rxg_set_box may be called once per handle"; return RXG_ERR_STATE; }
   c->box = *box;
   c->box.nbmesh = nullptr;
-  if (box->nprocs != 1) { c->err = "multi-rank decomposition needs rxg_comm_init (not available in this build)"; return RXG_ERR_ARG; }
   RXG_TRY(setup_grid(c, c->gb, box->cc, box->lcsize, RXG_MAXLAYERS));
   RXG_TRY(setup_grid(c, c->gnb, box->nbcc, box->nblcsize, RXG_MAXLAYERS_NB));
   // stencil -> z-runs, preserving the reference's mesh order (src/init.F90:563-592: i, j outer, k inner)
@@ -261,12 +361,26 @@ int rxg_set_box(rxg_handle h, const rxg_box *box) {
   return RXG_OK;
 }
 
+int rxg_comm_unique_id(void *out128) {
+  if (!out128) return RXG_ERR_ARG;
+  ncclUniqueId id;
+  if (ncclGetUniqueId(&id) != ncclSuccess) return RXG_ERR_NCCL;
+  static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
+  memcpy(out128, &id, 128);
+  return RXG_OK;
+}
+
 int rxg_comm_init(rxg_handle h, int rank, int nranks, const void *id) {
   Ctx *c = (Ctx *)h;
-  (void)rank; (void)id;
+  if (!c) return RXG_ERR_ARG;
   if (nranks == 1) return RXG_OK;
-  c->err = "rxg_comm_init: NCCL halo exchange not built in this version";
-  return RXG_ERR_NCCL;
+  if (!id) { c->err = "rxg_comm_init: null ncclUniqueId"; return RXG_ERR_ARG; }
+  RXG_CUDA(cudaSetDevice(c->dev));
+  ncclUniqueId uid;
+  memcpy(&uid, id, 128);
+  ncclResult_t r = ncclCommInitRank(&c->comm, nranks, uid, rank);
+  if (r != ncclSuccess) { c->err = std::string("ncclCommInitRank: ") + ncclGetErrorString(r); return RXG_ERR_NCCL; }
+  return RXG_OK;
 }
 
 int rxg_destroy(rxg_handle h) {
@@ -279,6 +393,9 @@ int rxg_destroy(rxg_handle h) {
     for (void *p : c->ff_allocs) cudaFree(p);
     for (void *p : {(void *)c->col, (void *)c->val, (void *)c->d_blk, (void *)c->d_blk64, (void *)c->d_runs, (void *)c->d_ff})
       if (p) cudaFree(p);
+    for (int k = 0; k < 2; k++) { if (c->sbuf[k]) cudaFree(c->sbuf[k]); if (c->rbuf[k]) cudaFree(c->rbuf[k]); }
+    if (c->comm) ncclCommDestroy(c->comm);
+    if (c->wl) cudaFree(c->wl);
     if (c->h_acc) cudaFreeHost(c->h_acc);
     if (c->h_int) cudaFreeHost(c->h_int);
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -448,18 +565,32 @@ int rxg_md_run(rxg_handle h, int nsteps, double dt, int qstep, double Lex_w2, in
   Ctx *c = (Ctx *)h;
   RXG_TRY(check_ready(c, c ? c->natoms : -1));
   if (qstep < 1) qstep = 1;
+  cudaEventRecord(c->evm0, c->st);
+  auto wall = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   for (int nstep = step0; nstep < step0 + nsteps; nstep++) {
     int n = c->natoms;
     // vkick(1) ; qsfv,qsfp ; pos += dt v      (src/main.F90:64-72)
     LAUNCH(c, k_md_first_half, cdiv(n, 256), 256, 0, n, c->NB, dt, Lex_w2, c->itype, c->d_ff, c->pos, c->v, c->f, c->q, c->qsfp, c->qsfv);
+    double t0 = wall();
     RXG_TRY(halo_move(c));                                   // :75
+    RXG_CUDA(cudaStreamSynchronize(c->st));
+    double t1 = wall();
     if (nstep % qstep == 0) RXG_TRY(qeq_device(c));          // :77-83
+    RXG_CUDA(cudaStreamSynchronize(c->st));
+    double t2 = wall();
     RXG_TRY(force_device(c));                                // :84
+    double t3 = wall();
+    c->timers_ms[6] += t1 - t0; c->timers_ms[4] += t2 - t1; c->timers_ms[5] += t3 - t2;
     n = c->natoms;
     // kinetic stress, vkick(1), qsfv                        (src/main.F90:86-98)
     LAUNCH(c, k_md_second_half, cdiv(n, 256), 256, 0, n, c->NB, dt, Lex_w2, c->itype, c->d_ff, c->v, c->f, c->q, c->qsfp, c->qsfv, c->d_acc + 40);
   }
+  cudaEventRecord(c->evm1, c->st);
   RXG_CUDA(cudaStreamSynchronize(c->st));
+  float ms = 0;
+  cudaEventElapsedTime(&ms, c->evm0, c->evm1);
+  c->timers_ms[3] += ms;
+  c->timers_ms[7] += nsteps;
   return RXG_OK;
 }
 

@@ -37,13 +37,14 @@ struct Bonds {   // per directed slot [i*MAXN + s]
 __global__ void __launch_bounds__(128) k_boprim(int ntot, const double *__restrict__ pos, int NB, const int *__restrict__ itype,
                                                 const DevFF *__restrict__ ffp, Bonds B, double *__restrict__ deltap1,
                                                 double *__restrict__ deltap2, double *__restrict__ cdbnd,
-                                                double *__restrict__ ccbnd) {
+                                                double *__restrict__ ccbnd, double *__restrict__ s3) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ntot) return;
   const DevFF &ff = *ffp;
   const int ity = itype[i];
   cdbnd[i] = 0.0;
   ccbnd[i] = 0.0;
+  s3[i] = 0.0; s3[NB + i] = 0.0; s3[2 * (size_t)NB + i] = 0.0;
   if (ity <= 0) { deltap1[i] = 0.0; deltap2[i] = 0.0; return; }
   const double xi = pos[i], yi = pos[NB + i], zi = pos[2 * NB + i];
   double dp = -ff.Val[ity - 1];
@@ -348,20 +349,31 @@ __device__ __forceinline__ void atomic_add3(double *__restrict__ f, int NB, int 
   atomicAdd(&f[2 * NB + i], z);
 }
 
-// C3: E3b, src/pot.F90:319-557.  One warp per centre atom j; lanes take the (i1<k1) pairs.
-__global__ void __launch_bounds__(128) k_e3b(int natoms, const double *__restrict__ pos, int NB, const int *__restrict__ itype,
-                                             const DevFF *__restrict__ ffp, Bonds B, const double *__restrict__ delta,
-                                             const double *__restrict__ nlp, const double *__restrict__ dDlp,
-                                             double *__restrict__ cdbnd, double *__restrict__ f, double *__restrict__ acc) {
+// ---------------------------------------------------------------------------------------------------
+// Angles and torsions are evaluated in two steps: an ENUMERATION kernel applies the reference's cut-off tests
+// (cheap, very divergent: ~8 of 66 candidate pairs and ~13 of ~50 candidate quadruples survive per atom) and
+// appends the survivors to a work list in HBM; an EVALUATION kernel then runs one thread per surviving
+// angle / torsion, so the expensive fp64 part (15 exp, pow, acos ...) executes with full warps.
+__device__ __forceinline__ int warp_append(bool valid, int *__restrict__ counter, int lane) {
+  unsigned m = __ballot_sync(0xffffffffu, valid);
+  int base = 0;
+  if (lane == 0 && m) base = atomicAdd(counter, __popc(m));
+  base = __shfl_sync(0xffffffffu, base, 0);
+  return valid ? base + __popc(m & ((1u << lane) - 1u)) : -1;
+}
+
+// C3a: E3b enumeration (src/pot.F90:356-386 tests).  One warp per centre atom j.  Also stores the per-centre sums.
+__global__ void __launch_bounds__(256) k_e3b_enum(int natoms, const int *__restrict__ itype, const DevFF *__restrict__ ffp,
+                                                  Bonds B, double2 *__restrict__ sbo, int2 *__restrict__ wl, int cap,
+                                                  int *__restrict__ counter) {
   const int lane = threadIdx.x & 31;
   const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  double part[3] = {0.0, 0.0, 0.0};   // PE(5..7)
-  if (j < natoms && itype[j] > 0) {
-    const DevFF &ff = *ffp;
-    const int jty = itype[j], tj = jty - 1;
-    const int n = B.cnt[j];
-    const size_t row = (size_t)j * B.MAXN;
-    // per-atom sums (every lane computes them redundantly from the same <=30 values)
+  if (j >= natoms || itype[j] <= 0) return;
+  const DevFF &ff = *ffp;
+  const int tj = itype[j] - 1;
+  const int n = B.cnt[j];
+  const size_t row = (size_t)j * B.MAXN;
+  if (lane == 0) {
     double sum_BO8 = 0.0, sum_SBO1 = 0.0;
     for (int s = 0; s < n; s++) {
       double b0 = B.BO0[row + s];
@@ -369,159 +381,175 @@ __global__ void __launch_bounds__(128) k_e3b(int natoms, const double *__restric
       sum_BO8 -= b4 * b4;
       sum_SBO1 += B.BO2[row + s] + B.BO3[row + s];
     }
-    const double prod_SBO = exp(sum_BO8);
+    sbo[j] = make_double2(exp(sum_BO8), sum_SBO1);
+  }
+  const int npairs = n * (n - 1) / 2;
+  for (int p0 = 0; p0 < npairs; p0 += 32) {
+    int p = p0 + lane;
+    bool valid = false;
+    int i1 = 0, k1 = 0;
+    if (p < npairs) {
+      int rem = p;
+      while (rem >= n - 1 - i1) { rem -= n - 1 - i1; i1++; }
+      k1 = i1 + 1 + rem;
+      double BOij0 = B.BO0[row + i1], BOjk0 = B.BO0[row + k1];
+      if ((BOij0 - CUTOF2_ESUB > 0.0) && (BOjk0 - CUTOF2_ESUB > 0.0) && (BOij0 * BOjk0 > CUTOF2_ESUB)) {
+        int ity = itype[B.lst[row + i1]], kty = itype[B.lst[row + k1]];
+        valid = ff.inxn3[(ity - 1) + ff.nso * (tj + ff.nso * (kty - 1))] != 0;
+      }
+    }
+    int w = warp_append(valid, counter, lane);
+    if (valid && w < cap) wl[w] = make_int2(j, i1 | (k1 << 8));
+  }
+}
+
+// C3b: E3b evaluation (src/pot.F90:388-541), one thread per angle.
+__global__ void __launch_bounds__(128) k_e3b_eval(int nwork, const int2 *__restrict__ wl, const double4 *__restrict__ pq, int NB,
+                                                  const int *__restrict__ itype, const DevFF *__restrict__ ffp, Bonds B,
+                                                  const double *__restrict__ delta, const double *__restrict__ nlp,
+                                                  const double *__restrict__ dDlp, const double2 *__restrict__ sbo,
+                                                  double *__restrict__ s3, double *__restrict__ f, double *__restrict__ acc) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  double part[3] = {0.0, 0.0, 0.0};   // PE(5..7)
+  if (t < nwork) {
+    const DevFF &ff = *ffp;
+    const int2 w = wl[t];
+    const int j = w.x, i1 = w.y & 0xff, k1 = (w.y >> 8) & 0xff;
+    const size_t row = (size_t)j * B.MAXN;
+    const int jty = itype[j], tj = jty - 1;
+    const int i = B.lst[row + i1], k = B.lst[row + k1];
+    const int ity = itype[i], kty = itype[k];
+    const int x = ff.inxn3[(ity - 1) + ff.nso * (tj + ff.nso * (kty - 1))] - 1;
+    const double BOij = B.BO0[row + i1] - CUTOF2_ESUB, BOjk = B.BO0[row + k1] - CUTOF2_ESUB;
+    const double2 sb = sbo[j];
+    const double prod_SBO = sb.x, sum_SBO1 = sb.y;
     const double dj = delta[j];
     const double delta_ang = dj + ff.Val[tj] - ff.Valangle[tj];
     const double nlpj = nlp[j], dDlpj = dDlp[j];
-    const double xj = pos[j], yj = pos[NB + j], zj = pos[2 * NB + j];
-    double S_d = 0.0, S_6 = 0.0, S_5 = 0.0;   // sums of CE3body_d(1), CEval(6), CEval(5) over this centre's angles
-    double fjx = 0, fjy = 0, fjz = 0;
-    const int npairs = n * (n - 1) / 2;
-    for (int p = lane; p < npairs; p += 32) {
-      // unrank p -> (i1 < k1)
-      int i1 = 0, rem = p;
-      while (rem >= n - 1 - i1) { rem -= n - 1 - i1; i1++; }
-      int k1 = i1 + 1 + rem;
-      double BOij0 = B.BO0[row + i1], BOjk0 = B.BO0[row + k1];
-      double BOij = BOij0 - CUTOF2_ESUB, BOjk = BOjk0 - CUTOF2_ESUB;
-      if (!(BOij > 0.0) || !(BOjk > 0.0) || !(BOij0 * BOjk0 > CUTOF2_ESUB)) continue;
-      int i = B.lst[row + i1], k = B.lst[row + k1];
-      int ity = itype[i], kty = itype[k];
-      int inxn = ff.inxn3[(ity - 1) + ff.nso * (tj + ff.nso * (kty - 1))];
-      if (inxn == 0) continue;
-      int x = inxn - 1;
-      double rij[3] = {pos[i] - xj, pos[NB + i] - yj, pos[2 * NB + i] - zj};
-      double rjk[3] = {xj - pos[k], yj - pos[NB + k], zj - pos[2 * NB + k]};
-      double nij = sqrt((rij[0] * rij[0] + rij[1] * rij[1]) + rij[2] * rij[2]);
-      double njk = sqrt((rjk[0] * rjk[0] + rjk[1] * rjk[1]) + rjk[2] * rjk[2]);
-      double cos_ijk = -((rij[0] * rjk[0] + rij[1] * rjk[1]) + rij[2] * rjk[2]) / (nij * njk);
-      if (cos_ijk > MAXANGLE) cos_ijk = MAXANGLE;
-      if (cos_ijk < MINANGLE) cos_ijk = MINANGLE;
-      double theta_ijk = acos(cos_ijk);
-      double sin_ijk = sin(theta_ijk);
-      // --- valence angle
-      double pv1 = ff.pval1[x], pv2 = ff.pval2[x], pv3 = ff.pval3[tj], pv4 = ff.pval4[x], pv5 = ff.pval5[tj];
-      double exp3ij = exp(-pv3 * pow(BOij, pv4)), exp3jk = exp(-pv3 * pow(BOjk, pv4));
-      double fn7ij = 1.0 - exp3ij, fn7jk = 1.0 - exp3jk;
-      double exp6 = exp(ff.pval6[x] * delta_ang), exp7 = exp(-ff.pval7[x] * delta_ang);
-      double trm8 = 1.0 + exp6 + exp7;
-      double fn8j = pv5 - (pv5 - 1.0) * (2.0 + exp6) / trm8;
-      double pv8 = ff.pval8[x], pv9 = ff.pval9[x], pv10 = ff.pval10[x];
-      double SBO = sum_SBO1 + (1.0 - prod_SBO) * (-delta_ang - pv8 * nlpj);
-      double SBO2 = 0.0, CSBO2 = 0.0;
-      if (SBO > 0) { SBO2 = pow(SBO, pv9); CSBO2 = pv9 * pow(SBO, pv9 - 1.0); }
-      if (SBO > 1) { SBO2 = 2.0 - pow(2.0 - SBO, pv9); CSBO2 = pv9 * pow(2.0 - SBO, pv9 - 1.0); }
-      if (SBO > 2) { SBO2 = 2.0; CSBO2 = 0.0; }
-      double th00 = ff.theta00[x];
-      double e10 = exp(-pv10 * (2.0 - SBO2));
-      double theta0 = PI_RX - th00 * (1.0 - e10);
-      double theta_diff = theta0 - theta_ijk;
-      double exp2 = exp(-pv2 * theta_diff * theta_diff);
-      double PEval = fn7ij * fn7jk * fn8j * (pv1 - pv1 * exp2);
-      double Cf7ij = pv3 * pv4 * pow(BOij, pv4 - 1.0) * exp3ij;
-      double Cf7jk = pv3 * pv4 * pow(BOjk, pv4 - 1.0) * exp3jk;
-      double Cf8j = (1.0 - pv5) / (trm8 * trm8) *
-                    (ff.pval6[x] * exp6 * trm8 - (2.0 + exp6) * (ff.pval6[x] * exp6 - ff.pval7[x] * exp7));
-      double Ctheta0 = pv10 * th00 * e10;
-      double dSBO1 = -8.0 * prod_SBO * (delta_ang + pv8 * nlpj);
-      double dSBO2 = (prod_SBO - 1.0) * (1.0 - pv8 * dDlpj);
-      double CEval1 = Cf7ij * fn7jk * fn8j * pv1 * (1.0 - exp2);
-      double CEval2 = fn7ij * Cf7jk * fn8j * pv1 * (1.0 - exp2);
-      double CEval3 = fn7ij * fn7jk * Cf8j * pv1 * (1.0 - exp2);
-      double CEval4 = 2.0 * pv1 * pv2 * fn7ij * fn7jk * fn8j * exp2 * theta_diff;
-      double CEval5 = CEval4 * Ctheta0 * CSBO2;
-      double CEval6 = CEval5 * dSBO1;
-      double CEval7 = CEval5 * dSBO2;
-      double CEval8 = CEval4 / sin_ijk;
-      // --- penalty
-      double pp2 = ff.ppen2[x], pp3 = ff.ppen3[x], pp4 = ff.ppen4[x];
-      double exp_pen3 = exp(-pp3 * dj), exp_pen4 = exp(pp4 * dj);
-      double trm_pen34 = 1.0 + exp_pen3 + exp_pen4;
-      double fn9 = (2.0 + exp_pen3) / trm_pen34;
-      double PEpen = ff.ppen1[x] * fn9 * exp(-pp2 * (BOij - 2.0) * (BOij - 2.0)) * exp(-pp2 * (BOjk - 2.0) * (BOjk - 2.0));
-      double Cf9j = (-pp3 * exp_pen3 * trm_pen34 - (2.0 + exp_pen3) * (-pp3 * exp_pen3 + pp4 * exp_pen4)) / (trm_pen34 * trm_pen34);
-      double CEpen1 = Cf9j / fn9 * PEpen;
-      double CEpen2 = -2.0 * pp2 * (BOij - 2.0) * PEpen;
-      double CEpen3 = -2.0 * pp2 * (BOjk - 2.0) * PEpen;
-      // --- 3-body conjugation
-      double sum_BOi = delta[i] + ff.Val[ity - 1], sum_BOk = delta[k] + ff.Val[kty - 1];
-      double delta_val = dj + ff.Val[tj] - ff.Valval[tj];
-      double pc2 = ff.pcoa2[x], pc3 = ff.pcoa3[x], pc4 = ff.pcoa4[x];
-      double exp_coa2 = exp(pc2 * delta_val);
-      double ui = -BOij + sum_BOi, uk = -BOjk + sum_BOk;
-      double PEcoa = ff.pcoa1[x] / (1.0 + exp_coa2) * exp(-pc3 * (ui * ui)) * exp(-pc3 * (uk * uk)) *
-                     exp(-pc4 * ((BOij - 1.5) * (BOij - 1.5))) * exp(-pc4 * ((BOjk - 1.5) * (BOjk - 1.5)));
-      double CEcoa1 = -2.0 * pc4 * (BOij - 1.5) * PEcoa;
-      double CEcoa2 = -2.0 * pc4 * (BOjk - 1.5) * PEcoa;
-      double CEcoa3 = -pc2 * exp_coa2 / (1.0 + exp_coa2) * PEcoa;
-      double CEcoa4 = -2.0 * pc3 * ui * PEcoa;
-      double CEcoa5 = -2.0 * pc3 * uk * PEcoa;
-      part[0] += PEval; part[1] += PEpen; part[2] += PEcoa;
-      // ForceB on BO_ij and BO_jk: both bonds are slots of this centre
-      atomicAdd(&B.cB0[row + i1], CEpen2 + CEcoa1 - CEcoa4 + CEval1);
-      atomicAdd(&B.cB0[row + k1], CEpen3 + CEcoa2 - CEcoa5 + CEval2);
-      // cdbnd(i) += CE3body_d(2) ; cdbnd(k) += CE3body_d(3)   -> addressed to the partners of those slots
-      atomicAdd(&B.cdslot[row + i1], CEcoa4);
-      atomicAdd(&B.cdslot[row + k1], CEcoa5);
-      S_d += CEpen1 + CEcoa3 + CEval3 + CEval7;
-      S_6 += CEval6;
-      S_5 += CEval5;
-      double fij[3], fjk[3];
-      a3_forces(CEval8, rij, nij, rjk, njk, fij, fjk);
-      atomic_add3(f, NB, i, fij[0], fij[1], fij[2]);
-      atomic_add3(f, NB, k, -fjk[0], -fjk[1], -fjk[2]);
-      fjx += -fij[0] + fjk[0]; fjy += -fij[1] + fjk[1]; fjz += -fij[2] + fjk[2];
-    }
-    S_d = warp_sum(S_d); S_6 = warp_sum(S_6); S_5 = warp_sum(S_5);
-    fjx = warp_sum(fjx); fjy = warp_sum(fjy); fjz = warp_sum(fjz);
-    if (lane == 0 && npairs > 0) atomic_add3(f, NB, j, fjx, fjy, fjz);
-    // the reference's inner loop over ALL neighbours of j per angle (src/pot.F90:526-532), summed analytically
-    if (S_d != 0.0 || S_6 != 0.0 || S_5 != 0.0) {
-      for (int s = lane; s < n; s += 32) {
-        double b0 = B.BO0[row + s];
-        double b2 = b0 * b0, b3 = b2 * b0;
-        atomicAdd(&B.cB0[row + s], S_d + S_6 * (b3 * b3 * b0));
-        atomicAdd(&B.cB1[row + s], S_5);
-        atomicAdd(&B.cB2[row + s], S_5);
-      }
-    }
+    const double4 pj = pq[j], pi = pq[i], pk = pq[k];
+    double rij[3] = {pi.x - pj.x, pi.y - pj.y, pi.z - pj.z};
+    double rjk[3] = {pj.x - pk.x, pj.y - pk.y, pj.z - pk.z};
+    double nij = sqrt((rij[0] * rij[0] + rij[1] * rij[1]) + rij[2] * rij[2]);
+    double njk = sqrt((rjk[0] * rjk[0] + rjk[1] * rjk[1]) + rjk[2] * rjk[2]);
+    double cos_ijk = -((rij[0] * rjk[0] + rij[1] * rjk[1]) + rij[2] * rjk[2]) / (nij * njk);
+    if (cos_ijk > MAXANGLE) cos_ijk = MAXANGLE;
+    if (cos_ijk < MINANGLE) cos_ijk = MINANGLE;
+    double theta_ijk = acos(cos_ijk);
+    double sin_ijk = sin(theta_ijk);
+    // --- valence angle
+    double pv1 = ff.pval1[x], pv2 = ff.pval2[x], pv3 = ff.pval3[tj], pv4 = ff.pval4[x], pv5 = ff.pval5[tj];
+    double exp3ij = exp(-pv3 * pow(BOij, pv4)), exp3jk = exp(-pv3 * pow(BOjk, pv4));
+    double fn7ij = 1.0 - exp3ij, fn7jk = 1.0 - exp3jk;
+    double pv6 = ff.pval6[x], pv7 = ff.pval7[x];
+    double exp6 = exp(pv6 * delta_ang), exp7 = exp(-pv7 * delta_ang);
+    double trm8 = 1.0 + exp6 + exp7;
+    double fn8j = pv5 - (pv5 - 1.0) * (2.0 + exp6) / trm8;
+    double pv8 = ff.pval8[x], pv9 = ff.pval9[x], pv10 = ff.pval10[x];
+    double SBO = sum_SBO1 + (1.0 - prod_SBO) * (-delta_ang - pv8 * nlpj);
+    double SBO2 = 0.0, CSBO2 = 0.0;
+    if (SBO > 0) { SBO2 = pow(SBO, pv9); CSBO2 = pv9 * pow(SBO, pv9 - 1.0); }
+    if (SBO > 1) { SBO2 = 2.0 - pow(2.0 - SBO, pv9); CSBO2 = pv9 * pow(2.0 - SBO, pv9 - 1.0); }
+    if (SBO > 2) { SBO2 = 2.0; CSBO2 = 0.0; }
+    double th00 = ff.theta00[x];
+    double e10 = exp(-pv10 * (2.0 - SBO2));
+    double theta0 = PI_RX - th00 * (1.0 - e10);
+    double theta_diff = theta0 - theta_ijk;
+    double exp2 = exp(-pv2 * theta_diff * theta_diff);
+    double PEval = fn7ij * fn7jk * fn8j * (pv1 - pv1 * exp2);
+    double Cf7ij = pv3 * pv4 * pow(BOij, pv4 - 1.0) * exp3ij;
+    double Cf7jk = pv3 * pv4 * pow(BOjk, pv4 - 1.0) * exp3jk;
+    double Cf8j = (1.0 - pv5) / (trm8 * trm8) * (pv6 * exp6 * trm8 - (2.0 + exp6) * (pv6 * exp6 - pv7 * exp7));
+    double Ctheta0 = pv10 * th00 * e10;
+    double dSBO1 = -8.0 * prod_SBO * (delta_ang + pv8 * nlpj);
+    double dSBO2 = (prod_SBO - 1.0) * (1.0 - pv8 * dDlpj);
+    double CEval1 = Cf7ij * fn7jk * fn8j * pv1 * (1.0 - exp2);
+    double CEval2 = fn7ij * Cf7jk * fn8j * pv1 * (1.0 - exp2);
+    double CEval3 = fn7ij * fn7jk * Cf8j * pv1 * (1.0 - exp2);
+    double CEval4 = 2.0 * pv1 * pv2 * fn7ij * fn7jk * fn8j * exp2 * theta_diff;
+    double CEval5 = CEval4 * Ctheta0 * CSBO2;
+    double CEval6 = CEval5 * dSBO1;
+    double CEval7 = CEval5 * dSBO2;
+    double CEval8 = CEval4 / sin_ijk;
+    // --- penalty
+    double pp2 = ff.ppen2[x], pp3 = ff.ppen3[x], pp4 = ff.ppen4[x];
+    double exp_pen3 = exp(-pp3 * dj), exp_pen4 = exp(pp4 * dj);
+    double trm_pen34 = 1.0 + exp_pen3 + exp_pen4;
+    double fn9 = (2.0 + exp_pen3) / trm_pen34;
+    double PEpen = ff.ppen1[x] * fn9 * exp(-pp2 * (BOij - 2.0) * (BOij - 2.0)) * exp(-pp2 * (BOjk - 2.0) * (BOjk - 2.0));
+    double Cf9j = (-pp3 * exp_pen3 * trm_pen34 - (2.0 + exp_pen3) * (-pp3 * exp_pen3 + pp4 * exp_pen4)) / (trm_pen34 * trm_pen34);
+    double CEpen1 = Cf9j / fn9 * PEpen;
+    double CEpen2 = -2.0 * pp2 * (BOij - 2.0) * PEpen;
+    double CEpen3 = -2.0 * pp2 * (BOjk - 2.0) * PEpen;
+    // --- 3-body conjugation
+    double sum_BOi = delta[i] + ff.Val[ity - 1], sum_BOk = delta[k] + ff.Val[kty - 1];
+    double delta_val = dj + ff.Val[tj] - ff.Valval[tj];
+    double pc2 = ff.pcoa2[x], pc3 = ff.pcoa3[x], pc4 = ff.pcoa4[x];
+    double exp_coa2 = exp(pc2 * delta_val);
+    double ui = -BOij + sum_BOi, uk = -BOjk + sum_BOk;
+    double PEcoa = ff.pcoa1[x] / (1.0 + exp_coa2) * exp(-pc3 * (ui * ui)) * exp(-pc3 * (uk * uk)) *
+                   exp(-pc4 * ((BOij - 1.5) * (BOij - 1.5))) * exp(-pc4 * ((BOjk - 1.5) * (BOjk - 1.5)));
+    double CEcoa1 = -2.0 * pc4 * (BOij - 1.5) * PEcoa;
+    double CEcoa2 = -2.0 * pc4 * (BOjk - 1.5) * PEcoa;
+    double CEcoa3 = -pc2 * exp_coa2 / (1.0 + exp_coa2) * PEcoa;
+    double CEcoa4 = -2.0 * pc3 * ui * PEcoa;
+    double CEcoa5 = -2.0 * pc3 * uk * PEcoa;
+    part[0] = PEval; part[1] = PEpen; part[2] = PEcoa;
+    // ForceB on BO_ij and BO_jk: both bonds are slots of the centre
+    atomicAdd(&B.cB0[row + i1], CEpen2 + CEcoa1 - CEcoa4 + CEval1);
+    atomicAdd(&B.cB0[row + k1], CEpen3 + CEcoa2 - CEcoa5 + CEval2);
+    // cdbnd(i) += CE3body_d(2) ; cdbnd(k) += CE3body_d(3)  -> addressed to the partners of those slots
+    atomicAdd(&B.cdslot[row + i1], CEcoa4);
+    atomicAdd(&B.cdslot[row + k1], CEcoa5);
+    // the reference's loop over ALL neighbours of j per angle (src/pot.F90:526-532) is linear in three per-centre
+    // sums: sum CE3body_d(1), sum CEval(6), sum CEval(5); k_final1 applies them to every bond of j
+    atomicAdd(&s3[j], CEpen1 + CEcoa3 + CEval3 + CEval7);
+    atomicAdd(&s3[NB + j], CEval6);
+    atomicAdd(&s3[2 * (size_t)NB + j], CEval5);
+    double fij[3], fjk[3];
+    a3_forces(CEval8, rij, nij, rjk, njk, fij, fjk);
+    atomic_add3(f, NB, i, fij[0], fij[1], fij[2]);
+    atomic_add3(f, NB, j, -fij[0] + fjk[0], -fij[1] + fjk[1], -fij[2] + fjk[2]);
+    atomic_add3(f, NB, k, -fjk[0], -fjk[1], -fjk[2]);
   }
   block_add<3>(part, acc + ACC_PE + 5);
 }
 
 // C5: Ehb, src/pot.F90:559-673.  One warp per resident i; for every donor-H bond the lanes scan i's 10 A row.
-__global__ void __launch_bounds__(128) k_ehb(int natoms, const double *__restrict__ pos, int NB, const int *__restrict__ itype,
+__global__ void __launch_bounds__(256) k_ehb(int natoms, const double4 *__restrict__ pq, const int2 *__restrict__ tg, int NB,
                                              const DevFF *__restrict__ ffp, Bonds B, const long long *__restrict__ rowptr,
                                              const int *__restrict__ col, double *__restrict__ f, double *__restrict__ acc) {
   const int lane = threadIdx.x & 31;
   const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   double part[1] = {0.0};
-  if (i < natoms && itype[i] > 0) {
+  if (i < natoms && tg[i].x > 0) {
     const DevFF &ff = *ffp;
-    const int ity = itype[i];
-    const int n = B.cnt[i];
+    const int ity = tg[i].x;
+    // can atom type ity be a donor at all?  (any acceptor type with inxn3hb(ity, H=2, kty) != 0)
+    bool donor = false;
+    for (int kt = 0; kt < ff.nso; kt++) donor |= ff.nso >= 2 && ff.inxn3hb[(ity - 1) + ff.nso * (1 + ff.nso * kt)] != 0;
+    const int n = donor ? B.cnt[i] : 0;
     const size_t row = (size_t)i * B.MAXN;
-    const double xi = pos[i], yi = pos[NB + i], zi = pos[2 * NB + i];
+    const double4 pi = pq[i];
     for (int s = 0; s < n; s++) {
       int j = B.lst[row + s];
-      int jty = itype[j];
+      int jty = tg[j].x;
       double bo = B.BO0[row + s];
       if (!((jty == 2) && (bo > MINBO0))) continue;   // hydrogen is hard-coded as type 2
-      const double xj = pos[j], yj = pos[NB + j], zj = pos[2 * NB + j];
-      double rij[3] = {xi - xj, yi - yj, zi - zj};
+      const double4 pj = pq[j];
+      double rij[3] = {pi.x - pj.x, pi.y - pj.y, pi.z - pj.z};
       double nij = sqrt((rij[0] * rij[0] + rij[1] * rij[1]) + rij[2] * rij[2]);
       double cb = 0.0, fi[3] = {0, 0, 0}, fj[3] = {0, 0, 0};
       long long rs = rowptr[i], re = rowptr[i + 1];
       for (long long kk = rs + lane; kk < re; kk += 32) {
         int k = col[kk];
-        int kty = itype[k];
+        int kty = tg[k].x;
         int inxnhb = ff.inxn3hb[(ity - 1) + ff.nso * ((jty - 1) + ff.nso * (kty - 1))];
         if (!((j != k) && (i != k) && (inxnhb != 0))) continue;
-        double xk = pos[k], yk = pos[NB + k], zk = pos[2 * NB + k];
-        double rik2 = dist2_rn(sub_rn(xi, xk), sub_rn(yi, yk), sub_rn(zi, zk));
+        const double4 pk = pq[k];
+        double rik2 = dist2_rn(sub_rn(pi.x, pk.x), sub_rn(pi.y, pk.y), sub_rn(pi.z, pk.z));
         if (!(rik2 < RCHB2)) continue;
         int x = inxnhb - 1;
-        double rjk[3] = {xj - xk, yj - yk, zj - zk};
+        double rjk[3] = {pj.x - pk.x, pj.y - pk.y, pj.z - pk.z};
         double njk = sqrt((rjk[0] * rjk[0] + rjk[1] * rjk[1]) + rjk[2] * rjk[2]);
         double cos_ijk = -((rij[0] * rjk[0] + rij[1] * rjk[1]) + rij[2] * rjk[2]) / (nij * njk);
         if (cos_ijk > MAXANGLE) cos_ijk = MAXANGLE;
@@ -552,8 +580,8 @@ __global__ void __launch_bounds__(128) k_ehb(int natoms, const double *__restric
       cb = warp_sum(cb);
 #pragma unroll
       for (int c = 0; c < 3; c++) { fi[c] = warp_sum(fi[c]); fj[c] = warp_sum(fj[c]); }
-      if (lane == 0) {
-        if (cb != 0.0) atomicAdd(&B.cB0[row + s], cb);   // ForceB(i,j1,...,CEhb(1))
+      if (lane == 0 && cb != 0.0) {
+        atomicAdd(&B.cB0[row + s], cb);   // ForceB(i,j1,...,CEhb(1))
         atomic_add3(f, NB, i, fi[0], fi[1], fi[2]);
         atomic_add3(f, NB, j, fj[0], fj[1], fj[2]);
       }
@@ -573,166 +601,163 @@ __device__ __forceinline__ double cross_n(const double *a, double na, const doub
   return n < NSMALL ? NSMALL : n;
 }
 
-// C4: E4b, src/pot.F90:980-1227.  One warp per atom j; central bonds j-k1 in sequence; lanes take the (i1,l1) pairs.
-__global__ void __launch_bounds__(128) k_e4b(int natoms, const double *__restrict__ pos, int NB, const int *__restrict__ itype,
-                                             const int *__restrict__ gid, const DevFF *__restrict__ ffp, Bonds B,
-                                             const double *__restrict__ delta, double *__restrict__ cdbnd,
-                                             double *__restrict__ f, double *__restrict__ acc) {
+// C4a: E4b enumeration (tests of src/pot.F90:1022-1081).  One warp per atom j; central bonds in sequence.
+__global__ void __launch_bounds__(256) k_e4b_enum(int natoms, const int *__restrict__ itype, const int *__restrict__ gid,
+                                                  const DevFF *__restrict__ ffp, Bonds B, int2 *__restrict__ wl, int cap,
+                                                  int *__restrict__ counter) {
   const int lane = threadIdx.x & 31;
   const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  double part[2] = {0.0, 0.0};   // PE(8..9)
-  if (j < natoms && itype[j] > 0) {
-    const DevFF &ff = *ffp;
-    const int jty = itype[j], jid = gid[j];
-    const int nj = B.cnt[j];
-    const size_t rowj = (size_t)j * B.MAXN;
-    const double delta_ang_j = delta[j] + ff.Val[jty - 1] - ff.Valangle[jty - 1];
-    const double xj = pos[j], yj = pos[NB + j], zj = pos[2 * NB + j];
-    double fj[3] = {0, 0, 0}, cdj = 0.0;
-    for (int k1 = 0; k1 < nj; k1++) {
-      double BOjk0 = B.BO0[rowj + k1];
-      if (!(BOjk0 > CUTOF2_ESUB)) continue;
-      int k = B.lst[rowj + k1];
-      if (!(jid < gid[k])) continue;
-      double BOjk = BOjk0 - CUTOF2_ESUB;
-      int kty = itype[k];
-      const int nk = B.cnt[k];
-      const size_t rowk = (size_t)k * B.MAXN;
-      double delta_ang_jk = delta_ang_j + (delta[k] + ff.Val[kty - 1] - ff.Valangle[kty - 1]);
-      const double xk = pos[k], yk = pos[NB + k], zk = pos[2 * NB + k];
-      double rjk[3] = {xj - xk, yj - yk, zj - zk};
-      double njk = sqrt((rjk[0] * rjk[0] + rjk[1] * rjk[1]) + rjk[2] * rjk[2]);
-      double BOpi_jk = B.BO2[rowj + k1];
-      double fk[3] = {0, 0, 0}, cdk = 0.0, cjk0 = 0.0, cjk1 = 0.0;
-      const int ncomb = nj * nk;
-      for (int p = lane; p < ncomb; p += 32) {
-        int i1 = p / nk, l1 = p - i1 * nk;
-        double BOij0 = B.BO0[rowj + i1];
-        if (!((BOij0 > CUTOF2_ESUB) && ((BOij0 * BOjk0) > CUTOF2_ESUB))) continue;
-        int i = B.lst[rowj + i1];
-        if (i == k) continue;
-        double BOkl0 = B.BO0[rowk + l1];
-        if (!((BOkl0 > CUTOF2_ESUB) && (BOjk0 * BOkl0 > CUTOF2_ESUB))) continue;
-        int l = B.lst[rowk + l1];
-        int ity = itype[i], lty = itype[l];
-        int inxn = ff.inxn4[(ity - 1) + ff.nso * ((jty - 1) + ff.nso * ((kty - 1) + ff.nso * (lty - 1)))];
-        if (!((inxn != 0) && (i != l) && (j != l))) continue;
-        if (!((BOij0 * (BOjk0 * BOjk0) * BOkl0) > MINBO0)) continue;
-        int x = inxn - 1;
-        double BOij = BOij0 - CUTOF2_ESUB, BOkl = BOkl0 - CUTOF2_ESUB;
-        double rij[3] = {pos[i] - xj, pos[NB + i] - yj, pos[2 * NB + i] - zj};
-        double nij = sqrt((rij[0] * rij[0] + rij[1] * rij[1]) + rij[2] * rij[2]);
-        double cos_ijk = -((rij[0] * rjk[0] + rij[1] * rjk[1]) + rij[2] * rjk[2]) / (nij * njk);
-        if (cos_ijk > MAXANGLE) cos_ijk = MAXANGLE;
-        if (cos_ijk < MINANGLE) cos_ijk = MINANGLE;
-        double theta_ijk = acos(cos_ijk);
-        double sin_ijk = sin(theta_ijk);
-        double tan_ijk_i = 1.0 / tan(theta_ijk);
-        double crs_ijk[3];
-        double ncr1 = cross_n(rij, nij, rjk, njk, crs_ijk);
-        double rkl[3] = {xk - pos[l], yk - pos[NB + l], zk - pos[2 * NB + l]};
-        double nkl = sqrt((rkl[0] * rkl[0] + rkl[1] * rkl[1]) + rkl[2] * rkl[2]);
-        double pt1 = ff.ptor1[x], pt2 = ff.ptor2[x], pt3 = ff.ptor3[x], pt4 = ff.ptor4[x];
-        double V1 = ff.V1[x], V2 = ff.V2[x], V3 = ff.V3[x], pc1 = ff.pcot1[x], pc2 = ff.pcot2[x];
-        double et1 = exp(-pt2 * BOij), et2 = exp(-pt2 * BOjk), et3 = exp(-pt2 * BOkl);
-        double exp_tor3 = exp(-pt3 * delta_ang_jk), exp_tor4 = exp(pt4 * delta_ang_jk);
-        double exp_tor34_i = 1.0 / (1.0 + exp_tor3 + exp_tor4);
-        double fn10 = (1.0 - et1) * (1.0 - et2) * (1.0 - et3);
-        double fn11 = (2.0 + exp_tor3) * exp_tor34_i;
-        double fn12 = exp(-pc2 * ((BOij - 1.5) * (BOij - 1.5) + (BOjk - 1.5) * (BOjk - 1.5) + (BOkl - 1.5) * (BOkl - 1.5)));
-        double btb2 = 2.0 - BOpi_jk - fn11;
-        double exp_tor1 = exp(pt1 * (btb2 * btb2));
-        double cos_jkl = -((rjk[0] * rkl[0] + rjk[1] * rkl[1]) + rjk[2] * rkl[2]) / (njk * nkl);
-        if (cos_jkl > MAXANGLE) cos_jkl = MAXANGLE;
-        if (cos_jkl < MINANGLE) cos_jkl = MINANGLE;
-        double theta_jkl = acos(cos_jkl);
-        double sin_jkl = sin(theta_jkl);
-        double tan_jkl_i = 1.0 / tan(theta_jkl);
-        double crs_jkl[3];
-        double ncr2 = cross_n(rjk, njk, rkl, nkl, crs_jkl);
-        double cw = ((crs_ijk[0] * crs_jkl[0] + crs_ijk[1] * crs_jkl[1]) + crs_ijk[2] * crs_jkl[2]) / (ncr1 * ncr2);
-        if (cw > MAXANGLE) cw = MAXANGLE;
-        if (cw < MINANGLE) cw = MINANGLE;
-        double omega = acos(cw);
-        double cw_sqr = cw * cw;
-        double cos_2w = cos(2.0 * omega);
-        double c2 = 1.0 - cos_2w;
-        double c3 = 1.0 + cos(3.0 * omega);
-        double Vsum = V1 * (1.0 + cw) + V2 * exp_tor1 * c2 + V3 * c3;
-        double PEtors = 0.5 * fn10 * sin_ijk * sin_jkl * Vsum;
-        double PEconj = pc1 * fn12 * (1.0 + (cw_sqr - 1.0) * sin_ijk * sin_jkl);
-        part[0] += PEtors; part[1] += PEconj;
-        double CEtors1 = 0.5 * sin_ijk * sin_jkl * Vsum;
-        double CEtors2 = -pt1 * fn10 * sin_ijk * sin_jkl * V2 * exp_tor1 * btb2 * c2;
-        double dfn11 = (-pt3 * exp_tor3 + (pt3 * exp_tor3 - pt4 * exp_tor4) * (2.0 + exp_tor3) * exp_tor34_i) * exp_tor34_i;
-        double CEtors3 = CEtors2 * dfn11;
-        double CEtors4 = CEtors1 * pt2 * et1 * (1.0 - et2) * (1.0 - et3);
-        double CEtors5 = CEtors1 * pt2 * (1.0 - et1) * et2 * (1.0 - et3);
-        double CEtors6 = CEtors1 * pt2 * (1.0 - et1) * (1.0 - et2) * et3;
-        double cmn = -0.5 * fn10 * Vsum;
-        double CEtors7 = cmn * sin_jkl * tan_ijk_i;
-        double CEtors8 = cmn * sin_ijk * tan_jkl_i;
-        double CEtors9 = fn10 * sin_ijk * sin_jkl * (0.5 * V1 - 2.0 * V2 * exp_tor1 * cw + 1.5 * V3 * (cos_2w + 2.0 * cw_sqr));
-        double Cconj = -2.0 * pc2 * PEconj;
-        double CEconj4 = -pc1 * fn12 * (cw_sqr - 1.0) * tan_ijk_i * sin_jkl;
-        double CEconj5 = -pc1 * fn12 * (cw_sqr - 1.0) * sin_ijk * tan_jkl_i;
-        double CEconj6 = 2.0 * pc1 * fn12 * cw * sin_ijk * sin_jkl;
-        double Cb_ij = Cconj * (BOij - 1.5) + CEtors4;
-        double Cb_jk = Cconj * (BOjk - 1.5) + CEtors5;
-        double Cb_kl = Cconj * (BOkl - 1.5) + CEtors6;
-        double Ca_ijk = CEconj4 + CEtors7, Ca_jkl = CEconj5 + CEtors8, Ca_ijkl = CEconj6 + CEtors9;
-        cdj += CEtors3;
-        cdk += CEtors3;
-        atomicAdd(&B.cB0[rowj + i1], Cb_ij);   // ForceB on BO_ij (slot of j)
-        cjk0 += Cb_jk;                         // ForceBbo on BO_jk: coeff (b, b+t2, b) -> cf (b, t2, 0)
-        cjk1 += CEtors2;
-        atomicAdd(&B.cB0[rowk + l1], Cb_kl);   // ForceB on BO_kl (slot of k)
-        // --- direction forces: ForceA3(i,j,k), ForceA3(j,k,l), ForceA4(i,j,k,l)  (src/pot.F90:1369-1521)
-        double f1[3], f2[3], g1[3], g2[3];
-        a3_forces(Ca_ijk, rij, nij, rjk, njk, f1, f2);
-        a3_forces(Ca_jkl, rjk, njk, rkl, nkl, g1, g2);
-        double C00 = nij * nij, C01 = (rij[0] * rjk[0] + rij[1] * rjk[1]) + rij[2] * rjk[2],
-               C02 = (rij[0] * rkl[0] + rij[1] * rkl[1]) + rij[2] * rkl[2];
-        double C11 = njk * njk, C12 = (rjk[0] * rkl[0] + rjk[1] * rkl[1]) + rjk[2] * rkl[2], C22 = nkl * nkl;
-        double D0 = C00 * C11 - C01 * C01, D1 = C11 * C22 - C12 * C12;
-        double coDD = Ca_ijkl * (1.0 / sqrt(D0 * D1));
-        double com = C01 * C12 - C02 * C11;
-        double Cwi0 = C11 / D0 * com, Cwi1 = -(C12 + C01 / D0 * com), Cwi2 = C11;
-        double Cwj0 = -(C12 + (C11 + C01) / D0 * com);
-        double Cwj1 = -(-C12 - 2 * C02 - C22 / D1 * com - (C00 + C01) / D0 * com);
-        double Cwj2 = -(C01 + C11 + C12 / D1 * com);
-        double Cwl0 = -C11, Cwl1 = (C01 + C12 / D1 * com), Cwl2 = -(C11 / D1 * com);
-        double Fi[3], Fl[3];
-#pragma unroll
-        for (int c = 0; c < 3; c++) {
-          double hij = coDD * (Cwi0 * rij[c] + Cwi1 * rjk[c] + Cwi2 * rkl[c]);
-          double hjk = coDD * ((Cwj0 + Cwi0) * rij[c] + (Cwj1 + Cwi1) * rjk[c] + (Cwj2 + Cwi2) * rkl[c]);
-          double hkl = -coDD * (Cwl0 * rij[c] + Cwl1 * rjk[c] + Cwl2 * rkl[c]);
-          Fi[c] = f1[c] + hij;
-          fj[c] += (-f1[c] + f2[c]) + g1[c] + (-hij + hjk);
-          fk[c] += -f2[c] + (-g1[c] + g2[c]) + (-hjk + hkl);
-          Fl[c] = -g2[c] - hkl;
+  if (j >= natoms || itype[j] <= 0) return;
+  const DevFF &ff = *ffp;
+  const int jty = itype[j], jid = gid[j];
+  const int nj = B.cnt[j];
+  const size_t rowj = (size_t)j * B.MAXN;
+  for (int k1 = 0; k1 < nj; k1++) {
+    double BOjk0 = B.BO0[rowj + k1];
+    if (!(BOjk0 > CUTOF2_ESUB)) continue;
+    int k = B.lst[rowj + k1];
+    if (!(jid < gid[k])) continue;
+    int kty = itype[k];
+    const int nk = B.cnt[k];
+    const size_t rowk = (size_t)k * B.MAXN;
+    const int ncomb = nj * nk;
+    for (int p0 = 0; p0 < ncomb; p0 += 32) {
+      int p = p0 + lane;
+      bool valid = false;
+      int i1 = 0, l1 = 0;
+      if (p < ncomb) {
+        i1 = p / nk; l1 = p - i1 * nk;
+        double BOij0 = B.BO0[rowj + i1], BOkl0 = B.BO0[rowk + l1];
+        int i = B.lst[rowj + i1], l = B.lst[rowk + l1];
+        if ((BOij0 > CUTOF2_ESUB) && ((BOij0 * BOjk0) > CUTOF2_ESUB) && (i != k) && (BOkl0 > CUTOF2_ESUB) &&
+            (BOjk0 * BOkl0 > CUTOF2_ESUB) && (i != l) && (j != l) && ((BOij0 * (BOjk0 * BOjk0) * BOkl0) > MINBO0)) {
+          int ity = itype[i], lty = itype[l];
+          valid = ff.inxn4[(ity - 1) + ff.nso * ((jty - 1) + ff.nso * ((kty - 1) + ff.nso * (lty - 1)))] != 0;
         }
-        atomic_add3(f, NB, i, Fi[0], Fi[1], Fi[2]);
-        atomic_add3(f, NB, l, Fl[0], Fl[1], Fl[2]);
       }
-      cdk = warp_sum(cdk); cjk0 = warp_sum(cjk0); cjk1 = warp_sum(cjk1);
-#pragma unroll
-      for (int c = 0; c < 3; c++) fk[c] = warp_sum(fk[c]);
-      if (lane == 0 && (cdk != 0.0 || cjk0 != 0.0 || fk[0] != 0.0 || fk[1] != 0.0 || fk[2] != 0.0)) {
-        atomicAdd(&cdbnd[k], cdk);
-        atomicAdd(&B.cB0[rowj + k1], cjk0);
-        atomicAdd(&B.cB1[rowj + k1], cjk1);
-        atomic_add3(f, NB, k, fk[0], fk[1], fk[2]);
-      }
+      int w = warp_append(valid, counter, lane);
+      if (valid && w < cap) wl[w] = make_int2(j, k1 | (i1 << 8) | (l1 << 16));
     }
-    cdj = warp_sum(cdj);
+  }
+}
+
+// C4b: E4b evaluation (src/pot.F90:1083-1205), one thread per torsion i-j-k-l.
+__global__ void __launch_bounds__(128) k_e4b_eval(int nwork, const int2 *__restrict__ wl, const double4 *__restrict__ pq, int NB,
+                                                  const int *__restrict__ itype, const DevFF *__restrict__ ffp, Bonds B,
+                                                  const double *__restrict__ delta, double *__restrict__ cdbnd,
+                                                  double *__restrict__ f, double *__restrict__ acc) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  double part[2] = {0.0, 0.0};   // PE(8..9)
+  if (t < nwork) {
+    const DevFF &ff = *ffp;
+    const int2 w = wl[t];
+    const int j = w.x, k1 = w.y & 0xff, i1 = (w.y >> 8) & 0xff, l1 = (w.y >> 16) & 0xff;
+    const size_t rowj = (size_t)j * B.MAXN;
+    const int k = B.lst[rowj + k1];
+    const size_t rowk = (size_t)k * B.MAXN;
+    const int i = B.lst[rowj + i1], l = B.lst[rowk + l1];
+    const int ity = itype[i], jty = itype[j], kty = itype[k], lty = itype[l];
+    const int x = ff.inxn4[(ity - 1) + ff.nso * ((jty - 1) + ff.nso * ((kty - 1) + ff.nso * (lty - 1)))] - 1;
+    const double BOij = B.BO0[rowj + i1] - CUTOF2_ESUB, BOjk = B.BO0[rowj + k1] - CUTOF2_ESUB, BOkl = B.BO0[rowk + l1] - CUTOF2_ESUB;
+    const double BOpi_jk = B.BO2[rowj + k1];
+    const double delta_ang_jk = (delta[j] + ff.Val[jty - 1] - ff.Valangle[jty - 1]) + (delta[k] + ff.Val[kty - 1] - ff.Valangle[kty - 1]);
+    const double4 pi = pq[i], pj = pq[j], pk = pq[k], pl = pq[l];
+    double rij[3] = {pi.x - pj.x, pi.y - pj.y, pi.z - pj.z};
+    double rjk[3] = {pj.x - pk.x, pj.y - pk.y, pj.z - pk.z};
+    double rkl[3] = {pk.x - pl.x, pk.y - pl.y, pk.z - pl.z};
+    double nij = sqrt((rij[0] * rij[0] + rij[1] * rij[1]) + rij[2] * rij[2]);
+    double njk = sqrt((rjk[0] * rjk[0] + rjk[1] * rjk[1]) + rjk[2] * rjk[2]);
+    double nkl = sqrt((rkl[0] * rkl[0] + rkl[1] * rkl[1]) + rkl[2] * rkl[2]);
+    double cos_ijk = -((rij[0] * rjk[0] + rij[1] * rjk[1]) + rij[2] * rjk[2]) / (nij * njk);
+    if (cos_ijk > MAXANGLE) cos_ijk = MAXANGLE;
+    if (cos_ijk < MINANGLE) cos_ijk = MINANGLE;
+    double theta_ijk = acos(cos_ijk);
+    double sin_ijk = sin(theta_ijk);
+    double tan_ijk_i = 1.0 / tan(theta_ijk);
+    double crs_ijk[3];
+    double ncr1 = cross_n(rij, nij, rjk, njk, crs_ijk);
+    double pt1 = ff.ptor1[x], pt2 = ff.ptor2[x], pt3 = ff.ptor3[x], pt4 = ff.ptor4[x];
+    double V1 = ff.V1[x], V2 = ff.V2[x], V3 = ff.V3[x], pc1 = ff.pcot1[x], pc2 = ff.pcot2[x];
+    double et1 = exp(-pt2 * BOij), et2 = exp(-pt2 * BOjk), et3 = exp(-pt2 * BOkl);
+    double exp_tor3 = exp(-pt3 * delta_ang_jk), exp_tor4 = exp(pt4 * delta_ang_jk);
+    double exp_tor34_i = 1.0 / (1.0 + exp_tor3 + exp_tor4);
+    double fn10 = (1.0 - et1) * (1.0 - et2) * (1.0 - et3);
+    double fn11 = (2.0 + exp_tor3) * exp_tor34_i;
+    double fn12 = exp(-pc2 * ((BOij - 1.5) * (BOij - 1.5) + (BOjk - 1.5) * (BOjk - 1.5) + (BOkl - 1.5) * (BOkl - 1.5)));
+    double btb2 = 2.0 - BOpi_jk - fn11;
+    double exp_tor1 = exp(pt1 * (btb2 * btb2));
+    double cos_jkl = -((rjk[0] * rkl[0] + rjk[1] * rkl[1]) + rjk[2] * rkl[2]) / (njk * nkl);
+    if (cos_jkl > MAXANGLE) cos_jkl = MAXANGLE;
+    if (cos_jkl < MINANGLE) cos_jkl = MINANGLE;
+    double theta_jkl = acos(cos_jkl);
+    double sin_jkl = sin(theta_jkl);
+    double tan_jkl_i = 1.0 / tan(theta_jkl);
+    double crs_jkl[3];
+    double ncr2 = cross_n(rjk, njk, rkl, nkl, crs_jkl);
+    double cw = ((crs_ijk[0] * crs_jkl[0] + crs_ijk[1] * crs_jkl[1]) + crs_ijk[2] * crs_jkl[2]) / (ncr1 * ncr2);
+    if (cw > MAXANGLE) cw = MAXANGLE;
+    if (cw < MINANGLE) cw = MINANGLE;
+    double omega = acos(cw);
+    double cw_sqr = cw * cw;
+    double cos_2w = cos(2.0 * omega);
+    double c2 = 1.0 - cos_2w;
+    double c3 = 1.0 + cos(3.0 * omega);
+    double Vsum = V1 * (1.0 + cw) + V2 * exp_tor1 * c2 + V3 * c3;
+    double PEtors = 0.5 * fn10 * sin_ijk * sin_jkl * Vsum;
+    double PEconj = pc1 * fn12 * (1.0 + (cw_sqr - 1.0) * sin_ijk * sin_jkl);
+    part[0] = PEtors; part[1] = PEconj;
+    double CEtors1 = 0.5 * sin_ijk * sin_jkl * Vsum;
+    double CEtors2 = -pt1 * fn10 * sin_ijk * sin_jkl * V2 * exp_tor1 * btb2 * c2;
+    double dfn11 = (-pt3 * exp_tor3 + (pt3 * exp_tor3 - pt4 * exp_tor4) * (2.0 + exp_tor3) * exp_tor34_i) * exp_tor34_i;
+    double CEtors3 = CEtors2 * dfn11;
+    double CEtors4 = CEtors1 * pt2 * et1 * (1.0 - et2) * (1.0 - et3);
+    double CEtors5 = CEtors1 * pt2 * (1.0 - et1) * et2 * (1.0 - et3);
+    double CEtors6 = CEtors1 * pt2 * (1.0 - et1) * (1.0 - et2) * et3;
+    double cmn = -0.5 * fn10 * Vsum;
+    double CEtors7 = cmn * sin_jkl * tan_ijk_i;
+    double CEtors8 = cmn * sin_ijk * tan_jkl_i;
+    double CEtors9 = fn10 * sin_ijk * sin_jkl * (0.5 * V1 - 2.0 * V2 * exp_tor1 * cw + 1.5 * V3 * (cos_2w + 2.0 * cw_sqr));
+    double Cconj = -2.0 * pc2 * PEconj;
+    double CEconj4 = -pc1 * fn12 * (cw_sqr - 1.0) * tan_ijk_i * sin_jkl;
+    double CEconj5 = -pc1 * fn12 * (cw_sqr - 1.0) * sin_ijk * tan_jkl_i;
+    double CEconj6 = 2.0 * pc1 * fn12 * cw * sin_ijk * sin_jkl;
+    double Ca_ijk = CEconj4 + CEtors7, Ca_jkl = CEconj5 + CEtors8, Ca_ijkl = CEconj6 + CEtors9;
+    atomicAdd(&cdbnd[j], CEtors3);
+    atomicAdd(&cdbnd[k], CEtors3);
+    atomicAdd(&B.cB0[rowj + i1], Cconj * (BOij - 1.5) + CEtors4);   // ForceB on BO_ij
+    atomicAdd(&B.cB0[rowj + k1], Cconj * (BOjk - 1.5) + CEtors5);   // ForceBbo on BO_jk: coeff (b, b+t2, b) -> cf (b, t2, 0)
+    atomicAdd(&B.cB1[rowj + k1], CEtors2);
+    atomicAdd(&B.cB0[rowk + l1], Cconj * (BOkl - 1.5) + CEtors6);   // ForceB on BO_kl
+    // --- direction forces: ForceA3(i,j,k), ForceA3(j,k,l), ForceA4(i,j,k,l)  (src/pot.F90:1369-1521)
+    double f1[3], f2[3], g1[3], g2[3];
+    a3_forces(Ca_ijk, rij, nij, rjk, njk, f1, f2);
+    a3_forces(Ca_jkl, rjk, njk, rkl, nkl, g1, g2);
+    double C00 = nij * nij, C01 = (rij[0] * rjk[0] + rij[1] * rjk[1]) + rij[2] * rjk[2],
+           C02 = (rij[0] * rkl[0] + rij[1] * rkl[1]) + rij[2] * rkl[2];
+    double C11 = njk * njk, C12 = (rjk[0] * rkl[0] + rjk[1] * rkl[1]) + rjk[2] * rkl[2], C22 = nkl * nkl;
+    double D0 = C00 * C11 - C01 * C01, D1 = C11 * C22 - C12 * C12;
+    double coDD = Ca_ijkl * (1.0 / sqrt(D0 * D1));
+    double com = C01 * C12 - C02 * C11;
+    double Cwi0 = C11 / D0 * com, Cwi1 = -(C12 + C01 / D0 * com), Cwi2 = C11;
+    double Cwj0 = -(C12 + (C11 + C01) / D0 * com);
+    double Cwj1 = -(-C12 - 2 * C02 - C22 / D1 * com - (C00 + C01) / D0 * com);
+    double Cwj2 = -(C01 + C11 + C12 / D1 * com);
+    double Cwl0 = -C11, Cwl1 = (C01 + C12 / D1 * com), Cwl2 = -(C11 / D1 * com);
+    double Fi[3], Fj[3], Fk[3], Fl[3];
 #pragma unroll
-    for (int c = 0; c < 3; c++) fj[c] = warp_sum(fj[c]);
-    if (lane == 0 && (cdj != 0.0 || fj[0] != 0.0 || fj[1] != 0.0 || fj[2] != 0.0)) {
-      atomicAdd(&cdbnd[j], cdj);
-      atomic_add3(f, NB, j, fj[0], fj[1], fj[2]);
+    for (int c = 0; c < 3; c++) {
+      double hij = coDD * (Cwi0 * rij[c] + Cwi1 * rjk[c] + Cwi2 * rkl[c]);
+      double hjk = coDD * ((Cwj0 + Cwi0) * rij[c] + (Cwj1 + Cwi1) * rjk[c] + (Cwj2 + Cwi2) * rkl[c]);
+      double hkl = -coDD * (Cwl0 * rij[c] + Cwl1 * rjk[c] + Cwl2 * rkl[c]);
+      Fi[c] = f1[c] + hij;
+      Fj[c] = (-f1[c] + f2[c]) + g1[c] + (-hij + hjk);
+      Fk[c] = -f2[c] + (-g1[c] + g2[c]) + (-hjk + hkl);
+      Fl[c] = -g2[c] - hkl;
     }
+    atomic_add3(f, NB, i, Fi[0], Fi[1], Fi[2]);
+    atomic_add3(f, NB, j, Fj[0], Fj[1], Fj[2]);
+    atomic_add3(f, NB, k, Fk[0], Fk[1], Fk[2]);
+    atomic_add3(f, NB, l, Fl[0], Fl[1], Fl[2]);
   }
   block_add<2>(part, acc + ACC_PE + 8);
 }
@@ -754,24 +779,29 @@ __global__ void k_final0(int ntot, Bonds B, double *__restrict__ cdbnd) {
 }
 // pass 1: bond forces on atom i from every one of its bonds, and ccbnd(i) with the reference's order predicate
 __global__ void __launch_bounds__(128) k_final1(int ntot, const double *__restrict__ pos, int NB, Bonds B,
-                                                const double *__restrict__ cdbnd, double *__restrict__ ccbnd,
-                                                double *__restrict__ f) {
+                                                const double *__restrict__ cdbnd, const double *__restrict__ s3,
+                                                double *__restrict__ ccbnd, double *__restrict__ f) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ntot) return;
   const int n = B.cnt[i];
   if (n == 0) { ccbnd[i] = 0.0; return; }
   const double xi = pos[i], yi = pos[NB + i], zi = pos[2 * NB + i];
   const double cdi = cdbnd[i];
+  const double sdi = s3[i], s6i = s3[NB + i], s5i = s3[2 * (size_t)NB + i];   // E3b per-centre sums of atom i
   double fx = 0, fy = 0, fz = 0, cc = 0.0;
   for (int k = 0; k < n; k++) {
     size_t a = (size_t)i * B.MAXN + k;
     int j = B.lst[a];
     size_t b = (size_t)j * B.MAXN + B.idx[a];
     double cdj = cdbnd[j];
-    double c1e = B.cB0[a] + B.cB0[b];                  // energy-term coefficients of both orientations
-    double c2 = B.cB1[a] + B.cB1[b], c3 = B.cB2[a] + B.cB2[b];
+    double b0 = B.BO0[a];
+    double b02 = b0 * b0, b03 = b02 * b0, b07 = b03 * b03 * b0;
+    // E3b's ForceBbo over every neighbour of a centre (src/pot.F90:526-532): coeff = d1 + CEval6*BO^7 + (0,CEval5,CEval5)
+    double e3c1 = (sdi + s3[j]) + (s6i + s3[NB + j]) * b07, e3c23 = s5i + s3[2 * (size_t)NB + j];
+    double c1e = B.cB0[a] + B.cB0[b] + e3c1;           // energy-term coefficients of both orientations
+    double c2 = B.cB1[a] + B.cB1[b] + e3c23, c3 = B.cB2[a] + B.cB2[b] + e3c23;
     double c1 = c1e + cdi + cdj;                       // + ForceD(i) and ForceD(j) (src/pot.F90:1243-1245)
-    double b0 = B.BO0[a], b2 = B.BO2[a], b3 = B.BO3[a], A1 = B.A1[a], db = B.dBOp[a];
+    double b2 = B.BO2[a], b3 = B.BO3[a], A1 = B.A1[a], db = B.dBOp[a];
     double Cb = c1 * (B.A0[a] + b0 * A1) * db + c2 * b2 * (B.dln2[a] + A1 * db) + c3 * b3 * (B.dln3[a] + A1 * db);
     double dx = xi - pos[j], dy = yi - pos[NB + j], dz = zi - pos[2 * NB + j];
     fx -= Cb * dx; fy -= Cb * dy; fz -= Cb * dz;
@@ -894,9 +924,13 @@ inline int force_device(Ctx *c) {
   RXG_TRY(build_nbrlist(c));                                    // :33
   RXG_TRY(build_pairlist<false>(c));                            // :34
   Bonds B = make_bonds(c);
-  LAUNCH(c, k_boprim, cdiv(nt, 128), 128, 0, nt, c->pos, NB, c->itype, c->d_ff, B, c->deltap1, c->deltap2, c->cdbnd, c->ccbnd);
+  LAUNCH(c, k_boprim, cdiv(nt, 128), 128, 0, nt, c->pos, NB, c->itype, c->d_ff, B, c->deltap1, c->deltap2, c->cdbnd, c->ccbnd, c->s3);
   LAUNCH(c, k_bofull, cdiv(nt, 128), 128, 0, nt, c->itype, c->d_ff, B, c->deltap1, c->deltap2, c->delta);
   // ---- energy terms (src/pot.F90:49-57)
+  if (!c->wl) {   // first call: size the work lists from the resident count
+    c->wl_cap3 = 16LL * NB + 1024; c->wl_cap4 = 32LL * NB + 1024;
+    RXG_CUDA(cudaMalloc((void **)&c->wl, sizeof(int2) * (size_t)(c->wl_cap3 + c->wl_cap4)));
+  }
   double4 *pq = (double4 *)c->tmp;                 // scratch: {x,y,z,q} and {itype,gid}
   int2 *tg = (int2 *)(c->tmp + 4 * (size_t)NB);
   LAUNCH(c, k_pack_pq, cdiv(nt, 256), 256, 0, nt, c->pos, NB, c->q, c->itype, c->gid, pq, tg);
@@ -909,13 +943,34 @@ inline int force_device(Ctx *c) {
   if (!full_ok) LAUNCH(c, (k_enbond<true>), wgrid, 256, 0, n, c->rowptr, c->col, pq, tg, c->d_ff, c->f, NB, c->d_acc);
   LAUNCH(c, k_elnpr_prep, cdiv(nt, 256), 256, 0, nt, c->itype, c->d_ff, c->delta, c->nlp, c->dDlp, c->deltalp);
   LAUNCH(c, k_ebond_elnpr, cdiv(n, 128), 128, 0, n, c->itype, c->gid, c->d_ff, B, c->delta, c->dDlp, c->deltalp, c->d_acc);
-  const int wgrid128 = cdiv((long long)n * 32, 128);
-  LAUNCH(c, k_ehb, wgrid128, 128, 0, n, c->pos, NB, c->itype, c->d_ff, B, c->rowptr, c->col, c->f, c->d_acc);
-  LAUNCH(c, k_e3b, wgrid128, 128, 0, n, c->pos, NB, c->itype, c->d_ff, B, c->delta, c->nlp, c->dDlp, c->cdbnd, c->f, c->d_acc);
-  LAUNCH(c, k_e4b, wgrid128, 128, 0, n, c->pos, NB, c->itype, c->gid, c->d_ff, B, c->delta, c->cdbnd, c->f, c->d_acc);
+  LAUNCH(c, k_ehb, wgrid, 256, 0, n, pq, tg, NB, c->d_ff, B, c->rowptr, c->col, c->f, c->d_acc);
+  // angles and torsions: enumerate survivors of the cut-off tests, then evaluate one per thread
+  for (int attempt = 0; attempt < 2; attempt++) {
+    RXG_CUDA(cudaMemsetAsync(c->d_flag + 12, 0, 2 * sizeof(int), c->st));
+    int2 *wl3 = c->wl, *wl4 = c->wl + c->wl_cap3;
+    LAUNCH(c, k_e3b_enum, wgrid, 256, 0, n, c->itype, c->d_ff, B, c->sbo, wl3, (int)c->wl_cap3, c->d_flag + 12);
+    LAUNCH(c, k_e4b_enum, wgrid, 256, 0, n, c->itype, c->gid, c->d_ff, B, wl4, (int)c->wl_cap4, c->d_flag + 13);
+    RXG_CUDA(cudaMemcpyAsync(c->h_int + 12, c->d_flag + 12, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    RXG_CUDA(cudaStreamSynchronize(c->st));
+    const long long n3 = c->h_int[12], n4 = c->h_int[13];
+    if (n3 <= c->wl_cap3 && n4 <= c->wl_cap4) {
+      c->n_angles = n3; c->n_torsions = n4;
+      if (n3 > 0)
+        LAUNCH(c, k_e3b_eval, cdiv(n3, 128), 128, 0, (int)n3, wl3, pq, NB, c->itype, c->d_ff, B, c->delta, c->nlp, c->dDlp, c->sbo,
+               c->s3, c->f, c->d_acc);
+      if (n4 > 0)
+        LAUNCH(c, k_e4b_eval, cdiv(n4, 128), 128, 0, (int)n4, wl4, pq, NB, c->itype, c->d_ff, B, c->delta, c->cdbnd, c->f, c->d_acc);
+      break;
+    }
+    if (attempt == 1) { c->err = "angle/torsion work list overflow"; return RXG_ERR_STATE; }
+    if (c->wl) cudaFree(c->wl);   // grow and enumerate again (rare: first call of a denser system)
+    c->wl_cap3 = std::max(c->wl_cap3, n3 + n3 / 4 + 1024);
+    c->wl_cap4 = std::max(c->wl_cap4, n4 + n4 / 4 + 1024);
+    RXG_CUDA(cudaMalloc((void **)&c->wl, sizeof(int2) * (size_t)(c->wl_cap3 + c->wl_cap4)));
+  }
   // ---- ForceBondedTerms (src/pot.F90:63)
   LAUNCH(c, k_final0, cdiv(nt, 128), 128, 0, nt, B, c->cdbnd);
-  LAUNCH(c, k_final1, cdiv(nt, 128), 128, 0, nt, c->pos, NB, B, c->cdbnd, c->ccbnd, c->f);
+  LAUNCH(c, k_final1, cdiv(nt, 128), 128, 0, nt, c->pos, NB, B, c->cdbnd, c->s3, c->ccbnd, c->f);
   LAUNCH(c, k_final2, cdiv(nt, 128), 128, 0, nt, c->pos, NB, B, c->ccbnd, c->f);
   LAUNCH(c, k_virial, cdiv(nt, 256), 256, 0, nt, c->pos, c->f, NB, c->d_acc);   // :65-72
   // full-row ENbond puts both halves of a pair force on residents, so its virial is taken per pair inside the kernel

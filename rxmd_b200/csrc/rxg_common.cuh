@@ -1,6 +1,8 @@
 // rxg_common.cuh -- shared declarations of the B200 hot-path library (device context, helpers).
 #pragma once
 #include <cuda_runtime.h>
+#include <nccl.h>
+#include <algorithm>
 #include <cstdint>
 #include <cstdio>
 #include <string>
@@ -75,7 +77,20 @@ struct Ctx {
   double2 *qst = nullptr;   // {qs, qt}      (reference qs(:), qt(:))
   double4 *hsq = nullptr;   // {hs, ht, q, -} gather pack of get_hsh; .z mirrors q for residents+ghosts
   double2 *gst = nullptr;   // {gs, gt}
+  double2 *hst = nullptr;   // {hs, ht} of the single-pass CG (residents + ghosts)
+  double2 *tst = nullptr;   // {eta*hs + H.hs, same for t} per resident row
+  double2 *ust = nullptr;   // resident-weighted H.h sums (Est bookkeeping)
+  double2 *wst = nullptr;   // resident-weighted H.qs, H.qt
   int *itype = nullptr, *gid = nullptr, *frcindx = nullptr;
+  // ---- COPYATOMS bookkeeping -----------------------------------------------------------------------------
+  int *sel = nullptr;       // concatenated selection lists of the six stages of the last MODE_COPY
+  int sel_cap = 0, selptr[7] = {0, 0, 0, 0, 0, 0, 0};
+  int ns[7] = {0, 0, 0, 0, 0, 0, 0}, nr[7] = {0, 0, 0, 0, 0, 0, 0};   // atoms sent / received per stage (1..6)
+  double *sbuf[2] = {nullptr, nullptr}, *rbuf[2] = {nullptr, nullptr};
+  size_t xbuf_cap = 0;
+  long long moved = 0, nccl_msgs = 0;
+  ncclComm_t comm = nullptr;
+  int qeq_mode = 0;         // 0 single-pass CG (default), 1 two-pass (literal kernels), strict => literal serial order
   double *tmp = nullptr;    // [12*NB] scratch for MOVE compaction
   // ---- cells -------------------------------------------------------------------------------------------
   DevGrid gb, gnb;
@@ -96,6 +111,10 @@ struct Ctx {
   double *cdslot = nullptr;                        // cdbnd contributions addressed to the partner of a slot
   double *delta = nullptr, *deltap1 = nullptr, *deltap2 = nullptr, *nlp = nullptr, *dDlp = nullptr, *deltalp = nullptr;
   double *ccbnd = nullptr, *cdbnd = nullptr;
+  double *s3 = nullptr;      // [3*NB] per-centre sums of E3b (CE3body_d(1), CEval(6), CEval(5))
+  double2 *sbo = nullptr;    // [NB] {prod_SBO, sum_SBO1} per centre
+  int2 *wl = nullptr;        // angle / torsion work lists
+  long long wl_cap3 = 0, wl_cap4 = 0, n_angles = 0, n_torsions = 0;
   // ---- scalars ---------------------------------------------------------------------------------------------
   double *d_acc = nullptr;   // [64] reduction targets
   int *d_flag = nullptr;     // [8]  error / overflow flags
@@ -112,7 +131,8 @@ struct Ctx {
   std::vector<void *> ff_allocs, allocs;
   bool strict = false;      // RXG_STRICT_ORDER=1: serial-order, FMA-free CG for bit-level validation (small systems)
   double timers_ms[30] = {0};
-  cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+  cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm0 = nullptr, evm1 = nullptr, evk[4] = {nullptr, nullptr, nullptr, nullptr};
+  bool grad_pending = false;
   // ---- staging (pinned) ------------------------------------------------------------------------------------
   double *h_stage = nullptr;
   size_t h_stage_bytes = 0;

@@ -152,52 +152,86 @@ __global__ void k_sel_count(const double *__restrict__ coord, const double *__re
   if (threadIdx.x == 0) blk[blockIdx.x] = tot;
 }
 
-// MODE_COPY stage (store_atoms + self send_recv + append_atoms fused; src/comm.F90:367-528): ghost m is written
-// at copyptr(dflag-1)+rank in selection order (stable), shifted by -/+LBOX along the stage's axis.
-__global__ void k_copy_append(double *__restrict__ pos, int NB, double *__restrict__ atype, double *__restrict__ q,
-                              double2 *__restrict__ qst, double4 *__restrict__ hsq, int *__restrict__ frcindx, int n,
-                              int axis, bool upper, double lbox, double dr, double sft, const int *__restrict__ blkoff,
-                              int dst0, int cap) {
+// ---------------------------------------------------------------------------------------------------
+// COPYATOMS as pack -> exchange -> unpack.  Messages are SoA inside the buffer: field f of atom k at [f*cnt + k].
+// The sender keeps the list of local indices it selected in each of the six stages (`sel`); every later refresh
+// (MODE_QCOPY*) and the force copy-back (MODE_CPBK) reuse those lists, so only MODE_COPY / MODE_MOVE ever test
+// positions (the reference re-tests them on every call, src/comm.F90:273-288, with the same outcome).
+constexpr int NE_COPY = 9;    // x y z atype q qs qt hs ht           (reference ne=10 also carries frcindx)
+constexpr int NE_MOVE = 12;   // x y z vx vy vz atype q qs qt qsfp qsfv
+
+// store_atoms for MODE_COPY (src/comm.F90:406-447): stable selection, coordinate shift by -/+LBOX (xshift :531)
+__global__ void k_pack_copy(const double *__restrict__ pos, int NB, const double *__restrict__ atype,
+                            const double *__restrict__ q, const double2 *__restrict__ qst, const double4 *__restrict__ hsq,
+                            int n, int axis, bool upper, double lbox, double dr, double sft, const int *__restrict__ blkoff,
+                            int cnt, int *__restrict__ sel, double *__restrict__ buf) {
   int i = blockIdx.x * SCAN_BLK + threadIdx.x;
   int fl = 0;
-  if (i < n) fl = in_buffer(upper, lbox, dr, pos[axis * NB + i]);
+  if (i < n) fl = in_buffer(upper, lbox, dr, pos[(size_t)axis * NB + i]);
   int ex = block_excl_scan<int>(fl, nullptr);
   if (!fl) return;
-  int m = dst0 + blkoff[blockIdx.x] + ex;
-  if (m >= cap) return;   // capacity is checked on the host before the launch
-  double p[3] = {pos[i], pos[NB + i], pos[2 * NB + i]};
+  int k = blkoff[blockIdx.x] + ex;
+  if (k >= cnt) return;
+  sel[k] = i;
+  double p[3] = {pos[i], pos[NB + i], pos[2 * (size_t)NB + i]};
   p[axis] = add_rn(p[axis], sft);
-  pos[m] = p[0]; pos[NB + m] = p[1]; pos[2 * NB + m] = p[2];
-  atype[m] = atype[i];
-  q[m] = q[i];
-  qst[m] = qst[i];
-  hsq[m] = hsq[i];
-  frcindx[m] = i;
+  double2 s = qst[i];
+  double4 h = hsq[i];
+  size_t c = cnt;
+  buf[k] = p[0]; buf[c + k] = p[1]; buf[2 * c + k] = p[2];
+  buf[3 * c + k] = atype[i]; buf[4 * c + k] = q[i];
+  buf[5 * c + k] = s.x; buf[6 * c + k] = s.y; buf[7 * c + k] = h.x; buf[8 * c + k] = h.y;
+}
+// append_atoms for MODE_COPY (src/comm.F90:497-522)
+__global__ void k_unpack_copy(double *__restrict__ pos, int NB, double *__restrict__ atype, double *__restrict__ q,
+                              double2 *__restrict__ qst, double4 *__restrict__ hsq, int cnt, int dst0,
+                              const double *__restrict__ buf) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= cnt) return;
+  size_t c = cnt;
+  int m = dst0 + k;
+  pos[m] = buf[k]; pos[NB + m] = buf[c + k]; pos[2 * (size_t)NB + m] = buf[2 * c + k];
+  atype[m] = buf[3 * c + k];
+  double qq = buf[4 * c + k];
+  q[m] = qq;
+  qst[m] = make_double2(buf[5 * c + k], buf[6 * c + k]);
+  hsq[m] = make_double4(buf[7 * c + k], buf[8 * c + k], qq, 0.0);
 }
 
-// MODE_MOVE stage: atoms that left through the stage's face are re-appended with the shifted coordinate and the
-// original is marked dead (atype = -1), src/comm.F90:406-447.
-__global__ void k_move_append(double *__restrict__ pos, double *__restrict__ v, int NB, double *__restrict__ atype,
-                              double *__restrict__ q, double2 *__restrict__ qst, double *__restrict__ qsfp,
-                              double *__restrict__ qsfv, int n, int axis, bool upper, double lbox, double sft,
-                              const int *__restrict__ blkoff, int dst0, int cap) {
+// store_atoms for MODE_MOVE: atoms that left through the stage's face; the original is marked dead (atype=-1)
+__global__ void k_pack_move(const double *__restrict__ pos, const double *__restrict__ v, int NB, double *__restrict__ atype,
+                            const double *__restrict__ q, const double2 *__restrict__ qst, const double *__restrict__ qsfp,
+                            const double *__restrict__ qsfv, int n, int axis, bool upper, double lbox, double sft,
+                            const int *__restrict__ blkoff, int cnt, double *__restrict__ buf) {
   int i = blockIdx.x * SCAN_BLK + threadIdx.x;
   int fl = 0;
-  if (i < n) fl = in_buffer(upper, lbox, 0.0, pos[axis * NB + i]) && !(atype[i] < 0.0);
+  if (i < n) fl = in_buffer(upper, lbox, 0.0, pos[(size_t)axis * NB + i]) && !(atype[i] < 0.0);
   int ex = block_excl_scan<int>(fl, nullptr);
   if (!fl) return;
-  int m = dst0 + blkoff[blockIdx.x] + ex;
-  if (m >= cap) return;
-  double p[3] = {pos[i], pos[NB + i], pos[2 * NB + i]};
+  int k = blkoff[blockIdx.x] + ex;
+  if (k >= cnt) return;
+  double p[3] = {pos[i], pos[NB + i], pos[2 * (size_t)NB + i]};
   p[axis] = add_rn(p[axis], sft);
-  pos[m] = p[0]; pos[NB + m] = p[1]; pos[2 * NB + m] = p[2];
-  v[m] = v[i]; v[NB + m] = v[NB + i]; v[2 * NB + m] = v[2 * NB + i];
-  atype[m] = atype[i];
-  q[m] = q[i];
-  qst[m] = qst[i];
-  qsfp[m] = qsfp[i];
-  qsfv[m] = qsfv[i];
+  double2 s = qst[i];
+  size_t c = cnt;
+  buf[k] = p[0]; buf[c + k] = p[1]; buf[2 * c + k] = p[2];
+  buf[3 * c + k] = v[i]; buf[4 * c + k] = v[NB + i]; buf[5 * c + k] = v[2 * (size_t)NB + i];
+  buf[6 * c + k] = atype[i]; buf[7 * c + k] = q[i]; buf[8 * c + k] = s.x; buf[9 * c + k] = s.y;
+  buf[10 * c + k] = qsfp[i]; buf[11 * c + k] = qsfv[i];
   atype[i] = -1.0;
+}
+__global__ void k_unpack_move(double *__restrict__ pos, double *__restrict__ v, int NB, double *__restrict__ atype,
+                              double *__restrict__ q, double2 *__restrict__ qst, double *__restrict__ qsfp,
+                              double *__restrict__ qsfv, int cnt, int dst0, const double *__restrict__ buf) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= cnt) return;
+  size_t c = cnt;
+  int m = dst0 + k;
+  pos[m] = buf[k]; pos[NB + m] = buf[c + k]; pos[2 * (size_t)NB + m] = buf[2 * c + k];
+  v[m] = buf[3 * c + k]; v[NB + m] = buf[4 * c + k]; v[2 * (size_t)NB + m] = buf[5 * c + k];
+  atype[m] = buf[6 * c + k]; q[m] = buf[7 * c + k];
+  qst[m] = make_double2(buf[8 * c + k], buf[9 * c + k]);
+  qsfp[m] = buf[10 * c + k]; qsfv[m] = buf[11 * c + k];
 }
 
 // finalize(MODE_MOVE): stable removal of dead atoms, src/comm.F90:238-256
@@ -234,35 +268,46 @@ __global__ void k_move_restore(const double *__restrict__ in, int n, int NB, dou
   qsfv[m] = in[(size_t)11 * NB + m];
 }
 
-// MODE_QCOPY1 / MODE_QCOPY2 on one axis phase: ghosts [lo,hi) take the fresh values of their source atom
-// (src/comm.F90:183-207; the source index is what MODE_COPY recorded in frcindx)
-__global__ void k_qcopy1(double2 *__restrict__ qst, const int *__restrict__ frcindx, int lo, int hi) {
-  int m = lo + blockIdx.x * blockDim.x + threadIdx.x;
-  if (m < hi) qst[m] = qst[frcindx[m]];
+// value refreshes through the stored selection lists.  which: 1 = (qs,qt) [MODE_QCOPY1], 2 = (hs,ht,q) [MODE_QCOPY2],
+// 3 = (hs,ht) only (single-pass CG)
+__global__ void k_pack_vals(int which, const int *__restrict__ sel, int cnt, const double2 *__restrict__ qst,
+                            const double4 *__restrict__ hsq, const double2 *__restrict__ hst, double *__restrict__ buf) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= cnt) return;
+  int i = sel[k];
+  size_t c = cnt;
+  if (which == 1) { double2 s = qst[i]; buf[k] = s.x; buf[c + k] = s.y; }
+  else if (which == 2) { double4 h = hsq[i]; buf[k] = h.x; buf[c + k] = h.y; buf[2 * c + k] = h.z; }
+  else { double2 h = hst[i]; buf[k] = h.x; buf[c + k] = h.y; }
 }
-__global__ void k_qcopy2(double4 *__restrict__ hsq, double *__restrict__ q, const int *__restrict__ frcindx, int lo, int hi) {
-  int m = lo + blockIdx.x * blockDim.x + threadIdx.x;
-  if (m < hi) {
-    double4 t = hsq[frcindx[m]];
-    hsq[m] = t;
-    q[m] = t.z;
-  }
+__global__ void k_unpack_vals(int which, int cnt, int dst0, const double *__restrict__ buf, double2 *__restrict__ qst,
+                              double4 *__restrict__ hsq, double2 *__restrict__ hst, double *__restrict__ q) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= cnt) return;
+  size_t c = cnt;
+  int m = dst0 + k;
+  if (which == 1) qst[m] = make_double2(buf[k], buf[c + k]);
+  else if (which == 2) { double qq = buf[2 * c + k]; hsq[m] = make_double4(buf[k], buf[c + k], qq, 0.0); q[m] = qq; }
+  else hst[m] = make_double2(buf[k], buf[c + k]);
 }
-// MODE_CPBK on one axis phase: ghost forces are added back onto their source (src/comm.F90:385-396,474-482)
-__global__ void k_cpbk(double *__restrict__ f, int NB, const int *__restrict__ frcindx, int lo, int hi) {
-  int m = lo + blockIdx.x * blockDim.x + threadIdx.x;
-  if (m < hi) {
-    int s = frcindx[m];
-    atomicAdd(&f[s], f[m]);
-    atomicAdd(&f[NB + s], f[NB + m]);
-    atomicAdd(&f[2 * NB + s], f[2 * NB + m]);
-  }
+// MODE_CPBK: ghost forces of one stage travel back to the rank that owns the source atoms and are added there
+// (src/comm.F90:385-396, 474-482); the owner addresses them through its own selection list
+__global__ void k_pack_force(const double *__restrict__ f, int NB, int lo, int cnt, double *__restrict__ buf) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= cnt) return;
+  size_t c = cnt;
+  buf[k] = f[lo + k]; buf[c + k] = f[(size_t)NB + lo + k]; buf[2 * c + k] = f[2 * (size_t)NB + lo + k];
+}
+__global__ void k_unpack_force(double *__restrict__ f, int NB, const int *__restrict__ sel, int cnt, const double *__restrict__ buf) {
+  int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= cnt) return;
+  size_t c = cnt;
+  int s = sel[k];
+  atomicAdd(&f[s], buf[k]);
+  atomicAdd(&f[(size_t)NB + s], buf[c + k]);
+  atomicAdd(&f[2 * (size_t)NB + s], buf[2 * c + k]);
 }
 
-__global__ void k_iota(int *__restrict__ a, int n) {
-  int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < n) a[i] = i;
-}
 // itype = nint(atype), gtype = l2g(atype): src/pot.F90:37-42, src/main.F90:582-593
 __global__ void k_types(const double *__restrict__ atype, int n, int *__restrict__ itype, int *__restrict__ gid) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -282,123 +327,237 @@ inline int ensure_blk(Ctx *c, long long n) {
     if (c->d_blk) cudaFree(c->d_blk);
     if (c->d_blk64) cudaFree(c->d_blk64);
     c->nblk_cap = need * 2;
-    RXG_CUDA(cudaMalloc(&c->d_blk, sizeof(int) * c->nblk_cap));
+    RXG_CUDA(cudaMalloc(&c->d_blk, sizeof(int) * 2 * c->nblk_cap));   // two directions of an axis side by side
     RXG_CUDA(cudaMalloc(&c->d_blk64, sizeof(long long) * c->nblk_cap));
   }
   return RXG_OK;
 }
 
-// COPYATOMS(MODE_COPY, dr): src/comm.F90:2-100 for a rank whose six neighbours are itself (periodic self images)
+inline int ensure_xbuf(Ctx *c, size_t doubles_each) {
+  if (doubles_each > c->xbuf_cap) {
+    for (int k = 0; k < 2; k++) {
+      if (c->sbuf[k]) cudaFree(c->sbuf[k]);
+      if (c->rbuf[k]) cudaFree(c->rbuf[k]);
+    }
+    c->xbuf_cap = doubles_each + doubles_each / 4 + 1024;
+    for (int k = 0; k < 2; k++) {
+      RXG_CUDA(cudaMalloc(&c->sbuf[k], sizeof(double) * c->xbuf_cap));
+      RXG_CUDA(cudaMalloc(&c->rbuf[k], sizeof(double) * c->xbuf_cap));
+    }
+  }
+  return RXG_OK;
+}
+
+#define RXG_NCCL(call)                                                                                      \
+  do {                                                                                                      \
+    ncclResult_t r_ = (call);                                                                               \
+    if (r_ != ncclSuccess) {                                                                                \
+      c->err = std::string("NCCL error: ") + ncclGetErrorString(r_) + " at " + __FILE__ + ":" + std::to_string(__LINE__); \
+      return RXG_ERR_NCCL;                                                                                  \
+    }                                                                                                       \
+  } while (0)
+
+// send_recv (src/comm.F90:291-364) for the two stages of one axis at once.  Stage `up` (dflag 2a+1) sends to the
+// +neighbour and receives from the -neighbour; stage `dn` (dflag 2a+2) the other way round.  cs/cr are counts in
+// doubles.  Neighbour == myself is the reference's self-copy branch (:305-315); here it is a pointer alias.
+inline int exchange_axis(Ctx *c, int axis, const size_t cs[2], const size_t cr[2], double *recv[2], bool reverse) {
+  const int tp = c->box.target_node[2 * axis], tm = c->box.target_node[2 * axis + 1];
+  const int me = c->box.myid;
+  // forward: buffer 0 (upper selection) goes to +neighbour, buffer 1 to -neighbour.  reverse (CPBK): buffer 0 holds
+  // forces of stage-`up` ghosts, which came from the -neighbour, so it goes back there.
+  const int dst0 = reverse ? tm : tp, dst1 = reverse ? tp : tm;
+  const int src0 = reverse ? tp : tm, src1 = reverse ? tm : tp;
+  if (dst0 == me && dst1 == me) {
+    recv[0] = c->sbuf[0]; recv[1] = c->sbuf[1];
+    return RXG_OK;
+  }
+  if (!c->comm) { c->err = "rxg_comm_init was not called for a multi-rank decomposition"; return RXG_ERR_NCCL; }
+  recv[0] = c->rbuf[0]; recv[1] = c->rbuf[1];
+  RXG_NCCL(ncclGroupStart());
+  if (cs[0]) RXG_NCCL(ncclSend(c->sbuf[0], cs[0], ncclDouble, dst0, c->comm, c->st));
+  if (cr[0]) RXG_NCCL(ncclRecv(c->rbuf[0], cr[0], ncclDouble, src0, c->comm, c->st));
+  if (cs[1]) RXG_NCCL(ncclSend(c->sbuf[1], cs[1], ncclDouble, dst1, c->comm, c->st));
+  if (cr[1]) RXG_NCCL(ncclRecv(c->rbuf[1], cr[1], ncclDouble, src1, c->comm, c->st));
+  RXG_NCCL(ncclGroupEnd());
+  c->nccl_msgs += 4;
+  return RXG_OK;
+}
+
+// the receive counts of a MODE_COPY / MODE_MOVE axis phase (the reference probes the message size, :335-336)
+inline int exchange_counts(Ctx *c, int axis, const int ns[2], int nr[2]) {
+  const int tp = c->box.target_node[2 * axis], tm = c->box.target_node[2 * axis + 1];
+  const int me = c->box.myid;
+  if (tp == me && tm == me) { nr[0] = ns[0]; nr[1] = ns[1]; return RXG_OK; }
+  if (!c->comm) { c->err = "rxg_comm_init was not called for a multi-rank decomposition"; return RXG_ERR_NCCL; }
+  c->h_int[8] = ns[0]; c->h_int[9] = ns[1];
+  RXG_CUDA(cudaMemcpyAsync(c->d_flag + 8, c->h_int + 8, 2 * sizeof(int), cudaMemcpyHostToDevice, c->st));
+  RXG_NCCL(ncclGroupStart());
+  RXG_NCCL(ncclSend(c->d_flag + 8, 1, ncclInt, tp, c->comm, c->st));
+  RXG_NCCL(ncclRecv(c->d_flag + 10, 1, ncclInt, tm, c->comm, c->st));
+  RXG_NCCL(ncclSend(c->d_flag + 9, 1, ncclInt, tm, c->comm, c->st));
+  RXG_NCCL(ncclRecv(c->d_flag + 11, 1, ncclInt, tp, c->comm, c->st));
+  RXG_NCCL(ncclGroupEnd());
+  RXG_CUDA(cudaMemcpyAsync(c->h_int + 10, c->d_flag + 10, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+  RXG_CUDA(cudaStreamSynchronize(c->st));
+  nr[0] = c->h_int[10]; nr[1] = c->h_int[11];
+  return RXG_OK;
+}
+
+// selection + counts of both directions of one axis (one host sync)
+inline int select_axis(Ctx *c, int axis, int n, const double dr[3], int skip_dead, int ns[2]) {
+  ns[0] = ns[1] = 0;
+  if (n <= 0) return RXG_OK;
+  RXG_TRY(ensure_blk(c, n));
+  const int nblk = cdiv(n, SCAN_BLK);
+  for (int k = 0; k < 2; k++) {
+    int *blk = c->d_blk + (size_t)k * c->nblk_cap;
+    LAUNCH(c, k_sel_count, nblk, SCAN_BLK, 0, c->pos + (size_t)axis * c->NB, c->atype, n, k == 0, c->box.LBOX[axis], dr[axis], skip_dead, blk);
+    LAUNCH(c, k_scan_phase2<int>, 1, SCAN_BLK, 0, blk, nblk, c->d_flag + 4 + k);
+  }
+  RXG_CUDA(cudaMemcpyAsync(c->h_int + 4, c->d_flag + 4, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+  RXG_CUDA(cudaStreamSynchronize(c->st));
+  ns[0] = c->h_int[4]; ns[1] = c->h_int[5];
+  return RXG_OK;
+}
+
+// COPYATOMS(MODE_COPY, dr), src/comm.F90:2-100
 inline int halo_copy(Ctx *c, const double dr[3]) {
   const int NB = c->NB;
   BoxDev b = make_boxdev(c->box);
   c->cp[0] = c->natoms;
-  if (c->natoms > 0) {
-    LAUNCH(c, k_to_norm, cdiv(c->natoms, 256), 256, 0, c->pos, NB, c->natoms, b);
-    LAUNCH(c, k_iota, cdiv(c->natoms, 256), 256, 0, c->frcindx, c->natoms);
-  }
-  for (int d = 1; d <= 6; d++) {
-    const int axis = (d - 1) / 2;
-    const bool upper = (d % 2) == 1;
-    const int n = c->cp[h_cptridx[d]];
-    const double sft = upper ? -c->box.LBOX[axis] : c->box.LBOX[axis];
-    int ns = 0;
-    if (n > 0) {
-      RXG_TRY(ensure_blk(c, n));
-      int nblk = cdiv(n, SCAN_BLK);
-      LAUNCH(c, k_sel_count, nblk, SCAN_BLK, 0, c->pos + (size_t)axis * NB, c->atype, n, upper, c->box.LBOX[axis], dr[axis], 0, c->d_blk);
-      LAUNCH(c, k_scan_phase2<int>, 1, SCAN_BLK, 0, c->d_blk, nblk, c->d_flag + 4);
-      RXG_CUDA(cudaMemcpyAsync(c->h_int, c->d_flag + 4, sizeof(int), cudaMemcpyDeviceToHost, c->st));
-      RXG_CUDA(cudaStreamSynchronize(c->st));
-      ns = c->h_int[0];
-      if (c->cp[d - 1] + ns > NB) {
-        c->err = "ERROR: over capacity in append_atoms (NBUFFER)";
-        return RXG_ERR_NBUFFER;
-      }
-      if (ns > 0)
-        LAUNCH(c, k_copy_append, nblk, SCAN_BLK, 0, c->pos, NB, c->atype, c->q, c->qst, c->hsq, c->frcindx, n, axis, upper,
-               c->box.LBOX[axis], dr[axis], sft, c->d_blk, c->cp[d - 1], NB);
+  c->selptr[0] = 0;
+  if (c->natoms > 0) LAUNCH(c, k_to_norm, cdiv(c->natoms, 256), 256, 0, c->pos, NB, c->natoms, b);
+  for (int axis = 0; axis < 3; axis++) {
+    const int d0 = 2 * axis + 1, d1 = d0 + 1;
+    const int n = c->cp[h_cptridx[d0]];
+    int ns[2], nr[2];
+    RXG_TRY(select_axis(c, axis, n, dr, 0, ns));
+    if (c->selptr[d0 - 1] + ns[0] + ns[1] > c->sel_cap) { c->err = "ERROR: over capacity in store_atoms (selection lists)"; return RXG_ERR_NBUFFER; }
+    c->selptr[d0] = c->selptr[d0 - 1] + ns[0];
+    c->selptr[d1] = c->selptr[d0] + ns[1];
+    RXG_TRY(exchange_counts(c, axis, ns, nr));
+    size_t need = (size_t)NE_COPY * (size_t)std::max(std::max(ns[0], ns[1]), std::max(nr[0], nr[1]));
+    RXG_TRY(ensure_xbuf(c, need));
+    const int nblk = cdiv(n > 0 ? n : 1, SCAN_BLK);
+    for (int k = 0; k < 2; k++)
+      if (ns[k] > 0)
+        LAUNCH(c, k_pack_copy, nblk, SCAN_BLK, 0, c->pos, NB, c->atype, c->q, c->qst, c->hsq, n, axis, k == 0, c->box.LBOX[axis],
+               dr[axis], k == 0 ? -c->box.LBOX[axis] : c->box.LBOX[axis], c->d_blk + (size_t)k * c->nblk_cap, ns[k],
+               c->sel + c->selptr[d0 - 1 + k], c->sbuf[k]);
+    if (c->cp[d0 - 1] + nr[0] + nr[1] > NB) {   // src/comm.F90:467-472
+      c->err = "ERROR: over capacity in append_atoms; na+nr > NBUFFER " + std::to_string(c->cp[d0 - 1] + nr[0] + nr[1]) + " > " + std::to_string(NB);
+      return RXG_ERR_NBUFFER;
     }
-    c->cp[d] = c->cp[d - 1] + ns;
+    size_t cs[2] = {(size_t)NE_COPY * ns[0], (size_t)NE_COPY * ns[1]}, cr[2] = {(size_t)NE_COPY * nr[0], (size_t)NE_COPY * nr[1]};
+    double *rb[2];
+    RXG_TRY(exchange_axis(c, axis, cs, cr, rb, false));
+    c->cp[d0] = c->cp[d0 - 1] + nr[0];
+    c->cp[d1] = c->cp[d0] + nr[1];
+    for (int k = 0; k < 2; k++) {
+      c->ns[d0 + k] = ns[k]; c->nr[d0 + k] = nr[k];
+      if (nr[k] > 0)
+        LAUNCH(c, k_unpack_copy, cdiv(nr[k], 256), 256, 0, c->pos, NB, c->atype, c->q, c->qst, c->hsq, nr[k], c->cp[d0 - 1 + k], rb[k]);
+    }
   }
   if (c->cp[6] > 0) LAUNCH(c, k_to_real, cdiv(c->cp[6], 256), 256, 0, c->pos, NB, c->cp[6], b);
   return RXG_OK;
 }
 
-// COPYATOMS(MODE_QCOPY1|2): value refresh of the ghosts created by the last MODE_COPY (+ the position round trip)
-inline int halo_qcopy(Ctx *c, int which) {
-  BoxDev b = make_boxdev(c->box);
-  for (int ph = 0; ph < 3; ph++) {
-    int lo = c->cp[2 * ph], hi = c->cp[2 * ph + 2];
-    if (hi > lo) {
-      if (which == 1) LAUNCH(c, k_qcopy1, cdiv(hi - lo, 256), 256, 0, c->qst, c->frcindx, lo, hi);
-      else LAUNCH(c, k_qcopy2, cdiv(hi - lo, 256), 256, 0, c->hsq, c->q, c->frcindx, lo, hi);
-    }
+// COPYATOMS(MODE_QCOPY1|2) (+ which=3: hs,ht only).  `roundtrips` position round trips are applied at the end
+// (the reference does one per call, src/comm.F90:222-227,260-264)
+inline int halo_refresh(Ctx *c, int which, int roundtrips) {
+  const int nf = (which == 2) ? 3 : 2;
+  for (int axis = 0; axis < 3; axis++) {
+    const int d0 = 2 * axis + 1;
+    const int ns[2] = {c->ns[d0], c->ns[d0 + 1]}, nr[2] = {c->nr[d0], c->nr[d0 + 1]};
+    if (ns[0] + ns[1] + nr[0] + nr[1] == 0) continue;
+    RXG_TRY(ensure_xbuf(c, (size_t)nf * (size_t)std::max(std::max(ns[0], ns[1]), std::max(nr[0], nr[1]))));
+    for (int k = 0; k < 2; k++)
+      if (ns[k] > 0) LAUNCH(c, k_pack_vals, cdiv(ns[k], 256), 256, 0, which, c->sel + c->selptr[d0 - 1 + k], ns[k], c->qst, c->hsq, c->hst, c->sbuf[k]);
+    size_t cs[2] = {(size_t)nf * ns[0], (size_t)nf * ns[1]}, cr[2] = {(size_t)nf * nr[0], (size_t)nf * nr[1]};
+    double *rb[2];
+    RXG_TRY(exchange_axis(c, axis, cs, cr, rb, false));
+    for (int k = 0; k < 2; k++)
+      if (nr[k] > 0) LAUNCH(c, k_unpack_vals, cdiv(nr[k], 256), 256, 0, which, nr[k], c->cp[d0 - 1 + k], rb[k], c->qst, c->hsq, c->hst, c->q);
   }
-  if (c->cp[6] > 0) LAUNCH(c, k_roundtrip, cdiv(c->cp[6], 256), 256, 0, c->pos, c->NB, c->cp[6], b, 1);
+  if (roundtrips > 0 && c->cp[6] > 0)
+    LAUNCH(c, k_roundtrip, cdiv(c->cp[6], 256), 256, 0, c->pos, c->NB, c->cp[6], make_boxdev(c->box), roundtrips);
   return RXG_OK;
 }
+inline int halo_qcopy(Ctx *c, int which) { return halo_refresh(c, which, 1); }
 
-// COPYATOMS(MODE_CPBK): reverse order z, y, x
+// COPYATOMS(MODE_CPBK): stages in reverse order z, y, x (src/comm.F90:72-78)
 inline int halo_cpbk(Ctx *c) {
-  for (int ph = 2; ph >= 0; ph--) {
-    int lo = c->cp[2 * ph], hi = c->cp[2 * ph + 2];
-    if (hi > lo) LAUNCH(c, k_cpbk, cdiv(hi - lo, 256), 256, 0, c->f, c->NB, c->frcindx, lo, hi);
+  for (int axis = 2; axis >= 0; axis--) {
+    const int d0 = 2 * axis + 1;
+    // what I received as ghosts goes back (nr), what I had sent comes home (ns)
+    const int nback[2] = {c->nr[d0], c->nr[d0 + 1]}, nhome[2] = {c->ns[d0], c->ns[d0 + 1]};
+    if (nback[0] + nback[1] + nhome[0] + nhome[1] == 0) continue;
+    RXG_TRY(ensure_xbuf(c, (size_t)3 * (size_t)std::max(std::max(nback[0], nback[1]), std::max(nhome[0], nhome[1]))));
+    for (int k = 0; k < 2; k++)
+      if (nback[k] > 0) LAUNCH(c, k_pack_force, cdiv(nback[k], 256), 256, 0, c->f, c->NB, c->cp[d0 - 1 + k], nback[k], c->sbuf[k]);
+    size_t cs[2] = {(size_t)3 * nback[0], (size_t)3 * nback[1]}, cr[2] = {(size_t)3 * nhome[0], (size_t)3 * nhome[1]};
+    double *rb[2];
+    RXG_TRY(exchange_axis(c, axis, cs, cr, rb, true));
+    for (int k = 0; k < 2; k++)
+      if (nhome[k] > 0) LAUNCH(c, k_unpack_force, cdiv(nhome[k], 256), 256, 0, c->f, c->NB, c->sel + c->selptr[d0 - 1 + k], nhome[k], rb[k]);
   }
   return RXG_OK;
 }
 
-// COPYATOMS(MODE_MOVE, dr=0): migration; on one rank atoms that left the box re-enter through the opposite face
+// COPYATOMS(MODE_MOVE, dr=0): atom migration (src/comm.F90:151-171, 238-256)
 inline int halo_move(Ctx *c) {
   const int NB = c->NB;
   BoxDev b = make_boxdev(c->box);
+  const double zero[3] = {0.0, 0.0, 0.0};
   c->cp[0] = c->natoms;
   if (c->natoms > 0) LAUNCH(c, k_to_norm, cdiv(c->natoms, 256), 256, 0, c->pos, NB, c->natoms, b);
-  for (int d = 1; d <= 6; d++) {
-    const int axis = (d - 1) / 2;
-    const bool upper = (d % 2) == 1;
-    const int n = c->cp[h_cptridx[d]];
-    const double sft = upper ? -c->box.LBOX[axis] : c->box.LBOX[axis];
-    int ns = 0;
-    if (n > 0) {
-      RXG_TRY(ensure_blk(c, n));
-      int nblk = cdiv(n, SCAN_BLK);
-      LAUNCH(c, k_sel_count, nblk, SCAN_BLK, 0, c->pos + (size_t)axis * NB, c->atype, n, upper, c->box.LBOX[axis], 0.0, 1, c->d_blk);
-      LAUNCH(c, k_scan_phase2<int>, 1, SCAN_BLK, 0, c->d_blk, nblk, c->d_flag + 4);
-      RXG_CUDA(cudaMemcpyAsync(c->h_int, c->d_flag + 4, sizeof(int), cudaMemcpyDeviceToHost, c->st));
-      RXG_CUDA(cudaStreamSynchronize(c->st));
-      ns = c->h_int[0];
-      if (c->cp[d - 1] + ns > NB) {
-        c->err = "ERROR: over capacity in append_atoms (NBUFFER)";
-        return RXG_ERR_NBUFFER;
-      }
-      if (ns > 0)
-        LAUNCH(c, k_move_append, nblk, SCAN_BLK, 0, c->pos, c->v, NB, c->atype, c->q, c->qst, c->qsfp, c->qsfv, n, axis, upper,
-               c->box.LBOX[axis], sft, c->d_blk, c->cp[d - 1], NB);
-    }
-    c->cp[d] = c->cp[d - 1] + ns;
+  for (int axis = 0; axis < 3; axis++) {
+    const int d0 = 2 * axis + 1, d1 = d0 + 1;
+    const int n = c->cp[h_cptridx[d0]];
+    int ns[2], nr[2];
+    RXG_TRY(select_axis(c, axis, n, zero, 1, ns));
+    RXG_TRY(exchange_counts(c, axis, ns, nr));
+    RXG_TRY(ensure_xbuf(c, (size_t)NE_MOVE * (size_t)std::max(std::max(ns[0], ns[1]), std::max(nr[0], nr[1]))));
+    const int nblk = cdiv(n > 0 ? n : 1, SCAN_BLK);
+    // the two selections of one axis are disjoint (an atom cannot leave through both faces), so marking the first
+    // direction's atoms dead before packing the second does not change the second's selection or its scan
+    for (int k = 0; k < 2; k++)
+      if (ns[k] > 0)
+        LAUNCH(c, k_pack_move, nblk, SCAN_BLK, 0, c->pos, c->v, NB, c->atype, c->q, c->qst, c->qsfp, c->qsfv, n, axis, k == 0,
+               c->box.LBOX[axis], k == 0 ? -c->box.LBOX[axis] : c->box.LBOX[axis], c->d_blk + (size_t)k * c->nblk_cap, ns[k], c->sbuf[k]);
+    if (c->cp[d0 - 1] + nr[0] + nr[1] > NB) { c->err = "ERROR: over capacity in append_atoms (NBUFFER)"; return RXG_ERR_NBUFFER; }
+    size_t cs[2] = {(size_t)NE_MOVE * ns[0], (size_t)NE_MOVE * ns[1]}, cr[2] = {(size_t)NE_MOVE * nr[0], (size_t)NE_MOVE * nr[1]};
+    double *rb[2];
+    RXG_TRY(exchange_axis(c, axis, cs, cr, rb, false));
+    c->cp[d0] = c->cp[d0 - 1] + nr[0];
+    c->cp[d1] = c->cp[d0] + nr[1];
+    for (int k = 0; k < 2; k++)
+      if (nr[k] > 0)
+        LAUNCH(c, k_unpack_move, cdiv(nr[k], 256), 256, 0, c->pos, c->v, NB, c->atype, c->q, c->qst, c->qsfp, c->qsfv, nr[k], c->cp[d0 - 1 + k], rb[k]);
+    c->moved += ns[0] + ns[1] + nr[0] + nr[1];
   }
   const int n6 = c->cp[6];
-  if (n6 > c->natoms) {   // something moved: compact (stable)
+  // compaction is needed whenever something was sent away or arrived (on one rank: whenever something wrapped)
+  if (c->moved > 0) {
     int *flag = c->gb.cell_of;   // scratch (rebuilt by the next binning)
-    int *dst = c->gb.order;
     RXG_TRY(ensure_blk(c, n6));
     LAUNCH(c, k_alive_flag, cdiv(n6, 256), 256, 0, c->atype, n6, flag);
-    // dst needs n6+1 entries; order[] has NB >= n6 entries; keep the total in d_flag[5]
     int nblk = cdiv(n6, SCAN_BLK);
     LAUNCH(c, k_scan_phase1<int>, nblk, SCAN_BLK, 0, flag, (long long)n6, c->d_blk);
     LAUNCH(c, k_scan_phase2<int>, 1, SCAN_BLK, 0, c->d_blk, nblk, c->d_flag + 5);
-    LAUNCH(c, k_scan_phase3<int>, nblk, SCAN_BLK, 0, flag, (long long)n6, c->d_blk, c->rowcnt /*>= NB+1 ints*/);
-    (void)dst;
+    LAUNCH(c, k_scan_phase3<int>, nblk, SCAN_BLK, 0, flag, (long long)n6, c->d_blk, c->rowcnt /* >= NB+1 ints */);
     LAUNCH(c, k_move_compact, cdiv(n6, 256), 256, 0, flag, c->rowcnt, n6, NB, c->pos, c->v, c->atype, c->q, c->qst, c->qsfp, c->qsfv, c->tmp);
     RXG_CUDA(cudaMemcpyAsync(c->h_int, c->d_flag + 5, sizeof(int), cudaMemcpyDeviceToHost, c->st));
     RXG_CUDA(cudaStreamSynchronize(c->st));
     int ni = c->h_int[0];
-    LAUNCH(c, k_move_restore, cdiv(ni, 256), 256, 0, c->tmp, ni, NB, c->pos, c->v, c->atype, c->q, c->qst, c->qsfp, c->qsfv);
+    if (ni > 0) LAUNCH(c, k_move_restore, cdiv(ni, 256), 256, 0, c->tmp, ni, NB, c->pos, c->v, c->atype, c->q, c->qst, c->qsfp, c->qsfv);
     c->natoms = ni;
+    c->moved = 0;
   }
   if (c->natoms > 0) LAUNCH(c, k_to_real, cdiv(c->natoms, 256), 256, 0, c->pos, NB, c->natoms, b);
   for (int d = 0; d <= 6; d++) c->cp[d] = c->natoms;
+  for (int d = 0; d <= 6; d++) { c->ns[d] = 0; c->nr[d] = 0; c->selptr[d] = 0; }
   return RXG_OK;
 }
 

@@ -71,13 +71,17 @@ __global__ void k_nbrindx(int ntot, int MAXN, const int *__restrict__ nbrcnt, co
 //   QEQ=true : qeq_initialize, real(4) dr2 < rctap2 and hessian = lerp of TBL_Eclmb_QEq in r^2 (src/qeq.F90:222-240)
 // FILL=false counts, FILL=true writes col (and val).
 template <bool QEQ, bool FILL>
-__global__ void __launch_bounds__(256) k_pairlist(DevGrid g, const DevFF *__restrict__ ffp, const int *__restrict__ runs,
-                                                  int nruns, int natoms, const double *__restrict__ pos, int NB,
+__global__ void __launch_bounds__(512) k_pairlist(DevGrid g, const DevFF *__restrict__ ffp, const int *__restrict__ runs,
+                                                  int nruns, int natoms, int ntot, const double *__restrict__ pos, int NB,
                                                   const int *__restrict__ itype, int *__restrict__ rowcnt,
                                                   const long long *__restrict__ rowptr, int *__restrict__ col,
                                                   double *__restrict__ val, int maxrow, int *__restrict__ ovf) {
   const int lane = threadIdx.x & 31;
-  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  // warps walk the atoms in cell order: the 8-16 warps of a CTA then scan (nearly) the same stencil runs, so the
+  // candidate records are served by L1 instead of L2
+  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (slot >= ntot) return;
+  const int i = rec_index(g.sorted[slot].w);
   if (i >= natoms) return;
   const DevFF &ff = *ffp;
   int cid = g.cell_of[i];
@@ -166,8 +170,9 @@ template <bool QEQ>
 int build_pairlist(Ctx *c) {
   const int n = c->natoms;
   RXG_CUDA(cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->st));
-  int grid = cdiv((long long)n * 32, 256);
-  LAUNCH(c, (k_pairlist<QEQ, false>), grid, 256, 0, c->gnb, c->d_ff, c->d_runs, c->nruns, n, c->pos, c->NB, c->itype, c->rowcnt,
+  RXG_CUDA(cudaMemsetAsync(c->rowcnt, 0, sizeof(int) * (size_t)(n + 1), c->st));
+  int grid = cdiv((long long)c->cp[6] * 32, 512);
+  LAUNCH(c, (k_pairlist<QEQ, false>), grid, 512, 0, c->gnb, c->d_ff, c->d_runs, c->nruns, n, c->cp[6], c->pos, c->NB, c->itype, c->rowcnt,
          c->rowptr, c->col, c->val, c->cfg.maxneighbs10, c->d_flag);
   RXG_TRY(ensure_blk(c, n));
   RXG_TRY(device_scan<long long>(c, c->rowcnt, n, c->rowptr, c->d_blk64, (long long *)(c->d_acc + 32)));
@@ -188,7 +193,7 @@ int build_pairlist(Ctx *c) {
   }
   c->nnz = nnz;
   c->list_is_qeq = QEQ;
-  LAUNCH(c, (k_pairlist<QEQ, true>), grid, 256, 0, c->gnb, c->d_ff, c->d_runs, c->nruns, n, c->pos, c->NB, c->itype, c->rowcnt,
+  LAUNCH(c, (k_pairlist<QEQ, true>), grid, 512, 0, c->gnb, c->d_ff, c->d_runs, c->nruns, n, c->cp[6], c->pos, c->NB, c->itype, c->rowcnt,
          c->rowptr, c->col, c->val, c->cfg.maxneighbs10, c->d_flag);
   return RXG_OK;
 }
@@ -316,6 +321,105 @@ __global__ void __launch_bounds__(256) k_hsh(int natoms, const long long *__rest
   block_accumulate<5>(part, acc + 0);
 }
 
+
+
+// ---------------------------------------------------------------------------------------------------
+// Single-pass CG (default).  The reference does two sparse products per iteration, H.(hs,ht) in get_hsh and
+// H.(qs,qt) in get_gradient (src/qeq.F90:105,157).  Because qs_new = qs + lmin*hs, the second product is
+// H.qs_old + lmin*H.hs, so the gradient follows from the first product: gs_new = gs - lmin_s*(eta*hs + H.hs).
+// One matrix stream per iteration instead of two; identical in exact arithmetic (round-off: see DESIGN.md "QEq").
+// Est (src/qeq.F90:296-306) needs sum_j w_ij H_ij q_j with w = 2 for resident j, 1 for ghost j; it is
+// carried the same way in wst = resident-weighted H.(qs,qt), with q = qs - mu*qt.
+template <bool INIT>
+__global__ void __launch_bounds__(256) k_spmv1(int natoms, const long long *__restrict__ rowptr, const int *__restrict__ col,
+                                               const double *__restrict__ val, const double2 *__restrict__ x,
+                                               const double2 *__restrict__ qst, const double *__restrict__ q,
+                                               double2 *__restrict__ gst, double2 *__restrict__ tst,
+                                               double2 *__restrict__ ust, double2 *__restrict__ wst,
+                                               const int *__restrict__ itype, const DevFF *__restrict__ ffp,
+                                               double *__restrict__ acc) {
+  const int lane = threadIdx.x & 31;
+  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  double part[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  if (i < natoms) {
+    long long s = rowptr[i], e = rowptr[i + 1];
+    double a = 0.0, b = 0.0, ga = 0.0, gb = 0.0;
+    for (long long k = s + lane; k < e; k += 32) {
+      double h = __ldcs(val + k);
+      int j = __ldcs(col + k);
+      double2 v = x[j];
+      double pa = h * v.x, pb = h * v.y;
+      a += pa; b += pb;
+      if (j >= natoms) { ga += pa; gb += pb; }
+    }
+    a = warp_sum(a); b = warp_sum(b); ga = warp_sum(ga); gb = warp_sum(gb);
+    if (lane == 0) {
+      int t = itype[i] - 1;
+      double eta = ffp->eta[t], chi = ffp->chi[t];
+      double2 me = x[i];
+      if (INIT) {
+        double g1 = sub_rn(sub_rn(-chi, mul_rn(eta, me.x)), a);
+        double g2 = sub_rn(sub_rn(-1.0, mul_rn(eta, me.y)), b);
+        gst[i] = make_double2(g1, g2);
+        wst[i] = make_double2(2.0 * a - ga, 2.0 * b - gb);
+        part[0] = g1 * g1; part[1] = g2 * g2;
+      } else {
+        double ts = eta * me.x + a, tt = eta * me.y + b;
+        tst[i] = make_double2(ts, tt);
+        ust[i] = make_double2(2.0 * a - ga, 2.0 * b - gb);
+        double2 g = gst[i], w = wst[i];
+        double mu = acc[11], qi = q[i];
+        part[0] = chi * qi + 0.5 * eta * qi * qi + 0.5 * qi * (w.x - mu * w.y);
+        part[1] = ts * me.x; part[2] = tt * me.y; part[3] = g.x * me.x; part[4] = g.y * me.y;
+      }
+    }
+  }
+  if (INIT) { double p2[2] = {part[0], part[1]}; block_accumulate<2>(p2, acc + 7); }
+  else block_accumulate<5>(part, acc + 0);
+}
+__global__ void k_roll_g(double *__restrict__ acc) {
+  acc[9] = acc[7]; acc[10] = acc[8];
+  acc[5] = 0.0; acc[6] = 0.0; acc[7] = 0.0; acc[8] = 0.0;
+}
+// qs,qt step (src/qeq.F90:136-137) + gradient / Est-bookkeeping recurrences + partial sums (sum qs, sum qt, g.g)
+__global__ void __launch_bounds__(256) k_cg_update1(int natoms, float lmin_s, float lmin_t, const double2 *__restrict__ hst,
+                                                    const double2 *__restrict__ tst, const double2 *__restrict__ ust,
+                                                    double2 *__restrict__ qst, double2 *__restrict__ gst,
+                                                    double2 *__restrict__ wst, double *__restrict__ acc) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double part[4] = {0.0, 0.0, 0.0, 0.0};
+  if (i < natoms) {
+    const double ls = (double)lmin_s, lt = (double)lmin_t;   // real(4) lmin promoted, SURVEY Q3
+    double2 h = hst[i], x = qst[i], g = gst[i], t = tst[i], u = ust[i], w = wst[i];
+    x.x = add_rn(x.x, mul_rn(ls, h.x));
+    x.y = add_rn(x.y, mul_rn(lt, h.y));
+    g.x = sub_rn(g.x, mul_rn(ls, t.x));
+    g.y = sub_rn(g.y, mul_rn(lt, t.y));
+    w.x = add_rn(w.x, mul_rn(ls, u.x));
+    w.y = add_rn(w.y, mul_rn(lt, u.y));
+    qst[i] = x; gst[i] = g; wst[i] = w;
+    part[0] = x.x; part[1] = x.y; part[2] = g.x * g.x; part[3] = g.y * g.y;
+  }
+  block_accumulate<4>(part, acc + 5);
+}
+// mu, q = qs - mu*qt (src/qeq.F90:147-150) and the Fletcher-Reeves direction update (:160-161)
+__global__ void k_cg_update2(int natoms, const double2 *__restrict__ qst, const double2 *__restrict__ gst,
+                             double2 *__restrict__ hst, double *__restrict__ q, double *__restrict__ acc) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double mu = acc[5] / acc[6];
+  if (i == 0) acc[11] = mu;
+  if (i >= natoms) return;
+  double bs = acc[7] / acc[9], bt = acc[8] / acc[10];
+  double2 x = qst[i], g = gst[i], h = hst[i];
+  q[i] = sub_rn(x.x, mul_rn(mu, x.y));
+  h.x = add_rn(g.x, mul_rn(bs, h.x));
+  h.y = add_rn(g.y, mul_rn(bt, h.y));
+  hst[i] = h;
+}
+__global__ void k_h_from_g2(int natoms, const double2 *__restrict__ gst, double2 *__restrict__ hst) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < natoms) hst[i] = gst[i];
+}
 
 // ---------------------------------------------------------------------------------------------------
 // STRICT-ORDER validation path (RXG_STRICT_ORDER=1): the same CG with every sum taken in the reference's serial

@@ -47,6 +47,7 @@ def load_library():
     L.rxg_set_forcefield.argtypes = [vp, C.POINTER(RxgFF)]
     L.rxg_set_box.argtypes = [vp, C.POINTER(RxgBox)]
     L.rxg_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
+    L.rxg_comm_unique_id.argtypes = [vp]
     L.rxg_destroy.argtypes = [vp]
     L.rxg_last_error.argtypes = [vp]
     L.rxg_last_error.restype = C.c_char_p
@@ -107,6 +108,21 @@ class Engine:
             self.L.rxg_destroy(self.h)
             self.h = C.c_void_p()
 
+    def comm_init_torch(self, dist):
+        """NCCL communicator of the library: rank 0 creates the 128-byte ncclUniqueId, torch.distributed (any backend)
+        broadcasts it -- the job MPI_Bcast does in the Fortran shim."""
+        import torch
+        nranks, rank = dist.get_world_size(), dist.get_rank()
+        buf = (C.c_ubyte * 128)()
+        if rank == 0:
+            self._chk(self.L.rxg_comm_unique_id(C.cast(buf, C.c_void_p)))
+        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+        t = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device=dev)
+        dist.broadcast(t, src=0)
+        raw = bytes(t.cpu().tolist())
+        buf2 = (C.c_ubyte * 128).from_buffer_copy(raw)
+        self._chk(self.L.rxg_comm_init(self.h, rank, nranks, C.cast(buf2, C.c_void_p)))
+
     def host_arrays(self, rank_state):
         """Allocate the host's NBUFFER-capacity arrays (src/init.F90:110-114) from a rank's resident atoms."""
         nb = self.NBUFFER
@@ -166,6 +182,12 @@ class Engine:
         self._chk(self.L.rxg_md_observe(self.h, _dp(self.PE), C.byref(ke), C.byref(qs), C.byref(it), _dp(astr)))
         self.nstep_qeq = it.value
         return self.PE.copy(), ke.value, qs.value, it.value
+
+    def natoms_resident(self):
+        return int(self.fetch("copyptr")[0])
+
+    def fetch_copyptr(self):
+        return self.fetch("copyptr")
 
     def timers(self):
         t = np.zeros(30)

@@ -46,7 +46,7 @@ def read_xyz(path, atom_names, real_coords=False):
     return types, pos, tuple(lat)
 
 
-def replicate(types0, pos0, lat, mc, vprocs, no_shift=False):
+def replicate(types0, pos0, lat, mc, vprocs, no_shift=False, displace=None):
     """init/geninit.F90:446-527.  Returns dict with per-rank arrays.
 
     out['ranks'][r] = dict(pos_local[n,3] (normalised, minus OBOX), atype[n] (double,
@@ -68,6 +68,11 @@ def replicate(types0, pos0, lat, mc, vprocs, no_shift=False):
     if not no_shift:
         pos1 -= pos1.min(axis=0)
     pos1 = np.fmod(pos1, 1.0) + 1e-9
+    if displace is not None:
+        # synthetic thermal disorder (not part of geninit): `displace` = [ntot,3] normalised offsets; wrap back into [0,1)
+        pos1 = pos1 + displace(ntot)
+        pos1 = pos1 - np.floor(pos1)
+        pos1[pos1 >= 1.0] = 0.0
     vp = np.asarray(vprocs, dtype=np.int64)
     cell = (pos1 * vp).astype(np.int64)
     sid = cell[:, 0] + cell[:, 1] * vp[0] + cell[:, 2] * vp[0] * vp[1]

@@ -58,7 +58,13 @@ def build_system(xyz_path, ffield_path, mc=(1, 1, 1), vprocs=(1, 1, 1), isLG=Fal
                  displace_sigma=0.0, seed=20261017):
     ff = read_ffield(ffield_path, isLG=isLG)
     types0, pos0, lat0 = read_xyz(xyz_path, ff.atmname, real_coords=real_coords)
-    gen = replicate(types0, pos0, lat0, mc, vprocs)
+    displace = None
+    if displace_sigma > 0.0:
+        rng0 = np.random.default_rng(seed)
+        Hbig = S.get_box_params(lat0[0] * mc[0], lat0[1] * mc[1], lat0[2] * mc[2], lat0[3], lat0[4], lat0[5])
+        Hbig_i = np.linalg.inv(Hbig)
+        displace = lambda n: rng0.normal(0.0, displace_sigma, (n, 3)) @ Hbig_i.T
+    gen = replicate(types0, pos0, lat0, mc, vprocs, displace=displace)
     lattice = gen["lattice"]
     rctap = S.RCTAP0
     CTap = S.taper(rctap)
@@ -71,7 +77,6 @@ def build_system(xyz_path, ffield_path, mc=(1, 1, 1), vprocs=(1, 1, 1), isLG=Fal
     pff = PackedFF(ff, rc2, tables, rctap, cutoff_vpar30)
     nprocs = int(np.prod(vprocs))
     boxes = [PackedBox(lattice, vprocs, r, maxrc, rctap) for r in range(nprocs)]
-    rng = np.random.default_rng(seed)
     ranks = []
     for r in range(nprocs):
         g = gen["ranks"][r]
@@ -82,8 +87,6 @@ def build_system(xyz_path, ffield_path, mc=(1, 1, 1), vprocs=(1, 1, 1), isLG=Fal
         pos = np.empty((3, len(rn)))
         for c in range(3):
             pos[c] = (H[c, 0] * rn[:, 0] + H[c, 1] * rn[:, 1]) + H[c, 2] * rn[:, 2]
-        if displace_sigma > 0.0:
-            pos += rng.normal(0.0, displace_sigma, pos.shape)
         n = len(rn)
         ranks.append(dict(atype=g["atype"].copy(), pos=np.ascontiguousarray(pos), v=np.zeros((3, n)), q=np.zeros(n)))
     return System(ff=ff, pff=pff, boxes=boxes, vprocs=tuple(vprocs), lattice=lattice, ranks=ranks,

@@ -32,7 +32,7 @@ def main():
     e = Engine(s, cfg)
     st = s.ranks[0]
     atype, pos, v, f, q = e.host_arrays(st)
-    if sigma > 0:   # wrap displaced atoms back into the box on both sides
+    if sigma > 0:   # exercise MODE_MOVE (displaced atoms are already wrapped by build_system)
         o.move()
         e.COPYATOMS(2, [0, 0, 0], atype, pos, v, f, q)
         n = e.NATOMS
