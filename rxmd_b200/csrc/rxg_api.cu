@@ -42,6 +42,7 @@ int setup_grid(Ctx *c, DevGrid &g, const int *cc, const double *cs, int L) {
   RXG_TRY(dalloc(c, &g.start, (size_t)g.ncell + 2));
   RXG_TRY(dalloc(c, &g.fill, (size_t)g.ncell + 1));
   RXG_TRY(dalloc(c, &g.order, c->NB));
+  RXG_TRY(dalloc(c, &g.slot_of, c->NB));
   RXG_TRY(dalloc(c, &g.sorted, c->NB));
   return RXG_OK;
 }
@@ -93,7 +94,7 @@ int allreduce_acc(Ctx *c, int first, int count) {
 // literal two-product CG of src/qeq.F90:86-166 (qeq_mode 1) and its serial-order variant (strict)
 int qeq_cg_literal(Ctx *c, int nmax, int *iters) {
   const int n = c->natoms;
-  const int rgrid = cdiv((long long)n * 32, 256);
+  const int rgrid = cdiv((long long)c->cp[6] * 32, 256);
   const bool strict = c->strict;
   double4 *rowbuf = (double4 *)c->tmp;
   RXG_TRY(halo_qcopy(c, 1));
@@ -109,11 +110,11 @@ int qeq_cg_literal(Ctx *c, int nmax, int *iters) {
   auto gradient = [&]() -> int {
     if (!strict) {
       cudaEventRecord(c->evk[2], c->st);
-      LAUNCH(c, k_gradient, rgrid, 256, 0, n, c->rowptr, c->col, c->val, c->qst, c->itype, c->d_ff, c->gst, c->d_acc);
+      LAUNCH(c, k_gradient, rgrid, 256, 0, c->gnb.order, c->cp[6], n, c->rowbeg, c->rowend, c->col, c->val, c->qst, c->itype, c->d_ff, c->gst, c->d_acc);
       cudaEventRecord(c->evk[3], c->st);
       c->grad_pending = true;
     } else {
-      LAUNCH(c, k_rows_strict_grad, cdiv(n, 64), 64, 0, n, c->rowptr, c->col, c->val, c->qst, c->itype, c->d_ff, c->gst);
+      LAUNCH(c, k_rows_strict_grad, cdiv(n, 64), 64, 0, c->gnb.order, n, c->rowbeg, c->rowend, c->col, c->val, c->qst, c->itype, c->d_ff, c->gst);
       LAUNCH(c, k_seq_reduce, 1, 1, 0, 2, n, rowbuf, c->hsq, c->gst, c->qst, c->d_acc);
     }
     return allreduce_acc(c, 7, 2);
@@ -127,10 +128,10 @@ int qeq_cg_literal(Ctx *c, int nmax, int *iters) {
     LAUNCH(c, k_clear_iter, 1, 1, 0, c->d_acc);
     if (!strict) {
       cudaEventRecord(c->evk[0], c->st);
-      LAUNCH(c, k_hsh, rgrid, 256, 0, n, c->rowptr, c->col, c->val, c->hsq, c->gst, c->itype, c->d_ff, c->d_acc);
+      LAUNCH(c, k_hsh, rgrid, 256, 0, c->gnb.order, c->cp[6], n, c->rowbeg, c->rowend, c->col, c->val, c->hsq, c->gst, c->itype, c->d_ff, c->d_acc);
       cudaEventRecord(c->evk[1], c->st);
     } else {
-      LAUNCH(c, k_rows_strict_hsh, cdiv(n, 64), 64, 0, n, c->rowptr, c->col, c->val, c->hsq, c->itype, c->d_ff, rowbuf);
+      LAUNCH(c, k_rows_strict_hsh, cdiv(n, 64), 64, 0, c->gnb.order, n, c->rowbeg, c->rowend, c->col, c->val, c->hsq, c->itype, c->d_ff, rowbuf);
       LAUNCH(c, k_seq_reduce, 1, 1, 0, 0, n, rowbuf, c->hsq, c->gst, c->qst, c->d_acc);
     }
     RXG_TRY(allreduce_acc(c, 0, 5));
@@ -166,20 +167,31 @@ int qeq_cg_literal(Ctx *c, int nmax, int *iters) {
 // single-pass CG (default): one sparse product per iteration, see rxg_lists_qeq.cuh
 int qeq_cg_single(Ctx *c, int nmax, int *iters) {
   const int n = c->natoms;
-  const int rgrid = cdiv((long long)n * 32, 256);
+  const int rgrid = cdiv((long long)c->cp[6] * 32, 256);
   RXG_TRY(halo_refresh(c, 1, 0));   // ghost qs,qt (MODE_QCOPY1, src/qeq.F90:86)
-  LAUNCH(c, (k_spmv1<true>), rgrid, 256, 0, n, c->rowptr, c->col, c->val, c->qst, c->qst, c->q, c->gst, c->tst, c->ust, c->wst,
-         c->itype, c->d_ff, c->d_acc);
+  LAUNCH(c, k_to_slots, cdiv(c->cp[6], 256), 256, 0, c->cp[6], c->gnb.order, c->qst, c->xs);
+  const int tgrid = cdiv(c->cp[6], SP_ROWS);
+  const bool tma = !(getenv("RXG_SPMV_NOTMA") && getenv("RXG_SPMV_NOTMA")[0] == '1');
+  if (tma)
+    LAUNCH(c, (k_spmv1_tma<true>), tgrid, SP_ROWS * 32, 0, c->gnb.order, c->cp[6], n, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->xs,
+           c->qst, c->q, c->gst, c->tst, c->ust, c->wst, c->itype, c->d_ff, c->d_acc);
+  else
+    LAUNCH(c, (k_spmv1<true>), rgrid, 256, 0, c->gnb.order, c->cp[6], n, c->rowbeg, c->rowend, c->col, c->val, c->xs, c->qst, c->q, c->gst, c->tst, c->ust, c->wst,
+           c->itype, c->d_ff, c->d_acc);
   RXG_TRY(allreduce_acc(c, 7, 2));
-  LAUNCH(c, k_h_from_g2, cdiv(n, 256), 256, 0, n, c->gst, c->hst);
+  LAUNCH(c, k_h_from_g2, cdiv(n, 256), 256, 0, n, c->gst, c->hst, c->xs, c->gnb.slot_of);
   RXG_TRY(halo_refresh(c, 3, 0));   // ghost hs,ht (MODE_QCOPY2, :93)
   double GEst2 = 1e99;
   int it;
   for (it = 0; it < nmax; it++) {
     LAUNCH(c, k_clear_iter, 1, 1, 0, c->d_acc);
     cudaEventRecord(c->evk[0], c->st);
-    LAUNCH(c, (k_spmv1<false>), rgrid, 256, 0, n, c->rowptr, c->col, c->val, c->hst, c->qst, c->q, c->gst, c->tst, c->ust, c->wst,
-           c->itype, c->d_ff, c->d_acc);
+    if (tma)
+      LAUNCH(c, (k_spmv1_tma<false>), tgrid, SP_ROWS * 32, 0, c->gnb.order, c->cp[6], n, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->xs,
+             c->qst, c->q, c->gst, c->tst, c->ust, c->wst, c->itype, c->d_ff, c->d_acc);
+    else
+      LAUNCH(c, (k_spmv1<false>), rgrid, 256, 0, c->gnb.order, c->cp[6], n, c->rowbeg, c->rowend, c->col, c->val, c->xs, c->qst, c->q, c->gst, c->tst, c->ust, c->wst,
+             c->itype, c->d_ff, c->d_acc);
     cudaEventRecord(c->evk[1], c->st);
     RXG_TRY(allreduce_acc(c, 0, 5));
     RXG_CUDA(cudaMemcpyAsync(c->h_acc, c->d_acc, sizeof(double) * 5, cudaMemcpyDeviceToHost, c->st));
@@ -197,7 +209,7 @@ int qeq_cg_single(Ctx *c, int nmax, int *iters) {
     LAUNCH(c, k_roll_g, 1, 1, 0, c->d_acc);
     LAUNCH(c, k_cg_update1, cdiv(n, 256), 256, 0, n, lmin_s, lmin_t, c->hst, c->tst, c->ust, c->qst, c->gst, c->wst, c->d_acc);
     RXG_TRY(allreduce_acc(c, 5, 4));
-    LAUNCH(c, k_cg_update2, cdiv(n, 256), 256, 0, n, c->qst, c->gst, c->hst, c->q, c->d_acc);
+    LAUNCH(c, k_cg_update2, cdiv(n, 256), 256, 0, n, c->qst, c->gst, c->hst, c->xs, c->gnb.slot_of, c->q, c->d_acc);
     RXG_TRY(halo_refresh(c, 3, 0));
   }
   // the reference converts positions to normalised coordinates and back in every COPYATOMS call: QCOPY1 + QCOPY2
@@ -278,8 +290,10 @@ int rxg_create(const rxg_config *cfg, rxg_handle *out) {
   RXG_TRY(dalloc(c, &c->sel, NB)); c->sel_cap = (int)NB;
   RXG_TRY(dalloc(c, &c->itype, NB)); RXG_TRY(dalloc(c, &c->gid, NB)); RXG_TRY(dalloc(c, &c->frcindx, NB));
   RXG_TRY(dalloc(c, &c->tmp, 12 * NB));
+  RXG_TRY(dalloc(c, &c->xs, NB)); RXG_TRY(dalloc(c, &c->pqa, NB)); RXG_TRY(dalloc(c, &c->pqs, NB)); RXG_TRY(dalloc(c, &c->tgs, NB));
   RXG_TRY(dalloc(c, &c->nbrcnt, NB)); RXG_TRY(dalloc(c, &c->nbrlist, NS)); RXG_TRY(dalloc(c, &c->nbrindx, NS));
-  RXG_TRY(dalloc(c, &c->rowptr, NB + 2)); RXG_TRY(dalloc(c, &c->rowcnt, NB + 2));
+  RXG_TRY(dalloc(c, &c->rowoff, NB + 2)); RXG_TRY(dalloc(c, &c->rowbeg, NB + 2)); RXG_TRY(dalloc(c, &c->rowend, NB + 2));
+  RXG_TRY(dalloc(c, &c->rowcnt, NB + 2));
   for (int k = 0; k < 4; k++) RXG_TRY(dalloc(c, &c->BO[k], NS));
   for (int k = 0; k < 3; k++) { RXG_TRY(dalloc(c, &c->dln[k], NS)); RXG_TRY(dalloc(c, &c->cB[k], NS)); }
   RXG_TRY(dalloc(c, &c->dBOp, NS)); RXG_TRY(dalloc(c, &c->A0, NS)); RXG_TRY(dalloc(c, &c->A1, NS));
@@ -679,8 +693,9 @@ int rxg_debug_fetch(rxg_handle h, const char *name, void *out, long long cap, lo
   else if (s == "nbrcnt") dev(c->nbrcnt, n6, 4);
   else if (s == "nbrlist") dev(c->nbrlist, NS, 4);
   else if (s == "nbrindx") dev(c->nbrindx, NS, 4);
-  else if (s == "rowptr") dev(c->rowptr, nat + 1, 8);
-  else if (s == "col") dev(c->col, c->nnz, 4);
+  else if (s == "rowbeg") dev(c->rowbeg, nat, 8);
+  else if (s == "rowend") dev(c->rowend, nat, 8);
+  else if (s == "col") dev(c->col, c->nnz, 4);   // converted to atom indices below
   else if (s == "val") dev(c->val, c->nnz, 8);
   else if (s == "BO0") dev(c->BO[0], NS, 8);
   else if (s == "BO1") dev(c->BO[1], NS, 8);
@@ -707,6 +722,12 @@ int rxg_debug_fetch(rxg_handle h, const char *name, void *out, long long cap, lo
   if (out) {
     if (cap < bytes) return RXG_ERR_ARG;
     if (bytes) RXG_CUDA(cudaMemcpy(out, src, bytes, cudaMemcpyDeviceToHost));
+    if (s == "col" && cnt > 0) {   // slot | ghost-bit  ->  atom index, as the reference's nbplist holds it
+      std::vector<int> ord(n6);
+      RXG_CUDA(cudaMemcpy(ord.data(), c->gnb.order, sizeof(int) * n6, cudaMemcpyDeviceToHost));
+      int *o = (int *)out;
+      for (long long k = 0; k < cnt; k++) o[k] = ord[o[k] & 0x7fffffff];
+    }
   }
   return RXG_OK;
 }

@@ -159,39 +159,52 @@ __device__ __forceinline__ void block_add(double (&v)[NV], double *__restrict__ 
   block_accumulate<NV>(v, acc);
 }
 
-// pack {x,y,z,q} and {itype,gid} for the non-bonded gathers
+__device__ __forceinline__ void atomic_add3(double *__restrict__ f, int NB, int i, double x, double y, double z) {
+  atomicAdd(&f[i], x);
+  atomicAdd(&f[NB + i], y);
+  atomicAdd(&f[2 * NB + i], z);
+}
+
+// gather packs: {x,y,z,q} by atom (bonded kernels) and, in cell-sorted slot order, {x,y,z,q} + {itype,gid,atom}
+// (non-bonded kernels: the neighbours of a stencil run are contiguous slots)
 __global__ void k_pack_pq(int ntot, const double *__restrict__ pos, int NB, const double *__restrict__ q,
-                          const int *__restrict__ itype, const int *__restrict__ gid, double4 *__restrict__ pq,
-                          int2 *__restrict__ tg) {
+                          const int *__restrict__ itype, const int *__restrict__ gid, const int *__restrict__ slot_of,
+                          double4 *__restrict__ pqa, double4 *__restrict__ pqs, int4 *__restrict__ tgs) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ntot) return;
-  pq[i] = make_double4(pos[i], pos[NB + i], pos[2 * NB + i], q[i]);
-  tg[i] = make_int2(itype[i], gid[i]);
+  double4 p = make_double4(pos[i], pos[NB + i], pos[2 * (size_t)NB + i], q[i]);
+  pqa[i] = p;
+  int s = slot_of[i];
+  pqs[s] = p;
+  tgs[s] = make_int4(itype[i], gid[i], i, 0);
 }
 
 // C6: ENbond, src/pot.F90:676-781.  One warp per resident row of the 10 A list.
 // HALF=true is the literal form (gid(j)<gid(i), forces scattered to j); HALF=false evaluates the full row.
 template <bool HALF>
-__global__ void __launch_bounds__(256) k_enbond(int natoms, const long long *__restrict__ rowptr, const int *__restrict__ col,
-                                                const double4 *__restrict__ pq, const int2 *__restrict__ tg,
+__global__ void __launch_bounds__(256) k_enbond(int ntot, int natoms, const long long *__restrict__ rowbeg,
+                                                const long long *__restrict__ rowend, const int *__restrict__ col,
+                                                const double4 *__restrict__ pqs, const int4 *__restrict__ tgs,
                                                 const DevFF *__restrict__ ffp, double *__restrict__ f, int NB,
                                                 double *__restrict__ acc) {
   const int lane = threadIdx.x & 31;
-  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // rows are walked in cell order
   double part[3] = {0.0, 0.0, 0.0};
   double vir[6] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  int4 ti = make_int4(0, 0, natoms, 0);
+  if (slot < ntot) ti = tgs[slot];
+  const int i = ti.z;
   if (i < natoms) {
     const DevFF &ff = *ffp;
-    const double4 pi = pq[i];
-    const int2 ti = tg[i];
+    const double4 pi = pqs[slot];
     double fx = 0, fy = 0, fz = 0;
-    long long s = rowptr[i], e = rowptr[i + 1];
+    long long s = rowbeg[i], e = rowend[i];
     for (long long k = s + lane; k < e; k += 32) {
-      int j = __ldcs(col + k);
-      int2 tj = tg[j];
+      int js = __ldcs(col + k) & COL_MASK;
+      int4 tj = tgs[js];
       bool lower = tj.y < ti.y;
       if (HALF ? !lower : (tj.y == ti.y)) continue;
-      double4 pj = pq[j];
+      double4 pj = pqs[js];
       double dx = sub_rn(pi.x, pj.x), dy = sub_rn(pi.y, pj.y), dz = sub_rn(pi.z, pj.z);
       double dr2 = dist2_rn(dx, dy, dz);
       if (!(dr2 <= ff.rctap2)) continue;
@@ -215,17 +228,11 @@ __global__ void __launch_bounds__(256) k_enbond(int natoms, const long long *__r
         vir[0] += h * dx * dx; vir[1] += h * dy * dy; vir[2] += h * dz * dz;
         vir[3] += h * dy * dz; vir[4] += h * dz * dx; vir[5] += h * dx * dy;
       }
-      if (HALF) {
-        atomicAdd(&f[j], cc * dx);
-        atomicAdd(&f[NB + j], cc * dy);
-        atomicAdd(&f[2 * NB + j], cc * dz);
-      }
+      if (HALF) atomic_add3(f, NB, tj.z, cc * dx, cc * dy, cc * dz);
     }
     fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
     if (lane == 0) {
-      atomicAdd(&f[i], fx);
-      atomicAdd(&f[NB + i], fy);
-      atomicAdd(&f[2 * NB + i], fz);
+      atomic_add3(f, NB, i, fx, fy, fz);
       part[2] = CECHRGE * (ff.chi[ti.x - 1] * pi.w + 0.5 * ff.eta[ti.x - 1] * pi.w * pi.w);   // src/pot.F90:708
     }
   }
@@ -343,11 +350,6 @@ __device__ __forceinline__ void a3_forces(double coeff, const double *da0, doubl
   }
 }
 
-__device__ __forceinline__ void atomic_add3(double *__restrict__ f, int NB, int i, double x, double y, double z) {
-  atomicAdd(&f[i], x);
-  atomicAdd(&f[NB + i], y);
-  atomicAdd(&f[2 * NB + i], z);
-}
 
 // ---------------------------------------------------------------------------------------------------
 // Angles and torsions are evaluated in two steps: an ENUMERATION kernel applies the reference's cut-off tests
@@ -514,77 +516,91 @@ __global__ void __launch_bounds__(128) k_e3b_eval(int nwork, const int2 *__restr
   block_add<3>(part, acc + ACC_PE + 5);
 }
 
-// C5: Ehb, src/pot.F90:559-673.  One warp per resident i; for every donor-H bond the lanes scan i's 10 A row.
-__global__ void __launch_bounds__(256) k_ehb(int natoms, const double4 *__restrict__ pq, const int2 *__restrict__ tg, int NB,
-                                             const DevFF *__restrict__ ffp, Bonds B, const long long *__restrict__ rowptr,
-                                             const int *__restrict__ col, double *__restrict__ f, double *__restrict__ acc) {
+// C5a: Ehb enumeration: donor-H bonds (i, slot s) with jty == 2 and BO > MINBO0 (src/pot.F90:590-595).
+// hydrogen is hard-coded as atom type 2
+__global__ void k_ehb_enum(int natoms, const int *__restrict__ itype, const DevFF *__restrict__ ffp, Bonds B,
+                           int2 *__restrict__ wl, int cap, int *__restrict__ counter) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= natoms) return;
+  const DevFF &ff = *ffp;
+  const int ity = itype[i];
+  if (ity <= 0 || ff.nso < 2) return;
+  bool donor = false;   // any acceptor type with inxn3hb(ity, 2, kty) != 0 ?
+  for (int kt = 0; kt < ff.nso; kt++) donor |= ff.inxn3hb[(ity - 1) + ff.nso * (1 + ff.nso * kt)] != 0;
+  if (!donor) return;
+  const int n = B.cnt[i];
+  const size_t row = (size_t)i * B.MAXN;
+  for (int s = 0; s < n; s++) {
+    if (itype[B.lst[row + s]] == 2 && B.BO0[row + s] > MINBO0) {
+      int w = atomicAdd(counter, 1);
+      if (w < cap) wl[w] = make_int2(i, s);
+    }
+  }
+}
+// C5b: Ehb evaluation, src/pot.F90:597-661.  One warp per donor-H bond; the lanes scan i's 10 A row.
+__global__ void __launch_bounds__(256) k_ehb_eval(int nwork, const int2 *__restrict__ wl, const int *__restrict__ slot_of,
+                                                  const double4 *__restrict__ pqs, const int4 *__restrict__ tgs, int NB,
+                                                  const DevFF *__restrict__ ffp, Bonds B, const long long *__restrict__ rowbeg,
+                                                  const long long *__restrict__ rowend, const int *__restrict__ col,
+                                                  double *__restrict__ f, double *__restrict__ acc) {
   const int lane = threadIdx.x & 31;
-  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   double part[1] = {0.0};
-  if (i < natoms && tg[i].x > 0) {
+  if (t < nwork) {
     const DevFF &ff = *ffp;
-    const int ity = tg[i].x;
-    // can atom type ity be a donor at all?  (any acceptor type with inxn3hb(ity, H=2, kty) != 0)
-    bool donor = false;
-    for (int kt = 0; kt < ff.nso; kt++) donor |= ff.nso >= 2 && ff.inxn3hb[(ity - 1) + ff.nso * (1 + ff.nso * kt)] != 0;
-    const int n = donor ? B.cnt[i] : 0;
+    const int2 w = wl[t];
+    const int i = w.x, s = w.y;
     const size_t row = (size_t)i * B.MAXN;
-    const double4 pi = pq[i];
-    for (int s = 0; s < n; s++) {
-      int j = B.lst[row + s];
-      int jty = tg[j].x;
-      double bo = B.BO0[row + s];
-      if (!((jty == 2) && (bo > MINBO0))) continue;   // hydrogen is hard-coded as type 2
-      const double4 pj = pq[j];
-      double rij[3] = {pi.x - pj.x, pi.y - pj.y, pi.z - pj.z};
-      double nij = sqrt((rij[0] * rij[0] + rij[1] * rij[1]) + rij[2] * rij[2]);
-      double cb = 0.0, fi[3] = {0, 0, 0}, fj[3] = {0, 0, 0};
-      long long rs = rowptr[i], re = rowptr[i + 1];
-      for (long long kk = rs + lane; kk < re; kk += 32) {
-        int k = col[kk];
-        int kty = tg[k].x;
-        int inxnhb = ff.inxn3hb[(ity - 1) + ff.nso * ((jty - 1) + ff.nso * (kty - 1))];
-        if (!((j != k) && (i != k) && (inxnhb != 0))) continue;
-        const double4 pk = pq[k];
-        double rik2 = dist2_rn(sub_rn(pi.x, pk.x), sub_rn(pi.y, pk.y), sub_rn(pi.z, pk.z));
-        if (!(rik2 < RCHB2)) continue;
-        int x = inxnhb - 1;
-        double rjk[3] = {pj.x - pk.x, pj.y - pk.y, pj.z - pk.z};
-        double njk = sqrt((rjk[0] * rjk[0] + rjk[1] * rjk[1]) + rjk[2] * rjk[2]);
-        double cos_ijk = -((rij[0] * rjk[0] + rij[1] * rjk[1]) + rij[2] * rjk[2]) / (nij * njk);
-        if (cos_ijk > MAXANGLE) cos_ijk = MAXANGLE;
-        if (cos_ijk < MINANGLE) cos_ijk = MINANGLE;
-        double theta_ijk = acos(cos_ijk);
-        double sh = sin(0.5 * theta_ijk);
-        double s2 = sh * sh;
-        double sin_xhz4 = s2 * s2;
-        double cos_xhz1 = 1.0 - cos_ijk;
-        double r0 = ff.r0hb[x], p1 = ff.phb1[x], p2 = ff.phb2[x], p3 = ff.phb3[x];
-        double exp_hb2 = exp(-p2 * bo);
-        double exp_hb3 = exp(-p3 * (r0 / njk + njk / r0 - 2.0));
-        double PEhb = p1 * (1.0 - exp_hb2) * exp_hb3 * sin_xhz4;
-        part[0] += PEhb;
-        cb += p1 * p2 * exp_hb2 * exp_hb3 * sin_xhz4;
-        double CEhb2 = -0.5 * p1 * (1.0 - exp_hb2) * exp_hb3 * cos_xhz1;
-        double CEhb3 = -PEhb * p3 * (-r0 / (njk * njk) + 1.0 / r0) * (1.0 / njk);
-        double fij[3], fjk[3];
-        a3_forces(CEhb2, rij, nij, rjk, njk, fij, fjk);
-        double ff3[3] = {CEhb3 * rjk[0], CEhb3 * rjk[1], CEhb3 * rjk[2]};
+    const int j = B.lst[row + s];
+    const double bo = B.BO0[row + s];
+    const int si = slot_of[i], sj = slot_of[j];
+    const int ity = tgs[si].x, jty = 2;
+    const double4 pi = pqs[si], pj = pqs[sj];
+    double rij[3] = {pi.x - pj.x, pi.y - pj.y, pi.z - pj.z};
+    double nij = sqrt((rij[0] * rij[0] + rij[1] * rij[1]) + rij[2] * rij[2]);
+    double cb = 0.0, fi[3] = {0, 0, 0}, fj[3] = {0, 0, 0};
+    for (long long kk = rowbeg[i] + lane; kk < rowend[i]; kk += 32) {
+      int ks = col[kk] & COL_MASK;
+      int4 tk = tgs[ks];
+      int inxnhb = ff.inxn3hb[(ity - 1) + ff.nso * ((jty - 1) + ff.nso * (tk.x - 1))];
+      if (!((j != tk.z) && (i != tk.z) && (inxnhb != 0))) continue;
+      const double4 pk = pqs[ks];
+      double rik2 = dist2_rn(sub_rn(pi.x, pk.x), sub_rn(pi.y, pk.y), sub_rn(pi.z, pk.z));
+      if (!(rik2 < RCHB2)) continue;
+      int x = inxnhb - 1;
+      double rjk[3] = {pj.x - pk.x, pj.y - pk.y, pj.z - pk.z};
+      double njk = sqrt((rjk[0] * rjk[0] + rjk[1] * rjk[1]) + rjk[2] * rjk[2]);
+      double cos_ijk = -((rij[0] * rjk[0] + rij[1] * rjk[1]) + rij[2] * rjk[2]) / (nij * njk);
+      if (cos_ijk > MAXANGLE) cos_ijk = MAXANGLE;
+      if (cos_ijk < MINANGLE) cos_ijk = MINANGLE;
+      double cos_xhz1 = 1.0 - cos_ijk;
+      double s2 = 0.5 * cos_xhz1;          // sin^2(theta/2) = (1 - cos theta)/2 : the reference's acos/sin pair is not needed
+      double sin_xhz4 = s2 * s2;
+      double r0 = ff.r0hb[x], p1 = ff.phb1[x], p2 = ff.phb2[x], p3 = ff.phb3[x];
+      double exp_hb2 = exp(-p2 * bo);
+      double exp_hb3 = exp(-p3 * (r0 / njk + njk / r0 - 2.0));
+      double PEhb = p1 * (1.0 - exp_hb2) * exp_hb3 * sin_xhz4;
+      part[0] += PEhb;
+      cb += p1 * p2 * exp_hb2 * exp_hb3 * sin_xhz4;
+      double CEhb2 = -0.5 * p1 * (1.0 - exp_hb2) * exp_hb3 * cos_xhz1;
+      double CEhb3 = -PEhb * p3 * (-r0 / (njk * njk) + 1.0 / r0) * (1.0 / njk);
+      double fij[3], fjk[3];
+      a3_forces(CEhb2, rij, nij, rjk, njk, fij, fjk);
+      double ff3[3] = {CEhb3 * rjk[0], CEhb3 * rjk[1], CEhb3 * rjk[2]};
 #pragma unroll
-        for (int c = 0; c < 3; c++) {
-          fi[c] += fij[c];
-          fj[c] += -fij[c] + fjk[c] - ff3[c];
-        }
-        atomic_add3(f, NB, k, -fjk[0] + ff3[0], -fjk[1] + ff3[1], -fjk[2] + ff3[2]);
+      for (int c = 0; c < 3; c++) {
+        fi[c] += fij[c];
+        fj[c] += -fij[c] + fjk[c] - ff3[c];
       }
-      cb = warp_sum(cb);
+      atomic_add3(f, NB, tk.z, -fjk[0] + ff3[0], -fjk[1] + ff3[1], -fjk[2] + ff3[2]);
+    }
+    cb = warp_sum(cb);
 #pragma unroll
-      for (int c = 0; c < 3; c++) { fi[c] = warp_sum(fi[c]); fj[c] = warp_sum(fj[c]); }
-      if (lane == 0 && cb != 0.0) {
-        atomicAdd(&B.cB0[row + s], cb);   // ForceB(i,j1,...,CEhb(1))
-        atomic_add3(f, NB, i, fi[0], fi[1], fi[2]);
-        atomic_add3(f, NB, j, fj[0], fj[1], fj[2]);
-      }
+    for (int c = 0; c < 3; c++) { fi[c] = warp_sum(fi[c]); fj[c] = warp_sum(fj[c]); }
+    if (lane == 0 && cb != 0.0) {
+      atomicAdd(&B.cB0[row + s], cb);   // ForceB(i,j1,...,CEhb(1))
+      atomic_add3(f, NB, i, fi[0], fi[1], fi[2]);
+      atomic_add3(f, NB, j, fj[0], fj[1], fj[2]);
     }
   }
   block_add<1>(part, acc + ACC_PE + 10);
@@ -928,33 +944,36 @@ inline int force_device(Ctx *c) {
   LAUNCH(c, k_bofull, cdiv(nt, 128), 128, 0, nt, c->itype, c->d_ff, B, c->deltap1, c->deltap2, c->delta);
   // ---- energy terms (src/pot.F90:49-57)
   if (!c->wl) {   // first call: size the work lists from the resident count
-    c->wl_cap3 = 16LL * NB + 1024; c->wl_cap4 = 32LL * NB + 1024;
-    RXG_CUDA(cudaMalloc((void **)&c->wl, sizeof(int2) * (size_t)(c->wl_cap3 + c->wl_cap4)));
+    c->wl_cap3 = 16LL * NB + 1024; c->wl_cap4 = 32LL * NB + 1024; c->wl_caph = 2LL * NB + 1024;
+    RXG_CUDA(cudaMalloc((void **)&c->wl, sizeof(int2) * (size_t)(c->wl_cap3 + c->wl_cap4 + c->wl_caph)));
   }
-  double4 *pq = (double4 *)c->tmp;                 // scratch: {x,y,z,q} and {itype,gid}
-  int2 *tg = (int2 *)(c->tmp + 4 * (size_t)NB);
-  LAUNCH(c, k_pack_pq, cdiv(nt, 256), 256, 0, nt, c->pos, NB, c->q, c->itype, c->gid, pq, tg);
+  double4 *pq = c->pqa;
+  LAUNCH(c, k_pack_pq, cdiv(nt, 256), 256, 0, nt, c->pos, NB, c->q, c->itype, c->gid, c->gnb.slot_of, c->pqa, c->pqs, c->tgs);
   // the full-row form needs every partner's image inside this rank's halo: true when the FORCE halo >= rctap
   bool full_ok = true;
   const double lat[3] = {c->box.lata, c->box.latb, c->box.latc};
   for (int a = 0; a < 3; a++)
     if (dr[a] * lat[a] < c->ff.rctap) full_ok = false;
   const int wgrid = cdiv((long long)n * 32, 256);
-  if (!full_ok) LAUNCH(c, (k_enbond<true>), wgrid, 256, 0, n, c->rowptr, c->col, pq, tg, c->d_ff, c->f, NB, c->d_acc);
+  const int ogrid = cdiv((long long)nt * 32, 256);   // warps over cell-ordered slots (ghost slots exit at once)
+  if (!full_ok) LAUNCH(c, (k_enbond<true>), ogrid, 256, 0, nt, n, c->rowbeg, c->rowend, c->col, c->pqs, c->tgs, c->d_ff, c->f, NB, c->d_acc);
   LAUNCH(c, k_elnpr_prep, cdiv(nt, 256), 256, 0, nt, c->itype, c->d_ff, c->delta, c->nlp, c->dDlp, c->deltalp);
   LAUNCH(c, k_ebond_elnpr, cdiv(n, 128), 128, 0, n, c->itype, c->gid, c->d_ff, B, c->delta, c->dDlp, c->deltalp, c->d_acc);
-  LAUNCH(c, k_ehb, wgrid, 256, 0, n, pq, tg, NB, c->d_ff, B, c->rowptr, c->col, c->f, c->d_acc);
   // angles and torsions: enumerate survivors of the cut-off tests, then evaluate one per thread
   for (int attempt = 0; attempt < 2; attempt++) {
-    RXG_CUDA(cudaMemsetAsync(c->d_flag + 12, 0, 2 * sizeof(int), c->st));
-    int2 *wl3 = c->wl, *wl4 = c->wl + c->wl_cap3;
+    RXG_CUDA(cudaMemsetAsync(c->d_flag + 12, 0, 3 * sizeof(int), c->st));
+    int2 *wl3 = c->wl, *wl4 = c->wl + c->wl_cap3, *wlh = c->wl + c->wl_cap3 + c->wl_cap4;
+    LAUNCH(c, k_ehb_enum, cdiv(n, 128), 128, 0, n, c->itype, c->d_ff, B, wlh, (int)c->wl_caph, c->d_flag + 14);
     LAUNCH(c, k_e3b_enum, wgrid, 256, 0, n, c->itype, c->d_ff, B, c->sbo, wl3, (int)c->wl_cap3, c->d_flag + 12);
     LAUNCH(c, k_e4b_enum, wgrid, 256, 0, n, c->itype, c->gid, c->d_ff, B, wl4, (int)c->wl_cap4, c->d_flag + 13);
-    RXG_CUDA(cudaMemcpyAsync(c->h_int + 12, c->d_flag + 12, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    RXG_CUDA(cudaMemcpyAsync(c->h_int + 12, c->d_flag + 12, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
     RXG_CUDA(cudaStreamSynchronize(c->st));
-    const long long n3 = c->h_int[12], n4 = c->h_int[13];
-    if (n3 <= c->wl_cap3 && n4 <= c->wl_cap4) {
-      c->n_angles = n3; c->n_torsions = n4;
+    const long long n3 = c->h_int[12], n4 = c->h_int[13], nh = c->h_int[14];
+    if (n3 <= c->wl_cap3 && n4 <= c->wl_cap4 && nh <= c->wl_caph) {
+      c->n_angles = n3; c->n_torsions = n4; c->n_hbonds = nh;
+      if (nh > 0)
+        LAUNCH(c, k_ehb_eval, cdiv(nh * 32, 256), 256, 0, (int)nh, wlh, c->gnb.slot_of, c->pqs, c->tgs, NB, c->d_ff, B, c->rowbeg,
+               c->rowend, c->col, c->f, c->d_acc);
       if (n3 > 0)
         LAUNCH(c, k_e3b_eval, cdiv(n3, 128), 128, 0, (int)n3, wl3, pq, NB, c->itype, c->d_ff, B, c->delta, c->nlp, c->dDlp, c->sbo,
                c->s3, c->f, c->d_acc);
@@ -966,7 +985,8 @@ inline int force_device(Ctx *c) {
     if (c->wl) cudaFree(c->wl);   // grow and enumerate again (rare: first call of a denser system)
     c->wl_cap3 = std::max(c->wl_cap3, n3 + n3 / 4 + 1024);
     c->wl_cap4 = std::max(c->wl_cap4, n4 + n4 / 4 + 1024);
-    RXG_CUDA(cudaMalloc((void **)&c->wl, sizeof(int2) * (size_t)(c->wl_cap3 + c->wl_cap4)));
+    c->wl_caph = std::max(c->wl_caph, nh + nh / 4 + 1024);
+    RXG_CUDA(cudaMalloc((void **)&c->wl, sizeof(int2) * (size_t)(c->wl_cap3 + c->wl_cap4 + c->wl_caph)));
   }
   // ---- ForceBondedTerms (src/pot.F90:63)
   LAUNCH(c, k_final0, cdiv(nt, 128), 128, 0, nt, B, c->cdbnd);
@@ -974,7 +994,7 @@ inline int force_device(Ctx *c) {
   LAUNCH(c, k_final2, cdiv(nt, 128), 128, 0, nt, c->pos, NB, B, c->ccbnd, c->f);
   LAUNCH(c, k_virial, cdiv(nt, 256), 256, 0, nt, c->pos, c->f, NB, c->d_acc);   // :65-72
   // full-row ENbond puts both halves of a pair force on residents, so its virial is taken per pair inside the kernel
-  if (full_ok) LAUNCH(c, (k_enbond<false>), wgrid, 256, 0, n, c->rowptr, c->col, pq, tg, c->d_ff, c->f, NB, c->d_acc);
+  if (full_ok) LAUNCH(c, (k_enbond<false>), ogrid, 256, 0, nt, n, c->rowbeg, c->rowend, c->col, c->pqs, c->tgs, c->d_ff, c->f, NB, c->d_acc);
   RXG_TRY(halo_cpbk(c));                                                          // :74
   RXG_CUDA(cudaMemcpyAsync(c->h_acc + ACC_PE, c->d_acc + ACC_PE, sizeof(double) * 24, cudaMemcpyDeviceToHost, c->st));
   RXG_CUDA(cudaStreamSynchronize(c->st));

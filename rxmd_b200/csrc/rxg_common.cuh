@@ -55,6 +55,7 @@ struct DevGrid {
   int *cell_of;         // [NB] linear cell id of each atom (-1: atype==0, skipped like the reference)
   int *start;           // [ncell+1] exclusive prefix of the per-cell counts
   int *fill;            // [ncell] scratch
+  int *slot_of;         // [NB] inverse of `order`: slot of each atom in the cell-sorted sequence
   int *order;           // [NB] atom indices sorted by cell; inside a cell DESCENDING index (= the reference's
                         //      head-insertion order, so rows come out in the reference's own order)
   double4 *sorted;      // [NB] {x,y,z, bits(index | type<<32)} in `order` order
@@ -92,13 +93,18 @@ struct Ctx {
   ncclComm_t comm = nullptr;
   int qeq_mode = 0;         // 0 single-pass CG (default), 1 two-pass (literal kernels), strict => literal serial order
   double *tmp = nullptr;    // [12*NB] scratch for MOVE compaction
+  double2 *xs = nullptr;    // [NB] CG gather vector in CELL-SORTED order (slot space): {hs,ht} (or {qs,qt} at start)
+  double4 *pqa = nullptr;   // [NB] {x,y,z,q} by atom (bonded kernels)
+  double4 *pqs = nullptr;   // [NB] {x,y,z,q} by slot (non-bonded gathers)
+  int4 *tgs = nullptr;      // [NB] {itype, gid, atom index, -} by slot
   // ---- cells -------------------------------------------------------------------------------------------
   DevGrid gb, gnb;
   int *d_runs = nullptr;    // stencil runs {dx,dy,dzlo,dzhi}
   int nruns = 0;
   // ---- lists -------------------------------------------------------------------------------------------
   int *nbrcnt = nullptr, *nbrlist = nullptr, *nbrindx = nullptr;   // [NB], [NB*MAXN], [NB*MAXN]
-  long long *rowptr = nullptr;   // [NB+1] 10 A list, CSR over residents
+  long long *rowoff = nullptr;   // [NB+1] 10 A list: row offsets by CELL-ORDER slot (rows lie in HBM in cell order)
+  long long *rowbeg = nullptr, *rowend = nullptr;   // [NB] the same rows addressed by atom index
   int *rowcnt = nullptr;
   int *col = nullptr;            // [nnz_cap]
   double *val = nullptr;         // [nnz_cap] hessian (QEq list only)
@@ -114,7 +120,7 @@ struct Ctx {
   double *s3 = nullptr;      // [3*NB] per-centre sums of E3b (CE3body_d(1), CEval(6), CEval(5))
   double2 *sbo = nullptr;    // [NB] {prod_SBO, sum_SBO1} per centre
   int2 *wl = nullptr;        // angle / torsion work lists
-  long long wl_cap3 = 0, wl_cap4 = 0, n_angles = 0, n_torsions = 0;
+  long long wl_cap3 = 0, wl_cap4 = 0, wl_caph = 0, n_angles = 0, n_torsions = 0, n_hbonds = 0;
   // ---- scalars ---------------------------------------------------------------------------------------------
   double *d_acc = nullptr;   // [64] reduction targets
   int *d_flag = nullptr;     // [8]  error / overflow flags

@@ -281,14 +281,15 @@ __global__ void k_pack_vals(int which, const int *__restrict__ sel, int cnt, con
   else { double2 h = hst[i]; buf[k] = h.x; buf[c + k] = h.y; }
 }
 __global__ void k_unpack_vals(int which, int cnt, int dst0, const double *__restrict__ buf, double2 *__restrict__ qst,
-                              double4 *__restrict__ hsq, double2 *__restrict__ hst, double *__restrict__ q) {
+                              double4 *__restrict__ hsq, double2 *__restrict__ hst, double2 *__restrict__ xs,
+                              const int *__restrict__ slot_of, double *__restrict__ q) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= cnt) return;
   size_t c = cnt;
   int m = dst0 + k;
   if (which == 1) qst[m] = make_double2(buf[k], buf[c + k]);
   else if (which == 2) { double qq = buf[2 * c + k]; hsq[m] = make_double4(buf[k], buf[c + k], qq, 0.0); q[m] = qq; }
-  else hst[m] = make_double2(buf[k], buf[c + k]);
+  else { double2 v = make_double2(buf[k], buf[c + k]); hst[m] = v; xs[slot_of[m]] = v; }
 }
 // MODE_CPBK: ghost forces of one stage travel back to the rank that owns the source atoms and are added there
 // (src/comm.F90:385-396, 474-482); the owner addresses them through its own selection list
@@ -478,7 +479,7 @@ inline int halo_refresh(Ctx *c, int which, int roundtrips) {
     double *rb[2];
     RXG_TRY(exchange_axis(c, axis, cs, cr, rb, false));
     for (int k = 0; k < 2; k++)
-      if (nr[k] > 0) LAUNCH(c, k_unpack_vals, cdiv(nr[k], 256), 256, 0, which, nr[k], c->cp[d0 - 1 + k], rb[k], c->qst, c->hsq, c->hst, c->q);
+      if (nr[k] > 0) LAUNCH(c, k_unpack_vals, cdiv(nr[k], 256), 256, 0, which, nr[k], c->cp[d0 - 1 + k], rb[k], c->qst, c->hsq, c->hst, c->xs, c->gnb.slot_of, c->q);
   }
   if (roundtrips > 0 && c->cp[6] > 0)
     LAUNCH(c, k_roundtrip, cdiv(c->cp[6], 256), 256, 0, c->pos, c->NB, c->cp[6], make_boxdev(c->box), roundtrips);
@@ -606,6 +607,7 @@ __global__ void k_cell_finish(const double *__restrict__ pos, const int *__restr
   }
   for (int a = s; a < e; a++) {
     int i = g.order[a];
+    g.slot_of[i] = a;
     long long packed = (long long)(unsigned)i | ((long long)itype[i] << 32);
     g.sorted[a] = make_double4(pos[i], pos[NB + i], pos[2 * NB + i], __longlong_as_double(packed));
   }

@@ -66,84 +66,115 @@ __global__ void k_nbrindx(int ntot, int MAXN, const int *__restrict__ nbrcnt, co
 }
 
 // ---------------------------------------------------------------------------------------------------
-// A3 (+D1): 10 A pair list over the stencil runs; one warp per resident atom.
+// A3 (+D1): 10 A pair list over the stencil runs.  One warp per RESIDENT CELL: every stencil run is loaded once and
+// tested against all atoms of the cell (the cell's atoms sit in shared memory and are broadcast to the lanes).
 //   QEQ=false: GetNonbondingPairList, fp64 dr2 <= rctap2 (src/main.F90:456-458)
 //   QEQ=true : qeq_initialize, real(4) dr2 < rctap2 and hessian = lerp of TBL_Eclmb_QEq in r^2 (src/qeq.F90:222-240)
 // FILL=false counts, FILL=true writes col (and val).
+// Layout: rows lie in HBM in cell order (row of slot s starts at rowoff[s]); consumers address them by atom through
+// rowbeg[i] / rowend[i].  A column entry is the neighbour's SLOT in the cell-sorted sequence (so that gathers from
+// slot-ordered vectors are nearly contiguous), with bit 31 set when the neighbour is a ghost (Est weighting, Q3).
+// Inside a row the entries keep the reference's order: stencil cells in mesh order, descending index inside a cell.
+constexpr int PL_WARPS = 8, PL_MAXRUNS = 128;
+constexpr int COL_GHOST = (int)0x80000000, COL_MASK = 0x7fffffff;
 template <bool QEQ, bool FILL>
-__global__ void __launch_bounds__(512) k_pairlist(DevGrid g, const DevFF *__restrict__ ffp, const int *__restrict__ runs,
-                                                  int nruns, int natoms, int ntot, const double *__restrict__ pos, int NB,
-                                                  const int *__restrict__ itype, int *__restrict__ rowcnt,
-                                                  const long long *__restrict__ rowptr, int *__restrict__ col,
-                                                  double *__restrict__ val, int maxrow, int *__restrict__ ovf) {
-  const int lane = threadIdx.x & 31;
-  // warps walk the atoms in cell order: the 8-16 warps of a CTA then scan (nearly) the same stencil runs, so the
-  // candidate records are served by L1 instead of L2
-  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (slot >= ntot) return;
-  const int i = rec_index(g.sorted[slot].w);
-  if (i >= natoms) return;
+__global__ void __launch_bounds__(PL_WARPS * 32) k_pairlist(DevGrid g, const DevFF *__restrict__ ffp, const int *__restrict__ runs,
+                                                            int nruns, int natoms, int ncell_res, int *__restrict__ slotcnt,
+                                                            const long long *__restrict__ rowoff, long long *__restrict__ rowbeg,
+                                                            long long *__restrict__ rowend, int *__restrict__ col,
+                                                            double *__restrict__ val, int maxrow, int *__restrict__ ovf) {
+  __shared__ int sh_s[PL_WARPS][PL_MAXRUNS];
+  __shared__ int sh_l[PL_WARPS][PL_MAXRUNS];
+  __shared__ double4 sh_a[PL_WARPS][32];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int rc = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (rc >= ncell_res) return;
   const DevFF &ff = *ffp;
-  int cid = g.cell_of[i];
-  int c3 = -1000, c2 = 0, c1 = 0;
-  if (cid >= 0) { c3 = cid % g.dim[2] - g.L; c2 = (cid / g.dim[2]) % g.dim[1] - g.L; c1 = cid / (g.dim[2] * g.dim[1]) - g.L; }
-  // only atoms in resident cells 0..nbcc-1 own a row (src/main.F90:438-440, src/qeq.F90:202-204)
-  if (cid < 0 || c1 < 0 || c1 >= g.nc[0] || c2 < 0 || c2 >= g.nc[1] || c3 < 0 || c3 >= g.nc[2]) {
-    if (!FILL && lane == 0) rowcnt[i] = 0;
-    return;
-  }
-  const double xi = pos[i], yi = pos[NB + i], zi = pos[2 * NB + i];
-  const int ity = itype[i];
+  // resident cells only own rows (src/main.F90:438-440, src/qeq.F90:202-204)
+  const int c3 = rc % g.nc[2], c2 = (rc / g.nc[2]) % g.nc[1], c1 = rc / (g.nc[2] * g.nc[1]);
+  const int cid = ((c1 + g.L) * g.dim[1] + (c2 + g.L)) * g.dim[2] + (c3 + g.L);
+  const int a0 = g.start[cid], a1 = g.start[cid + 1];
+  if (a1 == a0) return;
   const float rctap2f = (float)ff.rctap2;
-  long long base = FILL ? rowptr[i] : 0;
-  int cnt = 0;
-  for (int r = 0; r < nruns; r++) {
-    int dx = runs[4 * r], dy = runs[4 * r + 1], zlo = runs[4 * r + 2], zhi = runs[4 * r + 3];
-    int a1 = c1 + dx, a2 = c2 + dy;
-    int z0 = c3 + zlo, z1 = c3 + zhi;
-    if (a1 < -g.L || a1 >= g.nc[0] + g.L || a2 < -g.L || a2 >= g.nc[1] + g.L) continue;
-    if (z0 < -g.L) z0 = -g.L;
-    if (z1 >= g.nc[2] + g.L) z1 = g.nc[2] + g.L - 1;
-    if (z1 < z0) continue;
-    int cbase = ((a1 + g.L) * g.dim[1] + (a2 + g.L)) * g.dim[2] + g.L;
-    int s = g.start[cbase + z0], e = g.start[cbase + z1 + 1];
-    for (int k0 = s; k0 < e; k0 += 32) {
-      int k = k0 + lane;
-      bool acc = false;
-      int j = -1, jty = 0;
-      double dr2 = 0.0;
-      if (k < e) {
-        double4 o = g.sorted[k];
-        j = rec_index(o.w);
-        jty = rec_type(o.w);
-        if (j != i) {
-          dr2 = dist2_rn(sub_rn(xi, o.x), sub_rn(yi, o.y), sub_rn(zi, o.z));
-          acc = QEQ ? ((float)dr2 < rctap2f) : (dr2 <= ff.rctap2);
-        }
-      }
-      unsigned mask = __ballot_sync(0xffffffffu, acc);
-      if (FILL && acc) {
-        int w = cnt + __popc(mask & ((1u << lane) - 1u));
-        col[base + w] = j;
-        if (QEQ) {
-          double d2 = (double)(float)dr2;                    // real(4) dr2 promoted back
-          int itb = (int)mul_rn(d2, ff.UDRi);
-          double drtb = mul_rn(sub_rn(d2, mul_rn((double)itb, ff.UDR)), ff.UDRi);
-          int inxn = ff.inxn2[(ity - 1) + ff.nso * (jty - 1)];
-          double h = 0.0;
-          if (inxn > 0 && itb >= 1 && itb < ff.ntable) {
-            const double *T = ff.TBL_Eclmb_QEq + (size_t)(inxn - 1) * ff.ntable + (itb - 1);
-            h = add_rn(mul_rn(sub_rn(1.0, drtb), T[0]), mul_rn(drtb, T[1]));
+  for (int ab = a0; ab < a1; ab += 32) {
+    const int nb = min(32, a1 - ab);
+    const int myslot = ab + lane;
+    double4 me = make_double4(0, 0, 0, 0);
+    int mi = natoms;
+    if (lane < nb) { me = g.sorted[myslot]; mi = rec_index(me.w); }
+    sh_a[wid][lane] = me;
+    const bool mine = mi < natoms;           // a ghost inside a resident cell owns no row (cannot happen after MOVE)
+    long long mybase = (FILL && lane < nb) ? rowoff[myslot] : 0;
+    int mycnt = 0;
+    __syncwarp();
+    for (int rb = 0; rb < nruns; rb += PL_MAXRUNS) {
+      const int nr = min(PL_MAXRUNS, nruns - rb);
+      // ---- bounds of this batch of stencil runs, lane parallel (independent loads)
+      for (int r = lane; r < nr; r += 32) {
+        const int4 rr = *reinterpret_cast<const int4 *>(runs + 4 * (rb + r));
+        int b1 = c1 + rr.x, b2 = c2 + rr.y, z0 = c3 + rr.z, z1 = c3 + rr.w, s = 0, len = 0;
+        if (b1 >= -g.L && b1 < g.nc[0] + g.L && b2 >= -g.L && b2 < g.nc[1] + g.L) {
+          if (z0 < -g.L) z0 = -g.L;
+          if (z1 >= g.nc[2] + g.L) z1 = g.nc[2] + g.L - 1;
+          if (z1 >= z0) {
+            int cbase = ((b1 + g.L) * g.dim[1] + (b2 + g.L)) * g.dim[2] + g.L;
+            s = g.start[cbase + z0];
+            len = g.start[cbase + z1 + 1] - s;
           }
-          val[base + w] = h;
+        }
+        sh_s[wid][r] = s; sh_l[wid][r] = len;
+      }
+      __syncwarp();
+      for (int r = 0; r < nr; r++) {
+        const int s = sh_s[wid][r], len = sh_l[wid][r];
+        for (int k0 = 0; k0 < len; k0 += 32) {
+          const int k = k0 + lane;
+          const bool have = k < len;
+          const int cslot = s + k;
+          double4 o = make_double4(0, 0, 0, 0);
+          if (have) o = g.sorted[cslot];
+          const int jt = rec_type(o.w);
+          const int cval = cslot | ((have && rec_index(o.w) >= natoms) ? COL_GHOST : 0);
+          for (int a = 0; a < nb; a++) {
+            const double4 at = sh_a[wid][a];
+            const double dr2 = dist2_rn(sub_rn(at.x, o.x), sub_rn(at.y, o.y), sub_rn(at.z, o.z));
+            const bool acc = have && (cslot != ab + a) && (QEQ ? ((float)dr2 < rctap2f) : (dr2 <= ff.rctap2));
+            const unsigned mask = __ballot_sync(0xffffffffu, acc);
+            if (FILL) {
+              const long long wb = __shfl_sync(0xffffffffu, mybase + mycnt, a);
+              if (acc) {
+                const long long w = wb + __popc(mask & ((1u << lane) - 1u));
+                col[w] = cval;
+                if (QEQ) {
+                  double d2 = (double)(float)dr2;                    // real(4) dr2 promoted back
+                  int itb = (int)mul_rn(d2, ff.UDRi);
+                  double drtb = mul_rn(sub_rn(d2, mul_rn((double)itb, ff.UDR)), ff.UDRi);
+                  int inxn = ff.inxn2[(rec_type(at.w) - 1) + ff.nso * (jt - 1)];
+                  double h = 0.0;
+                  if (inxn > 0 && itb >= 1 && itb < ff.ntable) {
+                    const double *T = ff.TBL_Eclmb_QEq + (size_t)(inxn - 1) * ff.ntable + (itb - 1);
+                    h = add_rn(mul_rn(sub_rn(1.0, drtb), T[0]), mul_rn(drtb, T[1]));
+                  }
+                  val[w] = h;
+                }
+              }
+            }
+            if (lane == a) mycnt += __popc(mask);
+          }
         }
       }
-      cnt += __popc(mask);
+      __syncwarp();
     }
-  }
-  if (!FILL && lane == 0) {
-    rowcnt[i] = cnt;
-    if (cnt > maxrow) atomicMax(ovf, cnt);
+    if (lane < nb && mine) {
+      if (!FILL) {
+        slotcnt[myslot] = (mycnt + 3) & ~3;   // rows start on 4-entry boundaries (bulk-copy alignment)
+        if (mycnt > maxrow) atomicMax(ovf, mycnt);
+      } else {
+        rowbeg[mi] = mybase;
+        rowend[mi] = mybase + mycnt;
+      }
+    }
+    __syncwarp();
   }
 }
 
@@ -168,14 +199,17 @@ inline int build_nbrlist(Ctx *c) {
 
 template <bool QEQ>
 int build_pairlist(Ctx *c) {
-  const int n = c->natoms;
+  const int n = c->natoms, nt = c->cp[6];
   RXG_CUDA(cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->st));
-  RXG_CUDA(cudaMemsetAsync(c->rowcnt, 0, sizeof(int) * (size_t)(n + 1), c->st));
-  int grid = cdiv((long long)c->cp[6] * 32, 512);
-  LAUNCH(c, (k_pairlist<QEQ, false>), grid, 512, 0, c->gnb, c->d_ff, c->d_runs, c->nruns, n, c->cp[6], c->pos, c->NB, c->itype, c->rowcnt,
-         c->rowptr, c->col, c->val, c->cfg.maxneighbs10, c->d_flag);
-  RXG_TRY(ensure_blk(c, n));
-  RXG_TRY(device_scan<long long>(c, c->rowcnt, n, c->rowptr, c->d_blk64, (long long *)(c->d_acc + 32)));
+  RXG_CUDA(cudaMemsetAsync(c->rowcnt, 0, sizeof(int) * (size_t)(nt + 1), c->st));
+  RXG_CUDA(cudaMemsetAsync(c->rowbeg, 0, sizeof(long long) * (size_t)n, c->st));
+  RXG_CUDA(cudaMemsetAsync(c->rowend, 0, sizeof(long long) * (size_t)n, c->st));
+  const int ncell_res = c->gnb.nc[0] * c->gnb.nc[1] * c->gnb.nc[2];
+  const int grid = cdiv((long long)ncell_res * 32, PL_WARPS * 32);
+  LAUNCH(c, (k_pairlist<QEQ, false>), grid, PL_WARPS * 32, 0, c->gnb, c->d_ff, c->d_runs, c->nruns, n, ncell_res, c->rowcnt,
+         c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->cfg.maxneighbs10, c->d_flag);
+  RXG_TRY(ensure_blk(c, nt));
+  RXG_TRY(device_scan<long long>(c, c->rowcnt, nt, c->rowoff, c->d_blk64, (long long *)(c->d_acc + 32)));
   RXG_CUDA(cudaMemcpyAsync(c->h_int, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->st));
   RXG_CUDA(cudaMemcpyAsync(c->h_acc + 32, c->d_acc + 32, sizeof(long long), cudaMemcpyDeviceToHost, c->st));
   RXG_CUDA(cudaStreamSynchronize(c->st));
@@ -193,8 +227,8 @@ int build_pairlist(Ctx *c) {
   }
   c->nnz = nnz;
   c->list_is_qeq = QEQ;
-  LAUNCH(c, (k_pairlist<QEQ, true>), grid, 512, 0, c->gnb, c->d_ff, c->d_runs, c->nruns, n, c->cp[6], c->pos, c->NB, c->itype, c->rowcnt,
-         c->rowptr, c->col, c->val, c->cfg.maxneighbs10, c->d_flag);
+  LAUNCH(c, (k_pairlist<QEQ, true>), grid, PL_WARPS * 32, 0, c->gnb, c->d_ff, c->d_runs, c->nruns, n, ncell_res, c->rowcnt,
+         c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->cfg.maxneighbs10, c->d_flag);
   return RXG_OK;
 }
 
@@ -205,6 +239,27 @@ __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
+}
+
+
+// Sum four per-lane doubles over the warp with 9 double-shuffles instead of 20 (shuffles share the L1 data pipe with
+// the gathers, which is the busiest unit of the SpMV): halve the set of values each lane carries in the first two
+// butterfly steps, finish with three single-value steps, then collect the four totals from lanes 0, 8, 16, 24.
+__device__ __forceinline__ void warp_sum4(double &v0, double &v1, double &v2, double &v3, int lane) {
+  const bool up16 = lane & 16, up8 = lane & 8;
+  double s0 = up16 ? v0 : v2, s1 = up16 ? v1 : v3;          // what this lane gives away
+  double k0 = up16 ? v2 : v0, k1 = up16 ? v3 : v1;          // what it keeps
+  k0 += __shfl_xor_sync(0xffffffffu, s0, 16);
+  k1 += __shfl_xor_sync(0xffffffffu, s1, 16);
+  double give = up8 ? k0 : k1, u = up8 ? k1 : k0;
+  u += __shfl_xor_sync(0xffffffffu, give, 8);
+  u += __shfl_xor_sync(0xffffffffu, u, 4);
+  u += __shfl_xor_sync(0xffffffffu, u, 2);
+  u += __shfl_xor_sync(0xffffffffu, u, 1);
+  v0 = __shfl_sync(0xffffffffu, u, 0);
+  v1 = __shfl_sync(0xffffffffu, u, 8);
+  v2 = __shfl_sync(0xffffffffu, u, 16);
+  v3 = __shfl_sync(0xffffffffu, u, 24);
 }
 
 template <int NV>
@@ -248,19 +303,21 @@ __global__ void k_qeq_init(int natoms, int ntot_prev, const double *__restrict__
 }
 
 // D3: get_gradient, src/qeq.F90:321-363.  One warp per row; 8 rows per 256-thread CTA.
-__global__ void __launch_bounds__(256) k_gradient(int natoms, const long long *__restrict__ rowptr, const int *__restrict__ col,
+__global__ void __launch_bounds__(256) k_gradient(const int *__restrict__ order, int ntot, int natoms, const long long *__restrict__ rowbeg, const long long *__restrict__ rowend, const int *__restrict__ col,
                                                   const double *__restrict__ val, const double2 *__restrict__ qst,
                                                   const int *__restrict__ itype, const DevFF *__restrict__ ffp,
                                                   double2 *__restrict__ gst, double *__restrict__ acc) {
   const int lane = threadIdx.x & 31;
-  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // rows are walked in cell order (L1-friendly gathers)
+  int i = natoms;
+  if (slot < ntot) i = order[slot];
   double part[2] = {0.0, 0.0};
   if (i < natoms) {
-    long long s = rowptr[i], e = rowptr[i + 1];
+    long long s = rowbeg[i], e = rowend[i];
     double gs = 0.0, gt = 0.0;
     for (long long k = s + lane; k < e; k += 32) {
       double h = __ldcs(val + k);
-      int j = __ldcs(col + k);
+      int j = order[__ldcs(col + k) & COL_MASK];
       double2 x = qst[j];
       gs += h * x.x;
       gt += h * x.y;
@@ -282,20 +339,22 @@ __global__ void __launch_bounds__(256) k_gradient(int natoms, const long long *_
 }
 
 // D2: get_hsh (src/qeq.F90:271-318) fused with the g.h dots of src/qeq.F90:119-124
-__global__ void __launch_bounds__(256) k_hsh(int natoms, const long long *__restrict__ rowptr, const int *__restrict__ col,
+__global__ void __launch_bounds__(256) k_hsh(const int *__restrict__ order, int ntot, int natoms, const long long *__restrict__ rowbeg, const long long *__restrict__ rowend, const int *__restrict__ col,
                                              const double *__restrict__ val, const double4 *__restrict__ hsq,
                                              const double2 *__restrict__ gst, const int *__restrict__ itype,
                                              const DevFF *__restrict__ ffp, double *__restrict__ acc) {
   const int lane = threadIdx.x & 31;
-  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // rows are walked in cell order (L1-friendly gathers)
+  int i = natoms;
+  if (slot < ntot) i = order[slot];
   double part[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
   if (i < natoms) {
-    long long s = rowptr[i], e = rowptr[i + 1];
+    long long s = rowbeg[i], e = rowend[i];
     double4 me = hsq[i];
     double ts = 0.0, tt = 0.0, es = 0.0;
     for (long long k = s + lane; k < e; k += 32) {
       double h = __ldcs(val + k);
-      int j = __ldcs(col + k);
+      int j = order[__ldcs(col + k) & COL_MASK];
       double4 x = hsq[j];
       ts += h * x.x;
       tt += h * x.y;
@@ -331,7 +390,7 @@ __global__ void __launch_bounds__(256) k_hsh(int natoms, const long long *__rest
 // Est (src/qeq.F90:296-306) needs sum_j w_ij H_ij q_j with w = 2 for resident j, 1 for ghost j; it is
 // carried the same way in wst = resident-weighted H.(qs,qt), with q = qs - mu*qt.
 template <bool INIT>
-__global__ void __launch_bounds__(256) k_spmv1(int natoms, const long long *__restrict__ rowptr, const int *__restrict__ col,
+__global__ void __launch_bounds__(256) k_spmv1(const int *__restrict__ order, int ntot, int natoms, const long long *__restrict__ rowbeg, const long long *__restrict__ rowend, const int *__restrict__ col,
                                                const double *__restrict__ val, const double2 *__restrict__ x,
                                                const double2 *__restrict__ qst, const double *__restrict__ q,
                                                double2 *__restrict__ gst, double2 *__restrict__ tst,
@@ -339,24 +398,26 @@ __global__ void __launch_bounds__(256) k_spmv1(int natoms, const long long *__re
                                                const int *__restrict__ itype, const DevFF *__restrict__ ffp,
                                                double *__restrict__ acc) {
   const int lane = threadIdx.x & 31;
-  const int i = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // rows are walked in cell order (L1-friendly gathers)
+  int i = natoms;
+  if (slot < ntot) i = order[slot];
   double part[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
   if (i < natoms) {
-    long long s = rowptr[i], e = rowptr[i + 1];
+    long long s = rowbeg[i], e = rowend[i];
     double a = 0.0, b = 0.0, ga = 0.0, gb = 0.0;
     for (long long k = s + lane; k < e; k += 32) {
       double h = __ldcs(val + k);
       int j = __ldcs(col + k);
-      double2 v = x[j];
+      double2 v = x[j & COL_MASK];            // x is in slot order: neighbours of a stencil run are contiguous
       double pa = h * v.x, pb = h * v.y;
       a += pa; b += pb;
-      if (j >= natoms) { ga += pa; gb += pb; }
+      if (j < 0) { ga += pa; gb += pb; }      // bit 31 = ghost column
     }
-    a = warp_sum(a); b = warp_sum(b); ga = warp_sum(ga); gb = warp_sum(gb);
+    warp_sum4(a, b, ga, gb, lane);
     if (lane == 0) {
       int t = itype[i] - 1;
       double eta = ffp->eta[t], chi = ffp->chi[t];
-      double2 me = x[i];
+      double2 me = x[slot];
       if (INIT) {
         double g1 = sub_rn(sub_rn(-chi, mul_rn(eta, me.x)), a);
         double g2 = sub_rn(sub_rn(-1.0, mul_rn(eta, me.y)), b);
@@ -377,6 +438,137 @@ __global__ void __launch_bounds__(256) k_spmv1(int natoms, const long long *__re
   if (INIT) { double p2[2] = {part[0], part[1]}; block_accumulate<2>(p2, acc + 7); }
   else block_accumulate<5>(part, acc + 0);
 }
+
+// ---------------------------------------------------------------------------------------------------
+// TMA-staged variant of k_spmv1 (the production kernel).  Rows lie in HBM in cell order, so the rows of SP_ROWS
+// consecutive slots form ONE contiguous span of (val, col).  One CTA per span: an elected thread issues two bulk
+// async copies (cp.async.bulk ... mbarrier::complete_tx) that bring the span into shared memory, the CTA's warps
+// then take one row each and read the matrix stream from shared memory while gathering x from L1/L2.  With several
+// CTAs resident per SM the copy engine always has tens of KB in flight per SM, which is what HBM needs; the SM's
+// load/store pipe is left to the gathers.  Rows start on 4-entry boundaries (16 B for col, 32 B for val).
+constexpr int SP_ROWS = 4, SP_CAP = 1920;   // 8 rows x up to 480 entries: 46 KB of shared memory per CTA
+
+__device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void *dst, const void *src, unsigned bytes, unsigned long long *bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(smem_u32(dst)),
+               "l"(src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+  unsigned done = 0;
+  while (!done) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(done)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+
+template <bool INIT>
+__global__ void __launch_bounds__(SP_ROWS * 32) k_spmv1_tma(const int *__restrict__ order, int ntot, int natoms,
+                                                            const long long *__restrict__ rowoff,
+                                                            const long long *__restrict__ rowbeg,
+                                                            const long long *__restrict__ rowend, const int *__restrict__ col,
+                                                            const double *__restrict__ val, const double2 *__restrict__ x,
+                                                            const double2 *__restrict__ qst, const double *__restrict__ q,
+                                                            double2 *__restrict__ gst, double2 *__restrict__ tst,
+                                                            double2 *__restrict__ ust, double2 *__restrict__ wst,
+                                                            const int *__restrict__ itype, const DevFF *__restrict__ ffp,
+                                                            double *__restrict__ acc) {
+  __shared__ __align__(128) double s_val[SP_CAP];
+  __shared__ __align__(128) int s_col[SP_CAP];
+  __shared__ __align__(8) unsigned long long bar;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int slot0 = blockIdx.x * SP_ROWS;
+  const int slot1 = min(slot0 + SP_ROWS, ntot);
+  const long long sb = rowoff[slot0], se = rowoff[slot1];
+  const int span = (int)(se - sb);
+  const bool staged = span > 0 && span <= SP_CAP;
+  if (staged) {
+    if (threadIdx.x == 0) {
+      mbar_init(&bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(&bar, (unsigned)span * 12u);
+      bulk_g2s(s_val, val + sb, (unsigned)span * 8u, &bar);
+      bulk_g2s(s_col, col + sb, (unsigned)span * 4u, &bar);
+    }
+  }
+  const int slot = slot0 + wid;
+  int i = natoms;
+  if (slot < ntot) i = order[slot];
+  double part[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  // per-row scalars are fetched while the bulk copies are in flight
+  long long rs = 0, re = 0;
+  double eta = 0, chi = 0, qi = 0, mu = 0;
+  double2 me = make_double2(0, 0), g = make_double2(0, 0), w = make_double2(0, 0);
+  if (i < natoms) {
+    rs = rowbeg[i]; re = rowend[i];
+    int t = itype[i] - 1;
+    eta = ffp->eta[t]; chi = ffp->chi[t];
+    me = x[slot];
+    if (!INIT) { g = gst[i]; w = wst[i]; qi = q[i]; mu = acc[11]; }
+  }
+  if (staged) mbar_wait(&bar, 0);
+  if (i < natoms) {
+    double a = 0.0, b = 0.0, ga = 0.0, gb = 0.0;
+    const int n = (int)(re - rs);
+    if (staged) {
+      const double *sv = s_val + (rs - sb);
+      const int *sc = s_col + (rs - sb);
+#pragma unroll 8
+      for (int k = lane; k < n; k += 32) {
+        double h = sv[k];
+        int j = sc[k];
+        double2 v = x[j & COL_MASK];
+        double pa = h * v.x, pb = h * v.y;
+        a += pa; b += pb;
+        if (j < 0) { ga += pa; gb += pb; }
+      }
+    } else {
+      for (long long k = rs + lane; k < re; k += 32) {
+        double h = __ldcs(val + k);
+        int j = __ldcs(col + k);
+        double2 v = x[j & COL_MASK];
+        double pa = h * v.x, pb = h * v.y;
+        a += pa; b += pb;
+        if (j < 0) { ga += pa; gb += pb; }
+      }
+    }
+    warp_sum4(a, b, ga, gb, lane);
+    if (lane == 0) {
+      if (INIT) {
+        double g1 = sub_rn(sub_rn(-chi, mul_rn(eta, me.x)), a);
+        double g2 = sub_rn(sub_rn(-1.0, mul_rn(eta, me.y)), b);
+        gst[i] = make_double2(g1, g2);
+        wst[i] = make_double2(2.0 * a - ga, 2.0 * b - gb);
+        part[0] = g1 * g1; part[1] = g2 * g2;
+      } else {
+        double ts = eta * me.x + a, tt = eta * me.y + b;
+        tst[i] = make_double2(ts, tt);
+        ust[i] = make_double2(2.0 * a - ga, 2.0 * b - gb);
+        part[0] = chi * qi + 0.5 * eta * qi * qi + 0.5 * qi * (w.x - mu * w.y);
+        part[1] = ts * me.x; part[2] = tt * me.y; part[3] = g.x * me.x; part[4] = g.y * me.y;
+      }
+    }
+  }
+  if (INIT) { double p2[2] = {part[0], part[1]}; block_accumulate<2>(p2, acc + 7); }
+  else block_accumulate<5>(part, acc + 0);
+}
+
 __global__ void k_roll_g(double *__restrict__ acc) {
   acc[9] = acc[7]; acc[10] = acc[8];
   acc[5] = 0.0; acc[6] = 0.0; acc[7] = 0.0; acc[8] = 0.0;
@@ -404,7 +596,8 @@ __global__ void __launch_bounds__(256) k_cg_update1(int natoms, float lmin_s, fl
 }
 // mu, q = qs - mu*qt (src/qeq.F90:147-150) and the Fletcher-Reeves direction update (:160-161)
 __global__ void k_cg_update2(int natoms, const double2 *__restrict__ qst, const double2 *__restrict__ gst,
-                             double2 *__restrict__ hst, double *__restrict__ q, double *__restrict__ acc) {
+                             double2 *__restrict__ hst, double2 *__restrict__ xs, const int *__restrict__ slot_of,
+                             double *__restrict__ q, double *__restrict__ acc) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   double mu = acc[5] / acc[6];
   if (i == 0) acc[11] = mu;
@@ -415,10 +608,17 @@ __global__ void k_cg_update2(int natoms, const double2 *__restrict__ qst, const 
   h.x = add_rn(g.x, mul_rn(bs, h.x));
   h.y = add_rn(g.y, mul_rn(bt, h.y));
   hst[i] = h;
+  xs[slot_of[i]] = h;
 }
-__global__ void k_h_from_g2(int natoms, const double2 *__restrict__ gst, double2 *__restrict__ hst) {
+__global__ void k_h_from_g2(int natoms, const double2 *__restrict__ gst, double2 *__restrict__ hst, double2 *__restrict__ xs,
+                            const int *__restrict__ slot_of) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
-  if (i < natoms) hst[i] = gst[i];
+  if (i < natoms) { double2 g = gst[i]; hst[i] = g; xs[slot_of[i]] = g; }
+}
+// xs[slot] = v[order[slot]] for residents and ghosts
+__global__ void k_to_slots(int ntot, const int *__restrict__ order, const double2 *__restrict__ v, double2 *__restrict__ xs) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s < ntot) xs[s] = v[order[s]];
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -427,14 +627,14 @@ __global__ void k_h_from_g2(int natoms, const double2 *__restrict__ gst, double2
 // The reference's CG amplifies round-off (its real(4) step length keeps it in a noise-dominated regime: an FMA
 // build of the same Fortran/C++ loops changes the converged charges by ~1e-5), so only this path can be compared
 // at 1e-8; the production kernels above differ from it by summation order alone.  Small systems only.
-__global__ void k_rows_strict_grad(int natoms, const long long *__restrict__ rowptr, const int *__restrict__ col,
+__global__ void k_rows_strict_grad(const int *__restrict__ order, int natoms, const long long *__restrict__ rowbeg, const long long *__restrict__ rowend, const int *__restrict__ col,
                                    const double *__restrict__ val, const double2 *__restrict__ qst,
                                    const int *__restrict__ itype, const DevFF *__restrict__ ffp, double2 *__restrict__ gst) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= natoms) return;
   double gs = 0.0, gt = 0.0;
-  for (long long k = rowptr[i]; k < rowptr[i + 1]; k++) {
-    double2 x = qst[col[k]];
+  for (long long k = rowbeg[i]; k < rowend[i]; k++) {
+    double2 x = qst[order[col[k] & COL_MASK]];
     gs = add_rn(gs, mul_rn(val[k], x.x));
     gt = add_rn(gt, mul_rn(val[k], x.y));
   }
@@ -443,7 +643,7 @@ __global__ void k_rows_strict_grad(int natoms, const long long *__restrict__ row
   double2 x = qst[i];
   gst[i] = make_double2(sub_rn(sub_rn(-chi, mul_rn(eta, x.x)), gs), sub_rn(sub_rn(-1.0, mul_rn(eta, x.y)), gt));
 }
-__global__ void k_rows_strict_hsh(int natoms, const long long *__restrict__ rowptr, const int *__restrict__ col,
+__global__ void k_rows_strict_hsh(const int *__restrict__ order, int natoms, const long long *__restrict__ rowbeg, const long long *__restrict__ rowend, const int *__restrict__ col,
                                   const double *__restrict__ val, const double4 *__restrict__ hsq,
                                   const int *__restrict__ itype, const DevFF *__restrict__ ffp, double4 *__restrict__ rowbuf) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -453,8 +653,8 @@ __global__ void k_rows_strict_hsh(int natoms, const long long *__restrict__ rowp
   double4 me = hsq[i];
   double ts = mul_rn(eta, me.x), tt = mul_rn(eta, me.y);
   double es = add_rn(mul_rn(chi, me.z), mul_rn(mul_rn(mul_rn(0.5, eta), me.z), me.z));
-  for (long long k = rowptr[i]; k < rowptr[i + 1]; k++) {
-    int j = col[k];
+  for (long long k = rowbeg[i]; k < rowend[i]; k++) {
+    int j = order[col[k] & COL_MASK];
     double4 x = hsq[j];
     ts = add_rn(ts, mul_rn(val[k], x.x));
     tt = add_rn(tt, mul_rn(val[k], x.y));

@@ -74,7 +74,7 @@ def _dp(a):
 
 _F64 = {"atype", "q", "qst", "gst", "hsq", "val", "BO0", "BO1", "BO2", "BO3", "dln_BOp1", "dln_BOp2", "dln_BOp3", "dBOp",
         "A0", "A1", "A2", "A3", "delta", "deltap1", "deltap2", "nlp", "dDlp", "deltalp", "cdbnd", "ccbnd", "pos", "f", "v"}
-_I64 = {"rowptr", "nnz"}
+_I64 = {"rowbeg", "rowend", "nnz"}
 
 
 class Engine:

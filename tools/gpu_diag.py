@@ -50,9 +50,9 @@ def main():
         print("  ghost pos diff", rel(e.fetch("pos").reshape(3, -1), o.f64("pos").reshape(3, -1)))
         print("  ghost atype equal", np.array_equal(e.fetch("atype"), o.f64("atype")))
     cnt_o = o.i32("nbpcnt")
-    rp = e.fetch("rowptr")
-    cnt_g = np.diff(rp)
-    print("  row counts equal", np.array_equal(cnt_o, cnt_g), "nnz", rp[-1], cnt_o.sum())
+    rb, re_ = e.fetch("rowbeg"), e.fetch("rowend")
+    cnt_g = re_ - rb
+    print("  row counts equal", np.array_equal(cnt_o, cnt_g), "nnz (true)", int(cnt_g.sum()), cnt_o.sum(), "padded", e.fetch("nnz")[0])
     W = cfg.maxneighbs10
     lst_o = o.i32("nbplist").reshape(n, W)
     hes_o = o.f64("hessian").reshape(n, W)
@@ -60,7 +60,7 @@ def main():
     same_order, same_set, hmax = True, True, 0.0
     for i in range(n):
         a = lst_o[i, :cnt_o[i]]
-        b = col[rp[i]:rp[i + 1]]
+        b = col[rb[i]:re_[i]]
         if len(a) != len(b):
             same_order = same_set = False
             continue
@@ -69,9 +69,9 @@ def main():
             if not np.array_equal(np.sort(a), np.sort(b)):
                 same_set = False
             else:
-                hmax = max(hmax, np.abs(hes_o[i, :cnt_o[i]][np.argsort(a)] - val[rp[i]:rp[i + 1]][np.argsort(b)]).max())
+                hmax = max(hmax, np.abs(hes_o[i, :cnt_o[i]][np.argsort(a)] - val[rb[i]:re_[i]][np.argsort(b)]).max())
         else:
-            hmax = max(hmax, np.abs(hes_o[i, :cnt_o[i]] - val[rp[i]:rp[i + 1]]).max())
+            hmax = max(hmax, np.abs(hes_o[i, :cnt_o[i]] - val[rb[i]:re_[i]]).max())
     print("  pair rows: same order", same_order, "same sets", same_set, "hessian max abs diff", hmax)
     print("  q diff (abs, rel)", rel(q[:n], o.f64("q")[:n]), " sum q", q[:n].sum())
     # ---------------- FORCE (identical charges on both sides: the oracle's)

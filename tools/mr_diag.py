@@ -1,0 +1,89 @@
+"""Multi-rank GPU-vs-oracle comparison (development diagnostic).
+
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 \
+        tools/mr_diag.py mcx mcy mcz [--sigma S]
+
+Every rank builds the same system, drives its own GPU through the C-ABI, and compares its arrays with the same rank
+of the oracle (which simulates all ranks of the identical `vprocs` decomposition in-process).
+"""
+import os
+import sys
+import numpy as np
+import torch
+import torch.distributed as dist
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from rxmd_b200.host.system import build_system  # noqa: E402
+from rxmd_b200.host.engine import Engine  # noqa: E402
+from oracle.pyoracle import Oracle  # noqa: E402
+
+G = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests/golden/inputs/init.rdx/")
+VP = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
+
+
+def rel(a, b):
+    d = np.abs(a - b).max() if a.size else 0.0
+    return d, d / max(np.abs(b).max() if b.size else 0.0, 1e-300)
+
+
+def main():
+    rank, world, local = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+    torch.cuda.set_device(local)
+    dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    args = [a for a in sys.argv[1:] if not a.startswith("--")]
+    mc = tuple(int(x) for x in args[:3])
+    sigma = float(sys.argv[sys.argv.index("--sigma") + 1]) if "--sigma" in sys.argv else 0.0
+    vp = VP[world]
+    s = build_system(G + "input.xyz", G + "ffield", mc=mc, vprocs=vp, displace_sigma=sigma)
+    cfg = s.config(device=local)
+    e = Engine(s, cfg, rank=rank)
+    e.comm_init_torch(dist)
+    o = Oracle(s, cfg)       # all ranks, simulated
+    atype, pos, v, f, q = e.host_arrays(s.ranks[rank])
+    n = e.NATOMS
+    out = [f"rank {rank}/{world} vprocs {vp} natoms {n} of {s.natoms}"]
+    o.qeq()
+    e.QEq(atype, pos, q)
+    cp_o, cp_g = o.i32("copyptr", rank), e.fetch("copyptr")
+    out.append(f"  QEq copyptr equal {np.array_equal(cp_o, cp_g)} {cp_g.tolist()} nstep {o.observe()[3]} vs {e.nstep_qeq}")
+    if np.array_equal(cp_o, cp_g):
+        out.append(f"  ghost pos diff {rel(e.fetch('pos').reshape(3, -1), o.f64('pos', rank).reshape(3, -1))} atype equal "
+                   f"{np.array_equal(e.fetch('atype'), o.f64('atype', rank))}")
+    rb, re_ = e.fetch("rowbeg"), e.fetch("rowend")
+    out.append(f"  row counts equal {np.array_equal(o.i32('nbpcnt', rank), re_ - rb)}")
+    out.append(f"  q diff {rel(q[:n], o.f64('q', rank)[:n])}")
+    q[:n] = o.f64("q", rank)[:n]
+    o.force()
+    e.FORCE(atype, pos, f, q)
+    cp_o, cp_g = o.i32("copyptr", rank), e.fetch("copyptr")
+    out.append(f"  FORCE copyptr equal {np.array_equal(cp_o, cp_g)} {cp_g.tolist()}")
+    pe_o = o.f64("PE", rank)
+    out.append(f"  PE rel diff max {np.max(np.abs(e.PE[1:] - pe_o[1:]) / np.maximum(np.abs(pe_o[1:]), 1e-300))}")
+    f_o = o.f64("f", rank).reshape(3, -1)[:, :n]
+    out.append(f"  f diff {rel(f[:, :n], f_o)}")
+    # device-resident MD with migration
+    UTIME = 1e3 / 20.455
+    dt = 0.25 / UTIME
+    lw2 = 2.0 * 2.0 / dt / dt
+    os.environ.setdefault("X", "")
+    e.state_upload(atype, pos, v, q)
+    e.md_prime()
+    o.qeq(); o.force()
+    e.md_run(10, dt, 1, lw2, 0)
+    o.md_run(10, dt, 1, lw2, 0)
+    pe_g, ke_g, qs_g, it_g = e.md_observe()
+    tot = torch.tensor([pe_g[1:].sum(), ke_g, float(e.natoms_resident())], dtype=torch.float64, device="cuda")
+    dist.all_reduce(tot)
+    pe_oa, ke_o, _, it_o = o.observe()
+    out.append(f"  MD10: natoms {e.natoms_resident()} vs {o.natoms(rank)}  global PE {tot[0].item():.9f} vs {pe_oa[0]:.9f}  KE {tot[1].item():.9e} vs {ke_o:.9e} "
+               f"natoms_total {int(tot[2].item())}")
+    for r in range(world):
+        dist.barrier()
+        if r == rank:
+            print("\n".join(out), flush=True)
+    e.close()
+    dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
