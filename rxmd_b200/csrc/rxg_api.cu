@@ -85,8 +85,8 @@ struct Timer {
 // MPI_ALLREDUCE(SUM) of a few doubles (src/qeq.F90:107,129,144,357) as ncclAllReduce on the compute stream
 int allreduce_acc(Ctx *c, int first, int count) {
   if (!c->comm) return RXG_OK;
-  ncclResult_t r = ncclAllReduce(c->d_acc + first, c->d_acc + first, count, ncclDouble, ncclSum, c->comm, c->st);
-  if (r != ncclSuccess) { c->err = std::string("NCCL error: ") + ncclGetErrorString(r); return RXG_ERR_NCCL; }
+  ncclResult_t r = nccl_api().AllReduce(c->d_acc + first, c->d_acc + first, count, ncclDouble, ncclSum, c->comm, c->st);
+  if (r != ncclSuccess) { c->err = std::string("NCCL error: ") + nccl_api().GetErrorString(r); return RXG_ERR_NCCL; }
   c->nccl_msgs++;
   return RXG_OK;
 }
@@ -378,7 +378,9 @@ int rxg_set_box(rxg_handle h, const rxg_box *box) {
 int rxg_comm_unique_id(void *out128) {
   if (!out128) return RXG_ERR_ARG;
   ncclUniqueId id;
-  if (ncclGetUniqueId(&id) != ncclSuccess) return RXG_ERR_NCCL;
+  std::string err;
+  if (!nccl_api().load(err)) return RXG_ERR_NCCL;
+  if (nccl_api().GetUniqueId(&id) != ncclSuccess) return RXG_ERR_NCCL;
   static_assert(sizeof(ncclUniqueId) == 128, "ncclUniqueId is 128 bytes");
   memcpy(out128, &id, 128);
   return RXG_OK;
@@ -392,8 +394,9 @@ int rxg_comm_init(rxg_handle h, int rank, int nranks, const void *id) {
   RXG_CUDA(cudaSetDevice(c->dev));
   ncclUniqueId uid;
   memcpy(&uid, id, 128);
-  ncclResult_t r = ncclCommInitRank(&c->comm, nranks, uid, rank);
-  if (r != ncclSuccess) { c->err = std::string("ncclCommInitRank: ") + ncclGetErrorString(r); return RXG_ERR_NCCL; }
+  if (!nccl_api().load(c->err)) return RXG_ERR_NCCL;
+  ncclResult_t r = nccl_api().CommInitRank(&c->comm, nranks, uid, rank);
+  if (r != ncclSuccess) { c->err = std::string("ncclCommInitRank: ") + nccl_api().GetErrorString(r); return RXG_ERR_NCCL; }
   return RXG_OK;
 }
 
@@ -408,7 +411,7 @@ int rxg_destroy(rxg_handle h) {
     for (void *p : {(void *)c->col, (void *)c->val, (void *)c->d_blk, (void *)c->d_blk64, (void *)c->d_runs, (void *)c->d_ff})
       if (p) cudaFree(p);
     for (int k = 0; k < 2; k++) { if (c->sbuf[k]) cudaFree(c->sbuf[k]); if (c->rbuf[k]) cudaFree(c->rbuf[k]); }
-    if (c->comm) ncclCommDestroy(c->comm);
+    if (c->comm) nccl_api().CommDestroy(c->comm);
     if (c->wl) cudaFree(c->wl);
     if (c->h_acc) cudaFreeHost(c->h_acc);
     if (c->h_int) cudaFreeHost(c->h_int);

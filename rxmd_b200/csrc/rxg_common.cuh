@@ -1,10 +1,12 @@
 // rxg_common.cuh -- shared declarations of the B200 hot-path library (device context, helpers).
 #pragma once
 #include <cuda_runtime.h>
-#include <nccl.h>
+#include <nccl.h>   // types only: the library is dlopen()ed at rxg_comm_init (see NcclApi)
+#include <dlfcn.h>
 #include <algorithm>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 #include "../../include/rxmd_b200.h"
@@ -13,6 +15,42 @@
 #define RXG_MAXLAYERS_NB 10   // reference src/module.F90:45
 
 namespace rxg {
+
+// NCCL entry points resolved at run time.  Linking libnccl at load time would pin whichever libnccl.so.2 the loader
+// finds first; a host process that loads its own NCCL later (PyTorch bundles a newer one) would then break.  With
+// dlopen at rxg_comm_init the library joins whatever NCCL the process already uses, or the system one otherwise.
+struct NcclApi {
+  void *handle = nullptr;
+  ncclResult_t (*GetUniqueId)(ncclUniqueId *) = nullptr;
+  ncclResult_t (*CommInitRank)(ncclComm_t *, int, ncclUniqueId, int) = nullptr;
+  ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+  ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*GroupStart)() = nullptr;
+  ncclResult_t (*GroupEnd)() = nullptr;
+  const char *(*GetErrorString)(ncclResult_t) = nullptr;
+  bool load(std::string &err) {
+    if (handle) return true;
+    const char *env = getenv("RXG_NCCL_LIB");
+    const char *names[] = {env, "libnccl.so.2", "libnccl.so"};
+    for (const char *n : names) {
+      if (!n) continue;
+      handle = dlopen(n, RTLD_NOW | RTLD_LOCAL);
+      if (handle) break;
+    }
+    if (!handle) { err = std::string("cannot dlopen libnccl: ") + dlerror(); return false; }
+#define RXG_SYM(field, name)                                                   \
+  field = reinterpret_cast<decltype(field)>(dlsym(handle, name));              \
+  if (!field) { err = std::string("libnccl lacks ") + name; return false; }
+    RXG_SYM(GetUniqueId, "ncclGetUniqueId") RXG_SYM(CommInitRank, "ncclCommInitRank") RXG_SYM(CommDestroy, "ncclCommDestroy")
+    RXG_SYM(Send, "ncclSend") RXG_SYM(Recv, "ncclRecv") RXG_SYM(AllReduce, "ncclAllReduce") RXG_SYM(GroupStart, "ncclGroupStart")
+    RXG_SYM(GroupEnd, "ncclGroupEnd") RXG_SYM(GetErrorString, "ncclGetErrorString")
+#undef RXG_SYM
+    return true;
+  }
+};
+inline NcclApi &nccl_api() { static NcclApi a; return a; }
 
 // ---- round-to-nearest fp64 arithmetic that ptxas may not contract into FMA.  Used wherever a result
 // feeds a comparison or an index (cell ids, cut-off tests, table weights) so that it is bit-identical to

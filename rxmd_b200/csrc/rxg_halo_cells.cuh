@@ -353,7 +353,7 @@ inline int ensure_xbuf(Ctx *c, size_t doubles_each) {
   do {                                                                                                      \
     ncclResult_t r_ = (call);                                                                               \
     if (r_ != ncclSuccess) {                                                                                \
-      c->err = std::string("NCCL error: ") + ncclGetErrorString(r_) + " at " + __FILE__ + ":" + std::to_string(__LINE__); \
+      c->err = std::string("NCCL error: ") + nccl_api().GetErrorString(r_) + " at " + __FILE__ + ":" + std::to_string(__LINE__); \
       return RXG_ERR_NCCL;                                                                                  \
     }                                                                                                       \
   } while (0)
@@ -374,12 +374,12 @@ inline int exchange_axis(Ctx *c, int axis, const size_t cs[2], const size_t cr[2
   }
   if (!c->comm) { c->err = "rxg_comm_init was not called for a multi-rank decomposition"; return RXG_ERR_NCCL; }
   recv[0] = c->rbuf[0]; recv[1] = c->rbuf[1];
-  RXG_NCCL(ncclGroupStart());
-  if (cs[0]) RXG_NCCL(ncclSend(c->sbuf[0], cs[0], ncclDouble, dst0, c->comm, c->st));
-  if (cr[0]) RXG_NCCL(ncclRecv(c->rbuf[0], cr[0], ncclDouble, src0, c->comm, c->st));
-  if (cs[1]) RXG_NCCL(ncclSend(c->sbuf[1], cs[1], ncclDouble, dst1, c->comm, c->st));
-  if (cr[1]) RXG_NCCL(ncclRecv(c->rbuf[1], cr[1], ncclDouble, src1, c->comm, c->st));
-  RXG_NCCL(ncclGroupEnd());
+  RXG_NCCL(nccl_api().GroupStart());
+  if (cs[0]) RXG_NCCL(nccl_api().Send(c->sbuf[0], cs[0], ncclDouble, dst0, c->comm, c->st));
+  if (cr[0]) RXG_NCCL(nccl_api().Recv(c->rbuf[0], cr[0], ncclDouble, src0, c->comm, c->st));
+  if (cs[1]) RXG_NCCL(nccl_api().Send(c->sbuf[1], cs[1], ncclDouble, dst1, c->comm, c->st));
+  if (cr[1]) RXG_NCCL(nccl_api().Recv(c->rbuf[1], cr[1], ncclDouble, src1, c->comm, c->st));
+  RXG_NCCL(nccl_api().GroupEnd());
   c->nccl_msgs += 4;
   return RXG_OK;
 }
@@ -392,12 +392,12 @@ inline int exchange_counts(Ctx *c, int axis, const int ns[2], int nr[2]) {
   if (!c->comm) { c->err = "rxg_comm_init was not called for a multi-rank decomposition"; return RXG_ERR_NCCL; }
   c->h_int[8] = ns[0]; c->h_int[9] = ns[1];
   RXG_CUDA(cudaMemcpyAsync(c->d_flag + 8, c->h_int + 8, 2 * sizeof(int), cudaMemcpyHostToDevice, c->st));
-  RXG_NCCL(ncclGroupStart());
-  RXG_NCCL(ncclSend(c->d_flag + 8, 1, ncclInt, tp, c->comm, c->st));
-  RXG_NCCL(ncclRecv(c->d_flag + 10, 1, ncclInt, tm, c->comm, c->st));
-  RXG_NCCL(ncclSend(c->d_flag + 9, 1, ncclInt, tm, c->comm, c->st));
-  RXG_NCCL(ncclRecv(c->d_flag + 11, 1, ncclInt, tp, c->comm, c->st));
-  RXG_NCCL(ncclGroupEnd());
+  RXG_NCCL(nccl_api().GroupStart());
+  RXG_NCCL(nccl_api().Send(c->d_flag + 8, 1, ncclInt, tp, c->comm, c->st));
+  RXG_NCCL(nccl_api().Recv(c->d_flag + 10, 1, ncclInt, tm, c->comm, c->st));
+  RXG_NCCL(nccl_api().Send(c->d_flag + 9, 1, ncclInt, tm, c->comm, c->st));
+  RXG_NCCL(nccl_api().Recv(c->d_flag + 11, 1, ncclInt, tp, c->comm, c->st));
+  RXG_NCCL(nccl_api().GroupEnd());
   RXG_CUDA(cudaMemcpyAsync(c->h_int + 10, c->d_flag + 10, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
   RXG_CUDA(cudaStreamSynchronize(c->st));
   nr[0] = c->h_int[10]; nr[1] = c->h_int[11];

@@ -72,6 +72,20 @@ def _dp(a):
     return None if a is None else a.ctypes.data_as(C.POINTER(C.c_double))
 
 
+def broadcast_bytes(dist, payload: bytes, src=0) -> bytes:
+    """Rank `src`'s byte string on every rank (used for the 128-byte ncclUniqueId; works with gloo and nccl)."""
+    import torch
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.tensor(list(payload), dtype=torch.uint8, device=dev)
+    dist.broadcast(t, src=src)
+    return bytes(t.cpu().tolist())
+
+
+def rank_of_vid(vid, vprocs):
+    """Sequential rank of a vector id, src/init.F90:97 (x fastest)."""
+    return vid[0] + vid[1] * vprocs[0] + vid[2] * vprocs[0] * vprocs[1]
+
+
 _F64 = {"atype", "q", "qst", "gst", "hsq", "val", "BO0", "BO1", "BO2", "BO3", "dln_BOp1", "dln_BOp2", "dln_BOp3", "dBOp",
         "A0", "A1", "A2", "A3", "delta", "deltap1", "deltap2", "nlp", "dDlp", "deltalp", "cdbnd", "ccbnd", "pos", "f", "v"}
 _I64 = {"rowbeg", "rowend", "nnz"}
@@ -111,15 +125,11 @@ class Engine:
     def comm_init_torch(self, dist):
         """NCCL communicator of the library: rank 0 creates the 128-byte ncclUniqueId, torch.distributed (any backend)
         broadcasts it -- the job MPI_Bcast does in the Fortran shim."""
-        import torch
         nranks, rank = dist.get_world_size(), dist.get_rank()
         buf = (C.c_ubyte * 128)()
         if rank == 0:
             self._chk(self.L.rxg_comm_unique_id(C.cast(buf, C.c_void_p)))
-        dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
-        t = torch.tensor(list(bytes(buf)), dtype=torch.uint8, device=dev)
-        dist.broadcast(t, src=0)
-        raw = bytes(t.cpu().tolist())
+        raw = broadcast_bytes(dist, bytes(buf))
         buf2 = (C.c_ubyte * 128).from_buffer_copy(raw)
         self._chk(self.L.rxg_comm_init(self.h, rank, nranks, C.cast(buf2, C.c_void_p)))
 

@@ -77,6 +77,13 @@ def main():
     pe_oa, ke_o, _, it_o = o.observe()
     out.append(f"  MD10: natoms {e.natoms_resident()} vs {o.natoms(rank)}  global PE {tot[0].item():.9f} vs {pe_oa[0]:.9f}  KE {tot[1].item():.9e} vs {ke_o:.9e} "
                f"natoms_total {int(tot[2].item())}")
+    if "--assert" in sys.argv:
+        assert np.array_equal(cp_o, cp_g)
+        assert np.array_equal(o.i32("nbpcnt", rank), re_ - rb)
+        assert rel(f[:, :n], f_o)[1] < 1e-9
+        assert np.max(np.abs(e.PE[1:] - pe_o[1:]) / np.maximum(np.abs(pe_o[1:]), 1e-6 * np.abs(pe_o[1:]).max())) < 1e-9
+        assert e.natoms_resident() == o.natoms(rank) and int(tot[2].item()) == s.natoms
+        assert abs(tot[0].item() - pe_oa[0]) < 1e-6 * abs(pe_oa[0])
     for r in range(world):
         dist.barrier()
         if r == rank:
