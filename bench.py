@@ -140,7 +140,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
     ap.add_argument("--mc", type=int, nargs=3, default=[18, 18, 18], help="unit-cell replication per GPU")
-    ap.add_argument("--cpu-mc", type=int, nargs=3, default=[3, 3, 3])
+    ap.add_argument("--cpu-mc", type=int, nargs=3, default=[6, 6, 6])
     ap.add_argument("--sigma", type=float, default=0.02)
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
@@ -229,14 +229,14 @@ def main():
     tp = os.path.join(ROOT, "profiles", "spmv_traffic.json")
     if os.path.exists(tp):
         try:
-            traffic = json.load(open(tp)).get("k_hsh_dram_bytes_per_launch")
+            traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    r_h = roof(d[10], d[11], 3)
+    r_h = roof(d[10], d[11], 2)      # the single-pass CG gathers two vectors (hs, ht)
     r_g = roof(d[12], d[13], 2)
     roofline = None
     if r_h:
-        roofline = {"kernel": "k_hsh (QEq CG get_hsh SpMV, 2 RHS + Est, fused dots)", "bound": "hbm", "achieved": r_h[1], "peak": peak,
+        roofline = {"kernel": "k_spmv1_tma (QEq CG SpMV: H.(hs,ht), TMA-staged matrix stream, fused Est + 4 dots)", "bound": "hbm", "achieved": r_h[1], "peak": peak,
                     "unit": "GB/s", "frac": r_h[1] / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": r_h[0], "avg_launch_ms": d[10] / d[11], "launches_timed": int(d[11]),
                     "step_share": d[10] / max(t_after[3] - t_before[3], 1e-9),
@@ -290,7 +290,7 @@ def main():
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu, _ = cpu_sample(args, 10, 2)
+        cpu, _ = cpu_sample(args, 20, 2)
 
     if rank == 0:
         line = {"metric": "atom-timesteps/s, RDX ReaxFF+QEq", "value": value, "unit": "atom-timesteps/s", "n_gpus": world,
