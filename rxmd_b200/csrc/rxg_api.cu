@@ -221,7 +221,9 @@ int qeq_cg_single(Ctx *c, int nmax, int *iters) {
 }
 
 // subroutine QEq on device-resident state, reference src/qeq.F90:2-178
-int qeq_device(Ctx *c) {
+// `for_force`: build the halo with FORCE's width and the 10 A list with FORCE's predicate as well, so that the FORCE call of
+// the same step can reuse them (device-resident stepping only; the per-call API stays literal)
+int qeq_device(Ctx *c, bool for_force = false) {
   const int isQEq = c->cfg.isQEq;
   if (isQEq != 1 && isQEq != 2) return RXG_OK;
   const int n = c->natoms;
@@ -230,10 +232,20 @@ int qeq_device(Ctx *c) {
   if (nprev > 0)
     LAUNCH(c, k_qeq_init, cdiv(nprev, 256), 256, 0, n, nprev, c->q, c->qst, c->hsq, c->qsfp, c->qsfv, isQEq, c->cfg.Lex_fqs);
   double QCopyDr[3] = {c->ff.rctap / c->box.lata, c->ff.rctap / c->box.latb, c->ff.rctap / c->box.latc};
+  c->lists_shared = false;
+  if (for_force && !c->strict) {
+    bool wide = true;
+    for (int a = 0; a < 3; a++) wide = wide && (c->cfg.nmincell * c->box.lcsize[a] >= QCopyDr[a]);
+    if (wide) {
+      for (int a = 0; a < 3; a++) QCopyDr[a] = c->cfg.nmincell * c->box.lcsize[a];
+      c->lists_shared = true;
+    }
+  }
   RXG_TRY(halo_copy(c, QCopyDr));
   if (c->cp[6] > 0) LAUNCH(c, k_types, cdiv(c->cp[6], 256), 256, 0, c->atype, c->cp[6], c->itype, c->gid);
   RXG_TRY(bin_grid(c, c->gnb));
-  RXG_TRY(build_pairlist<true>(c));
+  if (c->lists_shared) RXG_TRY(build_pairlist<2>(c));
+  else RXG_TRY(build_pairlist<1>(c));
   RXG_CUDA(cudaMemsetAsync(c->d_acc, 0, sizeof(double) * 16, c->st));
   int it = 0;
   if (c->strict || c->qeq_mode == 1) RXG_TRY(qeq_cg_literal(c, nmax, &it));
@@ -261,6 +273,8 @@ int rxg_create(const rxg_config *cfg, rxg_handle *out) {
   c->dev = cfg->device;
   const char *so = getenv("RXG_STRICT_ORDER");
   c->strict = so && so[0] == '1';
+  const char *nf = getenv("RXG_NO_FUSE");
+  c->fuse = !(nf && nf[0] == '1');
   const char *tp = getenv("RXG_QEQ_TWOPASS");
   c->qeq_mode = (tp && tp[0] == '1') ? 1 : 0;
   *out = c;   // returned even on failure so that rxg_last_error can be read
@@ -592,10 +606,12 @@ int rxg_md_run(rxg_handle h, int nsteps, double dt, int qstep, double Lex_w2, in
     RXG_TRY(halo_move(c));                                   // :75
     RXG_CUDA(cudaStreamSynchronize(c->st));
     double t1 = wall();
-    if (nstep % qstep == 0) RXG_TRY(qeq_device(c));          // :77-83
+    c->lists_shared = false;
+    if (nstep % qstep == 0) RXG_TRY(qeq_device(c, c->fuse)); // :77-83
     RXG_CUDA(cudaStreamSynchronize(c->st));
     double t2 = wall();
-    RXG_TRY(force_device(c));                                // :84
+    RXG_TRY(force_device(c, c->lists_shared));               // :84
+    c->lists_shared = false;
     double t3 = wall();
     c->timers_ms[6] += t1 - t0; c->timers_ms[4] += t2 - t1; c->timers_ms[5] += t3 - t2;
     n = c->natoms;

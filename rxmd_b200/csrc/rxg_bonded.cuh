@@ -926,19 +926,22 @@ inline Bonds make_bonds(Ctx *c) {
 }
 
 // subroutine FORCE on device-resident state, reference src/pot.F90:2-90
-inline int force_device(Ctx *c) {
+// `reuse`: the residents, ghosts, non-bonded cells and the 10 A list of the QEq that just ran are still valid (same step,
+// FORCE-width halo, see qeq_device); only the ghost charges are refreshed.
+inline int force_device(Ctx *c, bool reuse = false) {
   const int NB = c->NB, n = c->natoms;
   RXG_CUDA(cudaMemsetAsync(c->f, 0, sizeof(double) * 3 * NB, c->st));
   RXG_CUDA(cudaMemsetAsync(c->d_acc + ACC_PE, 0, sizeof(double) * 24, c->st));
   double dr[3];
   for (int a = 0; a < 3; a++) dr[a] = c->cfg.nmincell * c->box.lcsize[a];
-  RXG_TRY(halo_copy(c, dr));                                    // src/pot.F90:28
+  if (!reuse) RXG_TRY(halo_copy(c, dr));                        // src/pot.F90:28
+  else RXG_TRY(halo_refresh(c, 4, 1));   // ghost q; + the position round trip FORCE's own MODE_COPY would apply
   const int nt = c->cp[6];
-  LAUNCH(c, k_types, cdiv(nt, 256), 256, 0, c->atype, nt, c->itype, c->gid);
+  if (!reuse) LAUNCH(c, k_types, cdiv(nt, 256), 256, 0, c->atype, nt, c->itype, c->gid);
   RXG_TRY(bin_grid(c, c->gb));                                  // :30
-  RXG_TRY(bin_grid(c, c->gnb));                                 // :31
+  if (!reuse) RXG_TRY(bin_grid(c, c->gnb));                     // :31
   RXG_TRY(build_nbrlist(c));                                    // :33
-  RXG_TRY(build_pairlist<false>(c));                            // :34
+  if (!reuse) RXG_TRY(build_pairlist<0>(c));                    // :34
   Bonds B = make_bonds(c);
   LAUNCH(c, k_boprim, cdiv(nt, 128), 128, 0, nt, c->pos, NB, c->itype, c->d_ff, B, c->deltap1, c->deltap2, c->cdbnd, c->ccbnd, c->s3);
   LAUNCH(c, k_bofull, cdiv(nt, 128), 128, 0, nt, c->itype, c->d_ff, B, c->deltap1, c->deltap2, c->delta);
@@ -954,6 +957,9 @@ inline int force_device(Ctx *c) {
   const double lat[3] = {c->box.lata, c->box.latb, c->box.latc};
   for (int a = 0; a < 3; a++)
     if (dr[a] * lat[a] < c->ff.rctap) full_ok = false;
+  // measured on B200 (979 776-atom RDX): the literal half-list form with fp64 atomics (5.1 ms) beats the full-row form
+  // (7.1 ms, bound by the L1 data pipe on table gathers), so the literal form is the default
+  if (!(getenv("RXG_ENBOND_FULL") && getenv("RXG_ENBOND_FULL")[0] == '1')) full_ok = false;
   const int wgrid = cdiv((long long)n * 32, 256);
   const int ogrid = cdiv((long long)nt * 32, 256);   // warps over cell-ordered slots (ghost slots exit at once)
   if (!full_ok) LAUNCH(c, (k_enbond<true>), ogrid, 256, 0, nt, n, c->rowbeg, c->rowend, c->col, c->pqs, c->tgs, c->d_ff, c->f, NB, c->d_acc);

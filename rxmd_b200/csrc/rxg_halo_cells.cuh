@@ -269,13 +269,15 @@ __global__ void k_move_restore(const double *__restrict__ in, int n, int NB, dou
 }
 
 // value refreshes through the stored selection lists.  which: 1 = (qs,qt) [MODE_QCOPY1], 2 = (hs,ht,q) [MODE_QCOPY2],
-// 3 = (hs,ht) only (single-pass CG)
+// 3 = (hs,ht) only (single-pass CG), 4 = q only (FORCE reusing the QEq halo)
 __global__ void k_pack_vals(int which, const int *__restrict__ sel, int cnt, const double2 *__restrict__ qst,
-                            const double4 *__restrict__ hsq, const double2 *__restrict__ hst, double *__restrict__ buf) {
+                            const double4 *__restrict__ hsq, const double2 *__restrict__ hst, const double *__restrict__ q,
+                            double *__restrict__ buf) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= cnt) return;
   int i = sel[k];
   size_t c = cnt;
+  if (which == 4) { buf[k] = q[i]; return; }
   if (which == 1) { double2 s = qst[i]; buf[k] = s.x; buf[c + k] = s.y; }
   else if (which == 2) { double4 h = hsq[i]; buf[k] = h.x; buf[c + k] = h.y; buf[2 * c + k] = h.z; }
   else { double2 h = hst[i]; buf[k] = h.x; buf[c + k] = h.y; }
@@ -287,6 +289,7 @@ __global__ void k_unpack_vals(int which, int cnt, int dst0, const double *__rest
   if (k >= cnt) return;
   size_t c = cnt;
   int m = dst0 + k;
+  if (which == 4) { q[m] = buf[k]; return; }
   if (which == 1) qst[m] = make_double2(buf[k], buf[c + k]);
   else if (which == 2) { double qq = buf[2 * c + k]; hsq[m] = make_double4(buf[k], buf[c + k], qq, 0.0); q[m] = qq; }
   else { double2 v = make_double2(buf[k], buf[c + k]); hst[m] = v; xs[slot_of[m]] = v; }
@@ -467,14 +470,14 @@ inline int halo_copy(Ctx *c, const double dr[3]) {
 // COPYATOMS(MODE_QCOPY1|2) (+ which=3: hs,ht only).  `roundtrips` position round trips are applied at the end
 // (the reference does one per call, src/comm.F90:222-227,260-264)
 inline int halo_refresh(Ctx *c, int which, int roundtrips) {
-  const int nf = (which == 2) ? 3 : 2;
+  const int nf = (which == 2) ? 3 : (which == 4 ? 1 : 2);
   for (int axis = 0; axis < 3; axis++) {
     const int d0 = 2 * axis + 1;
     const int ns[2] = {c->ns[d0], c->ns[d0 + 1]}, nr[2] = {c->nr[d0], c->nr[d0 + 1]};
     if (ns[0] + ns[1] + nr[0] + nr[1] == 0) continue;
     RXG_TRY(ensure_xbuf(c, (size_t)nf * (size_t)std::max(std::max(ns[0], ns[1]), std::max(nr[0], nr[1]))));
     for (int k = 0; k < 2; k++)
-      if (ns[k] > 0) LAUNCH(c, k_pack_vals, cdiv(ns[k], 256), 256, 0, which, c->sel + c->selptr[d0 - 1 + k], ns[k], c->qst, c->hsq, c->hst, c->sbuf[k]);
+      if (ns[k] > 0) LAUNCH(c, k_pack_vals, cdiv(ns[k], 256), 256, 0, which, c->sel + c->selptr[d0 - 1 + k], ns[k], c->qst, c->hsq, c->hst, c->q, c->sbuf[k]);
     size_t cs[2] = {(size_t)nf * ns[0], (size_t)nf * ns[1]}, cr[2] = {(size_t)nf * nr[0], (size_t)nf * nr[1]};
     double *rb[2];
     RXG_TRY(exchange_axis(c, axis, cs, cr, rb, false));

@@ -77,7 +77,8 @@ __global__ void k_nbrindx(int ntot, int MAXN, const int *__restrict__ nbrcnt, co
 // Inside a row the entries keep the reference's order: stencil cells in mesh order, descending index inside a cell.
 constexpr int PL_WARPS = 8, PL_MAXRUNS = 128;
 constexpr int COL_GHOST = (int)0x80000000, COL_MASK = 0x7fffffff;
-template <bool QEQ, bool FILL>
+// MODE 0: FORCE list, 1: QEq list, 2: both at once (FORCE predicate; hessian = 0 where only the QEq predicate fails)
+template <int MODE, bool FILL>
 __global__ void __launch_bounds__(PL_WARPS * 32) k_pairlist(DevGrid g, const DevFF *__restrict__ ffp, const int *__restrict__ runs,
                                                             int nruns, int natoms, int ncell_res, int *__restrict__ slotcnt,
                                                             const long long *__restrict__ rowoff, long long *__restrict__ rowbeg,
@@ -138,20 +139,20 @@ __global__ void __launch_bounds__(PL_WARPS * 32) k_pairlist(DevGrid g, const Dev
           for (int a = 0; a < nb; a++) {
             const double4 at = sh_a[wid][a];
             const double dr2 = dist2_rn(sub_rn(at.x, o.x), sub_rn(at.y, o.y), sub_rn(at.z, o.z));
-            const bool acc = have && (cslot != ab + a) && (QEQ ? ((float)dr2 < rctap2f) : (dr2 <= ff.rctap2));
+            const bool acc = have && (cslot != ab + a) && (MODE == 1 ? ((float)dr2 < rctap2f) : (dr2 <= ff.rctap2));
             const unsigned mask = __ballot_sync(0xffffffffu, acc);
             if (FILL) {
               const long long wb = __shfl_sync(0xffffffffu, mybase + mycnt, a);
               if (acc) {
                 const long long w = wb + __popc(mask & ((1u << lane) - 1u));
                 col[w] = cval;
-                if (QEQ) {
+                if (MODE >= 1) {
                   double d2 = (double)(float)dr2;                    // real(4) dr2 promoted back
                   int itb = (int)mul_rn(d2, ff.UDRi);
                   double drtb = mul_rn(sub_rn(d2, mul_rn((double)itb, ff.UDR)), ff.UDRi);
                   int inxn = ff.inxn2[(rec_type(at.w) - 1) + ff.nso * (jt - 1)];
                   double h = 0.0;
-                  if (inxn > 0 && itb >= 1 && itb < ff.ntable) {
+                  if (inxn > 0 && itb >= 1 && itb < ff.ntable && (MODE == 1 || (float)dr2 < rctap2f)) {
                     const double *T = ff.TBL_Eclmb_QEq + (size_t)(inxn - 1) * ff.ntable + (itb - 1);
                     h = add_rn(mul_rn(sub_rn(1.0, drtb), T[0]), mul_rn(drtb, T[1]));
                   }
@@ -197,7 +198,7 @@ inline int build_nbrlist(Ctx *c) {
   return RXG_OK;
 }
 
-template <bool QEQ>
+template <int MODE>
 int build_pairlist(Ctx *c) {
   const int n = c->natoms, nt = c->cp[6];
   RXG_CUDA(cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->st));
@@ -206,7 +207,7 @@ int build_pairlist(Ctx *c) {
   RXG_CUDA(cudaMemsetAsync(c->rowend, 0, sizeof(long long) * (size_t)n, c->st));
   const int ncell_res = c->gnb.nc[0] * c->gnb.nc[1] * c->gnb.nc[2];
   const int grid = cdiv((long long)ncell_res * 32, PL_WARPS * 32);
-  LAUNCH(c, (k_pairlist<QEQ, false>), grid, PL_WARPS * 32, 0, c->gnb, c->d_ff, c->d_runs, c->nruns, n, ncell_res, c->rowcnt,
+  LAUNCH(c, (k_pairlist<MODE, false>), grid, PL_WARPS * 32, 0, c->gnb, c->d_ff, c->d_runs, c->nruns, n, ncell_res, c->rowcnt,
          c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->cfg.maxneighbs10, c->d_flag);
   RXG_TRY(ensure_blk(c, nt));
   RXG_TRY(device_scan<long long>(c, c->rowcnt, nt, c->rowoff, c->d_blk64, (long long *)(c->d_acc + 32)));
@@ -226,8 +227,8 @@ int build_pairlist(Ctx *c) {
     RXG_CUDA(cudaMalloc(&c->val, sizeof(double) * c->nnz_cap));
   }
   c->nnz = nnz;
-  c->list_is_qeq = QEQ;
-  LAUNCH(c, (k_pairlist<QEQ, true>), grid, PL_WARPS * 32, 0, c->gnb, c->d_ff, c->d_runs, c->nruns, n, ncell_res, c->rowcnt,
+  c->list_is_qeq = MODE >= 1;
+  LAUNCH(c, (k_pairlist<MODE, true>), grid, PL_WARPS * 32, 0, c->gnb, c->d_ff, c->d_runs, c->nruns, n, ncell_res, c->rowcnt,
          c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->cfg.maxneighbs10, c->d_flag);
   return RXG_OK;
 }
