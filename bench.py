@@ -236,7 +236,7 @@ def main():
     r_g = roof(d[12], d[13], 2)
     roofline = None
     if r_h:
-        roofline = {"kernel": "k_spmv1_tma (QEq CG SpMV: H.(hs,ht), TMA-staged matrix stream, fused Est + 4 dots)", "bound": "hbm", "achieved": r_h[1], "peak": peak,
+        roofline = {"kernel": "k_spmv_rows (QEq CG SpMV H.(hs,ht): TMA-staged matrix stream, 16 lanes per row)", "bound": "hbm", "achieved": r_h[1], "peak": peak,
                     "unit": "GB/s", "frac": r_h[1] / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": r_h[0], "avg_launch_ms": d[10] / d[11], "launches_timed": int(d[11]),
                     "step_share": d[10] / max(t_after[3] - t_before[3], 1e-9),

@@ -172,10 +172,22 @@ int qeq_cg_single(Ctx *c, int nmax, int *iters) {
   LAUNCH(c, k_to_slots, cdiv(c->cp[6], 256), 256, 0, c->cp[6], c->gnb.order, c->qst, c->xs);
   const int tgrid = cdiv(c->cp[6], SP_ROWS);
   const bool tma = !(getenv("RXG_SPMV_NOTMA") && getenv("RXG_SPMV_NOTMA")[0] == '1');
-  if (tma)
-    LAUNCH(c, (k_spmv1_tma<true>), tgrid, SP_ROWS * 32, 0, c->gnb.order, c->cp[6], n, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->xs,
-           c->qst, c->q, c->gst, c->tst, c->ust, c->wst, c->itype, c->d_ff, c->d_acc);
-  else
+  const int lpr = getenv("RXG_SPMV_LPR") ? atoi(getenv("RXG_SPMV_LPR")) : 16;   // measured: 16 lanes/row 1.04 ms, 32: 1.09, 8: 1.29
+  double4 *rowsum = (double4 *)c->tmp;
+  auto spmv_rows = [&]() {
+    const int nt = c->cp[6];
+    if (lpr == 16) LAUNCH(c, (k_spmv_rows<4, 16>), cdiv(nt, 4), 64, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->xs, rowsum);
+    else if (lpr == 816) LAUNCH(c, (k_spmv_rows<8, 16>), cdiv(nt, 8), 128, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->xs, rowsum);
+    else if (lpr == 216) LAUNCH(c, (k_spmv_rows<2, 16>), cdiv(nt, 2), 32, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->xs, rowsum);
+    else if (lpr == 8) LAUNCH(c, (k_spmv_rows<8, 8>), cdiv(nt, 8), 64, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->xs, rowsum);
+    else LAUNCH(c, (k_spmv_rows<4, 32>), cdiv(nt, 4), 128, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->xs, rowsum);
+  };
+  const int dgrid = cdiv(c->cp[6], 256);
+  (void)tgrid;
+  if (tma) {
+    spmv_rows();
+    LAUNCH(c, (k_cg_dots<true>), dgrid, 256, 0, c->gnb.order, c->cp[6], n, rowsum, c->xs, c->q, c->gst, c->tst, c->ust, c->wst, c->itype, c->d_ff, c->d_acc);
+  } else
     LAUNCH(c, (k_spmv1<true>), rgrid, 256, 0, c->gnb.order, c->cp[6], n, c->rowbeg, c->rowend, c->col, c->val, c->xs, c->qst, c->q, c->gst, c->tst, c->ust, c->wst,
            c->itype, c->d_ff, c->d_acc);
   RXG_TRY(allreduce_acc(c, 7, 2));
@@ -187,12 +199,13 @@ int qeq_cg_single(Ctx *c, int nmax, int *iters) {
     LAUNCH(c, k_clear_iter, 1, 1, 0, c->d_acc);
     cudaEventRecord(c->evk[0], c->st);
     if (tma)
-      LAUNCH(c, (k_spmv1_tma<false>), tgrid, SP_ROWS * 32, 0, c->gnb.order, c->cp[6], n, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->xs,
-             c->qst, c->q, c->gst, c->tst, c->ust, c->wst, c->itype, c->d_ff, c->d_acc);
+      spmv_rows();
     else
       LAUNCH(c, (k_spmv1<false>), rgrid, 256, 0, c->gnb.order, c->cp[6], n, c->rowbeg, c->rowend, c->col, c->val, c->xs, c->qst, c->q, c->gst, c->tst, c->ust, c->wst,
              c->itype, c->d_ff, c->d_acc);
     cudaEventRecord(c->evk[1], c->st);
+    if (tma)
+      LAUNCH(c, (k_cg_dots<false>), dgrid, 256, 0, c->gnb.order, c->cp[6], n, rowsum, c->xs, c->q, c->gst, c->tst, c->ust, c->wst, c->itype, c->d_ff, c->d_acc);
     RXG_TRY(allreduce_acc(c, 0, 5));
     RXG_CUDA(cudaMemcpyAsync(c->h_acc, c->d_acc, sizeof(double) * 5, cudaMemcpyDeviceToHost, c->st));
     RXG_CUDA(cudaStreamSynchronize(c->st));

@@ -570,6 +570,116 @@ __global__ void __launch_bounds__(SP_ROWS * 32) k_spmv1_tma(const int *__restric
   else block_accumulate<5>(part, acc + 0);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// Production SpMV, split in two so that the streaming kernel carries no epilogue (measured on B200: the fused epilogue
+// -- scattered loads of g, w, q by the row's lane 0, two vector stores and a 5-value CTA reduction per 4 rows -- cost
+// 0.26 ms of 1.39 ms):
+//   k_spmv_rows : TMA-staged matrix stream, LPR lanes per row, writes the four raw row sums {a, b, ghost a, ghost b}
+//                 of H.(x1,x2) per cell-order slot;
+//   k_cg_dots   : one thread per slot, coalesced; turns row sums into gradient / H.h products, Est and the dots.
+template <int ROWS, int LPR>
+__global__ void __launch_bounds__(ROWS * LPR) k_spmv_rows(const int *__restrict__ order, int ntot, int natoms,
+                                                          const long long *__restrict__ rowoff, const long long *__restrict__ rowbeg,
+                                                          const long long *__restrict__ rowend, const int *__restrict__ col,
+                                                          const double *__restrict__ val, const double2 *__restrict__ x,
+                                                          double4 *__restrict__ rowsum) {
+  constexpr int CAP = ROWS * 480;
+  __shared__ __align__(128) double s_val[CAP];
+  __shared__ __align__(128) int s_col[CAP];
+  __shared__ __align__(8) unsigned long long bar;
+  const int sub = threadIdx.x % LPR, rowid = threadIdx.x / LPR;
+  const int slot0 = blockIdx.x * ROWS;
+  const int slot1 = min(slot0 + ROWS, ntot);
+  const long long sb = rowoff[slot0], se = rowoff[slot1];
+  const int span = (int)(se - sb);
+  const bool staged = span > 0 && span <= CAP;
+  if (staged) {
+    if (threadIdx.x == 0) {
+      mbar_init(&bar, 1);
+      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      mbar_expect_tx(&bar, (unsigned)span * 12u);
+      bulk_g2s(s_val, val + sb, (unsigned)span * 8u, &bar);
+      bulk_g2s(s_col, col + sb, (unsigned)span * 4u, &bar);
+    }
+  }
+  const int slot = slot0 + rowid;
+  int i = natoms;
+  if (slot < ntot) i = order[slot];
+  long long rs = 0, re = 0;
+  if (i < natoms) { rs = rowbeg[i]; re = rowend[i]; }
+  if (staged) mbar_wait(&bar, 0);
+  double a = 0.0, b = 0.0, ga = 0.0, gb = 0.0;
+  if (i < natoms) {
+    if (staged) {
+      const int n = (int)(re - rs);
+      const double *sv = s_val + (rs - sb);
+      const int *sc = s_col + (rs - sb);
+#pragma unroll 8
+      for (int k = sub; k < n; k += LPR) {
+        double h = sv[k];
+        int j = sc[k];
+        double2 v = x[j & COL_MASK];            // x is in slot order: neighbours of a stencil run are contiguous
+        double pa = h * v.x, pb = h * v.y;
+        a += pa; b += pb;
+        if (j < 0) { ga += pa; gb += pb; }      // bit 31 = ghost column
+      }
+    } else {
+      for (long long k = rs + sub; k < re; k += LPR) {
+        double h = __ldcs(val + k);
+        int j = __ldcs(col + k);
+        double2 v = x[j & COL_MASK];
+        double pa = h * v.x, pb = h * v.y;
+        a += pa; b += pb;
+        if (j < 0) { ga += pa; gb += pb; }
+      }
+    }
+  }
+#pragma unroll
+  for (int o = LPR / 2; o > 0; o >>= 1) {
+    a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o);
+    ga += __shfl_xor_sync(0xffffffffu, ga, o); gb += __shfl_xor_sync(0xffffffffu, gb, o);
+  }
+  if (sub == 0 && i < natoms) rowsum[slot] = make_double4(a, b, ga, gb);
+}
+
+template <bool INIT>
+__global__ void __launch_bounds__(256) k_cg_dots(const int *__restrict__ order, int ntot, int natoms, const double4 *__restrict__ rowsum,
+                                                 const double2 *__restrict__ x, const double *__restrict__ q,
+                                                 double2 *__restrict__ gst, double2 *__restrict__ tst, double2 *__restrict__ ust,
+                                                 double2 *__restrict__ wst, const int *__restrict__ itype,
+                                                 const DevFF *__restrict__ ffp, double *__restrict__ acc) {
+  const int slot = blockIdx.x * blockDim.x + threadIdx.x;
+  double part[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
+  int i = natoms;
+  if (slot < ntot) i = order[slot];
+  if (i < natoms) {
+    const double4 r = rowsum[slot];
+    const double2 me = x[slot];
+    const int t = itype[i] - 1;
+    const double eta = ffp->eta[t], chi = ffp->chi[t];
+    if (INIT) {
+      double g1 = sub_rn(sub_rn(-chi, mul_rn(eta, me.x)), r.x);
+      double g2 = sub_rn(sub_rn(-1.0, mul_rn(eta, me.y)), r.y);
+      gst[i] = make_double2(g1, g2);
+      wst[i] = make_double2(2.0 * r.x - r.z, 2.0 * r.y - r.w);
+      part[0] = g1 * g1; part[1] = g2 * g2;
+    } else {
+      double ts = eta * me.x + r.x, tt = eta * me.y + r.y;
+      tst[i] = make_double2(ts, tt);
+      ust[i] = make_double2(2.0 * r.x - r.z, 2.0 * r.y - r.w);
+      const double2 g = gst[i], w = wst[i];
+      const double mu = acc[11], qi = q[i];
+      part[0] = chi * qi + 0.5 * eta * qi * qi + 0.5 * qi * (w.x - mu * w.y);
+      part[1] = ts * me.x; part[2] = tt * me.y; part[3] = g.x * me.x; part[4] = g.y * me.y;
+    }
+  }
+  if (INIT) { double p2[2] = {part[0], part[1]}; block_accumulate<2>(p2, acc + 7); }
+  else block_accumulate<5>(part, acc + 0);
+}
+
 __global__ void k_roll_g(double *__restrict__ acc) {
   acc[9] = acc[7]; acc[10] = acc[8];
   acc[5] = 0.0; acc[6] = 0.0; acc[7] = 0.0; acc[8] = 0.0;
