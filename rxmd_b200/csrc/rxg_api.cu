@@ -288,6 +288,8 @@ int rxg_create(const rxg_config *cfg, rxg_handle *out) {
   c->strict = so && so[0] == '1';
   const char *nf = getenv("RXG_NO_FUSE");
   c->fuse = !(nf && nf[0] == '1');
+  const char *fa = getenv("RXG_FUSE_API");
+  c->fuse_api = fa && fa[0] == '1';
   const char *tp = getenv("RXG_QEQ_TWOPASS");
   c->qeq_mode = (tp && tp[0] == '1') ? 1 : 0;
   *out = c;   // returned even on failure so that rxg_last_error can be read
@@ -473,7 +475,8 @@ int rxg_qeq(rxg_handle h, const int *natoms, const double *atype, double *pos, d
   if (c->cfg.isQEq == 2) { RXG_TRY(h2d_planes(c, c->qsfp, qsfp, 1, n)); }
   {
     Timer t(c, 0);
-    RXG_TRY(qeq_device(c));
+    c->lists_shared = false;
+    RXG_TRY(qeq_device(c, c->fuse_api));   // RXG_FUSE_API=1: build halo + list so that the next rxg_force may reuse them
   }
   RXG_TRY(d2h_planes(c, q, c->q, 1, c->cp[6] > n ? c->cp[6] : n));
   RXG_TRY(d2h_planes(c, pos, c->pos, 3, n));
@@ -494,14 +497,31 @@ int rxg_force(rxg_handle h, const int *natoms, const double *atype, double *pos,
   Ctx *c = (Ctx *)h;
   RXG_TRY(check_ready(c, natoms ? *natoms : -1));
   const int n = *natoms;
+  // RXG_FUSE_API=1: if this call follows rxg_qeq with bit-identical atoms (the host passes back what rxg_qeq returned),
+  // the halo and the 10 A list of that QEq are reused exactly as rxg_md_run does; otherwise the literal path runs
+  bool reuse = false;
+  if (c->fuse_api && c->lists_shared && n == c->natoms && n > 0) {
+    double *stage = c->tmp;   // [4][NB] scratch
+    for (int p = 0; p < 3; p++)
+      RXG_CUDA(cudaMemcpyAsync(stage + (size_t)p * c->NB, pos + (size_t)p * c->NB, sizeof(double) * n, cudaMemcpyHostToDevice, c->st));
+    RXG_CUDA(cudaMemcpyAsync(stage + 3 * (size_t)c->NB, atype, sizeof(double) * n, cudaMemcpyHostToDevice, c->st));
+    RXG_CUDA(cudaMemsetAsync(c->d_flag + 15, 0, sizeof(int), c->st));
+    LAUNCH(c, k_same_atoms, cdiv(n, 256), 256, 0, n, c->NB, stage, c->pos, c->atype, c->d_flag + 15);
+    RXG_CUDA(cudaMemcpyAsync(c->h_int + 15, c->d_flag + 15, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    RXG_CUDA(cudaStreamSynchronize(c->st));
+    reuse = c->h_int[15] == 0;
+  }
   c->natoms = n;
-  RXG_TRY(h2d_planes(c, c->atype, atype, 1, n));
-  RXG_TRY(h2d_planes(c, c->pos, pos, 3, n));
+  if (!reuse) {
+    RXG_TRY(h2d_planes(c, c->atype, atype, 1, n));
+    RXG_TRY(h2d_planes(c, c->pos, pos, 3, n));
+  }
   RXG_TRY(h2d_planes(c, c->q, q, 1, n));
   {
     Timer t(c, 1);
-    RXG_TRY(force_device(c));
+    RXG_TRY(force_device(c, reuse));
   }
+  c->lists_shared = false;
   RXG_TRY(d2h_planes(c, f, c->f, 3, n));
   RXG_TRY(d2h_planes(c, pos, c->pos, 3, n));
   RXG_CUDA(cudaStreamSynchronize(c->st));
@@ -528,6 +548,7 @@ int rxg_move(rxg_handle h, int *natoms, double *atype, double *pos, double *v, d
     for (int i = 0; i < n; i++) { c->h_stage[2 * i] = qs[i]; c->h_stage[2 * i + 1] = qt[i]; }
     RXG_CUDA(cudaMemcpyAsync(c->qst, c->h_stage, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, c->st));
   }
+  c->lists_shared = false;
   {
     Timer t(c, 2);
     RXG_TRY(halo_move(c));

@@ -129,7 +129,7 @@ struct Ctx {
   size_t xbuf_cap = 0;
   long long moved = 0, nccl_msgs = 0;
   ncclComm_t comm = nullptr;
-  bool fuse = true, lists_shared = false;   // md_run: QEq builds halo + 10 A list once for QEq and FORCE of the same step
+  bool fuse = true, fuse_api = false, lists_shared = false;   // md_run: QEq builds halo + 10 A list once for QEq and FORCE of the same step
   int qeq_mode = 0;         // 0 single-pass CG (default), 1 two-pass (literal kernels), strict => literal serial order
   double *tmp = nullptr;    // [12*NB] scratch for MOVE compaction
   double2 *xs = nullptr;    // [NB] CG gather vector in CELL-SORTED order (slot space): {hs,ht} (or {qs,qt} at start)

@@ -312,6 +312,16 @@ __global__ void k_unpack_force(double *__restrict__ f, int NB, const int *__rest
   atomicAdd(&f[2 * (size_t)NB + s], buf[2 * c + k]);
 }
 
+// are the host's residents bit-identical to the device's?  (flag != 0 if not)
+__global__ void k_same_atoms(int n, int NB, const double *__restrict__ stage, const double *__restrict__ pos,
+                             const double *__restrict__ atype, int *__restrict__ flag) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  bool same = stage[i] == pos[i] && stage[(size_t)NB + i] == pos[(size_t)NB + i] && stage[2 * (size_t)NB + i] == pos[2 * (size_t)NB + i] &&
+              stage[3 * (size_t)NB + i] == atype[i];
+  if (!same) atomicExch(flag, 1);
+}
+
 // itype = nint(atype), gtype = l2g(atype): src/pot.F90:37-42, src/main.F90:582-593
 __global__ void k_types(const double *__restrict__ atype, int n, int *__restrict__ itype, int *__restrict__ gid) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
