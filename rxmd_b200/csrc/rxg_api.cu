@@ -372,6 +372,13 @@ int rxg_set_forcefield(rxg_handle h, const rxg_ff *ff) {
       tnb[x * ff->ntable + i] = make_double4(ff->TBL_Evdw[k], ff->TBL_Evdw[k + 1], ff->TBL_Eclmb[k], ff->TBL_Eclmb[k + 1]);
     }
   RXG_TRY(upload(c, tnb.data(), tnb.size(), &d.TBL_nb));
+  std::vector<double2> tq2((size_t)ff->ntable * nb);
+  for (size_t x = 0; x < nb; x++)
+    for (size_t i = 0; i < (size_t)ff->ntable; i++) {
+      size_t k = i + (size_t)ff->ntable * x;
+      tq2[k] = make_double2(ff->TBL_Eclmb_QEq[k], i + 1 < (size_t)ff->ntable ? ff->TBL_Eclmb_QEq[k + 1] : 0.0);
+    }
+  RXG_TRY(upload(c, tq2.data(), tq2.size(), &d.TBL_qeq2));
   if (!c->d_ff) RXG_CUDA(cudaMalloc((void **)&c->d_ff, sizeof(DevFF)));
   RXG_CUDA(cudaMemcpy(c->d_ff, &d, sizeof(DevFF), cudaMemcpyHostToDevice));
   c->have_ff = true;

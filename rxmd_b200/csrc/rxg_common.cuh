@@ -82,6 +82,7 @@ struct DevFF {
   const double *phb1, *phb2, *phb3, *r0hb;
   const int *inxn2, *inxn3, *inxn3hb, *inxn4;
   const double *TBL_Eclmb_QEq;   // (NTABLE, nboty) column-major, as given
+  const double2 *TBL_qeq2;       // [(inxn-1)*NTABLE + (itb-1)] = {T(itb,inxn), T(itb+1,inxn)}
   const double4 *TBL_nb;         // [(inxn-1)*NTABLE + (itb-1)] = {Evdw, CEvdw, Eclmb, CEclmb}: one 32-byte sector per node
 };
 

@@ -147,16 +147,11 @@ __global__ void __launch_bounds__(PL_WARPS * 32) k_pairlist(DevGrid g, const Dev
                 const long long w = wb + __popc(mask & ((1u << lane) - 1u));
                 col[w] = cval;
                 if (MODE >= 1) {
-                  double d2 = (double)(float)dr2;                    // real(4) dr2 promoted back
-                  int itb = (int)mul_rn(d2, ff.UDRi);
-                  double drtb = mul_rn(sub_rn(d2, mul_rn((double)itb, ff.UDR)), ff.UDRi);
+                  // the hessian lerp is evaluated by k_hessian over the compacted rows (full lanes); here only the
+                  // fp32-rounded r^2 and the bond type are parked in the 8 bytes of the value slot
                   int inxn = ff.inxn2[(rec_type(at.w) - 1) + ff.nso * (jt - 1)];
-                  double h = 0.0;
-                  if (inxn > 0 && itb >= 1 && itb < ff.ntable && (MODE == 1 || (float)dr2 < rctap2f)) {
-                    const double *T = ff.TBL_Eclmb_QEq + (size_t)(inxn - 1) * ff.ntable + (itb - 1);
-                    h = add_rn(mul_rn(sub_rn(1.0, drtb), T[0]), mul_rn(drtb, T[1]));
-                  }
-                  val[w] = h;
+                  if (!(MODE == 1 || (float)dr2 < rctap2f)) inxn = 0;
+                  val[w] = __hiloint2double(inxn, __float_as_int((float)dr2));
                 }
               }
             }
@@ -173,9 +168,33 @@ __global__ void __launch_bounds__(PL_WARPS * 32) k_pairlist(DevGrid g, const Dev
       } else {
         rowbeg[mi] = mybase;
         rowend[mi] = mybase + mycnt;
+        if (MODE >= 1)
+          for (int p = mycnt; p < ((mycnt + 3) & ~3); p++) val[mybase + p] = 0.0;   // row padding: inxn = 0 -> hessian 0
       }
     }
     __syncwarp();
+  }
+}
+
+
+// D1: hessian(j1,i) = (1-drtb)*TBL_Eclmb_QEq(itb,inxn) + drtb*TBL_Eclmb_QEq(itb+1,inxn) with real(4) dr2 (src/qeq.F90:234-240).
+// One warp per row, lanes stride over the compacted entries; reads {float r^2, inxn} parked by k_pairlist.
+__global__ void __launch_bounds__(256) k_hessian(long long nnz, const DevFF *__restrict__ ffp, double *__restrict__ val) {
+  // flat over the padded entry range: row padding carries inxn = 0 (written by k_pairlist), which yields 0
+  const DevFF &ff = *ffp;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += stride) {
+    const double packed = val[k];
+    const int inxn = __double2hiint(packed);
+    const double d2 = (double)__int_as_float(__double2loint(packed));   // real(4) dr2 promoted back
+    const int itb = (int)mul_rn(d2, ff.UDRi);
+    const double drtb = mul_rn(sub_rn(d2, mul_rn((double)itb, ff.UDR)), ff.UDRi);
+    double h = 0.0;
+    if (inxn > 0 && itb >= 1 && itb < ff.ntable) {
+      const double2 T = ff.TBL_qeq2[(size_t)(inxn - 1) * ff.ntable + (itb - 1)];   // {T(itb), T(itb+1)}: one 16-byte gather
+      h = add_rn(mul_rn(sub_rn(1.0, drtb), T.x), mul_rn(drtb, T.y));
+    }
+    val[k] = h;
   }
 }
 
@@ -230,6 +249,8 @@ int build_pairlist(Ctx *c) {
   c->list_is_qeq = MODE >= 1;
   LAUNCH(c, (k_pairlist<MODE, true>), grid, PL_WARPS * 32, 0, c->gnb, c->d_ff, c->d_runs, c->nruns, n, ncell_res, c->rowcnt,
          c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->cfg.maxneighbs10, c->d_flag);
+  if (MODE >= 1)
+    LAUNCH(c, k_hessian, 148 * 16, 256, 0, nnz, c->d_ff, c->val);
   return RXG_OK;
 }
 
