@@ -261,25 +261,38 @@ def main():
         h2d = d2h = 0
 
         dthm_of_type = dt * 0.5 / np.maximum(mass, 1e-300)
-        state = {"dthm": dthm_of_type[h_atype[:n].astype(np.int32)]}             # int() truncation == nint here (atype = type + gid*1e-13)
+        # the host integrator (the Fortran driver's O(N) loops, src/main.F90:64-72,86-98) as compiled loops
+        import numba
+
+        @numba.njit(parallel=True, cache=False)
+        def first_half(n, dt, lw2, dthm_t, atype, v, f, q, qsfp, qsfv, pos):
+            for i in numba.prange(n):
+                d = dthm_t[int(atype[i])]                  # int() == nint here: atype = type + gid*1e-13
+                qsfv[i] += 0.5 * dt * lw2 * (q[i] - qsfp[i])
+                qsfp[i] += dt * qsfv[i]
+                for c in range(3):
+                    v[c, i] += d * f[c, i]
+                    pos[c, i] += dt * v[c, i]
+
+        @numba.njit(parallel=True, cache=False)
+        def second_half(n, dt, lw2, dthm_t, atype, v, f, q, qsfp, qsfv):
+            for i in numba.prange(n):
+                d = dthm_t[int(atype[i])]
+                for c in range(3):
+                    v[c, i] += d * f[c, i]
+                qsfv[i] += 0.5 * dt * lw2 * (q[i] - qsfp[i])
 
         def host_step():
             nonlocal n, h2d, d2h
-            dthm = state["dthm"]
-            h_v[:, :n] += dthm * h_f[:, :n]                                            # vkick, src/main.F90:64
-            e.qsfv[:n] += 0.5 * dt * lw2 * (h_q[:n] - e.qsfp[:n])                      # :67-68
-            e.qsfp[:n] += dt * e.qsfv[:n]
-            h_pos[:, :n] += dt * h_v[:, :n]                                            # :72
+            first_half(n, dt, lw2, dthm_of_type, h_atype, h_v, h_f, h_q, e.qsfp, e.qsfv, h_pos)   # :64-72
             e.COPYATOMS(MODE_MOVE, [0.0, 0.0, 0.0], h_atype, h_pos, h_v, h_f, h_q)    # :75
             h2d += 8 * n * 14; d2h_n = e.NATOMS; d2h += 8 * d2h_n * 14
             n = e.NATOMS
             e.QEq(h_atype, h_pos, h_q)                                                 # :80
-            h2d += 8 * n * 5; d2h += 8 * (int(e.fetch_copyptr()[6]) + 5 * n)
+            h2d += 8 * n * 5; d2h += 8 * 6 * n
             e.FORCE(h_atype, h_pos, h_f, h_q)                                          # :84
             h2d += 8 * n * 5; d2h += 8 * n * 6 + 8 * 20
-            dthm = state["dthm"] = dthm_of_type[h_atype[:n].astype(np.int32)]
-            h_v[:, :n] += dthm * h_f[:, :n]                                            # :97
-            e.qsfv[:n] += 0.5 * dt * lw2 * (h_q[:n] - e.qsfp[:n])
+            second_half(n, dt, lw2, dthm_of_type, h_atype, h_v, h_f, h_q, e.qsfp, e.qsfv)         # :86-98
         host_step()
         h2d = d2h = 0
         barrier()

@@ -485,7 +485,7 @@ int rxg_qeq(rxg_handle h, const int *natoms, const double *atype, double *pos, d
     c->lists_shared = false;
     RXG_TRY(qeq_device(c, c->fuse_api));   // RXG_FUSE_API=1: build halo + list so that the next rxg_force may reuse them
   }
-  RXG_TRY(d2h_planes(c, q, c->q, 1, c->cp[6] > n ? c->cp[6] : n));
+  RXG_TRY(d2h_planes(c, q, c->q, 1, n));   // resident charges (ghost entries of the host array are rewritten by every COPYATOMS)
   RXG_TRY(d2h_planes(c, pos, c->pos, 3, n));
   if (c->cfg.isQEq == 1 && qsfp && qsfv) { RXG_TRY(d2h_planes(c, qsfp, c->qsfp, 1, n)); RXG_TRY(d2h_planes(c, qsfv, c->qsfv, 1, n)); }
   RXG_CUDA(cudaStreamSynchronize(c->st));

@@ -172,6 +172,29 @@ def test_cg_modes_agree_within_reference_spread(built):
     e.close(); o.close()
 
 
+def test_fetch_bonds_matches_reference_layout(built):
+    """rxg_fetch_bonds hands WriteBND its inputs in the reference's layout: nbrlist(NBUFFER,0:MAXNEIGHBS), BO(0,:,:)
+    atom index fastest, 1-based neighbour indices (src/fileio.F90:56-121, src/init.F90:163,175)."""
+    import ctypes as C
+    s, cfg, e, o = make("rdx_1x1x1")
+    atype, pos, v, f, q = e.host_arrays(s.ranks[0])
+    o.qeq(); q[:e.NATOMS] = o.f64("q")[:e.NATOMS]
+    o.force(); e.FORCE(atype, pos, f, q)
+    NB, M = cfg.nbuffer, cfg.maxneighbs
+    nbr = np.zeros((M + 1) * NB, dtype=np.int32)
+    bo0 = np.zeros(M * NB)
+    e._chk(e.L.rxg_fetch_bonds(e.h, nbr.ctypes.data_as(C.POINTER(C.c_int)), bo0.ctypes.data_as(C.POINTER(C.c_double))))
+    nbr = nbr.reshape(M + 1, NB); bo0 = bo0.reshape(M, NB)
+    n6 = o.i32("copyptr")[6]
+    cnt, lst, bo_o = o.i32("nbrcnt"), o.i32("nbrlist").reshape(n6, M), o.f64("BO0").reshape(n6, M)
+    assert np.array_equal(nbr[0, :n6], cnt)
+    for i in range(0, n6, 37):
+        for s1 in range(cnt[i]):
+            assert nbr[s1 + 1, i] == lst[i, s1] + 1
+            assert abs(bo0[s1, i] - bo_o[i, s1]) <= 1e-10 * max(abs(bo_o[i, s1]), 1e-30)
+    e.close(); o.close()
+
+
 def test_move_migration_matches(built):
     """COPYATOMS(MODE_MOVE): atoms pushed out of the box re-enter in the reference's order."""
     s, cfg, e, o = make("rdx_2x2x2_disp")
