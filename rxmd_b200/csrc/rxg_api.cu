@@ -273,6 +273,27 @@ int qeq_device(Ctx *c, bool for_force = false) {
 
 }   // namespace
 
+// compact bond storage: 2 int + 16 double planes of `bond_cap` slots, grown on demand (contents need not survive: every
+// FORCE rebuilds them)
+namespace rxg {
+int ensure_bond_capacity(Ctx *c, long long need) {
+  if (need <= c->bond_cap) return RXG_OK;
+  const long long cap = need + need / 8 + 1024;
+  auto re = [&](auto **p) -> int {
+    if (*p) cudaFree(*p);
+    RXG_CUDA(cudaMalloc((void **)p, sizeof(**p) * (size_t)cap));
+    RXG_CUDA(cudaMemsetAsync(*p, 0, sizeof(**p) * (size_t)cap, c->st));
+    return RXG_OK;
+  };
+  RXG_TRY(re(&c->nbrlist)); RXG_TRY(re(&c->nbrindx));
+  for (int k = 0; k < 4; k++) RXG_TRY(re(&c->BO[k]));
+  for (int k = 0; k < 3; k++) { RXG_TRY(re(&c->dln[k])); RXG_TRY(re(&c->cB[k])); }
+  RXG_TRY(re(&c->dBOp)); RXG_TRY(re(&c->A0)); RXG_TRY(re(&c->A1)); RXG_TRY(re(&c->A2)); RXG_TRY(re(&c->A3)); RXG_TRY(re(&c->cdslot));
+  c->bond_cap = cap;
+  return RXG_OK;
+}
+}   // namespace rxg
+
 // ====================================================================================================
 extern "C" {
 
@@ -320,13 +341,10 @@ int rxg_create(const rxg_config *cfg, rxg_handle *out) {
   RXG_TRY(dalloc(c, &c->itype, NB)); RXG_TRY(dalloc(c, &c->gid, NB)); RXG_TRY(dalloc(c, &c->frcindx, NB));
   RXG_TRY(dalloc(c, &c->tmp, 12 * NB));
   RXG_TRY(dalloc(c, &c->xs, NB)); RXG_TRY(dalloc(c, &c->pqa, NB)); RXG_TRY(dalloc(c, &c->pqs, NB)); RXG_TRY(dalloc(c, &c->tgs, NB));
-  RXG_TRY(dalloc(c, &c->nbrcnt, NB)); RXG_TRY(dalloc(c, &c->nbrlist, NS)); RXG_TRY(dalloc(c, &c->nbrindx, NS));
+  RXG_TRY(dalloc(c, &c->nbrcnt, NB)); RXG_TRY(dalloc(c, &c->nbrpad, NS)); RXG_TRY(dalloc(c, &c->bptr, NB + 2));
   RXG_TRY(dalloc(c, &c->rowoff, NB + 2)); RXG_TRY(dalloc(c, &c->rowbeg, NB + 2)); RXG_TRY(dalloc(c, &c->rowend, NB + 2));
   RXG_TRY(dalloc(c, &c->rowcnt, NB + 2));
-  for (int k = 0; k < 4; k++) RXG_TRY(dalloc(c, &c->BO[k], NS));
-  for (int k = 0; k < 3; k++) { RXG_TRY(dalloc(c, &c->dln[k], NS)); RXG_TRY(dalloc(c, &c->cB[k], NS)); }
-  RXG_TRY(dalloc(c, &c->dBOp, NS)); RXG_TRY(dalloc(c, &c->A0, NS)); RXG_TRY(dalloc(c, &c->A1, NS));
-  RXG_TRY(dalloc(c, &c->A2, NS)); RXG_TRY(dalloc(c, &c->A3, NS)); RXG_TRY(dalloc(c, &c->cdslot, NS));
+  RXG_TRY(ensure_bond_capacity(c, 8 * (long long)NB));
   RXG_TRY(dalloc(c, &c->delta, NB)); RXG_TRY(dalloc(c, &c->deltap1, NB)); RXG_TRY(dalloc(c, &c->deltap2, NB));
   RXG_TRY(dalloc(c, &c->nlp, NB)); RXG_TRY(dalloc(c, &c->dDlp, NB)); RXG_TRY(dalloc(c, &c->deltalp, NB));
   RXG_TRY(dalloc(c, &c->ccbnd, NB)); RXG_TRY(dalloc(c, &c->cdbnd, NB));
@@ -449,6 +467,10 @@ int rxg_destroy(rxg_handle h) {
     for (int k = 0; k < 2; k++) { if (c->sbuf[k]) cudaFree(c->sbuf[k]); if (c->rbuf[k]) cudaFree(c->rbuf[k]); }
     if (c->comm) nccl_api().CommDestroy(c->comm);
     if (c->wl) cudaFree(c->wl);
+    for (void *p : {(void *)c->nbrlist, (void *)c->nbrindx, (void *)c->BO[0], (void *)c->BO[1], (void *)c->BO[2], (void *)c->BO[3], (void *)c->dln[0],
+                    (void *)c->dln[1], (void *)c->dln[2], (void *)c->cB[0], (void *)c->cB[1], (void *)c->cB[2], (void *)c->dBOp, (void *)c->A0,
+                    (void *)c->A1, (void *)c->A2, (void *)c->A3, (void *)c->cdslot})
+      if (p) cudaFree(p);
     if (c->h_acc) cudaFreeHost(c->h_acc);
     if (c->h_int) cudaFreeHost(c->h_int);
     if (c->h_stage) cudaFreeHost(c->h_stage);
@@ -583,16 +605,17 @@ int rxg_fetch_bonds(rxg_handle h, int *nbrlist, double *BO0) {
   RXG_TRY(check_ready(c, 0));
   // reference layout: nbrlist(NBUFFER,0:MAXNEIGHBS) / BO(0,NBUFFER,MAXNEIGHBS), atom index fastest (src/init.F90:163,175)
   const int n = c->cp[6], MAXN = c->MAXN, NB = c->NB;
-  std::vector<int> cnt(n), lst((size_t)n * MAXN);
-  std::vector<double> bo((size_t)n * MAXN);
+  std::vector<int> cnt(n), ptr(n + 1), lst((size_t)c->nbonds);
+  std::vector<double> bo((size_t)c->nbonds);
   RXG_CUDA(cudaMemcpy(cnt.data(), c->nbrcnt, sizeof(int) * n, cudaMemcpyDeviceToHost));
-  RXG_CUDA(cudaMemcpy(lst.data(), c->nbrlist, sizeof(int) * n * MAXN, cudaMemcpyDeviceToHost));
-  RXG_CUDA(cudaMemcpy(bo.data(), c->BO[0], sizeof(double) * n * MAXN, cudaMemcpyDeviceToHost));
+  RXG_CUDA(cudaMemcpy(ptr.data(), c->bptr, sizeof(int) * (n + 1), cudaMemcpyDeviceToHost));
+  RXG_CUDA(cudaMemcpy(lst.data(), c->nbrlist, sizeof(int) * c->nbonds, cudaMemcpyDeviceToHost));
+  RXG_CUDA(cudaMemcpy(bo.data(), c->BO[0], sizeof(double) * c->nbonds, cudaMemcpyDeviceToHost));
   for (int i = 0; i < n; i++) {
     if (nbrlist) nbrlist[i] = cnt[i];
     for (int s = 0; s < cnt[i] && s < MAXN; s++) {
-      if (nbrlist) nbrlist[(size_t)(s + 1) * NB + i] = lst[(size_t)i * MAXN + s] + 1;   // 1-based atom indices
-      if (BO0) BO0[(size_t)s * NB + i] = bo[(size_t)i * MAXN + s];
+      if (nbrlist) nbrlist[(size_t)(s + 1) * NB + i] = lst[(size_t)ptr[i] + s] + 1;   // 1-based atom indices
+      if (BO0) BO0[(size_t)s * NB + i] = bo[(size_t)ptr[i] + s];
     }
   }
   return RXG_OK;
@@ -778,6 +801,24 @@ int rxg_debug_fetch(rxg_handle h, const char *name, void *out, long long cap, lo
   else if (s == "cdbnd") dev(c->cdbnd, n6, 8);
   else if (s == "ccbnd") dev(c->ccbnd, n6, 8);
   else { c->err = "rxg_debug_fetch: unknown name " + s; return RXG_ERR_ARG; }
+  static const char *slot_names[] = {"nbrlist", "nbrindx", "BO0", "BO1", "BO2", "BO3", "dln_BOp1", "dln_BOp2", "dln_BOp3", "dBOp", "A0", "A1", "A2", "A3"};
+  bool is_slot = false;
+  for (const char *nm : slot_names) is_slot = is_slot || s == nm;
+  if (is_slot) {   // compact bond slots -> the reference's padded view [n6][MAXN]
+    const size_t esz = (s == "nbrlist" || s == "nbrindx") ? 4 : 8;
+    if (count) *count = NS;
+    if (!out) return RXG_OK;
+    if (cap < (long long)(NS * esz)) return RXG_ERR_ARG;
+    std::vector<int> hc(n6), hp(n6 + 1);
+    RXG_CUDA(cudaMemcpy(hc.data(), c->nbrcnt, sizeof(int) * n6, cudaMemcpyDeviceToHost));
+    RXG_CUDA(cudaMemcpy(hp.data(), c->bptr, sizeof(int) * (n6 + 1), cudaMemcpyDeviceToHost));
+    std::vector<char> hv((size_t)c->nbonds * esz + 8);
+    if (c->nbonds) RXG_CUDA(cudaMemcpy(hv.data(), src, (size_t)c->nbonds * esz, cudaMemcpyDeviceToHost));
+    memset(out, 0, NS * esz);
+    for (long long i = 0; i < n6; i++)
+      memcpy((char *)out + (size_t)i * c->MAXN * esz, hv.data() + (size_t)hp[i] * esz, (size_t)hc[i] * esz);
+    return RXG_OK;
+  }
   if (count) *count = cnt;
   if (out) {
     if (cap < bytes) return RXG_ERR_ARG;

@@ -24,8 +24,9 @@ constexpr double RCHB2 = 100.0;                                                 
 // d_acc layout for FORCE: 16+k = PE(k) k=1..13 ; 32.. reserved (nnz) ; 34..39 astr ; 40..45 kinetic astr ; 48 KE ; 49 sum q
 constexpr int ACC_PE = 16, ACC_ASTR = 34;
 
-struct Bonds {   // per directed slot [i*MAXN + s]
+struct Bonds {   // per directed bond slot, compact: slot of (atom i, s-th neighbour) = ptr[i] + s
   int MAXN;
+  const int *ptr;
   const int *cnt, *lst, *idx;
   double *BO0, *BO1, *BO2, *BO3, *dln1, *dln2, *dln3, *dBOp, *A0, *A1, *A2, *A3;
   double *cB0, *cB1, *cB2, *cdslot;
@@ -50,16 +51,18 @@ __global__ void __launch_bounds__(128) k_boprim(int ntot, const double *__restri
   double dp = -ff.Val[ity - 1];
   const int n = B.cnt[i];
   for (int s = 0; s < n; s++) {
-    size_t a = (size_t)i * B.MAXN + s;
+    size_t a = (size_t)B.ptr[i] + s;
     int j = B.lst[a];
     int x = ff.inxn2[(ity - 1) + ff.nso * (itype[j] - 1)] - 1;
     double dx = sub_rn(xi, pos[j]), dy = sub_rn(yi, pos[NB + j]), dz = sub_rn(zi, pos[2 * NB + j]);
     double dr2 = dist2_rn(dx, dy, dz);
     double b0 = 0, b1 = 0, b2 = 0, b3 = 0, l1 = 0, l2 = 0, l3 = 0, db = 0;
     if (x >= 0 && dr2 <= ff.rc2[x]) {
-      double a1 = ff.cBOp1[x] * pow(dr2, ff.pbo2h[x]);
-      double a2 = ff.cBOp3[x] * pow(dr2, ff.pbo4h[x]);
-      double a3 = ff.cBOp5[x] * pow(dr2, ff.pbo6h[x]);
+      // dr2**p as exp(p*log(dr2)) with one shared logarithm (src/bo.F90:67-69); relative error ~1e-15
+      const double lg = log(dr2);
+      double a1 = ff.cBOp1[x] * exp(ff.pbo2h[x] * lg);
+      double a2 = ff.cBOp3[x] * exp(ff.pbo4h[x] * lg);
+      double a3 = ff.cBOp5[x] * exp(ff.pbo6h[x] * lg);
       b1 = ff.swtch[3 * x] * exp(a1);
       b2 = ff.swtch[3 * x + 1] * exp(a2);
       b3 = ff.swtch[3 * x + 2] * exp(a3);
@@ -99,7 +102,7 @@ __global__ void __launch_bounds__(128) k_bofull(int ntot, const int *__restrict_
   double dsum = 0.0;
   const int n = B.cnt[i];
   for (int s = 0; s < n; s++) {
-    size_t a = (size_t)i * B.MAXN + s;
+    size_t a = (size_t)B.ptr[i] + s;
     int j = B.lst[a];
     int jty = itype[j];
     int x = ff.inxn2[(ity - 1) + ff.nso * (jty - 1)] - 1;
@@ -275,7 +278,7 @@ __global__ void __launch_bounds__(128) k_ebond_elnpr(int natoms, const int *__re
     const int n = B.cnt[i];
     double sum_ovun1 = 0.0, sum_ovun2 = 0.0;
     for (int s = 0; s < n; s++) {
-      size_t a = (size_t)i * B.MAXN + s;
+      size_t a = (size_t)B.ptr[i] + s;
       int j = B.lst[a];
       int x = ff.inxn2[t + ff.nso * (itype[j] - 1)] - 1;
       if (x < 0) continue;
@@ -318,7 +321,7 @@ __global__ void __launch_bounds__(128) k_ebond_elnpr(int natoms, const int *__re
     double CEunder3 = CEunder1 * (1.0 - dD * div1);
     double CEunder4 = CEunder1 * dlp * ff.povun4[t] * expovun1 * (div1 * div1) + CEunder2;
     for (int s = 0; s < n; s++) {
-      size_t a = (size_t)i * B.MAXN + s;
+      size_t a = (size_t)B.ptr[i] + s;
       int j = B.lst[a];
       int x = ff.inxn2[t + ff.nso * (itype[j] - 1)] - 1;
       if (x < 0) continue;
@@ -374,7 +377,7 @@ __global__ void __launch_bounds__(256) k_e3b_enum(int natoms, const int *__restr
   const DevFF &ff = *ffp;
   const int tj = itype[j] - 1;
   const int n = B.cnt[j];
-  const size_t row = (size_t)j * B.MAXN;
+  const size_t row = (size_t)B.ptr[j];
   if (lane == 0) {
     double sum_BO8 = 0.0, sum_SBO1 = 0.0;
     for (int s = 0; s < n; s++) {
@@ -417,7 +420,7 @@ __global__ void __launch_bounds__(128) k_e3b_eval(int nwork, const int2 *__restr
     const DevFF &ff = *ffp;
     const int2 w = wl[t];
     const int j = w.x, i1 = w.y & 0xff, k1 = (w.y >> 8) & 0xff;
-    const size_t row = (size_t)j * B.MAXN;
+    const size_t row = (size_t)B.ptr[j];
     const int jty = itype[j], tj = jty - 1;
     const int i = B.lst[row + i1], k = B.lst[row + k1];
     const int ity = itype[i], kty = itype[k];
@@ -529,7 +532,7 @@ __global__ void k_ehb_enum(int natoms, const int *__restrict__ itype, const DevF
   for (int kt = 0; kt < ff.nso; kt++) donor |= ff.inxn3hb[(ity - 1) + ff.nso * (1 + ff.nso * kt)] != 0;
   if (!donor) return;
   const int n = B.cnt[i];
-  const size_t row = (size_t)i * B.MAXN;
+  const size_t row = (size_t)B.ptr[i];
   for (int s = 0; s < n; s++) {
     if (itype[B.lst[row + s]] == 2 && B.BO0[row + s] > MINBO0) {
       int w = atomicAdd(counter, 1);
@@ -550,7 +553,7 @@ __global__ void __launch_bounds__(256) k_ehb_eval(int nwork, const int2 *__restr
     const DevFF &ff = *ffp;
     const int2 w = wl[t];
     const int i = w.x, s = w.y;
-    const size_t row = (size_t)i * B.MAXN;
+    const size_t row = (size_t)B.ptr[i];
     const int j = B.lst[row + s];
     const double bo = B.BO0[row + s];
     const int si = slot_of[i], sj = slot_of[j];
@@ -627,7 +630,7 @@ __global__ void __launch_bounds__(256) k_e4b_enum(int natoms, const int *__restr
   const DevFF &ff = *ffp;
   const int jty = itype[j], jid = gid[j];
   const int nj = B.cnt[j];
-  const size_t rowj = (size_t)j * B.MAXN;
+  const size_t rowj = (size_t)B.ptr[j];
   for (int k1 = 0; k1 < nj; k1++) {
     double BOjk0 = B.BO0[rowj + k1];
     if (!(BOjk0 > CUTOF2_ESUB)) continue;
@@ -635,7 +638,7 @@ __global__ void __launch_bounds__(256) k_e4b_enum(int natoms, const int *__restr
     if (!(jid < gid[k])) continue;
     int kty = itype[k];
     const int nk = B.cnt[k];
-    const size_t rowk = (size_t)k * B.MAXN;
+    const size_t rowk = (size_t)B.ptr[k];
     const int ncomb = nj * nk;
     for (int p0 = 0; p0 < ncomb; p0 += 32) {
       int p = p0 + lane;
@@ -668,9 +671,9 @@ __global__ void __launch_bounds__(128) k_e4b_eval(int nwork, const int2 *__restr
     const DevFF &ff = *ffp;
     const int2 w = wl[t];
     const int j = w.x, k1 = w.y & 0xff, i1 = (w.y >> 8) & 0xff, l1 = (w.y >> 16) & 0xff;
-    const size_t rowj = (size_t)j * B.MAXN;
+    const size_t rowj = (size_t)B.ptr[j];
     const int k = B.lst[rowj + k1];
-    const size_t rowk = (size_t)k * B.MAXN;
+    const size_t rowk = (size_t)B.ptr[k];
     const int i = B.lst[rowj + i1], l = B.lst[rowk + l1];
     const int ity = itype[i], jty = itype[j], kty = itype[k], lty = itype[l];
     const int x = ff.inxn4[(ity - 1) + ff.nso * ((jty - 1) + ff.nso * ((kty - 1) + ff.nso * (lty - 1)))] - 1;
@@ -787,9 +790,9 @@ __global__ void k_final0(int ntot, Bonds B, double *__restrict__ cdbnd) {
   double s = cdbnd[i];
   const int n = B.cnt[i];
   for (int k = 0; k < n; k++) {
-    size_t a = (size_t)i * B.MAXN + k;
+    size_t a = (size_t)B.ptr[i] + k;
     int j = B.lst[a];
-    s += B.cdslot[(size_t)j * B.MAXN + B.idx[a]];
+    s += B.cdslot[(size_t)B.ptr[j] + B.idx[a]];
   }
   cdbnd[i] = s;
 }
@@ -806,9 +809,9 @@ __global__ void __launch_bounds__(128) k_final1(int ntot, const double *__restri
   const double sdi = s3[i], s6i = s3[NB + i], s5i = s3[2 * (size_t)NB + i];   // E3b per-centre sums of atom i
   double fx = 0, fy = 0, fz = 0, cc = 0.0;
   for (int k = 0; k < n; k++) {
-    size_t a = (size_t)i * B.MAXN + k;
+    size_t a = (size_t)B.ptr[i] + k;
     int j = B.lst[a];
-    size_t b = (size_t)j * B.MAXN + B.idx[a];
+    size_t b = (size_t)B.ptr[j] + B.idx[a];
     double cdj = cdbnd[j];
     double b0 = B.BO0[a];
     double b02 = b0 * b0, b03 = b02 * b0, b07 = b03 * b03 * b0;
@@ -840,7 +843,7 @@ __global__ void __launch_bounds__(128) k_final2(int ntot, const double *__restri
   const double cci = ccbnd[i];
   double fx = 0, fy = 0, fz = 0;
   for (int k = 0; k < n; k++) {
-    size_t a = (size_t)i * B.MAXN + k;
+    size_t a = (size_t)B.ptr[i] + k;
     int j = B.lst[a];
     double w = (cci + ccbnd[j]) * B.dBOp[a];
     fx -= w * (xi - pos[j]); fy -= w * (yi - pos[NB + j]); fz -= w * (zi - pos[2 * NB + j]);
@@ -917,7 +920,7 @@ __global__ void __launch_bounds__(256) k_observe(int n, int NB, const int *__res
 // ---------------------------------------------------------------------------------------------------
 inline Bonds make_bonds(Ctx *c) {
   Bonds B;
-  B.MAXN = c->MAXN; B.cnt = c->nbrcnt; B.lst = c->nbrlist; B.idx = c->nbrindx;
+  B.MAXN = c->MAXN; B.ptr = c->bptr; B.cnt = c->nbrcnt; B.lst = c->nbrlist; B.idx = c->nbrindx;
   B.BO0 = c->BO[0]; B.BO1 = c->BO[1]; B.BO2 = c->BO[2]; B.BO3 = c->BO[3];
   B.dln1 = c->dln[0]; B.dln2 = c->dln[1]; B.dln3 = c->dln[2]; B.dBOp = c->dBOp;
   B.A0 = c->A0; B.A1 = c->A1; B.A2 = c->A2; B.A3 = c->A3;

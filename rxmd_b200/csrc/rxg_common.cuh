@@ -142,7 +142,10 @@ struct Ctx {
   int *d_runs = nullptr;    // stencil runs {dx,dy,dzlo,dzhi}
   int nruns = 0;
   // ---- lists -------------------------------------------------------------------------------------------
-  int *nbrcnt = nullptr, *nbrlist = nullptr, *nbrindx = nullptr;   // [NB], [NB*MAXN], [NB*MAXN]
+  int *nbrcnt = nullptr, *nbrpad = nullptr;       // [NB] counts, [NB*MAXN] padded scratch rows written by k_nbrlist
+  int *bptr = nullptr;                            // [NB+1] first bond slot of each atom (exclusive scan of nbrcnt)
+  int *nbrlist = nullptr, *nbrindx = nullptr;     // [bond_cap] compact: neighbour index / slot of the reverse bond
+  long long bond_cap = 0, nbonds = 0;
   long long *rowoff = nullptr;   // [NB+1] 10 A list: row offsets by CELL-ORDER slot (rows lie in HBM in cell order)
   long long *rowbeg = nullptr, *rowend = nullptr;   // [NB] the same rows addressed by atom index
   int *rowcnt = nullptr;
@@ -150,7 +153,7 @@ struct Ctx {
   double *val = nullptr;         // [nnz_cap] hessian (QEq list only)
   long long nnz_cap = 0, nnz = 0;
   bool list_is_qeq = false;
-  // ---- bond-order products, [NB*MAXN] unless noted -----------------------------------------------------------
+  // ---- bond-order products, [bond_cap] (compact bond slots) unless noted -----------------------------------------------------------
   double *BO[4] = {nullptr, nullptr, nullptr, nullptr}, *dln[3] = {nullptr, nullptr, nullptr}, *dBOp = nullptr;
   double *A0 = nullptr, *A1 = nullptr, *A2 = nullptr, *A3 = nullptr;
   double *cB[3] = {nullptr, nullptr, nullptr};   // accumulated bond coefficients (cf1,cf2,cf3 of ForceBbo) per directed slot

@@ -50,18 +50,27 @@ __global__ void k_nbrlist(DevGrid g, const DevFF *__restrict__ ffp, int ntot, in
   if (cnt > MAXN) atomicMax(ovf, cnt);
 }
 
+// rows of the padded scratch list -> compact bond storage (slot of (i,s) = bptr[i] + s)
+__global__ void k_compact_bonds(int ntot, int MAXN, const int *__restrict__ nbrcnt, const int *__restrict__ bptr,
+                                const int *__restrict__ pad, int *__restrict__ lst) {
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  int i = t / MAXN, s = t % MAXN;
+  if (i >= ntot || s >= nbrcnt[i]) return;
+  lst[(size_t)bptr[i] + s] = pad[(size_t)i * MAXN + s];
+}
 // reverse index: nbrindx(i,i1) = j1 with nbrlist(j,j1) == i, src/main.F90:383-398
-__global__ void k_nbrindx(int ntot, int MAXN, const int *__restrict__ nbrcnt, const int *__restrict__ nbrlist,
-                          int *__restrict__ nbrindx, int *__restrict__ bad) {
+__global__ void k_nbrindx(int ntot, int MAXN, const int *__restrict__ nbrcnt, const int *__restrict__ bptr,
+                          const int *__restrict__ nbrlist, int *__restrict__ nbrindx, int *__restrict__ bad) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   int i = t / MAXN, i1 = t % MAXN;
   if (i >= ntot || i1 >= nbrcnt[i]) return;
-  int j = nbrlist[(size_t)i * MAXN + i1];
+  int j = nbrlist[(size_t)bptr[i] + i1];
   int found = -1;
   int nj = nbrcnt[j];
+  const int *rowj = nbrlist + bptr[j];
   for (int j1 = 0; j1 < nj; j1++)
-    if (nbrlist[(size_t)j * MAXN + j1] == i) found = j1;
-  nbrindx[(size_t)i * MAXN + i1] = found;
+    if (rowj[j1] == i) found = j1;
+  nbrindx[(size_t)bptr[i] + i1] = found;
   if (found < 0) atomicExch(bad, 1);
 }
 
@@ -198,18 +207,27 @@ __global__ void __launch_bounds__(256) k_hessian(long long nnz, const DevFF *__r
   }
 }
 
+int ensure_bond_capacity(Ctx *c, long long need);   // rxg_api.cu
+
 inline int build_nbrlist(Ctx *c) {
   const int n = c->cp[6];
   RXG_CUDA(cudaMemsetAsync(c->d_flag, 0, 2 * sizeof(int), c->st));
   RXG_CUDA(cudaMemsetAsync(c->nbrcnt, 0, sizeof(int) * n, c->st));
-  LAUNCH(c, k_nbrlist, cdiv(n, 128), 128, 0, c->gb, c->d_ff, n, c->cfg.nmincell, c->MAXN, c->nbrcnt, c->nbrlist, c->d_flag);
-  LAUNCH(c, k_nbrindx, cdiv((long long)n * c->MAXN, 256), 256, 0, n, c->MAXN, c->nbrcnt, c->nbrlist, c->nbrindx, c->d_flag + 1);
-  RXG_CUDA(cudaMemcpyAsync(c->h_int, c->d_flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+  LAUNCH(c, k_nbrlist, cdiv(n, 128), 128, 0, c->gb, c->d_ff, n, c->cfg.nmincell, c->MAXN, c->nbrcnt, c->nbrpad, c->d_flag);
+  RXG_TRY(ensure_blk(c, n));
+  RXG_TRY(device_scan<int>(c, c->nbrcnt, n, c->bptr, c->d_blk, c->d_flag + 2));
+  RXG_CUDA(cudaMemcpyAsync(c->h_int, c->d_flag, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
   RXG_CUDA(cudaStreamSynchronize(c->st));
   if (c->h_int[0] > c->MAXN) {
     c->err = "ERROR: overflow of max # in neighbor list, " + std::to_string(c->h_int[0]);
     return RXG_ERR_MAXNEIGHBS;
   }
+  c->nbonds = c->h_int[2];
+  RXG_TRY(ensure_bond_capacity(c, c->nbonds));
+  LAUNCH(c, k_compact_bonds, cdiv((long long)n * c->MAXN, 256), 256, 0, n, c->MAXN, c->nbrcnt, c->bptr, c->nbrpad, c->nbrlist);
+  LAUNCH(c, k_nbrindx, cdiv((long long)n * c->MAXN, 256), 256, 0, n, c->MAXN, c->nbrcnt, c->bptr, c->nbrlist, c->nbrindx, c->d_flag + 1);
+  RXG_CUDA(cudaMemcpyAsync(c->h_int, c->d_flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+  RXG_CUDA(cudaStreamSynchronize(c->st));
   if (c->h_int[1]) {
     c->err = "ERROR: inconsistency between nbrlist and nbrindx found";
     return RXG_ERR_STATE;
