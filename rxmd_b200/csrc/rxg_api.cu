@@ -285,7 +285,7 @@ int ensure_bond_capacity(Ctx *c, long long need) {
     RXG_CUDA(cudaMemsetAsync(*p, 0, sizeof(**p) * (size_t)cap, c->st));
     return RXG_OK;
   };
-  RXG_TRY(re(&c->nbrlist)); RXG_TRY(re(&c->nbrindx));
+  RXG_TRY(re(&c->nbrlist)); RXG_TRY(re(&c->nbrindx)); RXG_TRY(re(&c->bown));
   for (int k = 0; k < 4; k++) RXG_TRY(re(&c->BO[k]));
   for (int k = 0; k < 3; k++) { RXG_TRY(re(&c->dln[k])); RXG_TRY(re(&c->cB[k])); }
   RXG_TRY(re(&c->dBOp)); RXG_TRY(re(&c->A0)); RXG_TRY(re(&c->A1)); RXG_TRY(re(&c->A2)); RXG_TRY(re(&c->A3)); RXG_TRY(re(&c->cdslot));
@@ -467,7 +467,7 @@ int rxg_destroy(rxg_handle h) {
     for (int k = 0; k < 2; k++) { if (c->sbuf[k]) cudaFree(c->sbuf[k]); if (c->rbuf[k]) cudaFree(c->rbuf[k]); }
     if (c->comm) nccl_api().CommDestroy(c->comm);
     if (c->wl) cudaFree(c->wl);
-    for (void *p : {(void *)c->nbrlist, (void *)c->nbrindx, (void *)c->BO[0], (void *)c->BO[1], (void *)c->BO[2], (void *)c->BO[3], (void *)c->dln[0],
+    for (void *p : {(void *)c->nbrlist, (void *)c->nbrindx, (void *)c->bown, (void *)c->BO[0], (void *)c->BO[1], (void *)c->BO[2], (void *)c->BO[3], (void *)c->dln[0],
                     (void *)c->dln[1], (void *)c->dln[2], (void *)c->cB[0], (void *)c->cB[1], (void *)c->cB[2], (void *)c->dBOp, (void *)c->A0,
                     (void *)c->A1, (void *)c->A2, (void *)c->A3, (void *)c->cdslot})
       if (p) cudaFree(p);

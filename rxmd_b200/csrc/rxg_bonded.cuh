@@ -26,7 +26,7 @@ constexpr int ACC_PE = 16, ACC_ASTR = 34;
 
 struct Bonds {   // per directed bond slot, compact: slot of (atom i, s-th neighbour) = ptr[i] + s
   int MAXN;
-  const int *ptr;
+  const int *ptr, *own;   // first slot of an atom; atom that owns a slot
   const int *cnt, *lst, *idx;
   double *BO0, *BO1, *BO2, *BO3, *dln1, *dln2, *dln3, *dBOp, *A0, *A1, *A2, *A3;
   double *cB0, *cB1, *cB2, *cdslot;
@@ -367,45 +367,75 @@ __device__ __forceinline__ int warp_append(bool valid, int *__restrict__ counter
   return valid ? base + __popc(m & ((1u << lane) - 1u)) : -1;
 }
 
-// C3a: E3b enumeration (src/pot.F90:356-386 tests).  One warp per centre atom j.  Also stores the per-centre sums.
-__global__ void __launch_bounds__(256) k_e3b_enum(int natoms, const int *__restrict__ itype, const DevFF *__restrict__ ffp,
-                                                  Bonds B, double2 *__restrict__ sbo, int2 *__restrict__ wl, int cap,
-                                                  int *__restrict__ counter) {
+// reserve `n` consecutive work-list entries for this thread with ONE atomic per warp; returns the thread's first index
+__device__ __forceinline__ int warp_reserve(int n, int *__restrict__ counter) {
   const int lane = threadIdx.x & 31;
-  const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  int inc = n;
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    int y = __shfl_up_sync(0xffffffffu, inc, o);
+    if (lane >= o) inc += y;
+  }
+  int total = __shfl_sync(0xffffffffu, inc, 31);
+  int base = 0;
+  if (lane == 0 && total > 0) base = atomicAdd(counter, total);
+  base = __shfl_sync(0xffffffffu, base, 0);
+  return base + inc - n;
+}
+
+// per-centre sums of E3b (src/pot.F90:360-366), one thread per resident
+__global__ void k_e3b_sums(int natoms, const int *__restrict__ itype, Bonds B, double2 *__restrict__ sbo) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
   if (j >= natoms || itype[j] <= 0) return;
-  const DevFF &ff = *ffp;
-  const int tj = itype[j] - 1;
   const int n = B.cnt[j];
   const size_t row = (size_t)B.ptr[j];
-  if (lane == 0) {
-    double sum_BO8 = 0.0, sum_SBO1 = 0.0;
-    for (int s = 0; s < n; s++) {
-      double b0 = B.BO0[row + s];
-      double b2 = b0 * b0, b4 = b2 * b2;
-      sum_BO8 -= b4 * b4;
-      sum_SBO1 += B.BO2[row + s] + B.BO3[row + s];
-    }
-    sbo[j] = make_double2(exp(sum_BO8), sum_SBO1);
+  double sum_BO8 = 0.0, sum_SBO1 = 0.0;
+  for (int s = 0; s < n; s++) {
+    double b0 = B.BO0[row + s];
+    double b2 = b0 * b0, b4 = b2 * b2;
+    sum_BO8 -= b4 * b4;
+    sum_SBO1 += B.BO2[row + s] + B.BO3[row + s];
   }
-  const int npairs = n * (n - 1) / 2;
-  for (int p0 = 0; p0 < npairs; p0 += 32) {
-    int p = p0 + lane;
-    bool valid = false;
-    int i1 = 0, k1 = 0;
-    if (p < npairs) {
-      int rem = p;
-      while (rem >= n - 1 - i1) { rem -= n - 1 - i1; i1++; }
-      k1 = i1 + 1 + rem;
-      double BOij0 = B.BO0[row + i1], BOjk0 = B.BO0[row + k1];
-      if ((BOij0 - CUTOF2_ESUB > 0.0) && (BOjk0 - CUTOF2_ESUB > 0.0) && (BOij0 * BOjk0 > CUTOF2_ESUB)) {
-        int ity = itype[B.lst[row + i1]], kty = itype[B.lst[row + k1]];
-        valid = ff.inxn3[(ity - 1) + ff.nso * (tj + ff.nso * (kty - 1))] != 0;
+  sbo[j] = make_double2(exp(sum_BO8), sum_SBO1);
+}
+
+// C3a: E3b enumeration (src/pot.F90:356-386 tests).  One thread per directed bond slot (j,i1): partners k1 > i1.
+__global__ void __launch_bounds__(256) k_e3b_enum(int nslots, int natoms, const int *__restrict__ itype,
+                                                  const DevFF *__restrict__ ffp, Bonds B, int2 *__restrict__ wl, int cap,
+                                                  int *__restrict__ counter) {
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
+  const DevFF &ff = *ffp;
+  int j = natoms, i1 = 0, n = 0, tj = 0, ity = 0;
+  size_t row = 0;
+  double BOij0 = 0.0;
+  bool live = false;
+  if (a < nslots) {
+    j = B.own[a];
+    if (j < natoms && itype[j] > 0) {
+      row = (size_t)B.ptr[j];
+      i1 = a - (int)row;
+      n = B.cnt[j];
+      BOij0 = B.BO0[a];
+      live = (BOij0 - CUTOF2_ESUB > 0.0) && i1 + 1 < n;
+      if (live) { tj = itype[j] - 1; ity = itype[B.lst[a]]; }
+    }
+  }
+  auto valid = [&](int k1) {
+    double BOjk0 = B.BO0[row + k1];
+    if (!((BOjk0 - CUTOF2_ESUB > 0.0) && (BOij0 * BOjk0 > CUTOF2_ESUB))) return false;
+    int kty = itype[B.lst[row + k1]];
+    return ff.inxn3[(ity - 1) + ff.nso * (tj + ff.nso * (kty - 1))] != 0;
+  };
+  int cnt = 0;
+  if (live)
+    for (int k1 = i1 + 1; k1 < n; k1++) cnt += valid(k1);
+  int w = warp_reserve(cnt, counter);
+  if (cnt > 0)
+    for (int k1 = i1 + 1; k1 < n; k1++)
+      if (valid(k1)) {
+        if (w < cap) wl[w] = make_int2(j, i1 | (k1 << 8));
+        w++;
       }
-    }
-    int w = warp_append(valid, counter, lane);
-    if (valid && w < cap) wl[w] = make_int2(j, i1 | (k1 << 8));
-  }
 }
 
 // C3b: E3b evaluation (src/pot.F90:388-541), one thread per angle.
@@ -620,44 +650,54 @@ __device__ __forceinline__ double cross_n(const double *a, double na, const doub
   return n < NSMALL ? NSMALL : n;
 }
 
-// C4a: E4b enumeration (tests of src/pot.F90:1022-1081).  One warp per atom j; central bonds in sequence.
-__global__ void __launch_bounds__(256) k_e4b_enum(int natoms, const int *__restrict__ itype, const int *__restrict__ gid,
+// C4a: E4b enumeration (tests of src/pot.F90:1022-1081).  One thread per directed bond slot (j,k1) = central bond j-k.
+__global__ void __launch_bounds__(256) k_e4b_enum(int nslots, int natoms, const int *__restrict__ itype, const int *__restrict__ gid,
                                                   const DevFF *__restrict__ ffp, Bonds B, int2 *__restrict__ wl, int cap,
                                                   int *__restrict__ counter) {
-  const int lane = threadIdx.x & 31;
-  const int j = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  if (j >= natoms || itype[j] <= 0) return;
+  const int a = blockIdx.x * blockDim.x + threadIdx.x;
   const DevFF &ff = *ffp;
-  const int jty = itype[j], jid = gid[j];
-  const int nj = B.cnt[j];
-  const size_t rowj = (size_t)B.ptr[j];
-  for (int k1 = 0; k1 < nj; k1++) {
-    double BOjk0 = B.BO0[rowj + k1];
-    if (!(BOjk0 > CUTOF2_ESUB)) continue;
-    int k = B.lst[rowj + k1];
-    if (!(jid < gid[k])) continue;
-    int kty = itype[k];
-    const int nk = B.cnt[k];
-    const size_t rowk = (size_t)B.ptr[k];
-    const int ncomb = nj * nk;
-    for (int p0 = 0; p0 < ncomb; p0 += 32) {
-      int p = p0 + lane;
-      bool valid = false;
-      int i1 = 0, l1 = 0;
-      if (p < ncomb) {
-        i1 = p / nk; l1 = p - i1 * nk;
-        double BOij0 = B.BO0[rowj + i1], BOkl0 = B.BO0[rowk + l1];
-        int i = B.lst[rowj + i1], l = B.lst[rowk + l1];
-        if ((BOij0 > CUTOF2_ESUB) && ((BOij0 * BOjk0) > CUTOF2_ESUB) && (i != k) && (BOkl0 > CUTOF2_ESUB) &&
-            (BOjk0 * BOkl0 > CUTOF2_ESUB) && (i != l) && (j != l) && ((BOij0 * (BOjk0 * BOjk0) * BOkl0) > MINBO0)) {
-          int ity = itype[i], lty = itype[l];
-          valid = ff.inxn4[(ity - 1) + ff.nso * ((jty - 1) + ff.nso * ((kty - 1) + ff.nso * (lty - 1)))] != 0;
-        }
+  int j = natoms, k = 0, k1 = 0, nj = 0, nk = 0, jty = 0, kty = 0;
+  size_t rowj = 0, rowk = 0;
+  double BOjk0 = 0.0;
+  bool live = false;
+  if (a < nslots) {
+    j = B.own[a];
+    if (j < natoms && itype[j] > 0) {
+      BOjk0 = B.BO0[a];
+      k = B.lst[a];
+      live = (BOjk0 > CUTOF2_ESUB) && (gid[j] < gid[k]);
+      if (live) {
+        rowj = (size_t)B.ptr[j]; rowk = (size_t)B.ptr[k];
+        k1 = a - (int)rowj;
+        nj = B.cnt[j]; nk = B.cnt[k];
+        jty = itype[j]; kty = itype[k];
       }
-      int w = warp_append(valid, counter, lane);
-      if (valid && w < cap) wl[w] = make_int2(j, k1 | (i1 << 8) | (l1 << 16));
     }
   }
+  auto valid = [&](int i1, int l1) {
+    double BOij0 = B.BO0[rowj + i1], BOkl0 = B.BO0[rowk + l1];
+    int i = B.lst[rowj + i1], l = B.lst[rowk + l1];
+    if (!((BOij0 > CUTOF2_ESUB) && ((BOij0 * BOjk0) > CUTOF2_ESUB) && (i != k) && (BOkl0 > CUTOF2_ESUB) &&
+          (BOjk0 * BOkl0 > CUTOF2_ESUB) && (i != l) && (j != l) && ((BOij0 * (BOjk0 * BOjk0) * BOkl0) > MINBO0)))
+      return false;
+    return ff.inxn4[(itype[i] - 1) + ff.nso * ((jty - 1) + ff.nso * ((kty - 1) + ff.nso * (itype[l] - 1)))] != 0;
+  };
+  int cnt = 0;
+  if (live)
+    for (int i1 = 0; i1 < nj; i1++) {
+      if (!(B.BO0[rowj + i1] > CUTOF2_ESUB) || i1 == k1) continue;
+      for (int l1 = 0; l1 < nk; l1++) cnt += valid(i1, l1);
+    }
+  int w = warp_reserve(cnt, counter);
+  if (cnt > 0)
+    for (int i1 = 0; i1 < nj; i1++) {
+      if (!(B.BO0[rowj + i1] > CUTOF2_ESUB) || i1 == k1) continue;
+      for (int l1 = 0; l1 < nk; l1++)
+        if (valid(i1, l1)) {
+          if (w < cap) wl[w] = make_int2(j, k1 | (i1 << 8) | (l1 << 16));
+          w++;
+        }
+    }
 }
 
 // C4b: E4b evaluation (src/pot.F90:1083-1205), one thread per torsion i-j-k-l.
@@ -920,7 +960,7 @@ __global__ void __launch_bounds__(256) k_observe(int n, int NB, const int *__res
 // ---------------------------------------------------------------------------------------------------
 inline Bonds make_bonds(Ctx *c) {
   Bonds B;
-  B.MAXN = c->MAXN; B.ptr = c->bptr; B.cnt = c->nbrcnt; B.lst = c->nbrlist; B.idx = c->nbrindx;
+  B.MAXN = c->MAXN; B.ptr = c->bptr; B.own = c->bown; B.cnt = c->nbrcnt; B.lst = c->nbrlist; B.idx = c->nbrindx;
   B.BO0 = c->BO[0]; B.BO1 = c->BO[1]; B.BO2 = c->BO[2]; B.BO3 = c->BO[3];
   B.dln1 = c->dln[0]; B.dln2 = c->dln[1]; B.dln3 = c->dln[2]; B.dBOp = c->dBOp;
   B.A0 = c->A0; B.A1 = c->A1; B.A2 = c->A2; B.A3 = c->A3;
@@ -973,8 +1013,10 @@ inline int force_device(Ctx *c, bool reuse = false) {
     RXG_CUDA(cudaMemsetAsync(c->d_flag + 12, 0, 3 * sizeof(int), c->st));
     int2 *wl3 = c->wl, *wl4 = c->wl + c->wl_cap3, *wlh = c->wl + c->wl_cap3 + c->wl_cap4;
     LAUNCH(c, k_ehb_enum, cdiv(n, 128), 128, 0, n, c->itype, c->d_ff, B, wlh, (int)c->wl_caph, c->d_flag + 14);
-    LAUNCH(c, k_e3b_enum, wgrid, 256, 0, n, c->itype, c->d_ff, B, c->sbo, wl3, (int)c->wl_cap3, c->d_flag + 12);
-    LAUNCH(c, k_e4b_enum, wgrid, 256, 0, n, c->itype, c->gid, c->d_ff, B, wl4, (int)c->wl_cap4, c->d_flag + 13);
+    const int nslots = (int)c->nbonds;
+    if (attempt == 0) LAUNCH(c, k_e3b_sums, cdiv(n, 128), 128, 0, n, c->itype, B, c->sbo);
+    LAUNCH(c, k_e3b_enum, cdiv(nslots, 256), 256, 0, nslots, n, c->itype, c->d_ff, B, wl3, (int)c->wl_cap3, c->d_flag + 12);
+    LAUNCH(c, k_e4b_enum, cdiv(nslots, 256), 256, 0, nslots, n, c->itype, c->gid, c->d_ff, B, wl4, (int)c->wl_cap4, c->d_flag + 13);
     RXG_CUDA(cudaMemcpyAsync(c->h_int + 12, c->d_flag + 12, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
     RXG_CUDA(cudaStreamSynchronize(c->st));
     const long long n3 = c->h_int[12], n4 = c->h_int[13], nh = c->h_int[14];

@@ -145,6 +145,7 @@ struct Ctx {
   int *nbrcnt = nullptr, *nbrpad = nullptr;       // [NB] counts, [NB*MAXN] padded scratch rows written by k_nbrlist
   int *bptr = nullptr;                            // [NB+1] first bond slot of each atom (exclusive scan of nbrcnt)
   int *nbrlist = nullptr, *nbrindx = nullptr;     // [bond_cap] compact: neighbour index / slot of the reverse bond
+  int *bown = nullptr;                            // [bond_cap] atom that owns each slot
   long long bond_cap = 0, nbonds = 0;
   long long *rowoff = nullptr;   // [NB+1] 10 A list: row offsets by CELL-ORDER slot (rows lie in HBM in cell order)
   long long *rowbeg = nullptr, *rowend = nullptr;   // [NB] the same rows addressed by atom index

@@ -52,11 +52,12 @@ __global__ void k_nbrlist(DevGrid g, const DevFF *__restrict__ ffp, int ntot, in
 
 // rows of the padded scratch list -> compact bond storage (slot of (i,s) = bptr[i] + s)
 __global__ void k_compact_bonds(int ntot, int MAXN, const int *__restrict__ nbrcnt, const int *__restrict__ bptr,
-                                const int *__restrict__ pad, int *__restrict__ lst) {
+                                const int *__restrict__ pad, int *__restrict__ lst, int *__restrict__ own) {
   int t = blockIdx.x * blockDim.x + threadIdx.x;
   int i = t / MAXN, s = t % MAXN;
   if (i >= ntot || s >= nbrcnt[i]) return;
   lst[(size_t)bptr[i] + s] = pad[(size_t)i * MAXN + s];
+  own[(size_t)bptr[i] + s] = i;
 }
 // reverse index: nbrindx(i,i1) = j1 with nbrlist(j,j1) == i, src/main.F90:383-398
 __global__ void k_nbrindx(int ntot, int MAXN, const int *__restrict__ nbrcnt, const int *__restrict__ bptr,
@@ -224,7 +225,7 @@ inline int build_nbrlist(Ctx *c) {
   }
   c->nbonds = c->h_int[2];
   RXG_TRY(ensure_bond_capacity(c, c->nbonds));
-  LAUNCH(c, k_compact_bonds, cdiv((long long)n * c->MAXN, 256), 256, 0, n, c->MAXN, c->nbrcnt, c->bptr, c->nbrpad, c->nbrlist);
+  LAUNCH(c, k_compact_bonds, cdiv((long long)n * c->MAXN, 256), 256, 0, n, c->MAXN, c->nbrcnt, c->bptr, c->nbrpad, c->nbrlist, c->bown);
   LAUNCH(c, k_nbrindx, cdiv((long long)n * c->MAXN, 256), 256, 0, n, c->MAXN, c->nbrcnt, c->bptr, c->nbrlist, c->nbrindx, c->d_flag + 1);
   RXG_CUDA(cudaMemcpyAsync(c->h_int, c->d_flag, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
   RXG_CUDA(cudaStreamSynchronize(c->st));
