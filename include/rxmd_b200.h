@@ -127,9 +127,18 @@ const char *rxg_last_error(rxg_handle h);
 /* subroutine QEq(atype,pos,q)   src/qeq.F90:2     (also writes qsfp,qsfv when isQEq==1, :42-43) */
 int rxg_qeq(rxg_handle h, const int *natoms, const double *atype, double *pos, double *q,
             double *qsfp, double *qsfv, int *nstep_qeq);
-/* subroutine PQEq(atype,pos,q)  src/pqeq.F90:2    (spos = shell displacements, inout) */
+/* subroutine PQEq(atype,pos,q)  src/pqeq.F90:2    (spos = shell displacements spos(NBUFFER,3), in/out: relaxed one capped
+ * step after the CG, :171,187-259).  Needs a handle created with isPQEq = 1 and the PQEq members of rxg_ff. */
 int rxg_pqeq(rxg_handle h, const int *natoms, const double *atype, double *pos, double *q,
              double *spos, double *qsfp, double *qsfv, int *nstep_qeq);
+/* module-global spos(NBUFFER,3) (src/module.F90:286) is shared state of PQEq, FORCE (ENbond_PQEq, src/pot.F90:784) and
+ * COPYATOMS(MODE_MOVE) (src/comm.F90:153,165-167).  The device keeps its own copy: rxg_pqeq refreshes it in both directions;
+ * a host that changes spos elsewhere (restart, MODE_MOVE through rxg_move) brackets the call with these two.
+ * rxg_pqeq_skips: how often get_coulomb_and_dcoulomb_pqeq returned early where the reference then reads an unassigned
+ * variable (src/pqeq.F90:219-231,340-343); this library adds nothing for those pairs. */
+int rxg_spos_upload(rxg_handle h, int natoms, const double *spos);
+int rxg_spos_download(rxg_handle h, int natoms, double *spos);
+long long rxg_pqeq_skips(rxg_handle h);
 /* subroutine FORCE(atype,pos,f,q) src/pot.F90:2   PE(0:13) overwritten, astr(1:6) incremented (:65-72) */
 int rxg_force(rxg_handle h, const int *natoms, const double *atype, double *pos, double *f,
               const double *q, double *PE, double *astr);

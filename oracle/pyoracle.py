@@ -36,6 +36,7 @@ def lib():
         L.orc_set_corrected.argtypes = [C.c_void_p, C.c_int]
         L.orc_set_terms.argtypes = [C.c_void_p, C.c_int]
         L.orc_natoms.argtypes = [C.c_void_p, C.c_int]
+        L.orc_set_spos.argtypes = [C.c_void_p, C.c_int, dp]
         for f in (L.orc_qeq, L.orc_force, L.orc_move):
             f.argtypes = [C.c_void_p]
         L.orc_md_run.argtypes = [C.c_void_p, C.c_int, C.c_double, C.c_int, C.c_double, C.c_int]
@@ -82,6 +83,10 @@ class Oracle:
         n = len(atype)
         a = [None if x is None else np.ascontiguousarray(x, dtype=np.float64) for x in (atype, pos, v, q, qsfp, qsfv)]
         self._chk(self.L.orc_set_atoms(self.h, rank, n, *[_dp(x) for x in a]))
+
+    def set_spos(self, rank, spos):
+        a = np.ascontiguousarray(spos, dtype=np.float64)
+        self._chk(self.L.orc_set_spos(self.h, rank, _dp(a)))
 
     def set_corrected(self, on):
         self.L.orc_set_corrected(self.h, int(on))

@@ -25,6 +25,9 @@ const double MAXANGLE = 0.999999999999, MINANGLE = -0.999999999999, NSMALL = 1e-
 const double PI_RX = 3.14159265358979;                                                  // src/module.F90:90
 const double MINBO0 = 1e-4, CUTOF2_ESUB = 1e-4;                                         // src/module.F90:61-62
 const double CECHRGE = 23.02;                                                           // src/module.F90:683
+const double CCLMB0 = 332.0638, CCLMB0_QEQ = 14.4;                                         // src/module.F90:681-682
+const double EEV_KCAL = 23.060538;                                                      // src/module.F90:191
+const double MAX_SHELL_DISPLACEMENT = 1e-3;                                             // src/pqeq.F90:190
 const double RCHB2 = 100.0;                                                             // src/module.F90:677-678
 const int MAXLAYERS = 5, MAXLAYERS_NB = 10;                                             // src/module.F90:44-45
 enum { MODE_COPY = 1, MODE_MOVE = 2, MODE_CPBK = 3, MODE_QCOPY1 = 4, MODE_QCOPY2 = 5 };   // src/module.F90:38-39
@@ -50,6 +53,16 @@ struct Params {
   std::vector<double> phb1, phb2, phb3, r0hb;
   std::vector<int> inxn2v, inxn3v, inxn3hbv, inxn4v;
   std::vector<double> TBL_Evdw, TBL_Eclmb, TBL_Eclmb_QEq;
+  // module pqeq_vars, src/module.F90:285-304 (after initialize_pqeq :488-613)
+  int ntype_pqeq = 0;
+  std::vector<int> isPolarizable, inxnpqeqv;
+  std::vector<double> Zpqeq, Kspqeq, TBL_pcc, TBL_psc, TBL_pss;
+  bool polarizable(int ity) const { return isPolarizable[ity - 1] != 0; }
+  int inxnpqeq(int a, int b) const { return inxnpqeqv[(a - 1) + ntype_pqeq * (b - 1)]; }
+  // TBL_Eclmb_p??(ntype_pqeq2, NTABLE, 0:1), column-major
+  double tblp(const std::vector<double> &T, int inxn, int itb, int c) const {
+    return T[(size_t)(inxn - 1) + (size_t)ntype_pqeq * ntype_pqeq * ((size_t)(itb - 1) + (size_t)ntable * c)];
+  }
   // 1-based type ids, column-major Fortran layout (see include/rxmd_b200.h)
   int inxn2(int a, int b) const { return (a < 1 || b < 1) ? 0 : inxn2v[(a - 1) + nso * (b - 1)]; }
   int inxn3(int a, int b, int c) const { return inxn3v[(a - 1) + nso * ((b - 1) + nso * (c - 1))]; }
@@ -87,6 +100,8 @@ struct Rank {
   int NB = 0, MAXN = 0, W10 = 0;
   int natoms = 0, copyptr[7] = {0, 0, 0, 0, 0, 0, 0};
   std::vector<double> atype, q, pos, v, f, qs, qt, gs, gt, hs, ht, qsfp, qsfv, frcindx;
+  std::vector<double> spos, fpqeq;   // PQEq: shell displacements spos(NBUFFER,3) src/module.F90:286; fpqeq src/pqeq.F90:20
+  long long pqeq_skips = 0;          // calls where the reference would read an undefined value (see get_clmb_pqeq)
   Grid g, nbg;
   std::vector<int> nbrcnt, nbrlist, nbrindx, nbpcnt, nbplist;
   std::vector<double> hessian;
@@ -146,15 +161,17 @@ struct PackSpec {
   int cpbk1d = -1;                          // index in p1d that carries frcindx (value = sender's index)
 };
 
-PackSpec make_spec(Rank &r, int imode) {    // src/comm.F90:104-229
+PackSpec make_spec(Rank &r, int imode, bool isPQEq) {    // src/comm.F90:104-229
   PackSpec s;
   switch (imode) {
     case MODE_COPY:
       s.p2d = {&r.pos}; s.shift2d = {1};
+      if (isPQEq) { s.p2d.push_back(&r.spos); s.shift2d.push_back(0); }   // :122,129-131
       s.p1d = {&r.atype, &r.q, &r.qs, &r.qt, &r.hs, &r.ht, &r.frcindx}; s.cpbk1d = 6;
       break;
     case MODE_MOVE:
       s.p2d = {&r.pos, &r.v}; s.shift2d = {1, 0};
+      if (isPQEq) { s.p2d.push_back(&r.spos); s.shift2d.push_back(0); }   // :153,165-167
       s.p1d = {&r.atype, &r.q, &r.qs, &r.qt, &r.qsfp, &r.qsfv};
       break;
     case MODE_QCOPY1: s.p1d = {&r.qs, &r.qt}; break;
@@ -186,7 +203,7 @@ int COPYATOMS(World &w, int imode, const double *dr) {
     Rank &r = w.R[ir];
     r.na = r.ns = r.nr = 0;
     r.copyptr[0] = r.natoms;
-    spec[ir] = make_spec(r, imode);
+    spec[ir] = make_spec(r, imode, w.P.cfg.isPQEq != 0);
     if (imode == MODE_CPBK) {
       r.ne = 4;
     } else {
@@ -369,6 +386,31 @@ int NEIGHBORLIST(World &w, Rank &r, int nlayer) {
   return 0;
 }
 
+// get_coulomb_and_dcoulomb_pqeq, src/module.F90:386-417 (the code after the first `return` is dead).
+// Returns false when the reference returns early (dr2 > rctap2) WITHOUT assigning Eclmb / ff.  Two call sites then read
+// a variable the reference never defined for that pair (pqeqs in qeq_initialize src/pqeq.F90:340-343, sf in
+// update_shell_positions :219-231): undefined behaviour in the reference.  The oracle (and the CUDA path) take the
+// physically intended value, a zero contribution (the taper is 0 at the cut-off), and count the events in pqeq_skips so
+// that parity tests can state that none occurred on their inputs.  Table indices outside 1..NTABLE (reference reads
+// out of bounds, like SURVEY Q9) give 0.
+bool get_clmb_pqeq(const Params &P, const double *rr, double &Eclmb, int inxn, const std::vector<double> &T, double *ff) {
+  double dr2 = sum3(rr[0] * rr[0], rr[1] * rr[1], rr[2] * rr[2]);
+  if (dr2 > P.rctap2) return false;
+  int itb = (int)(dr2 * P.UDRi);
+  int itb1 = itb + 1;
+  double drtb = dr2 - itb * P.UDR;
+  drtb = drtb * P.UDRi;
+  double drtb1 = 1.0 - drtb;
+  if (itb < 1 || itb1 > P.ntable) { Eclmb = 0.0; ff[0] = ff[1] = ff[2] = 0.0; return true; }
+  Eclmb = drtb1 * P.tblp(T, inxn, itb, 0) + drtb * P.tblp(T, inxn, itb1, 0);
+  double dEclmb = drtb1 * P.tblp(T, inxn, itb, 1) + drtb * P.tblp(T, inxn, itb1, 1);
+  ff[0] = dEclmb * rr[0]; ff[1] = dEclmb * rr[1]; ff[2] = dEclmb * rr[2];
+  return true;
+}
+#define SX(r, i) r.spos[(i)]
+#define SY(r, i) r.spos[(size_t)r.NB + (i)]
+#define SZ(r, i) r.spos[2 * (size_t)r.NB + (i)]
+
 // GetNonbondingPairList (fp64, <=) src/main.F90:420-477 and qeq_initialize (fp32, <, hessian) src/qeq.F90:183-268
 int PairList(World &w, Rank &r, bool qeq) {
   const Params &P = w.P;
@@ -376,7 +418,9 @@ int PairList(World &w, Rank &r, bool qeq) {
   const int nmesh = r.box.nbnmesh;
   std::fill(r.nbpcnt.begin(), r.nbpcnt.end(), 0);
   int status = 0;
-#pragma omp parallel for collapse(3) schedule(dynamic, 2)
+  const bool pqeq = qeq && P.cfg.isPQEq;
+  long long skips = 0;
+#pragma omp parallel for collapse(3) schedule(dynamic, 2) reduction(+ : skips)
   for (int c1 = 0; c1 < g.nc[0]; c1++)
     for (int c2 = 0; c2 < g.nc[1]; c2++)
       for (int c3 = 0; c3 < g.nc[2]; c3++) {
@@ -386,6 +430,7 @@ int PairList(World &w, Rank &r, bool qeq) {
           if (i >= r.natoms) { status = 1; continue; }
           int ity = nint(r.atype[i]);
           int cnt = 0;
+          double fp = 0.0;   // fpqeq(i), src/pqeq.F90:294
           for (int mn = 0; mn < nmesh; mn++) {
             int c4 = c1 + r.nbmesh[3 * mn], c5 = c2 + r.nbmesh[3 * mn + 1], c6 = c3 + r.nbmesh[3 * mn + 2];
             if (!g.inside(c4, c5, c6)) continue;   // the reference's array is sized so this never triggers
@@ -403,7 +448,19 @@ int PairList(World &w, Rank &r, bool qeq) {
               } else {
                 float dr2 = (float)dr2d;                 // real(4) :: dr2, src/qeq.F90:191
                 if (dr2 < (float)P.rctap2) {             // rctap2 = 100 or 156.25, exact in fp32
-                  if (cnt < r.W10) {
+                  if (cnt < r.W10 && pqeq) {             // qeq_initialize of src/pqeq.F90:262-365
+                    r.nbplist[(size_t)i * r.W10 + cnt] = j;
+                    int jty = nint(r.atype[j]);
+                    double rr[3] = {d0, d1, d2}, pqeqc = 0.0, pqeqs = 0.0, ffd[3];
+                    get_clmb_pqeq(P, rr, pqeqc, P.inxnpqeq(ity, jty), P.TBL_pcc, ffd);   // never skips: fp32 dr2 < rctap2
+                    r.hessian[(size_t)i * r.W10 + cnt] = CCLMB0_QEQ * pqeqc;
+                    fp = fp + CCLMB0_QEQ * pqeqc * P.Zpqeq[jty - 1];                    // Eq. 30, :336
+                    if (P.polarizable(jty)) {
+                      double rs[3] = {RX(r, i) - RX(r, j) - SX(r, j), RY(r, i) - RY(r, j) - SY(r, j), RZ(r, i) - RZ(r, j) - SZ(r, j)};
+                      if (!get_clmb_pqeq(P, rs, pqeqs, P.inxnpqeq(jty, ity), P.TBL_psc, ffd)) skips++;
+                      fp = fp - CCLMB0_QEQ * pqeqs * P.Zpqeq[jty - 1];
+                    }
+                  } else if (cnt < r.W10) {
                     r.nbplist[(size_t)i * r.W10 + cnt] = j;
                     int jty = nint(r.atype[j]);
                     // itb = int(dr2*UDRi): real(4)*real(8) promotes dr2 to double, src/qeq.F90:234-236
@@ -422,9 +479,11 @@ int PairList(World &w, Rank &r, bool qeq) {
             }
           }
           r.nbpcnt[i] = cnt;
+          if (pqeq) r.fpqeq[i] = fp;
           if (cnt > r.W10) status = 2;
         }
       }
+  r.pqeq_skips += skips;
   if (status == 2) { w.err = "ERROR: nbplist greater then MAXNEIGHBS10"; return RXG_ERR_MAXNEIGHBS10; }
   if (status == 1) { w.err = "PairList: ghost atom inside a resident non-bonded cell"; return RXG_ERR_STATE; }
   return 0;
@@ -557,6 +616,201 @@ int QEq(World &w) {   // src/qeq.F90:2-178
     COPYATOMS(w, MODE_QCOPY2, QCopyDr);
   }
   for (auto &r : w.R) r.nstep_qeq = nstep_qeq;
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// PQEq, src/pqeq.F90
+void get_hsh_pqeq(const Params &P, Rank &r, double &Est, double &hshs_sum, double &hsht_sum) {   // :368-439
+  double e = 0, s = 0, t = 0;
+#pragma omp parallel for schedule(static) reduction(+ : e, s, t)
+  for (int i = 0; i < r.natoms; i++) {
+    int ity = nint(r.atype[i]);
+    double eta_ity = P.eta[ity - 1];
+    double t_hshs = eta_ity * r.hs[i], t_hsht = eta_ity * r.ht[i];
+    double qic = r.q[i] + P.Zpqeq[ity - 1];
+    double shelli[3] = {RX(r, i) + SX(r, i), RY(r, i) + SY(r, i), RZ(r, i) + SZ(r, i)};
+    e = e + P.chi[ity - 1] * r.q[i] + 0.5 * eta_ity * r.q[i] * r.q[i];
+    const int *nl = &r.nbplist[(size_t)i * r.W10];
+    const double *hv = &r.hessian[(size_t)i * r.W10];
+    for (int j1 = 0; j1 < r.nbpcnt[i]; j1++) {
+      int j = nl[j1];
+      int jty = nint(r.atype[j]);
+      double qjc = r.q[j] + P.Zpqeq[jty - 1];
+      double shellj[3] = {RX(r, j) + SX(r, j), RY(r, j) + SY(r, j), RZ(r, j) + SZ(r, j)};
+      double Ccicj = 0.0, Csicj = 0.0, Csisj = 0.0, ffd[3];
+      Ccicj = hv[j1] * qic * qjc;
+      if (P.polarizable(ity)) {
+        double dr[3] = {shelli[0] - RX(r, j), shelli[1] - RY(r, j), shelli[2] - RZ(r, j)};
+        get_clmb_pqeq(P, dr, Csicj, P.inxnpqeq(ity, jty), P.TBL_psc, ffd);
+        Csicj = -CCLMB0_QEQ * Csicj * qjc * P.Zpqeq[ity - 1];
+        if (P.polarizable(jty)) {
+          double ds[3] = {shelli[0] - shellj[0], shelli[1] - shellj[1], shelli[2] - shellj[2]};
+          get_clmb_pqeq(P, ds, Csisj, P.inxnpqeq(ity, jty), P.TBL_pss, ffd);
+          Csisj = CCLMB0_QEQ * Csisj * P.Zpqeq[ity - 1] * P.Zpqeq[jty - 1];
+        }
+      }
+      t_hshs = t_hshs + hv[j1] * r.hs[j];
+      t_hsht = t_hsht + hv[j1] * r.ht[j];
+      double Est1 = 0.5 * (Ccicj + Csisj);
+      e = e + Est1 + Csicj;   // no resident/ghost distinction here (:430-433)
+    }
+    s = s + t_hshs * r.hs[i];
+    t = t + t_hsht * r.ht[i];
+  }
+  Est = e; hshs_sum = s; hsht_sum = t;
+}
+
+void get_gradient_pqeq(const Params &P, Rank &r, double *gg) {   // :442-477
+#pragma omp parallel for schedule(static)
+  for (int i = 0; i < r.natoms; i++) {
+    double gssum = 0, gtsum = 0;
+    const int *nl = &r.nbplist[(size_t)i * r.W10];
+    const double *hv = &r.hessian[(size_t)i * r.W10];
+    for (int j1 = 0; j1 < r.nbpcnt[i]; j1++) {
+      int j = nl[j1];
+      gssum = gssum + hv[j1] * r.qs[j];
+      gtsum = gtsum + hv[j1] * r.qt[j];
+    }
+    int ity = nint(r.atype[i]);
+    double eta_ity = P.eta[ity - 1];
+    r.gs[i] = -P.chi[ity - 1] - eta_ity * r.qs[i] - gssum - r.fpqeq[i];
+    r.gt[i] = -1.0 - eta_ity * r.qt[i] - gtsum;
+  }
+  double a = 0, b = 0;
+  for (int i = 0; i < r.natoms; i++) { a += r.gs[i] * r.gs[i]; b += r.gt[i] * r.gt[i]; }
+  gg[0] = a; gg[1] = b;
+}
+
+void update_shell_positions(const Params &P, Rank &r) {   // :187-259
+  std::vector<double> sforce(3 * (size_t)r.natoms, 0.0);
+  const size_t n = r.natoms;
+  long long skips = 0;
+#pragma omp parallel for schedule(guided) reduction(+ : skips)
+  for (int i = 0; i < r.natoms; i++) {
+    int ity = nint(r.atype[i]);
+    if (!P.polarizable(ity)) continue;
+    double sf0 = 0, sf1 = 0, sf2 = 0;
+    if (P.cfg.isEfield) {
+      double e = P.Zpqeq[ity - 1] * P.cfg.eFieldStrength * EEV_KCAL;
+      if (P.cfg.eFieldDir == 1) sf0 = sf0 - e; else if (P.cfg.eFieldDir == 2) sf1 = sf1 - e; else sf2 = sf2 - e;
+    }
+    sf0 = sf0 - P.Kspqeq[ity - 1] * SX(r, i); sf1 = sf1 - P.Kspqeq[ity - 1] * SY(r, i); sf2 = sf2 - P.Kspqeq[ity - 1] * SZ(r, i);   // Eq. 37
+    double shelli[3] = {RX(r, i) + SX(r, i), RY(r, i) + SY(r, i), RZ(r, i) + SZ(r, i)};
+    const int *nl = &r.nbplist[(size_t)i * r.W10];
+    for (int j1 = 0; j1 < r.nbpcnt[i]; j1++) {
+      int j = nl[j1];
+      int jty = nint(r.atype[j]);
+      double qjc = r.q[j] + P.Zpqeq[jty - 1];
+      double shellj[3] = {RX(r, j) + SX(r, j), RY(r, j) + SY(r, j), RZ(r, j) + SZ(r, j)};
+      double dr[3] = {shelli[0] - RX(r, j), shelli[1] - RY(r, j), shelli[2] - RZ(r, j)};
+      double Esc = 0, sf[3] = {0, 0, 0};
+      if (!get_clmb_pqeq(P, dr, Esc, P.inxnpqeq(ity, jty), P.TBL_psc, sf)) skips++;
+      double ff[3] = {-CCLMB0 * sf[0] * qjc * P.Zpqeq[ity - 1], -CCLMB0 * sf[1] * qjc * P.Zpqeq[ity - 1], -CCLMB0 * sf[2] * qjc * P.Zpqeq[ity - 1]};
+      sf0 = sf0 - ff[0]; sf1 = sf1 - ff[1]; sf2 = sf2 - ff[2];
+      if (P.polarizable(jty)) {
+        double ds[3] = {shelli[0] - shellj[0], shelli[1] - shellj[1], shelli[2] - shellj[2]};
+        double Ess = 0, ss[3] = {0, 0, 0};
+        if (!get_clmb_pqeq(P, ds, Ess, P.inxnpqeq(ity, jty), P.TBL_pss, ss)) skips++;
+        double f2[3] = {CCLMB0 * ss[0] * P.Zpqeq[ity - 1] * P.Zpqeq[jty - 1], CCLMB0 * ss[1] * P.Zpqeq[ity - 1] * P.Zpqeq[jty - 1],
+                        CCLMB0 * ss[2] * P.Zpqeq[ity - 1] * P.Zpqeq[jty - 1]};
+        sf0 = sf0 - f2[0]; sf1 = sf1 - f2[1]; sf2 = sf2 - f2[2];
+      }
+    }
+    sforce[i] = sf0; sforce[n + i] = sf1; sforce[2 * n + i] = sf2;
+  }
+  r.pqeq_skips += skips;
+  for (int i = 0; i < r.natoms; i++) {   // Eq. 39, :240-256
+    int ity = nint(r.atype[i]);
+    if (!P.polarizable(ity)) continue;   // (the reference divides by Kspqeq = 0 for them and discards the result)
+    double dr[3] = {sforce[i] / P.Kspqeq[ity - 1], sforce[n + i] / P.Kspqeq[ity - 1], sforce[2 * n + i] / P.Kspqeq[ity - 1]};
+    double ddr = std::sqrt(sum3(dr[0] * dr[0], dr[1] * dr[1], dr[2] * dr[2]));
+    if (ddr > MAX_SHELL_DISPLACEMENT)
+      for (int c = 0; c < 3; c++) dr[c] = dr[c] / ddr * MAX_SHELL_DISPLACEMENT;
+    SX(r, i) = SX(r, i) + dr[0]; SY(r, i) = SY(r, i) + dr[1]; SZ(r, i) = SZ(r, i) + dr[2];
+  }
+}
+
+int PQEq(World &w) {   // src/pqeq.F90:2-182: the QEq driver with the PQEq kernels and the shell relaxation at the end
+  const Params &P = w.P;
+  const int nr_ = (int)w.R.size();
+  int nmax;
+  if (P.cfg.isQEq == 1) {
+    for (auto &r : w.R) {
+      for (int i = 0; i < r.natoms; i++) { r.qsfp[i] = r.q[i]; r.qsfv[i] = 0.0; }
+      std::fill(r.qs.begin(), r.qs.end(), 0.0);
+      std::fill(r.qt.begin(), r.qt.end(), 0.0);
+      for (int i = 0; i < r.natoms; i++) r.qs[i] = r.q[i];
+    }
+    nmax = P.cfg.NMAXQEq;
+  } else if (P.cfg.isQEq == 2) {
+    for (auto &r : w.R)
+      for (int i = 0; i < r.natoms; i++) {
+        r.qs[i] = P.cfg.Lex_fqs * r.qsfp[i] + (1.0 - P.cfg.Lex_fqs) * r.q[i];
+        r.qt[i] = 0.0;
+      }
+    nmax = 1;
+  } else {
+    return 0;
+  }
+  double QCopyDr[3] = {P.rctap / w.R[0].box.lata, P.rctap / w.R[0].box.latb, P.rctap / w.R[0].box.latc};
+  int rc = COPYATOMS(w, MODE_COPY, QCopyDr);
+  if (rc) return rc;
+  for (auto &r : w.R) {
+    rc = LINKEDLIST(w, r, r.nbg, r.box.nblcsize);
+    if (rc) return rc;
+    rc = PairList(w, r, true);
+    if (rc) return rc;
+  }
+  COPYATOMS(w, MODE_QCOPY1, QCopyDr);
+  double Gnew[2] = {0, 0}, Gold[2];
+  for (auto &r : w.R) { double gg[2]; get_gradient_pqeq(P, r, gg); Gnew[0] += gg[0]; Gnew[1] += gg[1]; }
+  for (auto &r : w.R)
+    for (int i = 0; i < r.natoms; i++) { r.hs[i] = r.gs[i]; r.ht[i] = r.gt[i]; }
+  COPYATOMS(w, MODE_QCOPY2, QCopyDr);
+  double GEst2 = 1e99;
+  int nstep_qeq;
+  for (nstep_qeq = 0; nstep_qeq < nmax; nstep_qeq++) {
+    double GEst1 = 0, h_hsh[2] = {0, 0}, g_h[2] = {0, 0};
+    for (int ir = 0; ir < nr_; ir++) {
+      double Est, a, b;
+      get_hsh_pqeq(P, w.R[ir], Est, a, b);
+      GEst1 += Est; h_hsh[0] += a; h_hsh[1] += b;
+    }
+    if (0.5 * (std::fabs(GEst2) + std::fabs(GEst1)) < P.cfg.QEq_tol) break;
+    if (std::fabs(GEst2) > 0.0 && std::fabs(GEst1 / GEst2 - 1.0) < P.cfg.QEq_tol) break;
+    GEst2 = GEst1;
+    for (auto &r : w.R) {
+      double a = 0, b = 0;
+      for (int i = 0; i < r.natoms; i++) { a += r.gs[i] * r.hs[i]; b += r.gt[i] * r.ht[i]; }
+      g_h[0] += a; g_h[1] += b;
+    }
+    float lmin[2] = {(float)(g_h[0] / h_hsh[0]), (float)(g_h[1] / h_hsh[1])};   // real(4) :: lmin, src/pqeq.F90:27
+    double ssum = 0, tsum = 0;
+    for (auto &r : w.R) {
+      double a = 0, b = 0;
+      for (int i = 0; i < r.natoms; i++) {
+        r.qs[i] = r.qs[i] + (double)lmin[0] * r.hs[i];
+        r.qt[i] = r.qt[i] + (double)lmin[1] * r.ht[i];
+      }
+      for (int i = 0; i < r.natoms; i++) { a += r.qs[i]; b += r.qt[i]; }
+      ssum += a; tsum += b;
+    }
+    double mu = ssum / tsum;
+    for (auto &r : w.R)
+      for (int i = 0; i < r.natoms; i++) r.q[i] = r.qs[i] - mu * r.qt[i];
+    COPYATOMS(w, MODE_QCOPY1, QCopyDr);
+    Gold[0] = Gnew[0]; Gold[1] = Gnew[1];
+    Gnew[0] = Gnew[1] = 0;
+    for (auto &r : w.R) { double gg[2]; get_gradient_pqeq(P, r, gg); Gnew[0] += gg[0]; Gnew[1] += gg[1]; }
+    for (auto &r : w.R)
+      for (int i = 0; i < r.natoms; i++) {
+        r.hs[i] = r.gs[i] + (Gnew[0] / Gold[0]) * r.hs[i];
+        r.ht[i] = r.gt[i] + (Gnew[1] / Gold[1]) * r.ht[i];
+      }
+    COPYATOMS(w, MODE_QCOPY2, QCopyDr);
+  }
+  for (auto &r : w.R) { r.nstep_qeq = nstep_qeq; update_shell_positions(P, r); }   // :171
   return 0;
 }
 
@@ -841,6 +1095,84 @@ void ENbond(const Params &P, Rank &r) {   // src/pot.F90:676-781
     }
   }
   r.PE[11] += pe11; r.PE[12] += pe12; r.PE[13] += pe13;
+}
+
+void ENbond_PQEq(const Params &P, Rank &r) {   // src/pot.F90:784-923
+  double pe11 = 0, pe12 = 0, pe13 = 0;
+#pragma omp parallel for schedule(guided) reduction(+ : pe11, pe12, pe13)
+  for (int i = 0; i < r.natoms; i++) {
+    int ity = r.itype[i], iid = r.gtype[i];
+    double Eshell = 0.0;
+    if (P.polarizable(ity)) {
+      double dr2 = sum3(SX(r, i) * SX(r, i), SY(r, i) * SY(r, i), SZ(r, i) * SZ(r, i));
+      Eshell = 0.5 * P.Kspqeq[ity - 1] * dr2;
+    }
+    pe13 += CECHRGE * (P.chi[ity - 1] * r.q[i] + 0.5 * P.eta[ity - 1] * (r.q[i] * r.q[i])) + Eshell;
+    double qic = r.q[i] + P.Zpqeq[ity - 1];
+    const int *nl = &r.nbplist[(size_t)i * r.W10];
+    for (int j1 = 0; j1 < r.nbpcnt[i]; j1++) {
+      int j = nl[j1];
+      int jid = r.gtype[j];
+      if (iid < jid) {   // :838 (note: the opposite sense of ENbond's jid<iid)
+        double dr[3] = {RX(r, i) - RX(r, j), RY(r, i) - RY(r, j), RZ(r, i) - RZ(r, j)};
+        double dr2 = sum3(dr[0] * dr[0], dr[1] * dr[1], dr[2] * dr[2]);
+        int jty = r.itype[j];
+        int inxn = P.inxn2(ity, jty);
+        int itb = (int)(dr2 * P.UDRi);
+        int itb1 = itb + 1;
+        double drtb = dr2 - itb * P.UDR;
+        drtb = drtb * P.UDRi;
+        double drtb1 = 1.0 - drtb;
+        double PEvdw = 0.0, CEvdw = 0.0;
+        if (inxn > 0 && itb >= 1 && itb1 <= P.ntable) {   // out of bounds in the reference otherwise (Q9)
+          PEvdw = drtb1 * P.evdw(0, itb, inxn) + drtb * P.evdw(0, itb1, inxn);
+          CEvdw = drtb1 * P.evdw(1, itb, inxn) + drtb * P.evdw(1, itb1, inxn);
+        }
+        double qjc = r.q[j] + P.Zpqeq[jty - 1];
+        double qij = qic * qjc;
+        double Ecc = 0, Esc = 0, Ecs = 0, Ess = 0;
+        double fcc[3] = {0, 0, 0}, fsc[3] = {0, 0, 0}, fcs[3] = {0, 0, 0}, fss[3] = {0, 0, 0};
+        get_clmb_pqeq(P, dr, Ecc, P.inxnpqeq(ity, jty), P.TBL_pcc, fcc);
+        for (int c = 0; c < 3; c++) fcc[c] = CCLMB0 * qij * fcc[c];
+        Ecc = CCLMB0 * Ecc * qij;
+        if (P.polarizable(ity)) {
+          double d[3] = {dr[0] + SX(r, i), dr[1] + SY(r, i), dr[2] + SZ(r, i)};
+          get_clmb_pqeq(P, d, Esc, P.inxnpqeq(ity, jty), P.TBL_psc, fsc);
+          for (int c = 0; c < 3; c++) fsc[c] = -CCLMB0 * P.Zpqeq[ity - 1] * qjc * fsc[c];
+          Esc = -CCLMB0 * Esc * P.Zpqeq[ity - 1] * qjc;
+        }
+        if (P.polarizable(jty)) {
+          double d[3] = {dr[0] - SX(r, j), dr[1] - SY(r, j), dr[2] - SZ(r, j)};
+          get_clmb_pqeq(P, d, Ecs, P.inxnpqeq(jty, ity), P.TBL_psc, fcs);
+          for (int c = 0; c < 3; c++) fcs[c] = -CCLMB0 * P.Zpqeq[jty - 1] * qic * fcs[c];
+          Ecs = -CCLMB0 * Ecs * qic * P.Zpqeq[jty - 1];
+        }
+        if (P.polarizable(ity) && P.polarizable(jty)) {
+          double d[3] = {dr[0] + SX(r, i) - SX(r, j), dr[1] + SY(r, i) - SY(r, j), dr[2] + SZ(r, i) - SZ(r, j)};
+          get_clmb_pqeq(P, d, Ess, P.inxnpqeq(ity, jty), P.TBL_pss, fss);
+          for (int c = 0; c < 3; c++) fss[c] = CCLMB0 * P.Zpqeq[ity - 1] * P.Zpqeq[jty - 1] * fss[c];
+          Ess = CCLMB0 * Ess * P.Zpqeq[ity - 1] * P.Zpqeq[jty - 1];
+        }
+        double PEclmb = Ecc + Esc + Ecs + Ess;
+        pe11 += PEvdw;
+        pe12 += PEclmb;
+        double ff[3];
+        for (int c = 0; c < 3; c++) ff[c] = CEvdw * dr[c] + fcc[c] + fcs[c] + fsc[c] + fss[c];
+        addf(r, i, -ff[0], -ff[1], -ff[2]);
+        addf(r, j, ff[0], ff[1], ff[2]);
+      }
+    }
+  }
+  r.PE[11] += pe11; r.PE[12] += pe12; r.PE[13] += pe13;
+}
+
+void EEfield(const Params &P, Rank &r) {   // src/module.F90:359-383 (the energy is "to be determined" there: none added)
+  for (int i = 0; i < r.natoms; i++) {
+    int ity = nint(r.atype[i]);
+    double qic = r.q[i] + P.Zpqeq[ity - 1];
+    double Eforce = -qic * P.cfg.eFieldStrength * EEV_KCAL;
+    r.f[(size_t)(P.cfg.eFieldDir - 1) * r.NB + i] += Eforce;
+  }
 }
 
 void Ebond(const Params &P, Rank &r) {   // src/pot.F90:926-977
@@ -1289,12 +1621,13 @@ int FORCE(World &w) {   // src/pot.F90:2-90
     BOPRIM(P, r);
     BOFULL(P, r);
     const int tm = w.term_mask;   // diagnostic term selection; parity runs use all terms (0x3f)
-    if (tm & 1) ENbond(P, r);
+    if (tm & 1) { if (P.cfg.isPQEq) ENbond_PQEq(P, r); else ENbond(P, r); }
     if (tm & 2) Ebond(P, r);
     Elnpr(P, r, (tm & 4) != 0);   // the preparation loop feeds E3b and always runs
     if (tm & 8) Ehb(P, r);
     if (tm & 16) E3b(P, r);
     if (tm & 32) E4b(P, r);
+    if (P.cfg.isEfield && P.cfg.isPQEq) EEfield(P, r);   // src/pot.F90:61 (reads Zpqeq: only meaningful with PQEq)
     ForceBondedTerms(r, w.corrected);
     for (int i = 0; i < r.copyptr[6]; i++) {   // :65-72
       r.astr[0] += RX(r, i) * FX(r, i); r.astr[1] += RY(r, i) * FY(r, i); r.astr[2] += RZ(r, i) * FZ(r, i);
@@ -1340,6 +1673,14 @@ int orc_create(const rxg_config *cfg, const rxg_ff *ff, const rxg_box *boxes, in
   cpy(P.TBL_Evdw, ff->TBL_Evdw, (size_t)2 * P.ntable * nb);
   cpy(P.TBL_Eclmb, ff->TBL_Eclmb, (size_t)2 * P.ntable * nb);
   cpy(P.TBL_Eclmb_QEq, ff->TBL_Eclmb_QEq, (size_t)P.ntable * nb);
+  if (cfg->isPQEq) {
+    if (ff->ntype_pqeq < 1 || !ff->isPolarizable || !ff->TBL_Eclmb_pcc) { delete w; return RXG_ERR_ARG; }
+    const size_t np = ff->ntype_pqeq, nt2 = np * np * (size_t)P.ntable * 2;
+    P.ntype_pqeq = (int)np;
+    cpyi(P.isPolarizable, ff->isPolarizable, np); cpyi(P.inxnpqeqv, ff->inxnpqeq, np * np);
+    cpy(P.Zpqeq, ff->Zpqeq, np); cpy(P.Kspqeq, ff->Kspqeq, np);
+    cpy(P.TBL_pcc, ff->TBL_Eclmb_pcc, nt2); cpy(P.TBL_psc, ff->TBL_Eclmb_psc, nt2); cpy(P.TBL_pss, ff->TBL_Eclmb_pss, nt2);
+  }
   w->R.resize(nranks);
   for (int ir = 0; ir < nranks; ir++) {
     Rank &r = w->R[ir];
@@ -1351,7 +1692,8 @@ int orc_create(const rxg_config *cfg, const rxg_ff *ff, const rxg_box *boxes, in
     for (auto *p : {&r.atype, &r.q, &r.qs, &r.qt, &r.gs, &r.gt, &r.hs, &r.ht, &r.qsfp, &r.qsfv, &r.frcindx, &r.delta,
                     &r.deltap1, &r.deltap2, &r.nlp, &r.dDlp, &r.deltalp, &r.ccbnd, &r.cdbnd})
       p->assign(nb_, 0.0);
-    for (auto *p : {&r.pos, &r.v, &r.f}) p->assign(3 * nb_, 0.0);
+    for (auto *p : {&r.pos, &r.v, &r.f, &r.spos}) p->assign(3 * nb_, 0.0);
+    r.fpqeq.assign(nb_, 0.0);
     r.g.setup(r.box.cc, MAXLAYERS, r.NB);
     r.nbg.setup(r.box.nbcc, MAXLAYERS_NB, r.NB);
     r.nbrcnt.assign(nb_, 0);
@@ -1401,6 +1743,14 @@ int orc_set_atoms(orc_world h, int rank, int natoms, const double *atype, const 
 
 int orc_natoms(orc_world h, int rank) { return ((World *)h)->R[rank].natoms; }
 
+int orc_set_spos(orc_world h, int rank, const double *spos) {   // compact [3][natoms]
+  World *w = (World *)h;
+  Rank &r = w->R[rank];
+  for (int c = 0; c < 3; c++)
+    for (int i = 0; i < r.natoms; i++) r.spos[(size_t)c * r.NB + i] = spos[(size_t)c * r.natoms + i];
+  return 0;
+}
+
 static int check_rows(World *w) {
   for (auto &r : w->R)
     if ((size_t)r.natoms * r.W10 > r.nbplist.size()) {
@@ -1415,7 +1765,7 @@ int orc_qeq(orc_world h) {
   World *w = (World *)h;
   double t0 = now();
   check_rows(w);
-  int rc = QEq(*w);
+  int rc = w->P.cfg.isPQEq ? PQEq(*w) : QEq(*w);   // src/main.F90:27-31,78-82
   w->t_qeq += now() - t0;
   return rc;
 }
@@ -1440,6 +1790,7 @@ int orc_move(orc_world h) {
 int orc_md_run(orc_world h, int nsteps, double dt, int qstep, double Lex_w2, int step0) {
   World *w = (World *)h;
   const Params &P = w->P;
+  if (P.cfg.isEfield) { w->err = "orc_md_run: LinearMomentum (src/main.F90:71) is not restated; isEfield unsupported here"; return RXG_ERR_ARG; }
   for (int nstep = step0; nstep < step0 + nsteps; nstep++) {
     for (auto &r : w->R) {
       for (int i = 0; i < r.natoms; i++) {
@@ -1500,6 +1851,8 @@ long long orc_get_f64(orc_world h, int rank, const char *name, double *out, long
   if (s == "pos") return put3(r.pos, r.NB, n, out, cap);
   if (s == "v") return put3(r.v, r.NB, n, out, cap);
   if (s == "f") return put3(r.f, r.NB, n, out, cap);
+  if (s == "spos") return put3(r.spos, r.NB, n, out, cap);
+  if (s == "fpqeq") return put(r.fpqeq, r.natoms, out, cap);
   if (s == "BO0") return put(r.BO[0], ns, out, cap);
   if (s == "BO1") return put(r.BO[1], ns, out, cap);
   if (s == "BO2") return put(r.BO[2], ns, out, cap);
@@ -1529,6 +1882,7 @@ long long orc_get_i32(orc_world h, int rank, const char *name, int *out, long lo
   if (s == "nbplist") return puti(r.nbplist.data(), (size_t)r.natoms * r.W10);
   if (s == "nstep_qeq") return puti(&r.nstep_qeq, 1);
   if (s == "natoms") return puti(&r.natoms, 1);
+  if (s == "pqeq_skips") { int k = (int)r.pqeq_skips; return puti(&k, 1); }
   return -1;
 }
 

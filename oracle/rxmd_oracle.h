@@ -34,9 +34,11 @@ const char *orc_last_error(orc_world w);
 int orc_set_atoms(orc_world w, int rank, int natoms, const double *atype, const double *pos, const double *v,
                   const double *q, const double *qsfp, const double *qsfv);
 int orc_natoms(orc_world w, int rank);
+/* PQEq shell displacements spos(NBUFFER,3) of the residents, compact double[3*natoms] (zero after orc_set_atoms) */
+int orc_set_spos(orc_world w, int rank, const double *spos);
 
 /* the reference entry points, executed on every simulated rank */
-int orc_qeq(orc_world w);                    /* subroutine QEq   src/qeq.F90:2   */
+int orc_qeq(orc_world w);                    /* subroutine QEq src/qeq.F90:2, or PQEq src/pqeq.F90:2 when cfg.isPQEq */
 int orc_force(orc_world w);                  /* subroutine FORCE src/pot.F90:2   */
 int orc_move(orc_world w);                   /* COPYATOMS(MODE_MOVE) src/main.F90:75 */
 /* nsteps iterations of the main loop body src/main.F90:64-98 (mdmode 1); call orc_qeq+orc_force first */
@@ -44,8 +46,8 @@ int orc_md_run(orc_world w, int nsteps, double dt, int qstep, double Lex_w2, int
 
 /* fetch a per-rank array; returns element count (or -1). out may be NULL to query the count.
  * double names: atype q pos v f qs qt gs gt hs ht qsfp qsfv hessian BO(4 planes) dBOp dln_BOp A0 A1 A2 A3 delta
- *               deltap1 deltap2 nlp dDlp deltalp ccbnd cdbnd PE(14) astr(6) frcindx
- * int names   : copyptr(7) nbrcnt nbrlist nbrindx nbpcnt nbplist nstep_qeq natoms */
+ *               deltap1 deltap2 nlp dDlp deltalp ccbnd cdbnd PE(14) astr(6) frcindx spos fpqeq
+ * int names   : copyptr(7) nbrcnt nbrlist nbrindx nbpcnt nbplist nstep_qeq natoms pqeq_skips */
 long long orc_get_f64(orc_world w, int rank, const char *name, double *out, long long cap);
 long long orc_get_i32(orc_world w, int rank, const char *name, int *out, long long cap);
 /* global sums over ranks: PE(0:13), KE, sum q */

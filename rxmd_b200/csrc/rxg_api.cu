@@ -184,7 +184,12 @@ int qeq_cg_single(Ctx *c, int nmax, int *iters) {
   };
   const int dgrid = cdiv(c->cp[6], 256);
   (void)tgrid;
-  if (tma) {
+  const bool pq = c->cfg.isPQEq != 0;   // PQEq: same CG, other gradient constant and Est (rxg_pqeq.cuh)
+  if (pq) {
+    spmv_rows();
+    LAUNCH(c, (k_cg_dots_pqeq<true>), dgrid, 256, 0, c->gnb.order, c->cp[6], n, rowsum, c->xs, c->q, c->gst, c->tst, c->ust, c->wst, c->itype, c->d_ff,
+           c->prow, c->pcs, c->sps, c->d_acc);
+  } else if (tma) {
     spmv_rows();
     LAUNCH(c, (k_cg_dots<true>), dgrid, 256, 0, c->gnb.order, c->cp[6], n, rowsum, c->xs, c->q, c->gst, c->tst, c->ust, c->wst, c->itype, c->d_ff, c->d_acc);
   } else
@@ -198,13 +203,16 @@ int qeq_cg_single(Ctx *c, int nmax, int *iters) {
   for (it = 0; it < nmax; it++) {
     LAUNCH(c, k_clear_iter, 1, 1, 0, c->d_acc);
     cudaEventRecord(c->evk[0], c->st);
-    if (tma)
+    if (tma || pq)
       spmv_rows();
     else
       LAUNCH(c, (k_spmv1<false>), rgrid, 256, 0, c->gnb.order, c->cp[6], n, c->rowbeg, c->rowend, c->col, c->val, c->xs, c->qst, c->q, c->gst, c->tst, c->ust, c->wst,
              c->itype, c->d_ff, c->d_acc);
     cudaEventRecord(c->evk[1], c->st);
-    if (tma)
+    if (pq)
+      LAUNCH(c, (k_cg_dots_pqeq<false>), dgrid, 256, 0, c->gnb.order, c->cp[6], n, rowsum, c->xs, c->q, c->gst, c->tst, c->ust, c->wst, c->itype, c->d_ff,
+             c->prow, c->pcs, c->sps, c->d_acc);
+    else if (tma)
       LAUNCH(c, (k_cg_dots<false>), dgrid, 256, 0, c->gnb.order, c->cp[6], n, rowsum, c->xs, c->q, c->gst, c->tst, c->ust, c->wst, c->itype, c->d_ff, c->d_acc);
     RXG_TRY(allreduce_acc(c, 0, 5));
     RXG_CUDA(cudaMemcpyAsync(c->h_acc, c->d_acc, sizeof(double) * 5, cudaMemcpyDeviceToHost, c->st));
@@ -219,7 +227,8 @@ int qeq_cg_single(Ctx *c, int nmax, int *iters) {
     GEst2 = GEst1;
     float lmin_s = (float)(c->h_acc[3] / c->h_acc[1]);   // real(4) :: lmin, src/qeq.F90:23,133
     float lmin_t = (float)(c->h_acc[4] / c->h_acc[2]);
-    LAUNCH(c, k_roll_g, 1, 1, 0, c->d_acc);
+    if (pq) LAUNCH(c, k_roll_g_pqeq, 1, 1, 0, c->d_acc, lmin_s, lmin_t);
+    else LAUNCH(c, k_roll_g, 1, 1, 0, c->d_acc);
     LAUNCH(c, k_cg_update1, cdiv(n, 256), 256, 0, n, lmin_s, lmin_t, c->hst, c->tst, c->ust, c->qst, c->gst, c->wst, c->d_acc);
     RXG_TRY(allreduce_acc(c, 5, 4));
     LAUNCH(c, k_cg_update2, cdiv(n, 256), 256, 0, n, c->qst, c->gst, c->hst, c->xs, c->gnb.slot_of, c->q, c->d_acc);
@@ -254,15 +263,34 @@ int qeq_device(Ctx *c, bool for_force = false) {
       c->lists_shared = true;
     }
   }
+  const bool pq = c->cfg.isPQEq != 0;
   RXG_TRY(halo_copy(c, QCopyDr));
+  if (pq) RXG_TRY(halo_refresh(c, 5, 0));   // ghost spos travels with MODE_COPY in the reference (src/comm.F90:129-131)
   if (c->cp[6] > 0) LAUNCH(c, k_types, cdiv(c->cp[6], 256), 256, 0, c->atype, c->cp[6], c->itype, c->gid);
   RXG_TRY(bin_grid(c, c->gnb));
-  if (c->lists_shared) RXG_TRY(build_pairlist<2>(c));
-  else RXG_TRY(build_pairlist<1>(c));
-  RXG_CUDA(cudaMemsetAsync(c->d_acc, 0, sizeof(double) * 16, c->st));
+  if (c->lists_shared) RXG_TRY((build_pairlist<2>(c, !pq)));
+  else RXG_TRY((build_pairlist<1>(c, !pq)));
+  RXG_CUDA(cudaMemsetAsync(c->d_acc, 0, sizeof(double) * 24, c->st));
+  const int nt = c->cp[6];
+  const int rgrid = cdiv((long long)nt * 32, 256);
+  if (pq && nt > 0) {   // qeq_initialize of src/pqeq.F90:262-365 on the compacted rows
+    RXG_CUDA(cudaMemsetAsync(c->pcs, 0, sizeof(double) * (size_t)nt, c->st));
+    RXG_CUDA(cudaMemsetAsync(c->d_flag + 6, 0, sizeof(int), c->st));
+    LAUNCH(c, k_pack_sps, cdiv(nt, 256), 256, 0, nt, c->spos, c->NB, c->itype, c->gnb.slot_of, c->d_ff, c->sps);
+    LAUNCH(c, k_pqeq_rows, rgrid, 256, 0, c->gnb, nt, n, c->rowbeg, c->rowend, c->col, c->val, c->sps, c->d_ff, c->prow, c->pcs, c->d_acc, c->d_flag + 6);
+  }
   int it = 0;
-  if (c->strict || c->qeq_mode == 1) RXG_TRY(qeq_cg_literal(c, nmax, &it));
+  if (!pq && (c->strict || c->qeq_mode == 1)) RXG_TRY(qeq_cg_literal(c, nmax, &it));
   else RXG_TRY(qeq_cg_single(c, nmax, &it));
+  if (pq && nt > 0) {   // update_shell_positions, src/pqeq.F90:171,187-259, with the final charges of residents and ghosts
+    RXG_TRY(halo_refresh(c, 4, 0));
+    LAUNCH(c, k_pack_qsl, cdiv(nt, 256), 256, 0, nt, c->q, c->gnb.slot_of, c->qsl);
+    LAUNCH(c, k_shell_relax, rgrid, 256, 0, c->gnb, nt, n, c->rowbeg, c->rowend, c->col, c->sps, c->qsl, c->d_ff, c->cfg.isEfield, c->cfg.eFieldDir,
+           c->cfg.eFieldStrength, c->spos, c->NB, c->d_flag + 6);
+    RXG_CUDA(cudaMemcpyAsync(c->h_int + 6, c->d_flag + 6, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    RXG_CUDA(cudaStreamSynchronize(c->st));
+    c->pqeq_skips += c->h_int[6];
+  }
   c->nstep_qeq = it;
   c->timers_ms[14] = (double)c->nnz;
   c->timers_ms[15] = n;
@@ -339,7 +367,11 @@ int rxg_create(const rxg_config *cfg, rxg_handle *out) {
   RXG_TRY(dalloc(c, &c->hst, NB)); RXG_TRY(dalloc(c, &c->tst, NB)); RXG_TRY(dalloc(c, &c->ust, NB)); RXG_TRY(dalloc(c, &c->wst, NB));
   RXG_TRY(dalloc(c, &c->sel, NB)); c->sel_cap = (int)NB;
   RXG_TRY(dalloc(c, &c->itype, NB)); RXG_TRY(dalloc(c, &c->gid, NB)); RXG_TRY(dalloc(c, &c->frcindx, NB));
-  RXG_TRY(dalloc(c, &c->tmp, 12 * NB));
+  RXG_TRY(dalloc(c, &c->tmp, 15 * NB));
+  if (cfg->isPQEq) {
+    RXG_TRY(dalloc(c, &c->spos, 3 * NB)); RXG_TRY(dalloc(c, &c->sps, NB)); RXG_TRY(dalloc(c, &c->prow, NB));
+    RXG_TRY(dalloc(c, &c->pcs, NB)); RXG_TRY(dalloc(c, &c->qsl, NB));
+  }
   RXG_TRY(dalloc(c, &c->xs, NB)); RXG_TRY(dalloc(c, &c->pqa, NB)); RXG_TRY(dalloc(c, &c->pqs, NB)); RXG_TRY(dalloc(c, &c->tgs, NB));
   RXG_TRY(dalloc(c, &c->nbrcnt, NB)); RXG_TRY(dalloc(c, &c->nbrpad, NS)); RXG_TRY(dalloc(c, &c->bptr, NB + 2));
   RXG_TRY(dalloc(c, &c->rowoff, NB + 2)); RXG_TRY(dalloc(c, &c->rowbeg, NB + 2)); RXG_TRY(dalloc(c, &c->rowend, NB + 2));
@@ -397,6 +429,31 @@ int rxg_set_forcefield(rxg_handle h, const rxg_ff *ff) {
       tq2[k] = make_double2(ff->TBL_Eclmb_QEq[k], i + 1 < (size_t)ff->ntable ? ff->TBL_Eclmb_QEq[k + 1] : 0.0);
     }
   RXG_TRY(upload(c, tq2.data(), tq2.size(), &d.TBL_qeq2));
+  d.ntype_pqeq = 0;
+  d.isPolarizable = d.inxnpqeq = nullptr; d.Zpqeq = d.Kspqeq = nullptr; d.TBL_pcc = d.TBL_psc = d.TBL_pss = nullptr;
+  if (c->cfg.isPQEq) {
+    if (ff->ntype_pqeq < 1 || !ff->isPolarizable || !ff->Zpqeq || !ff->Kspqeq || !ff->inxnpqeq || !ff->TBL_Eclmb_pcc ||
+        !ff->TBL_Eclmb_psc || !ff->TBL_Eclmb_pss) {
+      c->err = "rxg_set_forcefield: isPQEq is set but the PQEq parameters of rxg_ff are missing";
+      return RXG_ERR_ARG;
+    }
+    const size_t np = ff->ntype_pqeq, np2 = np * np, ntab = ff->ntable;
+    d.ntype_pqeq = (int)np;
+    RXG_TRY(upload(c, ff->isPolarizable, np, &d.isPolarizable)); RXG_TRY(upload(c, ff->inxnpqeq, np2, &d.inxnpqeq));
+    RXG_TRY(upload(c, ff->Zpqeq, np, &d.Zpqeq)); RXG_TRY(upload(c, ff->Kspqeq, np, &d.Kspqeq));
+    // TBL(ntype_pqeq2, NTABLE, 0:1) column-major -> {E(itb), E(itb+1), dE(itb), dE(itb+1)} per (inxn, itb)
+    auto pack = [&](const double *T, const double4 **dst) -> int {
+      std::vector<double4> t4(np2 * ntab);
+      for (size_t x = 0; x < np2; x++)
+        for (size_t i = 0; i < ntab; i++) {
+          const size_t e0 = x + np2 * i, e1 = x + np2 * (i + 1), d0 = x + np2 * (i + ntab), d1 = x + np2 * (i + 1 + ntab);
+          const bool last = i + 1 >= ntab;
+          t4[x * ntab + i] = make_double4(T[e0], last ? 0.0 : T[e1], T[d0], last ? 0.0 : T[d1]);
+        }
+      return upload(c, t4.data(), t4.size(), dst);
+    };
+    RXG_TRY(pack(ff->TBL_Eclmb_pcc, &d.TBL_pcc)); RXG_TRY(pack(ff->TBL_Eclmb_psc, &d.TBL_psc)); RXG_TRY(pack(ff->TBL_Eclmb_pss, &d.TBL_pss));
+  }
   if (!c->d_ff) RXG_CUDA(cudaMalloc((void **)&c->d_ff, sizeof(DevFF)));
   RXG_CUDA(cudaMemcpy(c->d_ff, &d, sizeof(DevFF), cudaMemcpyHostToDevice));
   c->have_ff = true;
@@ -515,11 +572,35 @@ int rxg_qeq(rxg_handle h, const int *natoms, const double *atype, double *pos, d
   return RXG_OK;
 }
 
-int rxg_pqeq(rxg_handle h, const int *, const double *, double *, double *, double *, double *, double *, int *) {
+int rxg_pqeq(rxg_handle h, const int *natoms, const double *atype, double *pos, double *q, double *spos, double *qsfp,
+             double *qsfv, int *nstep_qeq) {
   Ctx *c = (Ctx *)h;
-  if (c) c->err = "PQEq is not implemented in this version (SURVEY 8a row a18)";
-  return RXG_ERR_STATE;
+  RXG_TRY(check_ready(c, natoms ? *natoms : -1));
+  if (!c->cfg.isPQEq || !spos) { c->err = "rxg_pqeq: the handle was created with isPQEq = 0, or spos is null"; return RXG_ERR_ARG; }
+  RXG_TRY(h2d_planes(c, c->spos, spos, 3, *natoms));
+  RXG_TRY(rxg_qeq(h, natoms, atype, pos, q, qsfp, qsfv, nstep_qeq));   // qeq_device runs the PQEq variant for this handle
+  RXG_TRY(d2h_planes(c, spos, c->spos, 3, *natoms));
+  RXG_CUDA(cudaStreamSynchronize(c->st));
+  return RXG_OK;
 }
+
+int rxg_spos_upload(rxg_handle h, int natoms, const double *spos) {
+  Ctx *c = (Ctx *)h;
+  RXG_TRY(check_ready(c, natoms));
+  if (!c->cfg.isPQEq || !spos) { c->err = "rxg_spos_upload: isPQEq = 0 or null pointer"; return RXG_ERR_ARG; }
+  RXG_TRY(h2d_planes(c, c->spos, spos, 3, natoms));
+  RXG_CUDA(cudaStreamSynchronize(c->st));
+  return RXG_OK;
+}
+int rxg_spos_download(rxg_handle h, int natoms, double *spos) {
+  Ctx *c = (Ctx *)h;
+  RXG_TRY(check_ready(c, natoms));
+  if (!c->cfg.isPQEq || !spos) { c->err = "rxg_spos_download: isPQEq = 0 or null pointer"; return RXG_ERR_ARG; }
+  RXG_TRY(d2h_planes(c, spos, c->spos, 3, natoms));
+  RXG_CUDA(cudaStreamSynchronize(c->st));
+  return RXG_OK;
+}
+long long rxg_pqeq_skips(rxg_handle h) { return h ? ((Ctx *)h)->pqeq_skips : 0; }
 
 int rxg_force(rxg_handle h, const int *natoms, const double *atype, double *pos, double *f, const double *q, double *PE,
               double *astr) {
@@ -660,6 +741,7 @@ int rxg_md_run(rxg_handle h, int nsteps, double dt, int qstep, double Lex_w2, in
   Ctx *c = (Ctx *)h;
   RXG_TRY(check_ready(c, c ? c->natoms : -1));
   if (qstep < 1) qstep = 1;
+  if (c->cfg.isEfield) { c->err = "rxg_md_run: LinearMomentum (src/main.F90:71) is host work; isEfield runs go through rxg_pqeq/rxg_force"; return RXG_ERR_ARG; }
   cudaEventRecord(c->evm0, c->st);
   auto wall = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   for (int nstep = step0; nstep < step0 + nsteps; nstep++) {
@@ -752,8 +834,8 @@ int rxg_debug_fetch(rxg_handle h, const char *name, void *out, long long cap, lo
     return RXG_OK;
   }
   // 3-vector planes are returned compact [3][n6]
-  if (s == "pos" || s == "f" || s == "v") {
-    const double *p = s == "pos" ? c->pos : (s == "f" ? c->f : c->v);
+  if (s == "pos" || s == "f" || s == "v" || (s == "spos" && c->spos)) {
+    const double *p = s == "pos" ? c->pos : (s == "f" ? c->f : (s == "v" ? c->v : c->spos));
     cnt = 3 * n6;
     if (count) *count = cnt;
     if (out) {
@@ -800,6 +882,7 @@ int rxg_debug_fetch(rxg_handle h, const char *name, void *out, long long cap, lo
   else if (s == "deltalp") dev(c->deltalp, n6, 8);
   else if (s == "cdbnd") dev(c->cdbnd, n6, 8);
   else if (s == "ccbnd") dev(c->ccbnd, n6, 8);
+  else if (s == "prow" && c->prow) dev(c->prow, 4 * n6, 8);   // by slot: {fpqeq, sum H Z, column sum, Z}
   else { c->err = "rxg_debug_fetch: unknown name " + s; return RXG_ERR_ARG; }
   static const char *slot_names[] = {"nbrlist", "nbrindx", "BO0", "BO1", "BO2", "BO3", "dln_BOp1", "dln_BOp2", "dln_BOp3", "dBOp", "A0", "A1", "A2", "A3"};
   bool is_slot = false;

@@ -957,6 +957,10 @@ __global__ void __launch_bounds__(256) k_observe(int n, int NB, const int *__res
   block_add<2>(part, acc);
 }
 
+}   // namespace rxg
+#include "rxg_pqeq.cuh"
+namespace rxg {
+
 // ---------------------------------------------------------------------------------------------------
 inline Bonds make_bonds(Ctx *c) {
   Bonds B;
@@ -977,8 +981,10 @@ inline int force_device(Ctx *c, bool reuse = false) {
   RXG_CUDA(cudaMemsetAsync(c->d_acc + ACC_PE, 0, sizeof(double) * 24, c->st));
   double dr[3];
   for (int a = 0; a < 3; a++) dr[a] = c->cfg.nmincell * c->box.lcsize[a];
+  const bool pqeq = c->cfg.isPQEq != 0;
   if (!reuse) RXG_TRY(halo_copy(c, dr));                        // src/pot.F90:28
   else RXG_TRY(halo_refresh(c, 4, 1));   // ghost q; + the position round trip FORCE's own MODE_COPY would apply
+  if (pqeq) RXG_TRY(halo_refresh(c, 5, 0));   // ghost spos (part of MODE_COPY in the reference, src/comm.F90:129-131)
   const int nt = c->cp[6];
   if (!reuse) LAUNCH(c, k_types, cdiv(nt, 256), 256, 0, c->atype, nt, c->itype, c->gid);
   RXG_TRY(bin_grid(c, c->gb));                                  // :30
@@ -1005,7 +1011,13 @@ inline int force_device(Ctx *c, bool reuse = false) {
   if (!(getenv("RXG_ENBOND_FULL") && getenv("RXG_ENBOND_FULL")[0] == '1')) full_ok = false;
   const int wgrid = cdiv((long long)n * 32, 256);
   const int ogrid = cdiv((long long)nt * 32, 256);   // warps over cell-ordered slots (ghost slots exit at once)
-  if (!full_ok) LAUNCH(c, (k_enbond<true>), ogrid, 256, 0, nt, n, c->rowbeg, c->rowend, c->col, c->pqs, c->tgs, c->d_ff, c->f, NB, c->d_acc);
+  if (pqeq) {   // src/pot.F90:48-49
+    full_ok = false;
+    LAUNCH(c, k_pack_sps, cdiv(nt, 256), 256, 0, nt, c->spos, NB, c->itype, c->gnb.slot_of, c->d_ff, c->sps);
+    LAUNCH(c, k_enbond_pqeq, ogrid, 256, 0, nt, n, c->rowbeg, c->rowend, c->col, c->pqs, c->tgs, c->sps, c->d_ff, c->f, NB, c->d_acc);
+    if (c->cfg.isEfield && n > 0)   // :61
+      LAUNCH(c, k_efield, cdiv(n, 256), 256, 0, n, c->q, c->itype, c->d_ff, c->cfg.eFieldDir, c->cfg.eFieldStrength, c->f, NB);
+  } else if (!full_ok) LAUNCH(c, (k_enbond<true>), ogrid, 256, 0, nt, n, c->rowbeg, c->rowend, c->col, c->pqs, c->tgs, c->d_ff, c->f, NB, c->d_acc);
   LAUNCH(c, k_elnpr_prep, cdiv(nt, 256), 256, 0, nt, c->itype, c->d_ff, c->delta, c->nlp, c->dDlp, c->deltalp);
   LAUNCH(c, k_ebond_elnpr, cdiv(n, 128), 128, 0, n, c->itype, c->gid, c->d_ff, B, c->delta, c->dDlp, c->deltalp, c->d_acc);
   // angles and torsions: enumerate survivors of the cut-off tests, then evaluate one per thread

@@ -84,6 +84,12 @@ struct DevFF {
   const double *TBL_Eclmb_QEq;   // (NTABLE, nboty) column-major, as given
   const double2 *TBL_qeq2;       // [(inxn-1)*NTABLE + (itb-1)] = {T(itb,inxn), T(itb+1,inxn)}
   const double4 *TBL_nb;         // [(inxn-1)*NTABLE + (itb-1)] = {Evdw, CEvdw, Eclmb, CEclmb}: one 32-byte sector per node
+  // PQEq (module pqeq_vars, reference src/module.F90:285-304); ntype_pqeq == 0 when isPQEq is off
+  int ntype_pqeq;
+  const int *isPolarizable, *inxnpqeq;   // [ntype_pqeq], (ntype_pqeq,ntype_pqeq) column-major, 1-based values
+  const double *Zpqeq, *Kspqeq;
+  // TBL_Eclmb_pcc/psc/pss re-packed: [(inxn-1)*NTABLE + (itb-1)] = {E(itb), E(itb+1), dE(itb), dE(itb+1)}: one 32-byte gather per lerp
+  const double4 *TBL_pcc, *TBL_psc, *TBL_pss;
 };
 
 // One linked-cell grid (replaces header/llist/nacell, reference src/main.F90:277-318) as a counting sort.
@@ -122,6 +128,13 @@ struct Ctx {
   double2 *ust = nullptr;   // resident-weighted H.h sums (Est bookkeeping)
   double2 *wst = nullptr;   // resident-weighted H.qs, H.qt
   int *itype = nullptr, *gid = nullptr, *frcindx = nullptr;
+  // ---- PQEq (isPQEq): shell displacements and the per-call products of qeq_initialize (reference src/pqeq.F90) ----------
+  double *spos = nullptr;   // [3*NB] spos(NBUFFER,3), planes
+  double4 *sps = nullptr;   // [NB] by SLOT: {sx, sy, sz, Zpqeq(type)} of residents and ghosts
+  double4 *prow = nullptr;  // [NB] by SLOT (resident rows): {fpqeq, sum_j H_ij Z_j, column sum of the shell-core coupling over resident rows, Z_i}
+  double *pcs = nullptr;    // [NB] by SLOT: column sums of the shell-core coupling taken by atomics (ghost columns)
+  double *qsl = nullptr;    // [NB] by SLOT: q (final charges, for the shell relaxation and ENbond_PQEq)
+  long long pqeq_skips = 0;
   // ---- COPYATOMS bookkeeping -----------------------------------------------------------------------------
   int *sel = nullptr;       // concatenated selection lists of the six stages of the last MODE_COPY
   int sel_cap = 0, selptr[7] = {0, 0, 0, 0, 0, 0, 0};

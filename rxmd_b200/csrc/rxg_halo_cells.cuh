@@ -158,7 +158,7 @@ __global__ void k_sel_count(const double *__restrict__ coord, const double *__re
 // (MODE_QCOPY*) and the force copy-back (MODE_CPBK) reuse those lists, so only MODE_COPY / MODE_MOVE ever test
 // positions (the reference re-tests them on every call, src/comm.F90:273-288, with the same outcome).
 constexpr int NE_COPY = 9;    // x y z atype q qs qt hs ht           (reference ne=10 also carries frcindx)
-constexpr int NE_MOVE = 12;   // x y z vx vy vz atype q qs qt qsfp qsfv
+constexpr int NE_MOVE = 12;   // x y z vx vy vz atype q qs qt qsfp qsfv  (+ sx sy sz with PQEq, src/comm.F90:153,165-167)
 
 // store_atoms for MODE_COPY (src/comm.F90:406-447): stable selection, coordinate shift by -/+LBOX (xshift :531)
 __global__ void k_pack_copy(const double *__restrict__ pos, int NB, const double *__restrict__ atype,
@@ -201,8 +201,8 @@ __global__ void k_unpack_copy(double *__restrict__ pos, int NB, double *__restri
 // store_atoms for MODE_MOVE: atoms that left through the stage's face; the original is marked dead (atype=-1)
 __global__ void k_pack_move(const double *__restrict__ pos, const double *__restrict__ v, int NB, double *__restrict__ atype,
                             const double *__restrict__ q, const double2 *__restrict__ qst, const double *__restrict__ qsfp,
-                            const double *__restrict__ qsfv, int n, int axis, bool upper, double lbox, double sft,
-                            const int *__restrict__ blkoff, int cnt, double *__restrict__ buf) {
+                            const double *__restrict__ qsfv, const double *__restrict__ spos, int n, int axis, bool upper,
+                            double lbox, double sft, const int *__restrict__ blkoff, int cnt, double *__restrict__ buf) {
   int i = blockIdx.x * SCAN_BLK + threadIdx.x;
   int fl = 0;
   if (i < n) fl = in_buffer(upper, lbox, 0.0, pos[(size_t)axis * NB + i]) && !(atype[i] < 0.0);
@@ -218,15 +218,18 @@ __global__ void k_pack_move(const double *__restrict__ pos, const double *__rest
   buf[3 * c + k] = v[i]; buf[4 * c + k] = v[NB + i]; buf[5 * c + k] = v[2 * (size_t)NB + i];
   buf[6 * c + k] = atype[i]; buf[7 * c + k] = q[i]; buf[8 * c + k] = s.x; buf[9 * c + k] = s.y;
   buf[10 * c + k] = qsfp[i]; buf[11 * c + k] = qsfv[i];
+  if (spos) { buf[12 * c + k] = spos[i]; buf[13 * c + k] = spos[(size_t)NB + i]; buf[14 * c + k] = spos[2 * (size_t)NB + i]; }
   atype[i] = -1.0;
 }
 __global__ void k_unpack_move(double *__restrict__ pos, double *__restrict__ v, int NB, double *__restrict__ atype,
                               double *__restrict__ q, double2 *__restrict__ qst, double *__restrict__ qsfp,
-                              double *__restrict__ qsfv, int cnt, int dst0, const double *__restrict__ buf) {
+                              double *__restrict__ qsfv, double *__restrict__ spos, int cnt, int dst0,
+                              const double *__restrict__ buf) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= cnt) return;
   size_t c = cnt;
   int m = dst0 + k;
+  if (spos) { spos[m] = buf[12 * c + k]; spos[(size_t)NB + m] = buf[13 * c + k]; spos[2 * (size_t)NB + m] = buf[14 * c + k]; }
   pos[m] = buf[k]; pos[NB + m] = buf[c + k]; pos[2 * (size_t)NB + m] = buf[2 * c + k];
   v[m] = buf[3 * c + k]; v[NB + m] = buf[4 * c + k]; v[2 * (size_t)NB + m] = buf[5 * c + k];
   atype[m] = buf[6 * c + k]; q[m] = buf[7 * c + k];
@@ -243,7 +246,7 @@ __global__ void k_move_compact(const int *__restrict__ flag, const int *__restri
                                const double *__restrict__ pos, const double *__restrict__ v,
                                const double *__restrict__ atype, const double *__restrict__ q,
                                const double2 *__restrict__ qst, const double *__restrict__ qsfp,
-                               const double *__restrict__ qsfv, double *__restrict__ out) {
+                               const double *__restrict__ qsfv, const double *__restrict__ spos, double *__restrict__ out) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n || !flag[i]) return;
   int m = dst[i];
@@ -254,12 +257,16 @@ __global__ void k_move_compact(const int *__restrict__ flag, const int *__restri
   out[(size_t)9 * NB + m] = qst[i].y;
   out[(size_t)10 * NB + m] = qsfp[i];
   out[(size_t)11 * NB + m] = qsfv[i];
+  if (spos)
+    for (int a = 0; a < 3; a++) out[(size_t)(12 + a) * NB + m] = spos[(size_t)a * NB + i];
 }
 __global__ void k_move_restore(const double *__restrict__ in, int n, int NB, double *__restrict__ pos, double *__restrict__ v,
                                double *__restrict__ atype, double *__restrict__ q, double2 *__restrict__ qst,
-                               double *__restrict__ qsfp, double *__restrict__ qsfv) {
+                               double *__restrict__ qsfp, double *__restrict__ qsfv, double *__restrict__ spos) {
   int m = blockIdx.x * blockDim.x + threadIdx.x;
   if (m >= n) return;
+  if (spos)
+    for (int a = 0; a < 3; a++) spos[(size_t)a * NB + m] = in[(size_t)(12 + a) * NB + m];
   for (int a = 0; a < 3; a++) { pos[(size_t)a * NB + m] = in[(size_t)a * NB + m]; v[(size_t)a * NB + m] = in[(size_t)(3 + a) * NB + m]; }
   atype[m] = in[(size_t)6 * NB + m];
   q[m] = in[(size_t)7 * NB + m];
@@ -269,27 +276,30 @@ __global__ void k_move_restore(const double *__restrict__ in, int n, int NB, dou
 }
 
 // value refreshes through the stored selection lists.  which: 1 = (qs,qt) [MODE_QCOPY1], 2 = (hs,ht,q) [MODE_QCOPY2],
-// 3 = (hs,ht) only (single-pass CG), 4 = q only (FORCE reusing the QEq halo)
+// 3 = (hs,ht) only (single-pass CG), 4 = q only (FORCE reusing the QEq halo), 5 = spos (PQEq: the reference packs spos
+// into MODE_COPY itself, src/comm.F90:122,129-131; here it follows through the same selection lists)
 __global__ void k_pack_vals(int which, const int *__restrict__ sel, int cnt, const double2 *__restrict__ qst,
                             const double4 *__restrict__ hsq, const double2 *__restrict__ hst, const double *__restrict__ q,
-                            double *__restrict__ buf) {
+                            const double *__restrict__ spos, int NB, double *__restrict__ buf) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= cnt) return;
   int i = sel[k];
   size_t c = cnt;
   if (which == 4) { buf[k] = q[i]; return; }
+  if (which == 5) { buf[k] = spos[i]; buf[c + k] = spos[(size_t)NB + i]; buf[2 * c + k] = spos[2 * (size_t)NB + i]; return; }
   if (which == 1) { double2 s = qst[i]; buf[k] = s.x; buf[c + k] = s.y; }
   else if (which == 2) { double4 h = hsq[i]; buf[k] = h.x; buf[c + k] = h.y; buf[2 * c + k] = h.z; }
   else { double2 h = hst[i]; buf[k] = h.x; buf[c + k] = h.y; }
 }
 __global__ void k_unpack_vals(int which, int cnt, int dst0, const double *__restrict__ buf, double2 *__restrict__ qst,
                               double4 *__restrict__ hsq, double2 *__restrict__ hst, double2 *__restrict__ xs,
-                              const int *__restrict__ slot_of, double *__restrict__ q) {
+                              const int *__restrict__ slot_of, double *__restrict__ q, double *__restrict__ spos, int NB) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= cnt) return;
   size_t c = cnt;
   int m = dst0 + k;
   if (which == 4) { q[m] = buf[k]; return; }
+  if (which == 5) { spos[m] = buf[k]; spos[(size_t)NB + m] = buf[c + k]; spos[2 * (size_t)NB + m] = buf[2 * c + k]; return; }
   if (which == 1) qst[m] = make_double2(buf[k], buf[c + k]);
   else if (which == 2) { double qq = buf[2 * c + k]; hsq[m] = make_double4(buf[k], buf[c + k], qq, 0.0); q[m] = qq; }
   else { double2 v = make_double2(buf[k], buf[c + k]); hst[m] = v; xs[slot_of[m]] = v; }
@@ -480,19 +490,19 @@ inline int halo_copy(Ctx *c, const double dr[3]) {
 // COPYATOMS(MODE_QCOPY1|2) (+ which=3: hs,ht only).  `roundtrips` position round trips are applied at the end
 // (the reference does one per call, src/comm.F90:222-227,260-264)
 inline int halo_refresh(Ctx *c, int which, int roundtrips) {
-  const int nf = (which == 2) ? 3 : (which == 4 ? 1 : 2);
+  const int nf = (which == 2 || which == 5) ? 3 : (which == 4 ? 1 : 2);
   for (int axis = 0; axis < 3; axis++) {
     const int d0 = 2 * axis + 1;
     const int ns[2] = {c->ns[d0], c->ns[d0 + 1]}, nr[2] = {c->nr[d0], c->nr[d0 + 1]};
     if (ns[0] + ns[1] + nr[0] + nr[1] == 0) continue;
     RXG_TRY(ensure_xbuf(c, (size_t)nf * (size_t)std::max(std::max(ns[0], ns[1]), std::max(nr[0], nr[1]))));
     for (int k = 0; k < 2; k++)
-      if (ns[k] > 0) LAUNCH(c, k_pack_vals, cdiv(ns[k], 256), 256, 0, which, c->sel + c->selptr[d0 - 1 + k], ns[k], c->qst, c->hsq, c->hst, c->q, c->sbuf[k]);
+      if (ns[k] > 0) LAUNCH(c, k_pack_vals, cdiv(ns[k], 256), 256, 0, which, c->sel + c->selptr[d0 - 1 + k], ns[k], c->qst, c->hsq, c->hst, c->q, c->spos, c->NB, c->sbuf[k]);
     size_t cs[2] = {(size_t)nf * ns[0], (size_t)nf * ns[1]}, cr[2] = {(size_t)nf * nr[0], (size_t)nf * nr[1]};
     double *rb[2];
     RXG_TRY(exchange_axis(c, axis, cs, cr, rb, false));
     for (int k = 0; k < 2; k++)
-      if (nr[k] > 0) LAUNCH(c, k_unpack_vals, cdiv(nr[k], 256), 256, 0, which, nr[k], c->cp[d0 - 1 + k], rb[k], c->qst, c->hsq, c->hst, c->xs, c->gnb.slot_of, c->q);
+      if (nr[k] > 0) LAUNCH(c, k_unpack_vals, cdiv(nr[k], 256), 256, 0, which, nr[k], c->cp[d0 - 1 + k], rb[k], c->qst, c->hsq, c->hst, c->xs, c->gnb.slot_of, c->q, c->spos, c->NB);
   }
   if (roundtrips > 0 && c->cp[6] > 0)
     LAUNCH(c, k_roundtrip, cdiv(c->cp[6], 256), 256, 0, c->pos, c->NB, c->cp[6], make_boxdev(c->box), roundtrips);
@@ -524,6 +534,8 @@ inline int halo_move(Ctx *c) {
   const int NB = c->NB;
   BoxDev b = make_boxdev(c->box);
   const double zero[3] = {0.0, 0.0, 0.0};
+  double *sp = c->cfg.isPQEq ? c->spos : nullptr;
+  const int NE_MOVE = c->cfg.isPQEq ? 15 : rxg::NE_MOVE;
   c->cp[0] = c->natoms;
   if (c->natoms > 0) LAUNCH(c, k_to_norm, cdiv(c->natoms, 256), 256, 0, c->pos, NB, c->natoms, b);
   for (int axis = 0; axis < 3; axis++) {
@@ -538,7 +550,7 @@ inline int halo_move(Ctx *c) {
     // direction's atoms dead before packing the second does not change the second's selection or its scan
     for (int k = 0; k < 2; k++)
       if (ns[k] > 0)
-        LAUNCH(c, k_pack_move, nblk, SCAN_BLK, 0, c->pos, c->v, NB, c->atype, c->q, c->qst, c->qsfp, c->qsfv, n, axis, k == 0,
+        LAUNCH(c, k_pack_move, nblk, SCAN_BLK, 0, c->pos, c->v, NB, c->atype, c->q, c->qst, c->qsfp, c->qsfv, sp, n, axis, k == 0,
                c->box.LBOX[axis], k == 0 ? -c->box.LBOX[axis] : c->box.LBOX[axis], c->d_blk + (size_t)k * c->nblk_cap, ns[k], c->sbuf[k]);
     if (c->cp[d0 - 1] + nr[0] + nr[1] > NB) { c->err = "ERROR: over capacity in append_atoms (NBUFFER)"; return RXG_ERR_NBUFFER; }
     size_t cs[2] = {(size_t)NE_MOVE * ns[0], (size_t)NE_MOVE * ns[1]}, cr[2] = {(size_t)NE_MOVE * nr[0], (size_t)NE_MOVE * nr[1]};
@@ -548,7 +560,7 @@ inline int halo_move(Ctx *c) {
     c->cp[d1] = c->cp[d0] + nr[1];
     for (int k = 0; k < 2; k++)
       if (nr[k] > 0)
-        LAUNCH(c, k_unpack_move, cdiv(nr[k], 256), 256, 0, c->pos, c->v, NB, c->atype, c->q, c->qst, c->qsfp, c->qsfv, nr[k], c->cp[d0 - 1 + k], rb[k]);
+        LAUNCH(c, k_unpack_move, cdiv(nr[k], 256), 256, 0, c->pos, c->v, NB, c->atype, c->q, c->qst, c->qsfp, c->qsfv, sp, nr[k], c->cp[d0 - 1 + k], rb[k]);
     c->moved += ns[0] + ns[1] + nr[0] + nr[1];
   }
   const int n6 = c->cp[6];
@@ -561,11 +573,11 @@ inline int halo_move(Ctx *c) {
     LAUNCH(c, k_scan_phase1<int>, nblk, SCAN_BLK, 0, flag, (long long)n6, c->d_blk);
     LAUNCH(c, k_scan_phase2<int>, 1, SCAN_BLK, 0, c->d_blk, nblk, c->d_flag + 5);
     LAUNCH(c, k_scan_phase3<int>, nblk, SCAN_BLK, 0, flag, (long long)n6, c->d_blk, c->rowcnt /* >= NB+1 ints */);
-    LAUNCH(c, k_move_compact, cdiv(n6, 256), 256, 0, flag, c->rowcnt, n6, NB, c->pos, c->v, c->atype, c->q, c->qst, c->qsfp, c->qsfv, c->tmp);
+    LAUNCH(c, k_move_compact, cdiv(n6, 256), 256, 0, flag, c->rowcnt, n6, NB, c->pos, c->v, c->atype, c->q, c->qst, c->qsfp, c->qsfv, sp, c->tmp);
     RXG_CUDA(cudaMemcpyAsync(c->h_int, c->d_flag + 5, sizeof(int), cudaMemcpyDeviceToHost, c->st));
     RXG_CUDA(cudaStreamSynchronize(c->st));
     int ni = c->h_int[0];
-    if (ni > 0) LAUNCH(c, k_move_restore, cdiv(ni, 256), 256, 0, c->tmp, ni, NB, c->pos, c->v, c->atype, c->q, c->qst, c->qsfp, c->qsfv);
+    if (ni > 0) LAUNCH(c, k_move_restore, cdiv(ni, 256), 256, 0, c->tmp, ni, NB, c->pos, c->v, c->atype, c->q, c->qst, c->qsfp, c->qsfv, sp);
     c->natoms = ni;
     c->moved = 0;
   }

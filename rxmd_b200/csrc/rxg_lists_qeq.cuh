@@ -236,8 +236,9 @@ inline int build_nbrlist(Ctx *c) {
   return RXG_OK;
 }
 
+// `hessian`: run k_hessian over the parked (r^2, type) pairs (QEq); PQEq fills `val` itself (k_pqeq_rows)
 template <int MODE>
-int build_pairlist(Ctx *c) {
+int build_pairlist(Ctx *c, bool hessian = true) {
   const int n = c->natoms, nt = c->cp[6];
   RXG_CUDA(cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->st));
   RXG_CUDA(cudaMemsetAsync(c->rowcnt, 0, sizeof(int) * (size_t)(nt + 1), c->st));
@@ -268,7 +269,7 @@ int build_pairlist(Ctx *c) {
   c->list_is_qeq = MODE >= 1;
   LAUNCH(c, (k_pairlist<MODE, true>), grid, PL_WARPS * 32, 0, c->gnb, c->d_ff, c->d_runs, c->nruns, n, ncell_res, c->rowcnt,
          c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->cfg.maxneighbs10, c->d_flag);
-  if (MODE >= 1)
+  if (MODE >= 1 && hessian)
     LAUNCH(c, k_hessian, 148 * 16, 256, 0, nnz, c->d_ff, c->val);
   return RXG_OK;
 }

@@ -60,7 +60,7 @@ def _iptr(a):
 class PackedFF:
     """Owns the contiguous buffers behind an RxgFF (keeps them alive)."""
 
-    def __init__(self, ff: ForceField, rc2, tables, rctap, cutoff_vpar30):
+    def __init__(self, ff: ForceField, rc2, tables, rctap, cutoff_vpar30, pqeq=None, chi=None, eta=None):
         T_vdw, T_clmb, T_qeq, UDR, UDRi = tables
         self.keep = {}
         st = RxgFF()
@@ -80,6 +80,10 @@ class PackedFF:
                 put(n, np.asarray(ff.switch)[1:, 1:].ravel(order="F"))      # switch(1:3,1:nboty) column-major
             elif n == "rc2":
                 put(n, np.asarray(rc2)[1:])
+            elif n == "chi" and chi is not None:      # initialize_pqeq overwrites chi/eta (src/module.F90:517-523)
+                put(n, np.asarray(chi)[1:])
+            elif n == "eta" and eta is not None:
+                put(n, np.asarray(eta)[1:])
             else:
                 put(n, np.asarray(getattr(ff, n))[1:])
         for n, nd in (("inxn2", 2), ("inxn3", 3), ("inxn3hb", 3), ("inxn4", 4)):
@@ -92,6 +96,18 @@ class PackedFF:
         put("TBL_Eclmb", T_clmb[:, 1:, 1:].ravel(order="F"))
         put("TBL_Eclmb_QEq", T_qeq[1:, 1:].ravel(order="F"))
         st.ntype_pqeq = 0
+        if pqeq is not None:
+            # module pqeq_vars as the Fortran host holds it: 1-based arrays by their first element, column-major
+            n = pqeq.ntype
+            st.ntype_pqeq = n
+            pol = np.ascontiguousarray(np.asarray(pqeq.polarizable)[1:], dtype=np.int32)
+            inx = np.ascontiguousarray(np.asarray(pqeq.inxnpqeq)[1:, 1:].ravel(order="F"), dtype=np.int32)
+            self.keep["isPolarizable"], self.keep["inxnpqeq"] = pol, inx
+            st.isPolarizable, st.inxnpqeq = _iptr(pol), _iptr(inx)
+            put("Zpqeq", np.asarray(pqeq.Z)[1:])
+            put("Kspqeq", np.asarray(pqeq.Ks)[1:])
+            for nm, T in (("TBL_Eclmb_pcc", pqeq.T_pcc), ("TBL_Eclmb_psc", pqeq.T_psc), ("TBL_Eclmb_pss", pqeq.T_pss)):
+                put(nm, T[1:, 1:, :].ravel(order="F"))   # (ntype_pqeq2, NTABLE, 0:1)
         self.struct = st
 
 

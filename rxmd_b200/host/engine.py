@@ -52,6 +52,11 @@ def load_library():
     L.rxg_last_error.argtypes = [vp]
     L.rxg_last_error.restype = C.c_char_p
     L.rxg_qeq.argtypes = [vp, ip, dp, dp, dp, dp, dp, ip]
+    L.rxg_pqeq.argtypes = [vp, ip, dp, dp, dp, dp, dp, dp, ip]
+    L.rxg_spos_upload.argtypes = [vp, C.c_int, dp]
+    L.rxg_spos_download.argtypes = [vp, C.c_int, dp]
+    L.rxg_pqeq_skips.argtypes = [vp]
+    L.rxg_pqeq_skips.restype = C.c_longlong
     L.rxg_force.argtypes = [vp, ip, dp, dp, dp, dp, dp, dp]
     L.rxg_move.argtypes = [vp, ip, dp, dp, dp, dp, dp, dp, dp, dp]
     L.rxg_fetch_bonds.argtypes = [vp, ip, dp]
@@ -87,7 +92,8 @@ def rank_of_vid(vid, vprocs):
 
 
 _F64 = {"atype", "q", "qst", "gst", "hsq", "val", "BO0", "BO1", "BO2", "BO3", "dln_BOp1", "dln_BOp2", "dln_BOp3", "dBOp",
-        "A0", "A1", "A2", "A3", "delta", "deltap1", "deltap2", "nlp", "dDlp", "deltalp", "cdbnd", "ccbnd", "pos", "f", "v"}
+        "A0", "A1", "A2", "A3", "delta", "deltap1", "deltap2", "nlp", "dDlp", "deltalp", "cdbnd", "ccbnd", "pos", "f", "v", "spos",
+        "prow"}
 _I64 = {"rowbeg", "rowend", "nnz"}
 
 
@@ -110,6 +116,7 @@ class Engine:
         self.nstep_qeq = 0
         nb = self.NBUFFER
         self.qsfp, self.qsfv, self.qs, self.qt = (np.zeros(nb) for _ in range(4))
+        self.spos = np.zeros((3, nb)) if cfg.isPQEq else None   # spos(NBUFFER,3), src/init.F90:117-120
 
     # -- error convention of the reference: print 'ERROR: ...' and stop (src/main.F90:403-407, src/comm.F90:467-472)
     def _chk(self, rc):
@@ -155,6 +162,19 @@ class Engine:
         self._chk(self.L.rxg_qeq(self.h, C.byref(n), _dp(atype), _dp(pos), _dp(q), _dp(self.qsfp), _dp(self.qsfv), C.byref(it)))
         self.nstep_qeq = it.value
 
+    # -- subroutine PQEq(atype, pos, q), src/pqeq.F90:2 (module-global spos is relaxed at its end)
+    def PQEq(self, atype, pos, q):
+        if self.spos is None:
+            raise RxmdError("ERROR: PQEq called without PQEq parameters (isPQEq = 0)")
+        n = C.c_int(self.NATOMS)
+        it = C.c_int(0)
+        self._chk(self.L.rxg_pqeq(self.h, C.byref(n), _dp(atype), _dp(pos), _dp(q), _dp(self.spos), _dp(self.qsfp), _dp(self.qsfv),
+                                  C.byref(it)))
+        self.nstep_qeq = it.value
+
+    def pqeq_skips(self):
+        return int(self.L.rxg_pqeq_skips(self.h))
+
     # -- subroutine FORCE(atype, pos, f, q), src/pot.F90:2
     def FORCE(self, atype, pos, f, q):
         n = C.c_int(self.NATOMS)
@@ -166,9 +186,13 @@ class Engine:
         if imode != MODE_MOVE:
             raise RxmdError(f"ERROR: imode doesn't match in COPYATOMS: {imode}")
         n = C.c_int(self.NATOMS)
+        if self.spos is not None:   # spos migrates with the atom (src/comm.F90:153,165-167)
+            self._chk(self.L.rxg_spos_upload(self.h, self.NATOMS, _dp(self.spos)))
         self._chk(self.L.rxg_move(self.h, C.byref(n), _dp(atype), _dp(pos), _dp(v), _dp(q), _dp(self.qs), _dp(self.qt),
                                   _dp(self.qsfp), _dp(self.qsfv)))
         self.NATOMS = n.value
+        if self.spos is not None:
+            self._chk(self.L.rxg_spos_download(self.h, self.NATOMS, _dp(self.spos)))
 
     # -- device-resident stepping
     def state_upload(self, atype, pos, v=None, q=None, qsfp=None, qsfv=None):

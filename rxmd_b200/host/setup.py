@@ -253,6 +253,14 @@ def read_pqeq_parms(path):
     return p
 
 
+def truncate_pqeq(p: PQEqParams, n):
+    """Keep the first n element rows (see system.build_system)."""
+    p.ntype = n
+    p.elem = p.elem[:n + 1]
+    for k in ("polarizable", "X0", "J0", "Z", "Rc", "Rs", "Ks"):
+        setattr(p, k, getattr(p, k)[:n + 1])
+
+
 def initialize_pqeq(p: PQEqParams, chi, eta, rctap, CTap):
     """set_alphaij_pqeq + initialize_pqeq, src/module.F90:448-613.
 

@@ -1,0 +1,163 @@
+"""PQEq (BASELINE config 5) on the GPU against the oracle, through the C-ABI.
+
+Inputs: the reference's examples/3-reaxpq+ polyethylene cell (12 atoms, C/H) with its pqeq1.par, replicated like the
+example's own `geninit -mc 2 3 5` (360 atoms, rctap = 12.5 A), displaced, with non-zero shell displacements.
+
+Bars: 12.5 A list and hessian bit-exact; fpqeq <= 1e-12 relative; one shell relaxation step with identical charges
+<= 1e-9; energies/forces of FORCE (ENbond_PQEq + the bonded terms) with identical charges and shells <= 1e-9; charges of
+the production CG within the reference's own build-to-build spread (see test_gpu_parity.py) and < 1e-6 at tight tolerance.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from rxmd_b200.host.system import build_system
+
+pytestmark = pytest.mark.gpu
+
+INP = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "inputs", "init.pe.pqeq")
+UTIME = 1.0e3 / 20.455
+
+
+def make(mc=(2, 3, 5), sigma=0.03, par="pqeq1.par", shell_sigma=4e-3, **cfgkw):
+    from rxmd_b200.host.engine import Engine
+    from oracle.pyoracle import Oracle
+    s = build_system(os.path.join(INP, "input.xyz"), os.path.join(INP, "ffield"), mc=mc, displace_sigma=sigma,
+                     pqeq_path=os.path.join(INP, par))
+    cfg = s.config(**cfgkw)
+    assert cfg.isPQEq == 1
+    e, o = Engine(s, cfg), Oracle(s, cfg)
+    n = len(s.ranks[0]["atype"])
+    sp = np.random.default_rng(7).normal(0.0, shell_sigma, (3, n)) if shell_sigma > 0 else np.zeros((3, n))
+    return s, cfg, e, o, sp
+
+
+def test_pqeq_initialize_and_shell_relaxation(built):
+    """NMAXQEq = 0: the CG loop is skipped, so PQEq = halo + list + qeq_initialize + one shell relaxation with the INPUT
+    charges -- every product can be compared at round-off level."""
+    s, cfg, e, o, sp = make(NMAXQEq=0)
+    atype, pos, v, f, q = e.host_arrays(s.ranks[0])
+    n = e.NATOMS
+    q0 = np.random.default_rng(3).normal(0.0, 0.05, n)
+    q0 -= q0.mean()
+    q[:n] = q0
+    e.spos[:, :n] = sp
+    o.set_atoms(0, s.ranks[0]["atype"], s.ranks[0]["pos"], None, q0)
+    o.set_spos(0, sp)
+    o.qeq()
+    e.PQEq(atype, pos, q)
+    assert np.array_equal(e.fetch("copyptr"), o.i32("copyptr"))
+    rb, re_, col, val = e.fetch("rowbeg"), e.fetch("rowend"), e.fetch("col"), e.fetch("val")
+    cnt_o = o.i32("nbpcnt")
+    assert np.array_equal(re_ - rb, cnt_o)
+    W = cfg.maxneighbs10
+    lst_o, hes_o = o.i32("nbplist").reshape(n, W), o.f64("hessian").reshape(n, W)
+    for i in range(n):
+        assert np.array_equal(col[rb[i]:re_[i]], lst_o[i, :cnt_o[i]]), f"12.5 A row {i}"
+        assert np.array_equal(val[rb[i]:re_[i]], hes_o[i, :cnt_o[i]]), f"hessian row {i}"
+    # fpqeq enters the s-gradient, gs(i) = -chi - eta*qs - H.qs - fpqeq(i) (src/pqeq.F90:463): compared per atom
+    g_d = e.fetch("gst").reshape(-1, 2)[:n]
+    assert np.abs(g_d[:, 0] - o.f64("gs")[:n]).max() <= 1e-11 * np.abs(o.f64("gs")[:n]).max()
+    assert np.abs(g_d[:, 1] - o.f64("gt")[:n]).max() <= 1e-11 * np.abs(o.f64("gt")[:n]).max()
+    fp_o = o.f64("fpqeq")
+    fp_d = e.fetch("prow").reshape(-1, 4)[:, 0]                       # by cell-order slot on the device
+    assert np.abs(np.sort(fp_d[fp_d != 0.0]) - np.sort(fp_o[fp_o != 0.0])).max() <= 1e-12 * np.abs(fp_o).max()
+    # charges untouched, shells relaxed by the same capped step
+    assert np.array_equal(q[:n], q0)
+    sp_o = o.f64("spos").reshape(3, -1)[:, :n]
+    step = sp_o - sp
+    assert np.abs(step).max() > 1e-5                                  # the relaxation did something
+    assert np.abs(e.spos[:, :n] - sp_o).max() <= 1e-9 * np.abs(step).max() + 1e-15
+    assert e.pqeq_skips() == o.i32("pqeq_skips")[0]
+    e.close(); o.close()
+
+
+@pytest.mark.parametrize("shell_sigma", [0.0, 4e-3])
+def test_pqeq_charges_and_forces(built, shell_sigma):
+    s, cfg, e, o, sp = make(shell_sigma=shell_sigma)
+    atype, pos, v, f, q = e.host_arrays(s.ranks[0])
+    n = e.NATOMS
+    e.spos[:, :n] = sp
+    o.set_spos(0, sp)
+    o.qeq()
+    e.PQEq(atype, pos, q)
+    qo = o.f64("q")[:n]
+    assert abs(q[:n].sum()) < 1e-9
+    assert np.abs(q[:n] - qo).max() < 2e-3                             # production order vs serial order (reference spread)
+    assert abs(e.nstep_qeq - o.i32("nstep_qeq")[0]) <= 3
+    sp_o = o.f64("spos").reshape(3, -1)[:, :n]
+    assert np.abs(e.spos[:, :n] - sp_o).max() < 2e-5                   # shells follow the charges
+    # ---- FORCE with identical charges and shells
+    q[:n] = qo
+    e.spos[:, :n] = sp_o
+    e._chk(e.L.rxg_spos_upload(e.h, n, e.spos.ctypes.data_as(e.L.rxg_spos_upload.argtypes[2])))
+    o.force()
+    e.FORCE(atype, pos, f, q)
+    pe_o = o.f64("PE")
+    for k in range(1, 14):
+        assert abs(e.PE[k] - pe_o[k]) <= 1e-9 * max(abs(pe_o[k]), 1e-6 * np.abs(pe_o[1:]).max()), f"PE({k})"
+    fo = o.f64("f").reshape(3, -1)[:, :n]
+    assert np.abs(f[:, :n] - fo).max() <= 1e-9 * np.abs(fo).max()
+    assert np.abs(f[:, :n].sum(axis=1)).max() < 1e-9 * np.abs(fo).max() * n
+    assert np.allclose(e.astr, o.f64("astr"), rtol=1e-8, atol=1e-8 * np.abs(o.f64("astr")).max())
+    e.close(); o.close()
+
+
+def test_pqeq_tight_tolerance_converges_to_oracle(built):
+    s, cfg, e, o, sp = make(QEq_tol=1e-12, NMAXQEq=200)
+    atype, pos, v, f, q = e.host_arrays(s.ranks[0])
+    n = e.NATOMS
+    e.spos[:, :n] = sp
+    o.set_spos(0, sp)
+    o.qeq()
+    e.PQEq(atype, pos, q)
+    assert np.abs(q[:n] - o.f64("q")[:n]).max() < 1e-6
+    e.close(); o.close()
+
+
+def test_pqeq_efield_and_nine_element_file(built):
+    """rxmd.in of examples/3-reaxpq+ switches the electric field on (efield 1 0.01); conf/init.pe.pqeq/pqeq.in lists nine
+    elements for a seven-element force field (rows past nso dropped, see host/system.py)."""
+    s, cfg, e, o, sp = make(par="pqeq.in", efield=(1, 0.01))
+    assert cfg.isEfield == 1 and s.pqeq.ntype == 7
+    atype, pos, v, f, q = e.host_arrays(s.ranks[0])
+    n = e.NATOMS
+    e.spos[:, :n] = sp
+    o.set_spos(0, sp)
+    o.qeq()
+    e.PQEq(atype, pos, q)
+    qo = o.f64("q")[:n]
+    sp_o = o.f64("spos").reshape(3, -1)[:, :n]
+    assert np.abs(q[:n] - qo).max() < 2e-3
+    q[:n] = qo
+    e.spos[:, :n] = sp_o
+    e._chk(e.L.rxg_spos_upload(e.h, n, e.spos.ctypes.data_as(e.L.rxg_spos_upload.argtypes[2])))
+    o.force()
+    e.FORCE(atype, pos, f, q)
+    fo = o.f64("f").reshape(3, -1)[:, :n]
+    assert np.abs(f[:, :n] - fo).max() <= 1e-9 * np.abs(fo).max()
+    assert abs(f[0, :n].sum()) > 1e-6          # the field pushes the net core charge along x
+    e.close(); o.close()
+
+
+def test_pqeq_md_steps_with_migration(built):
+    """Device-resident stepping with PQEq (spos migrates with MODE_MOVE): 8 NVE steps against the oracle."""
+    s, cfg, e, o, sp = make(shell_sigma=0.0)
+    atype, pos, v, f, q = e.host_arrays(s.ranks[0])
+    n = e.NATOMS
+    rng = np.random.default_rng(11)
+    v[:, :n] = rng.normal(0.0, 2e-2, (3, n))     # fast enough that atoms cross the periodic faces
+    o.set_atoms(0, s.ranks[0]["atype"], s.ranks[0]["pos"], v[:, :n].copy(), None)
+    dt = 0.25 / UTIME
+    o.qeq(); o.force()
+    o.md_run(8, dt)
+    e.state_upload(atype, pos, v, q)
+    e.md_prime()
+    e.md_run(8, dt)
+    pe_o, ke_o, qs_o, _ = o.observe()
+    pe, ke, qs, _ = e.md_observe()
+    assert abs(pe[1:].sum() - pe_o[1:].sum()) < 1e-5 * abs(pe_o[1:].sum())
+    assert abs(ke - ke_o) < 1e-5 * abs(ke_o)
+    assert e.natoms_resident() == o.natoms(0) == n
+    e.close(); o.close()

@@ -10,14 +10,18 @@ CONFIGS = {
     "rdx1m": dict(d="init.rdx.lg", xyz="input.xyz", mc=(18, 18, 18), isLG=True),
     "water2m": dict(d="init.water", xyz="ice-1h.xyz", mc=(60, 35, 40), real_coords=True),
     "sic4m": dict(d="init.sicnp", xyz="input.xyz", mc=(20, 20, 18)),
+    "pe1m": dict(d="init.pe.pqeq", xyz="input.xyz", mc=(30, 45, 88), pqeq="pqeq1.par"),     # BASELINE config 5 (PQEq, rctap 12.5 A)
+    "pe_small": dict(d="init.pe.pqeq", xyz="input.xyz", mc=(10, 15, 30), pqeq="pqeq1.par"),
 }
 name = sys.argv[1]
 steps = int(sys.argv[2]) if len(sys.argv) > 2 else 5
 kw = dict(CONFIGS[name])
 d = kw.pop("d"); xyz = kw.pop("xyz")
+if "pqeq" in kw:
+    kw["pqeq_path"] = os.path.join(INP, d, kw.pop("pqeq"))
 t0 = time.time()
 s = build_system(os.path.join(INP, d, xyz), os.path.join(INP, d, "ffield"), displace_sigma=0.02, **kw)
-cfg = s.config()
+cfg = s.config(maxneighbs10=2400 if s.pqeq is not None else 1500)
 print(name, "natoms", s.natoms, "nbuffer", cfg.nbuffer, "maxrc", round(s.maxrc, 3), "build", round(time.time() - t0, 1), "s", flush=True)
 e = Engine(s, cfg)
 atype, pos, v, f, q = e.host_arrays(s.ranks[0])
