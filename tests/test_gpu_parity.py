@@ -292,3 +292,17 @@ def test_two_gpus_match_oracle(built):
                           "--master-port", "29533", os.path.join(root, "tools", "mr_diag.py"), "4", "2", "2", "--sigma", "0.02", "--assert"],
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+def test_two_gpus_pqeq_match_oracle(built):
+    """PQEq over 2 GPUs: shell displacements travel with the halo (MODE_COPY) and with migrating atoms (MODE_MOVE)."""
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                          "--master-port", "29534", os.path.join(root, "tools", "mr_diag.py"), "4", "3", "5", "--sigma", "0.03", "--pqeq", "--assert"],
+                         capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]

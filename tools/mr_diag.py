@@ -34,7 +34,12 @@ def main():
     mc = tuple(int(x) for x in args[:3])
     sigma = float(sys.argv[sys.argv.index("--sigma") + 1]) if "--sigma" in sys.argv else 0.0
     vp = VP[world]
-    s = build_system(G + "input.xyz", G + "ffield", mc=mc, vprocs=vp, displace_sigma=sigma)
+    pqeq = "--pqeq" in sys.argv      # PQEq: examples/3-reaxpq+ polyethylene, shells displaced, spos through halo and migration
+    if pqeq:
+        GP = G.replace("init.rdx/", "init.pe.pqeq/")
+        s = build_system(GP + "input.xyz", GP + "ffield", mc=mc, vprocs=vp, displace_sigma=sigma, pqeq_path=GP + "pqeq1.par")
+    else:
+        s = build_system(G + "input.xyz", G + "ffield", mc=mc, vprocs=vp, displace_sigma=sigma)
     cfg = s.config(device=local)
     e = Engine(s, cfg, rank=rank)
     e.comm_init_torch(dist)
@@ -42,8 +47,18 @@ def main():
     atype, pos, v, f, q = e.host_arrays(s.ranks[rank])
     n = e.NATOMS
     out = [f"rank {rank}/{world} vprocs {vp} natoms {n} of {s.natoms}"]
+    if pqeq:
+        for r in range(world):
+            nr = len(s.ranks[r]["atype"])
+            sp = np.random.default_rng(100 + r).normal(0.0, 4e-3, (3, nr))
+            o.set_spos(r, sp)
+            if r == rank:
+                e.spos[:, :n] = sp
     o.qeq()
-    e.QEq(atype, pos, q)
+    if pqeq:
+        e.PQEq(atype, pos, q)
+    else:
+        e.QEq(atype, pos, q)
     cp_o, cp_g = o.i32("copyptr", rank), e.fetch("copyptr")
     out.append(f"  QEq copyptr equal {np.array_equal(cp_o, cp_g)} {cp_g.tolist()} nstep {o.observe()[3]} vs {e.nstep_qeq}")
     if np.array_equal(cp_o, cp_g):
@@ -55,6 +70,11 @@ def main():
     out.append(f"  row counts equal {rows_ok}")
     out.append(f"  q diff {rel(q[:n], o.f64('q', rank)[:n])}")
     q[:n] = o.f64("q", rank)[:n]
+    if pqeq:
+        sp_o = o.f64("spos", rank).reshape(3, -1)[:, :n]
+        out.append(f"  spos diff {rel(e.spos[:, :n], sp_o)} skips {e.pqeq_skips()} vs {o.i32('pqeq_skips', rank)[0]}")
+        e.spos[:, :n] = sp_o
+        e._chk(e.L.rxg_spos_upload(e.h, n, e.spos.ctypes.data_as(e.L.rxg_spos_upload.argtypes[2])))
     o.force()
     e.FORCE(atype, pos, f, q)
     cp_o, cp_g = o.i32("copyptr", rank), e.fetch("copyptr")
@@ -70,6 +90,18 @@ def main():
     dt = 0.25 / UTIME
     lw2 = 2.0 * 2.0 / dt / dt
     os.environ.setdefault("X", "")
+    if pqeq:   # fast atoms so that some cross the rank boundary and carry their shells along
+        vv = np.random.default_rng(5).normal(0.0, 2e-2, (3, s.natoms))
+        off = 0
+        for r in range(world):
+            nr = len(s.ranks[r]["atype"])
+            st = s.ranks[r]
+            o.set_atoms(r, st["atype"], st["pos"], vv[:, off:off + nr].copy(), o.f64("q", r)[:nr].copy())
+            o.set_spos(r, o.f64("spos", r).reshape(3, -1)[:, :nr].copy())
+            if r == rank:
+                v[:, :n] = vv[:, off:off + nr]
+                pos[:, :n] = st["pos"]
+            off += nr
     e.state_upload(atype, pos, v, q)
     e.md_prime()
     o.qeq(); o.force()
