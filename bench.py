@@ -239,7 +239,9 @@ def main():
     r_g = roof(d[12], d[13], 2)
     roofline = None
     if r_h:
-        roofline = {"kernel": "k_spmv_rows (QEq CG SpMV H.(hs,ht): TMA-staged matrix stream, 16 lanes per row)", "bound": "hbm", "achieved": r_h[1], "peak": peak,
+        kname = ("k_spmv_rows16 (QEq CG SpMV H.(hs,ht): TMA-staged fp64 values + 16-bit column stream, 16 lanes per row)" if t_after[19] > 0
+                 else "k_spmv_rows (QEq CG SpMV H.(hs,ht): TMA-staged matrix stream, 16 lanes per row)")
+        roofline = {"kernel": kname, "bound": "hbm", "achieved": r_h[1], "peak": peak,
                     "unit": "GB/s", "frac": r_h[1] / peak, "traffic": traffic, "peak_source": peak_src,
                     "algorithmic_bytes_per_launch": r_h[0], "avg_launch_ms": d[10] / d[11], "launches_timed": int(d[11]),
                     "step_share": d[10] / max(t_after[3] - t_before[3], 1e-9),

@@ -174,9 +174,28 @@ int qeq_cg_single(Ctx *c, int nmax, int *iters) {
   const bool tma = !(getenv("RXG_SPMV_NOTMA") && getenv("RXG_SPMV_NOTMA")[0] == '1');
   const int lpr = getenv("RXG_SPMV_LPR") ? atoi(getenv("RXG_SPMV_LPR")) : 16;   // measured: 16 lanes/row 1.04 ms, 32: 1.09, 8: 1.29
   double4 *rowsum = (double4 *)c->tmp;
+  const int rows16 = getenv("RXG_SPMV_ROWS") ? atoi(getenv("RXG_SPMV_ROWS")) : 4;
+  static int carve_set = -2;
+  const int carve = getenv("RXG_SPMV_CARVEOUT") ? atoi(getenv("RXG_SPMV_CARVEOUT")) : -1;   // % of the SM's L1/shared array given to shared memory
+  if (carve != carve_set) {
+    carve_set = carve;
+    if (carve >= 0) {
+      cudaFuncSetAttribute(k_spmv_rows16<4, 16>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+      cudaFuncSetAttribute(k_spmv_rows16<8, 16>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+      cudaFuncSetAttribute(k_spmv_rows16<2, 16>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+      cudaFuncSetAttribute(k_spmv_rows16<4, 32>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
+    }
+  }
   auto spmv_rows = [&]() {
     const int nt = c->cp[6];
-    if (lpr == 16) LAUNCH(c, (k_spmv_rows<4, 16>), cdiv(nt, 4), 64, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->xs, rowsum);
+    if (c->have_col16) {
+      if (rows16 == 8) LAUNCH(c, (k_spmv_rows16<8, 16>), cdiv(nt, 8), 128, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col16, c->cbase, c->col, c->val, c->xs, rowsum);
+      else if (rows16 == 2) LAUNCH(c, (k_spmv_rows16<2, 16>), cdiv(nt, 2), 32, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col16, c->cbase, c->col, c->val, c->xs, rowsum);
+      else if (rows16 == 40) LAUNCH(c, (k_spmv_rows16<4, 16, false>), cdiv(nt, 4), 64, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col16, c->cbase, c->col, c->val, c->xs, rowsum);
+      else if (rows16 == 80) LAUNCH(c, (k_spmv_rows16<8, 16, false>), cdiv(nt, 8), 128, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col16, c->cbase, c->col, c->val, c->xs, rowsum);
+      else if (rows16 == 432) LAUNCH(c, (k_spmv_rows16<4, 32>), cdiv(nt, 4), 128, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col16, c->cbase, c->col, c->val, c->xs, rowsum);
+      else LAUNCH(c, (k_spmv_rows16<4, 16>), cdiv(nt, 4), 64, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col16, c->cbase, c->col, c->val, c->xs, rowsum);
+    } else if (lpr == 16) LAUNCH(c, (k_spmv_rows<4, 16>), cdiv(nt, 4), 64, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->xs, rowsum);
     else if (lpr == 816) LAUNCH(c, (k_spmv_rows<8, 16>), cdiv(nt, 8), 128, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->xs, rowsum);
     else if (lpr == 216) LAUNCH(c, (k_spmv_rows<2, 16>), cdiv(nt, 2), 32, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->xs, rowsum);
     else if (lpr == 8) LAUNCH(c, (k_spmv_rows<8, 8>), cdiv(nt, 8), 64, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->xs, rowsum);
@@ -184,6 +203,11 @@ int qeq_cg_single(Ctx *c, int nmax, int *iters) {
   };
   const int dgrid = cdiv(c->cp[6], 256);
   (void)tgrid;
+  if (c->have_col16) {   // did every offset fit 15 bits?  (k_col16 ran right after the list fill)
+    RXG_CUDA(cudaMemcpyAsync(c->h_int + 7, c->d_flag + 7, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    RXG_CUDA(cudaStreamSynchronize(c->st));
+    if (c->h_int[7]) c->have_col16 = false;
+  }
   const bool pq = c->cfg.isPQEq != 0;   // PQEq: same CG, other gradient constant and Est (rxg_pqeq.cuh)
   if (pq) {
     spmv_rows();
@@ -292,7 +316,9 @@ int qeq_device(Ctx *c, bool for_force = false) {
     c->pqeq_skips += c->h_int[6];
   }
   c->nstep_qeq = it;
-  c->timers_ms[14] = (double)c->nnz;
+  c->timers_ms[14] = (double)c->nnz_real;
+  c->timers_ms[18] = (double)c->nnz;
+  c->timers_ms[19] = c->have_col16 ? 1.0 : 0.0;
   c->timers_ms[15] = n;
   c->timers_ms[16] = c->cp[6];
   c->timers_ms[17] += it;
@@ -339,6 +365,8 @@ int rxg_create(const rxg_config *cfg, rxg_handle *out) {
   c->fuse = !(nf && nf[0] == '1');
   const char *fa = getenv("RXG_FUSE_API");
   c->fuse_api = fa && fa[0] == '1';
+  const char *c16 = getenv("RXG_COL16");
+  c->use_col16 = c16 && c16[0] == '1';
   const char *tp = getenv("RXG_QEQ_TWOPASS");
   c->qeq_mode = (tp && tp[0] == '1') ? 1 : 0;
   *out = c;   // returned even on failure so that rxg_last_error can be read
@@ -519,7 +547,7 @@ int rxg_destroy(rxg_handle h) {
     cudaStreamSynchronize(c->st);
     for (void *p : c->allocs) cudaFree(p);
     for (void *p : c->ff_allocs) cudaFree(p);
-    for (void *p : {(void *)c->col, (void *)c->val, (void *)c->d_blk, (void *)c->d_blk64, (void *)c->d_runs, (void *)c->d_ff})
+    for (void *p : {(void *)c->col, (void *)c->val, (void *)c->col16, (void *)c->cbase, (void *)c->d_blk, (void *)c->d_blk64, (void *)c->d_runs, (void *)c->d_ff})
       if (p) cudaFree(p);
     for (int k = 0; k < 2; k++) { if (c->sbuf[k]) cudaFree(c->sbuf[k]); if (c->rbuf[k]) cudaFree(c->rbuf[k]); }
     if (c->comm) nccl_api().CommDestroy(c->comm);

@@ -165,7 +165,10 @@ struct Ctx {
   int *rowcnt = nullptr;
   int *col = nullptr;            // [nnz_cap]
   double *val = nullptr;         // [nnz_cap] hessian (QEq list only)
-  long long nnz_cap = 0, nnz = 0;
+  unsigned short *col16 = nullptr;   // [nnz_cap] 16-bit column stream of the CG SpMV (k_col16): offset from cbase[k>>4], bit 15 = ghost
+  int *cbase = nullptr;              // [nnz_cap/16+2]
+  bool use_col16 = false, have_col16 = false;   // RXG_COL16=1 (see k_col16)
+  long long nnz_cap = 0, nnz = 0, nnz_real = 0;   // nnz counts the row padding, nnz_real does not
   bool list_is_qeq = false;
   // ---- bond-order products, [bond_cap] (compact bond slots) unless noted -----------------------------------------------------------
   double *BO[4] = {nullptr, nullptr, nullptr, nullptr}, *dln[3] = {nullptr, nullptr, nullptr}, *dBOp = nullptr;

@@ -634,7 +634,8 @@ __global__ void k_cell_finish(const double *__restrict__ pos, const int *__restr
     int i = g.order[a];
     g.slot_of[i] = a;
     long long packed = (long long)(unsigned)i | ((long long)itype[i] << 32);
-    g.sorted[a] = make_double4(pos[i], pos[NB + i], pos[2 * NB + i], __longlong_as_double(packed));
+    const double x = pos[i], y = pos[NB + i], z = pos[2 * NB + i];
+    g.sorted[a] = make_double4(x, y, z, __longlong_as_double(packed));
   }
 }
 
