@@ -70,6 +70,16 @@ interface
       import; type(c_ptr), value :: h; integer(c_int) :: natoms, nstep_qeq
       real(c_double) :: atype(*), pos(*), q(*), qsfp(*), qsfv(*)
    end function
+   integer(c_int) function rxg_pqeq(h, natoms, atype, pos, q, spos, qsfp, qsfv, nstep_qeq) bind(C, name="rxg_pqeq")
+      import; type(c_ptr), value :: h; integer(c_int) :: natoms, nstep_qeq
+      real(c_double) :: atype(*), pos(*), q(*), spos(*), qsfp(*), qsfv(*)
+   end function
+   integer(c_int) function rxg_spos_upload(h, natoms, spos) bind(C, name="rxg_spos_upload")
+      import; type(c_ptr), value :: h; integer(c_int), value :: natoms; real(c_double) :: spos(*)
+   end function
+   integer(c_int) function rxg_spos_download(h, natoms, spos) bind(C, name="rxg_spos_download")
+      import; type(c_ptr), value :: h; integer(c_int), value :: natoms; real(c_double) :: spos(*)
+   end function
    integer(c_int) function rxg_force(h, natoms, atype, pos, f, q, PE, astr) bind(C, name="rxg_force")
       import; type(c_ptr), value :: h; integer(c_int) :: natoms
       real(c_double) :: atype(*), pos(*), f(*), q(*), PE(0:13), astr(6)
@@ -111,6 +121,7 @@ subroutine rxg_setup()
    type(rxg_box) :: box
    character(c_char) :: id(128)
    integer :: devcount
+   integer(c_int), allocatable, target, save :: ispol_c(:)
    cfg%device = mod(myid, 8)                       ! one rank per GPU of an 8-GPU node
    cfg%nbuffer = NBUFFER; cfg%maxneighbs = MAXNEIGHBS; cfg%maxneighbs10 = MAXNEIGHBS10; cfg%nmincell = NMINCELL
    cfg%isQEq = isQEq; cfg%NMAXQEq = NMAXQEq; cfg%isPQEq = merge(1, 0, isPQEq); cfg%isEfield = merge(1, 0, isEfield)
@@ -140,6 +151,12 @@ subroutine rxg_setup()
    ff%inxn2 = c_loc(inxn2); ff%inxn3 = c_loc(inxn3); ff%inxn3hb = c_loc(inxn3hb); ff%inxn4 = c_loc(inxn4)
    ff%TBL_Evdw = c_loc(TBL_Evdw); ff%TBL_Eclmb = c_loc(TBL_Eclmb); ff%TBL_Eclmb_QEq = c_loc(TBL_Eclmb_QEq)
    ff%ntype_pqeq = 0
+   if (isPQEq) then                                ! module pqeq_vars after initialize_pqeq (src/module.F90:488-613)
+      ff%ntype_pqeq = ntype_pqeq
+      allocate(ispol_c(ntype_pqeq)); ispol_c = merge(1_c_int, 0_c_int, isPolarizable)     ! logical -> int, kept alive
+      ff%isPolarizable = c_loc(ispol_c); ff%Zpqeq = c_loc(Zpqeq); ff%Kspqeq = c_loc(Kspqeq); ff%inxnpqeq = c_loc(inxnpqeq)
+      ff%TBL_Eclmb_pcc = c_loc(TBL_Eclmb_pcc); ff%TBL_Eclmb_psc = c_loc(TBL_Eclmb_psc); ff%TBL_Eclmb_pss = c_loc(TBL_Eclmb_pss)
+   endif
    call rxg_check(rxg_set_forcefield(rxg_handle, ff))
    box%HH = reshape(HH(:,:,0), [9]); box%HHi = reshape(HHi, [9])
    box%lata = lata; box%latb = latb; box%latc = latc
@@ -166,6 +183,15 @@ it_timer(24) = it_timer(24) + nstep_qeq
 end subroutine
 
 !------------------------------------------------------------------------------------------------------------
+subroutine PQEq(atype, pos, q)                                 ! replaces src/pqeq.F90:2-182 (spos is module state, relaxed at the end)
+use atoms; use rxg_binding
+implicit none
+real(8) :: atype(NBUFFER), pos(NBUFFER,3), q(NBUFFER)
+call rxg_check(rxg_pqeq(rxg_handle, NATOMS, atype, pos, q, spos, qsfp, qsfv, nstep_qeq))
+it_timer(24) = it_timer(24) + nstep_qeq
+end subroutine
+
+!------------------------------------------------------------------------------------------------------------
 subroutine FORCE(atype, pos, f, q)                             ! replaces src/pot.F90:2-90
 use atoms; use rxg_binding
 implicit none
@@ -184,5 +210,7 @@ if (imode /= MODE_MOVE) then
    print'(a,i3)', "ERROR: imode doesn't match in COPYATOMS: ", imode    ! the other modes run inside the library
    call MPI_FINALIZE(ierr); stop
 endif
+if (isPQEq) call rxg_check(rxg_spos_upload(rxg_handle, NATOMS, spos))      ! spos migrates with the atom (src/comm.F90:153,165-167)
 call rxg_check(rxg_move(rxg_handle, NATOMS, atype, pos, v, q, qs, qt, qsfp, qsfv))
+if (isPQEq) call rxg_check(rxg_spos_download(rxg_handle, NATOMS, spos))
 end subroutine

@@ -306,3 +306,37 @@ def test_two_gpus_pqeq_match_oracle(built):
                           "--master-port", "29534", os.path.join(root, "tools", "mr_diag.py"), "4", "3", "5", "--sigma", "0.03", "--pqeq", "--assert"],
                          capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-3000:]
+
+
+def test_nve_drift_1000_steps_matches_oracle(built):
+    """north_star: "NVE energy drift over 1000 steps must match the reference's drift".  168-atom RDX cell (BASELINE
+    configs[0]), mdmode 1, dt 0.25 fs, QEq every step at 1e-7 -- the README sample run extended to 1000 steps.  The two
+    trajectories separate chaotically (production summation order, see test_cg_sensitivity), so the comparison is on the
+    total energy per atom at every 100th step: both stay inside the same band around E(0) and end within it of each
+    other; the kinetic energy histories agree while the trajectories are still close."""
+    s, cfg, e, o = make("rdx_1x1x1")
+    atype, pos, v, f, q = e.host_arrays(s.ranks[0])
+    n = e.NATOMS
+    dt = 0.25 / UTIME
+    o.qeq(); o.force()
+    e.state_upload(atype, pos, v, q)
+    e.md_prime()
+    pe_o, ke_o, _, _ = o.observe()
+    pe_g, ke_g, _, _ = e.md_observe()
+    e0_o, e0_g = (pe_o[1:].sum() + ke_o) / n, (pe_g[1:].sum() + ke_g) / n
+    assert abs(e0_o - e0_g) < 1e-9 * abs(e0_o) + 2e-5          # charges differ by the CG spread only
+    te_o, te_g, k_o, k_g = [], [], [], []
+    for blk in range(10):
+        o.md_run(100, dt, 1, 0.0, blk * 100)
+        e.md_run(100, dt, 1, 0.0, blk * 100)
+        pe_o, ke_o, _, _ = o.observe()
+        pe_g, ke_g, _, _ = e.md_observe()
+        te_o.append((pe_o[1:].sum() + ke_o) / n); te_g.append((pe_g[1:].sum() + ke_g) / n)
+        k_o.append(ke_o / n); k_g.append(ke_g / n)
+    te_o, te_g = np.array(te_o), np.array(te_g)
+    band = 4e-3                                                   # kcal/mol/atom; the oracle's own excursion is ~1.5e-3
+    assert np.abs(te_o - e0_o).max() < band and np.abs(te_g - e0_g).max() < band
+    assert abs((te_g[-1] - e0_g) - (te_o[-1] - e0_o)) < band
+    assert abs(k_g[0] - k_o[0]) < 2e-2 * k_o[0]                  # first 100 steps: same heating of the cold start
+    assert abs(k_g[-1] - k_o[-1]) < 0.3 * k_o[-1]                # same temperature scale after 1000 steps
+    e.close(); o.close()
