@@ -394,6 +394,7 @@ int rxg_create(const rxg_config *cfg, rxg_handle *out) {
   RXG_TRY(dalloc(c, &c->qst, NB)); RXG_TRY(dalloc(c, &c->hsq, NB)); RXG_TRY(dalloc(c, &c->gst, NB));
   RXG_TRY(dalloc(c, &c->hst, NB)); RXG_TRY(dalloc(c, &c->tst, NB)); RXG_TRY(dalloc(c, &c->ust, NB)); RXG_TRY(dalloc(c, &c->wst, NB));
   RXG_TRY(dalloc(c, &c->sel, NB)); c->sel_cap = (int)NB;
+  RXG_TRY(dalloc(c, &c->gsrc, NB));
   RXG_TRY(dalloc(c, &c->itype, NB)); RXG_TRY(dalloc(c, &c->gid, NB)); RXG_TRY(dalloc(c, &c->frcindx, NB));
   RXG_TRY(dalloc(c, &c->tmp, 15 * NB));
   if (cfg->isPQEq) {

@@ -136,6 +136,8 @@ struct Ctx {
   double *qsl = nullptr;    // [NB] by SLOT: q (final charges, for the shell relaxation and ENbond_PQEq)
   long long pqeq_skips = 0;
   // ---- COPYATOMS bookkeeping -----------------------------------------------------------------------------
+  int *gsrc = nullptr;      // [NB] vprocs 1 1 1 only: the resident each ghost is a periodic image of (halo_self)
+  bool halo_self = false;
   int *sel = nullptr;       // concatenated selection lists of the six stages of the last MODE_COPY
   int sel_cap = 0, selptr[7] = {0, 0, 0, 0, 0, 0, 0};
   int ns[7] = {0, 0, 0, 0, 0, 0, 0}, nr[7] = {0, 0, 0, 0, 0, 0, 0};   // atoms sent / received per stage (1..6)

@@ -183,13 +183,16 @@ __global__ void k_pack_copy(const double *__restrict__ pos, int NB, const double
   buf[5 * c + k] = s.x; buf[6 * c + k] = s.y; buf[7 * c + k] = h.x; buf[8 * c + k] = h.y;
 }
 // append_atoms for MODE_COPY (src/comm.F90:497-522)
+// `sel` (self-exchange only, else null): the sender's selection list IS this rank's, so ghost m is an image of local atom
+// sel[k]; gsrc[m] = the RESIDENT it descends from (an image of an image resolves through the earlier stage's entry)
 __global__ void k_unpack_copy(double *__restrict__ pos, int NB, double *__restrict__ atype, double *__restrict__ q,
                               double2 *__restrict__ qst, double4 *__restrict__ hsq, int cnt, int dst0,
-                              const double *__restrict__ buf) {
+                              const double *__restrict__ buf, const int *__restrict__ sel, int natoms, int *__restrict__ gsrc) {
   int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k >= cnt) return;
   size_t c = cnt;
   int m = dst0 + k;
+  if (sel) { int i = sel[k]; gsrc[m] = i < natoms ? i : gsrc[i]; }
   pos[m] = buf[k]; pos[NB + m] = buf[c + k]; pos[2 * (size_t)NB + m] = buf[2 * c + k];
   atype[m] = buf[3 * c + k];
   double qq = buf[4 * c + k];
@@ -303,6 +306,19 @@ __global__ void k_unpack_vals(int which, int cnt, int dst0, const double *__rest
   if (which == 1) qst[m] = make_double2(buf[k], buf[c + k]);
   else if (which == 2) { double qq = buf[2 * c + k]; hsq[m] = make_double4(buf[k], buf[c + k], qq, 0.0); q[m] = qq; }
   else { double2 v = make_double2(buf[k], buf[c + k]); hst[m] = v; xs[slot_of[m]] = v; }
+}
+// the same refreshes when every ghost is a periodic image of a resident of this rank: one gather through gsrc
+__global__ void k_refresh_self(int which, int natoms, int ntot, const int *__restrict__ gsrc, double2 *__restrict__ qst,
+                               double4 *__restrict__ hsq, double2 *__restrict__ hst, double2 *__restrict__ xs,
+                               const int *__restrict__ slot_of, double *__restrict__ q, double *__restrict__ spos, int NB) {
+  int m = natoms + blockIdx.x * blockDim.x + threadIdx.x;
+  if (m >= ntot) return;
+  const int i = gsrc[m];
+  if (which == 4) { q[m] = q[i]; return; }
+  if (which == 5) { spos[m] = spos[i]; spos[(size_t)NB + m] = spos[(size_t)NB + i]; spos[2 * (size_t)NB + m] = spos[2 * (size_t)NB + i]; return; }
+  if (which == 1) qst[m] = qst[i];
+  else if (which == 2) { double4 h = hsq[i]; hsq[m] = make_double4(h.x, h.y, h.z, 0.0); q[m] = h.z; }
+  else { double2 v = hst[i]; hst[m] = v; xs[slot_of[m]] = v; }
 }
 // MODE_CPBK: ghost forces of one stage travel back to the rank that owns the source atoms and are added there
 // (src/comm.F90:385-396, 474-482); the owner addresses them through its own selection list
@@ -450,6 +466,8 @@ inline int halo_copy(Ctx *c, const double dr[3]) {
   BoxDev b = make_boxdev(c->box);
   c->cp[0] = c->natoms;
   c->selptr[0] = 0;
+  c->halo_self = true;   // every neighbour is this rank itself (vprocs 1 1 1): ghosts are periodic images of residents
+  for (int t = 0; t < 6; t++) c->halo_self = c->halo_self && c->box.target_node[t] == c->box.myid;
   if (c->natoms > 0) LAUNCH(c, k_to_norm, cdiv(c->natoms, 256), 256, 0, c->pos, NB, c->natoms, b);
   for (int axis = 0; axis < 3; axis++) {
     const int d0 = 2 * axis + 1, d1 = d0 + 1;
@@ -480,7 +498,8 @@ inline int halo_copy(Ctx *c, const double dr[3]) {
     for (int k = 0; k < 2; k++) {
       c->ns[d0 + k] = ns[k]; c->nr[d0 + k] = nr[k];
       if (nr[k] > 0)
-        LAUNCH(c, k_unpack_copy, cdiv(nr[k], 256), 256, 0, c->pos, NB, c->atype, c->q, c->qst, c->hsq, nr[k], c->cp[d0 - 1 + k], rb[k]);
+        LAUNCH(c, k_unpack_copy, cdiv(nr[k], 256), 256, 0, c->pos, NB, c->atype, c->q, c->qst, c->hsq, nr[k], c->cp[d0 - 1 + k], rb[k],
+               c->halo_self ? c->sel + c->selptr[d0 - 1 + k] : (const int *)nullptr, c->natoms, c->gsrc);
     }
   }
   if (c->cp[6] > 0) LAUNCH(c, k_to_real, cdiv(c->cp[6], 256), 256, 0, c->pos, NB, c->cp[6], b);
@@ -491,7 +510,11 @@ inline int halo_copy(Ctx *c, const double dr[3]) {
 // (the reference does one per call, src/comm.F90:222-227,260-264)
 inline int halo_refresh(Ctx *c, int which, int roundtrips) {
   const int nf = (which == 2 || which == 5) ? 3 : (which == 4 ? 1 : 2);
-  for (int axis = 0; axis < 3; axis++) {
+  const int nghost = c->cp[6] - c->natoms;
+  if (c->halo_self && nghost > 0)
+    LAUNCH(c, k_refresh_self, cdiv(nghost, 256), 256, 0, which, c->natoms, c->cp[6], c->gsrc, c->qst, c->hsq, c->hst, c->xs, c->gnb.slot_of,
+           c->q, c->spos, c->NB);
+  for (int axis = 0; axis < 3 && !c->halo_self; axis++) {
     const int d0 = 2 * axis + 1;
     const int ns[2] = {c->ns[d0], c->ns[d0 + 1]}, nr[2] = {c->nr[d0], c->nr[d0 + 1]};
     if (ns[0] + ns[1] + nr[0] + nr[1] == 0) continue;
