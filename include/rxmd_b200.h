@@ -171,6 +171,13 @@ int rxg_state_download(rxg_handle h, int *natoms, double *atype, double *pos, do
  * last nstep_qeq, accumulated astr(1:6) */
 int rxg_md_observe(rxg_handle h, double *PE, double *KE, double *qsum, int *nstep_qeq, double *astr);
 
+/* thermostat hooks for resident velocities: the thermostats stay host logic (mdmode 4/5/7/8 and LinearMomentum,
+ * src/main.F90:49-62,684-803); these two calls are the O(N) parts they need.
+ * stats[6*t .. 6*t+5], t = type-1 < nso: {atom count, sum 1/2 m v^2, sum m, sum m vx, sum m vy, sum m vz} of THIS rank's
+ * residents (the host sums over ranks like the reference's MPI_ALLREDUCE);  affine: v(i) = scale[type(i)-1]*v(i) - shift. */
+int rxg_md_velocity_stats(rxg_handle h, double *stats);
+int rxg_md_velocity_affine(rxg_handle h, const double *scale, const double *shift);
+
 /* ---- introspection used by the parity tests (device -> host copies of hot-path products) ---- */
 /* name in: "copyptr"(7 ints) "nbrlist" "nbrindx" "nbp_rowptr"(int64) "nbp_col" "qeq_rowptr" "qeq_col"
  * "qeq_val" "BO"(4 planes) "delta" "deltap" "atype" "pos" "q" "f" "qs" "qt" "gs" "gt" "hs" "ht" "cdbnd" "ccbnd"

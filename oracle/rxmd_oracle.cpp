@@ -1790,7 +1790,6 @@ int orc_move(orc_world h) {
 int orc_md_run(orc_world h, int nsteps, double dt, int qstep, double Lex_w2, int step0) {
   World *w = (World *)h;
   const Params &P = w->P;
-  if (P.cfg.isEfield) { w->err = "orc_md_run: LinearMomentum (src/main.F90:71) is not restated; isEfield unsupported here"; return RXG_ERR_ARG; }
   for (int nstep = step0; nstep < step0 + nsteps; nstep++) {
     for (auto &r : w->R) {
       for (int i = 0; i < r.natoms; i++) {
@@ -1799,9 +1798,23 @@ int orc_md_run(orc_world h, int nsteps, double dt, int qstep, double Lex_w2, int
       }
       for (int i = 0; i < r.natoms; i++) r.qsfv[i] = r.qsfv[i] + 0.5 * dt * Lex_w2 * (r.q[i] - r.qsfp[i]);
       for (int i = 0; i < r.natoms; i++) r.qsfp[i] = r.qsfp[i] + dt * r.qsfv[i];
+    }
+    if (P.cfg.isEfield) {   // "always correct the linear momentum when electric field is applied", src/main.F90:70-71; LinearMomentum :773-803
+      double mm = 0, vcm[3] = {0, 0, 0};
+      for (auto &r : w->R)
+        for (int i = 0; i < r.natoms; i++) {
+          double m = P.mass[nint(r.atype[i]) - 1];
+          for (int c = 0; c < 3; c++) vcm[c] = vcm[c] + m * r.v[(size_t)c * r.NB + i];
+          mm = mm + m;
+        }
+      for (int c = 0; c < 3; c++) vcm[c] = vcm[c] / mm;
+      for (auto &r : w->R)
+        for (int c = 0; c < 3; c++)
+          for (int i = 0; i < r.natoms; i++) r.v[(size_t)c * r.NB + i] = r.v[(size_t)c * r.NB + i] - vcm[c];
+    }
+    for (auto &r : w->R)
       for (int c = 0; c < 3; c++)
         for (int i = 0; i < r.natoms; i++) r.pos[(size_t)c * r.NB + i] = r.pos[(size_t)c * r.NB + i] + dt * r.v[(size_t)c * r.NB + i];
-    }
     int rc = orc_move(h);
     if (rc) return rc;
     if (nstep % qstep == 0 && (rc = orc_qeq(h))) return rc;

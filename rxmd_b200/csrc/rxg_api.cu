@@ -770,13 +770,19 @@ int rxg_md_run(rxg_handle h, int nsteps, double dt, int qstep, double Lex_w2, in
   Ctx *c = (Ctx *)h;
   RXG_TRY(check_ready(c, c ? c->natoms : -1));
   if (qstep < 1) qstep = 1;
-  if (c->cfg.isEfield) { c->err = "rxg_md_run: LinearMomentum (src/main.F90:71) is host work; isEfield runs go through rxg_pqeq/rxg_force"; return RXG_ERR_ARG; }
   cudaEventRecord(c->evm0, c->st);
   auto wall = []() { return std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now().time_since_epoch()).count(); };
   for (int nstep = step0; nstep < step0 + nsteps; nstep++) {
     int n = c->natoms;
     // vkick(1) ; qsfv,qsfp ; pos += dt v      (src/main.F90:64-72)
-    LAUNCH(c, k_md_first_half, cdiv(n, 256), 256, 0, n, c->NB, dt, Lex_w2, c->itype, c->d_ff, c->pos, c->v, c->f, c->q, c->qsfp, c->qsfv);
+    const bool ef = c->cfg.isEfield != 0;
+    LAUNCH(c, k_md_first_half, cdiv(n, 256), 256, 0, n, c->NB, dt, Lex_w2, c->itype, c->d_ff, c->pos, c->v, c->f, c->q, c->qsfp, c->qsfv, !ef);
+    if (ef) {   // LinearMomentum between the kick and the drift (src/main.F90:70-72)
+      RXG_CUDA(cudaMemsetAsync(c->d_acc + 52, 0, sizeof(double) * 4, c->st));
+      LAUNCH(c, k_momentum, cdiv(n, 256), 256, 0, n, c->NB, c->itype, c->d_ff, c->v, c->d_acc + 52);
+      RXG_TRY(allreduce_acc(c, 52, 4));
+      LAUNCH(c, k_sub_vcm_drift, cdiv(n, 256), 256, 0, n, c->NB, dt, c->v, c->pos, c->d_acc + 52, true);
+    }
     double t0 = wall();
     RXG_TRY(halo_move(c));                                   // :75
     RXG_CUDA(cudaStreamSynchronize(c->st));
@@ -836,6 +842,33 @@ int rxg_md_observe(rxg_handle h, double *PE, double *KE, double *qsum, int *nste
   if (qsum) *qsum = c->h_acc[49];
   if (nstep_qeq) *nstep_qeq = c->nstep_qeq;
   if (astr) for (int k = 0; k < 6; k++) astr[k] = c->astr[k] + c->h_acc[40 + k];
+  return RXG_OK;
+}
+
+// ---- thermostat hooks: what the host's mdmode 4/5/7/8 code needs from resident velocities (src/main.F90:49-62,684-770)
+int rxg_md_velocity_stats(rxg_handle h, double *stats) {
+  Ctx *c = (Ctx *)h;
+  RXG_TRY(check_ready(c, c ? c->natoms : -1));
+  if (!stats) return RXG_ERR_ARG;
+  const int n = c->natoms, ns = c->ff.nso < VSTAT_MAXT ? c->ff.nso : VSTAT_MAXT;
+  double *d = c->tmp;   // scratch
+  RXG_CUDA(cudaMemsetAsync(d, 0, sizeof(double) * 6 * VSTAT_MAXT, c->st));
+  if (n > 0) LAUNCH(c, k_types, cdiv(n, 256), 256, 0, c->atype, n, c->itype, c->gid);   // valid right after rxg_state_upload too
+  if (n > 0) LAUNCH(c, k_velocity_stats, cdiv(n, 256), 256, 0, n, c->NB, c->itype, c->d_ff, c->v, d);
+  RXG_CUDA(cudaMemcpyAsync(stats, d, sizeof(double) * 6 * ns, cudaMemcpyDeviceToHost, c->st));
+  RXG_CUDA(cudaStreamSynchronize(c->st));
+  return RXG_OK;
+}
+int rxg_md_velocity_affine(rxg_handle h, const double *scale, const double *shift) {
+  Ctx *c = (Ctx *)h;
+  RXG_TRY(check_ready(c, c ? c->natoms : -1));
+  if (!scale || !shift) return RXG_ERR_ARG;
+  const int n = c->natoms;
+  double *d = c->tmp;
+  RXG_CUDA(cudaMemcpyAsync(d, scale, sizeof(double) * c->ff.nso, cudaMemcpyHostToDevice, c->st));
+  if (n > 0) LAUNCH(c, k_types, cdiv(n, 256), 256, 0, c->atype, n, c->itype, c->gid);
+  if (n > 0) LAUNCH(c, k_velocity_affine, cdiv(n, 256), 256, 0, n, c->NB, c->itype, d, shift[0], shift[1], shift[2], c->v);
+  RXG_CUDA(cudaStreamSynchronize(c->st));
   return RXG_OK;
 }
 

@@ -908,7 +908,7 @@ __global__ void __launch_bounds__(256) k_virial(int ntot, const double *__restri
 __global__ void k_md_first_half(int n, int NB, double dt, double Lex_w2, const int *__restrict__ itype,
                                 const DevFF *__restrict__ ffp, double *__restrict__ pos, double *__restrict__ v,
                                 const double *__restrict__ f, const double *__restrict__ q, double *__restrict__ qsfp,
-                                double *__restrict__ qsfv) {
+                                double *__restrict__ qsfv, bool drift) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   double dthm = dt * 0.5 / ffp->mass[itype[i] - 1];
@@ -919,8 +919,65 @@ __global__ void k_md_first_half(int n, int NB, double dt, double Lex_w2, const i
   for (int c = 0; c < 3; c++) {
     double vv = add_rn(v[(size_t)c * NB + i], mul_rn(mul_rn(1.0, dthm), f[(size_t)c * NB + i]));
     v[(size_t)c * NB + i] = vv;
-    pos[(size_t)c * NB + i] = add_rn(pos[(size_t)c * NB + i], mul_rn(dt, vv));
+    if (drift) pos[(size_t)c * NB + i] = add_rn(pos[(size_t)c * NB + i], mul_rn(dt, vv));
   }
+}
+// LinearMomentum, src/main.F90:773-803 (called every step when an electric field is applied, :70-71):
+// acc[0] = sum m, acc[1..3] = sum m v
+__global__ void __launch_bounds__(256) k_momentum(int n, int NB, const int *__restrict__ itype, const DevFF *__restrict__ ffp,
+                                                  const double *__restrict__ v, double *__restrict__ acc) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  double part[4] = {0, 0, 0, 0};
+  if (i < n) {
+    double m = ffp->mass[itype[i] - 1];
+    part[0] = m; part[1] = m * v[i]; part[2] = m * v[NB + i]; part[3] = m * v[2 * (size_t)NB + i];
+  }
+  block_add<4>(part, acc);
+}
+__global__ void k_sub_vcm_drift(int n, int NB, double dt, double *__restrict__ v, double *__restrict__ pos,
+                                const double *__restrict__ acc, bool drift) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double mm = acc[0];
+#pragma unroll
+  for (int c = 0; c < 3; c++) {
+    double vv = sub_rn(v[(size_t)c * NB + i], acc[1 + c] / mm);
+    v[(size_t)c * NB + i] = vv;
+    if (drift) pos[(size_t)c * NB + i] = add_rn(pos[(size_t)c * NB + i], mul_rn(dt, vv));
+  }
+}
+// thermostat hooks for device-resident stepping (the thermostats themselves stay host logic, src/main.F90:49-62,684-770):
+// per atom type t: out[6t..6t+5] += {count, sum 1/2 m v^2, sum m, sum m vx, sum m vy, sum m vz}
+constexpr int VSTAT_MAXT = 20;   // MAX_ELEMENT of ScaleTemperature, src/main.F90:727
+__global__ void __launch_bounds__(256) k_velocity_stats(int n, int NB, const int *__restrict__ itype, const DevFF *__restrict__ ffp,
+                                                        const double *__restrict__ v, double *__restrict__ out) {
+  __shared__ double sh[6 * VSTAT_MAXT];
+  for (int k = threadIdx.x; k < 6 * VSTAT_MAXT; k += blockDim.x) sh[k] = 0.0;
+  __syncthreads();
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) {
+    int t = itype[i] - 1;
+    if (t >= 0 && t < VSTAT_MAXT) {
+      double m = ffp->mass[t], vx = v[i], vy = v[NB + i], vz = v[2 * (size_t)NB + i];
+      atomicAdd(&sh[6 * t], 1.0);
+      atomicAdd(&sh[6 * t + 1], 0.5 * m * ((vx * vx + vy * vy) + vz * vz));
+      atomicAdd(&sh[6 * t + 2], m);
+      atomicAdd(&sh[6 * t + 3], m * vx); atomicAdd(&sh[6 * t + 4], m * vy); atomicAdd(&sh[6 * t + 5], m * vz);
+    }
+  }
+  __syncthreads();
+  for (int k = threadIdx.x; k < 6 * VSTAT_MAXT; k += blockDim.x)
+    if (sh[k] != 0.0) atomicAdd(&out[k], sh[k]);
+}
+// v(i) = scale[type(i)] * v(i) - shift
+__global__ void k_velocity_affine(int n, int NB, const int *__restrict__ itype, const double *__restrict__ scale,
+                                  double sx, double sy, double sz, double *__restrict__ v) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  const double a = scale[itype[i] - 1];
+  v[i] = sub_rn(mul_rn(a, v[i]), sx);
+  v[NB + i] = sub_rn(mul_rn(a, v[NB + i]), sy);
+  v[2 * (size_t)NB + i] = sub_rn(mul_rn(a, v[2 * (size_t)NB + i]), sz);
 }
 __global__ void __launch_bounds__(256) k_md_second_half(int n, int NB, double dt, double Lex_w2, const int *__restrict__ itype,
                                                         const DevFF *__restrict__ ffp, double *__restrict__ v,

@@ -66,6 +66,8 @@ def load_library():
     L.rxg_md_prime.argtypes = [vp]
     L.rxg_state_download.argtypes = [vp, ip, dp, dp, dp, dp, dp, dp, dp]
     L.rxg_md_observe.argtypes = [vp, dp, dp, dp, ip, dp]
+    L.rxg_md_velocity_stats.argtypes = [vp, dp]
+    L.rxg_md_velocity_affine.argtypes = [vp, dp, dp]
     L.rxg_debug_fetch.argtypes = [vp, C.c_char_p, vp, C.c_longlong, C.POINTER(C.c_longlong)]
     L.rxg_launch_count.argtypes = [vp]
     L.rxg_launch_count.restype = C.c_longlong
@@ -216,6 +218,21 @@ class Engine:
         self._chk(self.L.rxg_md_observe(self.h, _dp(self.PE), C.byref(ke), C.byref(qs), C.byref(it), _dp(astr)))
         self.nstep_qeq = it.value
         return self.PE.copy(), ke.value, qs.value, it.value
+
+    # -- thermostat hooks (the host's mdmode 4/5/7/8 logic drives them; src/main.F90:49-62,684-803)
+    def velocity_stats(self):
+        """Per atom type: count, sum 1/2 m v^2, sum m, sum m v (3) of this rank's residents -> array [nso, 6]."""
+        nso = self.sys.pff.struct.nso
+        out = np.zeros(6 * nso)
+        self._chk(self.L.rxg_md_velocity_stats(self.h, _dp(out)))
+        return out.reshape(nso, 6)
+
+    def velocity_affine(self, scale, shift=(0.0, 0.0, 0.0)):
+        """v(i) = scale[type(i)-1] * v(i) - shift on the resident velocities."""
+        sc = np.ascontiguousarray(scale, dtype=np.float64)
+        sh = np.ascontiguousarray(shift, dtype=np.float64)
+        assert sc.size == self.sys.pff.struct.nso and sh.size == 3
+        self._chk(self.L.rxg_md_velocity_affine(self.h, _dp(sc), _dp(sh)))
 
     def natoms_resident(self):
         return int(self.fetch("copyptr")[0])

@@ -340,3 +340,39 @@ def test_nve_drift_1000_steps_matches_oracle(built):
     assert abs(k_g[0] - k_o[0]) < 2e-2 * k_o[0]                  # first 100 steps: same heating of the cold start
     assert abs(k_g[-1] - k_o[-1]) < 0.3 * k_o[-1]                # same temperature scale after 1000 steps
     e.close(); o.close()
+
+
+def test_thermostat_hooks_scale_temperature(built):
+    """rxg_md_velocity_stats / rxg_md_velocity_affine carry the host's thermostats on resident velocities: here mdmode 7's
+    ScaleTemperature (element-wise rescale to treq, src/main.F90:720-770) followed by LinearMomentum (:773-803)."""
+    s, cfg, e, o = make("rdx_2x2x2_disp")
+    atype, pos, v, f, q = e.host_arrays(s.ranks[0])
+    n = e.NATOMS
+    rng = np.random.default_rng(2)
+    v[:, :n] = rng.normal(0.0, 1e-2, (3, n)) + 3e-3
+    e.state_upload(atype, pos, v, q)
+    ity = np.rint(atype[:n]).astype(int)
+    mass = np.asarray(s.mass)
+    st = e.velocity_stats()
+    nso = st.shape[0]
+    for t in range(1, nso + 1):
+        m = ity == t
+        ref = [m.sum(), (0.5 * mass[t] * (v[:, :n][:, m] ** 2).sum()), mass[t] * m.sum(), *(mass[t] * v[:, :n][:, m].sum(axis=1))]
+        assert np.allclose(st[t - 1], ref, rtol=1e-12, atol=1e-12 * max(1.0, np.abs(ref).max()))
+    UTEMP0 = 503.398008
+    UTEMP = UTEMP0 * 2.0 / 3.0
+    treq = 300.0 / UTEMP0 * UTEMP0 / UTEMP0   # any positive target in the reference's reduced units
+    scale = np.zeros(nso)
+    for t in range(nso):
+        if st[t, 0] > 1.0:
+            scale[t] = np.sqrt((treq * UTEMP0) / ((st[t, 1] / st[t, 0]) * UTEMP))
+    e.velocity_affine(scale)                                  # ScaleTemperature's rescale
+    st2 = e.velocity_stats()
+    vcm = st2[:, 3:6].sum(axis=0) / st2[:, 2].sum()
+    e.velocity_affine(np.ones(nso), vcm)                      # LinearMomentum
+    st3 = e.velocity_stats()
+    for t in range(nso):
+        if st[t, 0] > 1.0:
+            assert abs((st2[t, 1] / st2[t, 0]) * UTEMP - treq * UTEMP0) < 1e-10 * treq * UTEMP0
+    assert np.abs(st3[:, 3:6].sum(axis=0)).max() < 1e-12 * st3[:, 2].sum()
+    e.close(); o.close()

@@ -161,3 +161,28 @@ def test_pqeq_md_steps_with_migration(built):
     assert abs(ke - ke_o) < 1e-5 * abs(ke_o)
     assert e.natoms_resident() == o.natoms(0) == n
     e.close(); o.close()
+
+
+def test_pqeq_efield_md_steps_linear_momentum(built):
+    """examples/3-reaxpq+ as shipped: PQEq + `efield 1 0.01`.  The main loop then removes the centre-of-mass velocity every
+    step (LinearMomentum, src/main.F90:70-71); 6 device-resident steps against the oracle."""
+    s, cfg, e, o, sp = make(shell_sigma=0.0, efield=(1, 0.01))
+    atype, pos, v, f, q = e.host_arrays(s.ranks[0])
+    n = e.NATOMS
+    dt = 0.25 / UTIME
+    o.qeq(); o.force()
+    o.md_run(6, dt)
+    e.state_upload(atype, pos, v, q)
+    e.md_prime()
+    e.md_run(6, dt)
+    pe_o, ke_o, _, _ = o.observe()
+    pe, ke, _, _ = e.md_observe()
+    assert abs(pe[1:].sum() - pe_o[1:].sum()) < 1e-6 * abs(pe_o[1:].sum())
+    assert abs(ke - ke_o) < 1e-4 * abs(ke_o)
+    # total momentum after the closing half kick (the field acts on the net core charge, so it is not zero): same as the oracle's
+    st = e.velocity_stats()
+    vo = o.f64("v").reshape(3, -1)[:, :n]
+    mo = np.asarray(s.mass)[np.rint(o.f64("atype")[:n]).astype(int)]
+    p_o = (mo[None, :] * vo).sum(axis=1)
+    assert np.abs(st[:, 3:6].sum(axis=0) - p_o).max() < 1e-6 * np.abs(mo[None, :] * vo).sum()
+    e.close(); o.close()
