@@ -240,7 +240,9 @@ int qeq_cg_single(Ctx *c, int nmax, int *iters) {
       LAUNCH(c, (k_cg_dots<false>), dgrid, 256, 0, c->gnb.order, c->cp[6], n, rowsum, c->xs, c->q, c->gst, c->tst, c->ust, c->wst, c->itype, c->d_ff, c->d_acc);
     RXG_TRY(allreduce_acc(c, 0, 5));
     RXG_CUDA(cudaMemcpyAsync(c->h_acc, c->d_acc, sizeof(double) * 5, cudaMemcpyDeviceToHost, c->st));
+    if (c->peer_ok) RXG_CUDA(cudaMemcpyAsync(c->h_int + 3, c->d_flag + 3, sizeof(int), cudaMemcpyDeviceToHost, c->st));
     RXG_CUDA(cudaStreamSynchronize(c->st));
+    if (c->peer_ok && c->h_int[3]) { c->err = "peer halo: a neighbour's ghost values did not arrive (timeout)"; return RXG_ERR_NCCL; }
     float ms = 0;
     cudaEventElapsedTime(&ms, c->evk[0], c->evk[1]);
     c->timers_ms[10] += ms;
@@ -537,8 +539,58 @@ int rxg_comm_init(rxg_handle h, int rank, int nranks, const void *id) {
   if (!nccl_api().load(c->err)) return RXG_ERR_NCCL;
   ncclResult_t r = nccl_api().CommInitRank(&c->comm, nranks, uid, rank);
   if (r != ncclSuccess) { c->err = std::string("ncclCommInitRank: ") + nccl_api().GetErrorString(r); return RXG_ERR_NCCL; }
+  // ---- peer windows for the per-iteration ghost refreshes (halo_refresh_peer).  Needs every neighbour on this node with
+  // peer access; otherwise (or with RXG_PEER_HALO=0) the NCCL send/recv path stays.
+  const char *ph = getenv("RXG_PEER_HALO");
+  int want = !(ph && ph[0] == '0');
+  c->peer.assign(nranks, nullptr);
+  c->pw_cap = (size_t)3 * (size_t)c->NB / 2;
+  const size_t wbytes = sizeof(double) * (PW_HDR + 12 * c->pw_cap);
+  int *d_ok = c->d_flag + 2;
+  cudaIpcMemHandle_t *d_h = nullptr, *d_all = nullptr;
+  std::vector<cudaIpcMemHandle_t> all(nranks);
+  int ok = want;
+  if (ok && cudaMalloc((void **)&c->pw, wbytes) != cudaSuccess) { cudaGetLastError(); c->pw = nullptr; ok = 0; }
+  RXG_CUDA(cudaMalloc((void **)&d_h, sizeof(cudaIpcMemHandle_t)));
+  RXG_CUDA(cudaMalloc((void **)&d_all, sizeof(cudaIpcMemHandle_t) * nranks));
+  RXG_CUDA(cudaMalloc((void **)&c->d_pushcnt, 2 * sizeof(int)));
+  RXG_CUDA(cudaMemset(c->d_pushcnt, 0, 2 * sizeof(int)));
+  cudaIpcMemHandle_t mine;
+  memset(&mine, 0, sizeof(mine));
+  if (ok) {
+    RXG_CUDA(cudaMemset(c->pw, 0, sizeof(double) * PW_HDR));
+    if (cudaIpcGetMemHandle(&mine, c->pw) != cudaSuccess) { cudaGetLastError(); ok = 0; }
+  }
+  RXG_CUDA(cudaMemcpy(d_h, &mine, sizeof(mine), cudaMemcpyHostToDevice));
+  RXG_CUDA(cudaDeviceSynchronize());
+  r = nccl_api().AllGather(d_h, d_all, sizeof(cudaIpcMemHandle_t), ncclChar, c->comm, c->st);
+  if (r != ncclSuccess) { c->err = std::string("ncclAllGather: ") + nccl_api().GetErrorString(r); return RXG_ERR_NCCL; }
+  RXG_CUDA(cudaStreamSynchronize(c->st));
+  RXG_CUDA(cudaMemcpy(all.data(), d_all, sizeof(cudaIpcMemHandle_t) * nranks, cudaMemcpyDeviceToHost));
+  if (ok) {
+    c->peer[rank] = c->pw;
+    for (int t = 0; t < 6 && ok; t++) {
+      const int nb = c->box.target_node[t];
+      if (nb < 0 || nb >= nranks) { ok = 0; break; }
+      if (c->peer[nb]) continue;
+      void *p = nullptr;
+      if (cudaIpcOpenMemHandle(&p, all[nb], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = 0; break; }
+      c->peer[nb] = (double *)p;
+    }
+  }
+  // every rank must take the same path: all-reduce(min) of the local outcome
+  RXG_CUDA(cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice));
+  r = nccl_api().AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, c->comm, c->st);
+  if (r != ncclSuccess) { c->err = std::string("ncclAllReduce: ") + nccl_api().GetErrorString(r); return RXG_ERR_NCCL; }
+  RXG_CUDA(cudaStreamSynchronize(c->st));
+  RXG_CUDA(cudaMemcpy(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost));
+  RXG_CUDA(cudaMemset(d_ok, 0, 2 * sizeof(int)));
+  c->peer_ok = ok != 0;
+  cudaFree(d_h); cudaFree(d_all);
   return RXG_OK;
 }
+
+int rxg_comm_peer_halo(rxg_handle h) { return h && ((Ctx *)h)->peer_ok ? 1 : 0; }
 
 int rxg_destroy(rxg_handle h) {
   Ctx *c = (Ctx *)h;
@@ -551,6 +603,10 @@ int rxg_destroy(rxg_handle h) {
     for (void *p : {(void *)c->col, (void *)c->val, (void *)c->col16, (void *)c->cbase, (void *)c->d_blk, (void *)c->d_blk64, (void *)c->d_runs, (void *)c->d_ff})
       if (p) cudaFree(p);
     for (int k = 0; k < 2; k++) { if (c->sbuf[k]) cudaFree(c->sbuf[k]); if (c->rbuf[k]) cudaFree(c->rbuf[k]); }
+    for (size_t r = 0; r < c->peer.size(); r++)
+      if (c->peer[r] && c->peer[r] != c->pw) cudaIpcCloseMemHandle(c->peer[r]);
+    if (c->pw) cudaFree(c->pw);
+    if (c->d_pushcnt) cudaFree(c->d_pushcnt);
     if (c->comm) nccl_api().CommDestroy(c->comm);
     if (c->wl) cudaFree(c->wl);
     for (void *p : {(void *)c->nbrlist, (void *)c->nbrindx, (void *)c->bown, (void *)c->BO[0], (void *)c->BO[1], (void *)c->BO[2], (void *)c->BO[3], (void *)c->dln[0],

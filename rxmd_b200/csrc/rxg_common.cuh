@@ -27,6 +27,7 @@ struct NcclApi {
   ncclResult_t (*Send)(const void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*Recv)(void *, size_t, ncclDataType_t, int, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*AllReduce)(const void *, void *, size_t, ncclDataType_t, ncclRedOp_t, ncclComm_t, cudaStream_t) = nullptr;
+  ncclResult_t (*AllGather)(const void *, void *, size_t, ncclDataType_t, ncclComm_t, cudaStream_t) = nullptr;
   ncclResult_t (*GroupStart)() = nullptr;
   ncclResult_t (*GroupEnd)() = nullptr;
   const char *(*GetErrorString)(ncclResult_t) = nullptr;
@@ -44,7 +45,7 @@ struct NcclApi {
   field = reinterpret_cast<decltype(field)>(dlsym(handle, name));              \
   if (!field) { err = std::string("libnccl lacks ") + name; return false; }
     RXG_SYM(GetUniqueId, "ncclGetUniqueId") RXG_SYM(CommInitRank, "ncclCommInitRank") RXG_SYM(CommDestroy, "ncclCommDestroy")
-    RXG_SYM(Send, "ncclSend") RXG_SYM(Recv, "ncclRecv") RXG_SYM(AllReduce, "ncclAllReduce") RXG_SYM(GroupStart, "ncclGroupStart")
+    RXG_SYM(Send, "ncclSend") RXG_SYM(Recv, "ncclRecv") RXG_SYM(AllReduce, "ncclAllReduce") RXG_SYM(AllGather, "ncclAllGather") RXG_SYM(GroupStart, "ncclGroupStart")
     RXG_SYM(GroupEnd, "ncclGroupEnd") RXG_SYM(GetErrorString, "ncclGetErrorString")
 #undef RXG_SYM
     return true;
@@ -145,6 +146,14 @@ struct Ctx {
   size_t xbuf_cap = 0;
   long long moved = 0, nccl_msgs = 0;
   ncclComm_t comm = nullptr;
+  // ---- peer-memory halo refresh (multi-rank, one node): every rank owns a window that its neighbours write into directly
+  // over NVLink (cudaIpc), see halo_refresh_peer.  Window = 256 B of flags + 6 stages x 2 parities x pw_cap doubles.
+  double *pw = nullptr;
+  size_t pw_cap = 0;                 // doubles per buffer
+  std::vector<double *> peer;        // [nranks] window of each neighbour rank (my own for myself), nullptr otherwise
+  bool peer_ok = false;
+  int pseq = 0;                      // refresh sequence number, identical on every rank
+  int *d_pushcnt = nullptr;          // [2] block-completion counters of the push kernels
   bool fuse = true, fuse_api = false, lists_shared = false;   // md_run: QEq builds halo + 10 A list once for QEq and FORCE of the same step
   int qeq_mode = 0;         // 0 single-pass CG (default), 1 two-pass (literal kernels), strict => literal serial order
   double *tmp = nullptr;    // [12*NB] scratch for MOVE compaction

@@ -320,6 +320,94 @@ __global__ void k_refresh_self(int which, int natoms, int ntot, const int *__res
   else if (which == 2) { double4 h = hsq[i]; hsq[m] = make_double4(h.x, h.y, h.z, 0.0); q[m] = h.z; }
   else { double2 v = hst[i]; hst[m] = v; xs[slot_of[m]] = v; }
 }
+// ---------------------------------------------------------------------------------------------------
+// Peer-memory variant of the value refreshes (MODE_QCOPY1/2 and friends) for ranks that share a node: instead of
+// pack -> ncclSend/ncclRecv -> unpack, the sender's kernel gathers the selected values and STORES them straight into the
+// receiver's window over NVLink, then publishes a sequence number; the receiver's kernel waits for that number and scatters
+// the values to its ghosts.  One push + one pull kernel per direction, no library call on the critical path of a CG
+// iteration.  Stage order (x, then y, then z, so that edge and corner images are forwarded) is kept by stream order: a
+// rank's y-push runs after its x-pull.
+// Buffer reuse: message number s of a stage goes to parity s&1.  A rank can only send number s+2 after it pulled number
+// s+1 from the same neighbour, which that neighbour pushed after its own pulls of number s (same stream) -- so the buffer
+// being overwritten has been consumed.
+constexpr int PW_HDR = 32;   // doubles (256 B) reserved for the 12 flags
+constexpr long long PEER_SPIN_LIMIT = 4000000000LL;   // ~2 s at 1.9 GHz, then the pull gives up and raises an error flag
+
+__global__ void k_peer_push(int which, const int *__restrict__ sel, int cnt, const double2 *__restrict__ qst,
+                            const double4 *__restrict__ hsq, const double2 *__restrict__ hst, const double *__restrict__ q,
+                            const double *__restrict__ spos, int NB, double *__restrict__ rdata, int *rflag, int seq,
+                            int *__restrict__ counter) {
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < cnt) {
+    const int i = sel[k];
+    const size_t c = cnt;
+    if (which == 4) rdata[k] = q[i];
+    else if (which == 5) { rdata[k] = spos[i]; rdata[c + k] = spos[(size_t)NB + i]; rdata[2 * c + k] = spos[2 * (size_t)NB + i]; }
+    else if (which == 1) { double2 s = qst[i]; rdata[k] = s.x; rdata[c + k] = s.y; }
+    else if (which == 2) { double4 h = hsq[i]; rdata[k] = h.x; rdata[c + k] = h.y; rdata[2 * c + k] = h.z; }
+    else { double2 h = hst[i]; rdata[k] = h.x; rdata[c + k] = h.y; }
+  }
+  __threadfence_system();   // my stores are visible system-wide before anything I (or my block) signal afterwards
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const int done = atomicAdd(counter, 1);
+    if (done == (int)gridDim.x - 1) {   // last block: every block's data is out
+      *counter = 0;
+      __threadfence_system();
+      asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(rflag), "r"(seq) : "memory");
+    }
+  }
+}
+__global__ void k_peer_pull(int which, int cnt, int dst0, const double *__restrict__ ldata, const int *lflag, int seq,
+                            double2 *__restrict__ qst, double4 *__restrict__ hsq, double2 *__restrict__ hst,
+                            double2 *__restrict__ xs, const int *__restrict__ slot_of, double *__restrict__ q,
+                            double *__restrict__ spos, int NB, int *__restrict__ err) {
+  if (threadIdx.x == 0) {
+    const long long t0 = clock64();
+    int v;
+    do {
+      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(lflag) : "memory");
+      if (v != seq && clock64() - t0 > PEER_SPIN_LIMIT) { atomicExch(err, 1); break; }
+    } while (v != seq);
+  }
+  __syncthreads();
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= cnt) return;
+  const size_t c = cnt;
+  const int m = dst0 + k;
+  // the window was written by another GPU: read it past L1 (which is not coherent with remote stores)
+  if (which == 4) { q[m] = __ldcg(ldata + k); return; }
+  if (which == 5) { spos[m] = __ldcg(ldata + k); spos[(size_t)NB + m] = __ldcg(ldata + c + k); spos[2 * (size_t)NB + m] = __ldcg(ldata + 2 * c + k); return; }
+  if (which == 1) qst[m] = make_double2(__ldcg(ldata + k), __ldcg(ldata + c + k));
+  else if (which == 2) { double qq = __ldcg(ldata + 2 * c + k); hsq[m] = make_double4(__ldcg(ldata + k), __ldcg(ldata + c + k), qq, 0.0); q[m] = qq; }
+  else { double2 v = make_double2(__ldcg(ldata + k), __ldcg(ldata + c + k)); hst[m] = v; xs[slot_of[m]] = v; }
+}
+
+inline int halo_refresh_peer_axis(Ctx *c, int which, int axis, int seq) {
+  const int nf = (which == 2 || which == 5) ? 3 : (which == 4 ? 1 : 2);
+  const int par = seq & 1;
+  int *err = c->d_flag + 3;   // read back with the CG scalars of the iteration (qeq_cg_single)
+  const int d0 = 2 * axis + 1;
+  const int ns[2] = {c->ns[d0], c->ns[d0 + 1]}, nr[2] = {c->nr[d0], c->nr[d0 + 1]};
+  const int tgt[2] = {c->box.target_node[2 * axis], c->box.target_node[2 * axis + 1]};
+  if ((size_t)nf * (size_t)std::max(std::max(ns[0], ns[1]), std::max(nr[0], nr[1])) > c->pw_cap) {
+    c->err = "peer halo window too small for this halo (raise nbuffer)";
+    return RXG_ERR_NBUFFER;
+  }
+  for (int k = 0; k < 2; k++) {   // my selection of stage d0+k lands in the target's buffer of the same stage
+    const int slot = (d0 - 1 + k) * 2 + par;
+    double *base = c->peer[tgt[k]];
+    LAUNCH(c, k_peer_push, cdiv(std::max(ns[k], 1), 256), 256, 0, which, c->sel + c->selptr[d0 - 1 + k], ns[k], c->qst, c->hsq, c->hst, c->q,
+           c->spos, c->NB, base + PW_HDR + (size_t)slot * c->pw_cap, (int *)base + slot, seq, c->d_pushcnt + k);
+  }
+  for (int k = 0; k < 2; k++) {
+    const int slot = (d0 - 1 + k) * 2 + par;
+    LAUNCH(c, k_peer_pull, cdiv(std::max(nr[k], 1), 256), 256, 0, which, nr[k], c->cp[d0 - 1 + k], c->pw + PW_HDR + (size_t)slot * c->pw_cap,
+           (const int *)c->pw + slot, seq, c->qst, c->hsq, c->hst, c->xs, c->gnb.slot_of, c->q, c->spos, c->NB, err);
+  }
+  return RXG_OK;
+}
+
 // MODE_CPBK: ghost forces of one stage travel back to the rank that owns the source atoms and are added there
 // (src/comm.F90:385-396, 474-482); the owner addresses them through its own selection list
 __global__ void k_pack_force(const double *__restrict__ f, int NB, int lo, int cnt, double *__restrict__ buf) {
@@ -514,8 +602,14 @@ inline int halo_refresh(Ctx *c, int which, int roundtrips) {
   if (c->halo_self && nghost > 0)
     LAUNCH(c, k_refresh_self, cdiv(nghost, 256), 256, 0, which, c->natoms, c->cp[6], c->gsrc, c->qst, c->hsq, c->hst, c->xs, c->gnb.slot_of,
            c->q, c->spos, c->NB);
+  const int seq = ++c->pseq;   // advances identically on every rank (same sequence of refresh calls)
   for (int axis = 0; axis < 3 && !c->halo_self; axis++) {
     const int d0 = 2 * axis + 1;
+    const bool self_axis = c->box.target_node[2 * axis] == c->box.myid && c->box.target_node[2 * axis + 1] == c->box.myid;
+    if (c->peer_ok && !self_axis) {   // neighbours' kernels store into my window over NVLink; self axes stay a local pack/unpack
+      RXG_TRY(halo_refresh_peer_axis(c, which, axis, seq));
+      continue;
+    }
     const int ns[2] = {c->ns[d0], c->ns[d0 + 1]}, nr[2] = {c->nr[d0], c->nr[d0 + 1]};
     if (ns[0] + ns[1] + nr[0] + nr[1] == 0) continue;
     RXG_TRY(ensure_xbuf(c, (size_t)nf * (size_t)std::max(std::max(ns[0], ns[1]), std::max(nr[0], nr[1]))));

@@ -48,6 +48,7 @@ def load_library():
     L.rxg_set_box.argtypes = [vp, C.POINTER(RxgBox)]
     L.rxg_comm_init.argtypes = [vp, C.c_int, C.c_int, vp]
     L.rxg_comm_unique_id.argtypes = [vp]
+    L.rxg_comm_peer_halo.argtypes = [vp]
     L.rxg_destroy.argtypes = [vp]
     L.rxg_last_error.argtypes = [vp]
     L.rxg_last_error.restype = C.c_char_p
@@ -141,6 +142,10 @@ class Engine:
         raw = broadcast_bytes(dist, bytes(buf))
         buf2 = (C.c_ubyte * 128).from_buffer_copy(raw)
         self._chk(self.L.rxg_comm_init(self.h, rank, nranks, C.cast(buf2, C.c_void_p)))
+
+    def peer_halo(self):
+        """True when the per-iteration ghost refreshes use peer-memory windows (NVLink stores) instead of NCCL send/recv."""
+        return bool(self.L.rxg_comm_peer_halo(self.h))
 
     def host_arrays(self, rank_state):
         """Allocate the host's NBUFFER-capacity arrays (src/init.F90:110-114) from a rank's resident atoms."""

@@ -46,7 +46,7 @@ def main():
     o = Oracle(s, cfg)       # all ranks, simulated
     atype, pos, v, f, q = e.host_arrays(s.ranks[rank])
     n = e.NATOMS
-    out = [f"rank {rank}/{world} vprocs {vp} natoms {n} of {s.natoms}"]
+    out = [f"rank {rank}/{world} vprocs {vp} natoms {n} of {s.natoms} peer_halo {e.peer_halo()}"]
     if pqeq:
         for r in range(world):
             nr = len(s.ranks[r]["atype"])
