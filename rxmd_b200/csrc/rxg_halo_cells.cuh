@@ -333,10 +333,22 @@ __global__ void k_refresh_self(int which, int natoms, int ntot, const int *__res
 constexpr int PW_HDR = 32;   // doubles (256 B) reserved for the 12 flags
 constexpr long long PEER_SPIN_LIMIT = 4000000000LL;   // ~2 s at 1.9 GHz, then the pull gives up and raises an error flag
 
-__global__ void k_peer_push(int which, const int *__restrict__ sel, int cnt, const double2 *__restrict__ qst,
+struct PeerDir {   // the two directions of one axis (blockIdx.y)
+  const int *sel[2];
+  int cnt[2], dst0[2], nblk[2];
+  double *data[2];   // push: the target's buffer; pull: my buffer
+  int *flag[2];
+};
+__global__ void k_peer_push(int which, PeerDir d, const double2 *__restrict__ qst,
                             const double4 *__restrict__ hsq, const double2 *__restrict__ hst, const double *__restrict__ q,
-                            const double *__restrict__ spos, int NB, double *__restrict__ rdata, int *rflag, int seq,
-                            int *__restrict__ counter) {
+                            const double *__restrict__ spos, int NB, int seq, int *__restrict__ counters) {
+  const int dir = blockIdx.y;
+  if ((int)blockIdx.x >= d.nblk[dir]) return;
+  const int *__restrict__ sel = d.sel[dir];
+  const int cnt = d.cnt[dir];
+  double *__restrict__ rdata = d.data[dir];
+  int *rflag = d.flag[dir];
+  int *counter = counters + dir;
   const int k = blockIdx.x * blockDim.x + threadIdx.x;
   if (k < cnt) {
     const int i = sel[k];
@@ -351,17 +363,22 @@ __global__ void k_peer_push(int which, const int *__restrict__ sel, int cnt, con
   __syncthreads();
   if (threadIdx.x == 0) {
     const int done = atomicAdd(counter, 1);
-    if (done == (int)gridDim.x - 1) {   // last block: every block's data is out
+    if (done == d.nblk[dir] - 1) {   // last block of this direction: every block's data is out
       *counter = 0;
       __threadfence_system();
       asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(rflag), "r"(seq) : "memory");
     }
   }
 }
-__global__ void k_peer_pull(int which, int cnt, int dst0, const double *__restrict__ ldata, const int *lflag, int seq,
+__global__ void k_peer_pull(int which, PeerDir d, int seq,
                             double2 *__restrict__ qst, double4 *__restrict__ hsq, double2 *__restrict__ hst,
                             double2 *__restrict__ xs, const int *__restrict__ slot_of, double *__restrict__ q,
                             double *__restrict__ spos, int NB, int *__restrict__ err) {
+  const int dir = blockIdx.y;
+  if ((int)blockIdx.x >= d.nblk[dir]) return;
+  const int cnt = d.cnt[dir], dst0 = d.dst0[dir];
+  const double *__restrict__ ldata = d.data[dir];
+  const int *lflag = d.flag[dir];
   if (threadIdx.x == 0) {
     const long long t0 = clock64();
     int v;
@@ -383,6 +400,21 @@ __global__ void k_peer_pull(int which, int cnt, int dst0, const double *__restri
   else { double2 v = make_double2(__ldcg(ldata + k), __ldcg(ldata + c + k)); hst[m] = v; xs[slot_of[m]] = v; }
 }
 
+// an axis whose neighbour is this rank itself (vprocs = 1 along it): ghost cp[stage]+j is the image of local atom sel[j]
+__global__ void k_refresh_axis_local(int which, PeerDir d, double2 *__restrict__ qst, double4 *__restrict__ hsq,
+                                     double2 *__restrict__ hst, double2 *__restrict__ xs, const int *__restrict__ slot_of,
+                                     double *__restrict__ q, double *__restrict__ spos, int NB) {
+  const int dir = blockIdx.y;
+  const int k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= d.cnt[dir]) return;
+  const int i = d.sel[dir][k], m = d.dst0[dir] + k;
+  if (which == 4) { q[m] = q[i]; return; }
+  if (which == 5) { spos[m] = spos[i]; spos[(size_t)NB + m] = spos[(size_t)NB + i]; spos[2 * (size_t)NB + m] = spos[2 * (size_t)NB + i]; return; }
+  if (which == 1) qst[m] = qst[i];
+  else if (which == 2) { double4 h = hsq[i]; hsq[m] = make_double4(h.x, h.y, h.z, 0.0); q[m] = h.z; }
+  else { double2 v = hst[i]; hst[m] = v; xs[slot_of[m]] = v; }
+}
+
 inline int halo_refresh_peer_axis(Ctx *c, int which, int axis, int seq) {
   const int nf = (which == 2 || which == 5) ? 3 : (which == 4 ? 1 : 2);
   const int par = seq & 1;
@@ -394,17 +426,18 @@ inline int halo_refresh_peer_axis(Ctx *c, int which, int axis, int seq) {
     c->err = "peer halo window too small for this halo (raise nbuffer)";
     return RXG_ERR_NBUFFER;
   }
+  PeerDir ps, pl;
   for (int k = 0; k < 2; k++) {   // my selection of stage d0+k lands in the target's buffer of the same stage
     const int slot = (d0 - 1 + k) * 2 + par;
     double *base = c->peer[tgt[k]];
-    LAUNCH(c, k_peer_push, cdiv(std::max(ns[k], 1), 256), 256, 0, which, c->sel + c->selptr[d0 - 1 + k], ns[k], c->qst, c->hsq, c->hst, c->q,
-           c->spos, c->NB, base + PW_HDR + (size_t)slot * c->pw_cap, (int *)base + slot, seq, c->d_pushcnt + k);
+    ps.sel[k] = c->sel + c->selptr[d0 - 1 + k]; ps.cnt[k] = ns[k]; ps.dst0[k] = 0; ps.nblk[k] = cdiv(std::max(ns[k], 1), 256);
+    ps.data[k] = base + PW_HDR + (size_t)slot * c->pw_cap; ps.flag[k] = (int *)base + slot;
+    pl.sel[k] = nullptr; pl.cnt[k] = nr[k]; pl.dst0[k] = c->cp[d0 - 1 + k]; pl.nblk[k] = cdiv(std::max(nr[k], 1), 256);
+    pl.data[k] = c->pw + PW_HDR + (size_t)slot * c->pw_cap; pl.flag[k] = (int *)c->pw + slot;
   }
-  for (int k = 0; k < 2; k++) {
-    const int slot = (d0 - 1 + k) * 2 + par;
-    LAUNCH(c, k_peer_pull, cdiv(std::max(nr[k], 1), 256), 256, 0, which, nr[k], c->cp[d0 - 1 + k], c->pw + PW_HDR + (size_t)slot * c->pw_cap,
-           (const int *)c->pw + slot, seq, c->qst, c->hsq, c->hst, c->xs, c->gnb.slot_of, c->q, c->spos, c->NB, err);
-  }
+  LAUNCH(c, k_peer_push, dim3(std::max(ps.nblk[0], ps.nblk[1]), 2), 256, 0, which, ps, c->qst, c->hsq, c->hst, c->q, c->spos, c->NB, seq, c->d_pushcnt);
+  LAUNCH(c, k_peer_pull, dim3(std::max(pl.nblk[0], pl.nblk[1]), 2), 256, 0, which, pl, seq, c->qst, c->hsq, c->hst, c->xs, c->gnb.slot_of, c->q,
+         c->spos, c->NB, err);
   return RXG_OK;
 }
 
@@ -606,7 +639,14 @@ inline int halo_refresh(Ctx *c, int which, int roundtrips) {
   for (int axis = 0; axis < 3 && !c->halo_self; axis++) {
     const int d0 = 2 * axis + 1;
     const bool self_axis = c->box.target_node[2 * axis] == c->box.myid && c->box.target_node[2 * axis + 1] == c->box.myid;
-    if (c->peer_ok && !self_axis) {   // neighbours' kernels store into my window over NVLink; self axes stay a local pack/unpack
+    if (self_axis) {   // stage `up` sends my upper selection to myself: it arrives as my stage-d0 ghosts (and likewise down)
+      PeerDir d;
+      for (int k = 0; k < 2; k++) { d.sel[k] = c->sel + c->selptr[d0 - 1 + k]; d.cnt[k] = c->ns[d0 + k]; d.dst0[k] = c->cp[d0 - 1 + k]; }
+      const int mx = std::max(d.cnt[0], d.cnt[1]);
+      if (mx > 0) LAUNCH(c, k_refresh_axis_local, dim3(cdiv(mx, 256), 2), 256, 0, which, d, c->qst, c->hsq, c->hst, c->xs, c->gnb.slot_of, c->q, c->spos, c->NB);
+      continue;
+    }
+    if (c->peer_ok) {   // neighbours' kernels store into my window over NVLink
       RXG_TRY(halo_refresh_peer_axis(c, which, axis, seq));
       continue;
     }
