@@ -320,6 +320,8 @@ def main():
                            "vprocs": list(vp), "atoms_per_gpu": nres, "parallelism": f"spatial decomposition {vp[0]}x{vp[1]}x{vp[2]}",
                            "ghost_refresh": ("peer-memory windows over NVLink (cudaIpc)" if (world > 1 and e.peer_halo()) else
                                              ("ncclSend/ncclRecv" if world > 1 else "periodic images, local gather")),
+                           "cg_allreduce": ("peer-memory windows, rank-ordered sum" if (world > 1 and e.peer_allreduce()) else
+                                            ("ncclAllReduce" if world > 1 else "none (1 rank)")),
                            "l2_policy": "inputs larger than L2 (QEq matrix ~5 GB per SpMV pass, >> 126 MB)",
                            "cg_iterations_per_step": cg_iters, "nnz": nnz, "pe_per_atom": pe[1:].sum() / max(e.natoms_resident(), 1)},
                 "phase_ms_per_step": {"QEq": d[4] / args.steps, "FORCE": d[5] / args.steps, "MOVE": d[6] / args.steps},

@@ -118,8 +118,9 @@ int rxg_set_box(rxg_handle h, const rxg_box *box);
  * the Fortran shim, TCPStore in the harness).  Not needed when nprocs == 1.
  * Replaces MPI_SEND/MPI_RECV/MPI_ALLREDUCE inside COPYATOMS/QEq (src/comm.F90:291-364, src/qeq.F90:107-144,357). */
 int rxg_comm_init(rxg_handle h, int rank, int nranks, const void *nccl_unique_id);
-/* 1 if the per-iteration ghost refreshes go through peer memory (cudaIpc windows written over NVLink by the neighbours'
- * kernels) rather than ncclSend/ncclRecv; decided collectively in rxg_comm_init (RXG_PEER_HALO=0 forces NCCL). */
+/* bit 0: the per-iteration ghost refreshes go through peer memory (cudaIpc windows written over NVLink by the neighbours'
+ * kernels) rather than ncclSend/ncclRecv; bit 1: the CG's scalar all-reduces go through the windows too (summed in rank
+ * order).  Decided collectively in rxg_comm_init; RXG_PEER_HALO=0 / RXG_PEER_ALLREDUCE=0 force NCCL. */
 int rxg_comm_peer_halo(rxg_handle h);
 /* rank 0 creates the 128-byte id and the host broadcasts it (MPI_Bcast / TCPStore) before rxg_comm_init */
 int rxg_comm_unique_id(void *out128);

@@ -85,6 +85,13 @@ struct Timer {
 // MPI_ALLREDUCE(SUM) of a few doubles (src/qeq.F90:107,129,144,357) as ncclAllReduce on the compute stream
 int allreduce_acc(Ctx *c, int first, int count) {
   if (!c->comm) return RXG_OK;
+  if (c->peer_all && count <= PW_ARW) {   // through the peer windows, summed in rank order (k_peer_allreduce)
+    PeerAll pa;
+    const int nr = (int)c->peer.size();
+    for (int r = 0; r < nr; r++) pa.win[r] = c->peer[r];
+    LAUNCH(c, k_peer_allreduce, 1, PW_MAXR, 0, pa, nr, c->box.myid, (size_t)PW_HDR + 12 * c->pw_cap, ++c->arseq, c->d_acc + first, count, c->d_flag + 3);
+    return RXG_OK;
+  }
   ncclResult_t r = nccl_api().AllReduce(c->d_acc + first, c->d_acc + first, count, ncclDouble, ncclSum, c->comm, c->st);
   if (r != ncclSuccess) { c->err = std::string("NCCL error: ") + nccl_api().GetErrorString(r); return RXG_ERR_NCCL; }
   c->nccl_msgs++;
@@ -545,7 +552,7 @@ int rxg_comm_init(rxg_handle h, int rank, int nranks, const void *id) {
   int want = !(ph && ph[0] == '0');
   c->peer.assign(nranks, nullptr);
   c->pw_cap = (size_t)3 * (size_t)c->NB / 2;
-  const size_t wbytes = sizeof(double) * (PW_HDR + 12 * c->pw_cap);
+  const size_t wbytes = sizeof(double) * (PW_HDR + 12 * c->pw_cap + PW_AR_DOUBLES);
   int *d_ok = c->d_flag + 2;
   cudaIpcMemHandle_t *d_h = nullptr, *d_all = nullptr;
   std::vector<cudaIpcMemHandle_t> all(nranks);
@@ -559,6 +566,7 @@ int rxg_comm_init(rxg_handle h, int rank, int nranks, const void *id) {
   memset(&mine, 0, sizeof(mine));
   if (ok) {
     RXG_CUDA(cudaMemset(c->pw, 0, sizeof(double) * PW_HDR));
+    RXG_CUDA(cudaMemset(c->pw + PW_HDR + 12 * c->pw_cap, 0, sizeof(double) * PW_AR_DOUBLES));
     if (cudaIpcGetMemHandle(&mine, c->pw) != cudaSuccess) { cudaGetLastError(); ok = 0; }
   }
   RXG_CUDA(cudaMemcpy(d_h, &mine, sizeof(mine), cudaMemcpyHostToDevice));
@@ -578,19 +586,30 @@ int rxg_comm_init(rxg_handle h, int rank, int nranks, const void *id) {
       c->peer[nb] = (double *)p;
     }
   }
+  // the all-reduce through the windows needs every rank's window, not only the neighbours'
+  const char *pa_env = getenv("RXG_PEER_ALLREDUCE");
+  int all_ok = ok && nranks <= PW_MAXR && !(pa_env && pa_env[0] == '0');
+  for (int q = 0; q < nranks && all_ok; q++) {
+    if (c->peer[q]) continue;
+    void *p = nullptr;
+    if (cudaIpcOpenMemHandle(&p, all[q], cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); all_ok = 0; break; }
+    c->peer[q] = (double *)p;
+  }
   // every rank must take the same path: all-reduce(min) of the local outcome
-  RXG_CUDA(cudaMemcpy(d_ok, &ok, sizeof(int), cudaMemcpyHostToDevice));
-  r = nccl_api().AllReduce(d_ok, d_ok, 1, ncclInt, ncclMin, c->comm, c->st);
+  int oks[2] = {ok, all_ok};
+  RXG_CUDA(cudaMemcpy(d_ok, oks, 2 * sizeof(int), cudaMemcpyHostToDevice));
+  r = nccl_api().AllReduce(d_ok, d_ok, 2, ncclInt, ncclMin, c->comm, c->st);
   if (r != ncclSuccess) { c->err = std::string("ncclAllReduce: ") + nccl_api().GetErrorString(r); return RXG_ERR_NCCL; }
   RXG_CUDA(cudaStreamSynchronize(c->st));
-  RXG_CUDA(cudaMemcpy(&ok, d_ok, sizeof(int), cudaMemcpyDeviceToHost));
+  RXG_CUDA(cudaMemcpy(oks, d_ok, 2 * sizeof(int), cudaMemcpyDeviceToHost));
   RXG_CUDA(cudaMemset(d_ok, 0, 2 * sizeof(int)));
-  c->peer_ok = ok != 0;
+  c->peer_ok = oks[0] != 0;
+  c->peer_all = oks[0] != 0 && oks[1] != 0;
   cudaFree(d_h); cudaFree(d_all);
   return RXG_OK;
 }
 
-int rxg_comm_peer_halo(rxg_handle h) { return h && ((Ctx *)h)->peer_ok ? 1 : 0; }
+int rxg_comm_peer_halo(rxg_handle h) { return h ? (((Ctx *)h)->peer_ok ? 1 : 0) + (((Ctx *)h)->peer_all ? 2 : 0) : 0; }
 
 int rxg_destroy(rxg_handle h) {
   Ctx *c = (Ctx *)h;

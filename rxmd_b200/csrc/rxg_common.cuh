@@ -153,6 +153,8 @@ struct Ctx {
   std::vector<double *> peer;        // [nranks] window of each neighbour rank (my own for myself), nullptr otherwise
   bool peer_ok = false;
   int pseq = 0;                      // refresh sequence number, identical on every rank
+  int arseq = 0;                     // all-reduce sequence number
+  bool peer_all = false;             // every rank's window is open here: CG scalars are reduced through the windows
   int *d_pushcnt = nullptr;          // [2] block-completion counters of the push kernels
   bool fuse = true, fuse_api = false, lists_shared = false;   // md_run: QEq builds halo + 10 A list once for QEq and FORCE of the same step
   int qeq_mode = 0;         // 0 single-pass CG (default), 1 two-pass (literal kernels), strict => literal serial order

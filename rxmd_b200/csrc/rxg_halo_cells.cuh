@@ -331,6 +331,9 @@ __global__ void k_refresh_self(int which, int natoms, int ntot, const int *__res
 // s+1 from the same neighbour, which that neighbour pushed after its own pulls of number s (same stream) -- so the buffer
 // being overwritten has been consumed.
 constexpr int PW_HDR = 32;   // doubles (256 B) reserved for the 12 flags
+// all-reduce area that follows the 12 halo buffers: [2 parities][PW_MAXR ranks][PW_ARW doubles] then [2][PW_MAXR] int flags
+constexpr int PW_MAXR = 64, PW_ARW = 8;
+constexpr size_t PW_AR_DOUBLES = 2 * PW_MAXR * PW_ARW + PW_MAXR;   // values + flags (2*PW_MAXR ints)
 constexpr long long PEER_SPIN_LIMIT = 4000000000LL;   // ~2 s at 1.9 GHz, then the pull gives up and raises an error flag
 
 struct PeerDir {   // the two directions of one axis (blockIdx.y)
@@ -439,6 +442,38 @@ inline int halo_refresh_peer_axis(Ctx *c, int which, int axis, int seq) {
   LAUNCH(c, k_peer_pull, dim3(std::max(pl.nblk[0], pl.nblk[1]), 2), 256, 0, which, pl, seq, c->qst, c->hsq, c->hst, c->xs, c->gnb.slot_of, c->q,
          c->spos, c->NB, err);
   return RXG_OK;
+}
+
+// MPI_ALLREDUCE(SUM) of a few doubles through the windows: every rank stores its `count` values into slot [me] of every
+// rank's all-reduce area, publishes the sequence number, waits for the other ranks' numbers in its own area and adds the
+// contributions in RANK ORDER -- every rank gets the bit-identical sum (ncclAllReduce does not promise an order).
+// One block of PW_MAXR threads; thread r talks to rank r.
+struct PeerAll { double *win[PW_MAXR]; };
+__global__ void __launch_bounds__(PW_MAXR) k_peer_allreduce(PeerAll pa, int nranks, int me, size_t aroff, int seq, double *__restrict__ acc,
+                                                           int count, int *__restrict__ err) {
+  const int r = threadIdx.x, par = seq & 1;
+  if (r < nranks) {
+    double *dst = pa.win[r] + aroff + ((size_t)par * PW_MAXR + me) * PW_ARW;
+    for (int k = 0; k < count; k++) dst[k] = acc[k];
+    __threadfence_system();
+    int *flag = (int *)(pa.win[r] + aroff + 2 * PW_MAXR * PW_ARW) + par * PW_MAXR + me;
+    asm volatile("st.release.sys.global.s32 [%0], %1;" ::"l"(flag), "r"(seq) : "memory");
+    const int *mine = (const int *)(pa.win[me] + aroff + 2 * PW_MAXR * PW_ARW) + par * PW_MAXR + r;
+    const long long t0 = clock64();
+    int v;
+    do {
+      asm volatile("ld.acquire.sys.global.s32 %0, [%1];" : "=r"(v) : "l"(mine) : "memory");
+      if (v != seq && clock64() - t0 > PEER_SPIN_LIMIT) { atomicExch(err, 1); break; }
+    } while (v != seq);
+    __threadfence();
+  }
+  __syncthreads();
+  if (r < count) {
+    const double *src = pa.win[me] + aroff + (size_t)par * PW_MAXR * PW_ARW;
+    double sum = 0.0;
+    for (int q = 0; q < nranks; q++) sum = add_rn(sum, __ldcg(src + (size_t)q * PW_ARW + r));
+    acc[r] = sum;
+  }
 }
 
 // MODE_CPBK: ghost forces of one stage travel back to the rank that owns the source atoms and are added there

@@ -145,7 +145,10 @@ class Engine:
 
     def peer_halo(self):
         """True when the per-iteration ghost refreshes use peer-memory windows (NVLink stores) instead of NCCL send/recv."""
-        return bool(self.L.rxg_comm_peer_halo(self.h))
+        return bool(self.L.rxg_comm_peer_halo(self.h) & 1)
+
+    def peer_allreduce(self):
+        return bool(self.L.rxg_comm_peer_halo(self.h) & 2)
 
     def host_arrays(self, rank_state):
         """Allocate the host's NBUFFER-capacity arrays (src/init.F90:110-114) from a rank's resident atoms."""
