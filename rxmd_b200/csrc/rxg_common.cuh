@@ -183,6 +183,7 @@ struct Ctx {
   bool use_col16 = false, have_col16 = false;   // RXG_COL16=1 (see k_col16)
   long long nnz_cap = 0, nnz = 0, nnz_real = 0;   // nnz counts the row padding, nnz_real does not
   bool list_is_qeq = false;
+  int maxrow = 0;                // longest row of the current list (entries)
   // ---- bond-order products, [bond_cap] (compact bond slots) unless noted -----------------------------------------------------------
   double *BO[4] = {nullptr, nullptr, nullptr, nullptr}, *dln[3] = {nullptr, nullptr, nullptr}, *dBOp = nullptr;
   double *A0 = nullptr, *A1 = nullptr, *A2 = nullptr, *A3 = nullptr;

@@ -324,6 +324,7 @@ int build_pairlist(Ctx *c, bool hessian = true) {
     RXG_CUDA(cudaMalloc(&c->cbase, sizeof(int) * (c->nnz_cap / 16 + 2)));
   }
   c->nnz = nnz;
+  c->maxrow = c->h_int[0];
   c->nnz_real = *(long long *)(c->h_acc + 33);
   c->list_is_qeq = MODE >= 1;
   LAUNCH(c, (k_pairlist<MODE, true>), grid, PL_WARPS * 32, 0, c->gnb, c->d_ff, c->d_runs, c->nruns, n, ncell_res, c->rowcnt,
@@ -683,13 +684,13 @@ __global__ void __launch_bounds__(SP_ROWS * 32) k_spmv1_tma(const int *__restric
 //   k_spmv_rows : TMA-staged matrix stream, LPR lanes per row, writes the four raw row sums {a, b, ghost a, ghost b}
 //                 of H.(x1,x2) per cell-order slot;
 //   k_cg_dots   : one thread per slot, coalesced; turns row sums into gradient / H.h products, Est and the dots.
-template <int ROWS, int LPR>
+template <int ROWS, int LPR, int CAPROW = 480>
 __global__ void __launch_bounds__(ROWS * LPR) k_spmv_rows(const int *__restrict__ order, int ntot, int natoms,
                                                           const long long *__restrict__ rowoff, const long long *__restrict__ rowbeg,
                                                           const long long *__restrict__ rowend, const int *__restrict__ col,
                                                           const double *__restrict__ val, const double2 *__restrict__ x,
                                                           double4 *__restrict__ rowsum) {
-  constexpr int CAP = ROWS * 480;
+  constexpr int CAP = ROWS * CAPROW;   // CAPROW = longest row the staged path takes (480: 10 A lists; 1216: the 12.5 A lists of PQEq)
   __shared__ __align__(128) double s_val[CAP];
   __shared__ __align__(128) int s_col[CAP];
   __shared__ __align__(8) unsigned long long bar;
