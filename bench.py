@@ -265,6 +265,9 @@ def main():
         dthm_of_type = dt * 0.5 / np.maximum(mass, 1e-300)
         # the host integrator (the Fortran driver's O(N) loops, src/main.F90:64-72,86-98) as compiled loops
         import numba
+        # one rank per GPU shares the host's cores: give each rank's integrator its share instead of a full-size thread pool
+        ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        numba.set_num_threads(max(1, min(numba.config.NUMBA_NUM_THREADS, ncores // max(world, 1))))
 
         @numba.njit(parallel=True, cache=False)
         def first_half(n, dt, lw2, dthm_t, atype, v, f, q, qsfp, qsfv, pos):
@@ -305,7 +308,8 @@ def main():
         t_e2e = allmax(time.perf_counter() - t0)
         e2e = {"value": natoms_total * ksteps / t_e2e, "unit": "atom-timesteps/s", "h2d_bytes_per_step": int(h2d / ksteps),
                "d2h_bytes_per_step": int(d2h / ksteps), "steps": ksteps, "ms_per_step": t_e2e / ksteps * 1e3,
-               "api": "Engine.COPYATOMS(MODE_MOVE) + Engine.QEq + Engine.FORCE over rxg_move/rxg_qeq/rxg_force, pinned host arrays, host integrator"}
+               "api": "Engine.COPYATOMS(MODE_MOVE) + Engine.QEq + Engine.FORCE over rxg_move/rxg_qeq/rxg_force, pinned host arrays, host integrator",
+               "host_threads_per_rank": int(numba.get_num_threads())}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
