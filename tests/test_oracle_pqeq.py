@@ -1,0 +1,170 @@
+"""Validation of the oracle's PQEq restatement (src/pqeq.F90, ENbond_PQEq, EEfield) on the CPU.
+
+The reference ships no PQEq numbers at all (README's sample run is plain QEq), so this part of the oracle is "parity
+unpinned" by reference data; what can be checked are the physics relations the reference's own formulas must satisfy:
+
+  * charge neutrality and Newton's third law;
+  * forces of ENbond_PQEq = -dE/dr of its own energies (PE(11..13)) at fixed charges and shells, to the accuracy of the
+    r^2-space table lerp (the force table holds the analytic derivative at the nodes, src/module.F90:556-607);
+  * the shell relaxation step of update_shell_positions points down the gradient of the same energy in the shell
+    coordinates (Eq. 37-39) -- this ties src/pqeq.F90:187-259 to src/pot.F90:784-923;
+  * one rank vs two ranks (the reference's examples 1 vs 2 idea) give the same energies: spos travels with MODE_COPY;
+  * the PQEq tables against direct evaluation of erf(alpha r)/r * Tap(r).
+"""
+import math
+import os
+
+import numpy as np
+import pytest
+
+from rxmd_b200.host import setup as S
+from rxmd_b200.host.system import build_system
+
+INP = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "inputs", "init.pe.pqeq")
+XYZ, FF, PAR = (os.path.join(INP, f) for f in ("input.xyz", "ffield", "pqeq1.par"))
+
+
+@pytest.fixture(scope="module")
+def pe(built):
+    from oracle.pyoracle import Oracle
+    s = build_system(XYZ, FF, mc=(2, 3, 5), displace_sigma=0.03, pqeq_path=PAR)
+    o = Oracle(s, s.config())
+    n = s.natoms
+    sp = np.random.default_rng(7).normal(0.0, 4e-3, (3, n))
+    o.set_spos(0, sp)
+    o.qeq()
+    yield s, o, n, sp
+    o.close()
+
+
+def test_pqeq_parameters_and_tables():
+    p = S.read_pqeq_parms(PAR)
+    assert p.ntype == 2 and p.elem[1:] == ["C", "H"] and p.polarizable[1:].all()        # src/cmdline.F90:212: always polarizable
+    chi, eta = np.array([0.0, 1.0, 2.0]), np.array([0.0, 3.0, 4.0])
+    rctap = S.RCTAP0_PQEQ
+    CTap = S.taper(rctap)
+    chi2, eta2 = S.initialize_pqeq(p, chi, eta, rctap, CTap)
+    assert np.allclose(chi2[1:], p.X0[1:]) and np.allclose(eta2[1:], 2.0 * p.J0[1:])       # :517-523 (eta doubled once more)
+    assert p.inxnpqeq[1, 2] == p.inxnpqeq[2, 1] == 2 and p.inxnpqeq[2, 2] == 3
+    # table node i holds C(r) = erf(alpha r)/r * Tap(r) at r^2 = i*UDR and its derivative in the (dE/dr)/r convention
+    UDR = rctap ** 2 / S.NTABLE
+    for i in (50, 800, 3000, 4900):
+        r = math.sqrt(UDR * i)
+        tap = sum(CTap[k] * r ** k for k in (0, 4, 5, 6, 7))
+        a = p.alphacc[1, 2]
+        assert abs(p.T_pcc[2, i, 0] - math.erf(a * r) / r * tap) < 1e-13
+        num = (p.T_pcc[2, i + 1, 0] - p.T_pcc[2, i - 1, 0]) / (2 * UDR) * 2                  # d/d(r^2) * 2 = (dE/dr)/r
+        assert abs(num - p.T_pcc[2, i, 1]) < 2e-4 * abs(p.T_pcc[2, i, 1]) + 1e-9
+    assert abs(p.T_pcc[1, S.NTABLE, 0]) < 1e-12                                              # tapered to zero at rctap
+
+
+def test_pqeq_neutrality_and_newton(pe):
+    s, o, n, sp = pe
+    q = o.f64("q")[:n]
+    assert abs(q.sum()) < 1e-10
+    assert o.i32("nstep_qeq")[0] > 3
+    o.force()
+    f = o.f64("f").reshape(3, -1)[:, :n]
+    assert np.abs(f.sum(axis=1)).max() < 1e-9 * np.abs(f).max() * n
+    # C and H carry opposite mean charges in polyethylene
+    ity = np.rint(o.f64("atype")[:n]).astype(int)
+    assert q[ity == 1].mean() < 0 < q[ity == 2].mean()
+
+
+def test_enbond_pqeq_forces_are_the_gradient_of_its_energy(built, monkeypatch):
+    """Coulomb part (core-core, core-shell, shell-core, shell-shell) + charge and shell self-energies against central
+    differences of their own energy at fixed charges and shells.
+
+    Arranged so that the check sees formula errors rather than table noise: (i) the vdW table is zeroed; (ii) the shells are
+    displaced by ~0.15 A instead of the physical ~1e-3 A (with physical shells the four Coulomb terms of a pair, each of
+    order 332/r kcal/mol, cancel to ~1e-2 kcal/mol/A); (iii) the r^2 tables are built 10x finer than the reference's
+    NTABLE = 5000.  The reference interpolates energy and force tables separately, so its forces are not the gradient of
+    its energies at table resolution: the rms mismatch of this very check is 0.38 kcal/mol/A at
+    NTABLE = 5000, 0.016 at 50 000 and 2e-4 at 500 000 -- it vanishes with the table spacing, i.e. the formulas agree."""
+    from oracle.pyoracle import Oracle
+    monkeypatch.setattr(S, "NTABLE", 50000)
+    s0 = build_system(XYZ, FF, mc=(2, 3, 5), displace_sigma=0.03, pqeq_path=PAR)
+    s0.pff.keep["TBL_Evdw"][:] = 0.0
+    o0 = Oracle(s0, s0.config())
+    n = s0.natoms
+    at = s0.ranks[0]["atype"]
+    pos0 = s0.ranks[0]["pos"].copy()
+    q = np.random.default_rng(3).normal(0.0, 0.03, n)
+    q -= q.mean()
+    big = np.random.default_rng(9).normal(0.0, 0.15, (3, n))
+    o0.set_terms(1)                                 # ENbond_PQEq only: PE(12) Coulomb (4 terms), PE(13) charge + shell
+    o0.set_atoms(0, at, pos0, None, q); o0.set_spos(0, big); o0.force()
+    f = o0.f64("f").reshape(3, -1)[:, :n].copy()
+    assert abs(o0.observe()[0][11]) == 0.0
+    scale = np.abs(f).max()
+    assert scale > 10.0                             # the terms no longer cancel
+    h = 2e-4
+    for c, i in [(0, 0), (1, 7), (2, 100), (0, 201), (1, 333), (2, 50)]:
+        e = []
+        for sgn in (+1, -1):
+            p = pos0.copy(); p[c, i] += sgn * h
+            o0.set_atoms(0, at, p, None, q); o0.set_spos(0, big); o0.force()
+            e.append(o0.observe()[0][0])
+        fd = -(e[0] - e[1]) / (2 * h)
+        assert abs(fd - f[c, i]) < 4e-3 * scale, (c, i, fd, f[c, i])
+    o0.close()
+
+
+def test_shell_relaxation_descends_the_same_energy(built, monkeypatch):
+    """update_shell_positions moves shell i by sforce_i / Ks_i (capped at 1e-3 A); sforce must be -dE/dspos_i of the energy
+    ENbond_PQEq reports, at fixed charges.  Tables 10x finer than the reference's for the reason given above (at
+    NTABLE = 5000 the directions agree to cos = 0.99)."""
+    from oracle.pyoracle import Oracle
+    monkeypatch.setattr(S, "NTABLE", 50000)
+    s = build_system(XYZ, FF, mc=(2, 3, 5), displace_sigma=0.03, pqeq_path=PAR)
+    n = s.natoms
+    sp = np.random.default_rng(7).normal(0.0, 4e-3, (3, n))
+    q = np.random.default_rng(3).normal(0.0, 0.03, n)
+    q -= q.mean()
+    o2 = Oracle(s, s.config(NMAXQEq=0))             # no CG iterations: charges stay as given, only the relaxation acts
+    at, pos0 = s.ranks[0]["atype"], s.ranks[0]["pos"]
+    o2.set_atoms(0, at, pos0, None, q); o2.set_spos(0, sp); o2.qeq()
+    step = o2.f64("spos").reshape(3, -1)[:, :n] - sp
+    assert np.allclose(o2.f64("q")[:n], q)
+    lens = np.sqrt((step ** 2).sum(axis=0))
+    assert lens.max() <= 1e-3 * (1 + 1e-12) and lens.min() > 0
+    o2.set_terms(1)
+    h = 1e-4
+    for i in (3, 50, 177, 290):
+        g = np.zeros(3)
+        for c in range(3):
+            e = []
+            for sgn in (+1, -1):
+                s2 = sp.copy(); s2[c, i] += sgn * h
+                o2.set_atoms(0, at, pos0, None, q); o2.set_spos(0, s2); o2.force()
+                e.append(o2.observe()[0][0])
+            g[c] = (e[0] - e[1]) / (2 * h)
+        cosang = -(g @ step[:, i]) / (np.linalg.norm(g) * np.linalg.norm(step[:, i]))
+        assert cosang > 0.9995, (i, cosang)
+        ks = s.pqeq.Ks[int(round(at[i]))]
+        if lens[i] < 0.999e-3:                       # not capped: the step is exactly -grad/Ks
+            assert np.allclose(step[:, i], -g / ks, rtol=2e-2, atol=1e-7)
+    o2.close()
+
+
+def test_pqeq_decomposition_invariance(built):
+    from oracle.pyoracle import Oracle
+    kw = dict(mc=(4, 3, 5), displace_sigma=0.03, pqeq_path=PAR)
+    s1 = build_system(XYZ, FF, vprocs=(1, 1, 1), **kw)
+    s2 = build_system(XYZ, FF, vprocs=(2, 1, 1), **kw)
+    o1, o2 = Oracle(s1, s1.config()), Oracle(s2, s2.config())
+    rng = np.random.default_rng(1)
+    gid1 = np.rint((s1.ranks[0]["atype"] - np.rint(s1.ranks[0]["atype"])) * 1e13).astype(int)
+    sp_by_gid = {g: rng.normal(0.0, 4e-3, 3) for g in gid1}
+    o1.set_spos(0, np.array([sp_by_gid[g] for g in gid1]).T)
+    for r in range(2):
+        at = s2.ranks[r]["atype"]
+        gid = np.rint((at - np.rint(at)) * 1e13).astype(int)
+        o2.set_spos(r, np.array([sp_by_gid[g] for g in gid]).T)
+    o1.qeq(); o1.force()
+    o2.qeq(); o2.force()
+    pe1, pe2 = o1.observe()[0], o2.observe()[0]
+    assert np.allclose(pe1[1:11], pe2[1:11], rtol=1e-10, atol=1e-9)          # bonded terms do not depend on q or shells
+    assert abs(pe1[0] - pe2[0]) / abs(pe1[0]) < 1e-6
+    assert abs(o1.observe()[2]) < 1e-9 and abs(o2.observe()[2]) < 1e-9
+    o1.close(); o2.close()
