@@ -179,39 +179,18 @@ int qeq_cg_single(Ctx *c, int nmax, int *iters) {
   LAUNCH(c, k_to_slots, cdiv(c->cp[6], 256), 256, 0, c->cp[6], c->gnb.order, c->qst, c->xs);
   const int tgrid = cdiv(c->cp[6], SP_ROWS);
   const bool tma = !(getenv("RXG_SPMV_NOTMA") && getenv("RXG_SPMV_NOTMA")[0] == '1');
-  const int lpr = getenv("RXG_SPMV_LPR") ? atoi(getenv("RXG_SPMV_LPR")) : 16;   // measured: 16 lanes/row 1.04 ms, 32: 1.09, 8: 1.29
   double4 *rowsum = (double4 *)c->tmp;
-  const int rows16 = getenv("RXG_SPMV_ROWS") ? atoi(getenv("RXG_SPMV_ROWS")) : 4;
-  static int carve_set = -2;
-  const int carve = getenv("RXG_SPMV_CARVEOUT") ? atoi(getenv("RXG_SPMV_CARVEOUT")) : -1;   // % of the SM's L1/shared array given to shared memory
-  if (carve != carve_set) {
-    carve_set = carve;
-    if (carve >= 0) {
-      cudaFuncSetAttribute(k_spmv_rows16<4, 16>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-      cudaFuncSetAttribute(k_spmv_rows16<8, 16>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-      cudaFuncSetAttribute(k_spmv_rows16<2, 16>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-      cudaFuncSetAttribute(k_spmv_rows16<4, 32>, cudaFuncAttributePreferredSharedMemoryCarveout, carve);
-    }
-  }
   auto spmv_rows = [&]() {
     const int nt = c->cp[6];
-    if (c->have_col16) {
-      if (rows16 == 8) LAUNCH(c, (k_spmv_rows16<8, 16>), cdiv(nt, 8), 128, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col16, c->cbase, c->col, c->val, c->xs, rowsum);
-      else if (rows16 == 2) LAUNCH(c, (k_spmv_rows16<2, 16>), cdiv(nt, 2), 32, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col16, c->cbase, c->col, c->val, c->xs, rowsum);
-      else if (rows16 == 40) LAUNCH(c, (k_spmv_rows16<4, 16, false>), cdiv(nt, 4), 64, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col16, c->cbase, c->col, c->val, c->xs, rowsum);
-      else if (rows16 == 80) LAUNCH(c, (k_spmv_rows16<8, 16, false>), cdiv(nt, 8), 128, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col16, c->cbase, c->col, c->val, c->xs, rowsum);
-      else if (rows16 == 432) LAUNCH(c, (k_spmv_rows16<4, 32>), cdiv(nt, 4), 128, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col16, c->cbase, c->col, c->val, c->xs, rowsum);
-      else LAUNCH(c, (k_spmv_rows16<4, 16>), cdiv(nt, 4), 64, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col16, c->cbase, c->col, c->val, c->xs, rowsum);
+    if (c->have_col16) {   // RXG_COL16=1
+      LAUNCH(c, (k_spmv_rows16<4, 16>), cdiv(nt, 4), 64, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col16, c->cbase, c->col, c->val, c->xs, rowsum);
     } else if (c->maxrow + 16 <= 256 && !getenv("RXG_SPMV_NOSHORT"))   // short rows (sparse systems such as the SiC nanoparticles): 8 rows per CTA, 8 lanes per row
       // measured at 3.94 M SiC atoms (117 entries per row): 1.78 ms vs 2.56 ms with the 4x16 shape; 16x8, 8x4, 16x4, 4x8 are slower
       LAUNCH(c, (k_spmv_rows<8, 8, 256>), cdiv(nt, 8), 64, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->xs, rowsum);
     else if (c->maxrow + 16 > 480 && c->maxrow + 16 <= 1216)   // 12.5 A lists (PQEq): two long rows per CTA, a full warp per row
       LAUNCH(c, (k_spmv_rows<2, 32, 1216>), cdiv(nt, 2), 64, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->xs, rowsum);
-    else if (lpr == 16) LAUNCH(c, (k_spmv_rows<4, 16>), cdiv(nt, 4), 64, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->xs, rowsum);
-    else if (lpr == 816) LAUNCH(c, (k_spmv_rows<8, 16>), cdiv(nt, 8), 128, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->xs, rowsum);
-    else if (lpr == 216) LAUNCH(c, (k_spmv_rows<2, 16>), cdiv(nt, 2), 32, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->xs, rowsum);
-    else if (lpr == 8) LAUNCH(c, (k_spmv_rows<8, 8>), cdiv(nt, 8), 64, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->xs, rowsum);
-    else LAUNCH(c, (k_spmv_rows<4, 32>), cdiv(nt, 4), 128, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->xs, rowsum);
+    else   // 10 A lists: 4 rows per CTA, 16 lanes per row (measured: 1.03 ms; 32 lanes 1.09, 8 lanes 1.29, 8 or 2 rows slower)
+      LAUNCH(c, (k_spmv_rows<4, 16>), cdiv(nt, 4), 64, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->xs, rowsum);
   };
   const int dgrid = cdiv(c->cp[6], 256);
   (void)tgrid;
