@@ -180,14 +180,16 @@ int qeq_cg_single(Ctx *c, int nmax, int *iters) {
   const int tgrid = cdiv(c->cp[6], SP_ROWS);
   const bool tma = !(getenv("RXG_SPMV_NOTMA") && getenv("RXG_SPMV_NOTMA")[0] == '1');
   double4 *rowsum = (double4 *)c->tmp;
+  const double avgrow = (double)c->nnz_real / (double)std::max(n, 1);   // picks the launch shape of the SpMV
   auto spmv_rows = [&]() {
     const int nt = c->cp[6];
     if (c->have_col16) {   // RXG_COL16=1
       LAUNCH(c, (k_spmv_rows16<4, 16>), cdiv(nt, 4), 64, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col16, c->cbase, c->col, c->val, c->xs, rowsum);
-    } else if (c->maxrow + 16 <= 256 && !getenv("RXG_SPMV_NOSHORT"))   // short rows (sparse systems such as the SiC nanoparticles): 8 rows per CTA, 8 lanes per row
-      // measured at 3.94 M SiC atoms (117 entries per row): 1.78 ms vs 2.56 ms with the 4x16 shape; 16x8, 8x4, 16x4, 4x8 are slower
+    } else if (avgrow <= 160.0)   // short rows (sparse systems such as the SiC nanoparticles, 117 entries): 8 rows per CTA, 8 lanes per row.
+      // Measured at 3.94 M SiC atoms: 1.78 ms vs 2.56 ms with the 4x16 shape; 16x8, 8x4, 16x4, 4x8 are slower.  A CTA whose
+      // 8 rows do not fit the 2048 staged entries reads them straight from HBM (same result).
       LAUNCH(c, (k_spmv_rows<8, 8, 256>), cdiv(nt, 8), 64, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->xs, rowsum);
-    else if (c->maxrow + 16 > 480 && c->maxrow + 16 <= 1216)   // 12.5 A lists (PQEq): two long rows per CTA, a full warp per row
+    else if (avgrow > 440.0)   // 12.5 A lists (PQEq, 1060 entries): two long rows per CTA, a full warp per row (5.8 -> 4.7 ms at 1.43 M atoms)
       LAUNCH(c, (k_spmv_rows<2, 32, 1216>), cdiv(nt, 2), 64, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->xs, rowsum);
     else   // 10 A lists: 4 rows per CTA, 16 lanes per row (measured: 1.03 ms; 32 lanes 1.09, 8 lanes 1.29, 8 or 2 rows slower)
       LAUNCH(c, (k_spmv_rows<4, 16>), cdiv(nt, 4), 64, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->xs, rowsum);
@@ -403,9 +405,9 @@ int rxg_create(const rxg_config *cfg, rxg_handle *out) {
   RXG_TRY(dalloc(c, &c->nlp, NB)); RXG_TRY(dalloc(c, &c->dDlp, NB)); RXG_TRY(dalloc(c, &c->deltalp, NB));
   RXG_TRY(dalloc(c, &c->ccbnd, NB)); RXG_TRY(dalloc(c, &c->cdbnd, NB));
   RXG_TRY(dalloc(c, &c->s3, 3 * NB)); RXG_TRY(dalloc(c, &c->sbo, NB));
-  RXG_TRY(dalloc(c, &c->d_acc, 64)); RXG_TRY(dalloc(c, &c->d_flag, 16));
+  RXG_TRY(dalloc(c, &c->d_acc, 64)); RXG_TRY(dalloc(c, &c->d_flag, 32));
   RXG_CUDA(cudaMallocHost((void **)&c->h_acc, sizeof(double) * 64));
-  RXG_CUDA(cudaMallocHost((void **)&c->h_int, sizeof(int) * 16));
+  RXG_CUDA(cudaMallocHost((void **)&c->h_int, sizeof(int) * 32));
   RXG_TRY(ensure_blk(c, NB));
   RXG_CUDA(cudaStreamSynchronize(c->st));
   return RXG_OK;

@@ -189,9 +189,11 @@ __global__ void __launch_bounds__(PL_WARPS * 32) k_pairlist(DevGrid g, const Dev
       }
       __syncwarp();
     }
-    if (!FILL) {   // exact entry count (without row padding): the algorithmic-bytes figure of the roofline uses it
+    if (!FILL) {   // exact entry count (without row padding): the algorithmic-bytes figure of the roofline uses it;
+                   // longest row: picks the SpMV launch shape
       const int real = __reduce_add_sync(0xffffffffu, (lane < nb && mine) ? mycnt : 0);
-      if (lane == 0 && real) atomicAdd(nnz_real, (unsigned long long)real);
+      const int longest = __reduce_max_sync(0xffffffffu, (lane < nb && mine) ? mycnt : 0);
+      if (lane == 0 && real) { atomicAdd(nnz_real, (unsigned long long)real); atomicMax(ovf + 16, longest); }
     }
     if (lane < nb && mine) {
       if (!FILL) {
@@ -292,6 +294,7 @@ template <int MODE>
 int build_pairlist(Ctx *c, bool hessian = true) {
   const int n = c->natoms, nt = c->cp[6];
   RXG_CUDA(cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->st));
+  RXG_CUDA(cudaMemsetAsync(c->d_flag + 16, 0, sizeof(int), c->st));
   RXG_CUDA(cudaMemsetAsync(c->d_acc + 33, 0, sizeof(double), c->st));
   RXG_CUDA(cudaMemsetAsync(c->rowcnt, 0, sizeof(int) * (size_t)(nt + 1), c->st));
   RXG_CUDA(cudaMemsetAsync(c->rowbeg, 0, sizeof(long long) * (size_t)n, c->st));
@@ -305,6 +308,7 @@ int build_pairlist(Ctx *c, bool hessian = true) {
   RXG_TRY(ensure_blk(c, nt));
   RXG_TRY(device_scan<long long>(c, c->rowcnt, nt, c->rowoff, c->d_blk64, (long long *)(c->d_acc + 32)));
   RXG_CUDA(cudaMemcpyAsync(c->h_int, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+  RXG_CUDA(cudaMemcpyAsync(c->h_int + 16, c->d_flag + 16, sizeof(int), cudaMemcpyDeviceToHost, c->st));
   RXG_CUDA(cudaMemcpyAsync(c->h_acc + 32, c->d_acc + 32, 2 * sizeof(long long), cudaMemcpyDeviceToHost, c->st));
   RXG_CUDA(cudaStreamSynchronize(c->st));
   if (c->h_int[0] > c->cfg.maxneighbs10) {
@@ -324,7 +328,7 @@ int build_pairlist(Ctx *c, bool hessian = true) {
     RXG_CUDA(cudaMalloc(&c->cbase, sizeof(int) * (c->nnz_cap / 16 + 2)));
   }
   c->nnz = nnz;
-  c->maxrow = c->h_int[0];
+  c->maxrow = c->h_int[16];
   c->nnz_real = *(long long *)(c->h_acc + 33);
   c->list_is_qeq = MODE >= 1;
   LAUNCH(c, (k_pairlist<MODE, true>), grid, PL_WARPS * 32, 0, c->gnb, c->d_ff, c->d_runs, c->nruns, n, ncell_res, c->rowcnt,
