@@ -8,7 +8,7 @@ A "step" is one pass of the reference's main-loop body (src/main.F90:64-98): int
 QEq (CG to QEq_tol 1e-7) and FORCE over one synthetic RDX configuration.  N=1 workload = BASELINE.json configs[1]:
 conf/init.rdx.lg (LG force field) replicated 18x18x18 = 979 776 atoms, Gaussian sigma=0.02 A displacements
 (seed 20261017), zero initial velocities and charges.  N>1: weak scaling, the same 18^3 block per GPU, vprocs
-(2,1,1) (2,2,1) (2,2,2).
+(2,1,1) (2,2,1) (2,2,2); `--strong` keeps the 18^3 block in total and splits it over the ranks instead.
 
 value : device-resident stepping (rxg_md_run), inputs in HBM when the clock starts, timed with CUDA events on the
         library's own stream, max over ranks.
@@ -41,7 +41,8 @@ VPROCS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
 def workload(args, nranks):
     from rxmd_b200.host.system import build_system
     vp = VPROCS[nranks]
-    mc = tuple(args.mc[a] * vp[a] for a in range(3))
+    # weak scaling (default): --mc unit cells per GPU; --strong: --mc unit cells in total, split over the ranks
+    mc = tuple(args.mc) if args.strong else tuple(args.mc[a] * vp[a] for a in range(3))
     g = os.path.join(INPUTS, "init.rdx.lg")
     s = build_system(os.path.join(g, "input.xyz"), os.path.join(g, "ffield"), mc=mc, vprocs=vp, isLG=True,
                      displace_sigma=args.sigma)
@@ -142,6 +143,7 @@ def main():
     ap.add_argument("--mc", type=int, nargs=3, default=[18, 18, 18], help="unit-cell replication per GPU")
     ap.add_argument("--cpu-mc", type=int, nargs=3, default=[6, 6, 6])
     ap.add_argument("--sigma", type=float, default=0.02)
+    ap.add_argument("--strong", action="store_true", help="strong scaling: --mc is the TOTAL replication, split over the GPUs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
     args = ap.parse_args()
@@ -318,7 +320,7 @@ def main():
     if rank == 0:
         line = {"metric": "atom-timesteps/s, RDX ReaxFF+QEq", "value": value, "unit": "atom-timesteps/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
-                "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+                "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
                 "config": {"workload": f"RDX conf/init.rdx.lg (LG ffield) x{mc[0]}x{mc[1]}x{mc[2]} = {int(natoms_total)} atoms, ReaxFF+QEq "
                                        f"(QEq_tol 1e-7, NMAXQEq 500, every step), NVE dt {DT_FS} fs, gaussian displacements sigma={args.sigma} A",
                            "vprocs": list(vp), "atoms_per_gpu": nres, "parallelism": f"spatial decomposition {vp[0]}x{vp[1]}x{vp[2]}",
