@@ -158,7 +158,8 @@ int rxg_fetch_bonds(rxg_handle h, int *nbrlist, double *BO0);
  * [4] QEq inside md_run  [5] FORCE inside md_run  [6] MOVE inside md_run  [7] md steps (count)
  * [10] get_hsh SpMV kernel total (CUDA events)  [11] its launches  [12] get_gradient SpMV kernel  [13] its launches
  * [14] nnz of the last QEq matrix (entries, without row padding)  [15] residents  [16] residents+ghosts at the last QEq
- * [17] CG iterations (count)  [18] nnz including row padding  [19] 1 if the CG streams 16-bit columns (k_spmv_rows16) */
+ * [17] CG iterations (count)  [18] nnz including row padding  [19] 1 if the CG streams 16-bit columns (k_spmv_rows16)
+ * [20] bytes copied host->device by the entry points so far  [21] bytes copied device->host */
 int rxg_timers(rxg_handle h, double *it_timer_ms);
 
 /* ---- device-resident stepping: the reference main-loop body src/main.F90:64-98

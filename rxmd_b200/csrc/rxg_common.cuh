@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <functional>
 #include <string>
 #include <vector>
 #include "../../include/rxmd_b200.h"
@@ -145,6 +146,7 @@ struct Ctx {
   double *sbuf[2] = {nullptr, nullptr}, *rbuf[2] = {nullptr, nullptr};
   size_t xbuf_cap = 0;
   long long moved = 0, nccl_msgs = 0;
+  std::function<int()> lazy_upload;   // rxg_move: per-atom state beyond atype/pos is uploaded only once an atom actually migrates
   ncclComm_t comm = nullptr;
   // ---- peer-memory halo refresh (multi-rank, one node): every rank owns a window that its neighbours write into directly
   // over NVLink (cudaIpc), see halo_refresh_peer.  Window = 256 B of flags + 6 stages x 2 parities x pw_cap doubles.

@@ -736,6 +736,10 @@ inline int halo_move(Ctx *c) {
     int ns[2], nr[2];
     RXG_TRY(select_axis(c, axis, n, zero, 1, ns));
     RXG_TRY(exchange_counts(c, axis, ns, nr));
+    if (ns[0] + ns[1] + nr[0] + nr[1] > 0 && c->lazy_upload) {   // first atom that leaves or arrives: now the rest of the state is needed
+      RXG_TRY(c->lazy_upload());
+      c->lazy_upload = nullptr;
+    }
     RXG_TRY(ensure_xbuf(c, (size_t)NE_MOVE * (size_t)std::max(std::max(ns[0], ns[1]), std::max(nr[0], nr[1]))));
     const int nblk = cdiv(n > 0 ? n : 1, SCAN_BLK);
     // the two selections of one axis are disjoint (an atom cannot leave through both faces), so marking the first
