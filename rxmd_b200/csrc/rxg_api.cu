@@ -751,10 +751,11 @@ int rxg_move(rxg_handle h, int *natoms, double *atype, double *pos, double *v, d
     RXG_TRY(h2d_planes(c, c->qsfp, qsfp, 1, n));
     RXG_TRY(h2d_planes(c, c->qsfv, qsfv, 1, n));
     // qs/qt travel with the atom in the reference (src/comm.F90:164-171); the device keeps them packed
-    if (qs && qt) {
-      RXG_TRY(stage_ensure(c, sizeof(double) * 2 * (size_t)n));
-      for (int i = 0; i < n; i++) { c->h_stage[2 * i] = qs[i]; c->h_stage[2 * i + 1] = qt[i]; }
-      RXG_CUDA(cudaMemcpyAsync(c->qst, c->h_stage, sizeof(double) * 2 * n, cudaMemcpyHostToDevice, c->st));
+    if (qs && qt && n > 0) {   // two planes into scratch, packed on the device (tmp is free until the compaction, which runs after the packs)
+      double *sa = c->tmp + 13 * (size_t)c->NB, *sb = c->tmp + 14 * (size_t)c->NB;
+      RXG_CUDA(cudaMemcpyAsync(sa, qs, sizeof(double) * n, cudaMemcpyHostToDevice, c->st));
+      RXG_CUDA(cudaMemcpyAsync(sb, qt, sizeof(double) * n, cudaMemcpyHostToDevice, c->st));
+      LAUNCH(c, k_planes_to_pairs, cdiv(n, 256), 256, 0, n, sa, sb, c->qst);
       c->timers_ms[20] += 16.0 * n;
     }
     full = true;
@@ -776,12 +777,12 @@ int rxg_move(rxg_handle h, int *natoms, double *atype, double *pos, double *v, d
     RXG_TRY(d2h_planes(c, q, c->q, 1, m));
     RXG_TRY(d2h_planes(c, qsfp, c->qsfp, 1, m));
     RXG_TRY(d2h_planes(c, qsfv, c->qsfv, 1, m));
-    if (qs && qt) {
-      RXG_TRY(stage_ensure(c, sizeof(double) * 2 * (size_t)m));
-      RXG_CUDA(cudaMemcpyAsync(c->h_stage, c->qst, sizeof(double) * 2 * m, cudaMemcpyDeviceToHost, c->st));
+    if (qs && qt && m > 0) {
+      double *sa = c->tmp, *sb = c->tmp + (size_t)c->NB;
+      LAUNCH(c, k_pairs_to_planes, cdiv(m, 256), 256, 0, m, c->qst, sa, sb);
+      RXG_CUDA(cudaMemcpyAsync(qs, sa, sizeof(double) * m, cudaMemcpyDeviceToHost, c->st));
+      RXG_CUDA(cudaMemcpyAsync(qt, sb, sizeof(double) * m, cudaMemcpyDeviceToHost, c->st));
       c->timers_ms[21] += 16.0 * m;
-      RXG_CUDA(cudaStreamSynchronize(c->st));
-      for (int i = 0; i < m; i++) { qs[i] = c->h_stage[2 * i]; qt[i] = c->h_stage[2 * i + 1]; }
     }
   }
   RXG_CUDA(cudaStreamSynchronize(c->st));

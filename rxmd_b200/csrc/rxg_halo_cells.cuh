@@ -494,6 +494,16 @@ __global__ void k_unpack_force(double *__restrict__ f, int NB, const int *__rest
   atomicAdd(&f[2 * (size_t)NB + s], buf[2 * c + k]);
 }
 
+// qs(:), qt(:) of the host <-> the packed {qs,qt} of the device (rxg_move): two planes of scratch, no host loop
+__global__ void k_planes_to_pairs(int n, const double *__restrict__ a, const double *__restrict__ b, double2 *__restrict__ out) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = make_double2(a[i], b[i]);
+}
+__global__ void k_pairs_to_planes(int n, const double2 *__restrict__ in, double *__restrict__ a, double *__restrict__ b) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) { double2 v = in[i]; a[i] = v.x; b[i] = v.y; }
+}
+
 // are the host's residents bit-identical to the device's?  (flag != 0 if not)
 __global__ void k_same_atoms(int n, int NB, const double *__restrict__ stage, const double *__restrict__ pos,
                              const double *__restrict__ atype, int *__restrict__ flag) {
