@@ -204,7 +204,10 @@ def test_move_migration_matches(built):
     pos[:, :n] += rng.normal(0.0, 0.4, (3, n))           # large kicks: many atoms leave through faces, edges, corners
     v[:, :n] = rng.normal(0.0, 1.0, (3, n))
     q[:n] = rng.normal(0.0, 0.1, n)
-    o.set_atoms(0, atype[:n].copy(), pos[:, :n].copy(), v[:, :n].copy(), q[:n].copy())
+    # qs, qt, qsfp, qsfv travel with their atom too (src/comm.F90:164-171): tag them with the global id
+    gid0 = np.rint((atype[:n] - np.rint(atype[:n])) * 1e13)
+    e.qs[:n], e.qt[:n], e.qsfp[:n], e.qsfv[:n] = gid0 + 0.25, -gid0 - 0.5, gid0 * 2.0, gid0 * 3.0
+    o.set_atoms(0, atype[:n].copy(), pos[:, :n].copy(), v[:, :n].copy(), q[:n].copy(), e.qsfp[:n].copy(), e.qsfv[:n].copy())
     o.move()
     e.COPYATOMS(2, [0.0, 0.0, 0.0], atype, pos, v, f, q)
     m = e.NATOMS
@@ -213,6 +216,17 @@ def test_move_migration_matches(built):
     assert np.array_equal(pos[:, :m], o.f64("pos").reshape(3, -1)[:, :m])
     assert np.array_equal(v[:, :m], o.f64("v").reshape(3, -1)[:, :m])
     assert np.array_equal(q[:m], o.f64("q")[:m])
+    gid1 = np.rint((atype[:m] - np.rint(atype[:m])) * 1e13)
+    assert not np.array_equal(gid0, gid1)                                       # the order did change
+    assert np.array_equal(e.qs[:m], gid1 + 0.25) and np.array_equal(e.qt[:m], -gid1 - 0.5)
+    assert np.array_equal(e.qsfp[:m], o.f64("qsfp")[:m]) and np.array_equal(e.qsfv[:m], o.f64("qsfv")[:m])
+    assert np.array_equal(e.qsfp[:m], gid1 * 2.0)
+    # a call in which nothing leaves the box moves nothing but the positions' round trip (lazy state upload, rxg_move)
+    v_before, tag = v[:, :m].copy(), e.qs[:m].copy()
+    o.move()
+    e.COPYATOMS(2, [0.0, 0.0, 0.0], atype, pos, v, f, q)
+    assert e.NATOMS == m and np.array_equal(v[:, :m], v_before) and np.array_equal(e.qs[:m], tag)
+    assert np.array_equal(pos[:, :m], o.f64("pos").reshape(3, -1)[:, :m])
     e.close(); o.close()
 
 
