@@ -309,7 +309,9 @@ int qeq_device(Ctx *c, bool for_force = false) {
     LAUNCH(c, k_shell_relax, rgrid, 256, 0, c->gnb, nt, n, c->rowbeg, c->rowend, c->col, c->sps, c->qsl, c->d_ff, c->cfg.isEfield, c->cfg.eFieldDir,
            c->cfg.eFieldStrength, c->spos, c->NB, c->d_flag + 6);
     RXG_CUDA(cudaMemcpyAsync(c->h_int + 6, c->d_flag + 6, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+    if (c->peer_ok) RXG_CUDA(cudaMemcpyAsync(c->h_int + 3, c->d_flag + 3, sizeof(int), cudaMemcpyDeviceToHost, c->st));
     RXG_CUDA(cudaStreamSynchronize(c->st));
+    if (c->peer_ok && c->h_int[3]) { c->err = "peer halo: a neighbour's ghost values did not arrive (timeout)"; return RXG_ERR_NCCL; }
     c->pqeq_skips += c->h_int[6];
   }
   c->nstep_qeq = it;

@@ -1117,7 +1117,9 @@ inline int force_device(Ctx *c, bool reuse = false) {
   if (full_ok) LAUNCH(c, (k_enbond<false>), ogrid, 256, 0, nt, n, c->rowbeg, c->rowend, c->col, c->pqs, c->tgs, c->d_ff, c->f, NB, c->d_acc);
   RXG_TRY(halo_cpbk(c));                                                          // :74
   RXG_CUDA(cudaMemcpyAsync(c->h_acc + ACC_PE, c->d_acc + ACC_PE, sizeof(double) * 24, cudaMemcpyDeviceToHost, c->st));
+  if (c->peer_ok) RXG_CUDA(cudaMemcpyAsync(c->h_int + 3, c->d_flag + 3, sizeof(int), cudaMemcpyDeviceToHost, c->st));
   RXG_CUDA(cudaStreamSynchronize(c->st));
+  if (c->peer_ok && c->h_int[3]) { c->err = "peer halo: a neighbour's ghost values did not arrive (timeout)"; return RXG_ERR_NCCL; }
   c->PE[0] = 0.0;
   for (int k = 1; k < 14; k++) c->PE[k] = c->h_acc[ACC_PE + k];
   for (int k = 0; k < 6; k++) c->astr[k] = c->h_acc[ACC_ASTR + k];
