@@ -388,7 +388,7 @@ int rxg_create(const rxg_config *cfg, rxg_handle *out) {
   RXG_CUDA(cudaEventCreate(&c->evm1));
   for (int k = 0; k < 4; k++) RXG_CUDA(cudaEventCreate(&c->evk[k]));
   const size_t NB = c->NB, NS = NB * (size_t)c->MAXN;
-  RXG_TRY(dalloc(c, &c->pos, 3 * NB)); RXG_TRY(dalloc(c, &c->v, 3 * NB)); RXG_TRY(dalloc(c, &c->f, 3 * NB));
+  RXG_TRY(dalloc(c, &c->pos, 3 * NB)); RXG_TRY(dalloc(c, &c->v, 3 * NB)); RXG_TRY(dalloc(c, &c->f, 3 * NB)); RXG_TRY(dalloc(c, &c->fsl, 3 * NB));
   RXG_TRY(dalloc(c, &c->atype, NB)); RXG_TRY(dalloc(c, &c->q, NB)); RXG_TRY(dalloc(c, &c->qsfp, NB)); RXG_TRY(dalloc(c, &c->qsfv, NB));
   RXG_TRY(dalloc(c, &c->qst, NB)); RXG_TRY(dalloc(c, &c->hsq, NB)); RXG_TRY(dalloc(c, &c->gst, NB));
   RXG_TRY(dalloc(c, &c->hst, NB)); RXG_TRY(dalloc(c, &c->tst, NB)); RXG_TRY(dalloc(c, &c->ust, NB)); RXG_TRY(dalloc(c, &c->wst, NB));

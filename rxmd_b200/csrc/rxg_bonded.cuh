@@ -188,7 +188,7 @@ template <bool HALF>
 __global__ void __launch_bounds__(256) k_enbond(int ntot, int natoms, const long long *__restrict__ rowbeg,
                                                 const long long *__restrict__ rowend, const int *__restrict__ col,
                                                 const double4 *__restrict__ pqs, const int4 *__restrict__ tgs,
-                                                const DevFF *__restrict__ ffp, double *__restrict__ f, int NB,
+                                                const DevFF *__restrict__ ffp, double *__restrict__ f, double *__restrict__ fsl, int NB,
                                                 double *__restrict__ acc) {
   const int lane = threadIdx.x & 31;
   const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // rows are walked in cell order
@@ -231,7 +231,9 @@ __global__ void __launch_bounds__(256) k_enbond(int ntot, int natoms, const long
         vir[0] += h * dx * dx; vir[1] += h * dy * dy; vir[2] += h * dz * dz;
         vir[3] += h * dy * dz; vir[4] += h * dz * dx; vir[5] += h * dx * dy;
       }
-      if (HALF) atomic_add3(f, NB, tj.z, cc * dx, cc * dy, cc * dz);
+      // the partner's share goes to the SLOT-ordered accumulator: the partners of consecutive lanes are consecutive slots
+      // (a stencil run), so the fp64 reductions of a warp fall into a few sectors; indexed by atom they were 32 scattered ones
+      if (HALF) atomic_add3(fsl, NB, js, cc * dx, cc * dy, cc * dz);
     }
     fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
     if (lane == 0) {
@@ -575,7 +577,7 @@ __global__ void __launch_bounds__(256) k_ehb_eval(int nwork, const int2 *__restr
                                                   const double4 *__restrict__ pqs, const int4 *__restrict__ tgs, int NB,
                                                   const DevFF *__restrict__ ffp, Bonds B, const long long *__restrict__ rowbeg,
                                                   const long long *__restrict__ rowend, const int *__restrict__ col,
-                                                  double *__restrict__ f, double *__restrict__ acc) {
+                                                  double *__restrict__ f, double *__restrict__ fsl, double *__restrict__ acc) {
   const int lane = threadIdx.x & 31;
   const int t = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   double part[1] = {0.0};
@@ -625,7 +627,7 @@ __global__ void __launch_bounds__(256) k_ehb_eval(int nwork, const int2 *__restr
         fi[c] += fij[c];
         fj[c] += -fij[c] + fjk[c] - ff3[c];
       }
-      atomic_add3(f, NB, tk.z, -fjk[0] + ff3[0], -fjk[1] + ff3[1], -fjk[2] + ff3[2]);
+      atomic_add3(fsl, NB, ks, -fjk[0] + ff3[0], -fjk[1] + ff3[1], -fjk[2] + ff3[2]);   // slot-ordered accumulator, see k_enbond
     }
     cb = warp_sum(cb);
 #pragma unroll
@@ -1014,6 +1016,14 @@ __global__ void __launch_bounds__(256) k_observe(int n, int NB, const int *__res
   block_add<2>(part, acc);
 }
 
+// f(atom) += the slot-ordered partner forces of k_enbond / k_enbond_pqeq / k_ehb_eval (residents and ghosts)
+__global__ void k_fsl_to_f(int ntot, int NB, const int *__restrict__ order, const double *__restrict__ fsl, double *__restrict__ f) {
+  int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= ntot) return;
+  const int i = order[s];
+  f[i] += fsl[s]; f[(size_t)NB + i] += fsl[(size_t)NB + s]; f[2 * (size_t)NB + i] += fsl[2 * (size_t)NB + s];
+}
+
 }   // namespace rxg
 #include "rxg_pqeq.cuh"
 namespace rxg {
@@ -1035,6 +1045,7 @@ inline Bonds make_bonds(Ctx *c) {
 inline int force_device(Ctx *c, bool reuse = false) {
   const int NB = c->NB, n = c->natoms;
   RXG_CUDA(cudaMemsetAsync(c->f, 0, sizeof(double) * 3 * NB, c->st));
+  RXG_CUDA(cudaMemsetAsync(c->fsl, 0, sizeof(double) * 3 * NB, c->st));
   RXG_CUDA(cudaMemsetAsync(c->d_acc + ACC_PE, 0, sizeof(double) * 24, c->st));
   double dr[3];
   for (int a = 0; a < 3; a++) dr[a] = c->cfg.nmincell * c->box.lcsize[a];
@@ -1071,10 +1082,10 @@ inline int force_device(Ctx *c, bool reuse = false) {
   if (pqeq) {   // src/pot.F90:48-49
     full_ok = false;
     LAUNCH(c, k_pack_sps, cdiv(nt, 256), 256, 0, nt, c->spos, NB, c->itype, c->gnb.slot_of, c->d_ff, c->sps);
-    LAUNCH(c, k_enbond_pqeq, ogrid, 256, 0, nt, n, c->rowbeg, c->rowend, c->col, c->pqs, c->tgs, c->sps, c->d_ff, c->f, NB, c->d_acc);
+    LAUNCH(c, k_enbond_pqeq, ogrid, 256, 0, nt, n, c->rowbeg, c->rowend, c->col, c->pqs, c->tgs, c->sps, c->d_ff, c->f, c->fsl, NB, c->d_acc);
     if (c->cfg.isEfield && n > 0)   // :61
       LAUNCH(c, k_efield, cdiv(n, 256), 256, 0, n, c->q, c->itype, c->d_ff, c->cfg.eFieldDir, c->cfg.eFieldStrength, c->f, NB);
-  } else if (!full_ok) LAUNCH(c, (k_enbond<true>), ogrid, 256, 0, nt, n, c->rowbeg, c->rowend, c->col, c->pqs, c->tgs, c->d_ff, c->f, NB, c->d_acc);
+  } else if (!full_ok) LAUNCH(c, (k_enbond<true>), ogrid, 256, 0, nt, n, c->rowbeg, c->rowend, c->col, c->pqs, c->tgs, c->d_ff, c->f, c->fsl, NB, c->d_acc);
   LAUNCH(c, k_elnpr_prep, cdiv(nt, 256), 256, 0, nt, c->itype, c->d_ff, c->delta, c->nlp, c->dDlp, c->deltalp);
   LAUNCH(c, k_ebond_elnpr, cdiv(n, 128), 128, 0, n, c->itype, c->gid, c->d_ff, B, c->delta, c->dDlp, c->deltalp, c->d_acc);
   // angles and torsions: enumerate survivors of the cut-off tests, then evaluate one per thread
@@ -1093,7 +1104,7 @@ inline int force_device(Ctx *c, bool reuse = false) {
       c->n_angles = n3; c->n_torsions = n4; c->n_hbonds = nh;
       if (nh > 0)
         LAUNCH(c, k_ehb_eval, cdiv(nh * 32, 256), 256, 0, (int)nh, wlh, c->gnb.slot_of, c->pqs, c->tgs, NB, c->d_ff, B, c->rowbeg,
-               c->rowend, c->col, c->f, c->d_acc);
+               c->rowend, c->col, c->f, c->fsl, c->d_acc);
       if (n3 > 0)
         LAUNCH(c, k_e3b_eval, cdiv(n3, 128), 128, 0, (int)n3, wl3, pq, NB, c->itype, c->d_ff, B, c->delta, c->nlp, c->dDlp, c->sbo,
                c->s3, c->f, c->d_acc);
@@ -1108,13 +1119,14 @@ inline int force_device(Ctx *c, bool reuse = false) {
     c->wl_caph = std::max(c->wl_caph, nh + nh / 4 + 1024);
     RXG_CUDA(cudaMalloc((void **)&c->wl, sizeof(int2) * (size_t)(c->wl_cap3 + c->wl_cap4 + c->wl_caph)));
   }
+  LAUNCH(c, k_fsl_to_f, cdiv(nt, 256), 256, 0, nt, NB, c->gnb.order, c->fsl, c->f);
   // ---- ForceBondedTerms (src/pot.F90:63)
   LAUNCH(c, k_final0, cdiv(nt, 128), 128, 0, nt, B, c->cdbnd);
   LAUNCH(c, k_final1, cdiv(nt, 128), 128, 0, nt, c->pos, NB, B, c->cdbnd, c->s3, c->ccbnd, c->f);
   LAUNCH(c, k_final2, cdiv(nt, 128), 128, 0, nt, c->pos, NB, B, c->ccbnd, c->f);
   LAUNCH(c, k_virial, cdiv(nt, 256), 256, 0, nt, c->pos, c->f, NB, c->d_acc);   // :65-72
   // full-row ENbond puts both halves of a pair force on residents, so its virial is taken per pair inside the kernel
-  if (full_ok) LAUNCH(c, (k_enbond<false>), ogrid, 256, 0, nt, n, c->rowbeg, c->rowend, c->col, c->pqs, c->tgs, c->d_ff, c->f, NB, c->d_acc);
+  if (full_ok) LAUNCH(c, (k_enbond<false>), ogrid, 256, 0, nt, n, c->rowbeg, c->rowend, c->col, c->pqs, c->tgs, c->d_ff, c->f, c->fsl, NB, c->d_acc);
   RXG_TRY(halo_cpbk(c));                                                          // :74
   RXG_CUDA(cudaMemcpyAsync(c->h_acc + ACC_PE, c->d_acc + ACC_PE, sizeof(double) * 24, cudaMemcpyDeviceToHost, c->st));
   if (c->peer_ok) RXG_CUDA(cudaMemcpyAsync(c->h_int + 3, c->d_flag + 3, sizeof(int), cudaMemcpyDeviceToHost, c->st));

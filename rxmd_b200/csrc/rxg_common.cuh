@@ -121,6 +121,7 @@ struct Ctx {
   int natoms = 0;
   int cp[7] = {0, 0, 0, 0, 0, 0, 0};   // copyptr(0:6), reference src/module.F90:234
   double *pos = nullptr, *v = nullptr, *f = nullptr;            // [3*NB], x|y|z planes
+  double *fsl = nullptr;    // [3*NB] by SLOT: partner forces of the non-bonded and H-bond kernels, folded into f by k_fsl_to_f
   double *atype = nullptr, *q = nullptr, *qsfp = nullptr, *qsfv = nullptr;
   double2 *qst = nullptr;   // {qs, qt}      (reference qs(:), qt(:))
   double4 *hsq = nullptr;   // {hs, ht, q, -} gather pack of get_hsh; .z mirrors q for residents+ghosts

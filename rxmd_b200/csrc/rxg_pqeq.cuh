@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(256) k_enbond_pqeq(int ntot, int natoms, const
                                                      const long long *__restrict__ rowend, const int *__restrict__ col,
                                                      const double4 *__restrict__ pqs, const int4 *__restrict__ tgs,
                                                      const double4 *__restrict__ sps, const DevFF *__restrict__ ffp,
-                                                     double *__restrict__ f, int NB, double *__restrict__ acc) {
+                                                     double *__restrict__ f, double *__restrict__ fsl, int NB, double *__restrict__ acc) {
   const int lane = threadIdx.x & 31;
   const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   double part[3] = {0.0, 0.0, 0.0};
@@ -312,7 +312,7 @@ __global__ void __launch_bounds__(256) k_enbond_pqeq(int ntot, int natoms, const
       }
       part[0] += PEvdw; part[1] += Eclmb;
       fx -= gx; fy -= gy; fz -= gz;
-      atomic_add3(f, NB, tj.z, gx, gy, gz);
+      atomic_add3(fsl, NB, js, gx, gy, gz);   // slot-ordered accumulator, see k_enbond
     }
     fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
     if (lane == 0) {
