@@ -35,6 +35,7 @@ def lib():
         L.orc_set_atoms.argtypes = [C.c_void_p, C.c_int, C.c_int, dp, dp, dp, dp, dp, dp]
         L.orc_set_corrected.argtypes = [C.c_void_p, C.c_int]
         L.orc_set_terms.argtypes = [C.c_void_p, C.c_int]
+        L.orc_set_pqeq_stale.argtypes = [C.c_void_p, C.c_int]
         L.orc_natoms.argtypes = [C.c_void_p, C.c_int]
         L.orc_set_spos.argtypes = [C.c_void_p, C.c_int, dp]
         for f in (L.orc_qeq, L.orc_force, L.orc_move):
@@ -90,6 +91,9 @@ class Oracle:
 
     def set_corrected(self, on):
         self.L.orc_set_corrected(self.h, int(on))
+
+    def set_pqeq_stale(self, on):
+        self.L.orc_set_pqeq_stale(self.h, int(on))
 
     def set_terms(self, mask):
         self.L.orc_set_terms(self.h, int(mask))

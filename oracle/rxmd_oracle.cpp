@@ -123,6 +123,9 @@ struct World {
   double t_qeq = 0, t_force = 0, t_move = 0;
   bool corrected = false;
   int term_mask = 0x3f;
+  // diagnostic: what a SERIAL build of the reference does where get_coulomb_and_dcoulomb_pqeq returns early -- the output
+  // variable keeps the value of the last call that assigned it (see get_clmb_pqeq).  Parity uses false (zero contribution).
+  bool pqeq_stale = false;
 };
 
 #define RX(r, i) r.pos[(i)]
@@ -682,11 +685,12 @@ void get_gradient_pqeq(const Params &P, Rank &r, double *gg) {   // :442-477
   gg[0] = a; gg[1] = b;
 }
 
-void update_shell_positions(const Params &P, Rank &r) {   // :187-259
+void update_shell_positions(const Params &P, Rank &r, bool stale) {   // :187-259
   std::vector<double> sforce(3 * (size_t)r.natoms, 0.0);
   const size_t n = r.natoms;
   long long skips = 0;
-#pragma omp parallel for schedule(guided) reduction(+ : skips)
+  double sf_keep[3] = {0, 0, 0};   // `sf` of the reference: one variable for both calls, never reset (stale mode only)
+#pragma omp parallel for schedule(guided) reduction(+ : skips) if (!stale)
   for (int i = 0; i < r.natoms; i++) {
     int ity = nint(r.atype[i]);
     if (!P.polarizable(ity)) continue;
@@ -705,17 +709,21 @@ void update_shell_positions(const Params &P, Rank &r) {   // :187-259
       double shellj[3] = {RX(r, j) + SX(r, j), RY(r, j) + SY(r, j), RZ(r, j) + SZ(r, j)};
       double dr[3] = {shelli[0] - RX(r, j), shelli[1] - RY(r, j), shelli[2] - RZ(r, j)};
       double Esc = 0, sf[3] = {0, 0, 0};
+      if (stale) { sf[0] = sf_keep[0]; sf[1] = sf_keep[1]; sf[2] = sf_keep[2]; }
       if (!get_clmb_pqeq(P, dr, Esc, P.inxnpqeq(ity, jty), P.TBL_psc, sf)) skips++;
       double ff[3] = {-CCLMB0 * sf[0] * qjc * P.Zpqeq[ity - 1], -CCLMB0 * sf[1] * qjc * P.Zpqeq[ity - 1], -CCLMB0 * sf[2] * qjc * P.Zpqeq[ity - 1]};
       sf0 = sf0 - ff[0]; sf1 = sf1 - ff[1]; sf2 = sf2 - ff[2];
+      double ss[3] = {sf[0], sf[1], sf[2]};   // the same variable goes into the shell-shell call
       if (P.polarizable(jty)) {
         double ds[3] = {shelli[0] - shellj[0], shelli[1] - shellj[1], shelli[2] - shellj[2]};
-        double Ess = 0, ss[3] = {0, 0, 0};
+        double Ess = 0;
+        if (!stale) { ss[0] = ss[1] = ss[2] = 0.0; }
         if (!get_clmb_pqeq(P, ds, Ess, P.inxnpqeq(ity, jty), P.TBL_pss, ss)) skips++;
         double f2[3] = {CCLMB0 * ss[0] * P.Zpqeq[ity - 1] * P.Zpqeq[jty - 1], CCLMB0 * ss[1] * P.Zpqeq[ity - 1] * P.Zpqeq[jty - 1],
                         CCLMB0 * ss[2] * P.Zpqeq[ity - 1] * P.Zpqeq[jty - 1]};
         sf0 = sf0 - f2[0]; sf1 = sf1 - f2[1]; sf2 = sf2 - f2[2];
       }
+      if (stale) { sf_keep[0] = ss[0]; sf_keep[1] = ss[1]; sf_keep[2] = ss[2]; }
     }
     sforce[i] = sf0; sforce[n + i] = sf1; sforce[2 * n + i] = sf2;
   }
@@ -729,6 +737,36 @@ void update_shell_positions(const Params &P, Rank &r) {   // :187-259
       for (int c = 0; c < 3; c++) dr[c] = dr[c] / ddr * MAX_SHELL_DISPLACEMENT;
     SX(r, i) = SX(r, i) + dr[0]; SY(r, i) = SY(r, i) + dr[1]; SZ(r, i) = SZ(r, i) + dr[2];
   }
+}
+
+// Diagnostic (pqeq_stale): redo the shell term of fpqeq the way a serial build of the reference does it -- `pqeqs` keeps the
+// value of the last core-shell call that assigned it, across pairs and across atoms, in the loop order of qeq_initialize
+// (cells c1, c2, c3; atoms of a cell in list order; neighbours in row order).  src/pqeq.F90:298-345.
+void stale_fpqeq(const Params &P, Rank &r) {
+  Grid &g = r.nbg;
+  double pqeqs = 0.0, ffd[3];
+  for (int c1 = 0; c1 < g.nc[0]; c1++)
+    for (int c2 = 0; c2 < g.nc[1]; c2++)
+      for (int c3 = 0; c3 < g.nc[2]; c3++) {
+        size_t ci = g.idx(c1, c2, c3);
+        int i = g.header[ci];
+        for (int m = 0; m < g.nacell[ci]; m++, i = g.llist[i]) {
+          int ity = nint(r.atype[i]);
+          const int *nl = &r.nbplist[(size_t)i * r.W10];
+          double fp = 0.0;
+          for (int j1 = 0; j1 < r.nbpcnt[i]; j1++) {
+            int j = nl[j1];
+            int jty = nint(r.atype[j]);
+            fp = fp + r.hessian[(size_t)i * r.W10 + j1] * P.Zpqeq[jty - 1];
+            if (P.polarizable(jty)) {
+              double rs[3] = {RX(r, i) - RX(r, j) - SX(r, j), RY(r, i) - RY(r, j) - SY(r, j), RZ(r, i) - RZ(r, j) - SZ(r, j)};
+              get_clmb_pqeq(P, rs, pqeqs, P.inxnpqeq(jty, ity), P.TBL_psc, ffd);   // early return: pqeqs keeps its old value
+              fp = fp - CCLMB0_QEQ * pqeqs * P.Zpqeq[jty - 1];
+            }
+          }
+          r.fpqeq[i] = fp;
+        }
+      }
 }
 
 int PQEq(World &w) {   // src/pqeq.F90:2-182: the QEq driver with the PQEq kernels and the shell relaxation at the end
@@ -761,6 +799,7 @@ int PQEq(World &w) {   // src/pqeq.F90:2-182: the QEq driver with the PQEq kerne
     if (rc) return rc;
     rc = PairList(w, r, true);
     if (rc) return rc;
+    if (w.pqeq_stale) stale_fpqeq(P, r);
   }
   COPYATOMS(w, MODE_QCOPY1, QCopyDr);
   double Gnew[2] = {0, 0}, Gold[2];
@@ -810,7 +849,7 @@ int PQEq(World &w) {   // src/pqeq.F90:2-182: the QEq driver with the PQEq kerne
       }
     COPYATOMS(w, MODE_QCOPY2, QCopyDr);
   }
-  for (auto &r : w.R) { r.nstep_qeq = nstep_qeq; update_shell_positions(P, r); }   // :171
+  for (auto &r : w.R) { r.nstep_qeq = nstep_qeq; update_shell_positions(P, r, w.pqeq_stale); }   // :171
   return 0;
 }
 
@@ -1712,6 +1751,7 @@ int orc_create(const rxg_config *cfg, const rxg_ff *ff, const rxg_box *boxes, in
 
 int orc_set_corrected(orc_world h, int on) { ((World *)h)->corrected = on != 0; return 0; }
 int orc_set_terms(orc_world h, int mask) { ((World *)h)->term_mask = mask; return 0; }
+int orc_set_pqeq_stale(orc_world h, int on) { ((World *)h)->pqeq_stale = on != 0; return 0; }
 int orc_destroy(orc_world h) { delete (World *)h; return 0; }
 const char *orc_last_error(orc_world h) { return ((World *)h)->err.c_str(); }
 

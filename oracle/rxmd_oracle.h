@@ -28,6 +28,10 @@ int orc_destroy(orc_world w);
 int orc_set_corrected(orc_world w, int on);
 /* diagnostic: bit mask of energy terms FORCE evaluates: 1 ENbond, 2 Ebond, 4 Elnpr, 8 Ehb, 16 E3b, 32 E4b (default all) */
 int orc_set_terms(orc_world w, int mask);
+/* diagnostic: 1 = where get_coulomb_and_dcoulomb_pqeq returns early (src/module.F90:402) keep the output variable's previous
+ * value, as a serial build of the reference does (src/pqeq.F90:219-231,340-343), instead of the zero contribution that parity
+ * uses.  Quantifies the size of that deviation (tests/test_oracle_pqeq.py). */
+int orc_set_pqeq_stale(orc_world w, int on);
 const char *orc_last_error(orc_world w);
 
 /* resident state of one rank; pos is pos(NBUFFER,3) compact: double[3*n] = x[n] y[n] z[n] (REAL coordinates) */
