@@ -47,15 +47,6 @@ int setup_grid(Ctx *c, DevGrid &g, const int *cc, const double *cs, int L) {
   return RXG_OK;
 }
 
-int stage_ensure(Ctx *c, size_t bytes) {
-  if (bytes > c->h_stage_bytes) {
-    if (c->h_stage) cudaFreeHost(c->h_stage);
-    c->h_stage_bytes = bytes + bytes / 8;
-    RXG_CUDA(cudaMallocHost((void **)&c->h_stage, c->h_stage_bytes));
-  }
-  return RXG_OK;
-}
-
 // host array with leading dimension NB (planes) -> device plane array; n leading entries of each of `planes` planes
 int h2d_planes(Ctx *c, double *dev, const double *host, int planes, int n) {
   c->timers_ms[20] += 8.0 * (double)planes * (double)n;
@@ -624,7 +615,6 @@ int rxg_destroy(rxg_handle h) {
       if (p) cudaFree(p);
     if (c->h_acc) cudaFreeHost(c->h_acc);
     if (c->h_int) cudaFreeHost(c->h_int);
-    if (c->h_stage) cudaFreeHost(c->h_stage);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->st);

@@ -217,8 +217,6 @@ struct Ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm0 = nullptr, evm1 = nullptr, evk[4] = {nullptr, nullptr, nullptr, nullptr};
   bool grad_pending = false;
   // ---- staging (pinned) ------------------------------------------------------------------------------------
-  double *h_stage = nullptr;
-  size_t h_stage_bytes = 0;
 };
 
 #define RXG_CUDA(call)                                                                                   \
