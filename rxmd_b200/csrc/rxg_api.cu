@@ -449,6 +449,7 @@ int rxg_set_forcefield(rxg_handle h, const rxg_ff *ff) {
     }
   RXG_TRY(upload(c, tq2.data(), tq2.size(), &d.TBL_qeq2));
   d.ntype_pqeq = 0;
+  d.pq_same = 0;
   d.isPolarizable = d.inxnpqeq = nullptr; d.Zpqeq = d.Kspqeq = nullptr; d.TBL_pcc = d.TBL_psc = d.TBL_pss = nullptr;
   if (c->cfg.isPQEq) {
     if (ff->ntype_pqeq < 1 || !ff->isPolarizable || !ff->Zpqeq || !ff->Kspqeq || !ff->inxnpqeq || !ff->TBL_Eclmb_pcc ||
@@ -472,6 +473,9 @@ int rxg_set_forcefield(rxg_handle h, const rxg_ff *ff) {
       return upload(c, t4.data(), t4.size(), dst);
     };
     RXG_TRY(pack(ff->TBL_Eclmb_pcc, &d.TBL_pcc)); RXG_TRY(pack(ff->TBL_Eclmb_psc, &d.TBL_psc)); RXG_TRY(pack(ff->TBL_Eclmb_pss, &d.TBL_pss));
+    const size_t tb = sizeof(double) * np2 * ntab * 2;
+    const char *ns_env = getenv("RXG_PQEQ_NO_TABLE_CACHE");
+    d.pq_same = !(ns_env && ns_env[0] == '1') && memcmp(ff->TBL_Eclmb_pcc, ff->TBL_Eclmb_psc, tb) == 0 && memcmp(ff->TBL_Eclmb_psc, ff->TBL_Eclmb_pss, tb) == 0;
   }
   if (!c->d_ff) RXG_CUDA(cudaMalloc((void **)&c->d_ff, sizeof(DevFF)));
   RXG_CUDA(cudaMemcpy(c->d_ff, &d, sizeof(DevFF), cudaMemcpyHostToDevice));

@@ -92,6 +92,7 @@ struct DevFF {
   const double *Zpqeq, *Kspqeq;
   // TBL_Eclmb_pcc/psc/pss re-packed: [(inxn-1)*NTABLE + (itb-1)] = {E(itb), E(itb+1), dE(itb), dE(itb+1)}: one 32-byte gather per lerp
   const double4 *TBL_pcc, *TBL_psc, *TBL_pss;
+  int pq_same;   // the three tables hold identical numbers (every element has Rc == Rs): one record serves all terms of a pair
 };
 
 // One linked-cell grid (replaces header/llist/nacell, reference src/main.F90:277-318) as a counting sort.
