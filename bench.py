@@ -1,20 +1,29 @@
 #!/usr/bin/env python
 """bench.py -- atom-timesteps/s of the ReaxFF+QEq hot path on N B200s (BASELINE.json metric).
 
-    python bench.py --gpus N --steps K --warmup W            # this framework (one rank per GPU)
-    python bench.py --impl reference --steps K --warmup W    # CPU restatement of the reference on the host cores
+    python bench.py --gpus N --steps K --warmup W [--config rdx|water|sic|pqeq] [--strong]   # this framework, one rank per GPU
+    python bench.py --impl reference --steps K --warmup W [--config ...]                    # CPU restatement of the reference
 
 A "step" is one pass of the reference's main-loop body (src/main.F90:64-98): integrator halves, COPYATOMS(MOVE),
-QEq (CG to QEq_tol 1e-7) and FORCE over one synthetic RDX configuration.  N=1 workload = BASELINE.json configs[1]:
-conf/init.rdx.lg (LG force field) replicated 18x18x18 = 979 776 atoms, Gaussian sigma=0.02 A displacements
-(seed 20261017), zero initial velocities and charges.  N>1: weak scaling, the same 18^3 block per GPU, vprocs
-(2,1,1) (2,2,1) (2,2,2); `--strong` keeps the 18^3 block in total and splits it over the ranks instead.
+QEq / PQEq (CG to QEq_tol 1e-7) and FORCE over one synthetic replicated configuration with Gaussian sigma = 0.02 A
+displacements (counter-based, seed 20261017), zero initial velocities and charges.
+
+--config (rxmd_b200/host/configs.py; the headline is `rdx` = BASELINE.json configs[1], the one the metric is quoted on):
+    rdx    conf/init.rdx.lg (LG ffield) x18^3 = 979 776 atoms per GPU
+    water  conf/init.water ice Ih x(60,35,40) = 2 016 000 atoms          (configs[2]; north_star asks for --strong)
+    sic    conf/init.sicnp x(20,20,18) = 3 938 400 atoms per GPU         (configs[3], weak scaling to vprocs 2 2 2)
+    pqeq   conf/init.pe.pqeq + pqeq1.par x(30,45,88) = 1 425 600 atoms   (configs[4], PQEq, rctap 12.5 A)
+N>1 is weak scaling (the same block per GPU, vprocs (2,1,1) (2,2,1) (2,2,2)); `--strong` keeps the block in total and
+splits it over the ranks.  Every rank generates its own sub-domain only.
 
 value : device-resident stepping (rxg_md_run), inputs in HBM when the clock starts, timed with CUDA events on the
         library's own stream, max over ranks.
 e2e   : the same step driven through the reference-facing entry points COPYATOMS(MODE_MOVE) / QEq / FORCE with
         pinned HOST arrays (host<->device copies inside the timed region, integrator on the host like the Fortran
         driver).
+parity: (N > 1) before timing, a ~10 k-atom run over the same multi-GPU data plane (NCCL exchange, peer-memory ghost refresh
+        and all-reduce) is compared with the CPU oracle simulating the same vprocs: copyptr, 10 A row counts, forces 1e-9,
+        energies 1e-9, charges, migration over 10 MD steps.
 """
 from __future__ import annotations
 
@@ -34,19 +43,8 @@ sys.path.insert(0, ROOT)
 UTIME = 1.0e3 / 20.455            # reference src/module.F90:202
 DT_FS = 0.25                       # README sample run
 LEX_K = 2.0
-INPUTS = os.path.join(ROOT, "tests", "golden", "inputs")
-VPROCS = {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}
-
-
-def workload(args, nranks):
-    from rxmd_b200.host.system import build_system
-    vp = VPROCS[nranks]
-    # weak scaling (default): --mc unit cells per GPU; --strong: --mc unit cells in total, split over the ranks
-    mc = tuple(args.mc) if args.strong else tuple(args.mc[a] * vp[a] for a in range(3))
-    g = os.path.join(INPUTS, "init.rdx.lg")
-    s = build_system(os.path.join(g, "input.xyz"), os.path.join(g, "ffield"), mc=mc, vprocs=vp, isLG=True,
-                     displace_sigma=args.sigma)
-    return s, mc, vp
+CPU_MC = {"rdx": (10, 10, 10), "water": (24, 14, 16), "sic": (6, 6, 6), "pqeq": (10, 15, 28)}        # cpu_baseline leg: 10-30 s
+REF_MC = {"rdx": (12, 12, 13), "water": (32, 18, 20), "sic": (8, 8, 8), "pqeq": (14, 21, 40)}       # --impl reference: >= 300 k atoms
 
 
 class ClockSampler(threading.Thread):
@@ -96,42 +94,77 @@ def peak_hbm():
     return 6650.0, "fallback (B200_PROFILING.md)"
 
 
-def cpu_sample(args, steps, warmup):
-    """The CPU restatement of the reference (oracle/, OpenMP) on a bounded sample of the same workload."""
-    from rxmd_b200.host.system import build_system
-    from oracle.pyoracle import Oracle
-    g = os.path.join(INPUTS, "init.rdx.lg")
-    mc = tuple(args.cpu_mc)
-    s = build_system(os.path.join(g, "input.xyz"), os.path.join(g, "ffield"), mc=mc, isLG=True, displace_sigma=args.sigma)
-    o = Oracle(s, s.config())
+def host_cores():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def cpu_sample(config, mc, steps, warmup, sigma, budget_s=None):
+    """The CPU restatement of the reference (oracle/, OpenMP) on a bounded sample of the same workload, on all the host
+    cores this process may use (the team size is set explicitly: launchers such as torch.distributed.run export
+    OMP_NUM_THREADS=1).  With `budget_s` the number of timed steps shrinks so that the loop ends within the budget."""
+    from rxmd_b200.host.configs import build_config
+    from oracle.pyoracle import Oracle, set_threads
+    threads = set_threads(host_cores())
+    s, tot, vp, cfgkw, label = build_config(config, mc=mc, sigma=sigma)
+    o = Oracle(s, s.config(**cfgkw))
     dt = DT_FS / UTIME
     lw2 = 2.0 * LEX_K / dt / dt
     o.move(); o.qeq(); o.force()
+    t0 = time.perf_counter()
     o.md_run(warmup, dt, 1, lw2, 0)
+    t_warm = (time.perf_counter() - t0) / max(warmup, 1)
+    if budget_s is not None:
+        steps = max(1, min(steps, int(budget_s / max(t_warm, 1e-9))))
     t0 = time.perf_counter()
     o.md_run(steps, dt, 1, lw2, warmup)
     t = time.perf_counter() - t0
-    cores = int(os.environ.get("OMP_NUM_THREADS", os.cpu_count() or 1))
     o.close()
-    return {"value": s.natoms * steps / t, "unit": "atom-timesteps/s", "cores": cores, "kind": "port",
-            "sample": f"RDX (LG ffield) {mc[0]}x{mc[1]}x{mc[2]} = {s.natoms} atoms, {steps} steps after {warmup} warm-up, "
-                      f"sigma={args.sigma} A; OpenMP C++ restatement of the reference loops (no Fortran toolchain in the image)"}, t / steps * 1e3
+    return {"value": s.natoms * steps / t, "unit": "atom-timesteps/s", "cores": threads, "kind": "port",
+            "sample": f"{label} x{tot[0]}x{tot[1]}x{tot[2]} = {s.natoms} atoms, {steps} steps after {warmup} warm-up, sigma={sigma} A; "
+                      f"OpenMP C++ restatement of the reference loops with {threads} threads (omp_get_max_threads; no Fortran "
+                      f"toolchain in the image, oracle/_ref is empty)",
+            "natoms": s.natoms, "steps": steps, "warmup": warmup}, t / steps * 1e3, label
 
 
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    steps = max(1, min(args.steps, 20))
+    from rxmd_b200.host.configs import CONFIGS
+    mc = tuple(args.cpu_mc) if args.cpu_mc else REF_MC[args.config]
     warm = max(1, min(args.warmup, 3))
-    cb, ms = cpu_sample(args, steps, warm)
-    line = {"impl": "reference", "metric": "atom-timesteps/s, RDX ReaxFF+QEq", "value": cb["value"], "unit": "atom-timesteps/s",
-            "n_gpus": args.gpus, "steps": steps, "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+    cb, ms, label = cpu_sample(args.config, mc, args.steps, warm, args.sigma, budget_s=150.0)
+    full = CONFIGS[args.config]["mc"]
+    line = {"impl": "reference", "metric": "atom-timesteps/s, RDX ReaxFF+QEq" if args.config == "rdx" else f"atom-timesteps/s, {label}",
+            "value": cb["value"], "unit": "atom-timesteps/s",
+            "n_gpus": args.gpus, "steps": cb["steps"], "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": "RDX conf/init.rdx.lg (LG ffield) ReaxFF+QEq, QEq_tol 1e-7 every step, NVE dt 0.25 fs", "sample": cb["sample"]},
+            "config": {"workload": f"{label}, QEq_tol 1e-7 every step, NVE dt {DT_FS} fs", "sample": cb["sample"],
+                       "same_config": list(mc) == list(full), "full_config_replication": list(full), "sample_replication": list(mc)},
             "cpu_baseline": cb, "e2e": {"value": cb["value"], "unit": "atom-timesteps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
     print(json.dumps(line), flush=True)
+
+
+def preflight_parity(dist, rank, world, local):
+    """~10 k atoms over the same multi-GPU data plane against the oracle with identical vprocs (tools/mr_diag.py)."""
+    import torch
+    from tools.mr_diag import compare
+    mc = {2: (6, 3, 3), 4: (6, 6, 3), 8: (5, 5, 5)}[world]          # RDX 168-atom cells: 9 072 / 18 144 / 21 000 atoms
+    try:
+        res = compare(rank, world, local, mc, sigma=0.02, verbose=False)
+    except Exception as ex:   # a failed pre-flight is reported, never hidden
+        res = {"ok": False, "error": repr(ex)[:300], "dq": float("nan"), "f_rel": float("nan"), "md_pe_rel": float("nan"),
+               "nstep_same": False, "peer_halo": False, "peer_allreduce": False}
+    t = torch.tensor([1.0 if res["ok"] else 0.0, -res["dq"] if res["dq"] == res["dq"] else -1e9, -res["f_rel"] if res["f_rel"] == res["f_rel"] else -1e9,
+                      -res["md_pe_rel"] if res["md_pe_rel"] == res["md_pe_rel"] else -1e9, 1.0 if res["nstep_same"] else 0.0],
+                     dtype=torch.float64, device="cuda")
+    dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return {"ok": bool(t[0].item() > 0.5), "ranks": world, "atoms": int(np.prod(mc)) * 168, "replication": list(mc),
+            "max_dq": -t[1].item(), "max_force_rel": -t[2].item(), "md10_pe_rel": -t[3].item(), "nstep_qeq_same": bool(t[4].item() > 0.5),
+            "checked": "copyptr (QEq and FORCE halos), 10 A row counts, forces <= 1e-9, energies <= 1e-9, charges (3e-7 same stop / 1e-4), "
+                       "10 MD steps with migration: global PE <= 1e-6, atom counts", "peer_halo": res.get("peer_halo"),
+            "peer_allreduce": res.get("peer_allreduce"), "error": res.get("error")}
 
 
 def main():
@@ -140,12 +173,14 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours")
-    ap.add_argument("--mc", type=int, nargs=3, default=[18, 18, 18], help="unit-cell replication per GPU")
-    ap.add_argument("--cpu-mc", type=int, nargs=3, default=[6, 6, 6])
+    ap.add_argument("--config", default="rdx", choices=["rdx", "water", "sic", "pqeq"])
+    ap.add_argument("--mc", type=int, nargs=3, default=None, help="unit-cell replication per GPU (default: the configuration's own)")
+    ap.add_argument("--cpu-mc", type=int, nargs=3, default=None)
     ap.add_argument("--sigma", type=float, default=0.02)
-    ap.add_argument("--strong", action="store_true", help="strong scaling: --mc is the TOTAL replication, split over the GPUs")
+    ap.add_argument("--strong", action="store_true", help="strong scaling: the replication is the TOTAL, split over the GPUs")
     ap.add_argument("--no-cpu", action="store_true", help="skip the cpu_baseline leg")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the multi-GPU parity pre-flight")
     args = ap.parse_args()
     if args.impl == "reference":
         return run_reference(args)
@@ -164,11 +199,18 @@ def main():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from rxmd_b200.host.engine import Engine, MODE_MOVE
+    from rxmd_b200.host.configs import build_config
     # e2e leg: let rxg_force reuse the halo and 10 A list of the rxg_qeq that precedes it when the host hands back
     # bit-identical atoms (verified on the device); rxg_md_run does the same sharing internally
     os.environ.setdefault("RXG_FUSE_API", "1")
-    s, mc, vp = workload(args, world)
-    cfg = s.config(device=local)
+    parity = None
+    if world > 1 and not args.no_parity:
+        parity = preflight_parity(dist, rank, world, local)
+    t_setup0 = time.perf_counter()
+    s, mc, vp, cfgkw, label = build_config(args.config, mc=args.mc, nranks=world, strong=args.strong, sigma=args.sigma, only_rank=rank)
+    t_setup = time.perf_counter() - t_setup0
+    cfg = s.config(device=local, **cfgkw)
+    pq = bool(cfg.isPQEq)
     e = Engine(s, cfg, rank=rank)
     if world > 1:
         e.comm_init_torch(dist)
@@ -183,19 +225,14 @@ def main():
             dist.barrier()
             torch.cuda.synchronize()
 
-    def allmax(x):
+    def allred(x, op):
         if world == 1:
             return x
         t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dist.all_reduce(t, op=op)
         return float(t.item())
-
-    def allsum(x):
-        if world == 1:
-            return x
-        t = torch.tensor([x], dtype=torch.float64, device="cuda")
-        dist.all_reduce(t, op=dist.ReduceOp.SUM)
-        return float(t.item())
+    allmax = lambda x: allred(x, dist.ReduceOp.MAX)
+    allsum = lambda x: allred(x, dist.ReduceOp.SUM)
 
     # ---------------- device-resident stepping: `value`
     atype, pos, v, f, q = e.host_arrays(st)
@@ -219,36 +256,31 @@ def main():
     d = t_after - t_before
     cg_iters = d[17] / max(args.steps, 1)
     pe, ke, qsum, _ = e.md_observe()
+    pe_global, ke_global, q_global = allsum(float(pe[1:].sum())), allsum(ke), allsum(qsum)    # global observables (PRINTE's all-reduce)
 
-    # ---------------- roofline of the dominant kernel: the get_hsh SpMV (+ the get_gradient SpMV beside it)
-    nnz, nloc, ntot = t_after[14], t_after[15], t_after[16]
+    # ---------------- roofline of the dominant kernel: the CG's sparse product
+    nnz, nloc, ntot, nun = t_after[14], t_after[15], t_after[16], t_after[19]
     peak, peak_src = peak_hbm()
-
-    def roof(ms_sum, launches, k):
-        if launches <= 0:
-            return None
-        bytes_alg = 12.0 * nnz + 4.0 * (nloc + 1) + 8.0 * k * ntot + 40.0 * nloc
-        ach = bytes_alg / (ms_sum / launches * 1e-3) / 1e9
-        return bytes_alg, ach
     traffic = None
     tp = os.path.join(ROOT, "profiles", "spmv_traffic.json")
-    if os.path.exists(tp):
+    if os.path.exists(tp) and args.config == "rdx" and world == 1 and args.mc is None:
         try:
             traffic = json.load(open(tp)).get("dram_bytes_per_launch")
         except Exception:
             traffic = None
-    r_h = roof(d[10], d[11], 2)      # the single-pass CG gathers two vectors (hs, ht)
-    r_g = roof(d[12], d[13], 2)
     roofline = None
-    if r_h:
-        kname = ("k_spmv_rows16 (QEq CG SpMV H.(hs,ht): TMA-staged fp64 values + 16-bit column stream, 16 lanes per row)" if t_after[19] > 0
-                 else "k_spmv_rows (QEq CG SpMV H.(hs,ht): TMA-staged matrix stream, 16 lanes per row)")
-        roofline = {"kernel": kname, "bound": "hbm", "achieved": r_h[1], "peak": peak,
-                    "unit": "GB/s", "frac": r_h[1] / peak, "traffic": traffic, "peak_source": peak_src,
-                    "algorithmic_bytes_per_launch": r_h[0], "avg_launch_ms": d[10] / d[11], "launches_timed": int(d[11]),
-                    "step_share": d[10] / max(t_after[3] - t_before[3], 1e-9),
-                    "k_gradient": {"achieved": r_g[1], "frac": r_g[1] / peak, "avg_launch_ms": d[12] / d[13],
-                                   "step_share": d[12] / max(t_after[3] - t_before[3], 1e-9)} if r_g else None}
+    if d[11] > 0:
+        bytes_alg = 12.0 * nnz + 4.0 * (nloc + 1) + 8.0 * 2 * ntot + 40.0 * nloc      # SURVEY 8(d), two gathered vectors (hs, ht)
+        ach = bytes_alg / (d[10] / d[11] * 1e-3) / 1e9
+        rows = os.environ.get("RXG_SPMV") != "items"
+        roofline = {"kernel": ("k_spmv_rows (QEq CG SpMV H.(hs,ht): TMA-staged CSR stream, sub-warp per row)" if rows else
+                               "k_spmv_items (QEq CG SpMV H.(hs,ht): cell-blocked union column stream + compacted fp64 values, "
+                               "TMA ring, warp per row block)"),
+                    "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
+                    "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_alg,
+                    "stream_bytes_per_launch": (12.0 * t_after[18] if rows else 8.0 * t_after[18] + 5.0 * nun) + 16.0 * ntot + 32.0 * nloc,
+                    "avg_launch_ms": d[10] / d[11], "launches_timed": int(d[11]),
+                    "step_share": d[10] / max(t_after[3] - t_before[3], 1e-9)}
 
     # ---------------- e2e through the reference-facing entry points with pinned host arrays
     e2e = None
@@ -258,6 +290,9 @@ def main():
         h_atype, h_q = pin(nb), pin(nb)
         h_pos, h_v, h_f = pin(3, nb), pin(3, nb), pin(3, nb)
         e.qs, e.qt, e.qsfp, e.qsfv = pin(nb), pin(nb), pin(nb), pin(nb)
+        if pq:
+            e.spos = pin(3, nb)
+            e._chk(e.L.rxg_spos_download(e.h, e.natoms_resident(), e.spos.ctypes.data_as(e.L.rxg_spos_download.argtypes[2])))
         e.state_download(h_atype, h_pos, h_v, h_f, h_q)
         n = e.NATOMS
         mass = np.asarray(s.mass)
@@ -266,8 +301,7 @@ def main():
         # the host integrator (the Fortran driver's O(N) loops, src/main.F90:64-72,86-98) as compiled loops
         import numba
         # one rank per GPU shares the host's cores: give each rank's integrator its share instead of a full-size thread pool
-        ncores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
-        numba.set_num_threads(max(1, min(numba.config.NUMBA_NUM_THREADS, ncores // max(world, 1))))
+        numba.set_num_threads(max(1, min(numba.config.NUMBA_NUM_THREADS, host_cores() // max(world, 1))))
 
         @numba.njit(parallel=True, cache=False)
         def first_half(n, dt, lw2, dthm_t, atype, v, f, q, qsfp, qsfv, pos):
@@ -292,7 +326,10 @@ def main():
             first_half(n, dt, lw2, dthm_of_type, h_atype, h_v, h_f, h_q, e.qsfp, e.qsfv, h_pos)   # :64-72
             e.COPYATOMS(MODE_MOVE, [0.0, 0.0, 0.0], h_atype, h_pos, h_v, h_f, h_q)    # :75
             n = e.NATOMS
-            e.QEq(h_atype, h_pos, h_q)                                                 # :80
+            if pq:
+                e.PQEq(h_atype, h_pos, h_q)                                            # :78
+            else:
+                e.QEq(h_atype, h_pos, h_q)                                             # :80
             e.FORCE(h_atype, h_pos, h_f, h_q)                                          # :84
             second_half(n, dt, lw2, dthm_of_type, h_atype, h_v, h_f, h_q, e.qsfp, e.qsfv)         # :86-98
         host_step()
@@ -307,28 +344,32 @@ def main():
         h2d, d2h = ta[20] - tb[20], ta[21] - tb[21]     # bytes the entry points actually copied (counted in the library)
         e2e = {"value": natoms_total * ksteps / t_e2e, "unit": "atom-timesteps/s", "h2d_bytes_per_step": int(h2d / ksteps),
                "d2h_bytes_per_step": int(d2h / ksteps), "steps": ksteps, "ms_per_step": t_e2e / ksteps * 1e3,
-               "api": "Engine.COPYATOMS(MODE_MOVE) + Engine.QEq + Engine.FORCE over rxg_move/rxg_qeq/rxg_force, pinned host arrays, host integrator",
-               "host_threads_per_rank": int(numba.get_num_threads())}
+               "api": f"Engine.COPYATOMS(MODE_MOVE) + Engine.{'PQEq' if pq else 'QEq'} + Engine.FORCE over rxg_move/rxg_{'pqeq' if pq else 'qeq'}/rxg_force, "
+                      "pinned host arrays, host integrator",
+               "host_threads_per_rank": int(numba.get_num_threads()), "force_calls_reusing_qeq_list": int(ta[22] - tb[22])}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
-        cpu, _ = cpu_sample(args, 20, 2)
+        cpu, _, _ = cpu_sample(args.config, tuple(args.cpu_mc) if args.cpu_mc else CPU_MC[args.config], 8, 1, args.sigma, budget_s=25.0)
 
     if rank == 0:
-        line = {"metric": "atom-timesteps/s, RDX ReaxFF+QEq", "value": value, "unit": "atom-timesteps/s", "n_gpus": world,
+        line = {"metric": "atom-timesteps/s, RDX ReaxFF+QEq" if args.config == "rdx" else f"atom-timesteps/s, {label}",
+                "value": value, "unit": "atom-timesteps/s", "n_gpus": world,
                 "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True,
                 "scaling": "strong" if args.strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-                "config": {"workload": f"RDX conf/init.rdx.lg (LG ffield) x{mc[0]}x{mc[1]}x{mc[2]} = {int(natoms_total)} atoms, ReaxFF+QEq "
+                "config": {"workload": f"{label} x{mc[0]}x{mc[1]}x{mc[2]} = {int(natoms_total)} atoms, "
                                        f"(QEq_tol 1e-7, NMAXQEq 500, every step), NVE dt {DT_FS} fs, gaussian displacements sigma={args.sigma} A",
-                           "vprocs": list(vp), "atoms_per_gpu": nres, "parallelism": f"spatial decomposition {vp[0]}x{vp[1]}x{vp[2]}",
+                           "name": args.config, "vprocs": list(vp), "atoms_per_gpu": nres, "parallelism": f"spatial decomposition {vp[0]}x{vp[1]}x{vp[2]}",
                            "ghost_refresh": ("peer-memory windows over NVLink (cudaIpc)" if (world > 1 and e.peer_halo()) else
                                              ("ncclSend/ncclRecv" if world > 1 else "periodic images, local gather")),
                            "cg_allreduce": ("peer-memory windows, rank-ordered sum" if (world > 1 and e.peer_allreduce()) else
                                             ("ncclAllReduce" if world > 1 else "none (1 rank)")),
-                           "l2_policy": "inputs larger than L2 (QEq matrix ~5 GB per SpMV pass, >> 126 MB)",
-                           "cg_iterations_per_step": cg_iters, "nnz": nnz, "pe_per_atom": pe[1:].sum() / max(e.natoms_resident(), 1)},
+                           "l2_policy": "inputs larger than L2 (QEq matrix ~4 GB per SpMV pass, >> 126 MB)",
+                           "cg_iterations_per_step": cg_iters, "nnz": nnz, "union_entries": nun,
+                           "pe_per_atom_global": pe_global / max(natoms_total, 1), "ke_per_atom_global": ke_global / max(natoms_total, 1),
+                           "sum_q_global": q_global, "setup_seconds_per_rank": t_setup},
                 "phase_ms_per_step": {"QEq": d[4] / args.steps, "FORCE": d[5] / args.steps, "MOVE": d[6] / args.steps},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks,
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "parity": parity,
                 "gpu_launches": int(l_after - l_before)}
         print(json.dumps(line), flush=True)
     e.close()

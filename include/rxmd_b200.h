@@ -158,8 +158,9 @@ int rxg_fetch_bonds(rxg_handle h, int *nbrlist, double *BO0);
  * [4] QEq inside md_run  [5] FORCE inside md_run  [6] MOVE inside md_run  [7] md steps (count)
  * [10] get_hsh SpMV kernel total (CUDA events)  [11] its launches  [12] get_gradient SpMV kernel  [13] its launches
  * [14] nnz of the last QEq matrix (entries, without row padding)  [15] residents  [16] residents+ghosts at the last QEq
- * [17] CG iterations (count)  [18] nnz including row padding  [19] 1 if the CG streams 16-bit columns (k_spmv_rows16)
- * [20] bytes copied host->device by the entry points so far  [21] bytes copied device->host */
+ * [17] CG iterations (count)  [18] nnz including row padding  [19] entries of the SpMV's union stream (k_spmv_cells)
+ * [20] bytes copied host->device by the entry points so far  [21] bytes copied device->host
+ * [22] rxg_force calls that reused the halo and 10 A list of the preceding rxg_qeq (RXG_FUSE_API=1) */
 int rxg_timers(rxg_handle h, double *it_timer_ms);
 
 /* ---- device-resident stepping: the reference main-loop body src/main.F90:64-98
@@ -189,6 +190,10 @@ int rxg_md_velocity_affine(rxg_handle h, const double *scale, const double *shif
  * "nlp" "dDlp" "deltalp" "cell_bonded" "cell_nb" ...; returns element count through *count;
  * out may be NULL to query the count only. */
 int rxg_debug_fetch(rxg_handle h, const char *name, void *out, long long capacity_bytes, long long *count);
+/* the CG's sparse product H.(x1,x2) of the last QEq matrix as the production path launches it (get_hsh's inner sum,
+ * src/qeq.F90:290-306): x2 = {x1,x2} interleaved per atom (residents + ghosts), out4 = {sum H x1, sum H x2, the same sums over
+ * ghost columns only} per resident.  Test and timing hook (tests/test_gpu_spmv.py, tools/spmv_bench.py). */
+int rxg_debug_spmv(rxg_handle h, const double *x2, double *out4, int reps, double *ms_avg);
 /* kernels launched so far by this handle (bench.py's gpu_launches) */
 long long rxg_launch_count(rxg_handle h);
 

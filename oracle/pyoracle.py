@@ -47,8 +47,14 @@ def lib():
         L.orc_get_i32.restype = C.c_longlong
         L.orc_observe.argtypes = [C.c_void_p, dp, dp, dp, ip]
         L.orc_timers.argtypes = [C.c_void_p, dp, dp, dp]
+        L.orc_set_threads.argtypes = [C.c_int]
         _LIB = L
     return _LIB
+
+
+def set_threads(n=0):
+    """OpenMP team size of the oracle (n > 0 sets it); returns what the runtime will use."""
+    return int(lib().orc_set_threads(int(n)))
 
 
 def _dp(a):

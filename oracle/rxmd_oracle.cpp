@@ -13,6 +13,9 @@
 #include "rxmd_oracle.h"
 
 #include <chrono>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -1959,6 +1962,18 @@ int orc_observe(orc_world h, double *PE, double *KE, double *qsum, int *nstep_qe
   if (qsum) *qsum = qq;
   if (nstep_qeq) *nstep_qeq = w->R[0].nstep_qeq;
   return 0;
+}
+
+// OpenMP team size of the oracle's loops.  A launcher may export OMP_NUM_THREADS=1 (torch.distributed.run does), and the
+// runtime reads the environment only once, so bench.py sets the team size explicitly and reports what the runtime then uses.
+int orc_set_threads(int n) {
+#ifdef _OPENMP
+  if (n > 0) omp_set_num_threads(n);
+  return omp_get_max_threads();
+#else
+  (void)n;
+  return 1;
+#endif
 }
 
 int orc_timers(orc_world h, double *a, double *b, double *c) {

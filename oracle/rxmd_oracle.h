@@ -58,6 +58,8 @@ long long orc_get_i32(orc_world w, int rank, const char *name, int *out, long lo
 int orc_observe(orc_world w, double *PE, double *KE, double *qsum, int *nstep_qeq);
 /* wall-clock seconds spent inside orc_qeq / orc_force / orc_move since creation */
 int orc_timers(orc_world w, double *t_qeq, double *t_force, double *t_move);
+/* sets the OpenMP team size (n > 0) and returns the size the runtime will use */
+int orc_set_threads(int n);
 
 #ifdef __cplusplus
 }

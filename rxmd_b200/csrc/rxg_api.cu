@@ -96,7 +96,14 @@ int qeq_cg_literal(Ctx *c, int nmax, int *iters) {
   const int n = c->natoms;
   const int rgrid = cdiv((long long)c->cp[6] * 32, 256);
   const bool strict = c->strict;
+  const bool pq = c->cfg.isPQEq != 0;   // PQEq exists in the serial-order form only (validation); production PQEq is qeq_cg_single
   double4 *rowbuf = (double4 *)c->tmp;
+  double *fpq = nullptr;
+  if (pq) {
+    if (!strict) { c->err = "the literal two-product CG of PQEq exists in the serial-order validation mode only"; return RXG_ERR_STATE; }
+    fpq = c->qsl;   // free until the shell relaxation packs the final charges into it
+    if (n > 0) LAUNCH(c, k_fpqeq_strict, cdiv(n, 64), 64, 0, c->gnb, n, c->rowbeg, c->rowend, c->col, c->val, c->sps, c->d_ff, fpq);
+  }
   RXG_TRY(halo_qcopy(c, 1));
   auto harvest_grad = [&]() {   // call only after a stream sync
     if (c->grad_pending) {
@@ -114,7 +121,7 @@ int qeq_cg_literal(Ctx *c, int nmax, int *iters) {
       cudaEventRecord(c->evk[3], c->st);
       c->grad_pending = true;
     } else {
-      LAUNCH(c, k_rows_strict_grad, cdiv(n, 64), 64, 0, c->gnb.order, n, c->rowbeg, c->rowend, c->col, c->val, c->qst, c->itype, c->d_ff, c->gst);
+      LAUNCH(c, k_rows_strict_grad, cdiv(n, 64), 64, 0, c->gnb.order, n, c->rowbeg, c->rowend, c->col, c->val, c->qst, c->itype, c->d_ff, c->gst, fpq);
       LAUNCH(c, k_seq_reduce, 1, 1, 0, 2, n, rowbuf, c->hsq, c->gst, c->qst, c->d_acc);
     }
     return allreduce_acc(c, 7, 2);
@@ -131,7 +138,8 @@ int qeq_cg_literal(Ctx *c, int nmax, int *iters) {
       LAUNCH(c, k_hsh, rgrid, 256, 0, c->gnb.order, c->cp[6], n, c->rowbeg, c->rowend, c->col, c->val, c->hsq, c->gst, c->itype, c->d_ff, c->d_acc);
       cudaEventRecord(c->evk[1], c->st);
     } else {
-      LAUNCH(c, k_rows_strict_hsh, cdiv(n, 64), 64, 0, c->gnb.order, n, c->rowbeg, c->rowend, c->col, c->val, c->hsq, c->itype, c->d_ff, rowbuf);
+      if (pq) LAUNCH(c, k_rows_strict_hsh_pqeq, cdiv(n, 64), 64, 0, c->gnb, n, c->rowbeg, c->rowend, c->col, c->val, c->hsq, c->sps, c->d_ff, rowbuf);
+      else LAUNCH(c, k_rows_strict_hsh, cdiv(n, 64), 64, 0, c->gnb.order, n, c->rowbeg, c->rowend, c->col, c->val, c->hsq, c->itype, c->d_ff, rowbuf);
       LAUNCH(c, k_seq_reduce, 1, 1, 0, 0, n, rowbuf, c->hsq, c->gst, c->qst, c->d_acc);
     }
     RXG_TRY(allreduce_acc(c, 0, 5));
@@ -164,87 +172,111 @@ int qeq_cg_literal(Ctx *c, int nmax, int *iters) {
   return RXG_OK;
 }
 
-// single-pass CG (default): one sparse product per iteration, see rxg_lists_qeq.cuh
+// the CG's sparse product H.(x1,x2) -> four raw row sums per cell-order slot.  Default: the row-per-sub-warp, TMA-staged
+// kernel (k_spmv_rows) whose launch shape follows the average row length (RXG_SPMV_SHAPE=8x8|4x16|2x32 overrides it).
+// RXG_SPMV=items selects the cell-blocked kernel (k_spmv_items: union column stream, one gather of x per column of a row
+// block) -- correct and tested, but measured slower on B200, so it stays an experiment.  RXG_SPMV_STAGE=0
+// makes either kernel read the matrix straight from global memory (the path oversize rows take), RXG_SPMV_RING=<bytes>
+// shrinks the ring of k_spmv_items.
+template <int RG>
+int spmv_items_launch(Ctx *c, int slot) {
+  auto kern = k_spmv_items<RG>;
+  if (c->spmv_grid[slot] == 0) {
+    int sms = 0, optin = 0;
+    RXG_CUDA(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, c->dev));
+    RXG_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->dev));
+    cudaFuncAttributes fa;
+    RXG_CUDA(cudaFuncGetAttributes(&fa, kern));
+    c->spmv_ring = ((optin - (int)fa.sharedSizeBytes - 1024) / 128) * 128;   // one CTA per SM takes all the shared memory
+    if (c->spmv_ring_env > 0) c->spmv_ring = std::min(c->spmv_ring, c->spmv_ring_env);
+    RXG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, c->spmv_ring));
+    c->spmv_grid[slot] = std::max(1, sms);
+  }
+  const int grid = std::max(1, std::min(c->spmv_grid[slot], c->nitems));
+  LAUNCH(c, kern, grid, (SI_CONS + 1) * 32, c->spmv_ring, c->items, c->nitems, c->ucol, c->umask, c->val, c->xs, (double4 *)c->tmp, c->d_acc, c->spmv_ring,
+         c->spmv_stage);
+  return RXG_OK;
+}
+int spmv_launch(Ctx *c) {
+  const int n = c->natoms, nt = c->cp[6];
+  double4 *rowsum = (double4 *)c->tmp;
+  if (nt <= 0) return RXG_OK;
+  if (c->spmv_kind == 0) {
+    if (c->nitems < 0) {   // first product after a list build: the item count left by the fill pass
+      RXG_CUDA(cudaMemcpyAsync(c->h_int + 17, c->d_flag + 17, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+      RXG_CUDA(cudaStreamSynchronize(c->st));
+      c->nitems = c->h_int[17];
+    }
+    if (c->nitems == 0) return RXG_OK;
+    return c->spmv_rg == 4 ? spmv_items_launch<4>(c, 0) : spmv_items_launch<2>(c, 1);
+  }
+  const double avgrow = (double)c->nnz_real / (double)std::max(n, 1);
+  int shape = c->spmv_shape;
+  if (shape == 0) shape = avgrow <= 160.0 ? 1 : (avgrow > 440.0 ? 3 : 2);
+  if (shape == 1)   // short rows (sparse systems such as the SiC nanoparticles, 117 entries): 8 rows per CTA, 8 lanes per row
+    LAUNCH(c, (k_spmv_rows<8, 8, 256>), cdiv(nt, 8), 64, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->xs, rowsum, c->d_acc, c->spmv_stage);
+  else if (shape == 3)   // 12.5 A lists (PQEq, 1060 entries): two long rows per CTA, a full warp per row
+    LAUNCH(c, (k_spmv_rows<2, 32, 1216>), cdiv(nt, 2), 64, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->xs, rowsum, c->d_acc, c->spmv_stage);
+  else   // 10 A lists: 4 rows per CTA, 16 lanes per row
+    LAUNCH(c, (k_spmv_rows<4, 16>), cdiv(nt, 4), 64, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->xs, rowsum, c->d_acc, c->spmv_stage);
+  return RXG_OK;
+}
+
+// single-pass CG (default): one sparse product per iteration, see rxg_lists_qeq.cuh.  Control flow (stop rule, real(4) step
+// lengths) runs on the device (k_cg_ctrl); the host enqueues CG_BATCH iterations at a time and reads the stop flag once per
+// batch -- iterations enqueued past the stop return at their first instruction.
+constexpr int CG_BATCH = 4;
 int qeq_cg_single(Ctx *c, int nmax, int *iters) {
   const int n = c->natoms;
-  const int rgrid = cdiv((long long)c->cp[6] * 32, 256);
   RXG_TRY(halo_refresh(c, 1, 0));   // ghost qs,qt (MODE_QCOPY1, src/qeq.F90:86)
   LAUNCH(c, k_to_slots, cdiv(c->cp[6], 256), 256, 0, c->cp[6], c->gnb.order, c->qst, c->xs);
-  const int tgrid = cdiv(c->cp[6], SP_ROWS);
-  const bool tma = !(getenv("RXG_SPMV_NOTMA") && getenv("RXG_SPMV_NOTMA")[0] == '1');
   double4 *rowsum = (double4 *)c->tmp;
-  const double avgrow = (double)c->nnz_real / (double)std::max(n, 1);   // picks the launch shape of the SpMV
-  auto spmv_rows = [&]() {
-    const int nt = c->cp[6];
-    if (c->have_col16) {   // RXG_COL16=1
-      LAUNCH(c, (k_spmv_rows16<4, 16>), cdiv(nt, 4), 64, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col16, c->cbase, c->col, c->val, c->xs, rowsum);
-    } else if (avgrow <= 160.0)   // short rows (sparse systems such as the SiC nanoparticles, 117 entries): 8 rows per CTA, 8 lanes per row.
-      // Measured at 3.94 M SiC atoms: 1.78 ms vs 2.56 ms with the 4x16 shape; 16x8, 8x4, 16x4, 4x8 are slower.  A CTA whose
-      // 8 rows do not fit the 2048 staged entries reads them straight from HBM (same result).
-      LAUNCH(c, (k_spmv_rows<8, 8, 256>), cdiv(nt, 8), 64, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->xs, rowsum);
-    else if (avgrow > 440.0)   // 12.5 A lists (PQEq, 1060 entries): two long rows per CTA, a full warp per row (5.8 -> 4.7 ms at 1.43 M atoms)
-      LAUNCH(c, (k_spmv_rows<2, 32, 1216>), cdiv(nt, 2), 64, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->xs, rowsum);
-    else   // 10 A lists: 4 rows per CTA, 16 lanes per row (measured: 1.03 ms; 32 lanes 1.09, 8 lanes 1.29, 8 or 2 rows slower)
-      LAUNCH(c, (k_spmv_rows<4, 16>), cdiv(nt, 4), 64, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->xs, rowsum);
-  };
   const int dgrid = cdiv(c->cp[6], 256);
-  (void)tgrid;
-  if (c->have_col16) {   // did every offset fit 15 bits?  (k_col16 ran right after the list fill)
-    RXG_CUDA(cudaMemcpyAsync(c->h_int + 7, c->d_flag + 7, sizeof(int), cudaMemcpyDeviceToHost, c->st));
-    RXG_CUDA(cudaStreamSynchronize(c->st));
-    if (c->h_int[7]) c->have_col16 = false;
-  }
   const bool pq = c->cfg.isPQEq != 0;   // PQEq: same CG, other gradient constant and Est (rxg_pqeq.cuh)
-  if (pq) {
-    spmv_rows();
+  RXG_CUDA(cudaMemsetAsync(c->d_acc + ACC_DONE, 0, sizeof(double), c->st));
+  RXG_TRY(spmv_launch(c));
+  if (pq)
     LAUNCH(c, (k_cg_dots_pqeq<true>), dgrid, 256, 0, c->gnb.order, c->cp[6], n, rowsum, c->xs, c->q, c->gst, c->tst, c->ust, c->wst, c->itype, c->d_ff,
            c->prow, c->pcs, c->sps, c->d_acc);
-  } else if (tma) {
-    spmv_rows();
+  else
     LAUNCH(c, (k_cg_dots<true>), dgrid, 256, 0, c->gnb.order, c->cp[6], n, rowsum, c->xs, c->q, c->gst, c->tst, c->ust, c->wst, c->itype, c->d_ff, c->d_acc);
-  } else
-    LAUNCH(c, (k_spmv1<true>), rgrid, 256, 0, c->gnb.order, c->cp[6], n, c->rowbeg, c->rowend, c->col, c->val, c->xs, c->qst, c->q, c->gst, c->tst, c->ust, c->wst,
-           c->itype, c->d_ff, c->d_acc);
   RXG_TRY(allreduce_acc(c, 7, 2));
-  LAUNCH(c, k_h_from_g2, cdiv(n, 256), 256, 0, n, c->gst, c->hst, c->xs, c->gnb.slot_of);
+  LAUNCH(c, k_h_from_g2, cdiv(std::max(n, 1), 256), 256, 0, n, c->gst, c->hst, c->xs, c->gnb.slot_of, c->d_acc);
   RXG_TRY(halo_refresh(c, 3, 0));   // ghost hs,ht (MODE_QCOPY2, :93)
-  double GEst2 = 1e99;
-  int it;
-  for (it = 0; it < nmax; it++) {
-    LAUNCH(c, k_clear_iter, 1, 1, 0, c->d_acc);
-    cudaEventRecord(c->evk[0], c->st);
-    if (tma || pq)
-      spmv_rows();
-    else
-      LAUNCH(c, (k_spmv1<false>), rgrid, 256, 0, c->gnb.order, c->cp[6], n, c->rowbeg, c->rowend, c->col, c->val, c->xs, c->qst, c->q, c->gst, c->tst, c->ust, c->wst,
-             c->itype, c->d_ff, c->d_acc);
-    cudaEventRecord(c->evk[1], c->st);
-    if (pq)
-      LAUNCH(c, (k_cg_dots_pqeq<false>), dgrid, 256, 0, c->gnb.order, c->cp[6], n, rowsum, c->xs, c->q, c->gst, c->tst, c->ust, c->wst, c->itype, c->d_ff,
-             c->prow, c->pcs, c->sps, c->d_acc);
-    else if (tma)
-      LAUNCH(c, (k_cg_dots<false>), dgrid, 256, 0, c->gnb.order, c->cp[6], n, rowsum, c->xs, c->q, c->gst, c->tst, c->ust, c->wst, c->itype, c->d_ff, c->d_acc);
-    RXG_TRY(allreduce_acc(c, 0, 5));
-    RXG_CUDA(cudaMemcpyAsync(c->h_acc, c->d_acc, sizeof(double) * 5, cudaMemcpyDeviceToHost, c->st));
+  int launched = 0, it = 0;
+  bool done = false;
+  while (!done && launched < nmax) {
+    const int kb = std::min(CG_BATCH, nmax - launched);
+    for (int j = 0; j < kb; j++) {
+      cudaEventRecord(c->evs[2 * j], c->st);
+      RXG_TRY(spmv_launch(c));
+      cudaEventRecord(c->evs[2 * j + 1], c->st);
+      if (pq)
+        LAUNCH(c, (k_cg_dots_pqeq<false>), dgrid, 256, 0, c->gnb.order, c->cp[6], n, rowsum, c->xs, c->q, c->gst, c->tst, c->ust, c->wst, c->itype, c->d_ff,
+               c->prow, c->pcs, c->sps, c->d_acc);
+      else
+        LAUNCH(c, (k_cg_dots<false>), dgrid, 256, 0, c->gnb.order, c->cp[6], n, rowsum, c->xs, c->q, c->gst, c->tst, c->ust, c->wst, c->itype, c->d_ff, c->d_acc);
+      RXG_TRY(allreduce_acc(c, 0, 5));   // (PQEq's ghost-column sums acc[12..15] are per-rank quantities and stay local)
+      LAUNCH(c, k_cg_ctrl, 1, 1, 0, c->d_acc, c->cfg.QEq_tol, pq ? 1 : 0);
+      LAUNCH(c, k_cg_update1, cdiv(std::max(n, 1), 256), 256, 0, n, c->hst, c->tst, c->ust, c->qst, c->gst, c->wst, c->d_acc);
+      RXG_TRY(allreduce_acc(c, 5, 4));
+      LAUNCH(c, k_cg_update2, cdiv(std::max(n, 1), 256), 256, 0, n, c->qst, c->gst, c->hst, c->xs, c->gnb.slot_of, c->q, c->d_acc);
+      RXG_TRY(halo_refresh(c, 3, 0));
+    }
+    RXG_CUDA(cudaMemcpyAsync(c->h_acc + ACC_GEST2, c->d_acc + ACC_GEST2, sizeof(double) * 5, cudaMemcpyDeviceToHost, c->st));
     if (c->peer_ok) RXG_CUDA(cudaMemcpyAsync(c->h_int + 3, c->d_flag + 3, sizeof(int), cudaMemcpyDeviceToHost, c->st));
     RXG_CUDA(cudaStreamSynchronize(c->st));
     if (c->peer_ok && c->h_int[3]) { c->err = "peer halo: a neighbour's ghost values did not arrive (timeout)"; return RXG_ERR_NCCL; }
-    float ms = 0;
-    cudaEventElapsedTime(&ms, c->evk[0], c->evk[1]);
-    c->timers_ms[10] += ms;
-    c->timers_ms[11] += 1;
-    double GEst1 = c->h_acc[0];
-    if (0.5 * (std::fabs(GEst2) + std::fabs(GEst1)) < c->cfg.QEq_tol) break;                    // src/qeq.F90:114
-    if (std::fabs(GEst2) > 0.0 && std::fabs(GEst1 / GEst2 - 1.0) < c->cfg.QEq_tol) break;      // src/qeq.F90:115
-    GEst2 = GEst1;
-    float lmin_s = (float)(c->h_acc[3] / c->h_acc[1]);   // real(4) :: lmin, src/qeq.F90:23,133
-    float lmin_t = (float)(c->h_acc[4] / c->h_acc[2]);
-    if (pq) LAUNCH(c, k_roll_g_pqeq, 1, 1, 0, c->d_acc, lmin_s, lmin_t);
-    else LAUNCH(c, k_roll_g, 1, 1, 0, c->d_acc);
-    LAUNCH(c, k_cg_update1, cdiv(n, 256), 256, 0, n, lmin_s, lmin_t, c->hst, c->tst, c->ust, c->qst, c->gst, c->wst, c->d_acc);
-    RXG_TRY(allreduce_acc(c, 5, 4));
-    LAUNCH(c, k_cg_update2, cdiv(n, 256), 256, 0, n, c->qst, c->gst, c->hst, c->xs, c->gnb.slot_of, c->q, c->d_acc);
-    RXG_TRY(halo_refresh(c, 3, 0));
+    done = c->h_acc[ACC_DONE] != 0.0;
+    it = (int)c->h_acc[ACC_NITER];
+    for (int j = 0; j < kb; j++) {   // sparse products that did work: iterations 0..it (the one that met the stop rule included)
+      if (launched + j > it) break;
+      float ms = 0;
+      cudaEventElapsedTime(&ms, c->evs[2 * j], c->evs[2 * j + 1]);
+      c->timers_ms[10] += ms;
+      c->timers_ms[11] += 1;
+    }
+    launched += kb;
   }
   // the reference converts positions to normalised coordinates and back in every COPYATOMS call: QCOPY1 + QCOPY2
   // before the loop and two per completed iteration (src/qeq.F90:86,93,153,164); apply them in one launch
@@ -292,7 +324,7 @@ int qeq_device(Ctx *c, bool for_force = false) {
     LAUNCH(c, k_pqeq_rows, rgrid, 256, 0, c->gnb, nt, n, c->rowbeg, c->rowend, c->col, c->val, c->sps, c->d_ff, c->prow, c->pcs, c->d_acc, c->d_flag + 6);
   }
   int it = 0;
-  if (!pq && (c->strict || c->qeq_mode == 1)) RXG_TRY(qeq_cg_literal(c, nmax, &it));
+  if (c->strict || (!pq && c->qeq_mode == 1)) RXG_TRY(qeq_cg_literal(c, nmax, &it));
   else RXG_TRY(qeq_cg_single(c, nmax, &it));
   if (pq && nt > 0) {   // update_shell_positions, src/pqeq.F90:171,187-259, with the final charges of residents and ghosts
     RXG_TRY(halo_refresh(c, 4, 0));
@@ -308,7 +340,7 @@ int qeq_device(Ctx *c, bool for_force = false) {
   c->nstep_qeq = it;
   c->timers_ms[14] = (double)c->nnz_real;
   c->timers_ms[18] = (double)c->nnz;
-  c->timers_ms[19] = c->have_col16 ? 1.0 : 0.0;
+  c->timers_ms[19] = (double)c->nunion;
   c->timers_ms[15] = n;
   c->timers_ms[16] = c->cp[6];
   c->timers_ms[17] += it;
@@ -355,8 +387,14 @@ int rxg_create(const rxg_config *cfg, rxg_handle *out) {
   c->fuse = !(nf && nf[0] == '1');
   const char *fa = getenv("RXG_FUSE_API");
   c->fuse_api = fa && fa[0] == '1';
-  const char *c16 = getenv("RXG_COL16");
-  c->use_col16 = c16 && c16[0] == '1';
+  const char *sk = getenv("RXG_SPMV");
+  c->spmv_kind = (sk && std::string(sk) == "items") ? 0 : 1;   // 1: k_spmv_rows (default), 0: k_spmv_items (experiment)
+  const char *ss = getenv("RXG_SPMV_SHAPE");
+  c->spmv_shape = !ss ? 0 : (std::string(ss) == "8x8" ? 1 : (std::string(ss) == "4x16" ? 2 : (std::string(ss) == "2x32" ? 3 : 0)));
+  const char *sg = getenv("RXG_SPMV_STAGE");
+  c->spmv_stage = !(sg && sg[0] == '0');
+  const char *sl = getenv("RXG_SPMV_RING");   // ring size of k_spmv_items in bytes (default: all the shared memory of an SM)
+  c->spmv_ring_env = sl ? atoi(sl) : 0;
   const char *tp = getenv("RXG_QEQ_TWOPASS");
   c->qeq_mode = (tp && tp[0] == '1') ? 1 : 0;
   *out = c;   // returned even on failure so that rxg_last_error can be read
@@ -378,6 +416,7 @@ int rxg_create(const rxg_config *cfg, rxg_handle *out) {
   RXG_CUDA(cudaEventCreate(&c->evm0));
   RXG_CUDA(cudaEventCreate(&c->evm1));
   for (int k = 0; k < 4; k++) RXG_CUDA(cudaEventCreate(&c->evk[k]));
+  for (int k = 0; k < 2 * CG_BATCH; k++) RXG_CUDA(cudaEventCreate(&c->evs[k]));
   const size_t NB = c->NB, NS = NB * (size_t)c->MAXN;
   RXG_TRY(dalloc(c, &c->pos, 3 * NB)); RXG_TRY(dalloc(c, &c->v, 3 * NB)); RXG_TRY(dalloc(c, &c->f, 3 * NB)); RXG_TRY(dalloc(c, &c->fsl, 3 * NB));
   RXG_TRY(dalloc(c, &c->atype, NB)); RXG_TRY(dalloc(c, &c->q, NB)); RXG_TRY(dalloc(c, &c->qsfp, NB)); RXG_TRY(dalloc(c, &c->qsfv, NB));
@@ -394,7 +433,8 @@ int rxg_create(const rxg_config *cfg, rxg_handle *out) {
   RXG_TRY(dalloc(c, &c->xs, NB)); RXG_TRY(dalloc(c, &c->pqa, NB)); RXG_TRY(dalloc(c, &c->pqs, NB)); RXG_TRY(dalloc(c, &c->tgs, NB));
   RXG_TRY(dalloc(c, &c->nbrcnt, NB)); RXG_TRY(dalloc(c, &c->nbrpad, NS)); RXG_TRY(dalloc(c, &c->bptr, NB + 2));
   RXG_TRY(dalloc(c, &c->rowoff, NB + 2)); RXG_TRY(dalloc(c, &c->rowbeg, NB + 2)); RXG_TRY(dalloc(c, &c->rowend, NB + 2));
-  RXG_TRY(dalloc(c, &c->rowcnt, NB + 2));
+  RXG_TRY(dalloc(c, &c->rowcnt, NB + 2)); RXG_TRY(dalloc(c, &c->ucnt, NB + 2)); RXG_TRY(dalloc(c, &c->uoff, NB + 2));
+  RXG_TRY(dalloc(c, &c->items, NB + 2));
   RXG_TRY(ensure_bond_capacity(c, 8 * (long long)NB));
   RXG_TRY(dalloc(c, &c->delta, NB)); RXG_TRY(dalloc(c, &c->deltap1, NB)); RXG_TRY(dalloc(c, &c->deltap2, NB));
   RXG_TRY(dalloc(c, &c->nlp, NB)); RXG_TRY(dalloc(c, &c->dDlp, NB)); RXG_TRY(dalloc(c, &c->deltalp, NB));
@@ -604,7 +644,7 @@ int rxg_destroy(rxg_handle h) {
     cudaStreamSynchronize(c->st);
     for (void *p : c->allocs) cudaFree(p);
     for (void *p : c->ff_allocs) cudaFree(p);
-    for (void *p : {(void *)c->col, (void *)c->val, (void *)c->col16, (void *)c->cbase, (void *)c->d_blk, (void *)c->d_blk64, (void *)c->d_runs, (void *)c->d_ff})
+    for (void *p : {(void *)c->col, (void *)c->val, (void *)c->ucol, (void *)c->umask, (void *)c->d_blk, (void *)c->d_blk64, (void *)c->d_runs, (void *)c->d_ff})
       if (p) cudaFree(p);
     for (int k = 0; k < 2; k++) { if (c->sbuf[k]) cudaFree(c->sbuf[k]); if (c->rbuf[k]) cudaFree(c->rbuf[k]); }
     for (size_t r = 0; r < c->peer.size(); r++)
@@ -709,6 +749,7 @@ int rxg_force(rxg_handle h, const int *natoms, const double *atype, double *pos,
     RXG_CUDA(cudaMemcpyAsync(c->h_int + 15, c->d_flag + 15, sizeof(int), cudaMemcpyDeviceToHost, c->st));
     RXG_CUDA(cudaStreamSynchronize(c->st));
     reuse = c->h_int[15] == 0;
+    if (reuse) c->timers_ms[22] += 1;   // rxg_force calls that reused the halo and list of the preceding rxg_qeq
   }
   c->natoms = n;
   if (!reuse) {
@@ -948,6 +989,46 @@ int rxg_md_velocity_affine(rxg_handle h, const double *scale, const double *shif
   return RXG_OK;
 }
 
+// ---- kernel-level check and timing of the CG's sparse product (tests/test_gpu_spmv.py, tools/spmv_bench.py) -------
+// x2: {x1, x2} per atom (residents and ghosts of the last QEq, interleaved, by ATOM index); out4: {a, b, ghost a, ghost b}
+// per resident by atom index, a = sum_j H_ij x1_j etc. -- exactly what the production launch (spmv_launch, honouring the
+// RXG_SPMV* switches) hands to k_cg_dots.  reps > 1 repeats the launch and returns the average CUDA-event time.
+int rxg_debug_spmv(rxg_handle h, const double *x2, double *out4, int reps, double *ms_avg) {
+  Ctx *c = (Ctx *)h;
+  RXG_TRY(check_ready(c, c ? c->natoms : -1));
+  if (!c->list_is_qeq || c->nnz <= 0) { c->err = "rxg_debug_spmv: no QEq matrix on the device (call rxg_qeq first)"; return RXG_ERR_STATE; }
+  const int n = c->natoms, nt = c->cp[6];
+  double2 *stage = (double2 *)(c->tmp + 8 * (size_t)c->NB);   // rowsum occupies tmp[0 .. 4*NB)
+  if (x2) {
+    RXG_CUDA(cudaMemcpyAsync(stage, x2, sizeof(double2) * nt, cudaMemcpyHostToDevice, c->st));
+    LAUNCH(c, k_to_slots, cdiv(nt, 256), 256, 0, nt, c->gnb.order, stage, c->xs);
+  }
+  RXG_CUDA(cudaMemsetAsync(c->d_acc + ACC_DONE, 0, sizeof(double), c->st));
+  RXG_CUDA(cudaMemsetAsync(c->tmp, 0, sizeof(double4) * nt, c->st));
+  if (reps < 1) reps = 1;
+  RXG_TRY(spmv_launch(c));   // warm-up / the checked launch
+  cudaEventRecord(c->ev0, c->st);
+  for (int r = 1; r < reps; r++) RXG_TRY(spmv_launch(c));
+  cudaEventRecord(c->ev1, c->st);
+  RXG_CUDA(cudaStreamSynchronize(c->st));
+  if (ms_avg) {
+    float ms = 0;
+    if (reps > 1) cudaEventElapsedTime(&ms, c->ev0, c->ev1);
+    *ms_avg = reps > 1 ? ms / (reps - 1) : 0.0;
+  }
+  if (out4) {
+    std::vector<double4> rs(nt);
+    std::vector<int> ord(nt);
+    RXG_CUDA(cudaMemcpy(rs.data(), c->tmp, sizeof(double4) * nt, cudaMemcpyDeviceToHost));
+    RXG_CUDA(cudaMemcpy(ord.data(), c->gnb.order, sizeof(int) * nt, cudaMemcpyDeviceToHost));
+    for (int s = 0; s < nt; s++) {
+      const int i = ord[s];
+      if (i < n) { out4[4 * (size_t)i] = rs[s].x; out4[4 * (size_t)i + 1] = rs[s].y; out4[4 * (size_t)i + 2] = rs[s].z; out4[4 * (size_t)i + 3] = rs[s].w; }
+    }
+  }
+  return RXG_OK;
+}
+
 // ---- introspection for the parity tests ----------------------------------------------------------------------
 int rxg_debug_fetch(rxg_handle h, const char *name, void *out, long long cap, long long *count) {
   Ctx *c = (Ctx *)h;
@@ -1000,6 +1081,12 @@ int rxg_debug_fetch(rxg_handle h, const char *name, void *out, long long cap, lo
   else if (s == "rowend") dev(c->rowend, nat, 8);
   else if (s == "col") dev(c->col, c->nnz, 4);   // converted to atom indices below
   else if (s == "val") dev(c->val, c->nnz, 8);
+  else if (s == "ucol") dev(c->ucol, c->nunion, 4);
+  else if (s == "umask") dev(c->umask, c->nunion, 1);
+  else if (s == "uoff") dev(c->uoff, n6 + 1, 8);
+  else if (s == "rowoff") dev(c->rowoff, n6 + 1, 8);
+  else if (s == "order_nb") dev(c->gnb.order, n6, 4);
+  else if (s == "acc") dev(c->d_acc, 64, 8);
   else if (s == "BO0") dev(c->BO[0], NS, 8);
   else if (s == "BO1") dev(c->BO[1], NS, 8);
   else if (s == "BO2") dev(c->BO[2], NS, 8);

@@ -182,9 +182,16 @@ struct Ctx {
   int *rowcnt = nullptr;
   int *col = nullptr;            // [nnz_cap]
   double *val = nullptr;         // [nnz_cap] hessian (QEq list only)
-  unsigned short *col16 = nullptr;   // [nnz_cap] 16-bit column stream of the CG SpMV (k_col16): offset from cbase[k>>4], bit 15 = ghost
-  int *cbase = nullptr;              // [nnz_cap/16+2]
-  bool use_col16 = false, have_col16 = false;   // RXG_COL16=1 (see k_col16)
+  // union stream of the cell-blocked CG SpMV (k_spmv_cells): per block of <= 8 consecutive rows of a cell, the columns taken by
+  // at least one of the rows (ucol) with the set of rows that take each (umask); blocks start at uoff[first slot of the block]
+  int *ucnt = nullptr;               // [NB+2] padded entry count of the block that starts at a slot (0 elsewhere)
+  long long *uoff = nullptr;         // [NB+2] exclusive scan of ucnt
+  int *ucol = nullptr;               // [un_cap]
+  unsigned char *umask = nullptr;    // [un_cap]
+  long long un_cap = 0, nunion = 0;
+  struct SpItem *items = nullptr;    // [NB] work items of k_spmv_items, written by the list's fill pass
+  int nitems = 0, spmv_rg = 4;       // rows per item (4, or 2 for lists with rows longer than 480 entries)
+  int spmv_kind = 0, spmv_shape = 0, spmv_stage = 1, spmv_ring = 0, spmv_ring_env = 0, spmv_grid[2] = {0, 0};   // RXG_SPMV / _SHAPE / _STAGE / _RING (rxg_api.cu)
   long long nnz_cap = 0, nnz = 0, nnz_real = 0;   // nnz counts the row padding, nnz_real does not
   bool list_is_qeq = false;
   int maxrow = 0;                // longest row of the current list (entries)
@@ -216,6 +223,7 @@ struct Ctx {
   bool strict = false;      // RXG_STRICT_ORDER=1: serial-order, FMA-free CG for bit-level validation (small systems)
   double timers_ms[30] = {0};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm0 = nullptr, evm1 = nullptr, evk[4] = {nullptr, nullptr, nullptr, nullptr};
+  cudaEvent_t evs[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // SpMV timing, one pair per iteration of a CG batch
   bool grad_pending = false;
   // ---- staging (pinned) ------------------------------------------------------------------------------------
 };

@@ -89,14 +89,31 @@ constexpr int PL_WARPS = 8, PL_MAXRUNS = 128;
 // Row alignment in entries (run-time argument `ralign` of k_pairlist): 4 by default (32 B of val, 16 B of col: the
 // bulk-copy granularity); 16 with the optional 16-bit column stream, whose 16-entry blocks must not straddle two rows.
 constexpr int COL_GHOST = (int)0x80000000, COL_MASK = 0x7fffffff;
+// One work item of the CG's sparse product (k_spmv_items): up to `rg` consecutive rows of a block of <= 8 rows of one cell.
+// Its values are one contiguous span of `val` (rows lie in HBM in cell order), its columns the block's union stream.
+struct __align__(16) SpItem {
+  long long voff;   // first value of the item's first row
+  long long uoff;   // first entry of the block's union stream
+  int un;           // entries of the union stream (padded to 16)
+  int slot0;        // cell-order slot of the item's first row
+  int nrp;          // rows of the item (1..rg)
+  int vlen;         // values in the span (rows padded to 4)
+  int rshift;       // position of the item's first row in the block's 8-bit row sets
+  int rs[4];        // start of each row relative to voff
+  int pad[3];
+};
+static_assert(sizeof(SpItem) == 64, "SpItem is one 64-byte record");
 // MODE 0: FORCE list, 1: QEq list, 2: both at once (FORCE predicate; hessian = 0 where only the QEq predicate fails)
-template <int MODE, bool FILL>
+template <int MODE, bool FILL, bool UNION>
 __global__ void __launch_bounds__(PL_WARPS * 32) k_pairlist(DevGrid g, const DevFF *__restrict__ ffp, const int *__restrict__ runs,
                                                             int nruns, int natoms, int ncell_res, int *__restrict__ slotcnt,
                                                             const long long *__restrict__ rowoff, long long *__restrict__ rowbeg,
                                                             long long *__restrict__ rowend, int *__restrict__ col,
                                                             double *__restrict__ val, int maxrow, int *__restrict__ ovf,
-                                                            unsigned long long *__restrict__ nnz_real, int ralign) {
+                                                            unsigned long long *__restrict__ nnz_real, int ralign,
+                                                            int *__restrict__ ucnt, const long long *__restrict__ uoff,
+                                                            int *__restrict__ ucol, unsigned char *__restrict__ umask,
+                                                            SpItem *__restrict__ items, int *__restrict__ nitems, int rg) {
   __shared__ int sh_s[PL_WARPS][PL_MAXRUNS];       // first slot of each stencil run
   __shared__ int sh_p[PL_WARPS][PL_MAXRUNS + 1];   // exclusive prefix of the run lengths: position of each run in the flat candidate sequence
   __shared__ double4 sh_a[PL_WARPS][32];
@@ -120,6 +137,18 @@ __global__ void __launch_bounds__(PL_WARPS * 32) k_pairlist(DevGrid g, const Dev
     const bool mine = mi < natoms;           // a ghost inside a resident cell owns no row (cannot happen after MOVE)
     long long mybase = (FILL && lane < nb) ? rowoff[myslot] : 0;
     int mycnt = 0;
+    // union stream of the CG SpMV (k_spmv_cells): per block of up to 8 consecutive rows of this cell, the candidates accepted
+    // by at least one of them, in candidate order, with the 8-bit set of accepting rows.  ub* = running entry count of the
+    // (up to four) blocks of this batch of 32 rows; identical on every lane.
+    int ub0 = 0, ub1 = 0, ub2 = 0, ub3 = 0;
+    long long uw0 = 0, uw1 = 0, uw2 = 0, uw3 = 0;
+    if (UNION && FILL) {
+      uw0 = uoff[ab];
+      if (nb > 8) uw1 = uoff[ab + 8];
+      if (nb > 16) uw2 = uoff[ab + 16];
+      if (nb > 24) uw3 = uoff[ab + 24];
+    }
+    int lastcol = ab;
     __syncwarp();
     for (int rb = 0; rb < nruns; rb += PL_MAXRUNS) {
       const int nr = min(PL_MAXRUNS, nruns - rb);
@@ -165,6 +194,7 @@ __global__ void __launch_bounds__(PL_WARPS * 32) k_pairlist(DevGrid g, const Dev
         if (have) o = g.sorted[cslot];
         const int jt = rec_type(o.w);
         const int cval = cslot | ((have && rec_index(o.w) >= natoms) ? COL_GHOST : 0);
+        unsigned um = 0;   // rows of this batch whose list takes this lane's candidate
         for (int a = 0; a < nb; a++) {
           const double4 at = sh_a[wid][a];
           const double dr2 = dist2_rn(sub_rn(at.x, o.x), sub_rn(at.y, o.y), sub_rn(at.z, o.z));
@@ -185,9 +215,77 @@ __global__ void __launch_bounds__(PL_WARPS * 32) k_pairlist(DevGrid g, const Dev
             }
           }
           if (lane == a) mycnt += __popc(mask);
+          // (MODE 2: the row also holds the pairs that pass FORCE's fp64 test only; their hessian is 0 and they keep their
+          // place in the value stream, so the union must list them too)
+          if (UNION && acc) um |= 1u << a;
+        }
+        if (UNION) {
+#define RXG_UBLOCK(B, UB, UW)                                                          \
+          if (nb > 8 * B) {                                                            \
+            const unsigned m8 = (um >> (8 * B)) & 0xffu;                               \
+            const unsigned bal = __ballot_sync(0xffffffffu, m8 != 0);                  \
+            if (FILL && m8) {                                                          \
+              const long long w = UW + UB + __popc(bal & ((1u << lane) - 1u));         \
+              ucol[w] = cval;                                                          \
+              umask[w] = (unsigned char)m8;                                            \
+            }                                                                          \
+            UB += __popc(bal);                                                         \
+          }
+          RXG_UBLOCK(0, ub0, uw0) RXG_UBLOCK(1, ub1, uw1) RXG_UBLOCK(2, ub2, uw2) RXG_UBLOCK(3, ub3, uw3)
+#undef RXG_UBLOCK
+          if (FILL) {   // a valid column for the padding of the union stream
+            const unsigned any = __ballot_sync(0xffffffffu, um != 0);
+            if (any) lastcol = __shfl_sync(0xffffffffu, cval, 31 - __clz(any)) & COL_MASK;
+          }
         }
       }
       __syncwarp();
+    }
+    if (UNION) {   // close the union blocks: counts padded to 16 entries (64 B of ucol, 16 B of umask: bulk-copy granularity)
+      const int ubs[4] = {ub0, ub1, ub2, ub3};
+      const long long uws[4] = {uw0, uw1, uw2, uw3};
+#pragma unroll
+      for (int B = 0; B < 4; B++) {
+        if (nb > 8 * B) {
+          const int padded = (ubs[B] + 15) & ~15;
+          if (!FILL) { if (lane == 0) ucnt[ab + 8 * B] = padded; }
+          else if (lane < padded - ubs[B]) { ucol[uws[B] + ubs[B] + lane] = lastcol; umask[uws[B] + ubs[B] + lane] = 0; }
+        }
+      }
+      if (FILL) {
+        // work items of the SpMV: lane t describes pass (t % ppb) of block (t / ppb) of this batch of <= 32 rows
+        const int ppb = 8 / rg, B = lane / ppb, r0 = (lane % ppb) * rg;
+        const int row0 = 8 * B + r0;                       // first row of the item within the batch
+        const bool valid = row0 < nb && B < 4;
+        const int nrB = min(8, nb - 8 * B);                // rows of the block
+        const int nrp = valid ? min(rg, nrB - r0) : 0;
+        const int plen = (lane < nb && mine) ? ((mycnt + ralign - 1) & ~(ralign - 1)) : 0;
+        SpItem I;
+        I.voff = __shfl_sync(0xffffffffu, mybase, valid ? row0 : 0);
+        I.uoff = B == 0 ? uw0 : (B == 1 ? uw1 : (B == 2 ? uw2 : uw3));
+        I.un = ((B == 0 ? ub0 : (B == 1 ? ub1 : (B == 2 ? ub2 : ub3))) + 15) & ~15;
+        I.slot0 = ab + row0; I.nrp = nrp; I.rshift = r0;
+        I.pad[0] = I.pad[1] = I.pad[2] = 0;
+        int vlen = 0;
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          const int src = (valid && j < nrp) ? row0 + j : 0;
+          const long long bj = __shfl_sync(0xffffffffu, mybase, src);
+          const int lj = __shfl_sync(0xffffffffu, plen, src);
+          I.rs[j] = (valid && j < nrp) ? (int)(bj - I.voff) : 0;
+          if (valid && j < nrp) vlen = (int)(bj - I.voff) + lj;
+        }
+        I.vlen = vlen;
+        const unsigned bal = __ballot_sync(0xffffffffu, valid);
+        int base = 0;
+        if (lane == 0) base = atomicAdd(nitems, __popc(bal));
+        base = __shfl_sync(0xffffffffu, base, 0);
+        if (valid) {
+          const int4 *src = reinterpret_cast<const int4 *>(&I);
+          int4 *dst = reinterpret_cast<int4 *>(items + base + __popc(bal & ((1u << lane) - 1u)));
+          dst[0] = src[0]; dst[1] = src[1]; dst[2] = src[2]; dst[3] = src[3];
+        }
+      }
     }
     if (!FILL) {   // exact entry count (without row padding): the algorithmic-bytes figure of the roofline uses it;
                    // longest row: picks the SpMV launch shape
@@ -237,30 +335,6 @@ __global__ void __launch_bounds__(256) k_hessian(long long nnz, const DevFF *__r
   }
 }
 
-// 16-bit column stream for the CG SpMV: per 16-entry block of the (padded) entry sequence one 32-bit base = the smallest
-// slot of the block, per entry the 15-bit offset from it, bit 15 = ghost column.  Rows start on 16-entry boundaries, so
-// the entries of a block belong to one row and come from one or two neighbouring stencil runs: offsets stay far below
-// 32768; *ovf is raised otherwise and the 32-bit stream is used.  Canonical CSR is 12 B per entry; this
-// stream moves 10.25 B.  OPT-IN (RXG_COL16=1): measured on B200 at 979 776 atoms it cuts the SpMV's DRAM bytes by 14 %
-// (4.69 -> 4.07 GB) but its time by 1 % only (1.033 -> 1.019 ms) -- the kernel is bound by L1 data-pipe wavefronts
-// (74 % of peak: the 16-byte gathers of x take 7.5 wavefronts per warp request), not by HBM -- and the conversion pass
-// costs 0.4 ms per step, so the default stays the 32-bit stream.
-__global__ void __launch_bounds__(256) k_col16(long long nnz, const int *__restrict__ col, unsigned short *__restrict__ col16,
-                                               int *__restrict__ cbase, int *__restrict__ ovf) {
-  const long long stride = (long long)gridDim.x * blockDim.x;
-  for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += stride) {   // nnz is a multiple of 16
-    const int v = col[k];
-    const int slot = v & COL_MASK;
-    int m = slot;
-#pragma unroll
-    for (int o = 8; o > 0; o >>= 1) m = min(m, __shfl_xor_sync(0xffffffffu, m, o, 16));
-    const int off = slot - m;
-    if (off > 0x7fff && *(volatile int *)ovf == 0) atomicExch(ovf, 1);
-    col16[k] = (unsigned short)((off & 0x7fff) | (v < 0 ? 0x8000 : 0));
-    if ((k & 15) == 0) cbase[k >> 4] = m;
-  }
-}
-
 int ensure_bond_capacity(Ctx *c, long long need);   // rxg_api.cu
 
 inline int build_nbrlist(Ctx *c) {
@@ -297,19 +371,23 @@ int build_pairlist(Ctx *c, bool hessian = true) {
   RXG_CUDA(cudaMemsetAsync(c->d_flag + 16, 0, sizeof(int), c->st));
   RXG_CUDA(cudaMemsetAsync(c->d_acc + 33, 0, sizeof(double), c->st));
   RXG_CUDA(cudaMemsetAsync(c->rowcnt, 0, sizeof(int) * (size_t)(nt + 1), c->st));
+  const bool un_on = MODE >= 1 && c->spmv_kind == 0;   // the union stream is built only for the kernel that walks it
+  if (un_on) RXG_CUDA(cudaMemsetAsync(c->ucnt, 0, sizeof(int) * (size_t)(nt + 1), c->st));
   RXG_CUDA(cudaMemsetAsync(c->rowbeg, 0, sizeof(long long) * (size_t)n, c->st));
   RXG_CUDA(cudaMemsetAsync(c->rowend, 0, sizeof(long long) * (size_t)n, c->st));
   const int ncell_res = c->gnb.nc[0] * c->gnb.nc[1] * c->gnb.nc[2];
   const int grid = cdiv((long long)ncell_res * 32, PL_WARPS * 32);
-  const bool want16 = MODE >= 1 && !c->strict && c->use_col16;
-  const int ralign = want16 ? 16 : 4;
-  LAUNCH(c, (k_pairlist<MODE, false>), grid, PL_WARPS * 32, 0, c->gnb, c->d_ff, c->d_runs, c->nruns, n, ncell_res, c->rowcnt,
-         c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->cfg.maxneighbs10, c->d_flag, (unsigned long long *)(c->d_acc + 33), ralign);
+  const int ralign = 4;
+#define RXG_PL_ARGS c->gnb, c->d_ff, c->d_runs, c->nruns, n, ncell_res, c->rowcnt, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->cfg.maxneighbs10,   \
+                    c->d_flag, (unsigned long long *)(c->d_acc + 33), ralign, c->ucnt, c->uoff, c->ucol, c->umask, c->items, c->d_flag + 17
+  if (un_on) LAUNCH(c, (k_pairlist<MODE, false, (MODE >= 1)>), grid, PL_WARPS * 32, 0, RXG_PL_ARGS, 4);
+  else LAUNCH(c, (k_pairlist<MODE, false, false>), grid, PL_WARPS * 32, 0, RXG_PL_ARGS, 4);
   RXG_TRY(ensure_blk(c, nt));
   RXG_TRY(device_scan<long long>(c, c->rowcnt, nt, c->rowoff, c->d_blk64, (long long *)(c->d_acc + 32)));
+  if (un_on) RXG_TRY(device_scan<long long>(c, c->ucnt, nt, c->uoff, c->d_blk64, (long long *)(c->d_acc + 34)));
   RXG_CUDA(cudaMemcpyAsync(c->h_int, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->st));
   RXG_CUDA(cudaMemcpyAsync(c->h_int + 16, c->d_flag + 16, sizeof(int), cudaMemcpyDeviceToHost, c->st));
-  RXG_CUDA(cudaMemcpyAsync(c->h_acc + 32, c->d_acc + 32, 2 * sizeof(long long), cudaMemcpyDeviceToHost, c->st));
+  RXG_CUDA(cudaMemcpyAsync(c->h_acc + 32, c->d_acc + 32, 3 * sizeof(long long), cudaMemcpyDeviceToHost, c->st));
   RXG_CUDA(cudaStreamSynchronize(c->st));
   if (c->h_int[0] > c->cfg.maxneighbs10) {
     c->err = "ERROR: nbplist greater then MAXNEIGHBS10, value " + std::to_string(c->h_int[0]);
@@ -319,34 +397,40 @@ int build_pairlist(Ctx *c, bool hessian = true) {
   if (nnz > c->nnz_cap) {
     if (c->col) cudaFree(c->col);
     if (c->val) cudaFree(c->val);
-    if (c->col16) cudaFree(c->col16);
-    if (c->cbase) cudaFree(c->cbase);
     c->nnz_cap = nnz + nnz / 16 + 1024;
     RXG_CUDA(cudaMalloc(&c->col, sizeof(int) * c->nnz_cap));
     RXG_CUDA(cudaMalloc(&c->val, sizeof(double) * c->nnz_cap));
-    RXG_CUDA(cudaMalloc(&c->col16, sizeof(unsigned short) * c->nnz_cap));
-    RXG_CUDA(cudaMalloc(&c->cbase, sizeof(int) * (c->nnz_cap / 16 + 2)));
+  }
+  const long long nun = un_on ? *(long long *)(c->h_acc + 34) : 0;
+  if (nun > c->un_cap) {
+    if (c->ucol) cudaFree(c->ucol);
+    if (c->umask) cudaFree(c->umask);
+    c->un_cap = nun + nun / 16 + 1024;
+    RXG_CUDA(cudaMalloc(&c->ucol, sizeof(int) * c->un_cap));
+    RXG_CUDA(cudaMalloc(&c->umask, (size_t)c->un_cap));
   }
   c->nnz = nnz;
+  c->nunion = nun;
   c->maxrow = c->h_int[16];
   c->nnz_real = *(long long *)(c->h_acc + 33);
   c->list_is_qeq = MODE >= 1;
-  LAUNCH(c, (k_pairlist<MODE, true>), grid, PL_WARPS * 32, 0, c->gnb, c->d_ff, c->d_runs, c->nruns, n, ncell_res, c->rowcnt,
-         c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->cfg.maxneighbs10, c->d_flag, (unsigned long long *)(c->d_acc + 33), ralign);
+  // rows per SpMV work item: four while four of the longest rows fit a stage of k_spmv_items, else two (12.5 A lists of PQEq)
+  c->spmv_rg = c->maxrow <= 480 ? 4 : 2;
+  RXG_CUDA(cudaMemsetAsync(c->d_flag + 17, 0, sizeof(int), c->st));
+  if (un_on) LAUNCH(c, (k_pairlist<MODE, true, (MODE >= 1)>), grid, PL_WARPS * 32, 0, RXG_PL_ARGS, c->spmv_rg);
+  else LAUNCH(c, (k_pairlist<MODE, true, false>), grid, PL_WARPS * 32, 0, RXG_PL_ARGS, c->spmv_rg);
+#undef RXG_PL_ARGS
   if (MODE >= 1 && hessian)
     LAUNCH(c, k_hessian, 148 * 16, 256, 0, nnz, c->d_ff, c->val);
-  c->have_col16 = false;
-  if (want16 && nnz > 0) {
-    RXG_CUDA(cudaMemsetAsync(c->d_flag + 7, 0, sizeof(int), c->st));
-    LAUNCH(c, k_col16, 148 * 16, 256, 0, nnz, c->col, c->col16, c->cbase, c->d_flag + 7);
-    c->have_col16 = true;   // provisional: the overflow flag is read with the first CG scalars (qeq_cg_single)
-  }
+  c->nitems = un_on ? -1 : 0;   // read back with the CG's first synchronisation (spmv_launch)
   return RXG_OK;
 }
 
 // ---------------------------------------------------------------------------------------------------
 // QEq CG.  d_acc slots: 0 Est, 1 hshs, 2 hsht, 3 g.h (s), 4 g.h (t), 5 sum qs, 6 sum qt, 7 g.g (s) new, 8 g.g (t) new,
-// 9 g.g (s) old, 10 g.g (t) old.
+// 9 g.g (s) old, 10 g.g (t) old, 11 mu, 12-13 PQEq ghost-column sums of the iteration, 14-17 PQEq (rxg_pqeq.cuh),
+// 20-24 the CG's control block (k_cg_ctrl): Est of the previous iteration, stopped flag, completed iterations, lmin_s, lmin_t.
+constexpr int ACC_GEST2 = 20, ACC_DONE = 21, ACC_NITER = 22, ACC_LMIN = 23;
 __device__ __forceinline__ double warp_sum(double v) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
@@ -501,64 +585,9 @@ __global__ void __launch_bounds__(256) k_hsh(const int *__restrict__ order, int 
 // One matrix stream per iteration instead of two; identical in exact arithmetic (round-off: see DESIGN.md "QEq").
 // Est (src/qeq.F90:296-306) needs sum_j w_ij H_ij q_j with w = 2 for resident j, 1 for ghost j; it is
 // carried the same way in wst = resident-weighted H.(qs,qt), with q = qs - mu*qt.
-template <bool INIT>
-__global__ void __launch_bounds__(256) k_spmv1(const int *__restrict__ order, int ntot, int natoms, const long long *__restrict__ rowbeg, const long long *__restrict__ rowend, const int *__restrict__ col,
-                                               const double *__restrict__ val, const double2 *__restrict__ x,
-                                               const double2 *__restrict__ qst, const double *__restrict__ q,
-                                               double2 *__restrict__ gst, double2 *__restrict__ tst,
-                                               double2 *__restrict__ ust, double2 *__restrict__ wst,
-                                               const int *__restrict__ itype, const DevFF *__restrict__ ffp,
-                                               double *__restrict__ acc) {
-  const int lane = threadIdx.x & 31;
-  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // rows are walked in cell order (L1-friendly gathers)
-  int i = natoms;
-  if (slot < ntot) i = order[slot];
-  double part[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-  if (i < natoms) {
-    long long s = rowbeg[i], e = rowend[i];
-    double a = 0.0, b = 0.0, ga = 0.0, gb = 0.0;
-    for (long long k = s + lane; k < e; k += 32) {
-      double h = __ldcs(val + k);
-      int j = __ldcs(col + k);
-      double2 v = x[j & COL_MASK];            // x is in slot order: neighbours of a stencil run are contiguous
-      double pa = h * v.x, pb = h * v.y;
-      a += pa; b += pb;
-      if (j < 0) { ga += pa; gb += pb; }      // bit 31 = ghost column
-    }
-    warp_sum4(a, b, ga, gb, lane);
-    if (lane == 0) {
-      int t = itype[i] - 1;
-      double eta = ffp->eta[t], chi = ffp->chi[t];
-      double2 me = x[slot];
-      if (INIT) {
-        double g1 = sub_rn(sub_rn(-chi, mul_rn(eta, me.x)), a);
-        double g2 = sub_rn(sub_rn(-1.0, mul_rn(eta, me.y)), b);
-        gst[i] = make_double2(g1, g2);
-        wst[i] = make_double2(2.0 * a - ga, 2.0 * b - gb);
-        part[0] = g1 * g1; part[1] = g2 * g2;
-      } else {
-        double ts = eta * me.x + a, tt = eta * me.y + b;
-        tst[i] = make_double2(ts, tt);
-        ust[i] = make_double2(2.0 * a - ga, 2.0 * b - gb);
-        double2 g = gst[i], w = wst[i];
-        double mu = acc[11], qi = q[i];
-        part[0] = chi * qi + 0.5 * eta * qi * qi + 0.5 * qi * (w.x - mu * w.y);
-        part[1] = ts * me.x; part[2] = tt * me.y; part[3] = g.x * me.x; part[4] = g.y * me.y;
-      }
-    }
-  }
-  if (INIT) { double p2[2] = {part[0], part[1]}; block_accumulate<2>(p2, acc + 7); }
-  else block_accumulate<5>(part, acc + 0);
-}
-
 // ---------------------------------------------------------------------------------------------------
-// TMA-staged variant of k_spmv1 (the production kernel).  Rows lie in HBM in cell order, so the rows of SP_ROWS
-// consecutive slots form ONE contiguous span of (val, col).  One CTA per span: an elected thread issues two bulk
-// async copies (cp.async.bulk ... mbarrier::complete_tx) that bring the span into shared memory, the CTA's warps
-// then take one row each and read the matrix stream from shared memory while gathering x from L1/L2.  With several
-// CTAs resident per SM the copy engine always has tens of KB in flight per SM, which is what HBM needs; the SM's
-// load/store pipe is left to the gathers.  Rows start on 4-entry boundaries (16 B for col, 32 B for val).
-constexpr int SP_ROWS = 4, SP_CAP = 1920;   // 8 rows x up to 480 entries: 46 KB of shared memory per CTA
+// Bulk-copy (TMA) helpers.  Rows lie in HBM in cell order, so the rows of consecutive slots form ONE contiguous span of
+// (val, col); rows start on 4-entry boundaries (16 B for col, 32 B for val).
 
 __device__ __forceinline__ unsigned smem_u32(const void *p) { return (unsigned)__cvta_generic_to_shared(p); }
 __device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
@@ -578,107 +607,13 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
     asm volatile(
         "{\n"
         ".reg .pred p;\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, 0x989680;\n"   // suspend-time hint: the wait may park the warp
         "selp.u32 %0, 1, 0, p;\n"
         "}\n"
         : "=r"(done)
         : "r"(smem_u32(bar)), "r"(parity)
         : "memory");
   }
-}
-
-template <bool INIT>
-__global__ void __launch_bounds__(SP_ROWS * 32) k_spmv1_tma(const int *__restrict__ order, int ntot, int natoms,
-                                                            const long long *__restrict__ rowoff,
-                                                            const long long *__restrict__ rowbeg,
-                                                            const long long *__restrict__ rowend, const int *__restrict__ col,
-                                                            const double *__restrict__ val, const double2 *__restrict__ x,
-                                                            const double2 *__restrict__ qst, const double *__restrict__ q,
-                                                            double2 *__restrict__ gst, double2 *__restrict__ tst,
-                                                            double2 *__restrict__ ust, double2 *__restrict__ wst,
-                                                            const int *__restrict__ itype, const DevFF *__restrict__ ffp,
-                                                            double *__restrict__ acc) {
-  __shared__ __align__(128) double s_val[SP_CAP];
-  __shared__ __align__(128) int s_col[SP_CAP];
-  __shared__ __align__(8) unsigned long long bar;
-  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-  const int slot0 = blockIdx.x * SP_ROWS;
-  const int slot1 = min(slot0 + SP_ROWS, ntot);
-  const long long sb = rowoff[slot0], se = rowoff[slot1];
-  const int span = (int)(se - sb);
-  const bool staged = span > 0 && span <= SP_CAP;
-  if (staged) {
-    if (threadIdx.x == 0) {
-      mbar_init(&bar, 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      mbar_expect_tx(&bar, (unsigned)span * 12u);
-      bulk_g2s(s_val, val + sb, (unsigned)span * 8u, &bar);
-      bulk_g2s(s_col, col + sb, (unsigned)span * 4u, &bar);
-    }
-  }
-  const int slot = slot0 + wid;
-  int i = natoms;
-  if (slot < ntot) i = order[slot];
-  double part[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
-  // per-row scalars are fetched while the bulk copies are in flight
-  long long rs = 0, re = 0;
-  double eta = 0, chi = 0, qi = 0, mu = 0;
-  double2 me = make_double2(0, 0), g = make_double2(0, 0), w = make_double2(0, 0);
-  if (i < natoms) {
-    rs = rowbeg[i]; re = rowend[i];
-    int t = itype[i] - 1;
-    eta = ffp->eta[t]; chi = ffp->chi[t];
-    me = x[slot];
-    if (!INIT) { g = gst[i]; w = wst[i]; qi = q[i]; mu = acc[11]; }
-  }
-  if (staged) mbar_wait(&bar, 0);
-  if (i < natoms) {
-    double a = 0.0, b = 0.0, ga = 0.0, gb = 0.0;
-    const int n = (int)(re - rs);
-    if (staged) {
-      const double *sv = s_val + (rs - sb);
-      const int *sc = s_col + (rs - sb);
-#pragma unroll 8
-      for (int k = lane; k < n; k += 32) {
-        double h = sv[k];
-        int j = sc[k];
-        double2 v = x[j & COL_MASK];
-        double pa = h * v.x, pb = h * v.y;
-        a += pa; b += pb;
-        if (j < 0) { ga += pa; gb += pb; }
-      }
-    } else {
-      for (long long k = rs + lane; k < re; k += 32) {
-        double h = __ldcs(val + k);
-        int j = __ldcs(col + k);
-        double2 v = x[j & COL_MASK];
-        double pa = h * v.x, pb = h * v.y;
-        a += pa; b += pb;
-        if (j < 0) { ga += pa; gb += pb; }
-      }
-    }
-    warp_sum4(a, b, ga, gb, lane);
-    if (lane == 0) {
-      if (INIT) {
-        double g1 = sub_rn(sub_rn(-chi, mul_rn(eta, me.x)), a);
-        double g2 = sub_rn(sub_rn(-1.0, mul_rn(eta, me.y)), b);
-        gst[i] = make_double2(g1, g2);
-        wst[i] = make_double2(2.0 * a - ga, 2.0 * b - gb);
-        part[0] = g1 * g1; part[1] = g2 * g2;
-      } else {
-        double ts = eta * me.x + a, tt = eta * me.y + b;
-        tst[i] = make_double2(ts, tt);
-        ust[i] = make_double2(2.0 * a - ga, 2.0 * b - gb);
-        part[0] = chi * qi + 0.5 * eta * qi * qi + 0.5 * qi * (w.x - mu * w.y);
-        part[1] = ts * me.x; part[2] = tt * me.y; part[3] = g.x * me.x; part[4] = g.y * me.y;
-      }
-    }
-  }
-  if (INIT) { double p2[2] = {part[0], part[1]}; block_accumulate<2>(p2, acc + 7); }
-  else block_accumulate<5>(part, acc + 0);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -693,8 +628,9 @@ __global__ void __launch_bounds__(ROWS * LPR) k_spmv_rows(const int *__restrict_
                                                           const long long *__restrict__ rowoff, const long long *__restrict__ rowbeg,
                                                           const long long *__restrict__ rowend, const int *__restrict__ col,
                                                           const double *__restrict__ val, const double2 *__restrict__ x,
-                                                          double4 *__restrict__ rowsum) {
+                                                          double4 *__restrict__ rowsum, const double *__restrict__ acc, int stage) {
   constexpr int CAP = ROWS * CAPROW;   // CAPROW = longest row the staged path takes (480: 10 A lists; 1216: the 12.5 A lists of PQEq)
+  if (acc[ACC_DONE] != 0.0) return;   // the CG has stopped (k_cg_ctrl): iterations enqueued ahead of the host's check do nothing
   __shared__ __align__(128) double s_val[CAP];
   __shared__ __align__(128) int s_col[CAP];
   __shared__ __align__(8) unsigned long long bar;
@@ -703,7 +639,7 @@ __global__ void __launch_bounds__(ROWS * LPR) k_spmv_rows(const int *__restrict_
   const int slot1 = min(slot0 + ROWS, ntot);
   const long long sb = rowoff[slot0], se = rowoff[slot1];
   const int span = (int)(se - sb);
-  const bool staged = span > 0 && span <= CAP;
+  const bool staged = stage && span > 0 && span <= CAP;   // stage == 0: every CTA reads straight from HBM (the path long rows take)
   if (staged) {
     if (threadIdx.x == 0) {
       mbar_init(&bar, 1);
@@ -756,80 +692,191 @@ __global__ void __launch_bounds__(ROWS * LPR) k_spmv_rows(const int *__restrict_
   if (sub == 0 && i < natoms) rowsum[slot] = make_double4(a, b, ga, gb);
 }
 
-// k_spmv_rows with the 16-bit column stream of k_col16: 10.125 B per entry from HBM instead of 12.
-template <int ROWS, int LPR, bool STAGE_VAL = true>
-__global__ void __launch_bounds__(ROWS * LPR) k_spmv_rows16(const int *__restrict__ order, int ntot, int natoms,
-                                                            const long long *__restrict__ rowoff, const long long *__restrict__ rowbeg,
-                                                            const long long *__restrict__ rowend, const unsigned short *__restrict__ col16,
-                                                            const int *__restrict__ cbase, const int *__restrict__ col,
-                                                            const double *__restrict__ val, const double2 *__restrict__ x,
-                                                            double4 *__restrict__ rowsum) {
-  constexpr int CAP = ROWS * 480;
-  __shared__ __align__(128) double s_val[STAGE_VAL ? CAP : 16];
-  __shared__ __align__(128) unsigned short s_col[CAP];
-  __shared__ int s_base[CAP / 16 + 2];
-  __shared__ __align__(8) unsigned long long bar;
-  const int sub = threadIdx.x % LPR, rowid = threadIdx.x / LPR;
-  const int slot0 = blockIdx.x * ROWS;
-  const int slot1 = min(slot0 + ROWS, ntot);
-  const long long sb = rowoff[slot0], se = rowoff[slot1];
-  const int span = (int)(se - sb);
-  const bool staged = span > 0 && span <= CAP;
-  if (staged) {
-    if (threadIdx.x == 0) {
-      mbar_init(&bar, 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    if (threadIdx.x == 0) {
-      mbar_expect_tx(&bar, (unsigned)span * (STAGE_VAL ? 10u : 2u));
-      if (STAGE_VAL) bulk_g2s(s_val, val + sb, (unsigned)span * 8u, &bar);
-      bulk_g2s(s_col, col16 + sb, (unsigned)span * 2u, &bar);
-    }
-    const long long b0 = sb >> 4;
-    const int nb = span >> 4;
-    for (int t = threadIdx.x; t < nb; t += ROWS * LPR) s_base[t] = cbase[b0 + t];
-  }
-  const int slot = slot0 + rowid;
-  int i = natoms;
-  if (slot < ntot) i = order[slot];
-  long long rs = 0, re = 0;
-  if (i < natoms) { rs = rowbeg[i]; re = rowend[i]; }
-  if (staged) { mbar_wait(&bar, 0); __syncthreads(); }
-  double a = 0.0, b = 0.0, ga = 0.0, gb = 0.0;
-  if (i < natoms) {
-    if (staged) {
-      const int n = (int)(re - rs);
-      const int p0 = (int)(rs - sb);
-      const double *sv = STAGE_VAL ? s_val + p0 : val + rs;
-      const unsigned short *sc = s_col + p0;
-      const int *sbs = s_base + (p0 >> 4);
-#pragma unroll 8
-      for (int k = sub; k < n; k += LPR) {
-        const double h = STAGE_VAL ? sv[k] : __ldcs(sv + k);
-        const unsigned c16 = sc[k];
-        const double2 v = x[sbs[k >> 4] + (int)(c16 & 0x7fffu)];
-        const double pa = h * v.x, pb = h * v.y;
-        a += pa; b += pb;
-        if (c16 & 0x8000u) { ga += pa; gb += pb; }
-      }
-    } else {
-      for (long long k = rs + sub; k < re; k += LPR) {
-        double h = __ldcs(val + k);
-        int j = __ldcs(col + k);
-        double2 v = x[j & COL_MASK];
-        double pa = h * v.x, pb = h * v.y;
-        a += pa; b += pb;
-        if (j < 0) { ga += pa; gb += pb; }
+// ---------------------------------------------------------------------------------------------------
+// Cell-blocked SpMV (production).  The rows of one cell take nearly the same columns (the union of the lists of the ~3 atoms
+// of a 3 A cell is 0.44x the sum of their lengths at RDX density), and k_spmv_rows pays one 16-byte gather of x per stored
+// entry: its L1 data pipe, not HBM, is what saturates.  Here a work item (SpItem, written by k_pairlist's fill pass) is up
+// to RG consecutive rows of a block of <= 8 rows of one cell, with the block's UNION stream: per union entry a column (4 B)
+// and the 8-bit set of rows that hold it (1 B).  A lane gathers x[col] once and feeds it to every row of the set; the row's
+// value sits at the row's running position in its own compacted value stream (ballot + popc), so the fp64 values are stored
+// once, exactly as CSR stores them: 8 B of value + 5 B x 0.44 of column/mask = 10.2 B per stored entry instead of 12 B, and
+// 0.44 gathers instead of 1.
+// Execution: ONE persistent CTA per SM -- a producer warp and SI_CONS consumer warps around a shared-memory ring (~200 KB)
+// that is allocated item by item in exactly the bytes each item needs.  The producer's elected lane reads item records
+// (three items ahead, in registers), reserves ring space, and issues three bulk async copies per item (cp.async.bulk, UBLKCP
+// in SASS: values, columns, row sets) that complete on the slot's `full` mbarrier; space is reclaimed in item order as the
+// consumers signal `empty`.  Consumer warp w owns items w, w+SI_CONS, ... of its CTA and walks each alone: no cross-warp
+// reduction, no CTA barrier.  Per 128 union entries it issues four gathers of x, and while they are in flight multiplies out
+// the previous 128 from shared memory (branch-free: a row that lacks the column multiplies by a zero value).  HBM always has
+// the ring's free part (tens of KB per SM) in flight, whatever the gather latency of the walks.
+// An item that does not fit the ring is walked straight from global memory.
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+
+constexpr int SI_CONS = 12;    // consumer warps per CTA
+constexpr int SI_SLOTS = 32;   // items in flight per CTA (descriptors); power of two
+struct SiSlot { int off; int staged; };   // ring offset of the item's data; 0 = read from global memory
+
+template <int RG, bool STAGED>
+__device__ __forceinline__ void spmv_item_walk(const SpItem &I, const double *__restrict__ vv, const int *__restrict__ uc,
+                                               const unsigned char *__restrict__ um, const double2 *__restrict__ x,
+                                               double4 *__restrict__ rowsum, int lane) {
+  const unsigned lt = (1u << lane) - 1u;
+  int pos[RG];
+  double sa[RG], sb[RG], sga[RG], sgb[RG];
+#pragma unroll
+  for (int j = 0; j < RG; j++) { pos[j] = I.rs[j]; sa[j] = 0.0; sb[j] = 0.0; sga[j] = 0.0; sgb[j] = 0.0; }
+  const int un = I.un, rshift = I.rshift, nrp = I.nrp;
+  constexpr int G = 4;   // steps (of 32 union entries) per group: G gathers of x in flight per lane
+  int c[G], cn[G];
+  unsigned mm[G], mn[G];
+  double2 xv[G], xn[G];
+  auto load_group = [&](int u0, int (&cc)[G], unsigned (&mk)[G], double2 (&xx)[G]) {
+#pragma unroll
+    for (int t = 0; t < G; t++) {
+      const int u = u0 + 32 * t + lane;
+      cc[t] = 0; mk[t] = 0u;
+      if (u < un) {
+        cc[t] = STAGED ? uc[u] : __ldcs(uc + u);
+        mk[t] = ((unsigned)(STAGED ? um[u] : __ldcs(um + u)) >> rshift) & ((1u << RG) - 1u);
       }
     }
+#pragma unroll
+    for (int t = 0; t < G; t++) {
+      xx[t] = make_double2(0.0, 0.0);
+      if (mk[t]) xx[t] = x[cc[t] & COL_MASK];
+    }
+  };
+  load_group(0, c, mm, xv);
+  for (int u0 = 0; u0 < un; u0 += 32 * G) {
+    if (u0 + 32 * G < un) load_group(u0 + 32 * G, cn, mn, xn);   // next group's gathers fly while this one is multiplied out
+#pragma unroll
+    for (int t = 0; t < G; t++) {
+      const double gx = c[t] < 0 ? xv[t].x : 0.0, gy = c[t] < 0 ? xv[t].y : 0.0;   // bit 31 = ghost column (Est weighting)
+#pragma unroll
+      for (int j = 0; j < RG; j++) {
+        if (j < nrp) {   // warp-uniform
+          const bool bit = (mm[t] >> j) & 1u;
+          const unsigned bal = __ballot_sync(0xffffffffu, bit);
+          double h = 0.0;
+          if (bit) { const int k = pos[j] + __popc(bal & lt); h = STAGED ? vv[k] : __ldcs(vv + k); }
+          sa[j] = fma(h, xv[t].x, sa[j]); sb[j] = fma(h, xv[t].y, sb[j]);
+          sga[j] = fma(h, gx, sga[j]); sgb[j] = fma(h, gy, sgb[j]);
+          pos[j] += __popc(bal);
+        }
+      }
+    }
+#pragma unroll
+    for (int t = 0; t < G; t++) { c[t] = cn[t]; mm[t] = mn[t]; xv[t] = xn[t]; }
   }
 #pragma unroll
-  for (int o = LPR / 2; o > 0; o >>= 1) {
-    a += __shfl_xor_sync(0xffffffffu, a, o); b += __shfl_xor_sync(0xffffffffu, b, o);
-    ga += __shfl_xor_sync(0xffffffffu, ga, o); gb += __shfl_xor_sync(0xffffffffu, gb, o);
+  for (int j = 0; j < RG; j++) {
+    if (j < nrp) {
+      warp_sum4(sa[j], sb[j], sga[j], sgb[j], lane);
+      if (lane == 0) rowsum[I.slot0 + j] = make_double4(sa[j], sb[j], sga[j], sgb[j]);
+    }
   }
-  if (sub == 0 && i < natoms) rowsum[slot] = make_double4(a, b, ga, gb);
+}
+
+template <int RG>
+__global__ void __launch_bounds__((SI_CONS + 1) * 32, 1) k_spmv_items(const SpItem *__restrict__ items, int nitems,
+                                                                      const int *__restrict__ ucol, const unsigned char *__restrict__ umask,
+                                                                      const double *__restrict__ val, const double2 *__restrict__ x,
+                                                                      double4 *__restrict__ rowsum, const double *__restrict__ acc, int ring_bytes,
+                                                                      int stage_on) {
+  static_assert(RG <= 4, "at most four rows per item");
+  extern __shared__ __align__(128) unsigned char ring[];
+  __shared__ __align__(8) unsigned long long full[SI_SLOTS], empty[SI_SLOTS];
+  __shared__ SiSlot slots[SI_SLOTS];
+  __shared__ __align__(16) SpItem recs[SI_SLOTS];
+  if (acc[ACC_DONE] != 0.0) return;   // the CG has stopped (k_cg_ctrl)
+  const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < SI_SLOTS; s++) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const int g = gridDim.x;
+  if (w == SI_CONS) {
+    // ---- producer: reserve ring space in item order, copy, publish; reclaim space in item order
+    if (lane == 0) {
+      int4 qa[4], qb[4], qc[4];
+      auto fetch = [&](int4 (&q)[4], int it) {
+        if (it < nitems) {
+          const int4 *src = reinterpret_cast<const int4 *>(items + it);
+          q[0] = __ldg(src); q[1] = __ldg(src + 1); q[2] = __ldg(src + 2); q[3] = __ldg(src + 3);
+        }
+      };
+      fetch(qa, blockIdx.x); fetch(qb, blockIdx.x + g); fetch(qc, blockIdx.x + 2 * g);
+      int head = 0;          // next free byte of the ring
+      int tail = 0;          // oldest item whose space is still held (item index k of this CTA)
+      int k = 0;
+      for (int it = blockIdx.x; it < nitems; it += g, k++) {
+        const int s = k & (SI_SLOTS - 1);
+        const long long voff = ((long long)(unsigned)qa[0].x) | ((long long)qa[0].y << 32);
+        const long long uoff = ((long long)(unsigned)qa[0].z) | ((long long)qa[0].w << 32);
+        const int un = qa[1].x, vlen = qa[1].w;
+        const int bv = (vlen * 8 + 127) & ~127, bc = (un * 4 + 127) & ~127, bm = (un + 127) & ~127;
+        const int need = bv + bc + bm;
+        const bool staged = stage_on && vlen > 0 && un > 0 && need <= ring_bytes / 2;
+        // Wait for the slot's previous user (item k - SI_SLOTS) and for `need` contiguous bytes.  Live data is the circular
+        // interval [start of the oldest unreleased item, head); an unstaged item holds zero bytes at the head of its time.
+        const int nb = staged ? need : 0;
+        int off = head;
+        for (;;) {
+          bool ok = k - tail < SI_SLOTS;
+          if (ok && nb > 0) {
+            if (tail == k) { head = 0; off = 0; }                     // nothing live: restart at the ring's origin
+            else {
+              const int tail_off = slots[tail & (SI_SLOTS - 1)].off;
+              if (head >= tail_off) {                                  // live data does not wrap
+                if (head + nb <= ring_bytes) off = head;
+                else if (nb < tail_off) off = 0;                       // leave the ring's end unused and wrap
+                else ok = false;
+              } else {                                                 // live data wraps: free = [head, tail_off)
+                if (head + nb < tail_off) off = head; else ok = false;
+              }
+            }
+          }
+          if (ok) break;
+          mbar_wait(&empty[tail & (SI_SLOTS - 1)], (tail / SI_SLOTS) & 1);   // reclaim the oldest item's space
+          tail++;
+        }
+        head = off + nb;
+        slots[s].off = off; slots[s].staged = staged ? 1 : 0;
+        int4 *dst = reinterpret_cast<int4 *>(&recs[s]);
+        dst[0] = qa[0]; dst[1] = qa[1]; dst[2] = qa[2]; dst[3] = qa[3];
+        if (staged) {
+          mbar_expect_tx(&full[s], (unsigned)vlen * 8u + (unsigned)un * 5u);   // (arrives and sets the byte count)
+          bulk_g2s(ring + off, val + voff, (unsigned)vlen * 8u, &full[s]);
+          bulk_g2s(ring + off + bv, ucol + uoff, (unsigned)un * 4u, &full[s]);
+          bulk_g2s(ring + off + bv + bc, umask + uoff, (unsigned)un, &full[s]);
+        } else {
+          mbar_arrive(&full[s]);   // nothing to wait for: the consumer reads this item from global memory
+        }
+#pragma unroll
+        for (int q = 0; q < 4; q++) { qa[q] = qb[q]; qb[q] = qc[q]; }
+        fetch(qc, it + 3 * g);
+      }
+    }
+  } else {
+    for (int k = w, it = blockIdx.x + w * g; it < nitems; k += SI_CONS, it += SI_CONS * g) {
+      const int s = k & (SI_SLOTS - 1);
+      mbar_wait(&full[s], (k / SI_SLOTS) & 1);
+      const SpItem I = recs[s];
+      const int off = slots[s].off;
+      if (slots[s].staged) {
+        const int bv = (I.vlen * 8 + 127) & ~127, bc = (I.un * 4 + 127) & ~127;
+        spmv_item_walk<RG, true>(I, reinterpret_cast<const double *>(ring + off), reinterpret_cast<const int *>(ring + off + bv),
+                                 ring + off + bv + bc, x, rowsum, lane);
+      } else {
+        spmv_item_walk<RG, false>(I, val + I.voff, ucol + I.uoff, umask + I.uoff, x, rowsum, lane);
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[s]);
+    }
+  }
 }
 
 template <bool INIT>
@@ -838,6 +885,7 @@ __global__ void __launch_bounds__(256) k_cg_dots(const int *__restrict__ order, 
                                                  double2 *__restrict__ gst, double2 *__restrict__ tst, double2 *__restrict__ ust,
                                                  double2 *__restrict__ wst, const int *__restrict__ itype,
                                                  const DevFF *__restrict__ ffp, double *__restrict__ acc) {
+  if (!INIT && acc[ACC_DONE] != 0.0) return;
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
   double part[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
   int i = natoms;
@@ -867,19 +915,37 @@ __global__ void __launch_bounds__(256) k_cg_dots(const int *__restrict__ order, 
   else block_accumulate<5>(part, acc + 0);
 }
 
-__global__ void k_roll_g(double *__restrict__ acc) {
+// The CG's control step on the device (one thread, after the all-reduce of the five dots): the stop rule of
+// src/qeq.F90:114-115 on Est, the real(4) step lengths of :133, and the roll of the g.g sums -- what the host
+// did between two synchronisations per iteration in round 1.  Once the stop flag is set, the iteration's remaining kernels
+// and every later iteration already enqueued return at their first instruction, so the host only looks at the flag every
+// few iterations.  pq: PQEq's ghost-column recurrences (qs_ghost += lmin_s hs_ghost => acc[14] += lmin_s * acc[12]).
+__global__ void k_cg_ctrl(double *__restrict__ acc, double tol, int pq) {
+  if (acc[ACC_DONE] != 0.0) return;
+  const double GEst1 = acc[0], GEst2 = acc[ACC_GEST2];
+  bool stop = 0.5 * (fabs(GEst2) + fabs(GEst1)) < tol;                                        // src/qeq.F90:114
+  if (!stop && fabs(GEst2) > 0.0 && fabs(__ddiv_rn(GEst1, GEst2) - 1.0) < tol) stop = true;   // src/qeq.F90:115
+  if (stop) { acc[ACC_DONE] = 1.0; return; }
+  acc[ACC_GEST2] = GEst1;
+  const float lmin_s = (float)__ddiv_rn(acc[3], acc[1]);   // real(4) :: lmin, src/qeq.F90:23,133
+  const float lmin_t = (float)__ddiv_rn(acc[4], acc[2]);
+  acc[ACC_LMIN] = (double)lmin_s; acc[ACC_LMIN + 1] = (double)lmin_t;
+  if (pq) { acc[14] += (double)lmin_s * acc[12]; acc[15] += (double)lmin_t * acc[13]; }
   acc[9] = acc[7]; acc[10] = acc[8];
   acc[5] = 0.0; acc[6] = 0.0; acc[7] = 0.0; acc[8] = 0.0;
+  acc[0] = 0.0; acc[1] = 0.0; acc[2] = 0.0; acc[3] = 0.0; acc[4] = 0.0; acc[12] = 0.0; acc[13] = 0.0;   // the next iteration's dots start from zero
+  acc[ACC_NITER] += 1.0;
 }
 // qs,qt step (src/qeq.F90:136-137) + gradient / Est-bookkeeping recurrences + partial sums (sum qs, sum qt, g.g)
-__global__ void __launch_bounds__(256) k_cg_update1(int natoms, float lmin_s, float lmin_t, const double2 *__restrict__ hst,
+__global__ void __launch_bounds__(256) k_cg_update1(int natoms, const double2 *__restrict__ hst,
                                                     const double2 *__restrict__ tst, const double2 *__restrict__ ust,
                                                     double2 *__restrict__ qst, double2 *__restrict__ gst,
                                                     double2 *__restrict__ wst, double *__restrict__ acc) {
+  if (acc[ACC_DONE] != 0.0) return;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   double part[4] = {0.0, 0.0, 0.0, 0.0};
   if (i < natoms) {
-    const double ls = (double)lmin_s, lt = (double)lmin_t;   // real(4) lmin promoted, SURVEY Q3
+    const double ls = acc[ACC_LMIN], lt = acc[ACC_LMIN + 1];   // real(4) lmin promoted (k_cg_ctrl), SURVEY Q3
     double2 h = hst[i], x = qst[i], g = gst[i], t = tst[i], u = ust[i], w = wst[i];
     x.x = add_rn(x.x, mul_rn(ls, h.x));
     x.y = add_rn(x.y, mul_rn(lt, h.y));
@@ -896,6 +962,7 @@ __global__ void __launch_bounds__(256) k_cg_update1(int natoms, float lmin_s, fl
 __global__ void k_cg_update2(int natoms, const double2 *__restrict__ qst, const double2 *__restrict__ gst,
                              double2 *__restrict__ hst, double2 *__restrict__ xs, const int *__restrict__ slot_of,
                              double *__restrict__ q, double *__restrict__ acc) {
+  if (acc[ACC_DONE] != 0.0) return;
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   double mu = acc[5] / acc[6];
   if (i == 0) acc[11] = mu;
@@ -908,9 +975,14 @@ __global__ void k_cg_update2(int natoms, const double2 *__restrict__ qst, const 
   hst[i] = h;
   xs[slot_of[i]] = h;
 }
+// hs = gs, ht = gt (src/qeq.F90:90-91); also arms the CG's control block (GEst2 = 1e99, :94)
 __global__ void k_h_from_g2(int natoms, const double2 *__restrict__ gst, double2 *__restrict__ hst, double2 *__restrict__ xs,
-                            const int *__restrict__ slot_of) {
+                            const int *__restrict__ slot_of, double *__restrict__ acc) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i == 0) {
+    acc[ACC_GEST2] = 1e99; acc[ACC_DONE] = 0.0; acc[ACC_NITER] = 0.0;
+    acc[0] = 0.0; acc[1] = 0.0; acc[2] = 0.0; acc[3] = 0.0; acc[4] = 0.0; acc[5] = 0.0; acc[6] = 0.0; acc[12] = 0.0; acc[13] = 0.0;
+  }
   if (i < natoms) { double2 g = gst[i]; hst[i] = g; xs[slot_of[i]] = g; }
 }
 // xs[slot] = v[order[slot]] for residents and ghosts
@@ -927,7 +999,8 @@ __global__ void k_to_slots(int ntot, const int *__restrict__ order, const double
 // at 1e-8; the production kernels above differ from it by summation order alone.  Small systems only.
 __global__ void k_rows_strict_grad(const int *__restrict__ order, int natoms, const long long *__restrict__ rowbeg, const long long *__restrict__ rowend, const int *__restrict__ col,
                                    const double *__restrict__ val, const double2 *__restrict__ qst,
-                                   const int *__restrict__ itype, const DevFF *__restrict__ ffp, double2 *__restrict__ gst) {
+                                   const int *__restrict__ itype, const DevFF *__restrict__ ffp, double2 *__restrict__ gst,
+                                   const double *__restrict__ fpq) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= natoms) return;
   double gs = 0.0, gt = 0.0;
@@ -939,7 +1012,9 @@ __global__ void k_rows_strict_grad(const int *__restrict__ order, int natoms, co
   int t = itype[i] - 1;
   double eta = ffp->eta[t], chi = ffp->chi[t];
   double2 x = qst[i];
-  gst[i] = make_double2(sub_rn(sub_rn(-chi, mul_rn(eta, x.x)), gs), sub_rn(sub_rn(-1.0, mul_rn(eta, x.y)), gt));
+  double g1 = sub_rn(sub_rn(-chi, mul_rn(eta, x.x)), gs);
+  if (fpq) g1 = sub_rn(g1, fpq[i]);   // PQEq: - fpqeq(i), src/pqeq.F90:463
+  gst[i] = make_double2(g1, sub_rn(sub_rn(-1.0, mul_rn(eta, x.y)), gt));
 }
 __global__ void k_rows_strict_hsh(const int *__restrict__ order, int natoms, const long long *__restrict__ rowbeg, const long long *__restrict__ rowend, const int *__restrict__ col,
                                   const double *__restrict__ val, const double4 *__restrict__ hsq,

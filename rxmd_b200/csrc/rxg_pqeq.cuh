@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(256) k_pqeq_rows(const DevGrid g, int ntot, in
 
 // k_cg_dots (rxg_lists_qeq.cuh) with the PQEq gradient and Est.  Ghost slots contribute sum_j c_j (...) terms:
 //   INIT : acc[14] = sum_ghost c_j qs_j, acc[15] = sum_ghost c_j qt_j, acc[16] = sum_ghost c_j Z_j   (x = {qs,qt} by slot)
-//   else : acc[5], acc[6] = sum_ghost c_j hs_j, c_j ht_j (x = {hs,ht}); k_roll_g_pqeq advances acc[14], acc[15] with lmin
+//   else : acc[12], acc[13] = sum_ghost c_j hs_j, c_j ht_j (x = {hs,ht}); k_cg_ctrl advances acc[14], acc[15] with lmin
 template <bool INIT>
 __global__ void __launch_bounds__(256) k_cg_dots_pqeq(const int *__restrict__ order, int ntot, int natoms,
                                                       const double4 *__restrict__ rowsum, const double2 *__restrict__ x,
@@ -160,8 +160,9 @@ __global__ void __launch_bounds__(256) k_cg_dots_pqeq(const int *__restrict__ or
                                                       const DevFF *__restrict__ ffp, const double4 *__restrict__ prow,
                                                       const double *__restrict__ pcs, const double4 *__restrict__ sps,
                                                       double *__restrict__ acc) {
+  if (!INIT && acc[ACC_DONE] != 0.0) return;
   const int slot = blockIdx.x * blockDim.x + threadIdx.x;
-  double part[7] = {0.0, 0.0, 0.0, 0.0, 0.0, 0.0, 0.0};
+  double part[5] = {0.0, 0.0, 0.0, 0.0, 0.0};
   double gpart[3] = {0.0, 0.0, 0.0};
   int i = -1;
   if (slot < ntot) i = order[slot];
@@ -191,7 +192,7 @@ __global__ void __launch_bounds__(256) k_cg_dots_pqeq(const int *__restrict__ or
     const double cj = pcs[slot];
     const double2 v = x[slot];
     if (INIT) { gpart[0] = cj * v.x; gpart[1] = cj * v.y; gpart[2] = cj * sps[slot].w; }
-    else { part[5] = cj * v.x; part[6] = cj * v.y; }
+    else { gpart[0] = cj * v.x; gpart[1] = cj * v.y; }
   }
   if (INIT) {
     double p2[2] = {part[0], part[1]};
@@ -199,15 +200,81 @@ __global__ void __launch_bounds__(256) k_cg_dots_pqeq(const int *__restrict__ or
     block_accumulate<3>(gpart, acc + 14);
   } else {
     if (slot == 0) part[0] += (acc[14] - acc[11] * acc[15]) + acc[16] + acc[17];   // ghost columns + E_ss, once per rank
-    block_accumulate<7>(part, acc + 0);
+    block_accumulate<5>(part, acc + 0);
+    double g2[2] = {gpart[0], gpart[1]};
+    block_accumulate<2>(g2, acc + 12);
   }
 }
-// k_roll_g + the ghost-column recurrences: qs_ghost += lmin_s hs_ghost  =>  acc[14] += lmin_s * acc[5]
-__global__ void k_roll_g_pqeq(double *__restrict__ acc, float lmin_s, float lmin_t) {
-  acc[14] += (double)lmin_s * acc[5];
-  acc[15] += (double)lmin_t * acc[6];
-  acc[9] = acc[7]; acc[10] = acc[8];
-  acc[5] = 0.0; acc[6] = 0.0; acc[7] = 0.0; acc[8] = 0.0;
+
+// ---------------------------------------------------------------------------------------------------
+// STRICT-ORDER validation path of PQEq (RXG_STRICT_ORDER=1, small systems): the literal two-product CG of src/pqeq.F90:96-166
+// with every per-row sum in list order and without FMA, like k_rows_strict_* of rxg_lists_qeq.cuh does for QEq.
+// fpqeq(i) in qeq_initialize's own accumulation order (src/pqeq.F90:336-343): one thread per resident row.
+__global__ void k_fpqeq_strict(const DevGrid g, int natoms, const long long *__restrict__ rowbeg, const long long *__restrict__ rowend,
+                               const int *__restrict__ col, const double *__restrict__ val, const double4 *__restrict__ sps,
+                               const DevFF *__restrict__ ffp, double *__restrict__ fpq) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= natoms) return;
+  const DevFF &ff = *ffp;
+  const int slot = g.slot_of[i], np = ff.ntype_pqeq;
+  const double4 me = g.sorted[slot];
+  const int ity = rec_type(me.w);
+  double fp = 0.0;
+  for (long long k = rowbeg[i]; k < rowend[i]; k++) {
+    const int js = col[k] & COL_MASK;
+    const double4 oj = g.sorted[js];
+    const int jty = rec_type(oj.w);
+    const double4 sj = sps[js];
+    fp = add_rn(fp, mul_rn(val[k], sj.w));                       // fpqeq = fpqeq + Cclmb0_qeq*pqeqc*Z_j, :336
+    if (ff.isPolarizable[jty - 1]) {                             // core_i - shell_j, :340-343
+      double E, dE;
+      const double dx = sub_rn(me.x, oj.x), dy = sub_rn(me.y, oj.y), dz = sub_rn(me.z, oj.z);
+      clmb_pqeq(ff, ff.TBL_psc, ff.inxnpqeq[(jty - 1) + np * (ity - 1)], sub_rn(dx, sj.x), sub_rn(dy, sj.y), sub_rn(dz, sj.z), E, dE);
+      fp = sub_rn(fp, mul_rn(mul_rn(CCLMB0_QEQ, E), sj.w));
+    }
+  }
+  fpq[i] = fp;
+}
+// get_hsh of src/pqeq.F90:368-439 per row: rowbuf[i] = {eta*hs + sum H hs, same for t, the row's share of Est, -}
+__global__ void k_rows_strict_hsh_pqeq(const DevGrid g, int natoms, const long long *__restrict__ rowbeg,
+                                       const long long *__restrict__ rowend, const int *__restrict__ col, const double *__restrict__ val,
+                                       const double4 *__restrict__ hsq, const double4 *__restrict__ sps, const DevFF *__restrict__ ffp,
+                                       double4 *__restrict__ rowbuf) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= natoms) return;
+  const DevFF &ff = *ffp;
+  const int slot = g.slot_of[i], np = ff.ntype_pqeq;
+  const double4 pi = g.sorted[slot], si = sps[slot], me = hsq[i];
+  const int ity = rec_type(pi.w);
+  const double eta = ff.eta[ity - 1], chi = ff.chi[ity - 1];
+  const bool poli = ff.isPolarizable[ity - 1] != 0;
+  const double qic = add_rn(me.z, si.w);
+  const double shx = add_rn(pi.x, si.x), shy = add_rn(pi.y, si.y), shz = add_rn(pi.z, si.z);
+  double ts = mul_rn(eta, me.x), tt = mul_rn(eta, me.y);
+  double es = add_rn(mul_rn(chi, me.z), mul_rn(mul_rn(mul_rn(0.5, eta), me.z), me.z));
+  for (long long k = rowbeg[i]; k < rowend[i]; k++) {
+    const int js = col[k] & COL_MASK;
+    const double4 oj = g.sorted[js], sj = sps[js];
+    const int j = rec_index(oj.w), jty = rec_type(oj.w);
+    const double4 x = hsq[j];
+    const double qjc = add_rn(x.z, sj.w);
+    const double h = val[k];
+    const double Ccicj = mul_rn(mul_rn(h, qic), qjc);
+    double Csicj = 0.0, Csisj = 0.0, E, dE;
+    if (poli) {
+      const int ix = ff.inxnpqeq[(ity - 1) + np * (jty - 1)];
+      clmb_pqeq(ff, ff.TBL_psc, ix, sub_rn(shx, oj.x), sub_rn(shy, oj.y), sub_rn(shz, oj.z), E, dE);
+      Csicj = mul_rn(mul_rn(mul_rn(-CCLMB0_QEQ, E), qjc), si.w);
+      if (ff.isPolarizable[jty - 1]) {
+        clmb_pqeq(ff, ff.TBL_pss, ix, sub_rn(shx, add_rn(oj.x, sj.x)), sub_rn(shy, add_rn(oj.y, sj.y)), sub_rn(shz, add_rn(oj.z, sj.z)), E, dE);
+        Csisj = mul_rn(mul_rn(mul_rn(CCLMB0_QEQ, E), si.w), sj.w);
+      }
+    }
+    ts = add_rn(ts, mul_rn(h, x.x));
+    tt = add_rn(tt, mul_rn(h, x.y));
+    es = add_rn(add_rn(es, mul_rn(0.5, add_rn(Ccicj, Csisj))), Csicj);
+  }
+  rowbuf[i] = make_double4(ts, tt, es, 0.0);
 }
 
 // update_shell_positions, src/pqeq.F90:187-259.  One warp per resident row; reads the by-slot copy of spos (sps), writes

@@ -70,6 +70,7 @@ def load_library():
     L.rxg_md_velocity_stats.argtypes = [vp, dp]
     L.rxg_md_velocity_affine.argtypes = [vp, dp, dp]
     L.rxg_debug_fetch.argtypes = [vp, C.c_char_p, vp, C.c_longlong, C.POINTER(C.c_longlong)]
+    L.rxg_debug_spmv.argtypes = [vp, dp, dp, C.c_int, dp]
     L.rxg_launch_count.argtypes = [vp]
     L.rxg_launch_count.restype = C.c_longlong
     _LIB = L
@@ -96,8 +97,9 @@ def rank_of_vid(vid, vprocs):
 
 _F64 = {"atype", "q", "qst", "gst", "hsq", "val", "BO0", "BO1", "BO2", "BO3", "dln_BOp1", "dln_BOp2", "dln_BOp3", "dBOp",
         "A0", "A1", "A2", "A3", "delta", "deltap1", "deltap2", "nlp", "dDlp", "deltalp", "cdbnd", "ccbnd", "pos", "f", "v", "spos",
-        "prow"}
-_I64 = {"rowbeg", "rowend", "nnz"}
+        "prow", "acc"}
+_I64 = {"rowbeg", "rowend", "nnz", "uoff", "rowoff"}
+_U8 = {"umask"}
 
 
 class Engine:
@@ -242,6 +244,16 @@ class Engine:
         assert sc.size == self.sys.pff.struct.nso and sh.size == 3
         self._chk(self.L.rxg_md_velocity_affine(self.h, _dp(sc), _dp(sh)))
 
+    def debug_spmv(self, x2, reps=1):
+        """Row sums {H.x1, H.x2, ghost-column parts} of the production SpMV for x2[ntot, 2] (atom order); also its time."""
+        ntot = int(self.fetch("copyptr")[6])
+        n = int(self.fetch("copyptr")[0])
+        x = np.ascontiguousarray(x2, dtype=np.float64).reshape(ntot, 2)
+        out = np.zeros((n, 4))
+        ms = C.c_double(0.0)
+        self._chk(self.L.rxg_debug_spmv(self.h, _dp(x), _dp(out), int(reps), C.byref(ms)))
+        return out, ms.value
+
     def natoms_resident(self):
         return int(self.fetch("copyptr")[0])
 
@@ -264,6 +276,8 @@ class Engine:
             out = np.empty(cnt.value, dtype=np.float64)
         elif name in _I64:
             out = np.empty(cnt.value, dtype=np.int64)
+        elif name in _U8:
+            out = np.empty(cnt.value, dtype=np.uint8)
         else:
             out = np.empty(cnt.value, dtype=np.int32)
         if cnt.value:

@@ -12,7 +12,7 @@ import numpy as np
 
 from . import setup as S
 from .ffield import read_ffield
-from .geninit import read_xyz, replicate
+from .geninit import read_xyz, replicate, hash_normal
 from .binding import PackedFF, PackedBox, RxgConfig
 
 
@@ -35,7 +35,7 @@ class System:
                maxneighbs10=1500, nmincell=S.NMINCELL, Lex_fqs=1.0, efield=None):
         c = RxgConfig()
         if nbuffer is None:
-            nmax = max(len(r["atype"]) for r in self.ranks)
+            nmax = max(len(r["atype"]) for r in self.ranks if r is not None)
             nbuffer = estimate_nbuffer(self, nmax)
         c.device, c.nbuffer, c.maxneighbs, c.maxneighbs10, c.nmincell = device, int(nbuffer), maxneighbs, maxneighbs10, nmincell
         c.isQEq, c.NMAXQEq, c.isPQEq, c.isEfield, c.eFieldDir = isQEq, NMAXQEq, int(self.pqeq is not None), 0, 1
@@ -58,16 +58,18 @@ def estimate_nbuffer(sysm, nres):
 
 
 def build_system(xyz_path, ffield_path, mc=(1, 1, 1), vprocs=(1, 1, 1), isLG=False, real_coords=False,
-                 displace_sigma=0.0, seed=20261017, pqeq_path=None):
+                 displace_sigma=0.0, seed=20261017, pqeq_path=None, only_rank=None):
+    """`only_rank=r`: generate rank r's atoms alone (`ranks[r']` is None for the others) -- what one process of a multi-GPU
+    run needs; time and memory then scale with that rank's share."""
     ff = read_ffield(ffield_path, isLG=isLG)
     types0, pos0, lat0 = read_xyz(xyz_path, ff.atmname, real_coords=real_coords)
     displace = None
     if displace_sigma > 0.0:
-        rng0 = np.random.default_rng(seed)
         Hbig = S.get_box_params(lat0[0] * mc[0], lat0[1] * mc[1], lat0[2] * mc[2], lat0[3], lat0[4], lat0[5])
         Hbig_i = np.linalg.inv(Hbig)
-        displace = lambda n: rng0.normal(0.0, displace_sigma, (n, 3)) @ Hbig_i.T
-    gen = replicate(types0, pos0, lat0, mc, vprocs, displace=displace)
+        # Gaussian displacements indexed by global atom id (counter-based), so every decomposition sees the same geometry
+        displace = lambda gid: (displace_sigma * hash_normal(seed, gid)) @ Hbig_i.T
+    gen = replicate(types0, pos0, lat0, mc, vprocs, displace=displace, only_rank=only_rank)
     lattice = gen["lattice"]
     rctap = S.RCTAP0_PQEQ if pqeq_path else S.RCTAP0   # src/init.F90:28-32
     CTap = S.taper(rctap)
@@ -95,6 +97,9 @@ def build_system(xyz_path, ffield_path, mc=(1, 1, 1), vprocs=(1, 1, 1), isLG=Fal
     ranks = []
     for r in range(nprocs):
         g = gen["ranks"][r]
+        if g is None:
+            ranks.append(None)
+            continue
         b = boxes[r]
         obox = np.array(list(b.struct.OBOX))
         rn = g["pos_local"] + obox                       # xs2xu, src/main.F90:637-654

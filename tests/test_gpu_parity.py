@@ -4,9 +4,13 @@ Bars (BASELINE.json north_star):
   * cell assignments, 10 A lists, bond lists: bit-exact (here even in the reference's row ORDER);
   * QEq matrix (hessian): bit-exact;
   * energies and forces: relative <= 1e-9 (forces relative to max |f|), with identical charges on both sides;
-  * charges: <= 1e-8 in the serial-order validation mode (RXG_STRICT_ORDER=1), which is bit-identical to the oracle.
-    The production reduction order differs from the reference's serial loops by round-off only, which the reference's
-    CG amplifies (tests/test_cg_sensitivity.py); there the bar is the reference's own build-to-build spread.
+  * charges: <= 1e-8 in the serial-order validation mode (RXG_STRICT_ORDER=1), which is bit-identical to the oracle, on all
+    five systems.  The PRODUCTION CG (the kernels bench.py times) is held to the oracle iterate by iterate: after exactly k
+    iterations (NMAXQEq = k) the charges agree to the bars of CG_TRACE_BARS (1e-13 at k <= 4 ... 1e-6 at k = 20).  The growth
+    with k is the reference algorithm's own amplification of summation-order round-off (its real(4) step length keeps the CG
+    from converging cleanly; tests/test_cg_sensitivity.py shows 4e-5 between an FMA and a no-FMA build of the same loops),
+    measured on B200 in profiles/r02_cg_spread.log.  With the stop rule the bar is CG_STOP_BAR_SAME when both sides stop in
+    the same iteration and CG_STOP_BAR_DIFF when the round-off moves the stop by an iteration or more.
 """
 import os
 
@@ -22,6 +26,13 @@ FTOL = 1e-9          # relative to max |f|
 ETOL = 1e-9          # relative, per energy term
 QTOL = 1e-8          # charges, strict mode
 UTIME = 1.0e3 / 20.455
+# production CG vs oracle after exactly k iterations: measured 3e-15 (k<=4), 8e-14 (6), 7e-11 (10), 2e-7 (20) at worst over the
+# five systems (profiles/r02_cg_spread.log); bars = about 3x the worst case
+CG_TRACE_BARS = {1: 1e-14, 2: 1e-14, 3: 2e-14, 4: 1e-13, 6: 1e-12, 10: 1e-9, 20: 1e-6}
+# with the stop rule at QEq_tol 1e-7: measured <= 1.0e-7 when the iteration counts coincide (56 iterations on RDX 2x2x2),
+# <= 2.6e-5 when they differ (37 vs 41 on the 168-atom cell)
+CG_STOP_BAR_SAME = 3e-7
+CG_STOP_BAR_DIFF = 1e-4
 
 
 def systems():
@@ -55,10 +66,11 @@ def rows(e, n):
 
 @pytest.fixture(autouse=True)
 def _clean_env():
-    for k in ("RXG_STRICT_ORDER", "RXG_QEQ_TWOPASS", "RXG_SPMV_NOTMA"):
+    keys = ("RXG_STRICT_ORDER", "RXG_QEQ_TWOPASS", "RXG_FUSE_API", "RXG_NO_FUSE", "RXG_SPMV", "RXG_SPMV_SHAPE", "RXG_SPMV_STAGE", "RXG_SPMV_RING")
+    for k in keys:
         os.environ.pop(k, None)
     yield
-    for k in ("RXG_STRICT_ORDER", "RXG_QEQ_TWOPASS", "RXG_SPMV_NOTMA"):
+    for k in keys:
         os.environ.pop(k, None)
 
 
@@ -84,8 +96,10 @@ def test_lists_matrix_energies_forces(built, name):
         assert np.array_equal(col[rb[i]:re_[i]], lst_o[i, :cnt_o[i]]), f"10 A row {i}"
         assert np.array_equal(val[rb[i]:re_[i]], hes_o[i, :cnt_o[i]]), f"hessian row {i}"
     assert abs(q[:n].sum()) < 1e-9
-    # production CG vs the serial reference order: same solution to the reference's own reproducibility
-    assert np.abs(q[:n] - o.f64("q")[:n]).max() < 2e-3
+    # production CG vs the serial reference order (bars: module docstring)
+    dq, same = np.abs(q[:n] - o.f64("q")[:n]).max(), e.nstep_qeq == o.observe()[3]
+    print(f"{name}: nstep_qeq {e.nstep_qeq} vs {o.observe()[3]}, max |dq| {dq:.2e}")
+    assert dq <= (CG_STOP_BAR_SAME if same else CG_STOP_BAR_DIFF)
     # ---- FORCE with identical charges
     q[:n] = o.f64("q")[:n]
     o.force()
@@ -116,7 +130,112 @@ def test_lists_matrix_energies_forces(built, name):
     e.close(); o.close()
 
 
-@pytest.mark.parametrize("name", ["rdx_1x1x1", "rdx_2x2x2_disp"])
+@pytest.mark.parametrize("name", list(systems().keys()))
+@pytest.mark.parametrize("spmv", ["rows", "items"])
+def test_production_cg_follows_oracle_iterates(built, name, spmv):
+    """The benchmarked CG (single sparse product per iteration, residual recurrence, device-side stop rule and real(4) step
+    lengths) against the oracle's literal two-product CG after exactly k iterations, k = 1..20."""
+    if spmv == "items":
+        os.environ["RXG_SPMV"] = "items"
+    worst = {}
+    for k, bar in CG_TRACE_BARS.items():
+        s, cfg, e, o = make(name, NMAXQEq=k)
+        atype, pos, v, f, q = e.host_arrays(s.ranks[0])
+        n = e.NATOMS
+        o.qeq(); e.QEq(atype, pos, q)
+        assert e.nstep_qeq == o.observe()[3] == k
+        worst[k] = np.abs(q[:n] - o.f64("q")[:n]).max()
+        assert np.array_equal(e.fetch("pos"), o.f64("pos"))      # same number of COPYATOMS round trips (SURVEY Q8)
+        e.close(); o.close()
+        assert worst[k] <= bar, (k, worst[k])
+    print(f"{name} [{spmv}]: max |dq| after k iterations: " + ", ".join(f"{k}: {d:.1e}" for k, d in worst.items()))
+
+
+@pytest.mark.parametrize("name", ["rdx_2x2x2_disp", "water_4x3x3_disp"])
+def test_fused_api_list_and_forces(built, name):
+    """RXG_FUSE_API=1 (what bench.py's e2e leg and rxg_md_run use): rxg_qeq builds the halo at FORCE's width and ONE 10 A list
+    with FORCE's fp64 predicate (k_pairlist<2,*>), zero hessian where only the QEq real(4) test fails; the rxg_force that
+    follows reuses both.  Rows must equal the oracle's FORCE list entry by entry, the non-zero hessian entries must be the
+    oracle's QEq list as a set, and charges / forces must meet the same bars as the literal two-list path."""
+    os.environ["RXG_FUSE_API"] = "1"
+    s, cfg, e, o = make(name, NMAXQEq=4)
+    atype, pos, v, f, q = e.host_arrays(s.ranks[0])
+    n = e.NATOMS
+    W = cfg.maxneighbs10
+    o.qeq()
+    qeq_cnt, qeq_lst = o.i32("nbpcnt").copy(), o.i32("nbplist").reshape(n, W).copy()
+    qeq_hes, qeq_pos, qeq_at = o.f64("hessian").reshape(n, W).copy(), o.f64("pos").reshape(3, -1).copy(), o.f64("atype").copy()
+    e.QEq(atype, pos, q)
+    assert np.abs(q[:n] - o.f64("q")[:n]).max() <= CG_TRACE_BARS[4]
+    rb, re_, col = rows(e, n)
+    val = e.fetch("val")
+    g_pos, g_at = e.fetch("pos").reshape(3, -1), e.fetch("atype")
+    # (a) non-zero hessian entries == the oracle's QEq list, keyed by (neighbour's global id, separation vector)
+    def keyset(i, idx, P, A):
+        gid = np.rint((A[idx] - np.rint(A[idx])) * 1e13).astype(np.int64)
+        d = np.rint((P[:, idx] - P[:, [i]]) * 1e6).astype(np.int64)
+        return set(zip(gid.tolist(), d[0].tolist(), d[1].tolist(), d[2].tolist()))
+    for i in range(0, n, 7):
+        cg, hg = col[rb[i]:re_[i]], val[rb[i]:re_[i]]
+        co, ho = qeq_lst[i, :qeq_cnt[i]], qeq_hes[i, :qeq_cnt[i]]
+        assert keyset(i, cg[hg != 0.0], g_pos, g_at) == keyset(i, co[ho != 0.0], qeq_pos, qeq_at), f"QEq pairs of row {i}"
+        assert np.array_equal(np.sort(hg[hg != 0.0]), np.sort(ho[ho != 0.0])), f"hessian values of row {i}"
+    # (b) the FORCE that follows reuses halo and list: rows == the oracle's FORCE list (same halo, hence same local indices)
+    launches0, t0 = e.launches(), e.timers()
+    qo = q[:n].copy()
+    o.set_atoms(0, s.ranks[0]["atype"], s.ranks[0]["pos"], None, qo)
+    o.force()
+    e.FORCE(atype, pos, f, q)
+    assert e.timers()[22] - t0[22] == 1, "rxg_force did not reuse the list of the preceding rxg_qeq"
+    cnt_o, lst_o = o.i32("nbpcnt"), o.i32("nbplist").reshape(n, W)
+    assert np.array_equal(e.fetch("copyptr"), o.i32("copyptr"))
+    assert np.array_equal(re_ - rb, cnt_o)
+    for i in range(n):
+        assert np.array_equal(col[rb[i]:re_[i]], lst_o[i, :cnt_o[i]]), f"FORCE row {i}"
+    pe_o = o.f64("PE")
+    for k in range(1, 14):
+        assert abs(e.PE[k] - pe_o[k]) <= ETOL * max(abs(pe_o[k]), 1e-6 * np.abs(pe_o[1:]).max()), f"PE({k})"
+    fo = o.f64("f").reshape(3, -1)[:, :n]
+    assert np.abs(f[:, :n] - fo).max() <= FTOL * np.abs(fo).max()
+    # (c) one device-resident step (rxg_md_run shares the list the same way) against one oracle step
+    s2, cfg2, e2, o2 = make(name, NMAXQEq=4)
+    atype, pos, v, f, q = e2.host_arrays(s2.ranks[0])
+    dt = 0.25 / UTIME
+    e2.state_upload(atype, pos, v, q)
+    e2.md_prime(); o2.qeq(); o2.force()
+    e2.md_run(1, dt, 1, 0.0, 0); o2.md_run(1, dt, 1, 0.0, 0)
+    e2.state_download(atype, pos, v, f, q)
+    nn = e2.NATOMS
+    fo = o2.f64("f").reshape(3, -1)[:, :nn]
+    assert np.abs(q[:nn] - o2.f64("q")[:nn]).max() <= 10 * CG_TRACE_BARS[4]   # two QEq calls of 4 iterations each
+    assert np.abs(f[:, :nn] - fo).max() <= FTOL * np.abs(fo).max()
+    assert np.abs(pos[:, :nn] - o2.f64("pos").reshape(3, -1)[:, :nn]).max() < 1e-11
+    e.close(); o.close(); e2.close(); o2.close()
+
+
+@pytest.mark.parametrize("name", ["rdx_2x2x2_disp", "sicnp_1x1x1"])
+def test_extended_lagrangian_isqeq2(built, name):
+    """isQEq = 2 (src/qeq.F90:51-57): qs starts from the mix Lex_fqs*qsfp + (1-Lex_fqs)*q, ONE CG step, qsfp/qsfv untouched."""
+    s, cfg, e, o = make(name, isQEq=2, Lex_fqs=0.7)
+    atype, pos, v, f, q = e.host_arrays(s.ranks[0])
+    n = e.NATOMS
+    rng = np.random.default_rng(5)
+    q0 = rng.normal(0.0, 0.2, n); q0 -= q0.mean()
+    qsfp0 = q0 + rng.normal(0.0, 0.02, n)
+    qsfv0 = rng.normal(0.0, 1e-3, n)
+    q[:n] = q0
+    e.qsfp[:n], e.qsfv[:n] = qsfp0, qsfv0
+    o.set_atoms(0, s.ranks[0]["atype"], s.ranks[0]["pos"], None, q0, qsfp0, qsfv0)
+    o.qeq(); e.QEq(atype, pos, q)
+    assert e.nstep_qeq == o.observe()[3] == 1
+    assert np.abs(q[:n] - o.f64("q")[:n]).max() <= 1e-13
+    assert np.abs(q[:n] - q0).max() > 1e-3                          # the step did move the charges
+    assert np.array_equal(e.qsfp[:n], qsfp0) and np.array_equal(e.qsfv[:n], qsfv0)
+    assert np.array_equal(o.f64("qsfp")[:n], qsfp0)
+    e.close(); o.close()
+
+
+@pytest.mark.parametrize("name", list(systems().keys()))
 def test_strict_order_charges_and_trajectory(built, name):
     """Serial summation order, no FMA: charges, iteration counts and a 10-step NVE trajectory equal the oracle's."""
     os.environ["RXG_STRICT_ORDER"] = "1"
@@ -163,8 +282,8 @@ def test_cg_modes_agree_within_reference_spread(built):
         e.close(); o.close()
     for k in ("RXG_STRICT_ORDER", "RXG_QEQ_TWOPASS"):
         os.environ.pop(k, None)
-    assert np.abs(res["single"] - res["strict"]).max() < 2e-3
-    assert np.abs(res["twopass"] - res["strict"]).max() < 2e-3
+    assert np.abs(res["single"] - res["strict"]).max() <= CG_STOP_BAR_DIFF
+    assert np.abs(res["twopass"] - res["strict"]).max() <= CG_STOP_BAR_DIFF
     s, cfg, e, o = make("rdx_2x2x2_disp", QEq_tol=1e-13, NMAXQEq=400)
     atype, pos, v, f, q = e.host_arrays(s.ranks[0])
     o.qeq(); e.QEq(atype, pos, q)
@@ -282,7 +401,8 @@ def test_full_size_properties(built):
     assert abs(q[:n].sum()) < 1e-6
     rb, re_ = e.fetch("rowbeg"), e.fetch("rowend")
     assert np.array_equal(re_ - rb, cnt1[cell_atom])
-    assert np.abs(q[:n] - q1[cell_atom]).max() < 2e-3
+    # (two different systems, each stopped by its own Est: the 18^3 crystal runs more iterations than its 168-atom cell)
+    assert np.abs(q[:n] - q1[cell_atom]).max() <= 3 * CG_STOP_BAR_DIFF
     # FORCE with the tiled unit-cell charges: per-atom energies of the unit cell
     q[:n] = q1[cell_atom]
     e.FORCE(atype, pos, f, q)

@@ -4,8 +4,11 @@ Inputs: the reference's examples/3-reaxpq+ polyethylene cell (12 atoms, C/H) wit
 example's own `geninit -mc 2 3 5` (360 atoms, rctap = 12.5 A), displaced, with non-zero shell displacements.
 
 Bars: 12.5 A list and hessian bit-exact; fpqeq <= 1e-12 relative; one shell relaxation step with identical charges
-<= 1e-9; energies/forces of FORCE (ENbond_PQEq + the bonded terms) with identical charges and shells <= 1e-9; charges of
-the production CG within the reference's own build-to-build spread (see test_gpu_parity.py) and < 1e-6 at tight tolerance.
+<= 1e-9; energies/forces of FORCE (ENbond_PQEq + the bonded terms) with identical charges and shells <= 1e-9.  Charges: the
+serial-order validation mode (RXG_STRICT_ORDER=1, src/pqeq.F90:96-166 operation by operation) must reproduce the oracle's
+iteration count and charges to 1e-8 (it is bit-identical in practice); the PRODUCTION CG is held to the oracle after exactly
+k iterations (PQ_TRACE_BARS) and, with the stop rule, to PQ_STOP_BAR_SAME when both stop in the same iteration (measured
+2e-13 / 1.6e-11, profiles/r02_cg_spread.log) -- PQEq's CG takes 10-12 iterations and amplifies round-off far less than QEq's.
 """
 import os
 
@@ -18,6 +21,8 @@ pytestmark = pytest.mark.gpu
 
 INP = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "inputs", "init.pe.pqeq")
 UTIME = 1.0e3 / 20.455
+PQ_TRACE_BARS = {1: 1e-15, 2: 1e-14, 4: 1e-14, 6: 5e-14, 10: 2e-12}     # measured 3e-17, 1.5e-15, 1.3e-15, 5.7e-15, 2.1e-13
+PQ_STOP_BAR_SAME, PQ_STOP_BAR_DIFF = 1e-9, 1e-4
 
 
 def make(mc=(2, 3, 5), sigma=0.03, par="pqeq1.par", shell_sigma=4e-3, **cfgkw):
@@ -84,8 +89,10 @@ def test_pqeq_charges_and_forces(built, shell_sigma):
     e.PQEq(atype, pos, q)
     qo = o.f64("q")[:n]
     assert abs(q[:n].sum()) < 1e-9
-    assert np.abs(q[:n] - qo).max() < 2e-3                             # production order vs serial order (reference spread)
-    assert abs(e.nstep_qeq - o.i32("nstep_qeq")[0]) <= 8                 # the stop test is noise-sensitive (test_cg_sensitivity)
+    same = e.nstep_qeq == o.i32("nstep_qeq")[0]
+    print(f"pqeq shell_sigma={shell_sigma}: nstep {e.nstep_qeq} vs {o.i32('nstep_qeq')[0]}, max |dq| {np.abs(q[:n] - qo).max():.2e}")
+    assert np.abs(q[:n] - qo).max() <= (PQ_STOP_BAR_SAME if same else PQ_STOP_BAR_DIFF)   # production order vs serial order
+    assert abs(e.nstep_qeq - o.i32("nstep_qeq")[0]) <= 2
     sp_o = o.f64("spos").reshape(3, -1)[:, :n]
     assert np.abs(e.spos[:, :n] - sp_o).max() < 2e-5                   # shells follow the charges
     # ---- FORCE with identical charges and shells
@@ -102,6 +109,47 @@ def test_pqeq_charges_and_forces(built, shell_sigma):
     assert np.abs(f[:, :n].sum(axis=1)).max() < 1e-9 * np.abs(fo).max() * n
     assert np.allclose(e.astr, o.f64("astr"), rtol=1e-8, atol=1e-8 * np.abs(o.f64("astr")).max())
     e.close(); o.close()
+
+
+@pytest.mark.parametrize("shell_sigma", [0.0, 4e-3])
+def test_pqeq_production_cg_follows_oracle_iterates(built, shell_sigma):
+    """The benchmarked PQEq CG (one sparse product per iteration, Est from column sums, device-side stop rule) against the
+    oracle's literal get_hsh / get_gradient of src/pqeq.F90 after exactly k iterations."""
+    for k, bar in PQ_TRACE_BARS.items():
+        s, cfg, e, o, sp = make(shell_sigma=shell_sigma, NMAXQEq=k)
+        atype, pos, v, f, q = e.host_arrays(s.ranks[0])
+        n = e.NATOMS
+        e.spos[:, :n] = sp
+        o.set_spos(0, sp)
+        o.qeq(); e.PQEq(atype, pos, q)
+        assert e.nstep_qeq == o.i32("nstep_qeq")[0] == k
+        d = np.abs(q[:n] - o.f64("q")[:n]).max()
+        e.close(); o.close()
+        assert d <= bar, (k, d)
+
+
+@pytest.mark.parametrize("shell_sigma", [0.0, 4e-3])
+def test_pqeq_strict_order_matches_oracle(built, shell_sigma):
+    """RXG_STRICT_ORDER=1 for PQEq: fpqeq, the row sums of get_hsh / get_gradient and the scalar sums in the reference's serial
+    order without FMA -- same iteration count, charges <= 1e-8 (north_star), shells to round-off."""
+    os.environ["RXG_STRICT_ORDER"] = "1"
+    try:
+        s, cfg, e, o, sp = make(shell_sigma=shell_sigma)
+        atype, pos, v, f, q = e.host_arrays(s.ranks[0])
+        n = e.NATOMS
+        e.spos[:, :n] = sp
+        o.set_spos(0, sp)
+        o.qeq(); e.PQEq(atype, pos, q)
+        d = np.abs(q[:n] - o.f64("q")[:n]).max()
+        print(f"pqeq strict shell_sigma={shell_sigma}: nstep {e.nstep_qeq} vs {o.i32('nstep_qeq')[0]}, max |dq| {d:.2e}")
+        assert e.nstep_qeq == o.i32("nstep_qeq")[0]
+        assert d <= 1e-8
+        assert np.array_equal(e.fetch("pos"), o.f64("pos"))
+        sp_o = o.f64("spos").reshape(3, -1)[:, :n]
+        assert np.abs(e.spos[:, :n] - sp_o).max() <= 1e-12
+        e.close(); o.close()
+    finally:
+        os.environ.pop("RXG_STRICT_ORDER", None)
 
 
 def test_pqeq_tight_tolerance_converges_to_oracle(built):
@@ -129,7 +177,7 @@ def test_pqeq_efield_and_nine_element_file(built):
     e.PQEq(atype, pos, q)
     qo = o.f64("q")[:n]
     sp_o = o.f64("spos").reshape(3, -1)[:, :n]
-    assert np.abs(q[:n] - qo).max() < 2e-3
+    assert np.abs(q[:n] - qo).max() <= (PQ_STOP_BAR_SAME if e.nstep_qeq == o.i32("nstep_qeq")[0] else PQ_STOP_BAR_DIFF)
     q[:n] = qo
     e.spos[:, :n] = sp_o
     e._chk(e.L.rxg_spos_upload(e.h, n, e.spos.ctypes.data_as(e.L.rxg_spos_upload.argtypes[2])))

@@ -1,0 +1,146 @@
+"""Kernel-level parity of the CG's sparse product (the kernel bench.py's roofline is quoted on), through the C-ABI.
+
+`rxg_debug_spmv` runs exactly the launch the production CG issues -- k_spmv_rows, whose three launch shapes and unstaged
+path are forced in turn through the RXG_SPMV* switches; RXG_SPMV=items selects the experimental cell-blocked kernel
+k_spmv_items (full-size ring, small ring, unstaged walk) -- on a given vector pair and returns the four raw row sums per
+resident row.  They are compared with an extended-precision NumPy product of the SAME matrix, fetched from the device and
+already proven bit-identical to the oracle's hessian / nbplist (reference src/qeq.F90:222-240) in test_gpu_parity; the
+bar is 1e-13 of sum_j |H_ij x_j|, i.e. summation-order round-off only.  The union stream that k_spmv_items walks is checked
+structurally against the rows it was built from.
+"""
+import os
+
+import numpy as np
+import pytest
+
+from rxmd_b200.host.system import build_system
+
+pytestmark = pytest.mark.gpu
+
+INP = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "inputs")
+SPMV_ENV = ("RXG_SPMV", "RXG_SPMV_SHAPE", "RXG_SPMV_STAGE", "RXG_SPMV_RING", "RXG_FUSE_API")
+
+VARIANTS = {
+    "items": {},
+    "items_3stage": {"RXG_SPMV_RING": "3"},
+    "items_unstaged": {"RXG_SPMV_STAGE": "0"},
+    "items_shared_list": {"RXG_FUSE_API": "1"},      # the list rxg_md_run / bench.py use: FORCE predicate, zero hessian entries
+    "rows_auto": {"RXG_SPMV": "rows"},
+    "rows_8x8": {"RXG_SPMV": "rows", "RXG_SPMV_SHAPE": "8x8"},
+    "rows_4x16": {"RXG_SPMV": "rows", "RXG_SPMV_SHAPE": "4x16"},
+    "rows_2x32": {"RXG_SPMV": "rows", "RXG_SPMV_SHAPE": "2x32"},
+    "rows_unstaged": {"RXG_SPMV": "rows", "RXG_SPMV_STAGE": "0"},
+}
+
+
+def systems():
+    from test_gpu_parity import systems as base
+    s = dict(base())
+    pe = os.path.join(INP, "init.pe.pqeq")
+    # polyethylene with the 12.5 A PQEq cut-off: ~1060 entries per row, the long-row case (k_spmv_rows<2,32,1216>)
+    s["pe_pqeq_4x6x11"] = dict(xyz=os.path.join(pe, "input.xyz"), ff=os.path.join(pe, "ffield"), mc=(4, 6, 11), displace_sigma=0.02,
+                               pqeq_path=os.path.join(pe, "pqeq1.par"))
+    return s
+
+
+@pytest.fixture(autouse=True)
+def _clean_env():
+    for k in SPMV_ENV:
+        os.environ.pop(k, None)
+    yield
+    for k in SPMV_ENV:
+        os.environ.pop(k, None)
+
+
+def _engine(name, env):
+    from rxmd_b200.host.engine import Engine
+    os.environ.update(env)
+    kw = dict(systems()[name])
+    s = build_system(kw.pop("xyz"), kw.pop("ff"), **kw)
+    cfg = s.config(NMAXQEq=2)                     # two CG iterations are enough to leave the matrix on the device
+    e = Engine(s, cfg)
+    atype, pos, v, f, q = e.host_arrays(s.ranks[0])
+    if cfg.isPQEq:
+        e.PQEq(atype, pos, q)
+    else:
+        e.QEq(atype, pos, q)
+    return s, cfg, e
+
+
+def _reference_rowsums(e, x):
+    n = e.NATOMS
+    rb, re_, col, val = e.fetch("rowbeg"), e.fetch("rowend"), e.fetch("col"), e.fetch("val")
+    xl = x.astype(np.longdouble)
+    ref = np.zeros((n, 4), dtype=np.longdouble)
+    scale = np.zeros((n, 2))
+    for i in range(n):
+        c = col[rb[i]:re_[i]]
+        h = val[rb[i]:re_[i]].astype(np.longdouble)
+        p = h[:, None] * xl[c]
+        g = c >= n                                  # ghost columns (Est weighting)
+        ref[i, :2] = p.sum(axis=0)
+        ref[i, 2:] = p[g].sum(axis=0)
+        scale[i] = np.abs(p).sum(axis=0).astype(np.float64)
+    return ref.astype(np.float64), scale
+
+
+@pytest.mark.parametrize("name", list(systems().keys()))
+@pytest.mark.parametrize("variant", list(VARIANTS.keys()))
+def test_spmv_rowsums_match_numpy(built, name, variant):
+    s, cfg, e = _engine(name, VARIANTS[variant])
+    ntot = int(e.fetch("copyptr")[6])
+    rng = np.random.default_rng(11)
+    x = rng.normal(0.0, 1.0, (ntot, 2))
+    got, _ = e.debug_spmv(x)
+    ref, scale = _reference_rowsums(e, x)
+    sc = np.maximum(np.concatenate([scale, scale], axis=1), 1e-300)
+    err = np.abs(got - ref) / sc
+    print(f"{name} {variant}: max rel err {err.max():.2e} (rows {e.NATOMS}, nnz {int(e.fetch('nnz')[0])})")
+    assert err.max() <= 1e-13
+    e.close()
+
+
+@pytest.mark.parametrize("name", list(systems().keys()))
+def test_union_stream_matches_rows(built, name):
+    """Per block of <= 8 consecutive rows of a cell, the union stream holds exactly the columns of those rows: replaying a
+    row's bits in stream order reproduces the row (same columns, same order), so a value is found at the row's running
+    position; padding entries carry an empty row set."""
+    s, cfg, e = _engine(name, {"RXG_SPMV": "items"})
+    n = e.NATOMS
+    ntot = int(e.fetch("copyptr")[6])
+    rb, re_, col = e.fetch("rowbeg"), e.fetch("rowend"), e.fetch("col")
+    order, uoff, ucol, umask, cell = e.fetch("order_nb"), e.fetch("uoff"), e.fetch("ucol"), e.fetch("umask"), e.fetch("cell_nb")
+    ghost = ucol < 0
+    uatom = order[ucol & 0x7fffffff]
+    real_entry = umask != 0                             # padding repeats a column of the block without its ghost bit
+    assert np.array_equal(ghost[real_entry], (uatom >= n)[real_entry])
+    assert uoff[ntot] == len(ucol)
+    seen_rows = 0
+    s0 = 0
+    while s0 < ntot:
+        i0 = order[s0]
+        if i0 >= n:                                  # ghost slots own no block
+            assert uoff[s0 + 1] == uoff[s0]
+            s0 += 1
+            continue
+        # block = up to 8 consecutive slots of one cell
+        nr = 1
+        while nr < 8 and s0 + nr < ntot and cell[order[s0 + nr]] == cell[i0] and order[s0 + nr] < n:
+            nr += 1
+        # blocks start at the cell's first slot: a cell's 9th row starts a new block
+        a, b = uoff[s0], uoff[s0 + 1]
+        assert (b - a) % 16 == 0                        # bulk-copy granularity of the row sets
+        for r in range(1, nr):
+            assert uoff[s0 + r + 1] == uoff[s0 + r]
+        cols, bits = uatom[a:b], umask[a:b]
+        for r in range(nr):
+            i = order[s0 + r]
+            mine = cols[(bits >> r) & 1 == 1]
+            assert np.array_equal(mine, col[rb[i]:re_[i]]), f"row {i} (slot {s0 + r})"
+            seen_rows += 1
+        assert not np.any(bits >> nr)                # no bits beyond the block's rows
+        real = bits != 0
+        assert not np.any(real[np.argmin(real):]) if not real.all() else True    # padding sits at the end
+        s0 += nr
+    assert seen_rows == n
+    e.close()

@@ -20,6 +20,16 @@ for w in WANT:
     if w in hdr:
         i = hdr.index(w)
         out[w] = (r[i] + ' ' + units[i]).strip()
+# every warp-stall reason (per issue-active cycle), largest first
+stalls = {h: float(r[i]) for i, h in enumerate(hdr) if h.startswith('smsp__average_warps_issue_stalled_') and h.endswith('_per_issue_active.ratio') and r[i]}
+out['stalls_per_issue'] = {k.replace('smsp__average_warps_issue_stalled_', '').replace('_per_issue_active.ratio', ''): round(v, 3)
+                           for k, v in sorted(stalls.items(), key=lambda kv: -kv[1])[:8]}
+for w in ('launch__occupancy_limit_registers', 'launch__occupancy_limit_shared_mem', 'launch__occupancy_limit_warps', 'launch__shared_mem_per_block_dynamic',
+          'smsp__warps_eligible.avg.per_cycle_active', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum', 'l1tex__data_pipe_lsu_wavefronts.sum',
+          'lts__t_sectors_srcunit_tex_op_read_lookup_hit.sum', 'lts__t_sectors_srcunit_tex_op_read_lookup_miss.sum', 'sm__cycles_active.avg'):
+    if w in hdr:
+        i = hdr.index(w)
+        out[w] = (r[i] + ' ' + units[i]).strip()
 src = subprocess.run(['ncu', '-i', rep, '--page', 'source', '--csv'], capture_output=True, text=True).stdout
 srows = list(csv.reader(io.StringIO(src)))
 if len(srows) > 2:

@@ -6,12 +6,14 @@ import bench
 from rxmd_b200.host.engine import Engine
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--mc", type=int, nargs=3, default=[18, 18, 18])
+ap.add_argument("--config", default="rdx")
+ap.add_argument("--mc", type=int, nargs=3, default=None)
 ap.add_argument("--steps", type=int, default=2)
 ap.add_argument("--sigma", type=float, default=0.02)
 a = ap.parse_args()
-s, mc, vp = bench.workload(a, 1)
-cfg = s.config()
+from rxmd_b200.host.configs import build_config
+s, mc, vp, cfgkw, label = build_config(a.config, mc=a.mc, sigma=a.sigma)
+cfg = s.config(**cfgkw)
 e = Engine(s, cfg)
 atype, pos, v, f, q = e.host_arrays(s.ranks[0])
 e.state_upload(atype, pos, v, q)
