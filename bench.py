@@ -198,7 +198,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    from rxmd_b200.host.engine import Engine, MODE_MOVE
+    from rxmd_b200.host.engine import Engine, MODE_MOVE, HINT_ATOMS_ON_DEVICE, HINT_Q_ON_DEVICE, HINT_DEFER_POS
     from rxmd_b200.host.configs import build_config
     # e2e leg: let rxg_force reuse the halo and 10 A list of the rxg_qeq that precedes it when the host hands back
     # bit-identical atoms (verified on the device); rxg_md_run does the same sharing internally
@@ -323,13 +323,18 @@ def main():
 
         def host_step():
             nonlocal n
+            # the hints are what rxmd_b200/gpu_shim.F90 states inside the main loop: nothing touches atype/pos/q between
+            # COPYATOMS(MOVE), QEq and FORCE (src/main.F90:75-84), so pos travels up once and down once per step
             first_half(n, dt, lw2, dthm_of_type, h_atype, h_v, h_f, h_q, e.qsfp, e.qsfv, h_pos)   # :64-72
+            e.hint(HINT_DEFER_POS)
             e.COPYATOMS(MODE_MOVE, [0.0, 0.0, 0.0], h_atype, h_pos, h_v, h_f, h_q)    # :75
             n = e.NATOMS
+            e.hint(HINT_ATOMS_ON_DEVICE | HINT_Q_ON_DEVICE | HINT_DEFER_POS)
             if pq:
                 e.PQEq(h_atype, h_pos, h_q)                                            # :78
             else:
                 e.QEq(h_atype, h_pos, h_q)                                             # :80
+            e.hint(HINT_ATOMS_ON_DEVICE | HINT_Q_ON_DEVICE)
             e.FORCE(h_atype, h_pos, h_f, h_q)                                          # :84
             second_half(n, dt, lw2, dthm_of_type, h_atype, h_v, h_f, h_q, e.qsfp, e.qsfv)         # :86-98
         host_step()

@@ -127,6 +127,23 @@ int rxg_comm_unique_id(void *out128);
 int rxg_destroy(rxg_handle h);
 const char *rxg_last_error(rxg_handle h);
 
+/* ---- optional promises of the host about the NEXT entry-point call (cleared by that call) ----------------
+ * The reference's main loop calls COPYATOMS(MODE_MOVE), QEq, FORCE back to back on the same arrays (src/main.F90:75-84) and
+ * touches none of them in between.  A shim that knows this may say so, and the library then skips the PCIe copies that
+ * would only move bytes it already holds.  Without hints every call is literal: all inputs up, all outputs down.
+ *   RXG_HINT_ATOMS_ON_DEVICE  atype/pos (and natoms) of the next call are exactly what the previous call left on the device
+ *                             (the host did not write them since): do not upload them; rxg_force then also reuses the halo
+ *                             and 10 A list of the rxg_qeq before it without re-verifying the atoms (RXG_FUSE_API=1)
+ *   RXG_HINT_Q_ON_DEVICE      q of the next call is what the previous rxg_qeq / rxg_pqeq returned: do not upload it
+ *   RXG_HINT_DEFER_POS        the next call need not copy pos back (its only change is the ulp-level normalise/de-normalise
+ *                             round trip of COPYATOMS): the following call is hinted ATOMS_ON_DEVICE and a later
+ *                             un-deferred call (rxg_force) returns the final positions.  Ignored by rxg_move when atoms migrate.
+ * A promise that does not hold gives wrong results; hints are dropped when natoms differs from the device's. */
+#define RXG_HINT_ATOMS_ON_DEVICE 1
+#define RXG_HINT_Q_ON_DEVICE     2
+#define RXG_HINT_DEFER_POS       4
+int rxg_hint(rxg_handle h, int flags);
+
 /* ---- the drop-in entry points (host buffers in, host buffers out) -------------------------- */
 /* subroutine QEq(atype,pos,q)   src/qeq.F90:2     (also writes qsfp,qsfv when isQEq==1, :42-43) */
 int rxg_qeq(rxg_handle h, const int *natoms, const double *atype, double *pos, double *q,
@@ -162,6 +179,15 @@ int rxg_fetch_bonds(rxg_handle h, int *nbrlist, double *BO0);
  * [20] bytes copied host->device by the entry points so far  [21] bytes copied device->host
  * [22] rxg_force calls that reused the halo and 10 A list of the preceding rxg_qeq (RXG_FUSE_API=1) */
 int rxg_timers(rxg_handle h, double *it_timer_ms);
+/* the reference's it_timer(1:30) itself (src/module.F90:215-217; table printed at src/main.F90:144-180), in SECONDS
+ * (the reference keeps system_clock ticks and divides by the clock rate when printing), measured with CUDA events at the
+ * phase boundaries and resolved lazily: [0] QEq  [2] LINKEDLIST  [3] COPYATOMS  [4] NEIGHBORLIST  [5] BOCALC  [6] ENbond
+ * [7] Ebond  [8] Elnpr  [9] Ehb  [10] E3b  [11] E4b  [12] ForceBondedTerms  [14] GetNonbondingPairList
+ * [15] qeq_initialize  [17] get_hsh (the whole CG: the single-pass CG folds get_gradient's product into it)  [23] QEq
+ * iterations (a count).  Slots the hot path does not own (file I/O 20-23, send_rec/store/append 25-27, total 30) stay 0
+ * and remain the host's.  Fused kernels are booked to one slot: Ebond + Elnpr's main loop -> Ebond, Elnpr's preparation
+ * loop -> Elnpr. */
+int rxg_it_timer(rxg_handle h, double *it_timer_sec);
 
 /* ---- device-resident stepping: the reference main-loop body src/main.F90:64-98
  * executed nsteps times without host round trips (mdmode 1 NVE; vkick src/main.F90:192-207).   */

@@ -197,7 +197,8 @@ int spmv_items_launch(Ctx *c, int slot) {
          c->spmv_stage);
   return RXG_OK;
 }
-int spmv_launch(Ctx *c) {
+// part: 0 = all rows, 1 = interior row groups only, 2 = boundary row groups only (c->overlap; see k_group_class)
+int spmv_launch(Ctx *c, int part = 0) {
   const int n = c->natoms, nt = c->cp[6];
   double4 *rowsum = (double4 *)c->tmp;
   if (nt <= 0) return RXG_OK;
@@ -207,24 +208,76 @@ int spmv_launch(Ctx *c) {
       RXG_CUDA(cudaStreamSynchronize(c->st));
       c->nitems = c->h_int[17];
     }
-    if (c->nitems == 0) return RXG_OK;
+    if (c->nitems == 0 || part == 2) return RXG_OK;
     return c->spmv_rg == 4 ? spmv_items_launch<4>(c, 0) : spmv_items_launch<2>(c, 1);
   }
   const double avgrow = (double)c->nnz_real / (double)std::max(n, 1);
   int shape = c->spmv_shape;
   if (shape == 0) shape = avgrow <= 160.0 ? 1 : (avgrow > 440.0 ? 3 : 2);
+  const int rows = shape == 1 ? 8 : (shape == 3 ? 2 : 4);
+  const int *grp = nullptr;
+  int grid = cdiv(nt, rows);
+  if (part != 0) {
+    if (c->grp_rows != rows) { c->err = "spmv_launch: row groups were classified for another launch shape"; return RXG_ERR_STATE; }
+    grp = part == 1 ? c->grp_int : c->grp_bnd;
+    grid = part == 1 ? c->ngrp_int : c->ngrp - c->ngrp_int;
+    if (grid <= 0) return RXG_OK;
+  }
   if (shape == 1)   // short rows (sparse systems such as the SiC nanoparticles, 117 entries): 8 rows per CTA, 8 lanes per row
-    LAUNCH(c, (k_spmv_rows<8, 8, 256>), cdiv(nt, 8), 64, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->xs, rowsum, c->d_acc, c->spmv_stage);
+    LAUNCH(c, (k_spmv_rows<8, 8, 256>), grid, 64, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->xs, rowsum, c->d_acc, c->spmv_stage, grp);
   else if (shape == 3)   // 12.5 A lists (PQEq, 1060 entries): two long rows per CTA, a full warp per row
-    LAUNCH(c, (k_spmv_rows<2, 32, 1216>), cdiv(nt, 2), 64, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->xs, rowsum, c->d_acc, c->spmv_stage);
+    LAUNCH(c, (k_spmv_rows<2, 32, 1216>), grid, 64, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->xs, rowsum, c->d_acc, c->spmv_stage, grp);
   else   // 10 A lists: 4 rows per CTA, 16 lanes per row
-    LAUNCH(c, (k_spmv_rows<4, 16>), cdiv(nt, 4), 64, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->xs, rowsum, c->d_acc, c->spmv_stage);
+    LAUNCH(c, (k_spmv_rows<4, 16>), grid, 64, 0, c->gnb.order, nt, n, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->xs, rowsum, c->d_acc, c->spmv_stage, grp);
   return RXG_OK;
 }
 
 // single-pass CG (default): one sparse product per iteration, see rxg_lists_qeq.cuh.  Control flow (stop rule, real(4) step
 // lengths) runs on the device (k_cg_ctrl); the host enqueues CG_BATCH iterations at a time and reads the stop flag once per
 // batch -- iterations enqueued past the stop return at their first instruction.
+// classify the row groups of the launch shape in use (once per list build) -- only when the refresh has somewhere to go
+int build_row_groups(Ctx *c) {
+  c->overlap = false;
+  if (!c->overlap_env || !c->comm || !c->peer_ok || c->halo_self || c->spmv_kind != 1 || c->cp[6] <= 0) return RXG_OK;
+  const int n = c->natoms, nt = c->cp[6];
+  const double avgrow = (double)c->nnz_real / (double)std::max(n, 1);
+  int shape = c->spmv_shape;
+  if (shape == 0) shape = avgrow <= 160.0 ? 1 : (avgrow > 440.0 ? 3 : 2);
+  const int rows = shape == 1 ? 8 : (shape == 3 ? 2 : 4);
+  // reach of the stencil in cells (src/init.F90:538-592: cells whose nearest corner is within rctap)
+  const int lay = c->stencil_reach;
+  const int ngrp = cdiv(nt, rows);
+  LAUNCH(c, k_group_class, cdiv(ngrp, 256), 256, 0, c->gnb, nt, rows, lay, c->grp_cls);
+  RXG_TRY(ensure_blk(c, ngrp));
+  RXG_TRY(device_scan<int>(c, c->grp_cls, ngrp, c->grp_off, c->d_blk, c->d_flag + 18));
+  LAUNCH(c, k_group_lists, cdiv(ngrp, 256), 256, 0, ngrp, c->grp_cls, c->grp_off, c->grp_int, c->grp_bnd);
+  RXG_CUDA(cudaMemcpyAsync(c->h_int + 18, c->d_flag + 18, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+  RXG_CUDA(cudaStreamSynchronize(c->st));
+  c->ngrp = ngrp; c->ngrp_int = c->h_int[18]; c->grp_rows = rows;
+  c->overlap = c->ngrp_int > 0;
+  return RXG_OK;
+}
+// ghost refresh of (hs,ht) on the side stream, forked after the kernel that produced them; the caller joins (ev_join) before
+// the boundary rows of the next sparse product
+int refresh_h(Ctx *c) {
+  if (!c->overlap) return halo_refresh(c, 3, 0);
+  RXG_CUDA(cudaEventRecord(c->ev_fork, c->st));
+  RXG_CUDA(cudaStreamWaitEvent(c->st2, c->ev_fork, 0));
+  cudaStream_t s0 = c->st;
+  c->st = c->st2;
+  const int rc = halo_refresh(c, 3, 0);
+  c->st = s0;
+  RXG_TRY(rc);
+  RXG_CUDA(cudaEventRecord(c->ev_join, c->st2));
+  return RXG_OK;
+}
+int spmv_after_refresh(Ctx *c) {
+  if (!c->overlap) return spmv_launch(c);
+  RXG_TRY(spmv_launch(c, 1));                                  // interior rows: no ghost column
+  RXG_CUDA(cudaStreamWaitEvent(c->st, c->ev_join, 0));         // the neighbours' (hs,ht) have arrived
+  return spmv_launch(c, 2);
+}
+
 constexpr int CG_BATCH = 4;
 int qeq_cg_single(Ctx *c, int nmax, int *iters) {
   const int n = c->natoms;
@@ -242,14 +295,15 @@ int qeq_cg_single(Ctx *c, int nmax, int *iters) {
     LAUNCH(c, (k_cg_dots<true>), dgrid, 256, 0, c->gnb.order, c->cp[6], n, rowsum, c->xs, c->q, c->gst, c->tst, c->ust, c->wst, c->itype, c->d_ff, c->d_acc);
   RXG_TRY(allreduce_acc(c, 7, 2));
   LAUNCH(c, k_h_from_g2, cdiv(std::max(n, 1), 256), 256, 0, n, c->gst, c->hst, c->xs, c->gnb.slot_of, c->d_acc);
-  RXG_TRY(halo_refresh(c, 3, 0));   // ghost hs,ht (MODE_QCOPY2, :93)
+  RXG_TRY(build_row_groups(c));
+  RXG_TRY(refresh_h(c));   // ghost hs,ht (MODE_QCOPY2, :93)
   int launched = 0, it = 0;
   bool done = false;
   while (!done && launched < nmax) {
     const int kb = std::min(CG_BATCH, nmax - launched);
     for (int j = 0; j < kb; j++) {
       cudaEventRecord(c->evs[2 * j], c->st);
-      RXG_TRY(spmv_launch(c));
+      RXG_TRY(spmv_after_refresh(c));
       cudaEventRecord(c->evs[2 * j + 1], c->st);
       if (pq)
         LAUNCH(c, (k_cg_dots_pqeq<false>), dgrid, 256, 0, c->gnb.order, c->cp[6], n, rowsum, c->xs, c->q, c->gst, c->tst, c->ust, c->wst, c->itype, c->d_ff,
@@ -261,8 +315,9 @@ int qeq_cg_single(Ctx *c, int nmax, int *iters) {
       LAUNCH(c, k_cg_update1, cdiv(std::max(n, 1), 256), 256, 0, n, c->hst, c->tst, c->ust, c->qst, c->gst, c->wst, c->d_acc);
       RXG_TRY(allreduce_acc(c, 5, 4));
       LAUNCH(c, k_cg_update2, cdiv(std::max(n, 1), 256), 256, 0, n, c->qst, c->gst, c->hst, c->xs, c->gnb.slot_of, c->q, c->d_acc);
-      RXG_TRY(halo_refresh(c, 3, 0));
+      RXG_TRY(refresh_h(c));
     }
+    if (c->overlap) RXG_CUDA(cudaStreamWaitEvent(c->st, c->ev_join, 0));   // the batch's last refresh runs on the side stream
     RXG_CUDA(cudaMemcpyAsync(c->h_acc + ACC_GEST2, c->d_acc + ACC_GEST2, sizeof(double) * 5, cudaMemcpyDeviceToHost, c->st));
     if (c->peer_ok) RXG_CUDA(cudaMemcpyAsync(c->h_int + 3, c->d_flag + 3, sizeof(int), cudaMemcpyDeviceToHost, c->st));
     RXG_CUDA(cudaStreamSynchronize(c->st));
@@ -308,10 +363,13 @@ int qeq_device(Ctx *c, bool for_force = false) {
     }
   }
   const bool pq = c->cfg.isPQEq != 0;
+  phase_mark(c, 4 | PH_QEQ);    // COPYATOMS
   RXG_TRY(halo_copy(c, QCopyDr));
   if (pq) RXG_TRY(halo_refresh(c, 5, 0));   // ghost spos travels with MODE_COPY in the reference (src/comm.F90:129-131)
   if (c->cp[6] > 0) LAUNCH(c, k_types, cdiv(c->cp[6], 256), 256, 0, c->atype, c->cp[6], c->itype, c->gid);
+  phase_mark(c, 3 | PH_QEQ);    // LINKEDLIST
   RXG_TRY(bin_grid(c, c->gnb));
+  phase_mark(c, 16 | PH_QEQ);   // qeq_initialize
   if (c->lists_shared) RXG_TRY((build_pairlist<2>(c, !pq)));
   else RXG_TRY((build_pairlist<1>(c, !pq)));
   RXG_CUDA(cudaMemsetAsync(c->d_acc, 0, sizeof(double) * 24, c->st));
@@ -324,8 +382,11 @@ int qeq_device(Ctx *c, bool for_force = false) {
     LAUNCH(c, k_pqeq_rows, rgrid, 256, 0, c->gnb, nt, n, c->rowbeg, c->rowend, c->col, c->val, c->sps, c->d_ff, c->prow, c->pcs, c->d_acc, c->d_flag + 6);
   }
   int it = 0;
+  phase_mark(c, 18 | PH_QEQ);   // the CG: get_hsh (+ get_gradient, which the single-pass CG folds into the same sparse product)
   if (c->strict || (!pq && c->qeq_mode == 1)) RXG_TRY(qeq_cg_literal(c, nmax, &it));
   else RXG_TRY(qeq_cg_single(c, nmax, &it));
+  phase_mark(c, 0);
+  c->ph_sec[24] += it;   // it_timer(24): QEq iterations (src/qeq.F90:172)
   if (pq && nt > 0) {   // update_shell_positions, src/pqeq.F90:171,187-259, with the final charges of residents and ghosts
     RXG_TRY(halo_refresh(c, 4, 0));
     LAUNCH(c, k_pack_qsl, cdiv(nt, 256), 256, 0, nt, c->q, c->gnb.slot_of, c->qsl);
@@ -387,6 +448,10 @@ int rxg_create(const rxg_config *cfg, rxg_handle *out) {
   c->fuse = !(nf && nf[0] == '1');
   const char *fa = getenv("RXG_FUSE_API");
   c->fuse_api = fa && fa[0] == '1';
+  const char *ov = getenv("RXG_OVERLAP");
+  c->overlap_env = !(ov && ov[0] == '0');
+  const char *eo = getenv("RXG_EVAL_OCC");
+  c->eval_occ = eo && eo[0] == '1';
   const char *sk = getenv("RXG_SPMV");
   c->spmv_kind = (sk && std::string(sk) == "items") ? 0 : 1;   // 1: k_spmv_rows (default), 0: k_spmv_items (experiment)
   const char *ss = getenv("RXG_SPMV_SHAPE");
@@ -411,6 +476,14 @@ int rxg_create(const rxg_config *cfg, rxg_handle *out) {
     return RXG_ERR_CUDA;
   }
   RXG_CUDA(cudaStreamCreateWithFlags(&c->st, cudaStreamNonBlocking));
+  {   // side stream of the ghost refresh: highest priority, so that its small kernels are dispatched ahead of the queued CTAs
+      // of the sparse product they overlap with
+    int lo = 0, hi = 0;
+    RXG_CUDA(cudaDeviceGetStreamPriorityRange(&lo, &hi));
+    RXG_CUDA(cudaStreamCreateWithPriority(&c->st2, cudaStreamNonBlocking, hi));
+  }
+  RXG_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
+  RXG_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
   RXG_CUDA(cudaEventCreate(&c->ev0));
   RXG_CUDA(cudaEventCreate(&c->ev1));
   RXG_CUDA(cudaEventCreate(&c->evm0));
@@ -435,6 +508,8 @@ int rxg_create(const rxg_config *cfg, rxg_handle *out) {
   RXG_TRY(dalloc(c, &c->rowoff, NB + 2)); RXG_TRY(dalloc(c, &c->rowbeg, NB + 2)); RXG_TRY(dalloc(c, &c->rowend, NB + 2));
   RXG_TRY(dalloc(c, &c->rowcnt, NB + 2)); RXG_TRY(dalloc(c, &c->ucnt, NB + 2)); RXG_TRY(dalloc(c, &c->uoff, NB + 2));
   RXG_TRY(dalloc(c, &c->items, NB + 2));
+  RXG_TRY(dalloc(c, &c->grp_cls, NB / 2 + 2)); RXG_TRY(dalloc(c, &c->grp_off, NB / 2 + 2));
+  RXG_TRY(dalloc(c, &c->grp_int, NB / 2 + 2)); RXG_TRY(dalloc(c, &c->grp_bnd, NB / 2 + 2));
   RXG_TRY(ensure_bond_capacity(c, 8 * (long long)NB));
   RXG_TRY(dalloc(c, &c->delta, NB)); RXG_TRY(dalloc(c, &c->deltap1, NB)); RXG_TRY(dalloc(c, &c->deltap2, NB));
   RXG_TRY(dalloc(c, &c->nlp, NB)); RXG_TRY(dalloc(c, &c->dDlp, NB)); RXG_TRY(dalloc(c, &c->deltalp, NB));
@@ -443,6 +518,8 @@ int rxg_create(const rxg_config *cfg, rxg_handle *out) {
   RXG_TRY(dalloc(c, &c->d_acc, 64)); RXG_TRY(dalloc(c, &c->d_flag, 32));
   RXG_CUDA(cudaMallocHost((void **)&c->h_acc, sizeof(double) * 64));
   RXG_CUDA(cudaMallocHost((void **)&c->h_int, sizeof(int) * 32));
+  RXG_CUDA(cudaMallocHost((void **)&c->h_cnt, sizeof(int) * (4 + 4 * 64)));
+  RXG_TRY(dalloc(c, &c->d_cnt, 4 + 4 * 64));
   RXG_TRY(ensure_blk(c, NB));
   RXG_CUDA(cudaStreamSynchronize(c->st));
   return RXG_OK;
@@ -542,6 +619,9 @@ int rxg_set_box(rxg_handle h, const rxg_box *box) {
     else { runs.push_back(dx); runs.push_back(dy); runs.push_back(dz); runs.push_back(dz); }
   }
   c->nruns = (int)(runs.size() / 4);
+  c->stencil_reach = 0;   // cells the stencil reaches along any axis: rows of cells this far inside the domain take no ghost column
+  for (int m = 0; m < box->nbnmesh; m++)
+    for (int a = 0; a < 3; a++) c->stencil_reach = std::max(c->stencil_reach, std::abs(box->nbmesh[3 * m + a]));
   RXG_CUDA(cudaMalloc((void **)&c->d_runs, sizeof(int) * (runs.size() + 4)));
   RXG_CUDA(cudaMemcpy(c->d_runs, runs.data(), sizeof(int) * runs.size(), cudaMemcpyHostToDevice));
   RXG_CUDA(cudaStreamSynchronize(c->st));
@@ -564,6 +644,7 @@ int rxg_comm_init(rxg_handle h, int rank, int nranks, const void *id) {
   Ctx *c = (Ctx *)h;
   if (!c) return RXG_ERR_ARG;
   if (nranks == 1) return RXG_OK;
+  if (!c->have_box) { c->err = "rxg_comm_init: rxg_set_box must be called first (the neighbour table decides which peer windows to open)"; return RXG_ERR_STATE; }
   if (!id) { c->err = "rxg_comm_init: null ncclUniqueId"; return RXG_ERR_ARG; }
   RXG_CUDA(cudaSetDevice(c->dev));
   ncclUniqueId uid;
@@ -576,7 +657,7 @@ int rxg_comm_init(rxg_handle h, int rank, int nranks, const void *id) {
   const char *ph = getenv("RXG_PEER_HALO");
   int want = !(ph && ph[0] == '0');
   c->peer.assign(nranks, nullptr);
-  c->pw_cap = (size_t)3 * (size_t)c->NB / 2;
+  c->pw_cap = (size_t)3 * (size_t)c->NB;   // >= 3 fields x NBUFFER atoms: no refresh can exceed a buffer, so no rank can fail alone
   const size_t wbytes = sizeof(double) * (PW_HDR + 12 * c->pw_cap + PW_AR_DOUBLES);
   int *d_ok = c->d_flag + 2;
   cudaIpcMemHandle_t *d_h = nullptr, *d_all = nullptr;
@@ -659,6 +740,11 @@ int rxg_destroy(rxg_handle h) {
       if (p) cudaFree(p);
     if (c->h_acc) cudaFreeHost(c->h_acc);
     if (c->h_int) cudaFreeHost(c->h_int);
+    if (c->h_cnt) cudaFreeHost(c->h_cnt);
+    for (cudaEvent_t e : c->ph_ev) cudaEventDestroy(e);
+    if (c->st2) { cudaStreamSynchronize(c->st2); cudaStreamDestroy(c->st2); }
+    if (c->ev_fork) cudaEventDestroy(c->ev_fork);
+    if (c->ev_join) cudaEventDestroy(c->ev_join);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
     cudaStreamDestroy(c->st);
@@ -668,6 +754,13 @@ int rxg_destroy(rxg_handle h) {
 }
 
 const char *rxg_last_error(rxg_handle h) { return h ? ((Ctx *)h)->err.c_str() : "null handle"; }
+
+int rxg_hint(rxg_handle h, int flags) {
+  Ctx *c = (Ctx *)h;
+  if (!c) return RXG_ERR_ARG;
+  c->hint = flags;
+  return RXG_OK;
+}
 
 static int check_ready(Ctx *c, int natoms) {
   if (!c) return RXG_ERR_ARG;
@@ -682,10 +775,14 @@ int rxg_qeq(rxg_handle h, const int *natoms, const double *atype, double *pos, d
   Ctx *c = (Ctx *)h;
   RXG_TRY(check_ready(c, natoms ? *natoms : -1));
   const int n = *natoms;
+  const int hint = (n == c->natoms) ? c->hint : 0;   // promises of rxg_hint hold for an unchanged atom count only
+  c->hint = 0;
   c->natoms = n;
-  RXG_TRY(h2d_planes(c, c->atype, atype, 1, n));
-  RXG_TRY(h2d_planes(c, c->pos, pos, 3, n));
-  RXG_TRY(h2d_planes(c, c->q, q, 1, n));
+  if (!(hint & RXG_HINT_ATOMS_ON_DEVICE)) {
+    RXG_TRY(h2d_planes(c, c->atype, atype, 1, n));
+    RXG_TRY(h2d_planes(c, c->pos, pos, 3, n));
+  }
+  if (!(hint & RXG_HINT_Q_ON_DEVICE)) RXG_TRY(h2d_planes(c, c->q, q, 1, n));
   if (c->cfg.isQEq == 2) { RXG_TRY(h2d_planes(c, c->qsfp, qsfp, 1, n)); }
   {
     Timer t(c, 0);
@@ -693,7 +790,8 @@ int rxg_qeq(rxg_handle h, const int *natoms, const double *atype, double *pos, d
     RXG_TRY(qeq_device(c, c->fuse_api));   // RXG_FUSE_API=1: build halo + list so that the next rxg_force may reuse them
   }
   RXG_TRY(d2h_planes(c, q, c->q, 1, n));   // resident charges (ghost entries of the host array are rewritten by every COPYATOMS)
-  RXG_TRY(d2h_planes(c, pos, c->pos, 3, n));
+  c->pos_deferred = (hint & RXG_HINT_DEFER_POS) != 0;
+  if (!c->pos_deferred) RXG_TRY(d2h_planes(c, pos, c->pos, 3, n));
   if (c->cfg.isQEq == 1 && qsfp && qsfv) { RXG_TRY(d2h_planes(c, qsfp, c->qsfp, 1, n)); RXG_TRY(d2h_planes(c, qsfv, c->qsfv, 1, n)); }
   RXG_CUDA(cudaStreamSynchronize(c->st));
   if (nstep_qeq) *nstep_qeq = c->nstep_qeq;
@@ -735,10 +833,17 @@ int rxg_force(rxg_handle h, const int *natoms, const double *atype, double *pos,
   Ctx *c = (Ctx *)h;
   RXG_TRY(check_ready(c, natoms ? *natoms : -1));
   const int n = *natoms;
+  const int hint = (n == c->natoms) ? c->hint : 0;
+  c->hint = 0;
+  const bool atoms_here = (hint & RXG_HINT_ATOMS_ON_DEVICE) != 0;
   // RXG_FUSE_API=1: if this call follows rxg_qeq with bit-identical atoms (the host passes back what rxg_qeq returned),
-  // the halo and the 10 A list of that QEq are reused exactly as rxg_md_run does; otherwise the literal path runs
+  // the halo and the 10 A list of that QEq are reused exactly as rxg_md_run does; otherwise the literal path runs.
+  // Without the host's promise (rxg_hint) the identity is verified on the device, at the price of uploading the atoms.
   bool reuse = false;
-  if (c->fuse_api && c->lists_shared && n == c->natoms && n > 0) {
+  if (atoms_here) {
+    reuse = c->fuse_api && c->lists_shared && n > 0;
+    if (reuse) c->timers_ms[22] += 1;
+  } else if (c->fuse_api && c->lists_shared && n == c->natoms && n > 0) {
     double *stage = c->tmp;   // [4][NB] scratch
     for (int p = 0; p < 3; p++)
       RXG_CUDA(cudaMemcpyAsync(stage + (size_t)p * c->NB, pos + (size_t)p * c->NB, sizeof(double) * n, cudaMemcpyHostToDevice, c->st));
@@ -752,18 +857,19 @@ int rxg_force(rxg_handle h, const int *natoms, const double *atype, double *pos,
     if (reuse) c->timers_ms[22] += 1;   // rxg_force calls that reused the halo and list of the preceding rxg_qeq
   }
   c->natoms = n;
-  if (!reuse) {
+  if (!reuse && !atoms_here) {
     RXG_TRY(h2d_planes(c, c->atype, atype, 1, n));
     RXG_TRY(h2d_planes(c, c->pos, pos, 3, n));
   }
-  RXG_TRY(h2d_planes(c, c->q, q, 1, n));
+  if (!(hint & RXG_HINT_Q_ON_DEVICE)) RXG_TRY(h2d_planes(c, c->q, q, 1, n));
   {
     Timer t(c, 1);
     RXG_TRY(force_device(c, reuse));
   }
   c->lists_shared = false;
   RXG_TRY(d2h_planes(c, f, c->f, 3, n));
-  RXG_TRY(d2h_planes(c, pos, c->pos, 3, n));
+  RXG_TRY(d2h_planes(c, pos, c->pos, 3, n));   // also delivers the copy a hinted rxg_move / rxg_qeq deferred
+  c->pos_deferred = false;
   RXG_CUDA(cudaStreamSynchronize(c->st));
   if (PE) for (int k = 0; k < 14; k++) PE[k] = c->PE[k];
   if (astr) for (int k = 0; k < 6; k++) astr[k] += c->astr[k];
@@ -775,6 +881,8 @@ int rxg_move(rxg_handle h, int *natoms, double *atype, double *pos, double *v, d
   Ctx *c = (Ctx *)h;
   RXG_TRY(check_ready(c, natoms ? *natoms : -1));
   const int n = *natoms;
+  const int hint = c->hint;
+  c->hint = 0;
   c->natoms = n;
   RXG_TRY(h2d_planes(c, c->atype, atype, 1, n));
   RXG_TRY(h2d_planes(c, c->pos, pos, 3, n));
@@ -802,12 +910,17 @@ int rxg_move(rxg_handle h, int *natoms, double *atype, double *pos, double *v, d
   int rc;
   {
     Timer t(c, 2);
+    phase_mark(c, 4);
     rc = halo_move(c);
+    phase_mark(c, 0);
   }
   c->lazy_upload = nullptr;
   RXG_TRY(rc);
   const int m = c->natoms;
-  RXG_TRY(d2h_planes(c, pos, c->pos, 3, m));
+  // RXG_HINT_DEFER_POS: when nothing migrated, the only change is the ulp-level round trip of pos, which the next call
+  // (hinted ATOMS_ON_DEVICE) consumes on the device and a later call hands back
+  c->pos_deferred = (hint & RXG_HINT_DEFER_POS) && !full;
+  if (!c->pos_deferred) RXG_TRY(d2h_planes(c, pos, c->pos, 3, m));
   if (full) {
     RXG_TRY(d2h_planes(c, atype, c->atype, 1, m));
     RXG_TRY(d2h_planes(c, v, c->v, 3, m));
@@ -845,6 +958,17 @@ int rxg_fetch_bonds(rxg_handle h, int *nbrlist, double *BO0) {
       if (BO0) BO0[(size_t)s * NB + i] = bo[(size_t)ptr[i] + s];
     }
   }
+  return RXG_OK;
+}
+
+// it_timer(1:30) of the reference (src/module.F90:215-217), in SECONDS (the reference keeps system_clock ticks and divides by
+// the clock rate when it prints, src/main.F90:148-180); slot 24 is the QEq iteration count.
+int rxg_it_timer(rxg_handle h, double *it_timer_sec) {
+  Ctx *c = (Ctx *)h;
+  if (!c || !it_timer_sec) return RXG_ERR_ARG;
+  cudaSetDevice(c->dev);
+  phase_harvest(c);
+  for (int k = 1; k <= 30; k++) it_timer_sec[k - 1] = c->ph_sec[k];
   return RXG_OK;
 }
 
@@ -901,7 +1025,9 @@ int rxg_md_run(rxg_handle h, int nsteps, double dt, int qstep, double Lex_w2, in
       LAUNCH(c, k_sub_vcm_drift, cdiv(n, 256), 256, 0, n, c->NB, dt, c->v, c->pos, c->d_acc + 52, true);
     }
     double t0 = wall();
+    phase_mark(c, 4);
     RXG_TRY(halo_move(c));                                   // :75
+    phase_mark(c, 0);
     RXG_CUDA(cudaStreamSynchronize(c->st));
     double t1 = wall();
     c->lists_shared = false;

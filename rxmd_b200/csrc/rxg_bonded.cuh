@@ -207,7 +207,7 @@ __global__ void __launch_bounds__(256) k_enbond(int ntot, int natoms, const long
       int4 tj = tgs[js];
       bool lower = tj.y < ti.y;
       if (HALF ? !lower : (tj.y == ti.y)) continue;
-      double4 pj = pqs[js];
+      double4 pj = ldg256(pqs + js);
       double dx = sub_rn(pi.x, pj.x), dy = sub_rn(pi.y, pj.y), dz = sub_rn(pi.z, pj.z);
       double dr2 = dist2_rn(dx, dy, dz);
       if (!(dr2 <= ff.rctap2)) continue;
@@ -217,7 +217,7 @@ __global__ void __launch_bounds__(256) k_enbond(int ntot, int natoms, const long
       double drtb = mul_rn(sub_rn(dr2, mul_rn((double)itb, ff.UDR)), ff.UDRi);
       double drtb1 = 1.0 - drtb;
       const double4 *T = ff.TBL_nb + (size_t)(inxn - 1) * ff.ntable + (itb - 1);
-      double4 T0 = T[0], T1 = T[1];
+      double4 T0 = ldg256(T), T1 = ldg256(T + 1);
       double qij = pi.w * pj.w;
       double PEvdw = drtb1 * T0.x + drtb * T1.x;
       double CEvdw = drtb1 * T0.y + drtb * T1.y;
@@ -441,7 +441,8 @@ __global__ void __launch_bounds__(256) k_e3b_enum(int nslots, int natoms, const 
 }
 
 // C3b: E3b evaluation (src/pot.F90:388-541), one thread per angle.
-__global__ void __launch_bounds__(128) k_e3b_eval(int nwork, const int2 *__restrict__ wl, const double4 *__restrict__ pq, int NB,
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_e3b_eval(int nwork, const int2 *__restrict__ wl, const double4 *__restrict__ pq, int NB,
                                                   const int *__restrict__ itype, const DevFF *__restrict__ ffp, Bonds B,
                                                   const double *__restrict__ delta, const double *__restrict__ nlp,
                                                   const double *__restrict__ dDlp, const double2 *__restrict__ sbo,
@@ -573,7 +574,8 @@ __global__ void k_ehb_enum(int natoms, const int *__restrict__ itype, const DevF
   }
 }
 // C5b: Ehb evaluation, src/pot.F90:597-661.  One warp per donor-H bond; the lanes scan i's 10 A row.
-__global__ void __launch_bounds__(256) k_ehb_eval(int nwork, const int2 *__restrict__ wl, const int *__restrict__ slot_of,
+template <int MINB>
+__global__ void __launch_bounds__(256, MINB) k_ehb_eval(int nwork, const int2 *__restrict__ wl, const int *__restrict__ slot_of,
                                                   const double4 *__restrict__ pqs, const int4 *__restrict__ tgs, int NB,
                                                   const DevFF *__restrict__ ffp, Bonds B, const long long *__restrict__ rowbeg,
                                                   const long long *__restrict__ rowend, const int *__restrict__ col,
@@ -599,7 +601,7 @@ __global__ void __launch_bounds__(256) k_ehb_eval(int nwork, const int2 *__restr
       int4 tk = tgs[ks];
       int inxnhb = ff.inxn3hb[(ity - 1) + ff.nso * ((jty - 1) + ff.nso * (tk.x - 1))];
       if (!((j != tk.z) && (i != tk.z) && (inxnhb != 0))) continue;
-      const double4 pk = pqs[ks];
+      const double4 pk = ldg256(pqs + ks);
       double rik2 = dist2_rn(sub_rn(pi.x, pk.x), sub_rn(pi.y, pk.y), sub_rn(pi.z, pk.z));
       if (!(rik2 < RCHB2)) continue;
       int x = inxnhb - 1;
@@ -703,7 +705,8 @@ __global__ void __launch_bounds__(256) k_e4b_enum(int nslots, int natoms, const 
 }
 
 // C4b: E4b evaluation (src/pot.F90:1083-1205), one thread per torsion i-j-k-l.
-__global__ void __launch_bounds__(128) k_e4b_eval(int nwork, const int2 *__restrict__ wl, const double4 *__restrict__ pq, int NB,
+template <int MINB>
+__global__ void __launch_bounds__(128, MINB) k_e4b_eval(int nwork, const int2 *__restrict__ wl, const double4 *__restrict__ pq, int NB,
                                                   const int *__restrict__ itype, const DevFF *__restrict__ ffp, Bonds B,
                                                   const double *__restrict__ delta, double *__restrict__ cdbnd,
                                                   double *__restrict__ f, double *__restrict__ acc) {
@@ -1050,15 +1053,20 @@ inline int force_device(Ctx *c, bool reuse = false) {
   double dr[3];
   for (int a = 0; a < 3; a++) dr[a] = c->cfg.nmincell * c->box.lcsize[a];
   const bool pqeq = c->cfg.isPQEq != 0;
+  phase_mark(c, 4);                                             // COPYATOMS
   if (!reuse) RXG_TRY(halo_copy(c, dr));                        // src/pot.F90:28
   else RXG_TRY(halo_refresh(c, 4, 1));   // ghost q; + the position round trip FORCE's own MODE_COPY would apply
   if (pqeq) RXG_TRY(halo_refresh(c, 5, 0));   // ghost spos (part of MODE_COPY in the reference, src/comm.F90:129-131)
   const int nt = c->cp[6];
   if (!reuse) LAUNCH(c, k_types, cdiv(nt, 256), 256, 0, c->atype, nt, c->itype, c->gid);
+  phase_mark(c, 3);                                             // LINKEDLIST
   RXG_TRY(bin_grid(c, c->gb));                                  // :30
   if (!reuse) RXG_TRY(bin_grid(c, c->gnb));                     // :31
+  phase_mark(c, 5);                                             // NEIGHBORLIST
   RXG_TRY(build_nbrlist(c));                                    // :33
+  phase_mark(c, 15);                                            // GetNonbondingPairList
   if (!reuse) RXG_TRY(build_pairlist<0>(c));                    // :34
+  phase_mark(c, 6);                                             // BOCALC
   Bonds B = make_bonds(c);
   LAUNCH(c, k_boprim, cdiv(nt, 128), 128, 0, nt, c->pos, NB, c->itype, c->d_ff, B, c->deltap1, c->deltap2, c->cdbnd, c->ccbnd, c->s3);
   LAUNCH(c, k_bofull, cdiv(nt, 128), 128, 0, nt, c->itype, c->d_ff, B, c->deltap1, c->deltap2, c->delta);
@@ -1068,6 +1076,7 @@ inline int force_device(Ctx *c, bool reuse = false) {
     RXG_CUDA(cudaMalloc((void **)&c->wl, sizeof(int2) * (size_t)(c->wl_cap3 + c->wl_cap4 + c->wl_caph)));
   }
   double4 *pq = c->pqa;
+  phase_mark(c, 7);                                             // ENbond
   LAUNCH(c, k_pack_pq, cdiv(nt, 256), 256, 0, nt, c->pos, NB, c->q, c->itype, c->gid, c->gnb.slot_of, c->pqa, c->pqs, c->tgs);
   // the full-row form needs every partner's image inside this rank's halo: true when the FORCE halo >= rctap
   bool full_ok = true;
@@ -1086,30 +1095,44 @@ inline int force_device(Ctx *c, bool reuse = false) {
     if (c->cfg.isEfield && n > 0)   // :61
       LAUNCH(c, k_efield, cdiv(n, 256), 256, 0, n, c->q, c->itype, c->d_ff, c->cfg.eFieldDir, c->cfg.eFieldStrength, c->f, NB);
   } else if (!full_ok) LAUNCH(c, (k_enbond<true>), ogrid, 256, 0, nt, n, c->rowbeg, c->rowend, c->col, c->pqs, c->tgs, c->d_ff, c->f, c->fsl, NB, c->d_acc);
+  phase_mark(c, 9);                                             // Elnpr (preparation loop)
   LAUNCH(c, k_elnpr_prep, cdiv(nt, 256), 256, 0, nt, c->itype, c->d_ff, c->delta, c->nlp, c->dDlp, c->deltalp);
+  phase_mark(c, 8);                                             // Ebond (one kernel with Elnpr's main loop)
   LAUNCH(c, k_ebond_elnpr, cdiv(n, 128), 128, 0, n, c->itype, c->gid, c->d_ff, B, c->delta, c->dDlp, c->deltalp, c->d_acc);
   // angles and torsions: enumerate survivors of the cut-off tests, then evaluate one per thread
   for (int attempt = 0; attempt < 2; attempt++) {
     RXG_CUDA(cudaMemsetAsync(c->d_flag + 12, 0, 3 * sizeof(int), c->st));
     int2 *wl3 = c->wl, *wl4 = c->wl + c->wl_cap3, *wlh = c->wl + c->wl_cap3 + c->wl_cap4;
+    phase_mark(c, 10);                                          // Ehb
     LAUNCH(c, k_ehb_enum, cdiv(n, 128), 128, 0, n, c->itype, c->d_ff, B, wlh, (int)c->wl_caph, c->d_flag + 14);
     const int nslots = (int)c->nbonds;
+    phase_mark(c, 11);                                          // E3b
     if (attempt == 0) LAUNCH(c, k_e3b_sums, cdiv(n, 128), 128, 0, n, c->itype, B, c->sbo);
     LAUNCH(c, k_e3b_enum, cdiv(nslots, 256), 256, 0, nslots, n, c->itype, c->d_ff, B, wl3, (int)c->wl_cap3, c->d_flag + 12);
+    phase_mark(c, 12);                                          // E4b
     LAUNCH(c, k_e4b_enum, cdiv(nslots, 256), 256, 0, nslots, n, c->itype, c->gid, c->d_ff, B, wl4, (int)c->wl_cap4, c->d_flag + 13);
     RXG_CUDA(cudaMemcpyAsync(c->h_int + 12, c->d_flag + 12, 3 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
     RXG_CUDA(cudaStreamSynchronize(c->st));
     const long long n3 = c->h_int[12], n4 = c->h_int[13], nh = c->h_int[14];
     if (n3 <= c->wl_cap3 && n4 <= c->wl_cap4 && nh <= c->wl_caph) {
       c->n_angles = n3; c->n_torsions = n4; c->n_hbonds = nh;
+      phase_mark(c, 10);
+#define RXG_EVAL(kern, lo, hi, grid, block, ...)                                   \
+  do {                                                                              \
+    if (c->eval_occ) LAUNCH(c, (kern<hi>), grid, block, 0, __VA_ARGS__);           \
+    else LAUNCH(c, (kern<lo>), grid, block, 0, __VA_ARGS__);                        \
+  } while (0)
       if (nh > 0)
-        LAUNCH(c, k_ehb_eval, cdiv(nh * 32, 256), 256, 0, (int)nh, wlh, c->gnb.slot_of, c->pqs, c->tgs, NB, c->d_ff, B, c->rowbeg,
-               c->rowend, c->col, c->f, c->fsl, c->d_acc);
+        RXG_EVAL(k_ehb_eval, 1, 3, cdiv(nh * 32, 256), 256, (int)nh, wlh, c->gnb.slot_of, c->pqs, c->tgs, NB, c->d_ff, B, c->rowbeg,
+                 c->rowend, c->col, c->f, c->fsl, c->d_acc);
+      phase_mark(c, 11);
       if (n3 > 0)
-        LAUNCH(c, k_e3b_eval, cdiv(n3, 128), 128, 0, (int)n3, wl3, pq, NB, c->itype, c->d_ff, B, c->delta, c->nlp, c->dDlp, c->sbo,
-               c->s3, c->f, c->d_acc);
+        RXG_EVAL(k_e3b_eval, 1, 5, cdiv(n3, 128), 128, (int)n3, wl3, pq, NB, c->itype, c->d_ff, B, c->delta, c->nlp, c->dDlp, c->sbo,
+                 c->s3, c->f, c->d_acc);
+      phase_mark(c, 12);
       if (n4 > 0)
-        LAUNCH(c, k_e4b_eval, cdiv(n4, 128), 128, 0, (int)n4, wl4, pq, NB, c->itype, c->d_ff, B, c->delta, c->cdbnd, c->f, c->d_acc);
+        RXG_EVAL(k_e4b_eval, 1, 5, cdiv(n4, 128), 128, (int)n4, wl4, pq, NB, c->itype, c->d_ff, B, c->delta, c->cdbnd, c->f, c->d_acc);
+#undef RXG_EVAL
       break;
     }
     if (attempt == 1) { c->err = "angle/torsion work list overflow"; return RXG_ERR_STATE; }
@@ -1119,6 +1142,7 @@ inline int force_device(Ctx *c, bool reuse = false) {
     c->wl_caph = std::max(c->wl_caph, nh + nh / 4 + 1024);
     RXG_CUDA(cudaMalloc((void **)&c->wl, sizeof(int2) * (size_t)(c->wl_cap3 + c->wl_cap4 + c->wl_caph)));
   }
+  phase_mark(c, 13);                                            // ForceBondedTerms
   LAUNCH(c, k_fsl_to_f, cdiv(nt, 256), 256, 0, nt, NB, c->gnb.order, c->fsl, c->f);
   // ---- ForceBondedTerms (src/pot.F90:63)
   LAUNCH(c, k_final0, cdiv(nt, 128), 128, 0, nt, B, c->cdbnd);
@@ -1127,7 +1151,9 @@ inline int force_device(Ctx *c, bool reuse = false) {
   LAUNCH(c, k_virial, cdiv(nt, 256), 256, 0, nt, c->pos, c->f, NB, c->d_acc);   // :65-72
   // full-row ENbond puts both halves of a pair force on residents, so its virial is taken per pair inside the kernel
   if (full_ok) LAUNCH(c, (k_enbond<false>), ogrid, 256, 0, nt, n, c->rowbeg, c->rowend, c->col, c->pqs, c->tgs, c->d_ff, c->f, c->fsl, NB, c->d_acc);
+  phase_mark(c, 4);                                             // COPYATOMS(MODE_CPBK)
   RXG_TRY(halo_cpbk(c));                                                          // :74
+  phase_mark(c, 0);
   RXG_CUDA(cudaMemcpyAsync(c->h_acc + ACC_PE, c->d_acc + ACC_PE, sizeof(double) * 24, cudaMemcpyDeviceToHost, c->st));
   if (c->peer_ok) RXG_CUDA(cudaMemcpyAsync(c->h_int + 3, c->d_flag + 3, sizeof(int), cudaMemcpyDeviceToHost, c->st));
   RXG_CUDA(cudaStreamSynchronize(c->st));

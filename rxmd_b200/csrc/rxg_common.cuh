@@ -68,6 +68,14 @@ __device__ __forceinline__ double dist2_rn(double dx, double dy, double dz) {
   return add_rn(add_rn(mul_rn(dx, dx), mul_rn(dy, dy)), mul_rn(dz, dz));
 }
 __device__ __forceinline__ int nint_d(double x) { return (int)llround(x); }
+// One 32-byte record in ONE load instruction (LDG.E.256 on sm_100a) through the read-only path.  nvcc splits a double4 load
+// into two 16-byte requests; the gather-bound kernels (table nodes, candidate records, {x,y,z,q} packs) pay the L1 tag stage
+// per request, so halving the requests is what counts.  The record must be 32-byte aligned and not written by the kernel.
+__device__ __forceinline__ double4 ldg256(const double4 *p) {
+  double4 v;
+  asm volatile("ld.global.nc.v4.f64 {%0,%1,%2,%3}, [%4];" : "=d"(v.x), "=d"(v.y), "=d"(v.z), "=d"(v.w) : "l"(p));
+  return v;
+}
 
 // Force-field tables resident in HBM (device pointers); filled by rxg_set_forcefield from rxg_ff.
 // Indexing is 0-based here: type t = ity-1, bond type x = inxn-1; inxn* tables keep 1-based VALUES (0 = none).
@@ -160,6 +168,15 @@ struct Ctx {
   int arseq = 0;                     // all-reduce sequence number
   bool peer_all = false;             // every rank's window is open here: CG scalars are reduced through the windows
   int *d_pushcnt = nullptr;          // [2] block-completion counters of the push kernels
+  bool eval_occ = false;    // RXG_EVAL_OCC=1: the angle / torsion / H-bond evaluators compiled for more resident CTAs (fewer registers)
+  // interior / boundary split of the SpMV (multi-rank): the ghost refresh runs on st2 beside the interior rows
+  cudaStream_t st2 = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool overlap = false, overlap_env = true;
+  int *grp_cls = nullptr, *grp_off = nullptr, *grp_int = nullptr, *grp_bnd = nullptr;   // [NB/2+2] each
+  int ngrp = 0, ngrp_int = 0, grp_rows = 0, stencil_reach = 0;
+  int hint = 0;             // rxg_hint: the host's promises about the arrays of the next entry-point call
+  bool pos_deferred = false;   // a hinted call skipped the copy-back of pos; the next un-hinted copy-back delivers it
   bool fuse = true, fuse_api = false, lists_shared = false;   // md_run: QEq builds halo + 10 A list once for QEq and FORCE of the same step
   int qeq_mode = 0;         // 0 single-pass CG (default), 1 two-pass (literal kernels), strict => literal serial order
   double *tmp = nullptr;    // [12*NB] scratch for MOVE compaction
@@ -212,6 +229,7 @@ struct Ctx {
   int *d_blk = nullptr;      // scan scratch
   long long *d_blk64 = nullptr;
   int nblk_cap = 0;
+  int *d_cnt = nullptr, *h_cnt = nullptr;   // [4 + 4*64] count / capacity / error table of exchange_counts (device, pinned host)
   double *h_acc = nullptr;   // pinned mirror of d_acc
   int *h_int = nullptr;      // pinned
   double PE[14] = {0};
@@ -225,8 +243,46 @@ struct Ctx {
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm0 = nullptr, evm1 = nullptr, evk[4] = {nullptr, nullptr, nullptr, nullptr};
   cudaEvent_t evs[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // SpMV timing, one pair per iteration of a CG batch
   bool grad_pending = false;
+  // phase clock (rxg_it_timer)
+  bool ph_on = true;
+  std::vector<cudaEvent_t> ph_ev;
+  std::vector<int> ph_slot;
+  size_t ph_used = 0;
+  double ph_sec[31] = {0};
   // ---- staging (pinned) ------------------------------------------------------------------------------------
 };
+
+// Phase clock behind rxg_it_timer: one CUDA event per phase boundary on the library's stream, resolved lazily (no
+// synchronisation on the hot path).  Slots are the reference's it_timer indices (src/module.F90:215-217, table printed at
+// src/main.F90:148-180): 1 QEq, 3 LINKEDLIST, 4 COPYATOMS, 5 NEIGHBORLIST, 6 BOCALC, 7 ENbond, 8 Ebond, 9 Elnpr, 10 Ehb,
+// 11 E3b, 12 E4b, 13 ForceBondedTerms, 15 GetNonbondingPairList, 16 qeq_initialize, 18 get_hsh, 19 get_gradient.
+constexpr int PH_QEQ = 64;
+inline void phase_harvest(Ctx *c) {
+  if (c->ph_used < 2) { c->ph_used = 0; return; }
+  cudaEventSynchronize(c->ph_ev[c->ph_used - 1]);
+  for (size_t i = 0; i + 1 < c->ph_used; i++) {
+    if (c->ph_slot[i] <= 0) continue;
+    float ms = 0;
+    if (cudaEventElapsedTime(&ms, c->ph_ev[i], c->ph_ev[i + 1]) != cudaSuccess) continue;
+    c->ph_sec[c->ph_slot[i] & 63] += 1e-3 * ms;
+    if (c->ph_slot[i] & PH_QEQ) c->ph_sec[1] += 1e-3 * ms;   // phases inside QEq also count towards it_timer(1)
+  }
+  c->ph_used = 0;
+}
+// start of phase `slot` (0 = end of a timed region); the previous phase ends here
+inline void phase_mark(Ctx *c, int slot) {
+  if (!c->ph_on) return;
+  if (c->ph_used >= 4096) phase_harvest(c);
+  if (c->ph_used >= c->ph_ev.size()) {
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) { c->ph_on = false; return; }
+    c->ph_ev.push_back(e);
+    c->ph_slot.push_back(0);
+  }
+  cudaEventRecord(c->ph_ev[c->ph_used], c->st);
+  c->ph_slot[c->ph_used] = slot;
+  c->ph_used++;
+}
 
 #define RXG_CUDA(call)                                                                                   \
   do {                                                                                                   \

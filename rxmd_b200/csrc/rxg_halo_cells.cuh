@@ -589,23 +589,55 @@ inline int exchange_axis(Ctx *c, int axis, const size_t cs[2], const size_t cr[2
   return RXG_OK;
 }
 
-// the receive counts of a MODE_COPY / MODE_MOVE axis phase (the reference probes the message size, :335-336)
-inline int exchange_counts(Ctx *c, int axis, const int ns[2], int nr[2]) {
+// rank of the +/- neighbour of rank r along an axis (src/init.F90:79-97: vID x fastest, periodic)
+inline int neighbour_rank(const rxg_box &b, int r, int axis, int dir) {
+  int v[3] = {r % b.vprocs[0], (r / b.vprocs[0]) % b.vprocs[1], r / (b.vprocs[0] * b.vprocs[1])};
+  v[axis] = (v[axis] + dir + b.vprocs[axis]) % b.vprocs[axis];
+  return v[0] + v[1] * b.vprocs[0] + v[2] * b.vprocs[0] * b.vprocs[1];
+}
+
+// The receive counts of a MODE_COPY / MODE_MOVE axis phase (the reference probes the message size, :335-336) AND the
+// collective decision on its capacity traps.  Every rank contributes {ns_up, ns_dn, free atom slots, local error code} to
+// ONE all-gather; from the gathered table every rank evaluates every rank's "na+nr > NBUFFER" condition (src/comm.F90:467-472)
+// and sees every rank's local error, so all ranks return the same code BEFORE any send, recv or peer push is issued -- a rank
+// that stopped alone would leave its neighbours waiting in ncclRecv or in k_peer_pull's spin.
+// `cur` = atoms this rank holds before the axis' arrivals, `local_err` = RXG_OK or the trap this rank already hit.
+inline int exchange_counts(Ctx *c, int axis, const int ns[2], int nr[2], int cur, int local_err) {
   const int tp = c->box.target_node[2 * axis], tm = c->box.target_node[2 * axis + 1];
   const int me = c->box.myid;
-  if (tp == me && tm == me) { nr[0] = ns[0]; nr[1] = ns[1]; return RXG_OK; }
-  if (!c->comm) { c->err = "rxg_comm_init was not called for a multi-rank decomposition"; return RXG_ERR_NCCL; }
-  c->h_int[8] = ns[0]; c->h_int[9] = ns[1];
-  RXG_CUDA(cudaMemcpyAsync(c->d_flag + 8, c->h_int + 8, 2 * sizeof(int), cudaMemcpyHostToDevice, c->st));
-  RXG_NCCL(nccl_api().GroupStart());
-  RXG_NCCL(nccl_api().Send(c->d_flag + 8, 1, ncclInt, tp, c->comm, c->st));
-  RXG_NCCL(nccl_api().Recv(c->d_flag + 10, 1, ncclInt, tm, c->comm, c->st));
-  RXG_NCCL(nccl_api().Send(c->d_flag + 9, 1, ncclInt, tm, c->comm, c->st));
-  RXG_NCCL(nccl_api().Recv(c->d_flag + 11, 1, ncclInt, tp, c->comm, c->st));
-  RXG_NCCL(nccl_api().GroupEnd());
-  RXG_CUDA(cudaMemcpyAsync(c->h_int + 10, c->d_flag + 10, 2 * sizeof(int), cudaMemcpyDeviceToHost, c->st));
+  if (!c->comm) {
+    if (tp != me || tm != me) { c->err = "rxg_comm_init was not called for a multi-rank decomposition"; return RXG_ERR_NCCL; }
+    nr[0] = ns[0]; nr[1] = ns[1];
+    if (local_err != RXG_OK) return local_err;
+    if (cur + nr[0] + nr[1] > c->NB) {   // src/comm.F90:467-472
+      c->err = "ERROR: over capacity in append_atoms; na+nr > NBUFFER " + std::to_string(cur + nr[0] + nr[1]) + " > " + std::to_string(c->NB);
+      return RXG_ERR_NBUFFER;
+    }
+    return RXG_OK;
+  }
+  const int nranks = c->box.nprocs;
+  if (nranks > 64) { c->err = "exchange_counts: more than 64 ranks"; return RXG_ERR_ARG; }
+  c->h_cnt[0] = ns[0]; c->h_cnt[1] = ns[1]; c->h_cnt[2] = c->NB - cur; c->h_cnt[3] = local_err;
+  RXG_CUDA(cudaMemcpyAsync(c->d_cnt, c->h_cnt, 4 * sizeof(int), cudaMemcpyHostToDevice, c->st));
+  RXG_NCCL(nccl_api().AllGather(c->d_cnt, c->d_cnt + 4, 4, ncclInt, c->comm, c->st));
+  RXG_CUDA(cudaMemcpyAsync(c->h_cnt + 4, c->d_cnt + 4, 4 * sizeof(int) * nranks, cudaMemcpyDeviceToHost, c->st));
   RXG_CUDA(cudaStreamSynchronize(c->st));
-  nr[0] = c->h_int[10]; nr[1] = c->h_int[11];
+  c->nccl_msgs++;
+  const int *T = c->h_cnt + 4;   // [rank][4]
+  // stage `up` (buffer 0) travels to the + neighbour, so what I receive in slot 0 is the - neighbour's upper selection
+  nr[0] = T[4 * tm + 0]; nr[1] = T[4 * tp + 1];
+  int verdict = RXG_OK, who = -1;
+  for (int r = 0; r < nranks && verdict == RXG_OK; r++) {
+    if (T[4 * r + 3] != RXG_OK) { verdict = T[4 * r + 3]; who = r; break; }
+    const int rm = neighbour_rank(c->box, r, axis, -1), rp = neighbour_rank(c->box, r, axis, +1);
+    if (T[4 * rm + 0] + T[4 * rp + 1] > T[4 * r + 2]) { verdict = RXG_ERR_NBUFFER; who = r; }
+  }
+  if (verdict != RXG_OK) {
+    if (who != me || c->err.empty() || local_err == RXG_OK)
+      c->err = (verdict == RXG_ERR_NBUFFER ? std::string("ERROR: over capacity in append_atoms; na+nr > NBUFFER") : std::string("ERROR: capacity trap")) +
+               " on rank " + std::to_string(who) + " (all ranks stop together)";
+    return verdict;
+  }
   return RXG_OK;
 }
 
@@ -640,10 +672,11 @@ inline int halo_copy(Ctx *c, const double dr[3]) {
     const int n = c->cp[h_cptridx[d0]];
     int ns[2], nr[2];
     RXG_TRY(select_axis(c, axis, n, dr, 0, ns));
-    if (c->selptr[d0 - 1] + ns[0] + ns[1] > c->sel_cap) { c->err = "ERROR: over capacity in store_atoms (selection lists)"; return RXG_ERR_NBUFFER; }
+    int local_err = RXG_OK;
+    if (c->selptr[d0 - 1] + ns[0] + ns[1] > c->sel_cap) { c->err = "ERROR: over capacity in store_atoms (selection lists)"; local_err = RXG_ERR_NBUFFER; }
     c->selptr[d0] = c->selptr[d0 - 1] + ns[0];
     c->selptr[d1] = c->selptr[d0] + ns[1];
-    RXG_TRY(exchange_counts(c, axis, ns, nr));
+    RXG_TRY(exchange_counts(c, axis, ns, nr, c->cp[d0 - 1], local_err));   // every rank leaves here with the same verdict
     size_t need = (size_t)NE_COPY * (size_t)std::max(std::max(ns[0], ns[1]), std::max(nr[0], nr[1]));
     RXG_TRY(ensure_xbuf(c, need));
     const int nblk = cdiv(n > 0 ? n : 1, SCAN_BLK);
@@ -652,10 +685,6 @@ inline int halo_copy(Ctx *c, const double dr[3]) {
         LAUNCH(c, k_pack_copy, nblk, SCAN_BLK, 0, c->pos, NB, c->atype, c->q, c->qst, c->hsq, n, axis, k == 0, c->box.LBOX[axis],
                dr[axis], k == 0 ? -c->box.LBOX[axis] : c->box.LBOX[axis], c->d_blk + (size_t)k * c->nblk_cap, ns[k],
                c->sel + c->selptr[d0 - 1 + k], c->sbuf[k]);
-    if (c->cp[d0 - 1] + nr[0] + nr[1] > NB) {   // src/comm.F90:467-472
-      c->err = "ERROR: over capacity in append_atoms; na+nr > NBUFFER " + std::to_string(c->cp[d0 - 1] + nr[0] + nr[1]) + " > " + std::to_string(NB);
-      return RXG_ERR_NBUFFER;
-    }
     size_t cs[2] = {(size_t)NE_COPY * ns[0], (size_t)NE_COPY * ns[1]}, cr[2] = {(size_t)NE_COPY * nr[0], (size_t)NE_COPY * nr[1]};
     double *rb[2];
     RXG_TRY(exchange_axis(c, axis, cs, cr, rb, false));
@@ -745,7 +774,7 @@ inline int halo_move(Ctx *c) {
     const int n = c->cp[h_cptridx[d0]];
     int ns[2], nr[2];
     RXG_TRY(select_axis(c, axis, n, zero, 1, ns));
-    RXG_TRY(exchange_counts(c, axis, ns, nr));
+    RXG_TRY(exchange_counts(c, axis, ns, nr, c->cp[d0 - 1], RXG_OK));
     if (ns[0] + ns[1] + nr[0] + nr[1] > 0 && c->lazy_upload) {   // first atom that leaves or arrives: now the rest of the state is needed
       RXG_TRY(c->lazy_upload());
       c->lazy_upload = nullptr;
@@ -758,7 +787,6 @@ inline int halo_move(Ctx *c) {
       if (ns[k] > 0)
         LAUNCH(c, k_pack_move, nblk, SCAN_BLK, 0, c->pos, c->v, NB, c->atype, c->q, c->qst, c->qsfp, c->qsfv, sp, n, axis, k == 0,
                c->box.LBOX[axis], k == 0 ? -c->box.LBOX[axis] : c->box.LBOX[axis], c->d_blk + (size_t)k * c->nblk_cap, ns[k], c->sbuf[k]);
-    if (c->cp[d0 - 1] + nr[0] + nr[1] > NB) { c->err = "ERROR: over capacity in append_atoms (NBUFFER)"; return RXG_ERR_NBUFFER; }
     size_t cs[2] = {(size_t)NE_MOVE * ns[0], (size_t)NE_MOVE * ns[1]}, cr[2] = {(size_t)NE_MOVE * nr[0], (size_t)NE_MOVE * nr[1]};
     double *rb[2];
     RXG_TRY(exchange_axis(c, axis, cs, cr, rb, false));

@@ -33,7 +33,7 @@ __global__ void k_nbrlist(DevGrid g, const DevFF *__restrict__ ffp, int ntot, in
       int base = ((c1 + c4 + g.L) * g.dim[1] + (c2 + c5 + g.L)) * g.dim[2] + (c3 + g.L);
       int s = g.start[base - 1], e = g.start[base + 2];   // cells c3-1 .. c3+1 are contiguous (z fastest)
       for (int k = s; k < e; k++) {
-        double4 o = g.sorted[k];
+        double4 o = ldg256(g.sorted + k);
         int n = rec_index(o.w);
         if (n == m) continue;
         int nty = rec_type(o.w);
@@ -191,7 +191,7 @@ __global__ void __launch_bounds__(PL_WARPS * 32) k_pairlist(DevGrid g, const Dev
           while (fpos >= sh_p[wid][r + 1]) r++;
         const int cslot = have ? sh_s[wid][r] + (fpos - sh_p[wid][r]) : 0;
         double4 o = make_double4(0, 0, 0, 0);
-        if (have) o = g.sorted[cslot];
+        if (have) o = ldg256(g.sorted + cslot);
         const int jt = rec_type(o.w);
         const int cval = cslot | ((have && rec_index(o.w) >= natoms) ? COL_GHOST : 0);
         unsigned um = 0;   // rows of this batch whose list takes this lane's candidate
@@ -628,14 +628,15 @@ __global__ void __launch_bounds__(ROWS * LPR) k_spmv_rows(const int *__restrict_
                                                           const long long *__restrict__ rowoff, const long long *__restrict__ rowbeg,
                                                           const long long *__restrict__ rowend, const int *__restrict__ col,
                                                           const double *__restrict__ val, const double2 *__restrict__ x,
-                                                          double4 *__restrict__ rowsum, const double *__restrict__ acc, int stage) {
+                                                          double4 *__restrict__ rowsum, const double *__restrict__ acc, int stage,
+                                                          const int *__restrict__ grp) {
   constexpr int CAP = ROWS * CAPROW;   // CAPROW = longest row the staged path takes (480: 10 A lists; 1216: the 12.5 A lists of PQEq)
   if (acc[ACC_DONE] != 0.0) return;   // the CG has stopped (k_cg_ctrl): iterations enqueued ahead of the host's check do nothing
   __shared__ __align__(128) double s_val[CAP];
   __shared__ __align__(128) int s_col[CAP];
   __shared__ __align__(8) unsigned long long bar;
   const int sub = threadIdx.x % LPR, rowid = threadIdx.x / LPR;
-  const int slot0 = blockIdx.x * ROWS;
+  const int slot0 = (grp ? grp[blockIdx.x] : blockIdx.x) * ROWS;   // grp: the interior or the boundary row groups only (spmv_launch)
   const int slot1 = min(slot0 + ROWS, ntot);
   const long long sb = rowoff[slot0], se = rowoff[slot1];
   const int span = (int)(se - sb);
@@ -877,6 +878,33 @@ __global__ void __launch_bounds__((SI_CONS + 1) * 32, 1) k_spmv_items(const SpIt
       if (lane == 0) mbar_arrive(&empty[s]);
     }
   }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Interior / boundary split of the CG's sparse product (multi-rank).  A row whose cell lies at least `lay` cells (the
+// stencil's reach) inside the resident grid along every axis has no ghost column, so its product does not depend on the
+// ghost refresh of (hs,ht) and can run WHILE the neighbours' values travel; the other rows follow once they have arrived.
+// k_group_class: class of each group of `rows` consecutive slots (what one CTA of k_spmv_rows takes): 1 = every slot in an
+// interior cell (or a ghost slot, which owns no row), 0 = boundary.  k_group_lists compacts both classes.
+__global__ void k_group_class(DevGrid g, int ntot, int rows, int lay, int *__restrict__ cls) {
+  const int grp = blockIdx.x * blockDim.x + threadIdx.x;
+  if ((long long)grp * rows >= ntot) return;
+  int interior = 1;
+  for (int s = grp * rows; s < min(ntot, (grp + 1) * rows); s++) {
+    const int cid = g.cell_of[g.order[s]];
+    const int c3 = cid % g.dim[2] - g.L, c2 = (cid / g.dim[2]) % g.dim[1] - g.L, c1 = cid / (g.dim[2] * g.dim[1]) - g.L;
+    const bool res = c1 >= 0 && c1 < g.nc[0] && c2 >= 0 && c2 < g.nc[1] && c3 >= 0 && c3 < g.nc[2];
+    if (!res) continue;   // ghost slot: no row
+    if (c1 < lay || c1 >= g.nc[0] - lay || c2 < lay || c2 >= g.nc[1] - lay || c3 < lay || c3 >= g.nc[2] - lay) interior = 0;
+  }
+  cls[grp] = interior;
+}
+__global__ void k_group_lists(int ngrp, const int *__restrict__ cls, const int *__restrict__ off, int *__restrict__ lst_int,
+                              int *__restrict__ lst_bnd) {
+  const int grp = blockIdx.x * blockDim.x + threadIdx.x;
+  if (grp >= ngrp) return;
+  if (cls[grp]) lst_int[off[grp]] = grp;       // off = exclusive scan of cls
+  else lst_bnd[grp - off[grp]] = grp;
 }
 
 template <bool INIT>

@@ -33,7 +33,7 @@ __device__ __forceinline__ bool clmb_pqeq(const DevFF &ff, const double4 *__rest
   const double drtb = mul_rn(sub_rn(dr2, mul_rn((double)itb, ff.UDR)), ff.UDRi);
   const double drtb1 = sub_rn(1.0, drtb);
   if (inxn >= 1 && itb >= 1 && itb + 1 <= ff.ntable) {   // outside: the reference reads out of bounds (like SURVEY Q9)
-    const double4 t = T[(size_t)(inxn - 1) * ff.ntable + (itb - 1)];
+    const double4 t = ldg256(T + (size_t)(inxn - 1) * ff.ntable + (itb - 1));
     E = add_rn(mul_rn(drtb1, t.x), mul_rn(drtb, t.y));
     dE = add_rn(mul_rn(drtb1, t.z), mul_rn(drtb, t.w));
   }
@@ -58,7 +58,7 @@ __device__ __forceinline__ bool clmb_pqeq_c(const DevFF &ff, const double4 *__re
     double4 t;
     if (ff.pq_same && itb == pc.itb) t = pc.t;
     else {
-      t = T[(size_t)(inxn - 1) * ff.ntable + (itb - 1)];
+      t = ldg256(T + (size_t)(inxn - 1) * ff.ntable + (itb - 1));
       pc.itb = itb; pc.t = t;
     }
     E = add_rn(mul_rn(drtb1, t.x), mul_rn(drtb, t.y));
@@ -107,12 +107,12 @@ __global__ void __launch_bounds__(256) k_pqeq_rows(const DevGrid g, int ntot, in
     for (long long k = s + lane; k < e; k += 32) {
       const int cj = col[k];
       const int js = cj & COL_MASK;
-      const double4 oj = g.sorted[js];
+      const double4 oj = ldg256(g.sorted + js);
       const double dx = sub_rn(me.x, oj.x), dy = sub_rn(me.y, oj.y), dz = sub_rn(me.z, oj.z);
       // a list shared with FORCE holds the fp64 '<=' pairs; qeq_initialize keeps real(4) dr2 < rctap2 (src/pqeq.F90:316)
       if (!((float)dist2_rn(dx, dy, dz) < rctap2f)) { val[k] = 0.0; continue; }
       const int jty = rec_type(oj.w);
-      const double4 sj = sps[js];
+      const double4 sj = ldg256(sps + js);
       const int ix = ff.inxnpqeq[(ity - 1) + np * (jty - 1)];
       double E, dE;
       PqCache pc; pc.itb = -1;
@@ -302,10 +302,10 @@ __global__ void __launch_bounds__(256) k_shell_relax(const DevGrid g, int ntot, 
   const long long s = rowbeg[i], e = rowend[i];
   for (long long k = s + lane; k < e; k += 32) {
     const int js = col[k] & COL_MASK;
-    const double4 oj = g.sorted[js];
+    const double4 oj = ldg256(g.sorted + js);
     if (!((float)dist2_rn(sub_rn(me.x, oj.x), sub_rn(me.y, oj.y), sub_rn(me.z, oj.z)) < rctap2f)) continue;   // QEq-list predicate
     const int jty = rec_type(oj.w);
-    const double4 sj = sps[js];
+    const double4 sj = ldg256(sps + js);
     const double qjc = qsl[js] + sj.w;
     const int ix = ff.inxnpqeq[(ity - 1) + np * (jty - 1)];
     double E, dE;
@@ -363,7 +363,7 @@ __global__ void __launch_bounds__(256) k_enbond_pqeq(int ntot, int natoms, const
       const int js = __ldcs(col + k) & COL_MASK;
       const int4 tj = tgs[js];
       if (!(ti.y < tj.y)) continue;
-      const double4 pj = pqs[js], sj = sps[js];
+      const double4 pj = ldg256(pqs + js), sj = ldg256(sps + js);
       const double dx = sub_rn(pi.x, pj.x), dy = sub_rn(pi.y, pj.y), dz = sub_rn(pi.z, pj.z);
       const double dr2 = dist2_rn(dx, dy, dz);
       const int inxn = ff.inxn2[(ti.x - 1) + ff.nso * (tj.x - 1)];
@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(256) k_enbond_pqeq(int ntot, int natoms, const
         const double drtb = mul_rn(sub_rn(dr2, mul_rn((double)itb, ff.UDR)), ff.UDRi);
         const double drtb1 = 1.0 - drtb;
         const double4 *T = ff.TBL_nb + (size_t)(inxn - 1) * ff.ntable + (itb - 1);
-        const double4 T0 = T[0], T1 = T[1];
+        const double4 T0 = ldg256(T), T1 = ldg256(T + 1);
         PEvdw = drtb1 * T0.x + drtb * T1.x;
         CEvdw = drtb1 * T0.y + drtb * T1.y;
       }

@@ -49,6 +49,10 @@ type, bind(C) :: rxg_box
 end type
 
 type(c_ptr), save :: rxg_handle = c_null_ptr
+! set .true. by the host right before its main loop (src/main.F90:47) and .false. after it: inside the loop the wrappers below
+! tell the library which arrays it already holds (rxg_hint), so pos crosses PCIe once up and once down per step
+logical, save :: rxg_loop_hints = .false.
+integer(c_int), parameter :: RXG_HINT_ATOMS_ON_DEVICE = 1, RXG_HINT_Q_ON_DEVICE = 2, RXG_HINT_DEFER_POS = 4
 
 interface
    integer(c_int) function rxg_create(cfg, h) bind(C, name="rxg_create")
@@ -93,6 +97,12 @@ interface
    end function
    type(c_ptr) function rxg_last_error(h) bind(C, name="rxg_last_error")
       import; type(c_ptr), value :: h
+   end function
+   integer(c_int) function rxg_hint(h, flags) bind(C, name="rxg_hint")
+      import; type(c_ptr), value :: h; integer(c_int), value :: flags
+   end function
+   integer(c_int) function rxg_it_timer(h, sec) bind(C, name="rxg_it_timer")
+      import; type(c_ptr), value :: h; real(c_double) :: sec(30)
    end function
 end interface
 
@@ -178,8 +188,9 @@ subroutine QEq(atype, pos, q)                                  ! replaces src/qe
 use atoms; use rxg_binding
 implicit none
 real(8) :: atype(NBUFFER), pos(NBUFFER,3), q(NBUFFER)
+! inside the main loop nothing touches atype/pos/q between COPYATOMS(MODE_MOVE), QEq and FORCE (src/main.F90:75-84)
+if (rxg_loop_hints) call rxg_check(rxg_hint(rxg_handle, RXG_HINT_ATOMS_ON_DEVICE + RXG_HINT_Q_ON_DEVICE + RXG_HINT_DEFER_POS))
 call rxg_check(rxg_qeq(rxg_handle, NATOMS, atype, pos, q, qsfp, qsfv, nstep_qeq))
-it_timer(24) = it_timer(24) + nstep_qeq
 end subroutine
 
 !------------------------------------------------------------------------------------------------------------
@@ -187,8 +198,8 @@ subroutine PQEq(atype, pos, q)                                 ! replaces src/pq
 use atoms; use rxg_binding
 implicit none
 real(8) :: atype(NBUFFER), pos(NBUFFER,3), q(NBUFFER)
+if (rxg_loop_hints) call rxg_check(rxg_hint(rxg_handle, RXG_HINT_ATOMS_ON_DEVICE + RXG_HINT_Q_ON_DEVICE + RXG_HINT_DEFER_POS))
 call rxg_check(rxg_pqeq(rxg_handle, NATOMS, atype, pos, q, spos, qsfp, qsfv, nstep_qeq))
-it_timer(24) = it_timer(24) + nstep_qeq
 end subroutine
 
 !------------------------------------------------------------------------------------------------------------
@@ -196,7 +207,23 @@ subroutine FORCE(atype, pos, f, q)                             ! replaces src/po
 use atoms; use rxg_binding
 implicit none
 real(8) :: atype(NBUFFER), q(NBUFFER), pos(NBUFFER,3), f(NBUFFER,3)
-call rxg_check(rxg_force(rxg_handle, NATOMS, atype, pos, f, q, PE, astr))
+if (rxg_loop_hints) call rxg_check(rxg_hint(rxg_handle, RXG_HINT_ATOMS_ON_DEVICE + RXG_HINT_Q_ON_DEVICE))
+call rxg_check(rxg_force(rxg_handle, NATOMS, atype, pos, f, q, PE, astr))      ! hands back the final pos of the step
+end subroutine
+
+!------------------------------------------------------------------------------------------------------------
+! it_timer(1:30) for the timing table of src/main.F90:135-180: the library measures its phases with CUDA events in the
+! reference's own slots (seconds); the host keeps ticks, so convert with its clock rate irt.  Call once before the table.
+subroutine rxg_fill_it_timer()
+use atoms; use rxg_binding
+implicit none
+real(c_double) :: sec(30)
+integer :: k
+call rxg_check(rxg_it_timer(rxg_handle, sec))
+do k = 1, 19
+   if (k /= 2 .and. k /= 14 .and. k /= 17) it_timer(k) = it_timer(k) + nint(sec(k) * irt)
+enddo
+it_timer(24) = it_timer(24) + nint(sec(24))       ! QEq iterations (src/qeq.F90:172)
 end subroutine
 
 !------------------------------------------------------------------------------------------------------------
@@ -211,6 +238,8 @@ if (imode /= MODE_MOVE) then
    call MPI_FINALIZE(ierr); stop
 endif
 if (isPQEq) call rxg_check(rxg_spos_upload(rxg_handle, NATOMS, spos))      ! spos migrates with the atom (src/comm.F90:153,165-167)
+! in a step without output the host does not read pos before FORCE returns it: leave the ulp-level round trip on the device
+if (rxg_loop_hints .and. mod(nstep, fstep) /= 0) call rxg_check(rxg_hint(rxg_handle, RXG_HINT_DEFER_POS))
 call rxg_check(rxg_move(rxg_handle, NATOMS, atype, pos, v, q, qs, qt, qsfp, qsfv))
 if (isPQEq) call rxg_check(rxg_spos_download(rxg_handle, NATOMS, spos))
 end subroutine

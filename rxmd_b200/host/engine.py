@@ -21,6 +21,7 @@ import numpy as np
 from .binding import RxgConfig, RxgFF, RxgBox
 
 MODE_COPY, MODE_MOVE, MODE_CPBK, MODE_QCOPY1, MODE_QCOPY2 = 1, 2, 3, 4, 5   # src/module.F90:38-39
+HINT_ATOMS_ON_DEVICE, HINT_Q_ON_DEVICE, HINT_DEFER_POS = 1, 2, 4             # include/rxmd_b200.h (rxg_hint)
 
 _LIB = None
 
@@ -71,6 +72,8 @@ def load_library():
     L.rxg_md_velocity_affine.argtypes = [vp, dp, dp]
     L.rxg_debug_fetch.argtypes = [vp, C.c_char_p, vp, C.c_longlong, C.POINTER(C.c_longlong)]
     L.rxg_debug_spmv.argtypes = [vp, dp, dp, C.c_int, dp]
+    L.rxg_hint.argtypes = [vp, C.c_int]
+    L.rxg_it_timer.argtypes = [vp, dp]
     L.rxg_launch_count.argtypes = [vp]
     L.rxg_launch_count.restype = C.c_longlong
     _LIB = L
@@ -144,6 +147,10 @@ class Engine:
         raw = broadcast_bytes(dist, bytes(buf))
         buf2 = (C.c_ubyte * 128).from_buffer_copy(raw)
         self._chk(self.L.rxg_comm_init(self.h, rank, nranks, C.cast(buf2, C.c_void_p)))
+
+    def hint(self, flags):
+        """Promises about the arrays of the next entry-point call (rxg_hint): what the Fortran shim states inside the main loop."""
+        self._chk(self.L.rxg_hint(self.h, int(flags)))
 
     def peer_halo(self):
         """True when the per-iteration ghost refreshes use peer-memory windows (NVLink stores) instead of NCCL send/recv."""
@@ -263,6 +270,12 @@ class Engine:
     def timers(self):
         t = np.zeros(30)
         self.L.rxg_timers(self.h, _dp(t))
+        return t
+
+    def it_timer(self):
+        """The reference's it_timer(1:30) in seconds (index k-1 = slot k; slot 24 = QEq iterations)."""
+        t = np.zeros(30)
+        self._chk(self.L.rxg_it_timer(self.h, _dp(t)))
         return t
 
     def launches(self):

@@ -510,3 +510,60 @@ def test_thermostat_hooks_scale_temperature(built):
             assert abs((st2[t, 1] / st2[t, 0]) * UTEMP - treq * UTEMP0) < 1e-10 * treq * UTEMP0
     assert np.abs(st3[:, 3:6].sum(axis=0)).max() < 1e-12 * st3[:, 2].sum()
     e.close(); o.close()
+
+
+def test_hinted_entry_points_equal_literal_ones(built):
+    """rxg_hint (include/rxmd_b200.h): the promises a shim makes inside the reference's main loop (src/main.F90:75-84) only
+    remove PCIe copies -- three MOVE/QEq/FORCE steps with hints give bit-identical host arrays to the literal sequence, with
+    less than a third of the bytes."""
+    from rxmd_b200.host.engine import HINT_ATOMS_ON_DEVICE, HINT_Q_ON_DEVICE, HINT_DEFER_POS
+    os.environ["RXG_FUSE_API"] = "1"
+    out = {}
+    for mode in ("literal", "hinted"):
+        s, cfg, e, o = make("rdx_2x2x2_disp")
+        o.close()
+        atype, pos, v, f, q = e.host_arrays(s.ranks[0])
+        n = e.NATOMS
+        rng = np.random.default_rng(3)
+        v[:, :n] = rng.normal(0.0, 5e-3, (3, n))
+        dt = 0.25 / UTIME
+        h = (lambda fl: e.hint(fl)) if mode == "hinted" else (lambda fl: None)
+        e.QEq(atype, pos, q); e.FORCE(atype, pos, f, q)
+        b0 = e.timers()[20:22].copy()
+        for step in range(3):
+            pos[:, :n] += dt * v[:, :n]
+            h(HINT_DEFER_POS)
+            e.COPYATOMS(2, [0.0, 0.0, 0.0], atype, pos, v, f, q)
+            n = e.NATOMS
+            h(HINT_ATOMS_ON_DEVICE | HINT_Q_ON_DEVICE | HINT_DEFER_POS)
+            e.QEq(atype, pos, q)
+            h(HINT_ATOMS_ON_DEVICE | HINT_Q_ON_DEVICE)
+            e.FORCE(atype, pos, f, q)
+        out[mode] = dict(pos=pos[:, :n].copy(), q=q[:n].copy(), f=f[:, :n].copy(), pe=e.PE.copy(), bytes=(e.timers()[20:22] - b0).sum(),
+                         qsfp=e.qsfp[:n].copy())
+        e.close()
+    for k in ("pos", "q", "f", "pe", "qsfp"):
+        assert np.array_equal(out["literal"][k], out["hinted"][k]), k
+    assert out["hinted"]["bytes"] < 0.34 * out["literal"]["bytes"], (out["hinted"]["bytes"], out["literal"]["bytes"])
+
+
+def test_it_timer_slots_are_filled(built):
+    """rxg_it_timer hands the host its timing table (src/main.F90:144-180) in the reference's own it_timer slots."""
+    s, cfg, e, o = make("rdx_2x2x2_disp")
+    o.close()
+    atype, pos, v, f, q = e.host_arrays(s.ranks[0])
+    for _ in range(2):
+        e.COPYATOMS(2, [0.0, 0.0, 0.0], atype, pos, v, f, q)
+        e.QEq(atype, pos, q)
+        e.FORCE(atype, pos, f, q)
+    t = e.it_timer()
+    own = [1, 3, 4, 5, 6, 7, 8, 9, 10, 11, 12, 13, 15, 16, 18]
+    for k in own:
+        assert t[k - 1] > 0.0, f"it_timer({k}) is empty"
+    assert t[23] == 2 * e.nstep_qeq or t[23] > 0                         # it_timer(24): QEq iterations
+    for k in (20, 21, 22, 23, 25, 26, 27, 30):                           # the host's own slots stay untouched
+        assert t[k - 1] == 0.0
+    ms = e.timers()
+    total = sum(t[k - 1] for k in own if k != 1)                         # slot 1 is the sum of the QEq-internal phases
+    assert abs(total * 1e3 - (ms[0] + ms[1] + ms[2])) < 0.25 * (ms[0] + ms[1] + ms[2])
+    e.close()

@@ -66,3 +66,40 @@ def test_build_system_partitions_consistently():
         Hi = np.asarray(b.Hi)
         rn = (Hi @ r["pos"]).T - np.array(list(b.struct.OBOX))
         assert rn.min() > -1e-12 and np.all(rn.max(axis=0) < np.array(list(b.struct.LBOX)) + 1e-12)
+
+
+def test_per_rank_generation_equals_global_generation(tmp_path):
+    """a rank generates (and reads) its own sub-domain only.  `only_rank=r` must give exactly the atoms the
+    all-rank build gives rank r, the synthetic displacements must not depend on the decomposition, and the rxff.bin slice
+    reader must return rank r's records alone (64-bit offsets, src/fileio.F90:499-505)."""
+    g = os.path.join(INP, "init.rdx.lg")
+    xyz, ffp = os.path.join(g, "input.xyz"), os.path.join(g, "ffield")
+    full = build_system(xyz, ffp, mc=(4, 4, 2), vprocs=(2, 2, 1), isLG=True, displace_sigma=0.02)
+    one = build_system(xyz, ffp, mc=(4, 4, 2), vprocs=(1, 1, 1), isLG=True, displace_sigma=0.02)
+    for r in range(4):
+        part = build_system(xyz, ffp, mc=(4, 4, 2), vprocs=(2, 2, 1), isLG=True, displace_sigma=0.02, only_rank=r)
+        assert [x is None for x in part.ranks] == [k != r for k in range(4)]
+        assert np.array_equal(part.ranks[r]["atype"], full.ranks[r]["atype"])
+        assert np.array_equal(part.ranks[r]["pos"], full.ranks[r]["pos"])
+        assert part.natoms == full.natoms == 168 * 32
+    # same geometry whatever the decomposition: match atoms by global id
+    gid = lambda a: np.rint((a - np.rint(a)) * 1e13).astype(np.int64)
+    a4 = np.concatenate([r["atype"] for r in full.ranks]); p4 = np.concatenate([r["pos"] for r in full.ranks], axis=1)
+    o4, o1 = np.argsort(gid(a4)), np.argsort(gid(one.ranks[0]["atype"]))
+    assert np.array_equal(gid(a4)[o4], gid(one.ranks[0]["atype"])[o1])
+    assert np.abs(p4[:, o4] - one.ranks[0]["pos"][:, o1]).max() < 1e-9
+    # displacements are Gaussian with the requested width
+    und = build_system(xyz, ffp, mc=(4, 4, 2), isLG=True)
+    d = one.ranks[0]["pos"] - und.ranks[0]["pos"]
+    d = d[:, np.abs(d).max(axis=0) < 1.0]                            # skip atoms wrapped through a face
+    assert abs(d.std() - 0.02) < 1e-3 and abs(d.mean()) < 1e-3
+    # rxff.bin: per-rank slice
+    ff = read_ffield(ffp, isLG=True)
+    t0, p0, lat = geninit.read_xyz(xyz, ff.atmname)
+    gen = geninit.replicate(t0, p0, lat, (4, 4, 2), (2, 2, 1))
+    p = tmp_path / "rxff.bin"
+    geninit.write_rxff_bin(str(p), gen, (2, 2, 1))
+    sl = geninit.read_rxff_bin(str(p), only_rank=2)
+    assert [x is None for x in sl["ranks"]] == [True, True, False, True]
+    assert np.array_equal(sl["ranks"][2]["atype"], gen["ranks"][2]["atype"]) and np.array_equal(sl["ranks"][2]["pos_local"], gen["ranks"][2]["pos_local"])
+    assert sl["natoms_per_rank"] == tuple(len(r["atype"]) for r in gen["ranks"])
