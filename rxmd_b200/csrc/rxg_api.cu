@@ -451,7 +451,7 @@ int rxg_create(const rxg_config *cfg, rxg_handle *out) {
   const char *ov = getenv("RXG_OVERLAP");
   c->overlap_env = !(ov && ov[0] == '0');
   const char *eo = getenv("RXG_EVAL_OCC");
-  c->eval_occ = eo && eo[0] == '1';
+  c->eval_occ = !(eo && eo[0] == '0');   // default on: measured 15.7 -> 14.6 ms per FORCE at 979 776 RDX atoms
   const char *sk = getenv("RXG_SPMV");
   c->spmv_kind = (sk && std::string(sk) == "items") ? 0 : 1;   // 1: k_spmv_rows (default), 0: k_spmv_items (experiment)
   const char *ss = getenv("RXG_SPMV_SHAPE");

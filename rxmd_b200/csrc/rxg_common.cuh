@@ -168,7 +168,7 @@ struct Ctx {
   int arseq = 0;                     // all-reduce sequence number
   bool peer_all = false;             // every rank's window is open here: CG scalars are reduced through the windows
   int *d_pushcnt = nullptr;          // [2] block-completion counters of the push kernels
-  bool eval_occ = false;    // RXG_EVAL_OCC=1: the angle / torsion / H-bond evaluators compiled for more resident CTAs (fewer registers)
+  bool eval_occ = true;     // RXG_EVAL_OCC=0 switches back to the angle / torsion / H-bond evaluators compiled without a register cap
   // interior / boundary split of the SpMV (multi-rank): the ghost refresh runs on st2 beside the interior rows
   cudaStream_t st2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;

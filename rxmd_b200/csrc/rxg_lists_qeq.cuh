@@ -631,7 +631,7 @@ __global__ void __launch_bounds__(ROWS * LPR) k_spmv_rows(const int *__restrict_
                                                           double4 *__restrict__ rowsum, const double *__restrict__ acc, int stage,
                                                           const int *__restrict__ grp) {
   constexpr int CAP = ROWS * CAPROW;   // CAPROW = longest row the staged path takes (480: 10 A lists; 1216: the 12.5 A lists of PQEq)
-  if (acc[ACC_DONE] != 0.0) return;   // the CG has stopped (k_cg_ctrl): iterations enqueued ahead of the host's check do nothing
+  const double cg_done = acc[ACC_DONE];   // tested below, so that this load flies together with the row-offset loads
   __shared__ __align__(128) double s_val[CAP];
   __shared__ __align__(128) int s_col[CAP];
   __shared__ __align__(8) unsigned long long bar;
@@ -639,6 +639,7 @@ __global__ void __launch_bounds__(ROWS * LPR) k_spmv_rows(const int *__restrict_
   const int slot0 = (grp ? grp[blockIdx.x] : blockIdx.x) * ROWS;   // grp: the interior or the boundary row groups only (spmv_launch)
   const int slot1 = min(slot0 + ROWS, ntot);
   const long long sb = rowoff[slot0], se = rowoff[slot1];
+  if (cg_done != 0.0) return;   // the CG has stopped (k_cg_ctrl): iterations enqueued ahead of the host's check do nothing
   const int span = (int)(se - sb);
   const bool staged = stage && span > 0 && span <= CAP;   // stage == 0: every CTA reads straight from HBM (the path long rows take)
   if (staged) {
