@@ -151,20 +151,21 @@ def preflight_parity(dist, rank, world, local):
     import torch
     from tools.mr_diag import compare
     mc = {2: (6, 3, 3), 4: (6, 6, 3), 8: (5, 5, 5)}[world]          # RDX 168-atom cells: 9 072 / 18 144 / 21 000 atoms
-    try:
-        res = compare(rank, world, local, mc, sigma=0.02, verbose=False)
-    except Exception as ex:   # a failed pre-flight is reported, never hidden
-        res = {"ok": False, "error": repr(ex)[:300], "dq": float("nan"), "f_rel": float("nan"), "md_pe_rel": float("nan"),
-               "nstep_same": False, "peer_halo": False, "peer_allreduce": False}
-    t = torch.tensor([1.0 if res["ok"] else 0.0, -res["dq"] if res["dq"] == res["dq"] else -1e9, -res["f_rel"] if res["f_rel"] == res["f_rel"] else -1e9,
-                      -res["md_pe_rel"] if res["md_pe_rel"] == res["md_pe_rel"] else -1e9, 1.0 if res["nstep_same"] else 0.0],
+    res = compare(rank, world, local, mc, sigma=0.02, verbose=False)   # a failed comparison is reported in the line, never hidden
+    flags = ["ok", "copyptr_qeq", "copyptr_force", "rows", "pe_ok", "migration", "nstep_same"]
+    nums = ["dq", "f_rel", "md_pe_rel"]
+    neg = lambda x: -x if x == x else -1e9          # NaN (a rank that raised) reads as a huge difference
+    t = torch.tensor([1.0 if res.get(k) else 0.0 for k in flags] + [neg(float(res.get(k, float("nan")))) for k in nums],
                      dtype=torch.float64, device="cuda")
     dist.all_reduce(t, op=dist.ReduceOp.MIN)
-    return {"ok": bool(t[0].item() > 0.5), "ranks": world, "atoms": int(np.prod(mc)) * 168, "replication": list(mc),
-            "max_dq": -t[1].item(), "max_force_rel": -t[2].item(), "md10_pe_rel": -t[3].item(), "nstep_qeq_same": bool(t[4].item() > 0.5),
-            "checked": "copyptr (QEq and FORCE halos), 10 A row counts, forces <= 1e-9, energies <= 1e-9, charges (3e-7 same stop / 1e-4), "
-                       "10 MD steps with migration: global PE <= 1e-6, atom counts", "peer_halo": res.get("peer_halo"),
-            "peer_allreduce": res.get("peer_allreduce"), "error": res.get("error")}
+    out = {"ok": bool(t[0].item() > 0.5), "ranks": world, "atoms": int(np.prod(mc)) * 168, "replication": list(mc)}
+    for i, k in enumerate(flags[1:], start=1):
+        out[k] = bool(t[i].item() > 0.5)
+    out.update({"max_dq": -t[len(flags)].item(), "max_force_rel": -t[len(flags) + 1].item(), "md10_pe_rel": -t[len(flags) + 2].item(),
+                "checked": "copyptr (QEq and FORCE halos), 10 A row counts, forces <= 1e-9, energies <= 1e-9 (pe_ok), charges (3e-7 same stop / 1e-4), "
+                           "10 MD steps with migration: global PE <= 1e-6, atom counts", "peer_halo": res.get("peer_halo"),
+                "peer_allreduce": res.get("peer_allreduce"), "error": res.get("error")})
+    return out
 
 
 def main():

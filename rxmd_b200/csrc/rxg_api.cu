@@ -448,8 +448,8 @@ int rxg_create(const rxg_config *cfg, rxg_handle *out) {
   c->fuse = !(nf && nf[0] == '1');
   const char *fa = getenv("RXG_FUSE_API");
   c->fuse_api = fa && fa[0] == '1';
-  const char *ov = getenv("RXG_OVERLAP");
-  c->overlap_env = !(ov && ov[0] == '0');
+  const char *ov = getenv("RXG_OVERLAP");   // opt-in: measured slower at 2 GPUs
+  c->overlap_env = ov && ov[0] == '1';
   const char *eo = getenv("RXG_EVAL_OCC");
   c->eval_occ = !(eo && eo[0] == '0');   // default on: measured 15.7 -> 14.6 ms per FORCE at 979 776 RDX atoms
   const char *sk = getenv("RXG_SPMV");
@@ -657,7 +657,16 @@ int rxg_comm_init(rxg_handle h, int rank, int nranks, const void *id) {
   const char *ph = getenv("RXG_PEER_HALO");
   int want = !(ph && ph[0] == '0');
   c->peer.assign(nranks, nullptr);
-  c->pw_cap = (size_t)3 * (size_t)c->NB;   // >= 3 fields x NBUFFER atoms: no refresh can exceed a buffer, so no rank can fail alone
+  // The window layout must be the same on every rank (a rank addresses its neighbours' windows with its own offsets), but
+  // NBUFFER is a per-rank setting: size the buffers from the largest one.  3 fields x NBUFFER atoms per buffer: no refresh can
+  // exceed a buffer, so no rank can fail alone.
+  int nbmax = c->NB;
+  RXG_CUDA(cudaMemcpy(c->d_flag + 19, &nbmax, sizeof(int), cudaMemcpyHostToDevice));
+  r = nccl_api().AllReduce(c->d_flag + 19, c->d_flag + 19, 1, ncclInt, ncclMax, c->comm, c->st);
+  if (r != ncclSuccess) { c->err = std::string("ncclAllReduce: ") + nccl_api().GetErrorString(r); return RXG_ERR_NCCL; }
+  RXG_CUDA(cudaStreamSynchronize(c->st));
+  RXG_CUDA(cudaMemcpy(&nbmax, c->d_flag + 19, sizeof(int), cudaMemcpyDeviceToHost));
+  c->pw_cap = (size_t)3 * (size_t)nbmax;
   const size_t wbytes = sizeof(double) * (PW_HDR + 12 * c->pw_cap + PW_AR_DOUBLES);
   int *d_ok = c->d_flag + 2;
   cudaIpcMemHandle_t *d_h = nullptr, *d_all = nullptr;
@@ -723,6 +732,13 @@ int rxg_destroy(rxg_handle h) {
   if (c->st) {
     cudaSetDevice(c->dev);
     cudaStreamSynchronize(c->st);
+    if (c->st2) cudaStreamSynchronize(c->st2);
+    if (c->comm && c->d_flag) {
+      // Teardown is collective: a neighbour's kernels may still be storing into this rank's peer window.  An all-reduce in
+      // stream order completes only after every rank has drained its own stream up to its rxg_destroy.
+      nccl_api().AllReduce(c->d_flag + 19, c->d_flag + 19, 1, ncclInt, ncclSum, c->comm, c->st);
+      cudaStreamSynchronize(c->st);
+    }
     for (void *p : c->allocs) cudaFree(p);
     for (void *p : c->ff_allocs) cudaFree(p);
     for (void *p : {(void *)c->col, (void *)c->val, (void *)c->ucol, (void *)c->umask, (void *)c->d_blk, (void *)c->d_blk64, (void *)c->d_runs, (void *)c->d_ff})

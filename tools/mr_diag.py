@@ -26,7 +26,7 @@ def rel(a, b):
     return d, d / max(np.abs(b).max() if b.size else 0.0, 1e-300)
 
 
-def compare(rank, world, local, mc, sigma=0.0, pqeq=False, do_assert=False, verbose=True):
+def _compare_body(rank, world, local, mc, sigma, pqeq, holder):
     """One multi-rank comparison over the library's own data plane (NCCL exchange in MODE_COPY/MOVE/CPBK, peer-memory windows
     for the per-iteration refreshes and all-reduces) against the oracle simulating the same `vprocs`.  Needs an initialised
     torch.distributed NCCL group.  Returns a dict of this rank's findings (all-reduced into a verdict by the caller)."""
@@ -41,8 +41,10 @@ def compare(rank, world, local, mc, sigma=0.0, pqeq=False, do_assert=False, verb
         s = build_system(G + "input.xyz", G + "ffield", mc=mc, vprocs=vp, displace_sigma=sigma)
     cfg = s.config(device=local)
     e = Engine(s, cfg, rank=rank)
+    holder["e"] = e
     e.comm_init_torch(dist)
     o = Oracle(s, cfg)       # all ranks, simulated
+    holder["o"] = o
     atype, pos, v, f, q = e.host_arrays(s.ranks[rank])
     n = e.NATOMS
     out = [f"rank {rank}/{world} vprocs {vp} natoms {n} of {s.natoms} peer_halo {e.peer_halo()}"]
@@ -122,15 +124,34 @@ def compare(rank, world, local, mc, sigma=0.0, pqeq=False, do_assert=False, verb
     # charges: the production CG's bars (tests/test_gpu_parity.py: 3e-7 when both sides stop in the same iteration, 1e-4 otherwise)
     res["ok"] = bool(res["copyptr_qeq"] and res["copyptr_force"] and res["rows"] and res["f_rel"] < 1e-9 and res["pe_ok"] and
                      res["migration"] and res["md_pe_rel"] < 1e-6 and res["dq"] <= (3e-7 if nstep_same else 1e-4))
-    if do_assert:
-        assert res["ok"], res
+    return res, out
+
+
+def compare(rank, world, local, mc, sigma=0.0, pqeq=False, do_assert=False, verbose=True):
+    """Collective: every rank reaches the closing barrier and tears its engine down even if its own comparison raised, so
+    that a failure is reported instead of leaving the other ranks waiting."""
+    holder, out = {}, []
+    try:
+        res, out = _compare_body(rank, world, local, mc, sigma, pqeq, holder)
+    except Exception as ex:
+        res = {"ok": False, "error": repr(ex)[:300], "dq": float("nan"), "f_rel": float("nan"), "md_pe_rel": float("nan"),
+               "nstep_same": False, "peer_halo": False, "peer_allreduce": False}
     if verbose:
         for r in range(world):
             dist.barrier()
             if r == rank:
                 print("\n".join(out), flush=True)
-    e.close()
-    o.close()
+    try:
+        torch.cuda.synchronize()
+    except Exception:
+        pass
+    dist.barrier()           # nobody frees its peer window while a neighbour may still be writing into it
+    if "e" in holder:
+        holder["e"].close()
+    if "o" in holder:
+        holder["o"].close()
+    if do_assert:
+        assert res["ok"], res
     return res
 
 
