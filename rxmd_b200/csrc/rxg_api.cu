@@ -278,6 +278,33 @@ int spmv_after_refresh(Ctx *c) {
   return spmv_launch(c, 2);
 }
 
+// A list that was filled without a count pass (build_pairlist, `capped`) reports its traps and statistics through device flags.
+// Called right after a stream synchronisation that covered copy_capped_flags().  RXG_RETRY: a row outgrew its capacity, the
+// caller rebuilds the list with the count pass and starts the solve over.
+constexpr int RXG_RETRY = 100;
+int copy_capped_flags(Ctx *c) {
+  if (!c->list_capped) return RXG_OK;
+  RXG_CUDA(cudaMemcpyAsync(c->h_int + 20, c->d_flag + 20, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+  RXG_CUDA(cudaMemcpyAsync(c->h_int, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+  RXG_CUDA(cudaMemcpyAsync(c->h_int + 16, c->d_flag + 16, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+  RXG_CUDA(cudaMemcpyAsync(c->h_acc + 33, c->d_acc + 33, sizeof(long long), cudaMemcpyDeviceToHost, c->st));
+  if (c->comm) RXG_CUDA(cudaMemcpyAsync(c->h_acc + 26, c->d_acc + 26, sizeof(double), cudaMemcpyDeviceToHost, c->st));
+  return RXG_OK;
+}
+int check_capped_flags(Ctx *c) {
+  if (!c->list_capped) return RXG_OK;
+  c->list_capped = false;   // checked once per list
+  if (c->h_int[0] > c->cfg.maxneighbs10) {
+    c->err = "ERROR: nbplist greater then MAXNEIGHBS10, value " + std::to_string(c->h_int[0]);
+    return RXG_ERR_MAXNEIGHBS10;
+  }
+  // multi-rank: every rank must take the same decision -- the flags were summed over the ranks (qeq_cg_single)
+  if (c->comm ? c->h_acc[26] > 0.5 : c->h_int[20] != 0) { c->caps_overflows++; return RXG_RETRY; }
+  c->maxrow = c->h_int[16];
+  c->nnz_real = *(long long *)(c->h_acc + 33);
+  return RXG_OK;
+}
+
 constexpr int CG_BATCH = 4;
 int qeq_cg_single(Ctx *c, int nmax, int *iters) {
   const int n = c->natoms;
@@ -294,6 +321,10 @@ int qeq_cg_single(Ctx *c, int nmax, int *iters) {
   else
     LAUNCH(c, (k_cg_dots<true>), dgrid, 256, 0, c->gnb.order, c->cp[6], n, rowsum, c->xs, c->q, c->gst, c->tst, c->ust, c->wst, c->itype, c->d_ff, c->d_acc);
   RXG_TRY(allreduce_acc(c, 7, 2));
+  if (c->list_capped && c->comm) {   // did ANY rank's capped list overflow?  (all ranks retry together or not at all)
+    LAUNCH(c, k_flag_to_acc, 1, 1, 0, c->d_flag + 20, c->d_acc + 26);
+    RXG_TRY(allreduce_acc(c, 26, 1));
+  }
   LAUNCH(c, k_h_from_g2, cdiv(std::max(n, 1), 256), 256, 0, n, c->gst, c->hst, c->xs, c->gnb.slot_of, c->d_acc);
   RXG_TRY(build_row_groups(c));
   RXG_TRY(refresh_h(c));   // ghost hs,ht (MODE_QCOPY2, :93)
@@ -318,10 +349,12 @@ int qeq_cg_single(Ctx *c, int nmax, int *iters) {
       RXG_TRY(refresh_h(c));
     }
     if (c->overlap) RXG_CUDA(cudaStreamWaitEvent(c->st, c->ev_join, 0));   // the batch's last refresh runs on the side stream
+    RXG_TRY(copy_capped_flags(c));
     RXG_CUDA(cudaMemcpyAsync(c->h_acc + ACC_GEST2, c->d_acc + ACC_GEST2, sizeof(double) * 5, cudaMemcpyDeviceToHost, c->st));
     if (c->peer_ok) RXG_CUDA(cudaMemcpyAsync(c->h_int + 3, c->d_flag + 3, sizeof(int), cudaMemcpyDeviceToHost, c->st));
     RXG_CUDA(cudaStreamSynchronize(c->st));
     if (c->peer_ok && c->h_int[3]) { c->err = "peer halo: a neighbour's ghost values did not arrive (timeout)"; return RXG_ERR_NCCL; }
+    RXG_TRY(check_capped_flags(c));   // first batch after a capped list build: traps, overflow (-> RXG_RETRY), statistics
     done = c->h_acc[ACC_DONE] != 0.0;
     it = (int)c->h_acc[ACC_NITER];
     for (int j = 0; j < kb; j++) {   // sparse products that did work: iterations 0..it (the one that met the stop rule included)
@@ -350,6 +383,8 @@ int qeq_device(Ctx *c, bool for_force = false) {
   const int n = c->natoms;
   const int nmax = (isQEq == 1) ? c->cfg.NMAXQEq : 1;
   int nprev = c->cp[6] > n ? c->cp[6] : n;
+  const bool may_cap = c->caps_on && c->caps_valid && !c->strict && c->spmv_kind == 1 && c->qeq_mode == 0;
+  if (may_cap && n > 0) RXG_CUDA(cudaMemcpyAsync(c->q_save, c->q, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->st));
   if (nprev > 0)
     LAUNCH(c, k_qeq_init, cdiv(nprev, 256), 256, 0, n, nprev, c->q, c->qst, c->hsq, c->qsfp, c->qsfv, isQEq, c->cfg.Lex_fqs);
   double QCopyDr[3] = {c->ff.rctap / c->box.lata, c->ff.rctap / c->box.latb, c->ff.rctap / c->box.latc};
@@ -369,22 +404,41 @@ int qeq_device(Ctx *c, bool for_force = false) {
   if (c->cp[6] > 0) LAUNCH(c, k_types, cdiv(c->cp[6], 256), 256, 0, c->atype, c->cp[6], c->itype, c->gid);
   phase_mark(c, 3 | PH_QEQ);    // LINKEDLIST
   RXG_TRY(bin_grid(c, c->gnb));
-  phase_mark(c, 16 | PH_QEQ);   // qeq_initialize
-  if (c->lists_shared) RXG_TRY((build_pairlist<2>(c, !pq)));
-  else RXG_TRY((build_pairlist<1>(c, !pq)));
-  RXG_CUDA(cudaMemsetAsync(c->d_acc, 0, sizeof(double) * 24, c->st));
   const int nt = c->cp[6];
   const int rgrid = cdiv((long long)nt * 32, 256);
-  if (pq && nt > 0) {   // qeq_initialize of src/pqeq.F90:262-365 on the compacted rows
-    RXG_CUDA(cudaMemsetAsync(c->pcs, 0, sizeof(double) * (size_t)nt, c->st));
-    RXG_CUDA(cudaMemsetAsync(c->d_flag + 6, 0, sizeof(int), c->st));
-    LAUNCH(c, k_pack_sps, cdiv(nt, 256), 256, 0, nt, c->spos, c->NB, c->itype, c->gnb.slot_of, c->d_ff, c->sps);
-    LAUNCH(c, k_pqeq_rows, rgrid, 256, 0, c->gnb, nt, n, c->rowbeg, c->rowend, c->col, c->val, c->sps, c->d_ff, c->prow, c->pcs, c->d_acc, c->d_flag + 6);
-  }
   int it = 0;
-  phase_mark(c, 18 | PH_QEQ);   // the CG: get_hsh (+ get_gradient, which the single-pass CG folds into the same sparse product)
-  if (c->strict || (!pq && c->qeq_mode == 1)) RXG_TRY(qeq_cg_literal(c, nmax, &it));
-  else RXG_TRY(qeq_cg_single(c, nmax, &it));
+  for (int attempt = 0; attempt < 2; attempt++) {
+    phase_mark(c, 16 | PH_QEQ);   // qeq_initialize
+    // first attempt: rows laid out from last step's counts, no count pass (build_pairlist `capped`); if a row outgrew its
+    // capacity the solve that was started on the truncated list is thrown away and everything from here runs again with counts
+    const bool allow_capped = may_cap && attempt == 0;
+    if (c->lists_shared) RXG_TRY((build_pairlist<2>(c, !pq, allow_capped)));
+    else RXG_TRY((build_pairlist<1>(c, !pq, allow_capped)));
+    RXG_CUDA(cudaMemsetAsync(c->d_acc, 0, sizeof(double) * 24, c->st));
+    if (pq && nt > 0) {   // qeq_initialize of src/pqeq.F90:262-365 on the compacted rows
+      RXG_CUDA(cudaMemsetAsync(c->pcs, 0, sizeof(double) * (size_t)nt, c->st));
+      RXG_CUDA(cudaMemsetAsync(c->d_flag + 6, 0, sizeof(int), c->st));
+      LAUNCH(c, k_pack_sps, cdiv(nt, 256), 256, 0, nt, c->spos, c->NB, c->itype, c->gnb.slot_of, c->d_ff, c->sps);
+      LAUNCH(c, k_pqeq_rows, rgrid, 256, 0, c->gnb, nt, n, c->rowbeg, c->rowend, c->col, c->val, c->sps, c->d_ff, c->prow, c->pcs, c->d_acc, c->d_flag + 6);
+    }
+    phase_mark(c, 18 | PH_QEQ);   // the CG: get_hsh (+ get_gradient, which the single-pass CG folds into the same sparse product)
+    int rc;
+    if (c->strict || (!pq && c->qeq_mode == 1)) rc = qeq_cg_literal(c, nmax, &it);
+    else rc = qeq_cg_single(c, nmax, &it);
+    if (rc == RXG_OK && c->list_capped) {   // no CG batch synchronised (NMAXQEq = 0): look at the list's flags now
+      RXG_TRY(copy_capped_flags(c));
+      RXG_CUDA(cudaStreamSynchronize(c->st));
+      rc = check_capped_flags(c);
+    }
+    if (rc == RXG_RETRY && attempt == 0) {
+      RXG_CUDA(cudaMemcpyAsync(c->q, c->q_save, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->st));
+      if (n > 0) LAUNCH(c, k_qeq_init, cdiv(n, 256), 256, 0, n, n, c->q, c->qst, c->hsq, c->qsfp, c->qsfv, isQEq, c->cfg.Lex_fqs);
+      c->caps_valid = false;
+      continue;
+    }
+    RXG_TRY(rc);
+    break;
+  }
   phase_mark(c, 0);
   c->ph_sec[24] += it;   // it_timer(24): QEq iterations (src/qeq.F90:172)
   if (pq && nt > 0) {   // update_shell_positions, src/pqeq.F90:171,187-259, with the final charges of residents and ghosts
@@ -405,6 +459,7 @@ int qeq_device(Ctx *c, bool for_force = false) {
   c->timers_ms[15] = n;
   c->timers_ms[16] = c->cp[6];
   c->timers_ms[17] += it;
+  c->timers_ms[24] = (double)c->caps_overflows;
   return RXG_OK;
 }
 
@@ -450,6 +505,8 @@ int rxg_create(const rxg_config *cfg, rxg_handle *out) {
   c->fuse_api = fa && fa[0] == '1';
   const char *ov = getenv("RXG_OVERLAP");   // opt-in: measured slower at 2 GPUs
   c->overlap_env = ov && ov[0] == '1';
+  const char *hf = getenv("RXG_HESS_FUSE");
+  c->hess_fuse = hf && hf[0] == '1';
   const char *eo = getenv("RXG_EVAL_OCC");
   c->eval_occ = !(eo && eo[0] == '0');   // default on: measured 15.7 -> 14.6 ms per FORCE at 979 776 RDX atoms
   const char *sk = getenv("RXG_SPMV");
@@ -508,6 +565,19 @@ int rxg_create(const rxg_config *cfg, rxg_handle *out) {
   RXG_TRY(dalloc(c, &c->rowoff, NB + 2)); RXG_TRY(dalloc(c, &c->rowbeg, NB + 2)); RXG_TRY(dalloc(c, &c->rowend, NB + 2));
   RXG_TRY(dalloc(c, &c->rowcnt, NB + 2)); RXG_TRY(dalloc(c, &c->ucnt, NB + 2)); RXG_TRY(dalloc(c, &c->uoff, NB + 2));
   RXG_TRY(dalloc(c, &c->items, NB + 2));
+  {   // row counts by global atom id, for list builds without a count pass (RXG_NOCOUNT=0 keeps the count pass)
+    const char *nc = getenv("RXG_NOCOUNT");
+    c->caps_on = !(nc && nc[0] == '0');
+    const char *sl = getenv("RXG_CAP_SLACK");
+    if (sl) c->caps_slack = std::max(0, atoi(sl));
+    if (c->caps_on) {
+      size_t m = 1;
+      while (m < 2 * NB) m <<= 1;
+      c->cnt_mask = (unsigned)(m - 1);
+      RXG_TRY(dalloc(c, &c->cnt_tab, m));
+      RXG_TRY(dalloc(c, &c->q_save, NB));
+    }
+  }
   RXG_TRY(dalloc(c, &c->grp_cls, NB / 2 + 2)); RXG_TRY(dalloc(c, &c->grp_off, NB / 2 + 2));
   RXG_TRY(dalloc(c, &c->grp_int, NB / 2 + 2)); RXG_TRY(dalloc(c, &c->grp_bnd, NB / 2 + 2));
   RXG_TRY(ensure_bond_capacity(c, 8 * (long long)NB));

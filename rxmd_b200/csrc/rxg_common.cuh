@@ -168,6 +168,14 @@ struct Ctx {
   int arseq = 0;                     // all-reduce sequence number
   bool peer_all = false;             // every rank's window is open here: CG scalars are reduced through the windows
   int *d_pushcnt = nullptr;          // [2] block-completion counters of the push kernels
+  // list build without a count pass: last step's row counts by global atom id (direct-mapped table), see k_row_caps
+  int2 *cnt_tab = nullptr;
+  unsigned cnt_mask = 0;
+  bool caps_on = true, caps_valid = false, list_capped = false;
+  int caps_slack = 4;
+  long long caps_overflows = 0;
+  double *q_save = nullptr;   // [NB] charges at QEq entry, restored if a capped list overflows and the call starts over
+  bool hess_fuse = false;   // RXG_HESS_FUSE=1: experiment, the hessian lerp inside the list's fill pass instead of k_hessian
   bool eval_occ = true;     // RXG_EVAL_OCC=0 switches back to the angle / torsion / H-bond evaluators compiled without a register cap
   // interior / boundary split of the SpMV (multi-rank): the ghost refresh runs on st2 beside the interior rows
   cudaStream_t st2 = nullptr;

@@ -104,7 +104,13 @@ struct __align__(16) SpItem {
 };
 static_assert(sizeof(SpItem) == 64, "SpItem is one 64-byte record");
 // MODE 0: FORCE list, 1: QEq list, 2: both at once (FORCE predicate; hessian = 0 where only the QEq predicate fails)
-template <int MODE, bool FILL, bool UNION>
+// CAPPED (fill only): there was no count pass; rows were laid out with capacities taken from the previous step's counts
+// (k_row_caps), so every write is guarded by its row's capacity, an overflow raises ovf[20], and this pass also produces what
+// the count pass would have (entry total, longest row).  Every fill of a QEq list records the rows' counts by global atom id
+// (cnt_tab) for the next step.
+struct CntTab { int2 *tab; unsigned mask; const int *gid; };
+__device__ __forceinline__ unsigned cnt_hash(int gid, unsigned mask) { return ((unsigned)gid * 2654435761u) & mask; }
+template <int MODE, bool FILL, bool UNION, bool HFUSE = false, bool CAPPED = false>
 __global__ void __launch_bounds__(PL_WARPS * 32) k_pairlist(DevGrid g, const DevFF *__restrict__ ffp, const int *__restrict__ runs,
                                                             int nruns, int natoms, int ncell_res, int *__restrict__ slotcnt,
                                                             const long long *__restrict__ rowoff, long long *__restrict__ rowbeg,
@@ -113,7 +119,7 @@ __global__ void __launch_bounds__(PL_WARPS * 32) k_pairlist(DevGrid g, const Dev
                                                             unsigned long long *__restrict__ nnz_real, int ralign,
                                                             int *__restrict__ ucnt, const long long *__restrict__ uoff,
                                                             int *__restrict__ ucol, unsigned char *__restrict__ umask,
-                                                            SpItem *__restrict__ items, int *__restrict__ nitems, int rg) {
+                                                            SpItem *__restrict__ items, int *__restrict__ nitems, int rg, CntTab ct) {
   __shared__ int sh_s[PL_WARPS][PL_MAXRUNS];       // first slot of each stencil run
   __shared__ int sh_p[PL_WARPS][PL_MAXRUNS + 1];   // exclusive prefix of the run lengths: position of each run in the flat candidate sequence
   __shared__ double4 sh_a[PL_WARPS][32];
@@ -136,6 +142,7 @@ __global__ void __launch_bounds__(PL_WARPS * 32) k_pairlist(DevGrid g, const Dev
     sh_a[wid][lane] = me;
     const bool mine = mi < natoms;           // a ghost inside a resident cell owns no row (cannot happen after MOVE)
     long long mybase = (FILL && lane < nb) ? rowoff[myslot] : 0;
+    const int mycap = (CAPPED && lane < nb) ? (int)(rowoff[myslot + 1] - mybase) : 0;   // this row's capacity (k_row_caps)
     int mycnt = 0;
     // union stream of the CG SpMV (k_spmv_cells): per block of up to 8 consecutive rows of this cell, the candidates accepted
     // by at least one of them, in candidate order, with the 8-bit set of accepting rows.  ub* = running entry count of the
@@ -202,15 +209,27 @@ __global__ void __launch_bounds__(PL_WARPS * 32) k_pairlist(DevGrid g, const Dev
           const unsigned mask = __ballot_sync(0xffffffffu, acc);
           if (FILL) {
             const long long wb = __shfl_sync(0xffffffffu, mybase + mycnt, a);
-            if (acc) {
-              const long long w = wb + __popc(mask & ((1u << lane) - 1u));
+            const long long wend = CAPPED ? __shfl_sync(0xffffffffu, mybase + mycap, a) : 0;
+            const long long w = wb + __popc(mask & ((1u << lane) - 1u));
+            if (acc && (!CAPPED || w < wend)) {
               col[w] = cval;
               if (MODE >= 1) {
                 // the hessian lerp is evaluated by k_hessian over the compacted rows (full lanes); here only the
                 // fp32-rounded r^2 and the bond type are parked in the 8 bytes of the value slot
                 int inxn = ff.inxn2[(rec_type(at.w) - 1) + ff.nso * (jt - 1)];
                 if (!(MODE == 1 || (float)dr2 < rctap2f)) inxn = 0;
-                val[w] = __hiloint2double(inxn, __float_as_int((float)dr2));
+                if (HFUSE) {   // experiment (RXG_HESS_FUSE=1): the lerp of k_hessian evaluated here, by the accepted lanes only
+                  const double d2 = (double)(float)dr2;
+                  const int itb = (int)mul_rn(d2, ff.UDRi);
+                  const double drtb = mul_rn(sub_rn(d2, mul_rn((double)itb, ff.UDR)), ff.UDRi);
+                  double h = 0.0;
+                  if (inxn > 0 && itb >= 1 && itb < ff.ntable) {
+                    const double2 T = ff.TBL_qeq2[(size_t)(inxn - 1) * ff.ntable + (itb - 1)];
+                    h = add_rn(mul_rn(sub_rn(1.0, drtb), T.x), mul_rn(drtb, T.y));
+                  }
+                  val[w] = h;
+                } else
+                  val[w] = __hiloint2double(inxn, __float_as_int((float)dr2));
               }
             }
           }
@@ -287,8 +306,8 @@ __global__ void __launch_bounds__(PL_WARPS * 32) k_pairlist(DevGrid g, const Dev
         }
       }
     }
-    if (!FILL) {   // exact entry count (without row padding): the algorithmic-bytes figure of the roofline uses it;
-                   // longest row: picks the SpMV launch shape
+    if (!FILL || CAPPED) {   // exact entry count (without row padding): the algorithmic-bytes figure of the roofline uses it;
+                             // longest row: picks the SpMV launch shape
       const int real = __reduce_add_sync(0xffffffffu, (lane < nb && mine) ? mycnt : 0);
       const int longest = __reduce_max_sync(0xffffffffu, (lane < nb && mine) ? mycnt : 0);
       if (lane == 0 && real) { atomicAdd(nnz_real, (unsigned long long)real); atomicMax(ovf + 16, longest); }
@@ -298,14 +317,24 @@ __global__ void __launch_bounds__(PL_WARPS * 32) k_pairlist(DevGrid g, const Dev
         slotcnt[myslot] = (mycnt + ralign - 1) & ~(ralign - 1);
         if (mycnt > maxrow) atomicMax(ovf, mycnt);
       } else {
+        int kept = mycnt;
+        if (CAPPED) {
+          if (mycnt > maxrow) atomicMax(ovf, mycnt);               // the MAXNEIGHBS10 trap, checked by the host with the overflow flag
+          if (mycnt > mycap) { atomicExch(ovf + 20, 1); kept = mycap; }   // the row outgrew last step's count + slack: the host rebuilds
+        }
         rowbeg[mi] = mybase;
-        rowend[mi] = mybase + mycnt;
+        rowend[mi] = mybase + kept;
         // row padding: hessian 0, column = the row's last real column (written by some lane of this warp before the
-        // __syncwarp above), so that the padding does not stretch the 16-bit offsets of its block (k_col16)
-        const int padcol = mycnt > 0 ? __ldcg(col + mybase + mycnt - 1) : myslot;
-        for (int p = mycnt; p < ((mycnt + ralign - 1) & ~(ralign - 1)); p++) {
+        // __syncwarp above).  CAPPED: the whole unused capacity is padding (k_hessian runs flat over all entries).
+        const int padcol = kept > 0 ? __ldcg(col + mybase + kept - 1) : myslot;
+        const int pend = CAPPED ? mycap : ((mycnt + ralign - 1) & ~(ralign - 1));
+        for (int p = kept; p < pend; p++) {
           col[mybase + p] = padcol;
           if (MODE >= 1) val[mybase + p] = 0.0;
+        }
+        if (MODE >= 1 && ct.tab) {   // this step's count, by global id, is next step's capacity
+          const int gi = ct.gid[mi];
+          ct.tab[cnt_hash(gi, ct.mask)] = make_int2(gi, mycnt);
         }
       }
     }
@@ -333,6 +362,26 @@ __global__ void __launch_bounds__(256) k_hessian(long long nnz, const DevFF *__r
     }
     val[k] = h;
   }
+}
+
+// Row capacities without a count pass: last step's count of the same atom (looked up by global id) plus a slack, rounded to
+// the row alignment; atoms the table does not know (new on this rank, or a hash collision) get the default capacity.
+__global__ void k_row_caps(DevGrid g, int ntot, int natoms, CntTab ct, int slack, int defcap, int ralign, int *__restrict__ slotcnt) {
+  const int s = blockIdx.x * blockDim.x + threadIdx.x;
+  if (s >= ntot) return;
+  const int i = g.order[s];
+  int cap = 0;
+  if (i < natoms) {
+    const int cid = g.cell_of[i];
+    const int c3 = cid % g.dim[2] - g.L, c2 = (cid / g.dim[2]) % g.dim[1] - g.L, c1 = cid / (g.dim[2] * g.dim[1]) - g.L;
+    if (c1 >= 0 && c1 < g.nc[0] && c2 >= 0 && c2 < g.nc[1] && c3 >= 0 && c3 < g.nc[2]) {   // rows exist in resident cells only
+      const int gi = ct.gid[i];
+      const int2 e = ct.tab[cnt_hash(gi, ct.mask)];
+      cap = e.x == gi ? e.y + slack : defcap;
+      cap = (cap + ralign - 1) & ~(ralign - 1);
+    }
+  }
+  slotcnt[s] = cap;
 }
 
 int ensure_bond_capacity(Ctx *c, long long need);   // rxg_api.cu
@@ -365,7 +414,7 @@ inline int build_nbrlist(Ctx *c) {
 
 // `hessian`: run k_hessian over the parked (r^2, type) pairs (QEq); PQEq fills `val` itself (k_pqeq_rows)
 template <int MODE>
-int build_pairlist(Ctx *c, bool hessian = true) {
+int build_pairlist(Ctx *c, bool hessian = true, bool allow_capped = false) {
   const int n = c->natoms, nt = c->cp[6];
   RXG_CUDA(cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->st));
   RXG_CUDA(cudaMemsetAsync(c->d_flag + 16, 0, sizeof(int), c->st));
@@ -378,10 +427,18 @@ int build_pairlist(Ctx *c, bool hessian = true) {
   const int ncell_res = c->gnb.nc[0] * c->gnb.nc[1] * c->gnb.nc[2];
   const int grid = cdiv((long long)ncell_res * 32, PL_WARPS * 32);
   const int ralign = 4;
+  CntTab ct;
+  ct.tab = MODE >= 1 ? c->cnt_tab : nullptr; ct.mask = c->cnt_mask; ct.gid = c->gid;
+  // no count pass when last step's counts are on record (QEq lists of the production path only)
+  const bool capped = MODE >= 1 && allow_capped && c->caps_on && c->caps_valid && !c->strict && !un_on && c->cnt_tab;
+  c->list_capped = capped;
+  if (capped) c->timers_ms[23] += 1;   // list builds without a count pass
+  RXG_CUDA(cudaMemsetAsync(c->d_flag + 20, 0, sizeof(int), c->st));
 #define RXG_PL_ARGS c->gnb, c->d_ff, c->d_runs, c->nruns, n, ncell_res, c->rowcnt, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->cfg.maxneighbs10,   \
                     c->d_flag, (unsigned long long *)(c->d_acc + 33), ralign, c->ucnt, c->uoff, c->ucol, c->umask, c->items, c->d_flag + 17
-  if (un_on) LAUNCH(c, (k_pairlist<MODE, false, (MODE >= 1)>), grid, PL_WARPS * 32, 0, RXG_PL_ARGS, 4);
-  else LAUNCH(c, (k_pairlist<MODE, false, false>), grid, PL_WARPS * 32, 0, RXG_PL_ARGS, 4);
+  if (capped) LAUNCH(c, k_row_caps, cdiv(nt, 256), 256, 0, c->gnb, nt, n, ct, c->caps_slack, ((c->maxrow + 8 + ralign - 1) & ~(ralign - 1)), ralign, c->rowcnt);
+  else if (un_on) LAUNCH(c, (k_pairlist<MODE, false, (MODE >= 1)>), grid, PL_WARPS * 32, 0, RXG_PL_ARGS, 4, ct);
+  else LAUNCH(c, (k_pairlist<MODE, false, false>), grid, PL_WARPS * 32, 0, RXG_PL_ARGS, 4, ct);
   RXG_TRY(ensure_blk(c, nt));
   RXG_TRY(device_scan<long long>(c, c->rowcnt, nt, c->rowoff, c->d_blk64, (long long *)(c->d_acc + 32)));
   if (un_on) RXG_TRY(device_scan<long long>(c, c->ucnt, nt, c->uoff, c->d_blk64, (long long *)(c->d_acc + 34)));
@@ -389,7 +446,7 @@ int build_pairlist(Ctx *c, bool hessian = true) {
   RXG_CUDA(cudaMemcpyAsync(c->h_int + 16, c->d_flag + 16, sizeof(int), cudaMemcpyDeviceToHost, c->st));
   RXG_CUDA(cudaMemcpyAsync(c->h_acc + 32, c->d_acc + 32, 3 * sizeof(long long), cudaMemcpyDeviceToHost, c->st));
   RXG_CUDA(cudaStreamSynchronize(c->st));
-  if (c->h_int[0] > c->cfg.maxneighbs10) {
+  if (!capped && c->h_int[0] > c->cfg.maxneighbs10) {
     c->err = "ERROR: nbplist greater then MAXNEIGHBS10, value " + std::to_string(c->h_int[0]);
     return RXG_ERR_MAXNEIGHBS10;
   }
@@ -411,16 +468,22 @@ int build_pairlist(Ctx *c, bool hessian = true) {
   }
   c->nnz = nnz;
   c->nunion = nun;
-  c->maxrow = c->h_int[16];
-  c->nnz_real = *(long long *)(c->h_acc + 33);
+  if (!capped) {   // (capped: the fill pass produces them; list_stats_after_fill reads them at the CG's first synchronisation)
+    c->maxrow = c->h_int[16];
+    c->nnz_real = *(long long *)(c->h_acc + 33);
+  }
   c->list_is_qeq = MODE >= 1;
   // rows per SpMV work item: four while four of the longest rows fit a stage of k_spmv_items, else two (12.5 A lists of PQEq)
   c->spmv_rg = c->maxrow <= 480 ? 4 : 2;
   RXG_CUDA(cudaMemsetAsync(c->d_flag + 17, 0, sizeof(int), c->st));
-  if (un_on) LAUNCH(c, (k_pairlist<MODE, true, (MODE >= 1)>), grid, PL_WARPS * 32, 0, RXG_PL_ARGS, c->spmv_rg);
-  else LAUNCH(c, (k_pairlist<MODE, true, false>), grid, PL_WARPS * 32, 0, RXG_PL_ARGS, c->spmv_rg);
+  const bool hfuse = MODE >= 1 && hessian && c->hess_fuse && !un_on && !capped;
+  if (capped) LAUNCH(c, (k_pairlist<MODE, true, false, false, (MODE >= 1)>), grid, PL_WARPS * 32, 0, RXG_PL_ARGS, c->spmv_rg, ct);
+  else if (un_on) LAUNCH(c, (k_pairlist<MODE, true, (MODE >= 1)>), grid, PL_WARPS * 32, 0, RXG_PL_ARGS, c->spmv_rg, ct);
+  else if (hfuse) LAUNCH(c, (k_pairlist<MODE, true, false, (MODE >= 1)>), grid, PL_WARPS * 32, 0, RXG_PL_ARGS, c->spmv_rg, ct);
+  else LAUNCH(c, (k_pairlist<MODE, true, false>), grid, PL_WARPS * 32, 0, RXG_PL_ARGS, c->spmv_rg, ct);
 #undef RXG_PL_ARGS
-  if (MODE >= 1 && hessian)
+  if (MODE >= 1 && c->cnt_tab) c->caps_valid = true;
+  if (MODE >= 1 && hessian && !hfuse)
     LAUNCH(c, k_hessian, 148 * 16, 256, 0, nnz, c->d_ff, c->val);
   c->nitems = un_on ? -1 : 0;   // read back with the CG's first synchronisation (spmv_launch)
   return RXG_OK;
@@ -1004,6 +1067,7 @@ __global__ void k_cg_update2(int natoms, const double2 *__restrict__ qst, const 
   hst[i] = h;
   xs[slot_of[i]] = h;
 }
+__global__ void k_flag_to_acc(const int *__restrict__ flag, double *__restrict__ acc) { *acc = *flag ? 1.0 : 0.0; }
 // hs = gs, ht = gt (src/qeq.F90:90-91); also arms the CG's control block (GEst2 = 1e99, :94)
 __global__ void k_h_from_g2(int natoms, const double2 *__restrict__ gst, double2 *__restrict__ hst, double2 *__restrict__ xs,
                             const int *__restrict__ slot_of, double *__restrict__ acc) {

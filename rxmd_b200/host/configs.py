@@ -31,10 +31,7 @@ def build_config(name, mc=None, nranks=1, strong=False, sigma=0.02, only_rank=No
     vp = VPROCS[nranks]
     mc = tuple(mc) if mc is not None else c["mc"]
     if strong:
-        for a in range(3):
-            if mc[a] % vp[a]:
-                raise ValueError(f"--strong: replication {mc} is not divisible by vprocs {vp}")
-        tot = mc
+        tot = mc          # atoms go to ranks by position (init/geninit.F90:495-500): the replication need not divide by vprocs
     else:
         tot = tuple(mc[a] * vp[a] for a in range(3))
     d = os.path.join(INPUTS, c["d"])

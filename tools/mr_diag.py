@@ -121,9 +121,9 @@ def _compare_body(rank, world, local, mc, sigma, pqeq, holder):
            "peer_allreduce": bool(e.peer_allreduce()),
            "migration": bool(e.natoms_resident() == o.natoms(rank) and int(tot[2].item()) == s.natoms),
            "md_pe_rel": float(abs(tot[0].item() - pe_oa[0]) / abs(pe_oa[0]))}
-    # charges: the production CG's bars (tests/test_gpu_parity.py: 3e-7 when both sides stop in the same iteration, 1e-4 otherwise)
+    # charges: the production CG's bars (tests/test_gpu_parity.py: 1e-6 when both sides stop in the same iteration, 1e-4 otherwise)
     res["ok"] = bool(res["copyptr_qeq"] and res["copyptr_force"] and res["rows"] and res["f_rel"] < 1e-9 and res["pe_ok"] and
-                     res["migration"] and res["md_pe_rel"] < 1e-6 and res["dq"] <= (3e-7 if nstep_same else 1e-4))
+                     res["migration"] and res["md_pe_rel"] < 1e-6 and res["dq"] <= (1e-6 if nstep_same else 1e-4))
     return res, out
 
 
