@@ -276,12 +276,17 @@ def main():
         bytes_alg = 12.0 * nnz + 4.0 * (nloc + 1) + 8.0 * 2 * ntot + 40.0 * nloc      # SURVEY 8(d), two gathered vectors (hs, ht)
         ach = bytes_alg / (d[10] / d[11] * 1e-3) / 1e9
         rows = os.environ.get("RXG_SPMV") != "items"
-        roofline = {"kernel": ("k_spmv_rows (QEq CG SpMV H.(hs,ht): TMA-staged CSR stream, sub-warp per row)" if rows else
+        win = (t_after[25] - t_before[25]) > 0 and (t_after[26] - t_before[26]) == 0
+        roofline = {"kernel": ("k_spmv_win (QEq CG SpMV H.(hs,ht): x window of a cell group TMA-staged in shared memory, fp64 values + "
+                               "16-bit window-relative columns streamed once, warp per row)" if win else
+                               "k_spmv_rows (QEq CG SpMV H.(hs,ht): TMA-staged CSR stream, sub-warp per row)" if rows else
                                "k_spmv_items (QEq CG SpMV H.(hs,ht): cell-blocked union column stream + compacted fp64 values, "
                                "TMA ring, warp per row block)"),
                     "bound": "hbm", "achieved": ach, "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic,
                     "peak_source": peak_src, "algorithmic_bytes_per_launch": bytes_alg,
-                    "stream_bytes_per_launch": (12.0 * t_after[18] if rows else 8.0 * t_after[18] + 5.0 * nun) + 16.0 * ntot + 32.0 * nloc,
+                    "stream_bytes_per_launch": ((10.0 * t_after[18] + 12.0 * nloc) if win else 12.0 * t_after[18] if rows else
+                                                8.0 * t_after[18] + 5.0 * nun) + 16.0 * ntot + 32.0 * nloc,
+                    "cells_per_group": int(t_after[27]) if win else None, "largest_window_entries": int(t_after[28]) if win else None,
                     "avg_launch_ms": d[10] / d[11], "launches_timed": int(d[11]),
                     "step_share": d[10] / max(t_after[3] - t_before[3], 1e-9)}
 
@@ -374,6 +379,7 @@ def main():
                                             ("ncclAllReduce" if world > 1 else "none (1 rank)")),
                            "l2_policy": "inputs larger than L2 (QEq matrix ~4 GB per SpMV pass, >> 126 MB)",
                            "cg_iterations_per_step": cg_iters, "nnz": nnz, "union_entries": nun,
+                           "list_builds_without_count_pass": int(d[23]), "of_those_rebuilt_after_row_overflow": int(d[24]),
                            "pe_per_atom_global": pe_global / max(natoms_total, 1), "ke_per_atom_global": ke_global / max(natoms_total, 1),
                            "sum_q_global": q_global, "setup_seconds_per_rank": t_setup},
                 "phase_ms_per_step": {"QEq": d[4] / args.steps, "FORCE": d[5] / args.steps, "MOVE": d[6] / args.steps},

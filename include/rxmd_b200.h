@@ -179,7 +179,9 @@ int rxg_fetch_bonds(rxg_handle h, int *nbrlist, double *BO0);
  * [20] bytes copied host->device by the entry points so far  [21] bytes copied device->host
  * [22] rxg_force calls that reused the halo and 10 A list of the preceding rxg_qeq (RXG_FUSE_API=1)
  * [23] 10 A list builds without a count pass (rows laid out from the previous step's counts)  [24] of those, how many
- *      overflowed a row and were rebuilt with the count pass */
+ *      overflowed a row and were rebuilt with the count pass
+ * [25] sparse products taken by k_spmv_win  [26] by k_spmv_rows  [27] cells per group of the current list's window-relative
+ *      column stream  [28] entries of its largest window */
 int rxg_timers(rxg_handle h, double *it_timer_ms);
 /* the reference's it_timer(1:30) itself (src/module.F90:215-217; table printed at src/main.F90:144-180), in SECONDS
  * (the reference keeps system_clock ticks and divides by the clock rate when printing), measured with CUDA events at the

@@ -197,11 +197,66 @@ int spmv_items_launch(Ctx *c, int slot) {
          c->spmv_stage);
   return RXG_OK;
 }
+// ---- window SpMV (k_spmv_win, the default): group size and shared-memory budget --------------------------------------------
+// Cells per group: the largest G whose expected window (stencil runs lengthened by G-1 cells, at the average number of atoms
+// per cell, +10 %) fits the per-CTA budget (RXG_WIN_SMEM, default 64 KB: three CTAs per SM).  The list build reports the
+// largest window it saw (win_max); if that exceeds what a CTA can hold, the next build halves G, and a list whose windows do
+// not fit at all is multiplied by k_spmv_rows.
+template <int NW, int U, int MINB>
+int spmv_win_launch(Ctx *c, int slot, bool *took) {
+  auto kern = k_spmv_win<NW, U, MINB>;
+  int optin = 0;
+  RXG_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->dev));
+  const int limit = optin - 4096;   // static shared memory of the kernel + slack
+  int wcap = ((c->win_max + c->win_max / 64 + 16) + 7) & ~7;
+  if (wcap > 32768) wcap = 32768;
+  if (c->win_wcap_env > 0) wcap = std::min(wcap, c->win_wcap_env);   // (tests: forces the per-CTA fallback to global gathers)
+  *took = false;
+  if (c->win_max > 32768 || c->win_max * 16 > limit) {   // no group of this list fits: shrink the groups of the next build
+    if (c->win_g_env <= 0 && c->win_g > 1) c->win_g = std::max(1, c->win_g / 2);
+    return RXG_OK;
+  }
+  if (wcap * 16 > limit) wcap = (limit / 16) & ~7;
+  const int smem = wcap * 16;
+  if (smem > c->win_smem_set[slot]) {
+    RXG_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, limit));
+    c->win_smem_set[slot] = limit;
+  }
+  const DevGrid &g = c->gnb;
+  const int G = c->win_g_built;
+  const int grid = g.nc[0] * g.nc[1] * cdiv(g.nc[2], G);
+  LAUNCH(c, kern, grid, NW * 32, smem, g, c->nruns, G, c->stencil_reach, c->win_desc, c->rowoff, c->rowlen, c->col, c->col16, c->val, c->xs, (double4 *)c->tmp, c->d_acc, wcap);
+  // windows much larger than the budget: fewer cells per group from the next build on
+  if (c->win_g_env <= 0 && c->win_g > 1) {
+    if (c->win_max * 16 > 2 * c->win_smem_target) c->win_g = std::max(1, c->win_g / 2);
+    else if (c->win_max * 16 > c->win_smem_target + c->win_smem_target / 8) c->win_g = std::max(1, c->win_g - std::max(1, c->win_g / 6));
+  }
+  *took = true;
+  c->win_launches++;
+  return RXG_OK;
+}
 // part: 0 = all rows, 1 = interior row groups only, 2 = boundary row groups only (c->overlap; see k_group_class)
 int spmv_launch(Ctx *c, int part = 0) {
   const int n = c->natoms, nt = c->cp[6];
   double4 *rowsum = (double4 *)c->tmp;
   if (nt <= 0) return RXG_OK;
+  if (c->spmv_kind == 2 && c->win_built && part == 0 && c->nruns <= 4096) {
+    bool took = false;
+    // entries a lane keeps in flight per batch, from the average row length: a whole 10 A row (~400 entries) in one batch of
+    // 32 x 13, short rows (sparse systems: ~120 entries) in one batch of 32 x 4
+    int u = c->win_u;
+    if (u == 0) {
+      const double avgrow = (double)c->nnz_real / (double)std::max(n, 1);
+      u = avgrow <= 140.0 ? 4 : (avgrow <= 270.0 ? 8 : 13);
+    }
+    if (c->win_nw == 4 && u == 13) RXG_TRY((spmv_win_launch<4, 13, 6>(c, 0, &took)));
+    else if (c->win_nw == 4) RXG_TRY((spmv_win_launch<4, 8, 8>(c, 1, &took)));
+    else if (u == 4) RXG_TRY((spmv_win_launch<8, 4, 6>(c, 2, &took)));
+    else if (u == 13) RXG_TRY((spmv_win_launch<8, 13, 3>(c, 4, &took)));
+    else RXG_TRY((spmv_win_launch<8, 8, 4>(c, 3, &took)));
+    if (took) return RXG_OK;
+  }
+  c->rows_launches++;
   if (c->spmv_kind == 0) {
     if (c->nitems < 0) {   // first product after a list build: the item count left by the fill pass
       RXG_CUDA(cudaMemcpyAsync(c->h_int + 17, c->d_flag + 17, sizeof(int), cudaMemcpyDeviceToHost, c->st));
@@ -238,7 +293,7 @@ int spmv_launch(Ctx *c, int part = 0) {
 // classify the row groups of the launch shape in use (once per list build) -- only when the refresh has somewhere to go
 int build_row_groups(Ctx *c) {
   c->overlap = false;
-  if (!c->overlap_env || !c->comm || !c->peer_ok || c->halo_self || c->spmv_kind != 1 || c->cp[6] <= 0) return RXG_OK;
+  if (!c->overlap_env || !c->comm || !c->peer_ok || c->halo_self || c->spmv_kind != 1 || c->cp[6] <= 0) return RXG_OK;   // (k_spmv_rows only)
   const int n = c->natoms, nt = c->cp[6];
   const double avgrow = (double)c->nnz_real / (double)std::max(n, 1);
   int shape = c->spmv_shape;
@@ -287,6 +342,7 @@ int copy_capped_flags(Ctx *c) {
   RXG_CUDA(cudaMemcpyAsync(c->h_int + 20, c->d_flag + 20, sizeof(int), cudaMemcpyDeviceToHost, c->st));
   RXG_CUDA(cudaMemcpyAsync(c->h_int, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->st));
   RXG_CUDA(cudaMemcpyAsync(c->h_int + 16, c->d_flag + 16, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+  RXG_CUDA(cudaMemcpyAsync(c->h_int + 21, c->d_flag + 21, sizeof(int), cudaMemcpyDeviceToHost, c->st));
   RXG_CUDA(cudaMemcpyAsync(c->h_acc + 33, c->d_acc + 33, sizeof(long long), cudaMemcpyDeviceToHost, c->st));
   if (c->comm) RXG_CUDA(cudaMemcpyAsync(c->h_acc + 26, c->d_acc + 26, sizeof(double), cudaMemcpyDeviceToHost, c->st));
   return RXG_OK;
@@ -299,9 +355,18 @@ int check_capped_flags(Ctx *c) {
     return RXG_ERR_MAXNEIGHBS10;
   }
   // multi-rank: every rank must take the same decision -- the flags were summed over the ranks (qeq_cg_single)
-  if (c->comm ? c->h_acc[26] > 0.5 : c->h_int[20] != 0) { c->caps_overflows++; return RXG_RETRY; }
+  if (c->comm ? c->h_acc[26] > 0.5 : c->h_int[20] != 0) {
+    // a retry costs a list build and a CG batch, a count pass 2 ms: after an overflow the next builds count again, for twice
+    // as many steps each time it happens (8, 16, ... 4096), so a system whose rows keep outgrowing their slack cannot lose
+    // more than a few per cent to retries
+    c->caps_overflows++;
+    c->caps_skip = c->caps_cooldown ? (8 << std::min(c->caps_fails, 9)) : 0;
+    c->caps_fails++;
+    return RXG_RETRY;
+  }
   c->maxrow = c->h_int[16];
   c->nnz_real = *(long long *)(c->h_acc + 33);
+  if (c->win_built) c->win_max = c->h_int[21];   // the largest window of this list: sizes the next launches
   return RXG_OK;
 }
 
@@ -383,7 +448,8 @@ int qeq_device(Ctx *c, bool for_force = false) {
   const int n = c->natoms;
   const int nmax = (isQEq == 1) ? c->cfg.NMAXQEq : 1;
   int nprev = c->cp[6] > n ? c->cp[6] : n;
-  const bool may_cap = c->caps_on && c->caps_valid && !c->strict && c->spmv_kind == 1 && c->qeq_mode == 0;
+  if (c->caps_skip > 0) c->caps_skip--;
+  const bool may_cap = c->caps_on && c->caps_valid && c->caps_skip == 0 && !c->strict && c->spmv_kind >= 1 && c->qeq_mode == 0;
   if (may_cap && n > 0) RXG_CUDA(cudaMemcpyAsync(c->q_save, c->q, sizeof(double) * n, cudaMemcpyDeviceToDevice, c->st));
   if (nprev > 0)
     LAUNCH(c, k_qeq_init, cdiv(nprev, 256), 256, 0, n, nprev, c->q, c->qst, c->hsq, c->qsfp, c->qsfv, isQEq, c->cfg.Lex_fqs);
@@ -468,6 +534,22 @@ int qeq_device(Ctx *c, bool for_force = false) {
 // compact bond storage: 2 int + 16 double planes of `bond_cap` slots, grown on demand (contents need not survive: every
 // FORCE rebuilds them)
 namespace rxg {
+int win_pick_group(Ctx *c) {
+  if (c->win_g_env > 0) return c->win_g_env;
+  const DevGrid &g = c->gnb;
+  // atoms per cell where there are atoms: residents over resident cells (the ghost layers of the grid are mostly empty)
+  const double per_cell = (double)std::max(c->natoms, 1) / (double)std::max(g.nc[0] * g.nc[1] * g.nc[2], 1);
+  const int nr = (int)(c->h_runs.size() / 4);
+  int best = 1;
+  for (int G = 1; G <= std::min(32, g.nc[2]); G++) {
+    long long cells = 0;
+    for (int r = 0; r < nr; r++) cells += c->h_runs[4 * r + 3] - c->h_runs[4 * r + 2] + G;
+    if (1.1 * per_cell * (double)cells * 16.0 <= (double)c->win_smem_target) best = G;
+  }
+  // even split of the z-column: the same number of groups, none of them a small remainder
+  const int ngz = cdiv(g.nc[2], best);
+  return cdiv(g.nc[2], ngz);
+}
 int ensure_bond_capacity(Ctx *c, long long need) {
   if (need <= c->bond_cap) return RXG_OK;
   const long long cap = need + need / 8 + 1024;
@@ -510,7 +592,21 @@ int rxg_create(const rxg_config *cfg, rxg_handle *out) {
   const char *eo = getenv("RXG_EVAL_OCC");
   c->eval_occ = !(eo && eo[0] == '0');   // default on: measured 15.7 -> 14.6 ms per FORCE at 979 776 RDX atoms
   const char *sk = getenv("RXG_SPMV");
-  c->spmv_kind = (sk && std::string(sk) == "items") ? 0 : 1;   // 1: k_spmv_rows (default), 0: k_spmv_items (experiment)
+  // 2: k_spmv_win (default), 1: k_spmv_rows (round 1's kernel; also what lists with oversize windows fall back to),
+  // 0: k_spmv_items (experiment)
+  c->spmv_kind = (sk && std::string(sk) == "items") ? 0 : ((sk && std::string(sk) == "rows") ? 1 : 2);
+  {
+    const char *wg = getenv("RXG_WIN_G"), *ww = getenv("RXG_WIN_WARPS"), *wsm = getenv("RXG_WIN_SMEM");
+    c->win_g_env = wg ? std::max(0, atoi(wg)) : 0;
+    c->win_nw = ww ? atoi(ww) : 8;
+    if (c->win_nw != 4) c->win_nw = 8;
+    const char *wu = getenv("RXG_WIN_U");
+    c->win_u = wu ? atoi(wu) : 0;   // 0: from the average row length (spmv_launch)
+    if (c->win_u != 4 && c->win_u != 8 && c->win_u != 13) c->win_u = 0;
+    c->win_smem_target = wsm ? std::max(4096, atoi(wsm)) : 64 * 1024;
+    const char *wc = getenv("RXG_WIN_WCAP");
+    c->win_wcap_env = wc ? atoi(wc) : 0;
+  }
   const char *ss = getenv("RXG_SPMV_SHAPE");
   c->spmv_shape = !ss ? 0 : (std::string(ss) == "8x8" ? 1 : (std::string(ss) == "4x16" ? 2 : (std::string(ss) == "2x32" ? 3 : 0)));
   const char *sg = getenv("RXG_SPMV_STAGE");
@@ -564,12 +660,15 @@ int rxg_create(const rxg_config *cfg, rxg_handle *out) {
   RXG_TRY(dalloc(c, &c->nbrcnt, NB)); RXG_TRY(dalloc(c, &c->nbrpad, NS)); RXG_TRY(dalloc(c, &c->bptr, NB + 2));
   RXG_TRY(dalloc(c, &c->rowoff, NB + 2)); RXG_TRY(dalloc(c, &c->rowbeg, NB + 2)); RXG_TRY(dalloc(c, &c->rowend, NB + 2));
   RXG_TRY(dalloc(c, &c->rowcnt, NB + 2)); RXG_TRY(dalloc(c, &c->ucnt, NB + 2)); RXG_TRY(dalloc(c, &c->uoff, NB + 2));
+  RXG_TRY(dalloc(c, &c->rowlen, NB + 2));
   RXG_TRY(dalloc(c, &c->items, NB + 2));
   {   // row counts by global atom id, for list builds without a count pass (RXG_NOCOUNT=0 keeps the count pass)
     const char *nc = getenv("RXG_NOCOUNT");
     c->caps_on = !(nc && nc[0] == '0');
     const char *sl = getenv("RXG_CAP_SLACK");
     if (sl) c->caps_slack = std::max(0, atoi(sl));
+    const char *cd = getenv("RXG_CAP_COOLDOWN");
+    c->caps_cooldown = !(cd && cd[0] == '0');
     if (c->caps_on) {
       size_t m = 1;
       while (m < 2 * NB) m <<= 1;
@@ -689,6 +788,7 @@ int rxg_set_box(rxg_handle h, const rxg_box *box) {
     else { runs.push_back(dx); runs.push_back(dy); runs.push_back(dz); runs.push_back(dz); }
   }
   c->nruns = (int)(runs.size() / 4);
+  c->h_runs = runs;
   c->stencil_reach = 0;   // cells the stencil reaches along any axis: rows of cells this far inside the domain take no ghost column
   for (int m = 0; m < box->nbnmesh; m++)
     for (int a = 0; a < 3; a++) c->stencil_reach = std::max(c->stencil_reach, std::abs(box->nbmesh[3 * m + a]));
@@ -811,7 +911,7 @@ int rxg_destroy(rxg_handle h) {
     }
     for (void *p : c->allocs) cudaFree(p);
     for (void *p : c->ff_allocs) cudaFree(p);
-    for (void *p : {(void *)c->col, (void *)c->val, (void *)c->ucol, (void *)c->umask, (void *)c->d_blk, (void *)c->d_blk64, (void *)c->d_runs, (void *)c->d_ff})
+    for (void *p : {(void *)c->col, (void *)c->val, (void *)c->col16, (void *)c->win_desc, (void *)c->ucol, (void *)c->umask, (void *)c->d_blk, (void *)c->d_blk64, (void *)c->d_runs, (void *)c->d_ff})
       if (p) cudaFree(p);
     for (int k = 0; k < 2; k++) { if (c->sbuf[k]) cudaFree(c->sbuf[k]); if (c->rbuf[k]) cudaFree(c->rbuf[k]); }
     for (size_t r = 0; r < c->peer.size(); r++)
@@ -1061,6 +1161,8 @@ int rxg_it_timer(rxg_handle h, double *it_timer_sec) {
 int rxg_timers(rxg_handle h, double *t) {
   Ctx *c = (Ctx *)h;
   if (!c || !t) return RXG_ERR_ARG;
+  c->timers_ms[25] = (double)c->win_launches; c->timers_ms[26] = (double)c->rows_launches;
+  c->timers_ms[27] = (double)c->win_g_built; c->timers_ms[28] = (double)c->win_max;
   for (int k = 0; k < 30; k++) t[k] = c->timers_ms[k];
   return RXG_OK;
 }

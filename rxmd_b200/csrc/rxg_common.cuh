@@ -172,7 +172,8 @@ struct Ctx {
   int2 *cnt_tab = nullptr;
   unsigned cnt_mask = 0;
   bool caps_on = true, caps_valid = false, list_capped = false;
-  int caps_slack = 4;
+  bool caps_cooldown = true;
+  int caps_slack = 4, caps_skip = 0, caps_fails = 0;   // caps_skip: list builds that keep the count pass after an overflow
   long long caps_overflows = 0;
   double *q_save = nullptr;   // [NB] charges at QEq entry, restored if a capped list overflows and the call starts over
   bool hess_fuse = false;   // RXG_HESS_FUSE=1: experiment, the hessian lerp inside the list's fill pass instead of k_hessian
@@ -217,6 +218,16 @@ struct Ctx {
   struct SpItem *items = nullptr;    // [NB] work items of k_spmv_items, written by the list's fill pass
   int nitems = 0, spmv_rg = 4;       // rows per item (4, or 2 for lists with rows longer than 480 entries)
   int spmv_kind = 0, spmv_shape = 0, spmv_stage = 1, spmv_ring = 0, spmv_ring_env = 0, spmv_grid[2] = {0, 0};   // RXG_SPMV / _SHAPE / _STAGE / _RING (rxg_api.cu)
+  // window SpMV (k_spmv_win, spmv_kind 2): 16-bit window-relative columns, exact row lengths by slot, group size in cells
+  unsigned short *col16 = nullptr;   // [nnz_cap]
+  int *rowlen = nullptr;             // [NB+2]
+  int2 *win_desc = nullptr;          // [groups][nruns + 1] window descriptors (k_win_desc)
+  size_t win_desc_cap = 0;
+  int win_g = 0, win_g_env = 0, win_wcap_env = 0, win_nw = 8, win_u = 0, win_max = 0, win_smem_target = 0, win_smem_set[6] = {0, 0, 0, 0, 0, 0};
+  bool win_built = false;            // the current list carries col16 / rowlen for group size win_g_built
+  int win_g_built = 0;
+  std::vector<int> h_runs;           // host copy of the stencil runs (group-size estimate)
+  long long win_launches = 0, rows_launches = 0;   // sparse products taken by k_spmv_win / by k_spmv_rows
   long long nnz_cap = 0, nnz = 0, nnz_real = 0;   // nnz counts the row padding, nnz_real does not
   bool list_is_qeq = false;
   int maxrow = 0;                // longest row of the current list (entries)

@@ -109,6 +109,58 @@ static_assert(sizeof(SpItem) == 64, "SpItem is one 64-byte record");
 // the count pass would have (entry total, longest row).  Every fill of a QEq list records the rows' counts by global atom id
 // (cnt_tab) for the next step.
 struct CntTab { int2 *tab; unsigned mask; const int *gid; };
+// Window-relative column stream of k_spmv_win (below).  A GROUP is up to G consecutive resident cells of one z-column of the
+// grid; its WINDOW is the concatenation, in stencil-run order, of the slot ranges that the runs of ANY cell of the group cover
+// (run r of the group = cells [g0 + z0_r, g0 + gl - 1 + z1_r] of column (c1 + dx_r, c2 + dy_r), clipped to the grid).  The fill
+// pass writes, next to the 32-bit slot column, the entry's position in its group's window (15 bits) with the ghost flag in bit
+// 15, and the exact length of every row by slot; `winmax` collects the largest window.
+struct WinOut { unsigned short *c16; int *rowlen; int *winmax; int G; };
+// bounds of stencil run `rr` for the cells [za, zb] of column (c1, c2): first slot and number of slots (0 if outside the grid)
+__device__ __forceinline__ void run_span(const DevGrid &g, int4 rr, int c1, int c2, int za, int zb, int &s, int &len) {
+  s = 0; len = 0;
+  const int b1 = c1 + rr.x, b2 = c2 + rr.y;
+  int z0 = za + rr.z, z1 = zb + rr.w;
+  if (b1 >= -g.L && b1 < g.nc[0] + g.L && b2 >= -g.L && b2 < g.nc[1] + g.L) {
+    if (z0 < -g.L) z0 = -g.L;
+    if (z1 >= g.nc[2] + g.L) z1 = g.nc[2] + g.L - 1;
+    if (z1 >= z0) {
+      const int cbase = ((b1 + g.L) * g.dim[1] + (b2 + g.L)) * g.dim[2] + g.L;
+      s = g.start[cbase + z0];
+      len = g.start[cbase + z1 + 1] - s;
+    }
+  }
+}
+// Window descriptors, written once per list build (k_win_desc): for group `grp` and stencil run r the pair
+//   { first slot of the run's span, (position in the window << 12) | number of slots },
+// and in entry [nruns] the window's total {0, total << 12}.  A span of more than 4095 slots marks the group as unfit (total = 2^19).
+__global__ void k_win_desc(DevGrid g, const int *__restrict__ runs, int nruns, int G, int ngroups, int2 *__restrict__ desc) {
+  const int lane = threadIdx.x & 31;
+  const int grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (grp >= ngroups) return;
+  const int ngz = (g.nc[2] + G - 1) / G;
+  const int gz = grp % ngz, c2 = (grp / ngz) % g.nc[1], c1 = grp / (ngz * g.nc[1]);
+  const int g0 = gz * G, g1 = min(g0 + G, g.nc[2]) - 1;
+  int2 *d = desc + (size_t)grp * (nruns + 1);
+  int wcarry = 0;
+  bool unfit = false;
+  for (int r0 = 0; r0 < nruns; r0 += 32) {
+    const int r = r0 + lane;
+    int ws = 0, wlen = 0;
+    if (r < nruns) run_span(g, *reinterpret_cast<const int4 *>(runs + 4 * r), c1, c2, g0, g1, ws, wlen);
+    int winc = wlen;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int y = __shfl_up_sync(0xffffffffu, winc, o);
+      if (lane >= o) winc += y;
+    }
+    const int pos = wcarry + winc - wlen;
+    unfit = unfit || __any_sync(0xffffffffu, wlen > 4095);
+    if (r < nruns) d[r] = make_int2(ws, (min(pos, 0x7ffff) << 12) | min(wlen, 4095));
+    wcarry += __shfl_sync(0xffffffffu, winc, 31);
+  }
+  if (lane == 0) d[nruns] = make_int2(0, ((unfit || wcarry > 0x7ffff) ? 0x7ffff : wcarry) << 12);
+}
+
 __device__ __forceinline__ unsigned cnt_hash(int gid, unsigned mask) { return ((unsigned)gid * 2654435761u) & mask; }
 template <int MODE, bool FILL, bool UNION, bool HFUSE = false, bool CAPPED = false>
 __global__ void __launch_bounds__(PL_WARPS * 32) k_pairlist(DevGrid g, const DevFF *__restrict__ ffp, const int *__restrict__ runs,
@@ -119,8 +171,9 @@ __global__ void __launch_bounds__(PL_WARPS * 32) k_pairlist(DevGrid g, const Dev
                                                             unsigned long long *__restrict__ nnz_real, int ralign,
                                                             int *__restrict__ ucnt, const long long *__restrict__ uoff,
                                                             int *__restrict__ ucol, unsigned char *__restrict__ umask,
-                                                            SpItem *__restrict__ items, int *__restrict__ nitems, int rg, CntTab ct) {
+                                                            SpItem *__restrict__ items, int *__restrict__ nitems, int rg, CntTab ct, WinOut wo) {
   __shared__ int sh_s[PL_WARPS][PL_MAXRUNS];       // first slot of each stencil run
+  __shared__ int sh_w[PL_WARPS][PL_MAXRUNS];       // (fill, wo.c16) window position of the run's first slot: add the candidate's slot
   __shared__ int sh_p[PL_WARPS][PL_MAXRUNS + 1];   // exclusive prefix of the run lengths: position of each run in the flat candidate sequence
   __shared__ double4 sh_a[PL_WARPS][32];
   const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -133,6 +186,8 @@ __global__ void __launch_bounds__(PL_WARPS * 32) k_pairlist(DevGrid g, const Dev
   const int a0 = g.start[cid], a1 = g.start[cid + 1];
   if (a1 == a0) return;
   const float rctap2f = (float)ff.rctap2;
+  const bool win = wo.c16 != nullptr;   // both passes lay the window out (the count pass reports its size), the fill pass writes
+  const int wg0 = win ? (c3 / wo.G) * wo.G : 0, wg1 = win ? min(wg0 + wo.G, g.nc[2]) - 1 : 0;   // this cell's group (k_spmv_win)
   for (int ab = a0; ab < a1; ab += 32) {
     const int nb = min(32, a1 - ab);
     const int myslot = ab + lane;
@@ -156,6 +211,7 @@ __global__ void __launch_bounds__(PL_WARPS * 32) k_pairlist(DevGrid g, const Dev
       if (nb > 24) uw3 = uoff[ab + 24];
     }
     int lastcol = ab;
+    int wcarry = 0;   // window position of the next run
     __syncwarp();
     for (int rb = 0; rb < nruns; rb += PL_MAXRUNS) {
       const int nr = min(PL_MAXRUNS, nruns - rb);
@@ -164,28 +220,26 @@ __global__ void __launch_bounds__(PL_WARPS * 32) k_pairlist(DevGrid g, const Dev
       int carry = 0;
       for (int r0 = 0; r0 < nr; r0 += 32) {
         const int r = r0 + lane;
-        int s = 0, len = 0;
+        int s = 0, len = 0, ws = 0, wlen = 0;
         if (r < nr) {
           const int4 rr = *reinterpret_cast<const int4 *>(runs + 4 * (rb + r));
-          int b1 = c1 + rr.x, b2 = c2 + rr.y, z0 = c3 + rr.z, z1 = c3 + rr.w;
-          if (b1 >= -g.L && b1 < g.nc[0] + g.L && b2 >= -g.L && b2 < g.nc[1] + g.L) {
-            if (z0 < -g.L) z0 = -g.L;
-            if (z1 >= g.nc[2] + g.L) z1 = g.nc[2] + g.L - 1;
-            if (z1 >= z0) {
-              int cbase = ((b1 + g.L) * g.dim[1] + (b2 + g.L)) * g.dim[2] + g.L;
-              s = g.start[cbase + z0];
-              len = g.start[cbase + z1 + 1] - s;
-            }
-          }
+          run_span(g, rr, c1, c2, c3, c3, s, len);
+          if (win) run_span(g, rr, c1, c2, wg0, wg1, ws, wlen);
         }
-        int inc = len;
+        int inc = len, winc = wlen;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
           int y = __shfl_up_sync(0xffffffffu, inc, o);
           if (lane >= o) inc += y;
+          if (win) {
+            int yw = __shfl_up_sync(0xffffffffu, winc, o);
+            if (lane >= o) winc += yw;
+          }
         }
         if (r < nr) { sh_s[wid][r] = s; sh_p[wid][r] = carry + inc - len; }
+        if (win && r < nr) sh_w[wid][r] = wcarry + winc - wlen - ws;
         carry += __shfl_sync(0xffffffffu, inc, 31);
+        if (win) wcarry += __shfl_sync(0xffffffffu, winc, 31);
       }
       if (lane == 0) sh_p[wid][nr] = carry;
       __syncwarp();
@@ -201,6 +255,8 @@ __global__ void __launch_bounds__(PL_WARPS * 32) k_pairlist(DevGrid g, const Dev
         if (have) o = ldg256(g.sorted + cslot);
         const int jt = rec_type(o.w);
         const int cval = cslot | ((have && rec_index(o.w) >= natoms) ? COL_GHOST : 0);
+        // position in the group's window + ghost flag (garbage when the window exceeds 15 bits: k_spmv_win then reads `col`)
+        const unsigned short c16v = (win && have) ? (unsigned short)(((sh_w[wid][r] + cslot) & 0x7fff) | (cval < 0 ? 0x8000 : 0)) : 0;
         unsigned um = 0;   // rows of this batch whose list takes this lane's candidate
         for (int a = 0; a < nb; a++) {
           const double4 at = sh_a[wid][a];
@@ -213,6 +269,7 @@ __global__ void __launch_bounds__(PL_WARPS * 32) k_pairlist(DevGrid g, const Dev
             const long long w = wb + __popc(mask & ((1u << lane) - 1u));
             if (acc && (!CAPPED || w < wend)) {
               col[w] = cval;
+              if (win) wo.c16[w] = c16v;
               if (MODE >= 1) {
                 // the hessian lerp is evaluated by k_hessian over the compacted rows (full lanes); here only the
                 // fp32-rounded r^2 and the bond type are parked in the 8 bytes of the value slot
@@ -306,6 +363,10 @@ __global__ void __launch_bounds__(PL_WARPS * 32) k_pairlist(DevGrid g, const Dev
         }
       }
     }
+    if (win) {
+      if (FILL && lane < nb) wo.rowlen[myslot] = mine ? (CAPPED ? min(mycnt, mycap) : mycnt) : -1;
+      if (lane == 0 && ab == a0 && wcarry > __ldcg(wo.winmax)) atomicMax(wo.winmax, wcarry);
+    }
     if (!FILL || CAPPED) {   // exact entry count (without row padding): the algorithmic-bytes figure of the roofline uses it;
                              // longest row: picks the SpMV launch shape
       const int real = __reduce_add_sync(0xffffffffu, (lane < nb && mine) ? mycnt : 0);
@@ -385,6 +446,7 @@ __global__ void k_row_caps(DevGrid g, int ntot, int natoms, CntTab ct, int slack
 }
 
 int ensure_bond_capacity(Ctx *c, long long need);   // rxg_api.cu
+int win_pick_group(Ctx *c);                          // rxg_api.cu
 
 inline int build_nbrlist(Ctx *c) {
   const int n = c->cp[6];
@@ -433,17 +495,37 @@ int build_pairlist(Ctx *c, bool hessian = true, bool allow_capped = false) {
   const bool capped = MODE >= 1 && allow_capped && c->caps_on && c->caps_valid && !c->strict && !un_on && c->cnt_tab;
   c->list_capped = capped;
   if (capped) c->timers_ms[23] += 1;   // list builds without a count pass
-  RXG_CUDA(cudaMemsetAsync(c->d_flag + 20, 0, sizeof(int), c->st));
+  RXG_CUDA(cudaMemsetAsync(c->d_flag + 20, 0, 2 * sizeof(int), c->st));
+  // window SpMV: the fill pass also writes the 16-bit window-relative columns and the row lengths by slot
+  const bool win_on = MODE >= 1 && c->spmv_kind == 2 && !c->strict;
+  WinOut wo;
+  wo.c16 = nullptr; wo.rowlen = c->rowlen; wo.winmax = c->d_flag + 21; wo.G = 1;
+  if (win_on) {
+    if (c->win_g <= 0) c->win_g = win_pick_group(c);
+    wo.G = c->win_g;
+    wo.c16 = c->col16 ? c->col16 : (unsigned short *)c->rowlen;   // count pass before the first allocation: any non-null pointer (it only lays the window out)
+    // window descriptors of every group (k_spmv_win reads them instead of redoing the layout in every CTA of every product)
+    const int ngroups = c->gnb.nc[0] * c->gnb.nc[1] * cdiv(c->gnb.nc[2], wo.G);
+    const size_t need = (size_t)ngroups * (size_t)(c->nruns + 1);
+    if (need > c->win_desc_cap) {
+      if (c->win_desc) cudaFree(c->win_desc);
+      c->win_desc_cap = need + need / 8;
+      RXG_CUDA(cudaMalloc(&c->win_desc, sizeof(int2) * c->win_desc_cap));
+    }
+    LAUNCH(c, k_win_desc, cdiv((long long)ngroups * 32, 256), 256, 0, c->gnb, c->d_runs, c->nruns, wo.G, ngroups, c->win_desc);
+  }
+  c->win_built = false;
 #define RXG_PL_ARGS c->gnb, c->d_ff, c->d_runs, c->nruns, n, ncell_res, c->rowcnt, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->cfg.maxneighbs10,   \
                     c->d_flag, (unsigned long long *)(c->d_acc + 33), ralign, c->ucnt, c->uoff, c->ucol, c->umask, c->items, c->d_flag + 17
   if (capped) LAUNCH(c, k_row_caps, cdiv(nt, 256), 256, 0, c->gnb, nt, n, ct, c->caps_slack, ((c->maxrow + 8 + ralign - 1) & ~(ralign - 1)), ralign, c->rowcnt);
-  else if (un_on) LAUNCH(c, (k_pairlist<MODE, false, (MODE >= 1)>), grid, PL_WARPS * 32, 0, RXG_PL_ARGS, 4, ct);
-  else LAUNCH(c, (k_pairlist<MODE, false, false>), grid, PL_WARPS * 32, 0, RXG_PL_ARGS, 4, ct);
+  else if (un_on) LAUNCH(c, (k_pairlist<MODE, false, (MODE >= 1)>), grid, PL_WARPS * 32, 0, RXG_PL_ARGS, 4, ct, wo);
+  else LAUNCH(c, (k_pairlist<MODE, false, false>), grid, PL_WARPS * 32, 0, RXG_PL_ARGS, 4, ct, wo);
   RXG_TRY(ensure_blk(c, nt));
   RXG_TRY(device_scan<long long>(c, c->rowcnt, nt, c->rowoff, c->d_blk64, (long long *)(c->d_acc + 32)));
   if (un_on) RXG_TRY(device_scan<long long>(c, c->ucnt, nt, c->uoff, c->d_blk64, (long long *)(c->d_acc + 34)));
   RXG_CUDA(cudaMemcpyAsync(c->h_int, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->st));
   RXG_CUDA(cudaMemcpyAsync(c->h_int + 16, c->d_flag + 16, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+  if (win_on && !capped) RXG_CUDA(cudaMemcpyAsync(c->h_int + 21, c->d_flag + 21, sizeof(int), cudaMemcpyDeviceToHost, c->st));
   RXG_CUDA(cudaMemcpyAsync(c->h_acc + 32, c->d_acc + 32, 3 * sizeof(long long), cudaMemcpyDeviceToHost, c->st));
   RXG_CUDA(cudaStreamSynchronize(c->st));
   if (!capped && c->h_int[0] > c->cfg.maxneighbs10) {
@@ -454,9 +536,15 @@ int build_pairlist(Ctx *c, bool hessian = true, bool allow_capped = false) {
   if (nnz > c->nnz_cap) {
     if (c->col) cudaFree(c->col);
     if (c->val) cudaFree(c->val);
+    if (c->col16) { cudaFree(c->col16); c->col16 = nullptr; }
     c->nnz_cap = nnz + nnz / 16 + 1024;
     RXG_CUDA(cudaMalloc(&c->col, sizeof(int) * c->nnz_cap));
     RXG_CUDA(cudaMalloc(&c->val, sizeof(double) * c->nnz_cap));
+  }
+  if (win_on) {
+    if (!c->col16) RXG_CUDA(cudaMalloc(&c->col16, sizeof(unsigned short) * c->nnz_cap));
+    wo.c16 = c->col16;
+    if (!capped) c->win_max = c->h_int[21];   // (capped: the fill pass reports it, check_capped_flags reads it)
   }
   const long long nun = un_on ? *(long long *)(c->h_acc + 34) : 0;
   if (nun > c->un_cap) {
@@ -477,10 +565,11 @@ int build_pairlist(Ctx *c, bool hessian = true, bool allow_capped = false) {
   c->spmv_rg = c->maxrow <= 480 ? 4 : 2;
   RXG_CUDA(cudaMemsetAsync(c->d_flag + 17, 0, sizeof(int), c->st));
   const bool hfuse = MODE >= 1 && hessian && c->hess_fuse && !un_on && !capped;
-  if (capped) LAUNCH(c, (k_pairlist<MODE, true, false, false, (MODE >= 1)>), grid, PL_WARPS * 32, 0, RXG_PL_ARGS, c->spmv_rg, ct);
-  else if (un_on) LAUNCH(c, (k_pairlist<MODE, true, (MODE >= 1)>), grid, PL_WARPS * 32, 0, RXG_PL_ARGS, c->spmv_rg, ct);
-  else if (hfuse) LAUNCH(c, (k_pairlist<MODE, true, false, (MODE >= 1)>), grid, PL_WARPS * 32, 0, RXG_PL_ARGS, c->spmv_rg, ct);
-  else LAUNCH(c, (k_pairlist<MODE, true, false>), grid, PL_WARPS * 32, 0, RXG_PL_ARGS, c->spmv_rg, ct);
+  if (capped) LAUNCH(c, (k_pairlist<MODE, true, false, false, (MODE >= 1)>), grid, PL_WARPS * 32, 0, RXG_PL_ARGS, c->spmv_rg, ct, wo);
+  else if (un_on) LAUNCH(c, (k_pairlist<MODE, true, (MODE >= 1)>), grid, PL_WARPS * 32, 0, RXG_PL_ARGS, c->spmv_rg, ct, wo);
+  else if (hfuse) LAUNCH(c, (k_pairlist<MODE, true, false, (MODE >= 1)>), grid, PL_WARPS * 32, 0, RXG_PL_ARGS, c->spmv_rg, ct, wo);
+  else LAUNCH(c, (k_pairlist<MODE, true, false>), grid, PL_WARPS * 32, 0, RXG_PL_ARGS, c->spmv_rg, ct, wo);
+  if (win_on) { c->win_built = true; c->win_g_built = wo.G; }
 #undef RXG_PL_ARGS
   if (MODE >= 1 && c->cnt_tab) c->caps_valid = true;
   if (MODE >= 1 && hessian && !hfuse)
@@ -755,6 +844,146 @@ __global__ void __launch_bounds__(ROWS * LPR) k_spmv_rows(const int *__restrict_
     ga += __shfl_xor_sync(0xffffffffu, ga, o); gb += __shfl_xor_sync(0xffffffffu, gb, o);
   }
   if (sub == 0 && i < natoms) rowsum[slot] = make_double4(a, b, ga, gb);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Window SpMV (k_spmv_win).  k_spmv_rows is bound by the L1 data pipe, not by HBM: every stored entry costs a 16-byte gather of
+// x through the L1 tag stage (7.5 wavefronts per warp request, half of them L2 round trips), on top of the staged stream.
+// Here a CTA owns a GROUP of up to G consecutive resident cells of one z-column.  All rows of the group draw their columns
+// from the same few stencil runs, so the CTA first copies the group's WINDOW of x -- one cp.async.bulk (TMA, UBLKCP) per
+// stencil run, ~70 copies of ~0.7 KB, 40-75 KB in all -- into shared memory, and the rows then gather x from shared memory
+// (29-cycle LDS.128, no tag stage, no L2 round trip) through the 16-bit window-relative column stream that k_pairlist's fill
+// pass writes (struct WinOut): bits 0-14 position in the window, bit 15 ghost flag.  The matrix stream is 8 B of value +
+// 2 B of column per entry, read once, coalesced, straight into registers (evict-first), eight entries in flight per lane;
+// a warp takes whole rows, so a row sum needs one warp reduction and no atomics.  A group whose window does not fit the
+// shared-memory budget (or 15 bits) falls back to the 32-bit columns and global gathers for that CTA only.
+// Row table: start (rowoff) and exact length (rowlen, written by the fill pass) by cell-order slot, so that nothing on the
+// path depends on the atom-order indirection.
+// the rows of one group, streamed by one warp: rows wid, wid + NW, ... .  GH: the group may take ghost columns (bit 15 of a column)
+template <int NW, int U, bool GH>
+__device__ __forceinline__ void win_rows(const double2 *__restrict__ s_x, int a0, int nrows, int lane, int wid, const long long *__restrict__ rowoff,
+                                         const int *__restrict__ rowlen, const unsigned short *__restrict__ col16,
+                                         const double *__restrict__ val, double4 *__restrict__ rowsum, unsigned long long *bar) {
+  int t = wid;
+  if (t >= nrows) { mbar_wait(bar, 0); return; }
+  long long rs = __ldg(rowoff + a0 + t);
+  int n = __ldg(rowlen + a0 + t);
+  // the next row's start and length are requested one row ahead, so their round trip hides behind the current row
+  long long rs_next = 0;
+  int n_next = 0;
+  if (t + NW < nrows) { rs_next = __ldg(rowoff + a0 + t + NW); n_next = __ldg(rowlen + a0 + t + NW); }
+  double h[U];
+  unsigned short c[U];
+  int k0 = 0;
+  auto load = [&]() {
+    const double *pv = val + rs + k0 + lane;
+    const unsigned short *pc = col16 + rs + k0 + lane;
+    const int rem = n - k0 - lane;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      h[u] = 0.0; c[u] = 0;
+      if (32 * u < rem) { h[u] = __ldcs(pv + 32 * u); c[u] = __ldcs(pc + 32 * u); }
+    }
+  };
+  load();                // the first batch is requested BEFORE the wait for the window: the two round trips overlap
+  mbar_wait(bar, 0);
+  double a = 0.0, b = 0.0, ga = 0.0, gb = 0.0;
+  const char *sxb = reinterpret_cast<const char *>(s_x);
+  for (;;) {
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      const unsigned cu = c[u];
+      const double2 v = *reinterpret_cast<const double2 *>(sxb + (GH ? ((cu << 4) & 0x7fff0u) : (cu << 4)));
+      a = fma(h[u], v.x, a);
+      b = fma(h[u], v.y, b);
+      if (GH && (cu & 0x8000u)) { ga = fma(h[u], v.x, ga); gb = fma(h[u], v.y, gb); }
+    }
+    k0 += 32 * U;
+    if (k0 >= n) {
+      warp_sum4(a, b, ga, gb, lane);
+      if (lane == 0 && n >= 0) rowsum[a0 + t] = make_double4(a, b, ga, gb);   // n < 0: a ghost in a resident cell owns no row
+      a = b = ga = gb = 0.0;
+      t += NW;
+      if (t >= nrows) break;
+      rs = rs_next; n = n_next; k0 = 0;
+      if (t + NW < nrows) { rs_next = __ldg(rowoff + a0 + t + NW); n_next = __ldg(rowlen + a0 + t + NW); }
+    }
+    load();
+  }
+}
+
+template <int NW, int U, int MINB>
+__global__ void __launch_bounds__(NW * 32, MINB) k_spmv_win(DevGrid g, int nruns, int G, int reach, const int2 *__restrict__ desc,
+                                                            const long long *__restrict__ rowoff, const int *__restrict__ rowlen,
+                                                            const int *__restrict__ col, const unsigned short *__restrict__ col16,
+                                                            const double *__restrict__ val, const double2 *__restrict__ x,
+                                                            double4 *__restrict__ rowsum, const double *__restrict__ acc, int wcap) {
+  extern __shared__ __align__(128) unsigned char win_smem[];
+  double2 *s_x = reinterpret_cast<double2 *>(win_smem);
+  __shared__ __align__(8) unsigned long long bar;
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  if (threadIdx.x == 0) {
+    mbar_init(&bar, NW);   // one arrival (with its share of the expected bytes) per warp
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  __syncthreads();
+  const double cg_done = acc[ACC_DONE];
+  const int ngz = (g.nc[2] + G - 1) / G;
+  const int gz = blockIdx.x % ngz, c2 = (blockIdx.x / ngz) % g.nc[1], c1 = blockIdx.x / (ngz * g.nc[1]);
+  const int g0 = gz * G, g1 = min(g0 + G, g.nc[2]) - 1;
+  const int cid0 = ((c1 + g.L) * g.dim[1] + (c2 + g.L)) * g.dim[2] + (g0 + g.L);
+  const int a0 = g.start[cid0], a1 = g.start[cid0 + (g1 - g0) + 1];
+  // Two load chains start here side by side: window descriptors -> bulk copies of x (this block), and group bounds -> row
+  // start/length -> first batch of the matrix stream (win_rows); neither waits for the other until the first gather.  Warp w
+  // issues the copies of the runs r = w (mod NW): a bulk copy takes uniform operands, so a warp issues its copies one lane at
+  // a time.
+  const int2 *d = desc + (size_t)blockIdx.x * (nruns + 1);
+  const int tot = __ldg(&d[nruns].y) >> 12;
+  const bool staged = tot <= wcap && tot <= 32768;
+  {
+    unsigned issued = 0;
+    if (staged && cg_done == 0.0) {
+      for (int r = wid + NW * lane; r < nruns; r += NW * 32) {
+        const int2 e = __ldg(d + r);
+        const int wlen = e.y & 0xfff, pos = e.y >> 12;
+        if (wlen > 0) {
+          bulk_g2s(s_x + pos, x + e.x, (unsigned)wlen * 16u, &bar);
+          issued += (unsigned)wlen * 16u;
+        }
+      }
+    }
+    issued = __reduce_add_sync(0xffffffffu, issued);
+    // (a copy may complete before its warp's arrive: the phase cannot, it needs all NW arrivals; the tx-count is signed)
+    if (lane == 0) mbar_expect_tx(&bar, issued);
+  }
+  const int nrows = (cg_done != 0.0) ? 0 : a1 - a0;   // the CG has stopped (k_cg_ctrl): nothing to do (no copy was issued either)
+  if (staged) {
+    // a group at least `reach` cells inside the resident grid takes no ghost column: its rows skip the ghost sums altogether
+    const bool inner = c1 >= reach && c1 < g.nc[0] - reach && c2 >= reach && c2 < g.nc[1] - reach && g0 >= reach && g1 < g.nc[2] - reach;
+    if (inner) win_rows<NW, U, false>(s_x, a0, nrows, lane, wid, rowoff, rowlen, col16, val, rowsum, &bar);
+    else win_rows<NW, U, true>(s_x, a0, nrows, lane, wid, rowoff, rowlen, col16, val, rowsum, &bar);
+  } else {
+    mbar_wait(&bar, 0);
+    // the window does not fit: 32-bit columns, x gathered from global memory (this CTA only)
+    for (int t = wid; t < nrows; t += NW) {
+      const long long rs = rowoff[a0 + t];
+      const int n = rowlen[a0 + t];
+      if (n < 0) continue;
+      const double *pv = val + rs;
+      const int *pc = col + rs;
+      double a = 0.0, b = 0.0, ga = 0.0, gb = 0.0;
+      for (int k = lane; k < n; k += 32) {
+        const double hh = __ldcs(pv + k);
+        const int cc = __ldcs(pc + k);
+        const double2 v = x[cc & COL_MASK];
+        const double pa = hh * v.x, pb = hh * v.y;
+        a += pa; b += pb;
+        if (cc < 0) { ga += pa; gb += pb; }
+      }
+      warp_sum4(a, b, ga, gb, lane);
+      if (lane == 0) rowsum[a0 + t] = make_double4(a, b, ga, gb);
+    }
+  }
 }
 
 // ---------------------------------------------------------------------------------------------------

@@ -67,7 +67,8 @@ def rows(e, n):
 
 @pytest.fixture(autouse=True)
 def _clean_env():
-    keys = ("RXG_STRICT_ORDER", "RXG_QEQ_TWOPASS", "RXG_FUSE_API", "RXG_NO_FUSE", "RXG_SPMV", "RXG_SPMV_SHAPE", "RXG_SPMV_STAGE", "RXG_SPMV_RING")
+    keys = ("RXG_STRICT_ORDER", "RXG_QEQ_TWOPASS", "RXG_FUSE_API", "RXG_NO_FUSE", "RXG_SPMV", "RXG_SPMV_SHAPE", "RXG_SPMV_STAGE", "RXG_SPMV_RING",
+            "RXG_WIN_G", "RXG_WIN_WARPS", "RXG_WIN_WCAP", "RXG_WIN_SMEM")
     for k in keys:
         os.environ.pop(k, None)
     yield
@@ -138,12 +139,12 @@ def test_lists_matrix_energies_forces(built, name):
 
 
 @pytest.mark.parametrize("name", list(systems().keys()))
-@pytest.mark.parametrize("spmv", ["rows", "items"])
+@pytest.mark.parametrize("spmv", ["win", "rows", "items"])
 def test_production_cg_follows_oracle_iterates(built, name, spmv):
     """The benchmarked CG (single sparse product per iteration, residual recurrence, device-side stop rule and real(4) step
     lengths) against the oracle's literal two-product CG after exactly k iterations, k = 1..20."""
-    if spmv == "items":
-        os.environ["RXG_SPMV"] = "items"
+    if spmv != "win":               # "win" (k_spmv_win) is the default
+        os.environ["RXG_SPMV"] = spmv
     worst = {}
     for k, bar in CG_TRACE_BARS.items():
         s, cfg, e, o = make(name, NMAXQEq=k)
@@ -593,13 +594,17 @@ def test_it_timer_slots_are_filled(built):
     e.close()
 
 
-@pytest.mark.parametrize("slack", ["4", "0"])
-def test_list_build_without_count_pass(built, slack):
+@pytest.mark.parametrize("slack,cooldown", [("4", None), ("0", "0"), ("0", None)])
+def test_list_build_without_count_pass(built, slack, cooldown):
     """From the second QEq on, the 10 A list is laid out from last step's row counts (by global atom id) plus a slack instead of
     a count pass (k_row_caps, k_pairlist<..., CAPPED>).  The rows must still equal the oracle's entry by entry while atoms move
     and migrate; with slack 0 some row outgrows its capacity in nearly every step, so the overflow -> rebuild-with-counts ->
-    restart path runs too and must give the same lists and charges."""
+    restart path runs too and must give the same lists and charges.  After an overflow the library keeps the count pass for the
+    next 8, 16, ... builds (a retry costs far more than a count pass); RXG_CAP_COOLDOWN=0 switches that off so that every step
+    of this test overflows."""
     os.environ["RXG_CAP_SLACK"] = slack
+    if cooldown is not None:
+        os.environ["RXG_CAP_COOLDOWN"] = cooldown
     try:
         s, cfg, e, o = make("rdx_2x2x2_disp", NMAXQEq=4)
         atype, pos, v, f, q = e.host_arrays(s.ranks[0])
@@ -625,11 +630,15 @@ def test_list_build_without_count_pass(built, slack):
             assert np.abs(q[:n] - o.f64("q")[:n]).max() <= CG_TRACE_BARS[4]
             q[:n] = o.f64("q")[:n]
         t = e.timers()
-        assert t[23] >= 3, "the capped path never ran"                      # list builds without a count pass
-        if slack == "0":
-            assert t[24] >= 1, "no overflow was provoked"                   # rebuilds after an overflow
+        if slack == "0" and cooldown is None:
+            assert t[23] == 1 and t[24] == 1, "after an overflow the next builds must keep the count pass"
         else:
-            assert t[24] == 0
+            assert t[23] >= 3, "the capped path never ran"                  # list builds without a count pass
+            if slack == "0":
+                assert t[24] >= 1, "no overflow was provoked"               # rebuilds after an overflow
+            else:
+                assert t[24] == 0
         e.close(); o.close()
     finally:
         os.environ.pop("RXG_CAP_SLACK", None)
+        os.environ.pop("RXG_CAP_COOLDOWN", None)

@@ -18,13 +18,22 @@ from rxmd_b200.host.system import build_system
 pytestmark = pytest.mark.gpu
 
 INP = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "inputs")
-SPMV_ENV = ("RXG_SPMV", "RXG_SPMV_SHAPE", "RXG_SPMV_STAGE", "RXG_SPMV_RING", "RXG_FUSE_API")
+SPMV_ENV = ("RXG_SPMV", "RXG_SPMV_SHAPE", "RXG_SPMV_STAGE", "RXG_SPMV_RING", "RXG_FUSE_API", "RXG_WIN_G", "RXG_WIN_WARPS", "RXG_WIN_WCAP", "RXG_WIN_U",
+            "RXG_WIN_SMEM")
 
 VARIANTS = {
-    "items": {},
-    "items_3stage": {"RXG_SPMV_RING": "3"},
-    "items_unstaged": {"RXG_SPMV_STAGE": "0"},
-    "items_shared_list": {"RXG_FUSE_API": "1"},      # the list rxg_md_run / bench.py use: FORCE predicate, zero hessian entries
+    # k_spmv_win (production): window of x in shared memory, 16-bit window-relative columns
+    "win_auto": {},
+    "win_g1_w4": {"RXG_WIN_G": "1", "RXG_WIN_WARPS": "4"},
+    "win_g5_w4_u4": {"RXG_WIN_G": "5", "RXG_WIN_WARPS": "4", "RXG_WIN_U": "4"},
+    "win_g3_u4": {"RXG_WIN_G": "3", "RXG_WIN_U": "4"},
+    "win_g7": {"RXG_WIN_G": "7"},
+    "win_fallback": {"RXG_WIN_G": "2", "RXG_WIN_WCAP": "512"},   # no window fits 512 entries: every CTA gathers from global memory
+    "win_shared_list": {"RXG_FUSE_API": "1"},
+    "items": {"RXG_SPMV": "items"},
+    "items_3stage": {"RXG_SPMV": "items", "RXG_SPMV_RING": "3"},
+    "items_unstaged": {"RXG_SPMV": "items", "RXG_SPMV_STAGE": "0"},
+    "items_shared_list": {"RXG_SPMV": "items", "RXG_FUSE_API": "1"},      # the list rxg_md_run / bench.py use: FORCE predicate, zero hessian entries
     "rows_auto": {"RXG_SPMV": "rows"},
     "rows_8x8": {"RXG_SPMV": "rows", "RXG_SPMV_SHAPE": "8x8"},
     "rows_4x16": {"RXG_SPMV": "rows", "RXG_SPMV_SHAPE": "4x16"},
@@ -97,6 +106,12 @@ def test_spmv_rowsums_match_numpy(built, name, variant):
     err = np.abs(got - ref) / sc
     print(f"{name} {variant}: max rel err {err.max():.2e} (rows {e.NATOMS}, nnz {int(e.fetch('nnz')[0])})")
     assert err.max() <= 1e-13
+    t = e.timers()
+    if variant.startswith("win"):   # the launch really was k_spmv_win (a list whose windows do not fit falls back to k_spmv_rows)
+        print(f"  win launches {int(t[25])}, rows launches {int(t[26])}, G {int(t[27])}, largest window {int(t[28])}")
+        assert t[25] > 0 and t[26] == 0
+    else:
+        assert t[25] == 0
     e.close()
 
 

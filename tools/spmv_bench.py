@@ -42,7 +42,11 @@ def main():
         x = np.random.default_rng(1).normal(0.0, 1.0, (int(ntot), 2))
         _, ms = e.debug_spmv(x, reps=a.reps)
         canon = 12.0 * nnz + 4.0 * (n + 1) + 16.0 * ntot + 40.0 * n
-        held = 8.0 * t[18] + (5.0 * nun if os.environ.get("RXG_SPMV") == "items" else 4.0 * t[18])
+        t2 = e.timers()
+        win = t2[25] > 0
+        held = 8.0 * t[18] + (5.0 * nun if os.environ.get("RXG_SPMV") == "items" else (2.0 if win else 4.0) * t[18])
+        if win:
+            v += f" [win G={int(t2[27])} wmax={int(t2[28])}]"
         print(f"{a.config} {v:40s} {ms:8.4f} ms  canonical {canon / 1e9:.3f} GB -> {canon / ms / 1e6:8.1f} GB/s   streams {held / 1e9:.3f} GB -> "
               f"{held / ms / 1e6:8.1f} GB/s   (nnz {int(nnz)}, union {int(nun)}, ratio {nun / max(nnz, 1):.3f})", flush=True)
         e.close()
