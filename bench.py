@@ -199,7 +199,7 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
-    from rxmd_b200.host.engine import Engine, MODE_MOVE, HINT_ATOMS_ON_DEVICE, HINT_Q_ON_DEVICE, HINT_DEFER_POS
+    from rxmd_b200.host.engine import Engine, MODE_MOVE, HINT_ATOMS_ON_DEVICE, HINT_Q_ON_DEVICE, HINT_DEFER_POS, HINT_CHARGES_STAY
     from rxmd_b200.host.configs import build_config
     # e2e leg: let rxg_force reuse the halo and 10 A list of the rxg_qeq that precedes it when the host hands back
     # bit-identical atoms (verified on the device); rxg_md_run does the same sharing internally
@@ -243,6 +243,7 @@ def main():
     e.md_prime()
     e.md_run(args.warmup, dt, 1, lw2, 0)
     t_before = e.timers()
+    it_before = e.it_timer()
     l_before = e.launches()
     sampler = ClockSampler(local)
     if rank == 0:
@@ -252,8 +253,13 @@ def main():
     barrier()
     clocks = sampler.finish() if rank == 0 else None
     t_after = e.timers()
+    it_after = e.it_timer()
     l_after = e.launches()
     ms_total = allmax(t_after[3] - t_before[3])
+    # the reference's own phase table (it_timer slots, src/main.F90:135-180), CUDA-event times of rank 0, ms per step
+    IT_NAMES = {3: "LINKEDLIST", 4: "COPYATOMS", 5: "NEIGHBORLIST", 6: "BOCALC", 7: "ENbond", 8: "Ebond", 9: "Elnpr", 10: "Ehb", 11: "E3b",
+                12: "E4b", 13: "ForceBondedTerms", 15: "GetNonbondingPairList", 16: "qeq_initialize", 18: "get_hsh (CG)"}
+    it_ms = {f"{k} {nm}": round((it_after[k - 1] - it_before[k - 1]) * 1e3 / max(args.steps, 1), 3) for k, nm in IT_NAMES.items()}
     natoms_total = allsum(float(e.natoms_resident()))
     value = natoms_total * args.steps / (ms_total * 1e-3)
     d = t_after - t_before
@@ -329,24 +335,33 @@ def main():
                     v[c, i] += d * f[c, i]
                 qsfv[i] += 0.5 * dt * lw2 * (q[i] - qsfp[i])
 
+        e2e_parts = np.zeros(5)    # seconds in: first half, COPYATOMS(MOVE), QEq, FORCE, second half (host clock, this rank)
+
         def host_step():
             nonlocal n
+            t0 = time.perf_counter()
             # the hints are what rxmd_b200/gpu_shim.F90 states inside the main loop: nothing touches atype/pos/q between
             # COPYATOMS(MOVE), QEq and FORCE (src/main.F90:75-84), so pos travels up once and down once per step
             first_half(n, dt, lw2, dthm_of_type, h_atype, h_v, h_f, h_q, e.qsfp, e.qsfv, h_pos)   # :64-72
-            e.hint(HINT_DEFER_POS)
+            t1 = time.perf_counter()
+            e.hint(HINT_DEFER_POS | HINT_CHARGES_STAY)
             e.COPYATOMS(MODE_MOVE, [0.0, 0.0, 0.0], h_atype, h_pos, h_v, h_f, h_q)    # :75
             n = e.NATOMS
+            t2 = time.perf_counter()
             e.hint(HINT_ATOMS_ON_DEVICE | HINT_Q_ON_DEVICE | HINT_DEFER_POS)
             if pq:
                 e.PQEq(h_atype, h_pos, h_q)                                            # :78
             else:
                 e.QEq(h_atype, h_pos, h_q)                                             # :80
+            t3 = time.perf_counter()
             e.hint(HINT_ATOMS_ON_DEVICE | HINT_Q_ON_DEVICE)
             e.FORCE(h_atype, h_pos, h_f, h_q)                                          # :84
+            t4 = time.perf_counter()
             second_half(n, dt, lw2, dthm_of_type, h_atype, h_v, h_f, h_q, e.qsfp, e.qsfv)         # :86-98
+            e2e_parts[:] += (t1 - t0, t2 - t1, t3 - t2, t4 - t3, time.perf_counter() - t4)
         host_step()
         barrier()
+        e2e_parts[:] = 0.0
         tb = e.timers()
         t0 = time.perf_counter()
         for _ in range(ksteps):
@@ -359,7 +374,9 @@ def main():
                "d2h_bytes_per_step": int(d2h / ksteps), "steps": ksteps, "ms_per_step": t_e2e / ksteps * 1e3,
                "api": f"Engine.COPYATOMS(MODE_MOVE) + Engine.{'PQEq' if pq else 'QEq'} + Engine.FORCE over rxg_move/rxg_{'pqeq' if pq else 'qeq'}/rxg_force, "
                       "pinned host arrays, host integrator",
-               "host_threads_per_rank": int(numba.get_num_threads()), "force_calls_reusing_qeq_list": int(ta[22] - tb[22])}
+               "host_threads_per_rank": int(numba.get_num_threads()), "force_calls_reusing_qeq_list": int(ta[22] - tb[22]),
+               "ms_per_step_by_call": dict(zip(["host first half", "COPYATOMS(MOVE)", "QEq", "FORCE", "host second half"],
+                                               [round(float(x) / ksteps * 1e3, 3) for x in e2e_parts]))}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -383,6 +400,7 @@ def main():
                            "pe_per_atom_global": pe_global / max(natoms_total, 1), "ke_per_atom_global": ke_global / max(natoms_total, 1),
                            "sum_q_global": q_global, "setup_seconds_per_rank": t_setup},
                 "phase_ms_per_step": {"QEq": d[4] / args.steps, "FORCE": d[5] / args.steps, "MOVE": d[6] / args.steps},
+                "it_timer_ms_per_step": it_ms,
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "clocks": clocks, "parity": parity,
                 "gpu_launches": int(l_after - l_before)}
         print(json.dumps(line), flush=True)

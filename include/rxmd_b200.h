@@ -138,10 +138,15 @@ const char *rxg_last_error(rxg_handle h);
  *   RXG_HINT_DEFER_POS        the next call need not copy pos back (its only change is the ulp-level normalise/de-normalise
  *                             round trip of COPYATOMS): the following call is hinted ATOMS_ON_DEVICE and a later
  *                             un-deferred call (rxg_force) returns the final positions.  Ignored by rxg_move when atoms migrate.
+ *   RXG_HINT_CHARGES_STAY     (rxg_move) q, qs and qt of this call are what the library itself last produced and the host reads
+ *                             none of them before the next rxg_qeq / rxg_pqeq returns q: they migrate with their atoms on the
+ *                             device (src/comm.F90:164-171) but cross PCIe in neither direction -- qs/qt are QEq's own CG
+ *                             vectors, which no host loop of the reference touches (src/main.F90:64-98)
  * A promise that does not hold gives wrong results; hints are dropped when natoms differs from the device's. */
 #define RXG_HINT_ATOMS_ON_DEVICE 1
 #define RXG_HINT_Q_ON_DEVICE     2
 #define RXG_HINT_DEFER_POS       4
+#define RXG_HINT_CHARGES_STAY    8
 int rxg_hint(rxg_handle h, int flags);
 
 /* ---- the drop-in entry points (host buffers in, host buffers out) -------------------------- */

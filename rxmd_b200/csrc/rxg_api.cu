@@ -356,11 +356,29 @@ int check_capped_flags(Ctx *c) {
   }
   // multi-rank: every rank must take the same decision -- the flags were summed over the ranks (qeq_cg_single)
   if (c->comm ? c->h_acc[26] > 0.5 : c->h_int[20] != 0) {
-    // a retry costs a list build and a CG batch, a count pass 2 ms: after an overflow the next builds count again, for twice
-    // as many steps each time it happens (8, 16, ... 4096), so a system whose rows keep outgrowing their slack cannot lose
-    // more than a few per cent to retries
+    // A row's count changes by the atoms that cross its 10 A sphere in one step: ~0.1-0.5 on average, Poisson-distributed, so
+    // with a slack of s entries a row overflows with probability ~ lambda^(s+1)/(s+1)! -- times 10^6-10^7 rows per rank and
+    // step.  Measured at 979 776 atoms per rank (RDX, ~500 K): slack 4 overflows in ~10 % of the steps on one rank and in
+    // nearly every step on eight (every rank retries when one does).  The default slack is therefore 8; an overflow raises
+    // it by 4 (up to 32) and keeps the count pass for the next few builds (4, 8, ... 256): a retry costs a list build and a
+    // CG batch, a count pass 2 ms.
     c->caps_overflows++;
-    c->caps_skip = c->caps_cooldown ? (8 << std::min(c->caps_fails, 9)) : 0;
+    if (getenv("RXG_CAP_DEBUG")) {
+      int dbg[4] = {0, 0, 0, 0};
+      cudaMemcpy(dbg, c->d_flag + 22, sizeof(dbg), cudaMemcpyDeviceToHost);
+      double p3[3] = {0, 0, 0};
+      int cell = -1;
+      if (dbg[3] >= 0 && dbg[3] < c->NB) {
+        for (int a = 0; a < 3; a++) cudaMemcpy(&p3[a], c->pos + (size_t)a * c->NB + dbg[3], sizeof(double), cudaMemcpyDeviceToHost);
+        cudaMemcpy(&cell, c->gnb.cell_of + dbg[3], sizeof(int), cudaMemcpyDeviceToHost);
+      }
+      const DevGrid &g = c->gnb;
+      fprintf(stderr, "[rxg rank %d] capped list overflow: gid %d row count %d capacity %d (atom %d of %d residents, default capacity %d, slack %d) pos %.6f %.6f %.6f cell (%d %d %d) of (%d %d %d)\n",
+              c->box.myid, dbg[0], dbg[1], dbg[2], dbg[3], c->natoms, c->maxrow + 8, c->caps_slack, p3[0], p3[1], p3[2],
+              cell < 0 ? -1 : cell / (g.dim[2] * g.dim[1]) - g.L, cell < 0 ? -1 : (cell / g.dim[2]) % g.dim[1] - g.L, cell < 0 ? -1 : cell % g.dim[2] - g.L, g.nc[0], g.nc[1], g.nc[2]);
+    }
+    c->caps_skip = c->caps_cooldown ? (4 << std::min(c->caps_fails, 6)) : 0;
+    if (!c->caps_slack_env) c->caps_slack = std::min(32, c->caps_slack + 4);
     c->caps_fails++;
     return RXG_RETRY;
   }
@@ -666,7 +684,7 @@ int rxg_create(const rxg_config *cfg, rxg_handle *out) {
     const char *nc = getenv("RXG_NOCOUNT");
     c->caps_on = !(nc && nc[0] == '0');
     const char *sl = getenv("RXG_CAP_SLACK");
-    if (sl) c->caps_slack = std::max(0, atoi(sl));
+    if (sl) { c->caps_slack = std::max(0, atoi(sl)); c->caps_slack_env = true; }
     const char *cd = getenv("RXG_CAP_COOLDOWN");
     c->caps_cooldown = !(cd && cd[0] == '0');
     if (c->caps_on) {
@@ -1076,13 +1094,15 @@ int rxg_move(rxg_handle h, int *natoms, double *atype, double *pos, double *v, d
   // box).  Most steps nothing does: then the reference's MODE_MOVE only perturbs pos by its normalise/de-normalise round
   // trip, and 21 of the 28 per-atom planes of PCIe traffic are saved.
   bool full = false;
+  // RXG_HINT_CHARGES_STAY: the device's q / qs / qt are current and the host does not read them before the next QEq returns
+  const bool charges_stay = (hint & RXG_HINT_CHARGES_STAY) && n == c->natoms_prev_move;
   c->lazy_upload = [&]() -> int {
     RXG_TRY(h2d_planes(c, c->v, v, 3, n));
-    RXG_TRY(h2d_planes(c, c->q, q, 1, n));
+    if (!charges_stay) RXG_TRY(h2d_planes(c, c->q, q, 1, n));
     RXG_TRY(h2d_planes(c, c->qsfp, qsfp, 1, n));
     RXG_TRY(h2d_planes(c, c->qsfv, qsfv, 1, n));
     // qs/qt travel with the atom in the reference (src/comm.F90:164-171); the device keeps them packed
-    if (qs && qt && n > 0) {   // two planes into scratch, packed on the device (tmp is free until the compaction, which runs after the packs)
+    if (qs && qt && n > 0 && !charges_stay) {   // two planes into scratch, packed on the device (tmp is free until the compaction, which runs after the packs)
       double *sa = c->tmp + 13 * (size_t)c->NB, *sb = c->tmp + 14 * (size_t)c->NB;
       RXG_CUDA(cudaMemcpyAsync(sa, qs, sizeof(double) * n, cudaMemcpyHostToDevice, c->st));
       RXG_CUDA(cudaMemcpyAsync(sb, qt, sizeof(double) * n, cudaMemcpyHostToDevice, c->st));
@@ -1110,10 +1130,10 @@ int rxg_move(rxg_handle h, int *natoms, double *atype, double *pos, double *v, d
   if (full) {
     RXG_TRY(d2h_planes(c, atype, c->atype, 1, m));
     RXG_TRY(d2h_planes(c, v, c->v, 3, m));
-    RXG_TRY(d2h_planes(c, q, c->q, 1, m));
+    if (!charges_stay) RXG_TRY(d2h_planes(c, q, c->q, 1, m));
     RXG_TRY(d2h_planes(c, qsfp, c->qsfp, 1, m));
     RXG_TRY(d2h_planes(c, qsfv, c->qsfv, 1, m));
-    if (qs && qt && m > 0) {
+    if (qs && qt && m > 0 && !charges_stay) {
       double *sa = c->tmp, *sb = c->tmp + (size_t)c->NB;
       LAUNCH(c, k_pairs_to_planes, cdiv(m, 256), 256, 0, m, c->qst, sa, sb);
       RXG_CUDA(cudaMemcpyAsync(qs, sa, sizeof(double) * m, cudaMemcpyDeviceToHost, c->st));
@@ -1123,6 +1143,7 @@ int rxg_move(rxg_handle h, int *natoms, double *atype, double *pos, double *v, d
   }
   RXG_CUDA(cudaStreamSynchronize(c->st));
   *natoms = m;
+  c->natoms_prev_move = m;
   return RXG_OK;
 }
 

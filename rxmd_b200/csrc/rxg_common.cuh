@@ -172,8 +172,8 @@ struct Ctx {
   int2 *cnt_tab = nullptr;
   unsigned cnt_mask = 0;
   bool caps_on = true, caps_valid = false, list_capped = false;
-  bool caps_cooldown = true;
-  int caps_slack = 4, caps_skip = 0, caps_fails = 0;   // caps_skip: list builds that keep the count pass after an overflow
+  bool caps_cooldown = true, caps_slack_env = false;
+  int caps_slack = 8, caps_skip = 0, caps_fails = 0;   // caps_skip: list builds that keep the count pass after an overflow
   long long caps_overflows = 0;
   double *q_save = nullptr;   // [NB] charges at QEq entry, restored if a capped list overflows and the call starts over
   bool hess_fuse = false;   // RXG_HESS_FUSE=1: experiment, the hessian lerp inside the list's fill pass instead of k_hessian
@@ -184,6 +184,7 @@ struct Ctx {
   bool overlap = false, overlap_env = true;
   int *grp_cls = nullptr, *grp_off = nullptr, *grp_int = nullptr, *grp_bnd = nullptr;   // [NB/2+2] each
   int ngrp = 0, ngrp_int = 0, grp_rows = 0, stencil_reach = 0;
+  int natoms_prev_move = -1;   // residents after the last rxg_move / QEq (RXG_HINT_CHARGES_STAY is honoured only if the count still matches)
   int hint = 0;             // rxg_hint: the host's promises about the arrays of the next entry-point call
   bool pos_deferred = false;   // a hinted call skipped the copy-back of pos; the next un-hinted copy-back delivers it
   bool fuse = true, fuse_api = false, lists_shared = false;   // md_run: QEq builds halo + 10 A list once for QEq and FORCE of the same step

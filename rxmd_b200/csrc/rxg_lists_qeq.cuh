@@ -114,7 +114,7 @@ struct CntTab { int2 *tab; unsigned mask; const int *gid; };
 // (run r of the group = cells [g0 + z0_r, g0 + gl - 1 + z1_r] of column (c1 + dx_r, c2 + dy_r), clipped to the grid).  The fill
 // pass writes, next to the 32-bit slot column, the entry's position in its group's window (15 bits) with the ghost flag in bit
 // 15, and the exact length of every row by slot; `winmax` collects the largest window.
-struct WinOut { unsigned short *c16; int *rowlen; int *winmax; int G; };
+struct WinOut { unsigned short *c16; int *rowlen; const int2 *desc; int G; int park; };   // park: the 16-bit column rides in the parked value word, k_hessian stores it (coalesced)
 // bounds of stencil run `rr` for the cells [za, zb] of column (c1, c2): first slot and number of slots (0 if outside the grid)
 __device__ __forceinline__ void run_span(const DevGrid &g, int4 rr, int c1, int c2, int za, int zb, int &s, int &len) {
   s = 0; len = 0;
@@ -133,7 +133,7 @@ __device__ __forceinline__ void run_span(const DevGrid &g, int4 rr, int c1, int 
 // Window descriptors, written once per list build (k_win_desc): for group `grp` and stencil run r the pair
 //   { first slot of the run's span, (position in the window << 12) | number of slots },
 // and in entry [nruns] the window's total {0, total << 12}.  A span of more than 4095 slots marks the group as unfit (total = 2^19).
-__global__ void k_win_desc(DevGrid g, const int *__restrict__ runs, int nruns, int G, int ngroups, int2 *__restrict__ desc) {
+__global__ void k_win_desc(DevGrid g, const int *__restrict__ runs, int nruns, int G, int ngroups, int2 *__restrict__ desc, int *__restrict__ winmax) {
   const int lane = threadIdx.x & 31;
   const int grp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (grp >= ngroups) return;
@@ -158,12 +158,18 @@ __global__ void k_win_desc(DevGrid g, const int *__restrict__ runs, int nruns, i
     if (r < nruns) d[r] = make_int2(ws, (min(pos, 0x7ffff) << 12) | min(wlen, 4095));
     wcarry += __shfl_sync(0xffffffffu, winc, 31);
   }
-  if (lane == 0) d[nruns] = make_int2(0, ((unfit || wcarry > 0x7ffff) ? 0x7ffff : wcarry) << 12);
+  if (lane == 0) {
+    d[nruns] = make_int2(0, ((unfit || wcarry > 0x7ffff) ? 0x7ffff : wcarry) << 12);
+    if (wcarry > __ldcg(winmax)) atomicMax(winmax, wcarry);   // the largest window sizes the launches of k_spmv_win
+  }
 }
 
 __device__ __forceinline__ unsigned cnt_hash(int gid, unsigned mask) { return ((unsigned)gid * 2654435761u) & mask; }
+#ifndef RXG_PL_MINB
+#define RXG_PL_MINB 5   // resident CTAs per SM the fill pass is compiled for (48 registers; 64 without the cap)
+#endif
 template <int MODE, bool FILL, bool UNION, bool HFUSE = false, bool CAPPED = false>
-__global__ void __launch_bounds__(PL_WARPS * 32) k_pairlist(DevGrid g, const DevFF *__restrict__ ffp, const int *__restrict__ runs,
+__global__ void __launch_bounds__(PL_WARPS * 32, FILL ? RXG_PL_MINB : 1) k_pairlist(DevGrid g, const DevFF *__restrict__ ffp, const int *__restrict__ runs,
                                                             int nruns, int natoms, int ncell_res, int *__restrict__ slotcnt,
                                                             const long long *__restrict__ rowoff, long long *__restrict__ rowbeg,
                                                             long long *__restrict__ rowend, int *__restrict__ col,
@@ -186,8 +192,9 @@ __global__ void __launch_bounds__(PL_WARPS * 32) k_pairlist(DevGrid g, const Dev
   const int a0 = g.start[cid], a1 = g.start[cid + 1];
   if (a1 == a0) return;
   const float rctap2f = (float)ff.rctap2;
-  const bool win = wo.c16 != nullptr;   // both passes lay the window out (the count pass reports its size), the fill pass writes
-  const int wg0 = win ? (c3 / wo.G) * wo.G : 0, wg1 = win ? min(wg0 + wo.G, g.nc[2]) - 1 : 0;   // this cell's group (k_spmv_win)
+  const bool win = FILL && wo.c16 != nullptr;
+  // this cell's group (k_spmv_win) and its window descriptors (k_win_desc): run r starts at window position (d.y >> 12) with slot d.x
+  const int2 *wdesc = win ? wo.desc + (size_t)((c1 * g.nc[1] + c2) * ((g.nc[2] + wo.G - 1) / wo.G) + c3 / wo.G) * (nruns + 1) : nullptr;
   for (int ab = a0; ab < a1; ab += 32) {
     const int nb = min(32, a1 - ab);
     const int myslot = ab + lane;
@@ -198,6 +205,9 @@ __global__ void __launch_bounds__(PL_WARPS * 32) k_pairlist(DevGrid g, const Dev
     const bool mine = mi < natoms;           // a ghost inside a resident cell owns no row (cannot happen after MOVE)
     long long mybase = (FILL && lane < nb) ? rowoff[myslot] : 0;
     const int mycap = (CAPPED && lane < nb) ? (int)(rowoff[myslot + 1] - mybase) : 0;   // this row's capacity (k_row_caps)
+    // write positions travel through the warp as 32-bit offsets from the batch's first row (one shuffle per test instead of two)
+    const long long base0 = FILL ? __shfl_sync(0xffffffffu, mybase, 0) : 0;
+    const int myrel = (int)(mybase - base0);
     int mycnt = 0;
     // union stream of the CG SpMV (k_spmv_cells): per block of up to 8 consecutive rows of this cell, the candidates accepted
     // by at least one of them, in candidate order, with the 8-bit set of accepting rows.  ub* = running entry count of the
@@ -211,7 +221,6 @@ __global__ void __launch_bounds__(PL_WARPS * 32) k_pairlist(DevGrid g, const Dev
       if (nb > 24) uw3 = uoff[ab + 24];
     }
     int lastcol = ab;
-    int wcarry = 0;   // window position of the next run
     __syncwarp();
     for (int rb = 0; rb < nruns; rb += PL_MAXRUNS) {
       const int nr = min(PL_MAXRUNS, nruns - rb);
@@ -220,26 +229,20 @@ __global__ void __launch_bounds__(PL_WARPS * 32) k_pairlist(DevGrid g, const Dev
       int carry = 0;
       for (int r0 = 0; r0 < nr; r0 += 32) {
         const int r = r0 + lane;
-        int s = 0, len = 0, ws = 0, wlen = 0;
+        int s = 0, len = 0;
         if (r < nr) {
           const int4 rr = *reinterpret_cast<const int4 *>(runs + 4 * (rb + r));
           run_span(g, rr, c1, c2, c3, c3, s, len);
-          if (win) run_span(g, rr, c1, c2, wg0, wg1, ws, wlen);
+          if (win) { const int2 d = __ldg(wdesc + rb + r); sh_w[wid][r] = (d.y >> 12) - d.x; }
         }
-        int inc = len, winc = wlen;
+        int inc = len;
 #pragma unroll
         for (int o = 1; o < 32; o <<= 1) {
           int y = __shfl_up_sync(0xffffffffu, inc, o);
           if (lane >= o) inc += y;
-          if (win) {
-            int yw = __shfl_up_sync(0xffffffffu, winc, o);
-            if (lane >= o) winc += yw;
-          }
         }
         if (r < nr) { sh_s[wid][r] = s; sh_p[wid][r] = carry + inc - len; }
-        if (win && r < nr) sh_w[wid][r] = wcarry + winc - wlen - ws;
         carry += __shfl_sync(0xffffffffu, inc, 31);
-        if (win) wcarry += __shfl_sync(0xffffffffu, winc, 31);
       }
       if (lane == 0) sh_p[wid][nr] = carry;
       __syncwarp();
@@ -264,12 +267,14 @@ __global__ void __launch_bounds__(PL_WARPS * 32) k_pairlist(DevGrid g, const Dev
           const bool acc = have && (cslot != ab + a) && (MODE == 1 ? ((float)dr2 < rctap2f) : (dr2 <= ff.rctap2));
           const unsigned mask = __ballot_sync(0xffffffffu, acc);
           if (FILL) {
-            const long long wb = __shfl_sync(0xffffffffu, mybase + mycnt, a);
-            const long long wend = CAPPED ? __shfl_sync(0xffffffffu, mybase + mycap, a) : 0;
-            const long long w = wb + __popc(mask & ((1u << lane) - 1u));
-            if (acc && (!CAPPED || w < wend)) {
+            // one shuffle carries the row's write offset (20 bits) and, CAPPED, what is left of its capacity (12 bits, clamped:
+            // a step adds at most 32 entries)
+            const unsigned pk = __shfl_sync(0xffffffffu, (unsigned)(myrel + mycnt) | (CAPPED ? ((unsigned)min(max(mycap - mycnt, 0), 4095) << 20) : 0u), a);
+            const int before = __popc(mask & ((1u << lane) - 1u));
+            const long long w = base0 + (int)(pk & 0xfffffu) + before;
+            if (acc && (!CAPPED || before < (int)(pk >> 20))) {
               col[w] = cval;
-              if (win) wo.c16[w] = c16v;
+              if (win && !wo.park) wo.c16[w] = c16v;
               if (MODE >= 1) {
                 // the hessian lerp is evaluated by k_hessian over the compacted rows (full lanes); here only the
                 // fp32-rounded r^2 and the bond type are parked in the 8 bytes of the value slot
@@ -286,7 +291,7 @@ __global__ void __launch_bounds__(PL_WARPS * 32) k_pairlist(DevGrid g, const Dev
                   }
                   val[w] = h;
                 } else
-                  val[w] = __hiloint2double(inxn, __float_as_int((float)dr2));
+                  val[w] = __hiloint2double(max(inxn, 0) | ((win && wo.park) ? ((int)c16v << 16) : 0), __float_as_int((float)dr2));
               }
             }
           }
@@ -363,10 +368,7 @@ __global__ void __launch_bounds__(PL_WARPS * 32) k_pairlist(DevGrid g, const Dev
         }
       }
     }
-    if (win) {
-      if (FILL && lane < nb) wo.rowlen[myslot] = mine ? (CAPPED ? min(mycnt, mycap) : mycnt) : -1;
-      if (lane == 0 && ab == a0 && wcarry > __ldcg(wo.winmax)) atomicMax(wo.winmax, wcarry);
-    }
+    if (win && lane < nb) wo.rowlen[myslot] = mine ? (CAPPED ? min(mycnt, mycap) : mycnt) : -1;
     if (!FILL || CAPPED) {   // exact entry count (without row padding): the algorithmic-bytes figure of the roofline uses it;
                              // longest row: picks the SpMV launch shape
       const int real = __reduce_add_sync(0xffffffffu, (lane < nb && mine) ? mycnt : 0);
@@ -381,7 +383,10 @@ __global__ void __launch_bounds__(PL_WARPS * 32) k_pairlist(DevGrid g, const Dev
         int kept = mycnt;
         if (CAPPED) {
           if (mycnt > maxrow) atomicMax(ovf, mycnt);               // the MAXNEIGHBS10 trap, checked by the host with the overflow flag
-          if (mycnt > mycap) { atomicExch(ovf + 20, 1); kept = mycap; }   // the row outgrew last step's count + slack: the host rebuilds
+          if (mycnt > mycap) {   // the row outgrew last step's count + slack: the host rebuilds (ovf[22..25]: one such row, for diagnostics)
+            if (atomicExch(ovf + 20, 1) == 0) { ovf[22] = ct.gid[mi]; ovf[23] = mycnt; ovf[24] = mycap; ovf[25] = mi; }
+            kept = mycap;
+          }
         }
         rowbeg[mi] = mybase;
         rowend[mi] = mybase + kept;
@@ -406,13 +411,15 @@ __global__ void __launch_bounds__(PL_WARPS * 32) k_pairlist(DevGrid g, const Dev
 
 // D1: hessian(j1,i) = (1-drtb)*TBL_Eclmb_QEq(itb,inxn) + drtb*TBL_Eclmb_QEq(itb+1,inxn) with real(4) dr2 (src/qeq.F90:234-240).
 // One warp per row, lanes stride over the compacted entries; reads {float r^2, inxn} parked by k_pairlist.
-__global__ void __launch_bounds__(256) k_hessian(long long nnz, const DevFF *__restrict__ ffp, double *__restrict__ val) {
+__global__ void __launch_bounds__(256) k_hessian(long long nnz, const DevFF *__restrict__ ffp, double *__restrict__ val, unsigned short *__restrict__ c16) {
   // flat over the padded entry range: row padding carries inxn = 0 (written by k_pairlist), which yields 0
   const DevFF &ff = *ffp;
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long k = (long long)blockIdx.x * blockDim.x + threadIdx.x; k < nnz; k += stride) {
     const double packed = val[k];
-    const int inxn = __double2hiint(packed);
+    const int hi = __double2hiint(packed);
+    const int inxn = hi & 0xffff;
+    if (c16) c16[k] = (unsigned short)((unsigned)hi >> 16);   // the window-relative column parked beside the bond type (k_spmv_win)
     const double d2 = (double)__int_as_float(__double2loint(packed));   // real(4) dr2 promoted back
     const int itb = (int)mul_rn(d2, ff.UDRi);
     const double drtb = mul_rn(sub_rn(d2, mul_rn((double)itb, ff.UDR)), ff.UDRi);
@@ -478,6 +485,7 @@ inline int build_nbrlist(Ctx *c) {
 template <int MODE>
 int build_pairlist(Ctx *c, bool hessian = true, bool allow_capped = false) {
   const int n = c->natoms, nt = c->cp[6];
+  if (c->cfg.maxneighbs10 > 32000) { c->err = "MAXNEIGHBS10 above 32000 is not supported (20-bit row offsets in the list's fill pass)"; return RXG_ERR_ARG; }
   RXG_CUDA(cudaMemsetAsync(c->d_flag, 0, sizeof(int), c->st));
   RXG_CUDA(cudaMemsetAsync(c->d_flag + 16, 0, sizeof(int), c->st));
   RXG_CUDA(cudaMemsetAsync(c->d_acc + 33, 0, sizeof(double), c->st));
@@ -499,11 +507,11 @@ int build_pairlist(Ctx *c, bool hessian = true, bool allow_capped = false) {
   // window SpMV: the fill pass also writes the 16-bit window-relative columns and the row lengths by slot
   const bool win_on = MODE >= 1 && c->spmv_kind == 2 && !c->strict;
   WinOut wo;
-  wo.c16 = nullptr; wo.rowlen = c->rowlen; wo.winmax = c->d_flag + 21; wo.G = 1;
+  wo.c16 = nullptr; wo.rowlen = c->rowlen; wo.desc = nullptr; wo.G = 1; wo.park = 0;
   if (win_on) {
     if (c->win_g <= 0) c->win_g = win_pick_group(c);
     wo.G = c->win_g;
-    wo.c16 = c->col16 ? c->col16 : (unsigned short *)c->rowlen;   // count pass before the first allocation: any non-null pointer (it only lays the window out)
+    wo.c16 = c->col16;   // (allocated with col / val below, before the fill pass)
     // window descriptors of every group (k_spmv_win reads them instead of redoing the layout in every CTA of every product)
     const int ngroups = c->gnb.nc[0] * c->gnb.nc[1] * cdiv(c->gnb.nc[2], wo.G);
     const size_t need = (size_t)ngroups * (size_t)(c->nruns + 1);
@@ -512,7 +520,8 @@ int build_pairlist(Ctx *c, bool hessian = true, bool allow_capped = false) {
       c->win_desc_cap = need + need / 8;
       RXG_CUDA(cudaMalloc(&c->win_desc, sizeof(int2) * c->win_desc_cap));
     }
-    LAUNCH(c, k_win_desc, cdiv((long long)ngroups * 32, 256), 256, 0, c->gnb, c->d_runs, c->nruns, wo.G, ngroups, c->win_desc);
+    LAUNCH(c, k_win_desc, cdiv((long long)ngroups * 32, 256), 256, 0, c->gnb, c->d_runs, c->nruns, wo.G, ngroups, c->win_desc, c->d_flag + 21);
+    wo.desc = c->win_desc;
   }
   c->win_built = false;
 #define RXG_PL_ARGS c->gnb, c->d_ff, c->d_runs, c->nruns, n, ncell_res, c->rowcnt, c->rowoff, c->rowbeg, c->rowend, c->col, c->val, c->cfg.maxneighbs10,   \
@@ -544,7 +553,7 @@ int build_pairlist(Ctx *c, bool hessian = true, bool allow_capped = false) {
   if (win_on) {
     if (!c->col16) RXG_CUDA(cudaMalloc(&c->col16, sizeof(unsigned short) * c->nnz_cap));
     wo.c16 = c->col16;
-    if (!capped) c->win_max = c->h_int[21];   // (capped: the fill pass reports it, check_capped_flags reads it)
+    if (!capped) c->win_max = c->h_int[21];   // (capped: check_capped_flags reads it with the list's other flags)
   }
   const long long nun = un_on ? *(long long *)(c->h_acc + 34) : 0;
   if (nun > c->un_cap) {
@@ -565,6 +574,7 @@ int build_pairlist(Ctx *c, bool hessian = true, bool allow_capped = false) {
   c->spmv_rg = c->maxrow <= 480 ? 4 : 2;
   RXG_CUDA(cudaMemsetAsync(c->d_flag + 17, 0, sizeof(int), c->st));
   const bool hfuse = MODE >= 1 && hessian && c->hess_fuse && !un_on && !capped;
+  wo.park = (win_on && hessian && !hfuse) ? 1 : 0;
   if (capped) LAUNCH(c, (k_pairlist<MODE, true, false, false, (MODE >= 1)>), grid, PL_WARPS * 32, 0, RXG_PL_ARGS, c->spmv_rg, ct, wo);
   else if (un_on) LAUNCH(c, (k_pairlist<MODE, true, (MODE >= 1)>), grid, PL_WARPS * 32, 0, RXG_PL_ARGS, c->spmv_rg, ct, wo);
   else if (hfuse) LAUNCH(c, (k_pairlist<MODE, true, false, (MODE >= 1)>), grid, PL_WARPS * 32, 0, RXG_PL_ARGS, c->spmv_rg, ct, wo);
@@ -573,7 +583,7 @@ int build_pairlist(Ctx *c, bool hessian = true, bool allow_capped = false) {
 #undef RXG_PL_ARGS
   if (MODE >= 1 && c->cnt_tab) c->caps_valid = true;
   if (MODE >= 1 && hessian && !hfuse)
-    LAUNCH(c, k_hessian, 148 * 16, 256, 0, nnz, c->d_ff, c->val);
+    LAUNCH(c, k_hessian, 148 * 16, 256, 0, nnz, c->d_ff, c->val, wo.park ? c->col16 : (unsigned short *)nullptr);
   c->nitems = un_on ? -1 : 0;   // read back with the CG's first synchronisation (spmv_launch)
   return RXG_OK;
 }

@@ -52,7 +52,8 @@ type(c_ptr), save :: rxg_handle = c_null_ptr
 ! set .true. by the host right before its main loop (src/main.F90:47) and .false. after it: inside the loop the wrappers below
 ! tell the library which arrays it already holds (rxg_hint), so pos crosses PCIe once up and once down per step
 logical, save :: rxg_loop_hints = .false.
-integer(c_int), parameter :: RXG_HINT_ATOMS_ON_DEVICE = 1, RXG_HINT_Q_ON_DEVICE = 2, RXG_HINT_DEFER_POS = 4
+integer(c_int), parameter :: RXG_HINT_ATOMS_ON_DEVICE = 1, RXG_HINT_Q_ON_DEVICE = 2, RXG_HINT_DEFER_POS = 4, &
+                             RXG_HINT_CHARGES_STAY = 8
 
 interface
    integer(c_int) function rxg_create(cfg, h) bind(C, name="rxg_create")
@@ -233,13 +234,20 @@ implicit none
 integer, intent(in) :: imode
 real(8), intent(in) :: dr(3)
 real(8) :: atype(NBUFFER), q(NBUFFER), pos(NBUFFER,3), v(NBUFFER,3), f(NBUFFER,3)
+integer(c_int) :: ihint
 if (imode /= MODE_MOVE) then
    print'(a,i3)', "ERROR: imode doesn't match in COPYATOMS: ", imode    ! the other modes run inside the library
    call MPI_FINALIZE(ierr); stop
 endif
 if (isPQEq) call rxg_check(rxg_spos_upload(rxg_handle, NATOMS, spos))      ! spos migrates with the atom (src/comm.F90:153,165-167)
 ! in a step without output the host does not read pos before FORCE returns it: leave the ulp-level round trip on the device
-if (rxg_loop_hints .and. mod(nstep, fstep) /= 0) call rxg_check(rxg_hint(rxg_handle, RXG_HINT_DEFER_POS))
+! inside the main loop nothing reads or writes q, qs, qt between the QEq of one step and the QEq of the next except the
+! charge-Lagrangian lines, which read q AFTER this call's QEq returned it (src/main.F90:64-98): they migrate on the device
+! (only in steps whose QEq runs, mod(nstep,qstep)==0: otherwise the host's q must follow the migration)
+ihint = 0
+if (rxg_loop_hints .and. mod(nstep, fstep) /= 0) ihint = ihint + RXG_HINT_DEFER_POS
+if (rxg_loop_hints .and. mod(nstep, qstep) == 0) ihint = ihint + RXG_HINT_CHARGES_STAY
+if (ihint /= 0) call rxg_check(rxg_hint(rxg_handle, ihint))
 call rxg_check(rxg_move(rxg_handle, NATOMS, atype, pos, v, q, qs, qt, qsfp, qsfv))
 if (isPQEq) call rxg_check(rxg_spos_download(rxg_handle, NATOMS, spos))
 end subroutine

@@ -29,6 +29,9 @@ def build_config(name, mc=None, nranks=1, strong=False, sigma=0.02, only_rank=No
     """-> (System, total replication, vprocs, cfg_kwargs, label)."""
     c = dict(CONFIGS[name])
     vp = VPROCS[nranks]
+    if os.environ.get("RXG_BENCH_VPROCS"):      # diagnostics: another decomposition of the same rank count, e.g. "1,1,2"
+        vp = tuple(int(x) for x in os.environ["RXG_BENCH_VPROCS"].split(","))
+        assert vp[0] * vp[1] * vp[2] == nranks
     mc = tuple(mc) if mc is not None else c["mc"]
     if strong:
         tot = mc          # atoms go to ranks by position (init/geninit.F90:495-500): the replication need not divide by vprocs

@@ -21,7 +21,7 @@ import numpy as np
 from .binding import RxgConfig, RxgFF, RxgBox
 
 MODE_COPY, MODE_MOVE, MODE_CPBK, MODE_QCOPY1, MODE_QCOPY2 = 1, 2, 3, 4, 5   # src/module.F90:38-39
-HINT_ATOMS_ON_DEVICE, HINT_Q_ON_DEVICE, HINT_DEFER_POS = 1, 2, 4             # include/rxmd_b200.h (rxg_hint)
+HINT_ATOMS_ON_DEVICE, HINT_Q_ON_DEVICE, HINT_DEFER_POS, HINT_CHARGES_STAY = 1, 2, 4, 8   # include/rxmd_b200.h (rxg_hint)
 
 _LIB = None
 
