@@ -295,6 +295,9 @@ def main():
                     "cells_per_group": int(t_after[27]) if win else None, "largest_window_entries": int(t_after[28]) if win else None,
                     "avg_launch_ms": d[10] / d[11], "launches_timed": int(d[11]),
                     "step_share": d[10] / max(t_after[3] - t_before[3], 1e-9)}
+        # `frac` is quoted on the ALGORITHMIC bytes (12 B per entry); k_spmv_win moves 10 B per entry (16-bit columns),
+        # so the fraction of the peak its actual stream reaches is stated next to it
+        roofline["frac_on_bytes_moved"] = roofline["stream_bytes_per_launch"] / (roofline["avg_launch_ms"] * 1e-3) / 1e9 / peak
 
     # ---------------- e2e through the reference-facing entry points with pinned host arrays
     e2e = None
