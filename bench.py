@@ -98,6 +98,39 @@ def host_cores():
     return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
 
 
+def bind_rank_to_gpu_cores(local, world):
+    """One rank per GPU on one node: give each rank the share of the host cores that sits next to ITS GPU (what a launch
+    script does with numactl for the Fortran host).  The cores the driver reports as local to the GPU (NVML) are intersected
+    with the cores this process may use and split evenly among the ranks whose GPUs share them; pinned buffers allocated
+    afterwards land on that NUMA node.  Returns the cores taken, or None when the topology is not available."""
+    if world <= 1 or not hasattr(os, "sched_setaffinity"):
+        return None
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        allowed = sorted(os.sched_getaffinity(0))
+        ncpu = os.cpu_count() or 1
+        words = (ncpu + 63) // 64
+
+        def local_set(dev):
+            mask = pynvml.nvmlDeviceGetCpuAffinity(pynvml.nvmlDeviceGetHandleByIndex(dev), words)
+            cores = [64 * w + b for w, m in enumerate(mask) for b in range(64) if (int(m) >> b) & 1]
+            return tuple(c for c in cores if c in set(allowed))
+        sets = [local_set(d) for d in range(world)]
+        mine = sets[local]
+        if not mine:
+            return None
+        peers = [d for d in range(world) if sets[d] == mine]          # ranks whose GPUs hang off the same cores
+        k = peers.index(local)
+        share = [c for j, c in enumerate(mine) if j * len(peers) // len(mine) == k]
+        if not share:
+            return None
+        os.sched_setaffinity(0, share)
+        return share
+    except Exception:
+        return None
+
+
 def cpu_sample(config, mc, steps, warmup, sigma, budget_s=None):
     """The CPU restatement of the reference (oracle/, OpenMP) on a bounded sample of the same workload, on all the host
     cores this process may use (the team size is set explicitly: launchers such as torch.distributed.run export
@@ -196,6 +229,7 @@ def main():
         if world == 1 and args.gpus > 1:
             raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
     torch.cuda.set_device(local)
+    bound = bind_rank_to_gpu_cores(local, world)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -318,7 +352,7 @@ def main():
         # the host integrator (the Fortran driver's O(N) loops, src/main.F90:64-72,86-98) as compiled loops
         import numba
         # one rank per GPU shares the host's cores: give each rank's integrator its share instead of a full-size thread pool
-        numba.set_num_threads(max(1, min(numba.config.NUMBA_NUM_THREADS, host_cores() // max(world, 1))))
+        numba.set_num_threads(max(1, min(numba.config.NUMBA_NUM_THREADS, len(bound) if bound else host_cores() // max(world, 1))))
 
         @numba.njit(parallel=True, cache=False)
         def first_half(n, dt, lw2, dthm_t, atype, v, f, q, qsfp, qsfv, pos):
@@ -377,7 +411,8 @@ def main():
                "d2h_bytes_per_step": int(d2h / ksteps), "steps": ksteps, "ms_per_step": t_e2e / ksteps * 1e3,
                "api": f"Engine.COPYATOMS(MODE_MOVE) + Engine.{'PQEq' if pq else 'QEq'} + Engine.FORCE over rxg_move/rxg_{'pqeq' if pq else 'qeq'}/rxg_force, "
                       "pinned host arrays, host integrator",
-               "host_threads_per_rank": int(numba.get_num_threads()), "force_calls_reusing_qeq_list": int(ta[22] - tb[22]),
+               "host_threads_per_rank": int(numba.get_num_threads()), "host_cores_bound_to_gpu": (len(bound) if bound else None),
+               "force_calls_reusing_qeq_list": int(ta[22] - tb[22]),
                "ms_per_step_by_call": dict(zip(["host first half", "COPYATOMS(MOVE)", "QEq", "FORCE", "host second half"],
                                                [round(float(x) / ksteps * 1e3, 3) for x in e2e_parts]))}
 

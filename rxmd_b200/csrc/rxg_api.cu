@@ -674,7 +674,8 @@ int rxg_create(const rxg_config *cfg, rxg_handle *out) {
     RXG_TRY(dalloc(c, &c->spos, 3 * NB)); RXG_TRY(dalloc(c, &c->sps, NB)); RXG_TRY(dalloc(c, &c->prow, NB));
     RXG_TRY(dalloc(c, &c->pcs, NB)); RXG_TRY(dalloc(c, &c->qsl, NB));
   }
-  RXG_TRY(dalloc(c, &c->xs, NB)); RXG_TRY(dalloc(c, &c->pqa, NB)); RXG_TRY(dalloc(c, &c->pqs, NB)); RXG_TRY(dalloc(c, &c->tgs, NB));
+  RXG_TRY(dalloc(c, &c->xs, NB)); RXG_TRY(dalloc(c, &c->pqa, NB)); RXG_TRY(dalloc(c, &c->pqs, NB)); RXG_TRY(dalloc(c, &c->tgs, NB)); RXG_TRY(dalloc(c, &c->gts, NB));
+  { const char *eq = getenv("RXG_ENBOND_QUEUE"); c->enbond_queue = !(eq && eq[0] == '0'); }
   RXG_TRY(dalloc(c, &c->nbrcnt, NB)); RXG_TRY(dalloc(c, &c->nbrpad, NS)); RXG_TRY(dalloc(c, &c->bptr, NB + 2));
   RXG_TRY(dalloc(c, &c->rowoff, NB + 2)); RXG_TRY(dalloc(c, &c->rowbeg, NB + 2)); RXG_TRY(dalloc(c, &c->rowend, NB + 2));
   RXG_TRY(dalloc(c, &c->rowcnt, NB + 2)); RXG_TRY(dalloc(c, &c->ucnt, NB + 2)); RXG_TRY(dalloc(c, &c->uoff, NB + 2));

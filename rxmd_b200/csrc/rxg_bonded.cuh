@@ -172,7 +172,7 @@ __device__ __forceinline__ void atomic_add3(double *__restrict__ f, int NB, int 
 // (non-bonded kernels: the neighbours of a stencil run are contiguous slots)
 __global__ void k_pack_pq(int ntot, const double *__restrict__ pos, int NB, const double *__restrict__ q,
                           const int *__restrict__ itype, const int *__restrict__ gid, const int *__restrict__ slot_of,
-                          double4 *__restrict__ pqa, double4 *__restrict__ pqs, int4 *__restrict__ tgs) {
+                          double4 *__restrict__ pqa, double4 *__restrict__ pqs, int4 *__restrict__ tgs, int2 *__restrict__ gts) {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= ntot) return;
   double4 p = make_double4(pos[i], pos[NB + i], pos[2 * (size_t)NB + i], q[i]);
@@ -180,6 +180,7 @@ __global__ void k_pack_pq(int ntot, const double *__restrict__ pos, int NB, cons
   int s = slot_of[i];
   pqs[s] = p;
   tgs[s] = make_int4(itype[i], gid[i], i, 0);
+  gts[s] = make_int2(gid[i], itype[i]);   // the 8 bytes the half-list test of k_enbond_half gathers per list entry
 }
 
 // C6: ENbond, src/pot.F90:676-781.  One warp per resident row of the 10 A list.
@@ -243,6 +244,82 @@ __global__ void __launch_bounds__(256) k_enbond(int ntot, int natoms, const long
   }
   block_add<3>(part, acc + ACC_PE + 11);
   if (!HALF) block_add<6>(vir, acc + ACC_ASTR);
+}
+
+// The literal half-list form of ENbond (gid(j) < gid(i), partner forces scattered), as the production path runs it.
+// k_enbond<true> tests `lower` per list entry and lets the ~50 % of lanes that fail idle through the expensive part (a 32-byte
+// position gather, two 32-byte table-node gathers, ~40 fp64 operations, three reductions): a latency chain of four dependent
+// gathers per 32 entries for 16 useful pairs.  Here the test reads 8 bytes per entry ({gid, type} by slot, nearly contiguous),
+// survivors queue up in shared memory (ring of 64 per warp, partner slot | type << 26) and the expensive part runs on full
+// warps of them.  Same pairs, same arithmetic per pair; only the order in which a row's pair forces are summed changes.
+__global__ void __launch_bounds__(256) k_enbond_half(int ntot, int natoms, const long long *__restrict__ rowbeg,
+                                                     const long long *__restrict__ rowend, const int *__restrict__ col,
+                                                     const double4 *__restrict__ pqs, const int4 *__restrict__ tgs,
+                                                     const int2 *__restrict__ gts, const DevFF *__restrict__ ffp,
+                                                     double *__restrict__ f, double *__restrict__ fsl, int NB, double *__restrict__ acc) {
+  __shared__ int sh_q[8][64];
+  const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+  const int slot = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;   // rows are walked in cell order
+  double part[3] = {0.0, 0.0, 0.0};
+  int4 ti = make_int4(0, 0, natoms, 0);
+  if (slot < ntot) ti = tgs[slot];
+  const int i = ti.z;
+  if (i < natoms) {
+    const DevFF &ff = *ffp;
+    const double4 pi = pqs[slot];
+    double fx = 0, fy = 0, fz = 0;
+    int qh = 0, qn = 0;   // ring state, identical on every lane
+    auto eval = [&](bool full) {
+      if (full || lane < qn) {
+        const unsigned e = (unsigned)sh_q[wid][(qh + lane) & 63];
+        const int js = (int)(e & 0x3ffffffu), tjx = (int)(e >> 26);
+        const double4 pj = ldg256(pqs + js);
+        const double dx = sub_rn(pi.x, pj.x), dy = sub_rn(pi.y, pj.y), dz = sub_rn(pi.z, pj.z);
+        const double dr2 = dist2_rn(dx, dy, dz);
+        const int inxn = ff.inxn2[(ti.x - 1) + ff.nso * (tjx - 1)];
+        const int itb = (int)mul_rn(dr2, ff.UDRi);
+        // (out of bounds in the reference)
+        if (dr2 <= ff.rctap2 && inxn > 0 && itb >= 1 && itb + 1 <= ff.ntable) {
+          const double drtb = mul_rn(sub_rn(dr2, mul_rn((double)itb, ff.UDR)), ff.UDRi);
+          const double drtb1 = 1.0 - drtb;
+          const double4 *T = ff.TBL_nb + (size_t)(inxn - 1) * ff.ntable + (itb - 1);
+          const double4 T0 = ldg256(T), T1 = ldg256(T + 1);
+          const double qij = pi.w * pj.w;
+          const double PEvdw = drtb1 * T0.x + drtb * T1.x;
+          const double CEvdw = drtb1 * T0.y + drtb * T1.y;
+          const double PEclmb = (drtb1 * T0.z + drtb * T1.z) * qij;
+          const double CEclmb = (drtb1 * T0.w + drtb * T1.w) * qij;
+          part[0] += PEvdw; part[1] += PEclmb;
+          const double cc = CEvdw + CEclmb;
+          fx -= cc * dx; fy -= cc * dy; fz -= cc * dz;
+          // the partner's share goes to the SLOT-ordered accumulator (k_fsl_to_f folds it into f)
+          atomic_add3(fsl, NB, js, cc * dx, cc * dy, cc * dz);
+        }
+      }
+      __syncwarp();
+    };
+    const long long s = rowbeg[i], e = rowend[i];
+    for (long long k0 = s; k0 < e; k0 += 32) {
+      const long long k = k0 + lane;
+      const bool in = k < e;
+      const int js = in ? (__ldcs(col + k) & COL_MASK) : 0;
+      int2 gt = make_int2(0, 0);
+      if (in) gt = gts[js];
+      const bool lower = in && gt.x < ti.y;
+      const unsigned m = __ballot_sync(0xffffffffu, lower);
+      if (lower) sh_q[wid][(qh + qn + __popc(m & ((1u << lane) - 1u))) & 63] = js | (gt.y << 26);
+      qn += __popc(m);
+      __syncwarp();
+      if (qn >= 32) { eval(true); qh = (qh + 32) & 63; qn -= 32; }
+    }
+    if (qn > 0) eval(false);
+    fx = warp_sum(fx); fy = warp_sum(fy); fz = warp_sum(fz);
+    if (lane == 0) {
+      atomic_add3(f, NB, i, fx, fy, fz);
+      part[2] = CECHRGE * (ff.chi[ti.x - 1] * pi.w + 0.5 * ff.eta[ti.x - 1] * pi.w * pi.w);   // src/pot.F90:708
+    }
+  }
+  block_add<3>(part, acc + ACC_PE + 11);
 }
 
 // Elnpr preparation loop, src/pot.F90:183-209 (all atoms)
@@ -1077,7 +1154,7 @@ inline int force_device(Ctx *c, bool reuse = false) {
   }
   double4 *pq = c->pqa;
   phase_mark(c, 7);                                             // ENbond
-  LAUNCH(c, k_pack_pq, cdiv(nt, 256), 256, 0, nt, c->pos, NB, c->q, c->itype, c->gid, c->gnb.slot_of, c->pqa, c->pqs, c->tgs);
+  LAUNCH(c, k_pack_pq, cdiv(nt, 256), 256, 0, nt, c->pos, NB, c->q, c->itype, c->gid, c->gnb.slot_of, c->pqa, c->pqs, c->tgs, c->gts);
   // the full-row form needs every partner's image inside this rank's halo: true when the FORCE halo >= rctap
   bool full_ok = true;
   const double lat[3] = {c->box.lata, c->box.latb, c->box.latc};
@@ -1094,7 +1171,11 @@ inline int force_device(Ctx *c, bool reuse = false) {
     LAUNCH(c, k_enbond_pqeq, ogrid, 256, 0, nt, n, c->rowbeg, c->rowend, c->col, c->pqs, c->tgs, c->sps, c->d_ff, c->f, c->fsl, NB, c->d_acc);
     if (c->cfg.isEfield && n > 0)   // :61
       LAUNCH(c, k_efield, cdiv(n, 256), 256, 0, n, c->q, c->itype, c->d_ff, c->cfg.eFieldDir, c->cfg.eFieldStrength, c->f, NB);
-  } else if (!full_ok) LAUNCH(c, (k_enbond<true>), ogrid, 256, 0, nt, n, c->rowbeg, c->rowend, c->col, c->pqs, c->tgs, c->d_ff, c->f, c->fsl, NB, c->d_acc);
+  } else if (!full_ok) {
+    if (c->enbond_queue && NB < (1 << 26) && c->ff.nso < 32)
+      LAUNCH(c, k_enbond_half, ogrid, 256, 0, nt, n, c->rowbeg, c->rowend, c->col, c->pqs, c->tgs, c->gts, c->d_ff, c->f, c->fsl, NB, c->d_acc);
+    else LAUNCH(c, (k_enbond<true>), ogrid, 256, 0, nt, n, c->rowbeg, c->rowend, c->col, c->pqs, c->tgs, c->d_ff, c->f, c->fsl, NB, c->d_acc);
+  }
   phase_mark(c, 9);                                             // Elnpr (preparation loop)
   LAUNCH(c, k_elnpr_prep, cdiv(nt, 256), 256, 0, nt, c->itype, c->d_ff, c->delta, c->nlp, c->dDlp, c->deltalp);
   phase_mark(c, 8);                                             // Ebond (one kernel with Elnpr's main loop)

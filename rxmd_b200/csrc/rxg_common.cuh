@@ -194,6 +194,8 @@ struct Ctx {
   double4 *pqa = nullptr;   // [NB] {x,y,z,q} by atom (bonded kernels)
   double4 *pqs = nullptr;   // [NB] {x,y,z,q} by slot (non-bonded gathers)
   int4 *tgs = nullptr;      // [NB] {itype, gid, atom index, -} by slot
+  int2 *gts = nullptr;      // [NB] {gid, itype} by slot (k_enbond_half)
+  bool enbond_queue = true; // RXG_ENBOND_QUEUE=0: k_enbond<true> (no survivor compaction)
   // ---- cells -------------------------------------------------------------------------------------------
   DevGrid gb, gnb;
   int *d_runs = nullptr;    // stencil runs {dx,dy,dzlo,dzhi}
