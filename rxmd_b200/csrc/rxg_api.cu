@@ -622,6 +622,8 @@ int rxg_create(const rxg_config *cfg, rxg_handle *out) {
     c->win_u = wu ? atoi(wu) : 0;   // 0: from the average row length (spmv_launch)
     if (c->win_u != 4 && c->win_u != 8 && c->win_u != 13) c->win_u = 0;
     c->win_smem_target = wsm ? std::max(4096, atoi(wsm)) : 64 * 1024;
+    const char *wra = getenv("RXG_WIN_RALIGN");
+    if (wra && (atoi(wra) == 4 || atoi(wra) == 8 || atoi(wra) == 16)) c->win_ralign = atoi(wra);
     const char *wc = getenv("RXG_WIN_WCAP");
     c->win_wcap_env = wc ? atoi(wc) : 0;
   }

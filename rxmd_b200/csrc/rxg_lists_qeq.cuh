@@ -496,7 +496,7 @@ int build_pairlist(Ctx *c, bool hessian = true, bool allow_capped = false) {
   RXG_CUDA(cudaMemsetAsync(c->rowend, 0, sizeof(long long) * (size_t)n, c->st));
   const int ncell_res = c->gnb.nc[0] * c->gnb.nc[1] * c->gnb.nc[2];
   const int grid = cdiv((long long)ncell_res * 32, PL_WARPS * 32);
-  const int ralign = 4;
+  const int ralign = (MODE >= 1 && c->spmv_kind == 2 && !c->strict) ? c->win_ralign : 4;   // (RXG_WIN_RALIGN=16 puts the rows of k_spmv_win on 128-byte boundaries of the value stream: measured, no gain)
   CntTab ct;
   ct.tab = MODE >= 1 ? c->cnt_tab : nullptr; ct.mask = c->cnt_mask; ct.gid = c->gid;
   // no count pass when last step's counts are on record (QEq lists of the production path only)
@@ -948,13 +948,17 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_spmv_win(DevGrid g, int nruns
   // issues the copies of the runs r = w (mod NW): a bulk copy takes uniform operands, so a warp issues its copies one lane at
   // a time.
   const int2 *d = desc + (size_t)blockIdx.x * (nruns + 1);
+  // (this lane's first descriptor is requested together with the window's total, not after the decision that depends on it)
+  const int r_first = wid + NW * lane;
+  int2 e_first = make_int2(0, 0);
+  if (r_first < nruns) e_first = __ldg(d + r_first);
   const int tot = __ldg(&d[nruns].y) >> 12;
   const bool staged = tot <= wcap && tot <= 32768;
   {
     unsigned issued = 0;
     if (staged && cg_done == 0.0) {
-      for (int r = wid + NW * lane; r < nruns; r += NW * 32) {
-        const int2 e = __ldg(d + r);
+      for (int r = r_first; r < nruns; r += NW * 32) {
+        const int2 e = r == r_first ? e_first : __ldg(d + r);
         const int wlen = e.y & 0xfff, pos = e.y >> 12;
         if (wlen > 0) {
           bulk_g2s(s_x + pos, x + e.x, (unsigned)wlen * 16u, &bar);

@@ -68,7 +68,7 @@ def rows(e, n):
 @pytest.fixture(autouse=True)
 def _clean_env():
     keys = ("RXG_STRICT_ORDER", "RXG_QEQ_TWOPASS", "RXG_FUSE_API", "RXG_NO_FUSE", "RXG_SPMV", "RXG_SPMV_SHAPE", "RXG_SPMV_STAGE", "RXG_SPMV_RING",
-            "RXG_WIN_G", "RXG_WIN_WARPS", "RXG_WIN_WCAP", "RXG_WIN_SMEM")
+            "RXG_WIN_G", "RXG_WIN_WARPS", "RXG_WIN_WCAP", "RXG_WIN_SMEM", "RXG_ENBOND_QUEUE")
     for k in keys:
         os.environ.pop(k, None)
     yield
@@ -157,6 +157,26 @@ def test_production_cg_follows_oracle_iterates(built, name, spmv):
         e.close(); o.close()
         assert worst[k] <= bar, (k, worst[k])
     print(f"{name} [{spmv}]: max |dq| after k iterations: " + ", ".join(f"{k}: {d:.1e}" for k, d in worst.items()))
+
+
+def test_enbond_half_list_forms_agree(built):
+    """k_enbond_half (production: the half-list test on 8-byte records, survivors compacted so that the table gathers run on
+    full warps) against k_enbond<true> (RXG_ENBOND_QUEUE=0: one lane per list entry): the same pairs and the same arithmetic
+    per pair, so forces and energies agree to summation order; both are compared with the oracle by the tests above."""
+    out = {}
+    for queue in ("1", "0"):
+        os.environ["RXG_ENBOND_QUEUE"] = queue
+        s, cfg, e, o = make("rdx_2x2x2_disp", NMAXQEq=4)
+        o.close()
+        atype, pos, v, f, q = e.host_arrays(s.ranks[0])
+        n = e.NATOMS
+        e.QEq(atype, pos, q)
+        e.FORCE(atype, pos, f, q)
+        out[queue] = (f[:, :n].copy(), e.PE.copy())
+        e.close()
+    os.environ.pop("RXG_ENBOND_QUEUE", None)
+    assert np.abs(out["1"][0] - out["0"][0]).max() <= 1e-12 * np.abs(out["0"][0]).max()
+    assert np.abs(out["1"][1] - out["0"][1]).max() <= 1e-12 * np.abs(out["0"][1]).max()
 
 
 @pytest.mark.parametrize("name", ["rdx_2x2x2_disp", "water_4x3x3_disp"])
