@@ -340,7 +340,7 @@ constexpr int RXG_RETRY = 100;
 int copy_capped_flags(Ctx *c) {
   if (!c->list_capped) return RXG_OK;
   RXG_CUDA(cudaMemcpyAsync(c->h_int + 20, c->d_flag + 20, sizeof(int), cudaMemcpyDeviceToHost, c->st));
-  RXG_CUDA(cudaMemcpyAsync(c->h_int, c->d_flag, sizeof(int), cudaMemcpyDeviceToHost, c->st));
+  RXG_CUDA(cudaMemcpyAsync(c->h_int + 26, c->d_flag + 26, sizeof(int), cudaMemcpyDeviceToHost, c->st));
   RXG_CUDA(cudaMemcpyAsync(c->h_int + 16, c->d_flag + 16, sizeof(int), cudaMemcpyDeviceToHost, c->st));
   RXG_CUDA(cudaMemcpyAsync(c->h_int + 21, c->d_flag + 21, sizeof(int), cudaMemcpyDeviceToHost, c->st));
   RXG_CUDA(cudaMemcpyAsync(c->h_acc + 33, c->d_acc + 33, sizeof(long long), cudaMemcpyDeviceToHost, c->st));
@@ -350,8 +350,8 @@ int copy_capped_flags(Ctx *c) {
 int check_capped_flags(Ctx *c) {
   if (!c->list_capped) return RXG_OK;
   c->list_capped = false;   // checked once per list
-  if (c->h_int[0] > c->cfg.maxneighbs10) {
-    c->err = "ERROR: nbplist greater then MAXNEIGHBS10, value " + std::to_string(c->h_int[0]);
+  if (c->h_int[26] > c->cfg.maxneighbs10) {
+    c->err = "ERROR: nbplist greater then MAXNEIGHBS10, value " + std::to_string(c->h_int[26]);
     return RXG_ERR_MAXNEIGHBS10;
   }
   // multi-rank: every rank must take the same decision -- the flags were summed over the ranks (qeq_cg_single)
@@ -385,6 +385,22 @@ int check_capped_flags(Ctx *c) {
   c->maxrow = c->h_int[16];
   c->nnz_real = *(long long *)(c->h_acc + 33);
   if (c->win_built) c->win_max = c->h_int[21];   // the largest window of this list: sizes the next launches
+  return RXG_OK;
+}
+
+// The charge-independent part of FORCE (force_device stage 2: bond orders, bonded energy terms, ForceBondedTerms) on the
+// high-priority side stream, beside the CG: the sparse products are HBM-bound and leave the fp64 pipes idle, the bonded terms
+// are fp64- and latency-bound and leave HBM idle.  ev_bfork was recorded after the lists of this step were built.
+int launch_bonded_side(Ctx *c) {
+  RXG_CUDA(cudaStreamWaitEvent(c->st2, c->ev_bfork, 0));
+  cudaStream_t s0 = c->st;
+  const bool ph = c->ph_on;
+  c->st = c->st2; c->ph_on = false;   // (the phase clock follows one stream)
+  const int rc = force_device(c, true, 2);
+  c->st = s0; c->ph_on = ph;
+  RXG_TRY(rc);
+  RXG_CUDA(cudaEventRecord(c->ev_bjoin, c->st2));
+  c->bonded_stage = 2;
   return RXG_OK;
 }
 
@@ -431,6 +447,9 @@ int qeq_cg_single(Ctx *c, int nmax, int *iters) {
       LAUNCH(c, k_cg_update2, cdiv(std::max(n, 1), 256), 256, 0, n, c->qst, c->gst, c->hst, c->xs, c->gnb.slot_of, c->q, c->d_acc);
       RXG_TRY(refresh_h(c));
     }
+    // the first batch has been verified (a list without a count pass may have to be rebuilt): with the second one queued,
+    // start the bonded part of FORCE on the side stream
+    if (launched > 0 && c->bonded_stage == 1) RXG_TRY(launch_bonded_side(c));
     if (c->overlap) RXG_CUDA(cudaStreamWaitEvent(c->st, c->ev_join, 0));   // the batch's last refresh runs on the side stream
     RXG_TRY(copy_capped_flags(c));
     RXG_CUDA(cudaMemcpyAsync(c->h_acc + ACC_GEST2, c->d_acc + ACC_GEST2, sizeof(double) * 5, cudaMemcpyDeviceToHost, c->st));
@@ -449,6 +468,7 @@ int qeq_cg_single(Ctx *c, int nmax, int *iters) {
     }
     launched += kb;
   }
+  if (c->bonded_stage == 2) RXG_CUDA(cudaStreamWaitEvent(c->st, c->ev_bjoin, 0));   // the bonded terms read pos: before the round trips
   // the reference converts positions to normalised coordinates and back in every COPYATOMS call: QCOPY1 + QCOPY2
   // before the loop and two per completed iteration (src/qeq.F90:86,93,153,164); apply them in one launch
   if (c->cp[6] > 0)
@@ -457,11 +477,21 @@ int qeq_cg_single(Ctx *c, int nmax, int *iters) {
   return RXG_OK;
 }
 
+// FORCE after a QEq that may already have run its charge-independent part (qeq_device / launch_bonded_side)
+int force_staged(Ctx *c, bool reuse) {
+  const int st = reuse ? c->bonded_stage : 0;
+  c->bonded_stage = 0;
+  if (st == 2) return force_device(c, true, 3);
+  if (st == 1) { RXG_TRY(force_device(c, true, 2)); return force_device(c, true, 3); }
+  return force_device(c, reuse, 0);
+}
+
 // subroutine QEq on device-resident state, reference src/qeq.F90:2-178
 // `for_force`: build the halo with FORCE's width and the 10 A list with FORCE's predicate as well, so that the FORCE call of
 // the same step can reuse them (device-resident stepping only; the per-call API stays literal)
 int qeq_device(Ctx *c, bool for_force = false) {
   const int isQEq = c->cfg.isQEq;
+  c->bonded_stage = 0;
   if (isQEq != 1 && isQEq != 2) return RXG_OK;
   const int n = c->natoms;
   const int nmax = (isQEq == 1) ? c->cfg.NMAXQEq : 1;
@@ -504,6 +534,16 @@ int qeq_device(Ctx *c, bool for_force = false) {
       RXG_CUDA(cudaMemsetAsync(c->d_flag + 6, 0, sizeof(int), c->st));
       LAUNCH(c, k_pack_sps, cdiv(nt, 256), 256, 0, nt, c->spos, c->NB, c->itype, c->gnb.slot_of, c->d_ff, c->sps);
       LAUNCH(c, k_pqeq_rows, rgrid, 256, 0, c->gnb, nt, n, c->rowbeg, c->rowend, c->col, c->val, c->sps, c->d_ff, c->prow, c->pcs, c->d_acc, c->d_flag + 6);
+    }
+    // FORCE beside the CG (same step, shared halo and list): its bonded cells and bonded list now (host synchronisations),
+    // its charge-independent kernels on the side stream once the CG is under way (qeq_cg_single)
+    if (c->bonded_env && c->lists_shared && !c->strict && !pq && c->qeq_mode == 0 && n > 0 && nt > 0) {
+      if (c->bonded_stage == 0) {
+        phase_mark(c, 0);
+        RXG_TRY(force_device(c, true, 1));
+        c->bonded_stage = 1;
+      }
+      RXG_CUDA(cudaEventRecord(c->ev_bfork, c->st));   // (again after a rebuild: Ehb walks the 10 A list)
     }
     phase_mark(c, 18 | PH_QEQ);   // the CG: get_hsh (+ get_gradient, which the single-pass CG folds into the same sparse product)
     int rc;
@@ -657,6 +697,10 @@ int rxg_create(const rxg_config *cfg, rxg_handle *out) {
   }
   RXG_CUDA(cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming));
   RXG_CUDA(cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming));
+  RXG_CUDA(cudaEventCreateWithFlags(&c->ev_bfork, cudaEventDisableTiming));
+  RXG_CUDA(cudaEventCreateWithFlags(&c->ev_bjoin, cudaEventDisableTiming));
+  // opt-in (measured: zero-sum): RXG_BONDED_OVERLAP=1 runs FORCE's charge-independent part beside the QEq CG
+  { const char *bo = getenv("RXG_BONDED_OVERLAP"); c->bonded_env = bo && bo[0] == '1'; }
   RXG_CUDA(cudaEventCreate(&c->ev0));
   RXG_CUDA(cudaEventCreate(&c->ev1));
   RXG_CUDA(cudaEventCreate(&c->evm0));
@@ -705,8 +749,8 @@ int rxg_create(const rxg_config *cfg, rxg_handle *out) {
   RXG_TRY(dalloc(c, &c->nlp, NB)); RXG_TRY(dalloc(c, &c->dDlp, NB)); RXG_TRY(dalloc(c, &c->deltalp, NB));
   RXG_TRY(dalloc(c, &c->ccbnd, NB)); RXG_TRY(dalloc(c, &c->cdbnd, NB));
   RXG_TRY(dalloc(c, &c->s3, 3 * NB)); RXG_TRY(dalloc(c, &c->sbo, NB));
-  RXG_TRY(dalloc(c, &c->d_acc, 64)); RXG_TRY(dalloc(c, &c->d_flag, 32));
-  RXG_CUDA(cudaMallocHost((void **)&c->h_acc, sizeof(double) * 64));
+  RXG_TRY(dalloc(c, &c->d_acc, 128)); RXG_TRY(dalloc(c, &c->d_flag, 32));
+  RXG_CUDA(cudaMallocHost((void **)&c->h_acc, sizeof(double) * 128));
   RXG_CUDA(cudaMallocHost((void **)&c->h_int, sizeof(int) * 32));
   RXG_CUDA(cudaMallocHost((void **)&c->h_cnt, sizeof(int) * (4 + 4 * 64)));
   RXG_TRY(dalloc(c, &c->d_cnt, 4 + 4 * 64));
@@ -950,6 +994,8 @@ int rxg_destroy(rxg_handle h) {
     if (c->h_cnt) cudaFreeHost(c->h_cnt);
     for (cudaEvent_t e : c->ph_ev) cudaEventDestroy(e);
     if (c->st2) { cudaStreamSynchronize(c->st2); cudaStreamDestroy(c->st2); }
+    if (c->ev_bfork) cudaEventDestroy(c->ev_bfork);
+    if (c->ev_bjoin) cudaEventDestroy(c->ev_bjoin);
     if (c->ev_fork) cudaEventDestroy(c->ev_fork);
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     cudaEventDestroy(c->ev0);
@@ -1071,7 +1117,7 @@ int rxg_force(rxg_handle h, const int *natoms, const double *atype, double *pos,
   if (!(hint & RXG_HINT_Q_ON_DEVICE)) RXG_TRY(h2d_planes(c, c->q, q, 1, n));
   {
     Timer t(c, 1);
-    RXG_TRY(force_device(c, reuse));
+    RXG_TRY(force_staged(c, reuse));
   }
   c->lists_shared = false;
   RXG_TRY(d2h_planes(c, f, c->f, 3, n));
@@ -1246,7 +1292,7 @@ int rxg_md_run(rxg_handle h, int nsteps, double dt, int qstep, double Lex_w2, in
     if (nstep % qstep == 0) RXG_TRY(qeq_device(c, c->fuse)); // :77-83
     RXG_CUDA(cudaStreamSynchronize(c->st));
     double t2 = wall();
-    RXG_TRY(force_device(c, c->lists_shared));               // :84
+    RXG_TRY(force_staged(c, c->lists_shared));               // :84
     c->lists_shared = false;
     double t3 = wall();
     c->timers_ms[6] += t1 - t0; c->timers_ms[4] += t2 - t1; c->timers_ms[5] += t3 - t2;
@@ -1424,7 +1470,7 @@ int rxg_debug_fetch(rxg_handle h, const char *name, void *out, long long cap, lo
   else if (s == "uoff") dev(c->uoff, n6 + 1, 8);
   else if (s == "rowoff") dev(c->rowoff, n6 + 1, 8);
   else if (s == "order_nb") dev(c->gnb.order, n6, 4);
-  else if (s == "acc") dev(c->d_acc, 64, 8);
+  else if (s == "acc") dev(c->d_acc, 128, 8);
   else if (s == "BO0") dev(c->BO[0], NS, 8);
   else if (s == "BO1") dev(c->BO[1], NS, 8);
   else if (s == "BO2") dev(c->BO[2], NS, 8);

@@ -22,7 +22,7 @@ constexpr double CECHRGE = 23.02;                                               
 constexpr double RCHB2 = 100.0;                                                             // src/module.F90:677-678
 
 // d_acc layout for FORCE: 16+k = PE(k) k=1..13 ; 32.. reserved (nnz) ; 34..39 astr ; 40..45 kinetic astr ; 48 KE ; 49 sum q
-constexpr int ACC_PE = 16, ACC_ASTR = 34;
+constexpr int ACC_PE = 80, ACC_ASTR = 98;   // FORCE's own block of d_acc[128]: its charge-independent part may run beside the QEq CG (slots 0-39)
 
 struct Bonds {   // per directed bond slot, compact: slot of (atom i, s-th neighbour) = ptr[i] + s
   int MAXN;
@@ -1122,31 +1122,45 @@ inline Bonds make_bonds(Ctx *c) {
 // subroutine FORCE on device-resident state, reference src/pot.F90:2-90
 // `reuse`: the residents, ghosts, non-bonded cells and the 10 A list of the QEq that just ran are still valid (same step,
 // FORCE-width halo, see qeq_device); only the ghost charges are refreshed.
-inline int force_device(Ctx *c, bool reuse = false) {
+// `stage` (device-resident stepping and RXG_FUSE_API, reuse only): the charge-independent part of FORCE runs beside the QEq CG
+// of the same step (qeq_cg_single): 1 = bonded cells and bonded list (host synchronisations; before the CG starts),
+// 2 = bond orders, bonded energy terms and ForceBondedTerms (on the side stream, while the CG's HBM-bound sparse products leave
+// the fp64 pipes idle), 3 = ghost charges, ENbond, sums, MODE_CPBK (after the CG).  0 = everything in the reference's order.
+inline int force_device(Ctx *c, bool reuse = false, int stage = 0) {
   const int NB = c->NB, n = c->natoms;
-  RXG_CUDA(cudaMemsetAsync(c->f, 0, sizeof(double) * 3 * NB, c->st));
-  RXG_CUDA(cudaMemsetAsync(c->fsl, 0, sizeof(double) * 3 * NB, c->st));
-  RXG_CUDA(cudaMemsetAsync(c->d_acc + ACC_PE, 0, sizeof(double) * 24, c->st));
+  const bool s1 = stage == 0 || stage == 1, s2 = stage == 0 || stage == 2, s3 = stage == 0 || stage == 3;
+  if (s1) {
+    RXG_CUDA(cudaMemsetAsync(c->f, 0, sizeof(double) * 3 * NB, c->st));
+    RXG_CUDA(cudaMemsetAsync(c->fsl, 0, sizeof(double) * 3 * NB, c->st));
+    RXG_CUDA(cudaMemsetAsync(c->d_acc + ACC_PE, 0, sizeof(double) * 24, c->st));
+  }
   double dr[3];
   for (int a = 0; a < 3; a++) dr[a] = c->cfg.nmincell * c->box.lcsize[a];
   const bool pqeq = c->cfg.isPQEq != 0;
-  phase_mark(c, 4);                                             // COPYATOMS
-  if (!reuse) RXG_TRY(halo_copy(c, dr));                        // src/pot.F90:28
-  else RXG_TRY(halo_refresh(c, 4, 1));   // ghost q; + the position round trip FORCE's own MODE_COPY would apply
-  if (pqeq) RXG_TRY(halo_refresh(c, 5, 0));   // ghost spos (part of MODE_COPY in the reference, src/comm.F90:129-131)
+  if (stage == 0 || stage == 3) {
+    phase_mark(c, 4);                                             // COPYATOMS
+    if (!reuse) RXG_TRY(halo_copy(c, dr));                        // src/pot.F90:28
+    else RXG_TRY(halo_refresh(c, 4, 1));   // ghost q; + the position round trip FORCE's own MODE_COPY would apply
+    if (pqeq) RXG_TRY(halo_refresh(c, 5, 0));   // ghost spos (part of MODE_COPY in the reference, src/comm.F90:129-131)
+  }
   const int nt = c->cp[6];
-  if (!reuse) LAUNCH(c, k_types, cdiv(nt, 256), 256, 0, c->atype, nt, c->itype, c->gid);
-  phase_mark(c, 3);                                             // LINKEDLIST
-  RXG_TRY(bin_grid(c, c->gb));                                  // :30
-  if (!reuse) RXG_TRY(bin_grid(c, c->gnb));                     // :31
-  phase_mark(c, 5);                                             // NEIGHBORLIST
-  RXG_TRY(build_nbrlist(c));                                    // :33
-  phase_mark(c, 15);                                            // GetNonbondingPairList
-  if (!reuse) RXG_TRY(build_pairlist<0>(c));                    // :34
+  if (s1) {
+    if (!reuse) LAUNCH(c, k_types, cdiv(nt, 256), 256, 0, c->atype, nt, c->itype, c->gid);
+    phase_mark(c, 3);                                             // LINKEDLIST
+    RXG_TRY(bin_grid(c, c->gb));                                  // :30
+    if (!reuse) RXG_TRY(bin_grid(c, c->gnb));                     // :31
+    phase_mark(c, 5);                                             // NEIGHBORLIST
+    RXG_TRY(build_nbrlist(c));                                    // :33
+    phase_mark(c, 15);                                            // GetNonbondingPairList
+    if (!reuse) RXG_TRY(build_pairlist<0>(c));                    // :34
+    if (stage == 1) { phase_mark(c, 0); return RXG_OK; }
+  }
   phase_mark(c, 6);                                             // BOCALC
   Bonds B = make_bonds(c);
-  LAUNCH(c, k_boprim, cdiv(nt, 128), 128, 0, nt, c->pos, NB, c->itype, c->d_ff, B, c->deltap1, c->deltap2, c->cdbnd, c->ccbnd, c->s3);
-  LAUNCH(c, k_bofull, cdiv(nt, 128), 128, 0, nt, c->itype, c->d_ff, B, c->deltap1, c->deltap2, c->delta);
+  if (s2) {
+    LAUNCH(c, k_boprim, cdiv(nt, 128), 128, 0, nt, c->pos, NB, c->itype, c->d_ff, B, c->deltap1, c->deltap2, c->cdbnd, c->ccbnd, c->s3);
+    LAUNCH(c, k_bofull, cdiv(nt, 128), 128, 0, nt, c->itype, c->d_ff, B, c->deltap1, c->deltap2, c->delta);
+  }
   // ---- energy terms (src/pot.F90:49-57)
   if (!c->wl) {   // first call: size the work lists from the resident count
     c->wl_cap3 = 16LL * NB + 1024; c->wl_cap4 = 32LL * NB + 1024; c->wl_caph = 2LL * NB + 1024;
@@ -1154,6 +1168,7 @@ inline int force_device(Ctx *c, bool reuse = false) {
   }
   double4 *pq = c->pqa;
   phase_mark(c, 7);                                             // ENbond
+  // (stage 2 packs the positions the bonded terms read, with the charges of the previous step; stage 3 packs again once q is final)
   LAUNCH(c, k_pack_pq, cdiv(nt, 256), 256, 0, nt, c->pos, NB, c->q, c->itype, c->gid, c->gnb.slot_of, c->pqa, c->pqs, c->tgs, c->gts);
   // the full-row form needs every partner's image inside this rank's halo: true when the FORCE halo >= rctap
   bool full_ok = true;
@@ -1165,7 +1180,8 @@ inline int force_device(Ctx *c, bool reuse = false) {
   if (!(getenv("RXG_ENBOND_FULL") && getenv("RXG_ENBOND_FULL")[0] == '1')) full_ok = false;
   const int wgrid = cdiv((long long)n * 32, 256);
   const int ogrid = cdiv((long long)nt * 32, 256);   // warps over cell-ordered slots (ghost slots exit at once)
-  if (pqeq) {   // src/pot.F90:48-49
+  if (!s3) {
+  } else if (pqeq) {   // src/pot.F90:48-49
     full_ok = false;
     LAUNCH(c, k_pack_sps, cdiv(nt, 256), 256, 0, nt, c->spos, NB, c->itype, c->gnb.slot_of, c->d_ff, c->sps);
     LAUNCH(c, k_enbond_pqeq, ogrid, 256, 0, nt, n, c->rowbeg, c->rowend, c->col, c->pqs, c->tgs, c->sps, c->d_ff, c->f, c->fsl, NB, c->d_acc);
@@ -1176,6 +1192,7 @@ inline int force_device(Ctx *c, bool reuse = false) {
       LAUNCH(c, k_enbond_half, ogrid, 256, 0, nt, n, c->rowbeg, c->rowend, c->col, c->pqs, c->tgs, c->gts, c->d_ff, c->f, c->fsl, NB, c->d_acc);
     else LAUNCH(c, (k_enbond<true>), ogrid, 256, 0, nt, n, c->rowbeg, c->rowend, c->col, c->pqs, c->tgs, c->d_ff, c->f, c->fsl, NB, c->d_acc);
   }
+  if (s2) {
   phase_mark(c, 9);                                             // Elnpr (preparation loop)
   LAUNCH(c, k_elnpr_prep, cdiv(nt, 256), 256, 0, nt, c->itype, c->d_ff, c->delta, c->nlp, c->dDlp, c->deltalp);
   phase_mark(c, 8);                                             // Ebond (one kernel with Elnpr's main loop)
@@ -1223,12 +1240,17 @@ inline int force_device(Ctx *c, bool reuse = false) {
     c->wl_caph = std::max(c->wl_caph, nh + nh / 4 + 1024);
     RXG_CUDA(cudaMalloc((void **)&c->wl, sizeof(int2) * (size_t)(c->wl_cap3 + c->wl_cap4 + c->wl_caph)));
   }
+  }   // s2
   phase_mark(c, 13);                                            // ForceBondedTerms
-  LAUNCH(c, k_fsl_to_f, cdiv(nt, 256), 256, 0, nt, NB, c->gnb.order, c->fsl, c->f);
-  // ---- ForceBondedTerms (src/pot.F90:63)
-  LAUNCH(c, k_final0, cdiv(nt, 128), 128, 0, nt, B, c->cdbnd);
-  LAUNCH(c, k_final1, cdiv(nt, 128), 128, 0, nt, c->pos, NB, B, c->cdbnd, c->s3, c->ccbnd, c->f);
-  LAUNCH(c, k_final2, cdiv(nt, 128), 128, 0, nt, c->pos, NB, B, c->ccbnd, c->f);
+  if (stage == 0) LAUNCH(c, k_fsl_to_f, cdiv(nt, 256), 256, 0, nt, NB, c->gnb.order, c->fsl, c->f);
+  if (s2) {
+    // ---- ForceBondedTerms (src/pot.F90:63)
+    LAUNCH(c, k_final0, cdiv(nt, 128), 128, 0, nt, B, c->cdbnd);
+    LAUNCH(c, k_final1, cdiv(nt, 128), 128, 0, nt, c->pos, NB, B, c->cdbnd, c->s3, c->ccbnd, c->f);
+    LAUNCH(c, k_final2, cdiv(nt, 128), 128, 0, nt, c->pos, NB, B, c->ccbnd, c->f);
+    if (stage == 2) { phase_mark(c, 0); return RXG_OK; }
+  }
+  if (stage == 3) LAUNCH(c, k_fsl_to_f, cdiv(nt, 256), 256, 0, nt, NB, c->gnb.order, c->fsl, c->f);   // partner forces of Ehb (stage 2) and ENbond
   LAUNCH(c, k_virial, cdiv(nt, 256), 256, 0, nt, c->pos, c->f, NB, c->d_acc);   // :65-72
   // full-row ENbond puts both halves of a pair force on residents, so its virial is taken per pair inside the kernel
   if (full_ok) LAUNCH(c, (k_enbond<false>), ogrid, 256, 0, nt, n, c->rowbeg, c->rowend, c->col, c->pqs, c->tgs, c->d_ff, c->f, c->fsl, NB, c->d_acc);

@@ -181,6 +181,11 @@ struct Ctx {
   // interior / boundary split of the SpMV (multi-rank): the ghost refresh runs on st2 beside the interior rows
   cudaStream_t st2 = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  // FORCE's charge-independent part beside the QEq CG of the same step (force_device stages, launch_bonded_side):
+  // 0 nothing done, 1 bonded cells + bonded list built, 2 bonded terms launched on st2 (joined at the end of the CG)
+  cudaEvent_t ev_bfork = nullptr, ev_bjoin = nullptr;
+  int bonded_stage = 0;
+  bool bonded_env = false;  // RXG_BONDED_OVERLAP=1 (experiment): FORCE's charge-independent part beside the CG; default: FORCE after QEq, in the reference's order
   bool overlap = false, overlap_env = true;
   int *grp_cls = nullptr, *grp_off = nullptr, *grp_int = nullptr, *grp_bnd = nullptr;   // [NB/2+2] each
   int ngrp = 0, ngrp_int = 0, grp_rows = 0, stencil_reach = 0;
@@ -246,7 +251,7 @@ struct Ctx {
   int2 *wl = nullptr;        // angle / torsion work lists
   long long wl_cap3 = 0, wl_cap4 = 0, wl_caph = 0, n_angles = 0, n_torsions = 0, n_hbonds = 0;
   // ---- scalars ---------------------------------------------------------------------------------------------
-  double *d_acc = nullptr;   // [64] reduction targets
+  double *d_acc = nullptr;   // [128] reduction targets: 0-39 QEq / PQEq CG and list statistics, 40-55 integrator and observables, 80-103 FORCE (PE, stress)
   int *d_flag = nullptr;     // [8]  error / overflow flags
   int *d_blk = nullptr;      // scan scratch
   long long *d_blk64 = nullptr;

@@ -382,7 +382,8 @@ __global__ void __launch_bounds__(PL_WARPS * 32, FILL ? RXG_PL_MINB : 1) k_pairl
       } else {
         int kept = mycnt;
         if (CAPPED) {
-          if (mycnt > maxrow) atomicMax(ovf, mycnt);               // the MAXNEIGHBS10 trap, checked by the host with the overflow flag
+          if (mycnt > maxrow) atomicMax(ovf + 26, mycnt);          // the MAXNEIGHBS10 trap, checked by the host with the overflow flag
+                                                                   // (its own slot: ovf[0] is reused by the cell and bonded-list builds that may follow)
           if (mycnt > mycap) {   // the row outgrew last step's count + slack: the host rebuilds (ovf[22..25]: one such row, for diagnostics)
             if (atomicExch(ovf + 20, 1) == 0) { ovf[22] = ct.gid[mi]; ovf[23] = mycnt; ovf[24] = mycap; ovf[25] = mi; }
             kept = mycap;
@@ -504,6 +505,7 @@ int build_pairlist(Ctx *c, bool hessian = true, bool allow_capped = false) {
   c->list_capped = capped;
   if (capped) c->timers_ms[23] += 1;   // list builds without a count pass
   RXG_CUDA(cudaMemsetAsync(c->d_flag + 20, 0, 2 * sizeof(int), c->st));
+  RXG_CUDA(cudaMemsetAsync(c->d_flag + 26, 0, sizeof(int), c->st));
   // window SpMV: the fill pass also writes the 16-bit window-relative columns and the row lengths by slot
   const bool win_on = MODE >= 1 && c->spmv_kind == 2 && !c->strict;
   WinOut wo;

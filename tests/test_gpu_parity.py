@@ -68,7 +68,7 @@ def rows(e, n):
 @pytest.fixture(autouse=True)
 def _clean_env():
     keys = ("RXG_STRICT_ORDER", "RXG_QEQ_TWOPASS", "RXG_FUSE_API", "RXG_NO_FUSE", "RXG_SPMV", "RXG_SPMV_SHAPE", "RXG_SPMV_STAGE", "RXG_SPMV_RING",
-            "RXG_WIN_G", "RXG_WIN_WARPS", "RXG_WIN_WCAP", "RXG_WIN_SMEM", "RXG_ENBOND_QUEUE")
+            "RXG_WIN_G", "RXG_WIN_WARPS", "RXG_WIN_WCAP", "RXG_WIN_SMEM", "RXG_ENBOND_QUEUE", "RXG_BONDED_OVERLAP")
     for k in keys:
         os.environ.pop(k, None)
     yield
@@ -157,6 +157,39 @@ def test_production_cg_follows_oracle_iterates(built, name, spmv):
         e.close(); o.close()
         assert worst[k] <= bar, (k, worst[k])
     print(f"{name} [{spmv}]: max |dq| after k iterations: " + ", ".join(f"{k}: {d:.1e}" for k, d in worst.items()))
+
+
+def test_bonded_overlap_gives_the_same_step(built):
+    """RXG_BONDED_OVERLAP=1 (experiment): the charge-independent part of FORCE runs on a side stream beside the QEq CG
+    of the same device-resident step.  Same kernels on the same inputs (positions differ by the ulp-level COPYATOMS round trips
+    the bonded terms no longer wait for): energies, forces and charges of three md_run steps must agree with the sequential
+    order far inside the parity bars.  The CG is cut at 6 iterations per step so that both runs take exactly the same number
+    (with the stop rule the production CG's own run-to-run spread, 1e-7 in q, would be all this test sees)."""
+    out = {}
+    for ov in ("0", "1"):
+        os.environ["RXG_BONDED_OVERLAP"] = ov
+        s, cfg, e, o = make("rdx_2x2x2_disp", NMAXQEq=6)
+        o.close()
+        atype, pos, v, f, q = e.host_arrays(s.ranks[0])
+        n = e.NATOMS
+        e.state_upload(atype, pos, v, q)
+        e.md_prime()
+        dt = 0.25 / UTIME
+        e.md_run(3, dt, 1, 0.0, 0)
+        pe, ke, qsum, it = e.md_observe()
+        e.state_download(atype, pos, v, f, q)
+        out[ov] = dict(pe=np.array(pe[1:]), f=f[:, :n].copy(), q=q[:n].copy(), pos=pos[:, :n].copy(), it=it)
+        e.close()
+    os.environ.pop("RXG_BONDED_OVERLAP", None)
+    A, B = out["0"], out["1"]
+    assert A["it"] == B["it"] == 6
+    print("overlap vs sequential: max |dpos| %.1e, |df|/max|f| %.1e, |dPE|/max|PE| %.1e, |dq| %.1e" % (
+        np.abs(A["pos"] - B["pos"]).max(), np.abs(A["f"] - B["f"]).max() / np.abs(A["f"]).max(),
+        np.abs(A["pe"] - B["pe"]).max() / np.abs(A["pe"]).max(), np.abs(A["q"] - B["q"]).max()))
+    assert np.abs(A["pos"] - B["pos"]).max() < 1e-10
+    assert np.abs(A["q"] - B["q"]).max() <= 1e-9
+    assert np.abs(A["f"] - B["f"]).max() <= 1e-8 * np.abs(A["f"]).max()
+    assert np.abs(A["pe"] - B["pe"]).max() <= 1e-9 * np.abs(A["pe"]).max()
 
 
 def test_enbond_half_list_forms_agree(built):
