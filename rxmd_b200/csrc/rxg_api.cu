@@ -288,7 +288,7 @@ int spmv_launch(Ctx *c, int part = 0) {
 }
 
 // single-pass CG (default): one sparse product per iteration, see rxg_lists_qeq.cuh.  Control flow (stop rule, real(4) step
-// lengths) runs on the device (k_cg_ctrl); the host enqueues CG_BATCH iterations at a time and reads the stop flag once per
+// lengths) runs on the device (k_cg_ctrl); the host enqueues cg_batch (4) iterations at a time and reads the stop flag once per
 // batch -- iterations enqueued past the stop return at their first instruction.
 // classify the row groups of the launch shape in use (once per list build) -- only when the refresh has somewhere to go
 int build_row_groups(Ctx *c) {
@@ -404,7 +404,6 @@ int launch_bonded_side(Ctx *c) {
   return RXG_OK;
 }
 
-constexpr int CG_BATCH = 4;
 int qeq_cg_single(Ctx *c, int nmax, int *iters) {
   const int n = c->natoms;
   RXG_TRY(halo_refresh(c, 1, 0));   // ghost qs,qt (MODE_QCOPY1, src/qeq.F90:86)
@@ -430,7 +429,7 @@ int qeq_cg_single(Ctx *c, int nmax, int *iters) {
   int launched = 0, it = 0;
   bool done = false;
   while (!done && launched < nmax) {
-    const int kb = std::min(CG_BATCH, nmax - launched);
+    const int kb = std::min(c->cg_batch, nmax - launched);
     for (int j = 0; j < kb; j++) {
       cudaEventRecord(c->evs[2 * j], c->st);
       RXG_TRY(spmv_after_refresh(c));
@@ -706,7 +705,8 @@ int rxg_create(const rxg_config *cfg, rxg_handle *out) {
   RXG_CUDA(cudaEventCreate(&c->evm0));
   RXG_CUDA(cudaEventCreate(&c->evm1));
   for (int k = 0; k < 4; k++) RXG_CUDA(cudaEventCreate(&c->evk[k]));
-  for (int k = 0; k < 2 * CG_BATCH; k++) RXG_CUDA(cudaEventCreate(&c->evs[k]));
+  { const char *cb = getenv("RXG_CG_BATCH"); if (cb) c->cg_batch = std::max(1, std::min(16, atoi(cb))); }
+  for (int k = 0; k < 32; k++) RXG_CUDA(cudaEventCreate(&c->evs[k]));
   const size_t NB = c->NB, NS = NB * (size_t)c->MAXN;
   RXG_TRY(dalloc(c, &c->pos, 3 * NB)); RXG_TRY(dalloc(c, &c->v, 3 * NB)); RXG_TRY(dalloc(c, &c->f, 3 * NB)); RXG_TRY(dalloc(c, &c->fsl, 3 * NB));
   RXG_TRY(dalloc(c, &c->atype, NB)); RXG_TRY(dalloc(c, &c->q, NB)); RXG_TRY(dalloc(c, &c->qsfp, NB)); RXG_TRY(dalloc(c, &c->qsfv, NB));
@@ -1000,6 +1000,8 @@ int rxg_destroy(rxg_handle h) {
     if (c->ev_join) cudaEventDestroy(c->ev_join);
     cudaEventDestroy(c->ev0);
     cudaEventDestroy(c->ev1);
+    for (cudaEvent_t e : c->evs) if (e) cudaEventDestroy(e);
+    for (cudaEvent_t e : {c->evm0, c->evm1}) if (e) cudaEventDestroy(e);
     cudaStreamDestroy(c->st);
   }
   delete c;

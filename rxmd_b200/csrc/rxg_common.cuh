@@ -268,7 +268,8 @@ struct Ctx {
   bool strict = false;      // RXG_STRICT_ORDER=1: serial-order, FMA-free CG for bit-level validation (small systems)
   double timers_ms[30] = {0};
   cudaEvent_t ev0 = nullptr, ev1 = nullptr, evm0 = nullptr, evm1 = nullptr, evk[4] = {nullptr, nullptr, nullptr, nullptr};
-  cudaEvent_t evs[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};   // SpMV timing, one pair per iteration of a CG batch
+  cudaEvent_t evs[32] = {};   // SpMV timing, one pair per iteration of a CG batch
+  int cg_batch = 4;           // CG iterations enqueued between two looks at the stop flag (RXG_CG_BATCH, 1..16)
   bool grad_pending = false;
   // phase clock (rxg_it_timer)
   bool ph_on = true;
