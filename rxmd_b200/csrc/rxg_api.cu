@@ -202,9 +202,9 @@ int spmv_items_launch(Ctx *c, int slot) {
 // per cell, +10 %) fits the per-CTA budget (RXG_WIN_SMEM, default 64 KB: three CTAs per SM).  The list build reports the
 // largest window it saw (win_max); if that exceeds what a CTA can hold, the next build halves G, and a list whose windows do
 // not fit at all is multiplied by k_spmv_rows.
-template <int NW, int U, int MINB>
+template <int NW, int U, int MINB, int LPR = 32>
 int spmv_win_launch(Ctx *c, int slot, bool *took) {
-  auto kern = k_spmv_win<NW, U, MINB>;
+  auto kern = k_spmv_win<NW, U, MINB, LPR>;
   int optin = 0;
   RXG_CUDA(cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, c->dev));
   const int limit = optin - 4096;   // static shared memory of the kernel + slack
@@ -251,6 +251,7 @@ int spmv_launch(Ctx *c, int part = 0) {
     }
     if (c->win_nw == 4 && u == 13) RXG_TRY((spmv_win_launch<4, 13, 6>(c, 0, &took)));
     else if (c->win_nw == 4) RXG_TRY((spmv_win_launch<4, 8, 8>(c, 1, &took)));
+    else if (u == 4 && c->win_lpr == 16) RXG_TRY((spmv_win_launch<8, 8, 4, 16>(c, 5, &took)));   // short rows: two per warp, 16 lanes x 8 entries each
     else if (u == 4) RXG_TRY((spmv_win_launch<8, 4, 6>(c, 2, &took)));
     else if (u == 13) RXG_TRY((spmv_win_launch<8, 13, 3>(c, 4, &took)));
     else RXG_TRY((spmv_win_launch<8, 8, 4>(c, 3, &took)));
@@ -661,6 +662,8 @@ int rxg_create(const rxg_config *cfg, rxg_handle *out) {
     c->win_u = wu ? atoi(wu) : 0;   // 0: from the average row length (spmv_launch)
     if (c->win_u != 4 && c->win_u != 8 && c->win_u != 13) c->win_u = 0;
     c->win_smem_target = wsm ? std::max(4096, atoi(wsm)) : 64 * 1024;
+    const char *wl = getenv("RXG_WIN_LPR");
+    c->win_lpr = (wl && atoi(wl) == 16) ? 16 : 32;   // 16: two short rows per warp (experiment: slower on the SiC nanoparticles)
     const char *wra = getenv("RXG_WIN_RALIGN");
     if (wra && (atoi(wra) == 4 || atoi(wra) == 8 || atoi(wra) == 16)) c->win_ralign = atoi(wra);
     const char *wc = getenv("RXG_WIN_WCAP");

@@ -231,7 +231,7 @@ struct Ctx {
   int *rowlen = nullptr;             // [NB+2]
   int2 *win_desc = nullptr;          // [groups][nruns + 1] window descriptors (k_win_desc)
   size_t win_desc_cap = 0;
-  int win_ralign = 4, win_g = 0, win_g_env = 0, win_wcap_env = 0, win_nw = 8, win_u = 0, win_max = 0, win_smem_target = 0, win_smem_set[6] = {0, 0, 0, 0, 0, 0};
+  int win_ralign = 4, win_lpr = 32, win_g = 0, win_g_env = 0, win_wcap_env = 0, win_nw = 8, win_u = 0, win_max = 0, win_smem_target = 0, win_smem_set[6] = {0, 0, 0, 0, 0, 0};
   bool win_built = false;            // the current list carries col16 / rowlen for group size win_g_built
   int win_g_built = 0;
   std::vector<int> h_runs;           // host copy of the stencil runs (group-size estimate)

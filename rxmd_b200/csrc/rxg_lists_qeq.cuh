@@ -924,7 +924,83 @@ __device__ __forceinline__ void win_rows(const double2 *__restrict__ s_x, int a0
   }
 }
 
-template <int NW, int U, int MINB>
+// Short rows (sparse systems: ~120 entries per row): a full warp per row spends more instructions on the row's reduction and
+// bookkeeping than on its entries.  Here a warp takes TWO rows at a time, 16 lanes each, in lockstep (the number of batches is
+// the longer row's), and one 9-shuffle reduction serves both rows.
+template <int NW, int U, bool GH>
+__device__ __forceinline__ void win_rows_half(const double2 *__restrict__ s_x, int a0, int nrows, int lane, int wid, const long long *__restrict__ rowoff,
+                                              const int *__restrict__ rowlen, const unsigned short *__restrict__ col16,
+                                              const double *__restrict__ val, double4 *__restrict__ rowsum, unsigned long long *bar) {
+  const int sub = lane & 15, half = lane >> 4;
+  int t = 2 * wid + half;                       // this half-warp's row; the warp advances by 2 NW rows per pass
+  if (2 * wid >= nrows) { mbar_wait(bar, 0); return; }
+  long long rs = 0;
+  int n = -1;
+  if (t < nrows) { rs = __ldg(rowoff + a0 + t); n = __ldg(rowlen + a0 + t); }
+  long long rs_next = 0;
+  int n_next = -1;
+  if (t + 2 * NW < nrows) { rs_next = __ldg(rowoff + a0 + t + 2 * NW); n_next = __ldg(rowlen + a0 + t + 2 * NW); }
+  double h[U];
+  unsigned short c[U];
+  int k0 = 0;
+  auto load = [&]() {
+    const double *pv = val + rs + k0 + sub;
+    const unsigned short *pc = col16 + rs + k0 + sub;
+    const int rem = n - k0 - sub;
+#pragma unroll
+    for (int u = 0; u < U; u++) {
+      h[u] = 0.0; c[u] = 0;
+      if (16 * u < rem) { h[u] = __ldcs(pv + 16 * u); c[u] = __ldcs(pc + 16 * u); }
+    }
+  };
+  load();
+  mbar_wait(bar, 0);
+  const char *sxb = reinterpret_cast<const char *>(s_x);
+  for (;;) {   // one pass = two rows
+    const int nmax = max(n, __shfl_xor_sync(0xffffffffu, n, 16));
+    double a = 0.0, b = 0.0, ga = 0.0, gb = 0.0;
+    for (;;) {
+#pragma unroll
+      for (int u = 0; u < U; u++) {
+        const unsigned cu = c[u];
+        const double2 v = *reinterpret_cast<const double2 *>(sxb + (GH ? ((cu << 4) & 0x7fff0u) : (cu << 4)));
+        a = fma(h[u], v.x, a);
+        b = fma(h[u], v.y, b);
+        if (GH && (cu & 0x8000u)) { ga = fma(h[u], v.x, ga); gb = fma(h[u], v.y, gb); }
+      }
+      k0 += 16 * U;
+      if (k0 >= nmax) break;   // warp-uniform
+      load();
+    }
+    // four sums per half-warp: halve what a lane carries twice, then two plain steps; totals on lanes 0 / 4 / 8 / 12 of the half
+    {
+      const bool up8 = lane & 8, up4 = lane & 4;
+      const double s0 = up8 ? a : ga, s1 = up8 ? b : gb;
+      double k0v = up8 ? ga : a, k1v = up8 ? gb : b;
+      k0v += __shfl_xor_sync(0xffffffffu, s0, 8);
+      k1v += __shfl_xor_sync(0xffffffffu, s1, 8);
+      const double give = up4 ? k0v : k1v;
+      double u = up4 ? k1v : k0v;
+      u += __shfl_xor_sync(0xffffffffu, give, 4);
+      u += __shfl_xor_sync(0xffffffffu, u, 2);
+      u += __shfl_xor_sync(0xffffffffu, u, 1);
+      const int base = lane & 16;
+      a = __shfl_sync(0xffffffffu, u, base);
+      b = __shfl_sync(0xffffffffu, u, base + 4);
+      ga = __shfl_sync(0xffffffffu, u, base + 8);
+      gb = __shfl_sync(0xffffffffu, u, base + 12);
+    }
+    if (sub == 0 && n >= 0) rowsum[a0 + t] = make_double4(a, b, ga, gb);   // n < 0: no row (past the group, or a ghost's slot)
+    t += 2 * NW;
+    if (t - half >= nrows) break;   // warp-uniform: the pass's first row is past the group
+    rs = rs_next; n = n_next; k0 = 0;
+    rs_next = 0; n_next = -1;
+    if (t + 2 * NW < nrows) { rs_next = __ldg(rowoff + a0 + t + 2 * NW); n_next = __ldg(rowlen + a0 + t + 2 * NW); }
+    load();
+  }
+}
+
+template <int NW, int U, int MINB, int LPR = 32>
 __global__ void __launch_bounds__(NW * 32, MINB) k_spmv_win(DevGrid g, int nruns, int G, int reach, const int2 *__restrict__ desc,
                                                             const long long *__restrict__ rowoff, const int *__restrict__ rowlen,
                                                             const int *__restrict__ col, const unsigned short *__restrict__ col16,
@@ -958,7 +1034,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_spmv_win(DevGrid g, int nruns
   const bool staged = tot <= wcap && tot <= 32768;
   {
     unsigned issued = 0;
-    if (staged && cg_done == 0.0) {
+    if (staged && cg_done == 0.0 && a1 > a0) {   // (a group without rows -- vacuum -- copies nothing)
       for (int r = r_first; r < nruns; r += NW * 32) {
         const int2 e = r == r_first ? e_first : __ldg(d + r);
         const int wlen = e.y & 0xfff, pos = e.y >> 12;
@@ -976,8 +1052,13 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_spmv_win(DevGrid g, int nruns
   if (staged) {
     // a group at least `reach` cells inside the resident grid takes no ghost column: its rows skip the ghost sums altogether
     const bool inner = c1 >= reach && c1 < g.nc[0] - reach && c2 >= reach && c2 < g.nc[1] - reach && g0 >= reach && g1 < g.nc[2] - reach;
-    if (inner) win_rows<NW, U, false>(s_x, a0, nrows, lane, wid, rowoff, rowlen, col16, val, rowsum, &bar);
-    else win_rows<NW, U, true>(s_x, a0, nrows, lane, wid, rowoff, rowlen, col16, val, rowsum, &bar);
+    if (LPR == 16) {
+      if (inner) win_rows_half<NW, U, false>(s_x, a0, nrows, lane, wid, rowoff, rowlen, col16, val, rowsum, &bar);
+      else win_rows_half<NW, U, true>(s_x, a0, nrows, lane, wid, rowoff, rowlen, col16, val, rowsum, &bar);
+    } else {
+      if (inner) win_rows<NW, U, false>(s_x, a0, nrows, lane, wid, rowoff, rowlen, col16, val, rowsum, &bar);
+      else win_rows<NW, U, true>(s_x, a0, nrows, lane, wid, rowoff, rowlen, col16, val, rowsum, &bar);
+    }
   } else {
     mbar_wait(&bar, 0);
     // the window does not fit: 32-bit columns, x gathered from global memory (this CTA only)

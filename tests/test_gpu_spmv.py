@@ -18,7 +18,7 @@ from rxmd_b200.host.system import build_system
 pytestmark = pytest.mark.gpu
 
 INP = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "inputs")
-SPMV_ENV = ("RXG_SPMV", "RXG_SPMV_SHAPE", "RXG_SPMV_STAGE", "RXG_SPMV_RING", "RXG_FUSE_API", "RXG_WIN_G", "RXG_WIN_WARPS", "RXG_WIN_WCAP", "RXG_WIN_U", "RXG_WIN_RALIGN",
+SPMV_ENV = ("RXG_SPMV", "RXG_SPMV_SHAPE", "RXG_SPMV_STAGE", "RXG_SPMV_RING", "RXG_FUSE_API", "RXG_WIN_G", "RXG_WIN_WARPS", "RXG_WIN_WCAP", "RXG_WIN_U", "RXG_WIN_RALIGN", "RXG_WIN_LPR",
             "RXG_WIN_SMEM")
 
 VARIANTS = {
@@ -26,7 +26,8 @@ VARIANTS = {
     "win_auto": {},
     "win_g1_w4": {"RXG_WIN_G": "1", "RXG_WIN_WARPS": "4"},
     "win_g5_w4_u4": {"RXG_WIN_G": "5", "RXG_WIN_WARPS": "4", "RXG_WIN_U": "4"},
-    "win_g3_u4": {"RXG_WIN_G": "3", "RXG_WIN_U": "4"},
+    "win_g3_u4": {"RXG_WIN_G": "3", "RXG_WIN_U": "4"},                     # short rows: a full warp per row, 4 entries per lane
+    "win_g3_u4_lpr16": {"RXG_WIN_G": "3", "RXG_WIN_U": "4", "RXG_WIN_LPR": "16"},   # short rows: two rows per warp, 16 lanes each
     "win_g7": {"RXG_WIN_G": "7"},
     "win_ralign16": {"RXG_WIN_RALIGN": "16"},                   # rows on 128-byte boundaries of the value stream
     "win_fallback": {"RXG_WIN_G": "2", "RXG_WIN_WCAP": "512"},   # no window fits 512 entries: every CTA gathers from global memory
