@@ -1441,6 +1441,14 @@ int rxg_debug_fetch(rxg_handle h, const char *name, void *out, long long cap, lo
     if (out) { if (cap < 8) return RXG_ERR_ARG; memcpy(out, &c->nnz, 8); }
     return RXG_OK;
   }
+  if (s == "win_meta") {   // {list carries the window stream, cells per group, stencil runs, groups, resident cells x/y/z, ghost layers}
+    const DevGrid &g = c->gnb;
+    const int G = std::max(1, c->win_g_built);
+    const int meta[8] = {c->win_built ? 1 : 0, G, c->nruns, g.nc[0] * g.nc[1] * cdiv(g.nc[2], G), g.nc[0], g.nc[1], g.nc[2], g.L};
+    if (count) *count = 8;
+    if (out) { if (cap < 32) return RXG_ERR_ARG; memcpy(out, meta, 32); }
+    return RXG_OK;
+  }
   // 3-vector planes are returned compact [3][n6]
   if (s == "pos" || s == "f" || s == "v" || (s == "spos" && c->spos)) {
     const double *p = s == "pos" ? c->pos : (s == "f" ? c->f : (s == "v" ? c->v : c->spos));
@@ -1469,6 +1477,12 @@ int rxg_debug_fetch(rxg_handle h, const char *name, void *out, long long cap, lo
   else if (s == "rowbeg") dev(c->rowbeg, nat, 8);
   else if (s == "rowend") dev(c->rowend, nat, 8);
   else if (s == "col") dev(c->col, c->nnz, 4);   // converted to atom indices below
+  else if (s == "col_slot") dev(c->col, c->nnz, 4);   // raw: slot | ghost bit
+  else if (s == "col16" && c->col16 && c->win_built) dev(c->col16, c->nnz, 2);
+  else if (s == "rowlen" && c->win_built) dev(c->rowlen, n6, 4);
+  else if (s == "win_desc" && c->win_desc && c->win_built)
+    dev(c->win_desc, 2LL * c->gnb.nc[0] * c->gnb.nc[1] * cdiv(c->gnb.nc[2], std::max(1, c->win_g_built)) * (c->nruns + 1), 4);
+  else if (s == "cellstart_nb") dev(c->gnb.start, c->gnb.ncell + 1, 4);
   else if (s == "val") dev(c->val, c->nnz, 8);
   else if (s == "ucol") dev(c->ucol, c->nunion, 4);
   else if (s == "umask") dev(c->umask, c->nunion, 1);

