@@ -70,3 +70,16 @@ def test_product_never_imports_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 txt = open(os.path.join(dp, f), errors="ignore").read()
                 assert "pyoracle" not in txt and "rxmd_oracle" not in txt and "librxmd_oracle" not in txt, f
+
+
+def test_hint_flags_agree_across_header_python_and_shim():
+    """rxg_hint's flags are promises a shim makes (include/rxmd_b200.h): the ctypes mirror and the Fortran shim must carry the
+    header's values, and every flag the header defines must be known to both."""
+    hdr = dict(re.findall(r"#define\s+(RXG_HINT_[A-Z_]+)\s+(\d+)", open(HEADER).read()))
+    assert len(hdr) >= 4 and len(set(hdr.values())) == len(hdr)
+    for name, val in hdr.items():
+        assert int(val) & (int(val) - 1) == 0, f"{name} is not a single bit"
+        assert getattr(engine, name.replace("RXG_", "")) == int(val), name
+    shim = open(os.path.join(ROOT, "rxmd_b200", "gpu_shim.F90")).read()
+    for name, val in hdr.items():
+        assert re.search(name + r"\s*=\s*" + val + r"\b", shim), f"{name} = {val} missing from gpu_shim.F90"
