@@ -180,7 +180,7 @@ int rxg_fetch_bonds(rxg_handle h, int *nbrlist, double *BO0);
  * [4] QEq inside md_run  [5] FORCE inside md_run  [6] MOVE inside md_run  [7] md steps (count)
  * [10] get_hsh SpMV kernel total (CUDA events)  [11] its launches  [12] get_gradient SpMV kernel  [13] its launches
  * [14] nnz of the last QEq matrix (entries, without row padding)  [15] residents  [16] residents+ghosts at the last QEq
- * [17] CG iterations (count)  [18] nnz including row padding  [19] entries of the SpMV's union stream (k_spmv_cells)
+ * [17] CG iterations (count)  [18] nnz including row padding  [19] entries of the SpMV's union stream (k_spmv_items)
  * [20] bytes copied host->device by the entry points so far  [21] bytes copied device->host
  * [22] rxg_force calls that reused the halo and 10 A list of the preceding rxg_qeq (RXG_FUSE_API=1)
  * [23] 10 A list builds without a count pass (rows laid out from the previous step's counts)  [24] of those, how many

@@ -216,7 +216,7 @@ struct Ctx {
   int *rowcnt = nullptr;
   int *col = nullptr;            // [nnz_cap]
   double *val = nullptr;         // [nnz_cap] hessian (QEq list only)
-  // union stream of the cell-blocked CG SpMV (k_spmv_cells): per block of <= 8 consecutive rows of a cell, the columns taken by
+  // union stream of the cell-blocked CG SpMV (k_spmv_items): per block of <= 8 consecutive rows of a cell, the columns taken by
   // at least one of the rows (ucol) with the set of rows that take each (umask); blocks start at uoff[first slot of the block]
   int *ucnt = nullptr;               // [NB+2] padded entry count of the block that starts at a slot (0 elsewhere)
   long long *uoff = nullptr;         // [NB+2] exclusive scan of ucnt

@@ -209,7 +209,7 @@ __global__ void __launch_bounds__(PL_WARPS * 32, FILL ? RXG_PL_MINB : 1) k_pairl
     const long long base0 = FILL ? __shfl_sync(0xffffffffu, mybase, 0) : 0;
     const int myrel = (int)(mybase - base0);
     int mycnt = 0;
-    // union stream of the CG SpMV (k_spmv_cells): per block of up to 8 consecutive rows of this cell, the candidates accepted
+    // union stream of the CG SpMV (k_spmv_items): per block of up to 8 consecutive rows of this cell, the candidates accepted
     // by at least one of them, in candidate order, with the 8-bit set of accepting rows.  ub* = running entry count of the
     // (up to four) blocks of this batch of 32 rows; identical on every lane.
     int ub0 = 0, ub1 = 0, ub2 = 0, ub3 = 0;
@@ -1084,7 +1084,7 @@ __global__ void __launch_bounds__(NW * 32, MINB) k_spmv_win(DevGrid g, int nruns
 }
 
 // ---------------------------------------------------------------------------------------------------
-// Cell-blocked SpMV (production).  The rows of one cell take nearly the same columns (the union of the lists of the ~3 atoms
+// Cell-blocked SpMV (k_spmv_items; experiment, RXG_SPMV=items: correct, tested, slower -- DESIGN.md 4.3).  The rows of one cell take nearly the same columns (the union of the lists of the ~3 atoms
 // of a 3 A cell is 0.44x the sum of their lengths at RDX density), and k_spmv_rows pays one 16-byte gather of x per stored
 // entry: its L1 data pipe, not HBM, is what saturates.  Here a work item (SpItem, written by k_pairlist's fill pass) is up
 // to RG consecutive rows of a block of <= 8 rows of one cell, with the block's UNION stream: per union entry a column (4 B)
