@@ -77,6 +77,37 @@ def test_tables_are_self_consistent(rdx_paths):
             assert np.allclose(num[k - 1], F[k], rtol=2e-4)
 
 
+def test_lg_tables_are_self_consistent():
+    """The tables of the HEADLINE configuration (conf/init.rdx.lg, `isLG`): the low-gradient dispersion and inner-core terms the
+    LG force field adds to TBL_Evdw (src/init.F90:496-512) have no reference numbers to be pinned against, so they are held to
+    what the reference's own formulas must satisfy: TBL(1) = (dE/dr)/r of TBL(0) -- which checks dElg and dE_core against Elg and
+    E_core -- and the LG part must vanish from the Coulomb / QEq tables and be the exact difference to the tables of the same
+    file parsed without the LG columns' effect (C_lg = ecore = 0)."""
+    import os
+    from conftest import INPUTS
+    d = os.path.join(INPUTS, "init.rdx.lg")
+    s = build_system(os.path.join(d, "input.xyz"), os.path.join(d, "ffield"), isLG=True)
+    assert s.ff.isLG
+    T_vdw, T_clmb, T_qeq, UDR, UDRi = S.potential_table(s.ff, 10.0, S.taper(10.0))
+    k = np.array([200, 1000, 3000, 4500])
+    checked = 0
+    for inxn in range(1, T_vdw.shape[2]):
+        E, F = T_vdw[0, 1:, inxn], T_vdw[1, 1:, inxn]
+        if not np.any(E):
+            continue
+        num = (E[2:] - E[:-2]) / (2 * UDR) * 2
+        assert np.allclose(num[k - 1], F[k], rtol=2e-4, atol=1e-9), inxn
+        checked += 1
+    assert checked >= 6                                   # C, H, O, N pairs of RDX
+    # switching the LG parameters off changes TBL_Evdw only, by exactly Tap*(Elg + E_core)
+    import copy
+    ff0 = copy.deepcopy(s.ff)
+    ff0.C_lg = np.zeros_like(ff0.C_lg); ff0.ecore = np.zeros_like(ff0.ecore)
+    V0, C0, Q0, _, _ = S.potential_table(ff0, 10.0, S.taper(10.0))
+    assert np.array_equal(C0, T_clmb) and np.array_equal(Q0, T_qeq)
+    assert np.abs(V0 - T_vdw).max() > 1e-3                # the LG terms are not negligible for this field
+
+
 def test_bonded_forces_match_finite_differences(built, rdx_paths):
     """Derivative chain of every bonded term (Ebond, Elnpr, Ehb, E3b, E4b) in the oracle's `corrected` mode, where no
     ccbnd contribution is discarded; the literal mode differs from it by exactly those terms."""
