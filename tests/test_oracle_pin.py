@@ -108,11 +108,19 @@ def test_lg_tables_are_self_consistent():
     assert np.abs(V0 - T_vdw).max() > 1e-3                # the LG terms are not negligible for this field
 
 
-def test_bonded_forces_match_finite_differences(built, rdx_paths):
+@pytest.mark.parametrize("field", ["nitramine", "lg"])
+def test_bonded_forces_match_finite_differences(built, rdx_paths, field):
     """Derivative chain of every bonded term (Ebond, Elnpr, Ehb, E3b, E4b) in the oracle's `corrected` mode, where no
-    ccbnd contribution is discarded; the literal mode differs from it by exactly those terms."""
+    ccbnd contribution is discarded; the literal mode differs from it by exactly those terms.  Run on the
+    README's nitramine cell and on the LG cell of the headline configuration (conf/init.rdx.lg)."""
     from oracle.pyoracle import Oracle
-    s = build_system(*rdx_paths, displace_sigma=0.03)
+    if field == "lg":
+        import os
+        from conftest import INPUTS
+        d = os.path.join(INPUTS, "init.rdx.lg")
+        s = build_system(os.path.join(d, "input.xyz"), os.path.join(d, "ffield"), isLG=True, displace_sigma=0.03)
+    else:
+        s = build_system(*rdx_paths, displace_sigma=0.03)
     o = Oracle(s, s.config(nbuffer=30000))
     o.move()
     n = o.natoms()
